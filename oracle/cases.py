@@ -1,0 +1,42 @@
+"""Seeded synthetic cases shared by ``oracle/make_golden.py`` and ``tests/``.
+TEST INFRASTRUCTURE (see titanet_oracle.py header)."""
+import torch
+
+from titanet_oracle import TitaNetSpec
+
+TINY = dict(
+    tiny_k3=TitaNetSpec(hidden=64, kernel=3, n_mega_blocks=2, enc_out=96, attn_hidden=32, emb=48),
+    tiny_k7=TitaNetSpec(hidden=32, kernel=7, n_mega_blocks=1, enc_out=64, attn_hidden=16, emb=32),
+    tiny_k11=TitaNetSpec(hidden=32, kernel=11, n_mega_blocks=1, enc_out=64, attn_hidden=16, emb=32),
+)
+
+# name -> (spec, loss, n_classes, B, T, scale, margin, full_grads)
+TRAIN_CASES = {
+    "tiny_k3_ce": (TINY["tiny_k3"], "ce", 10, 4, 50, None, 0.0, True),
+    "tiny_k3_arc": (TINY["tiny_k3"], "arc", 10, 4, 50, 30, 0.2, True),
+    "tiny_k3_cos": (TINY["tiny_k3"], "cos", 10, 4, 37, 64, 0.2, True),
+    "tiny_k3_arc_noscale": (TINY["tiny_k3"], "arc", 10, 4, 37, None, 0.2, True),
+    "tiny_k7_ce": (TINY["tiny_k7"], "ce", 7, 3, 33, None, 0.0, True),
+    "tiny_k11_arc": (TINY["tiny_k11"], "arc", 7, 3, 64, 30, 0.2, True),
+    "s17_ce_b4": (TitaNetSpec.named("s", 17), "ce", 251, 4, 101, None, 0.0, False),
+}
+
+
+def train_inputs(spec, n_classes, B, T, seed=42):
+    g = torch.Generator().manual_seed(seed + 1)
+    x = 0.3 * torch.randn(B, spec.n_mels, T, generator=g)
+    y = torch.randint(0, n_classes, (B,), generator=g)
+    return x, y
+
+
+def mel_inputs():
+    g = torch.Generator().manual_seed(7)
+    odd = 0.1 * torch.randn(12345, generator=g)
+    silence = torch.zeros(4000)
+    loud = 3.0 * torch.randn(8000, generator=g)
+    return dict(mel_odd=odd, mel_silence=silence, mel_loud=loud)
+
+
+def eval_dx_inputs():
+    g = torch.Generator().manual_seed(5)
+    return torch.randn(3, 80, 40, generator=g)

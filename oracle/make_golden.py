@@ -1,0 +1,139 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference here.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU
+box):  ``python oracle/make_golden.py``.  It imports the reference's own
+``modules / models / losses / transforms`` from ``/root/reference/src``, loads the
+deterministic synthetic weights of ``oracle.titanet_oracle.synth_state_dict`` with
+``load_state_dict(strict=True)`` (which also pins the state_dict key schema), runs
+the reference forward (+ backward) on seeded synthetic inputs and stores the
+outputs.  Inputs and weights are NOT stored: tests regenerate them from the same
+seeds.  TEST INFRASTRUCTURE.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+REF = os.environ.get("TITANET_REFERENCE", "/root/reference/src")
+sys.path.insert(0, REF)
+warnings.filterwarnings("ignore")
+
+import titanet_oracle as O  # noqa: E402
+import modules, models, losses, transforms  # noqa: E402,F401  (the reference)
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(8)
+
+
+def ref_mel(wave_1d: torch.Tensor) -> torch.Tensor:
+    """The reference front end exactly as ``train.py:25-46`` configures it
+    (get_transforms defaults: n_fft 512, win 25 ms, hop 10 ms, 80 mels; SpecAugment
+    probability 0)."""
+    t = transforms.MelSpectrogram(16000, n_fft=512, win_length=400, hop_length=160, n_mels=80,
+                                  specaugment_probability=0.0)
+    return t({"waveform": wave_1d.view(1, -1), "sample_rate": 16000})["spectrogram"]
+
+
+def build_ref(spec: O.TitaNetSpec, loss, n_classes, scale=None, margin=None, seed=42):
+    lf = None
+    if loss == "ce":
+        lf = losses.CELoss(spec.emb, n_classes)
+    elif loss == "arc":
+        lf = losses.ArcFaceLoss(spec.emb, n_classes, scale=scale, margin=margin)
+    elif loss == "cos":
+        lf = losses.CosFaceLoss(spec.emb, n_classes, scale=scale, margin=margin)
+    elif loss == "sphere":
+        lf = losses.SphereFaceLoss(spec.emb, n_classes, scale=scale, margin=margin)
+    m = models.TitaNet(spec.n_mels, spec.n_mega_blocks, spec.n_sub_blocks, spec.hidden, spec.enc_out,
+                       spec.emb, spec.kernel, prolog_kernel_size=spec.prolog_kernel,
+                       epilog_kernel_size=spec.epilog_kernel, attention_hidden_size=spec.attn_hidden,
+                       se_reduction=spec.se_reduction, simple_pool=spec.simple_pool, loss_function=lf,
+                       dropout=spec.dropout)
+    sd = O.synth_state_dict(spec, loss, n_classes, seed=seed)
+    assert list(m.state_dict().keys()) == list(sd.keys()), "state_dict key schema mismatch"
+    m.load_state_dict(sd, strict=True)
+    return m
+
+
+def save(name, **arrs):
+    np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                        **{k: (v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
+                           for k, v in arrs.items()})
+    print("wrote", name, len(arrs), "arrays")
+
+
+def case_mel():
+    wave, _ = O.synthetic_batch(2, seconds=1.0, seed=42)
+    mels = torch.cat([ref_mel(w) for w in wave], dim=0)                 # [2, 80, 101]
+    extra = {k: ref_mel(w)[0] for k, w in mel_inputs().items()}
+    save("mel_1s", mel=mels, **extra)
+
+
+def case_cfg1():
+    """BASELINE.json configs[0]: TitaNet-S eval forward, batch 2, 1 s synthetic waveform."""
+    spec = O.TitaNetSpec.named("s", 17, dropout=0.1)
+    m = build_ref(spec, None, 0).eval()
+    wave, _ = O.synthetic_batch(2, seconds=1.0, seed=42)
+    x = torch.cat([ref_mel(w) for w in wave], dim=0)
+    with torch.no_grad():
+        emb = m(x)
+    save("cfg1_s17_eval", emb=emb, n_params=np.int64(m.get_n_params()))
+
+
+from cases import TINY, TRAIN_CASES, train_inputs, mel_inputs, eval_dx_inputs  # noqa: E402
+
+
+def train_case(name, spec, loss, n_classes, B, T, scale=None, margin=None, full_grads=True, seed=42,
+               input_grad=True):
+    m = build_ref(spec, loss, n_classes, scale, margin, seed).train()
+    x, y = train_inputs(spec, n_classes, B, T, seed)
+    x.requires_grad_(input_grad)
+    emb, preds, lval = m(x, speakers=y)
+    lval.backward()
+    out = dict(emb=emb, preds=preds, loss=lval)
+    names = [k for k, _ in m.named_parameters()]
+    gn = torch.stack([p.grad.norm() if p.grad is not None else torch.zeros(()) for _, p in m.named_parameters()])
+    out["grad_norms"] = gn
+    if full_grads:
+        for k, p in m.named_parameters():
+            out["grad:" + k] = p.grad
+    else:
+        for k, p in m.named_parameters():
+            if p.numel() <= 2048:
+                out["grad:" + k] = p.grad
+    if input_grad:
+        out["dx"] = x.grad
+    sd_after = m.state_dict()
+    for k in ("encoder.prolog.conv_block.1.running_mean", "encoder.prolog.conv_block.1.running_var",
+              "decoder.linear.1.running_mean", "decoder.linear.1.running_var",
+              "decoder.linear.1.num_batches_tracked"):
+        out["buf:" + k] = sd_after[k]
+    if loss != "ce":
+        out["buf:loss_function.fc.weight"] = sd_after["loss_function.fc.weight"]
+    save(name, **out)
+    return names
+
+
+def case_eval_input_grad():
+    """``utils.chart_dependencies`` (utils.py:451-468): eval-mode forward, backprop one
+    sample's outputs, only that sample's input gradient is non-zero."""
+    spec = TINY["tiny_k3"]
+    m = build_ref(spec, None, 0).eval()
+    x = eval_dx_inputs().requires_grad_(True)
+    out = m(x)
+    out[1].sum().backward()
+    save("tiny_k3_eval_dx", emb=out, dx=x.grad)
+
+
+if __name__ == "__main__":
+    case_mel()
+    case_cfg1()
+    for name, (spec, loss, nc, B, T, scale, margin, full) in TRAIN_CASES.items():
+        train_case(name, spec, loss, nc, B, T, scale if loss != "ce" else None,
+                   margin if loss != "ce" else None, full)
+    case_eval_input_grad()
