@@ -1,0 +1,144 @@
+/* titanet_b200.h -- C ABI of libtitanet_sm100.so (NVIDIA B200, sm_100a).
+ *
+ * The drop-in boundary for the TitaNet hot path of Wadaboa/titanet: the reference is
+ * pure Python on torch, so there is no FFI in it to replace; each entry point below
+ * is what a ctypes binding inside the reference's own modules would call instead of
+ * the torch op(s) named in its comment (paths relative to the reference checkout,
+ * commit 7b77053).  INTEGRATION.md shows the reference-side stubs.
+ *
+ * Conventions
+ *  - Every function returns 0 on success, a negative TN_E* code for a rejected
+ *    argument (shape / alignment / unsupported value) or a positive cudaError_t.
+ *    tn_last_error() returns the message for the calling thread.
+ *  - All tensors are device pointers to contiguous fp32 unless stated.  Activations
+ *    use the channels-last "NWC" layout [B*T, C] (row r = b*T + t); the reference's
+ *    [B, C, T] tensors cross the boundary through tn_ncw_to_nwc / tn_nwc_to_ncw (or
+ *    the mel / prolog kernels, which read [B, C, T] directly).
+ *  - Nothing allocates, synchronises or owns memory: outputs and scratch are passed
+ *    in by the caller; `stream` is a cudaStream_t.  All launches are CUDA-graph
+ *    capturable.
+ *  - "Lazy activation": a tensor produced by a conv in front of a BatchNorm is kept as
+ *    its pre-BN values z; consumers receive (scale, shift, relu, drop_p, seed, layer)
+ *    and compute a = dropout(relu(z*scale[c] + shift[c])) on load.  scale == NULL
+ *    means the tensor is already an activation.  Dropout masks come from a
+ *    counter-based Philox4x32-10 keyed by (seed, layer, element index), so the
+ *    backward pass regenerates them.
+ *  - "ACCUMULATED" outputs are added to (atomically); the caller zeroes them.
+ */
+#ifndef TITANET_B200_H_
+#define TITANET_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TN_OK 0
+#define TN_EINVAL (-1)
+#define TN_EUNSUPPORTED (-2)
+
+/* epilogue flags of the conv-GEMM entry points */
+#define TN_EPI_TANH 1   /* z = tanh(z)                       */
+#define TN_EPI_ACCUM 2  /* z += previous contents of Z       */
+
+const char* tn_last_error(void);
+int tn_version(void);
+int tn_device_check(void);                       /* fails unless the current device is sm_100 */
+int tn_zero(void* p, size_t bytes, void* stream);
+
+/* ---- layout ------------------------------------------------------------------ */
+int tn_ncw_to_nwc(const float* x, float* y, int B, int C, int T, void* stream);
+int tn_nwc_to_ncw(const float* x, float* y, int B, int C, int T, void* stream);
+
+/* ---- mel front end: transforms.MelSpectrogram.__call__ (src/transforms.py:158-184),
+ *      batched with datasets.collate_fn zero padding (src/datasets.py:48-73) -------- */
+int tn_mel_fwd(const float* wave, const int* lengths, const float* window, const float* fb, const int* band_lo,
+               const int* band_hi, float* out, int B, int L_stride, int L_full, int T_out, int n_fft, int hop,
+               int n_mels, int nwc, void* stream);
+
+/* ---- convolutions as GEMMs ------------------------------------------------------
+ * Z[r,co] = bias[co] + sum_{k,ci} X[r+k-K/2, ci] * W[co,ci,k]  (taps stay inside an
+ * utterance).  Replaces Conv1dSamePadding.forward (src/modules.py:14-40) for dense convs,
+ * the skip nn.Conv1d (src/models.py:452-455) and nn.Linear (src/models.py:549-551,
+ * 510-513; src/losses.py:30,70).  stats (fp64 [2*Co], ACCUMULATED) receives the
+ * per-channel sum and sum of squares of Z for the following BatchNorm.
+ * transpose_w = 1 computes the data gradient (X := dZ, weight read as W[ci',co',K-1-k]). */
+int tn_conv_gemm_simt(const float* X, const float* W, const float* bias, float* Z, double* stats, int B, int T, int Ci,
+                      int Co, int K, int transpose_w, int flags, void* stream);
+/* dW[co,ci,k] += sum_r dZ[r,co] X[r+k-K/2,ci];  dbias[co] += sum_r dZ[r,co]   (ACCUMULATED) */
+int tn_conv_wgrad_simt(const float* dZ, const float* X, float* dW, float* dbias, int B, int T, int Ci, int Co, int K,
+                       void* stream);
+
+/* ---- depthwise conv with fused lazy-activation prologue:
+ *      DepthwiseConv1d's first conv (src/modules.py:64-75) after BN/ReLU/Dropout
+ *      (src/modules.py:128-133) ---------------------------------------------------- */
+int tn_dw_fwd(const float* z, float* u, const float* w, const float* bias, const float* scale, const float* shift,
+              int relu, float drop_p, const unsigned long long* seed, unsigned int layer, int B, int T, int C, int K,
+              void* stream);
+int tn_dw_bwd(const float* du, const float* z, float* dz, const float* w, float* dw, float* dbias, float* dscale,
+              float* dshift, const float* scale, const float* shift, int relu, float drop_p, const unsigned long long* seed,
+              unsigned int layer, int B, int T, int C, int K, void* stream);
+
+/* ---- BatchNorm1d folded into per-channel (scale, shift): nn.BatchNorm1d in
+ *      ConvBlock1d (src/modules.py:128), skip (src/models.py:454), decoder
+ *      (src/models.py:506,512) ------------------------------------------------------ */
+int tn_colstats(const float* x, double* stats, int R, int C, void* stream);          /* ACCUMULATED */
+int tn_bn_finalize(const double* stats, double n, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, long long* num_batches_tracked, float momentum, float eps, int training,
+                   float* scale, float* shift, float* mean, float* invstd, int C, void* stream);
+int tn_bn_bwd_coef(const float* dscale, const float* dshift, const float* mean, const float* invstd, const float* gamma,
+                   double n, int training, float* dgamma, float* dbeta, double* dstats, int C, void* stream);
+/* out = (dz_direct or 0) + dstats[c] + 2 z dstats[C+c]: gradient of the statistics w.r.t. their tensor */
+int tn_stats_bwd(const float* dz_direct, const float* z, const double* dstats, float* out, int R, int C, void* stream);
+/* dropout seed stream: state = splitmix64 step, *out = this step's seed (device scalars) */
+int tn_seed_next(unsigned long long* state, unsigned long long* out, void* stream);
+int tn_act_fwd(const float* z, float* y, const float* scale, const float* shift, int relu, float drop_p,
+               const unsigned long long* seed, unsigned int layer, int R, int C, void* stream);
+int tn_act_bwd(const float* dy, const float* z, float* dz, float* dscale, float* dshift, const float* scale,
+               const float* shift, int relu, float drop_p, const unsigned long long* seed, unsigned int layer, int R, int C,
+               void* stream);                                                        /* dscale/dshift ACCUMULATED */
+int tn_tanh_bwd(const float* dh, const float* h, float* out, long long n, void* stream);
+
+/* ---- squeeze-excitation + mega-block tail: SqueezeExcitation.forward
+ *      (src/modules.py:173-189), MegaBlock.forward (src/models.py:467-472) ----------- */
+int tn_se_mean(const float* z3, float* m, const float* scale, const float* shift, int relu, float drop_p,
+               const unsigned long long* seed, unsigned int layer, int B, int T, int C, void* stream);
+int tn_se_mlp_fwd(const float* m, const float* W1, const float* W2, float* gate, int B, int C, int Cr, void* stream);
+int tn_se_mlp_bwd(const float* dgate, const float* gate, const float* m, const float* W1, const float* W2, float* dm,
+                  float* dW1, float* dW2, int B, int C, int Cr, void* stream);       /* dW1/dW2 ACCUMULATED */
+int tn_tail_fwd(const float* z3, const float* s, const float* gate, float* out, const float* scale3, const float* shift3,
+                float drop3, unsigned int layer3, const float* scale_s, const float* shift_s, float drop_o,
+                unsigned int layer_o, const unsigned long long* seed, int B, int T, int C, void* stream);
+int tn_tail_bwd1(const float* dout, const float* out, const float* z3, float* dgate, const float* scale3,
+                 const float* shift3, float drop3, unsigned int layer3, float drop_o, const unsigned long long* seed, int B, int T,
+                 int C, void* stream);
+int tn_tail_bwd2(const float* dout, const float* out, const float* z3, const float* s, const float* gate, const float* dm,
+                 float* dz3, float* ds, float* dsc3, float* dsh3, float* dscs, float* dshs, const float* scale3,
+                 const float* shift3, float drop3, unsigned int layer3, const float* scale_s, const float* shift_s,
+                 float drop_o, const unsigned long long* seed, int B, int T, int C, void* stream);
+
+/* ---- attentive statistics pooling: AttentiveStatsPooling.forward (src/models.py:570-584) */
+int tn_asp_pool_fwd(const float* e, const float* x, float* pooled, float* aux, int B, int T, int D, float eps,
+                    void* stream);
+int tn_asp_pool_bwd(const float* dpooled, const float* pooled, const float* aux, const float* e, const float* x, float* de,
+                    float* dx, int B, int T, int D, float eps, void* stream);
+
+/* ---- embedding normalisation + loss heads: F.normalize (src/models.py:333,
+ *      src/losses.py:43), CELoss.forward (src/losses.py:32-44),
+ *      AngularMarginLoss.forward (src/losses.py:77-132) ------------------------------ */
+int tn_l2norm_fwd(const float* x, float* y, float* norms, int B, int E, float eps, void* stream);
+int tn_l2norm_bwd(const float* dy, const float* y, const float* norms, const float* dnorm, float* dx, int B, int E,
+                  float eps, void* stream);
+/* dlogits (optional) = d(mean loss)/dlogits * (*gout or 1) */
+int tn_ce_fwd_bwd(const float* logits, const long long* targets, float* loss_row, float* loss, long long* preds,
+                  float* dlogits, const float* gout, int B, int Cn, void* stream);
+int tn_margin_fwd_bwd(const float* raw_cos, const float* norms, const long long* targets, float* loss_row, float* loss,
+                      long long* preds, float* draw, float* dnorm, const float* gout, int B, int Cn, float scale,
+                      int use_norm_scale, float m1, float m2, float m3, float eps, void* stream);
+int tn_rownorm_inplace(float* W, int rows, int cols, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TITANET_B200_H_ */

@@ -1,0 +1,128 @@
+"""ctypes binding of ``libtitanet_sm100.so`` (the C ABI in ``include/titanet_b200.h``).
+
+The argument types of every entry point are read from the header itself, so the
+binding cannot drift from the declaration.  There is no fallback: if the library is
+missing the first op raises (``TitanetLibraryError``), and every op refuses CPU
+tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from typing import Dict, List, Tuple
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "libtitanet_sm100.so")
+HEADER_CANDIDATES = (os.path.join(ROOT, "include", "titanet_b200.h"), os.path.join(HERE, "titanet_b200.h"))
+
+
+class TitanetLibraryError(RuntimeError):
+    pass
+
+
+_CTYPE = {
+    "int": ctypes.c_int, "unsigned int": ctypes.c_uint, "float": ctypes.c_float, "double": ctypes.c_double,
+    "long long": ctypes.c_longlong, "unsigned long long": ctypes.c_ulonglong, "size_t": ctypes.c_size_t,
+}
+
+
+def header_path() -> str:
+    for p in HEADER_CANDIDATES:
+        if os.path.exists(p):
+            return p
+    raise TitanetLibraryError("titanet_b200.h not found next to the package")
+
+
+def parse_header(path: str | None = None) -> Dict[str, Tuple[str, List[Tuple[str, str]]]]:
+    """name -> (return type, [(ctype string, arg name), ...]) for every prototype."""
+    text = open(path or header_path()).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    protos = {}
+    for m in re.finditer(r"(const char\*|int)\s+(tn_\w+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        alist = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                mm = re.match(r"(.*?)(\w+)$", a)
+                alist.append((mm.group(1).strip(), mm.group(2)))
+        protos[name] = (ret, alist)
+    return protos
+
+
+def _to_ctype(t: str):
+    if "*" in t:
+        return ctypes.c_void_p
+    t = t.replace("const ", "").strip()
+    return _CTYPE[t]
+
+
+class _Lib:
+    def __init__(self):
+        self._dll = None
+        self._fns = {}
+
+    def load(self):
+        if self._dll is not None:
+            return self
+        if not os.path.exists(LIB_PATH):
+            raise TitanetLibraryError(
+                f"{LIB_PATH} is missing: build it with `python -m titanet_b200._build` "
+                "(needs nvcc; there is no CPU or PyTorch fallback)")
+        self._dll = ctypes.CDLL(LIB_PATH)
+        for name, (ret, args) in parse_header().items():
+            try:
+                fn = getattr(self._dll, name)
+            except AttributeError as e:  # pragma: no cover
+                raise TitanetLibraryError(f"{LIB_PATH} does not export {name}") from e
+            fn.restype = ctypes.c_char_p if ret.startswith("const char") else ctypes.c_int
+            fn.argtypes = [_to_ctype(t) for t, _ in args]
+            self._fns[name] = fn
+        return self
+
+    def last_error(self) -> str:
+        msg = self._fns["tn_last_error"]()
+        return msg.decode() if msg else ""
+
+    def call(self, name: str, *args):
+        fn = self._fns.get(name)
+        if fn is None:
+            self.load()
+            fn = self._fns[name]
+        rc = fn(*args)
+        if rc != 0:
+            raise TitanetLibraryError(f"{name} failed (code {rc}): {self.last_error()}")
+
+
+LIB = _Lib()
+_checked_device = False
+
+
+def require_cuda(*tensors: torch.Tensor):
+    """No CPU path exists: reject anything that is not a CUDA tensor."""
+    global _checked_device
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise TitanetLibraryError(
+                "titanet_b200 runs on NVIDIA B200 (sm_100a) only: got a CPU tensor and there is no CPU fallback")
+    if not _checked_device:
+        LIB.load()
+        LIB.call("tn_device_check")
+        _checked_device = True
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    LIB.call(name, *args, stream())

@@ -1,0 +1,467 @@
+"""Autograd bindings of the libtitanet_sm100 kernels.
+
+Internal tensor convention: activations are channels-last ``[B*T, C]`` fp32 ("NWC").
+A tensor in front of a BatchNorm travels as its pre-BN values ``z`` plus the folded
+per-channel ``(scale, shift)`` -- the consumer kernel applies affine + ReLU + dropout
+while loading (see include/titanet_b200.h, "lazy activation").  BatchNorm statistics
+are an ordinary differentiable fp64 tensor ``stats = [sum | sum of squares]`` produced by
+the conv-GEMM epilogue; its gradient is folded back into ``dz`` by ``tn_stats_bwd``.
+
+Every op here launches hand-written CUDA kernels through the C ABI; nothing falls back
+to torch math.  torch is used for memory (``torch.empty``), streams and autograd only.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+
+from ._lib import LIB, call, ptr, require_cuda, stream
+
+Tensor = torch.Tensor
+EPI_TANH, EPI_ACCUM = 1, 2
+
+
+# ----------------------------------------------------------------------------
+# small helpers
+# ----------------------------------------------------------------------------
+def _c(t: Optional[Tensor]) -> Optional[Tensor]:
+    """contiguous fp32 CUDA tensor (or None)."""
+    if t is None:
+        return None
+    require_cuda(t)
+    if t.dtype != torch.float32:
+        raise TypeError(f"titanet_b200 kernels are fp32; got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def empty(shape, ref: Tensor, dtype=torch.float32) -> Tensor:
+    return torch.empty(shape, device=ref.device, dtype=dtype)
+
+
+def zeros(shape, ref: Tensor, dtype=torch.float32) -> Tensor:
+    t = torch.empty(shape, device=ref.device, dtype=dtype)
+    if t.numel():
+        LIB.call("tn_zero", t.data_ptr(), t.numel() * t.element_size(), stream())
+    return t
+
+
+def seed_next(state: Tensor) -> Tensor:
+    """Advance the int64[1] device seed state and return this step's seed tensor."""
+    require_cuda(state)
+    out = torch.empty(1, device=state.device, dtype=torch.int64)
+    call("tn_seed_next", ptr(state), ptr(out))
+    return out
+
+
+# ----------------------------------------------------------------------------
+# layout
+# ----------------------------------------------------------------------------
+class Transpose(Function):
+    """[B, C, T] -> [B, T, C] (to_nwc) or back."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, to_nwc: bool):
+        x = _c(x)
+        ctx.to_nwc = to_nwc
+        if to_nwc:
+            B, C, T = x.shape
+            y = empty((B, T, C), x)
+            call("tn_ncw_to_nwc", ptr(x), ptr(y), B, C, T)
+        else:
+            B, T, C = x.shape
+            y = empty((B, C, T), x)
+            call("tn_nwc_to_ncw", ptr(x), ptr(y), B, C, T)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return Transpose.apply(dy, not ctx.to_nwc), None
+
+
+def ncw_to_nwc(x: Tensor) -> Tensor:
+    return Transpose.apply(x, True)
+
+
+def nwc_to_ncw(x: Tensor) -> Tensor:
+    return Transpose.apply(x, False)
+
+
+# ----------------------------------------------------------------------------
+# conv / linear as GEMM  (+ BatchNorm statistics in the epilogue)
+# ----------------------------------------------------------------------------
+def _gemm_fwd(x, w3, bias, z, stats, B, T, transpose_w, flags):
+    Co, Ci, K = w3.shape
+    if transpose_w:
+        call("tn_conv_gemm_simt", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), B, T, Co, Ci, K, 1, flags)
+    else:
+        call("tn_conv_gemm_simt", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), B, T, Ci, Co, K, 0, flags)
+
+
+def _gemm_wgrad(dz, x, dw3, dbias, B, T):
+    Co, Ci, K = dw3.shape
+    call("tn_conv_wgrad_simt", ptr(dz), ptr(x), ptr(dw3), ptr(dbias), B, T, Ci, Co, K)
+
+
+class ConvGemm(Function):
+    """z[B*T, Co] = conv1d_same(x[B*T, Ci], w[Co, Ci, K]) + bias, optional tanh epilogue,
+    optional BatchNorm statistics of z.  ``w`` may be 2-D (a linear layer)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, B: int, T: int, want_stats: bool, tanh: bool):
+        x, w, bias = _c(x), _c(w), _c(bias)
+        w3 = w if w.dim() == 3 else w.unsqueeze(-1)
+        Co, Ci, K = w3.shape
+        assert x.shape == (B * T, Ci), (x.shape, B, T, Ci)
+        z = empty((B * T, Co), x)
+        stats = zeros((2 * Co,), x, torch.float64) if want_stats else None
+        _gemm_fwd(x, w3, bias, z, stats, B, T, 0, EPI_TANH if tanh else 0)
+        ctx.save_for_backward(x, w, bias, z if (want_stats or tanh) else None)
+        ctx.meta = (B, T, want_stats, tanh)
+        if want_stats:
+            return z, stats
+        return z, None
+
+    @staticmethod
+    def backward(ctx, dz, dstats):
+        x, w, bias, z = ctx.saved_tensors
+        B, T, want_stats, tanh = ctx.meta
+        w3 = w if w.dim() == 3 else w.unsqueeze(-1)
+        Co, Ci, K = w3.shape
+        if dz is None:
+            dz = zeros((B * T, Co), x)
+        dz = _c(dz)
+        if tanh:
+            g = empty(dz.shape, dz)
+            call("tn_tanh_bwd", ptr(dz), ptr(z), ptr(g), dz.numel())
+            dz = g
+        if want_stats and dstats is not None:
+            g = empty(dz.shape, dz)
+            call("tn_stats_bwd", ptr(dz), ptr(z), ptr(dstats.contiguous()), ptr(g), B * T, Co)
+            dz = g
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = empty((B * T, Ci), x)
+            _gemm_fwd(dz, w3, None, dx, None, B, T, 1, 0)
+        dw = zeros(w.shape, w)
+        db = zeros(bias.shape, bias) if bias is not None else None
+        _gemm_wgrad(dz, x, dw if dw.dim() == 3 else dw.unsqueeze(-1), db, B, T)
+        return dx, dw, db, None, None, None, None
+
+
+def conv_gemm(x, w, bias, B, T, want_stats=False, tanh=False):
+    return ConvGemm.apply(x, w, bias, B, T, want_stats, tanh)
+
+
+class ColStats(Function):
+    """stats = [sum_r x | sum_r x^2] per channel (fp64)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        R, C = x.shape
+        stats = zeros((2 * C,), x, torch.float64)
+        call("tn_colstats", ptr(x), ptr(stats), R, C)
+        ctx.save_for_backward(x)
+        return stats
+
+    @staticmethod
+    def backward(ctx, dstats):
+        (x,) = ctx.saved_tensors
+        dx = empty(x.shape, x)
+        call("tn_stats_bwd", None, ptr(x), ptr(dstats.contiguous()), ptr(dx), x.shape[0], x.shape[1])
+        return dx
+
+
+class BNFold(Function):
+    """BatchNorm1d folded to per-channel (scale, shift).
+
+    training: batch statistics from ``stats`` over ``n`` samples, biased variance; running
+    statistics updated in place with ``momentum`` (unbiased variance) and
+    ``num_batches_tracked += 1``.  eval: running statistics.  nn.BatchNorm1d semantics
+    (reference: src/modules.py:128, src/models.py:454,506,512)."""
+
+    @staticmethod
+    def forward(ctx, stats, gamma, beta, running_mean, running_var, nbt, n: float, momentum: float, eps: float,
+                training: bool):
+        gamma, beta = _c(gamma), _c(beta)
+        C = gamma.numel()
+        scale, shift = empty((C,), gamma), empty((C,), gamma)
+        mean, invstd = empty((C,), gamma), empty((C,), gamma)
+        call("tn_bn_finalize", ptr(stats), float(n), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(nbt),
+             float(momentum), float(eps), 1 if training else 0, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), C)
+        ctx.save_for_backward(gamma, mean, invstd)
+        ctx.meta = (float(n), training, stats is not None)
+        return scale, shift
+
+    @staticmethod
+    def backward(ctx, dscale, dshift):
+        gamma, mean, invstd = ctx.saved_tensors
+        n, training, has_stats = ctx.meta
+        C = gamma.numel()
+        dscale = _c(dscale) if dscale is not None else zeros((C,), gamma)
+        dshift = _c(dshift) if dshift is not None else zeros((C,), gamma)
+        dgamma, dbeta = empty((C,), gamma), empty((C,), gamma)
+        dstats = empty((2 * C,), gamma, torch.float64) if (training and has_stats) else None
+        call("tn_bn_bwd_coef", ptr(dscale), ptr(dshift), ptr(mean), ptr(invstd), ptr(gamma), n, 1 if dstats is not None else 0,
+             ptr(dgamma), ptr(dbeta), ptr(dstats), C)
+        return dstats, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def bn_fold(stats, bn: torch.nn.BatchNorm1d, n: float):
+    """(scale, shift) of ``bn`` applied to a tensor whose statistics are ``stats``."""
+    training = bn.training or (bn.running_mean is None)
+    if bn.momentum is None:
+        raise NotImplementedError("BatchNorm1d(momentum=None) (cumulative average) is not supported")
+    return BNFold.apply(stats if training else None, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                        bn.num_batches_tracked if training else None, n, bn.momentum, bn.eps, training)
+
+
+# ----------------------------------------------------------------------------
+# lazy activation: materialise / depthwise conv
+# ----------------------------------------------------------------------------
+class Act(Function):
+    """y = dropout(relu(z * scale + shift))."""
+
+    @staticmethod
+    def forward(ctx, z, scale, shift, seed, relu: bool, p: float, layer: int):
+        z, scale, shift = _c(z), _c(scale), _c(shift)
+        R, C = z.shape
+        y = empty(z.shape, z)
+        if p > 0 and seed is None:
+            raise ValueError("dropout needs a seed tensor")
+        call("tn_act_fwd", ptr(z), ptr(y), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer), R, C)
+        ctx.save_for_backward(z, scale, shift, seed)
+        ctx.meta = (relu, p, layer)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, scale, shift, seed = ctx.saved_tensors
+        relu, p, layer = ctx.meta
+        R, C = z.shape
+        dy = _c(dy)
+        dz = empty(z.shape, z)
+        dscale, dshift = zeros((C,), z), zeros((C,), z)
+        call("tn_act_bwd", ptr(dy), ptr(z), ptr(dz), ptr(dscale), ptr(dshift), ptr(scale), ptr(shift), int(relu), float(p),
+             ptr(seed), int(layer), R, C)
+        return dz, dscale, dshift, None, None, None, None
+
+
+class Depthwise(Function):
+    """u = depthwise_K(act(z)) + bias; act = identity when scale is None."""
+
+    @staticmethod
+    def forward(ctx, z, scale, shift, w, bias, seed, relu: bool, p: float, layer: int, B: int, T: int):
+        z, scale, shift, w, bias = _c(z), _c(scale), _c(shift), _c(w), _c(bias)
+        C, K = w.shape[0], w.shape[-1]
+        assert z.shape == (B * T, C)
+        u = empty(z.shape, z)
+        call("tn_dw_fwd", ptr(z), ptr(u), ptr(w), ptr(bias), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer),
+             B, T, C, K)
+        ctx.save_for_backward(z, scale, shift, w, bias, seed)
+        ctx.meta = (relu, p, layer, B, T)
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        z, scale, shift, w, bias, seed = ctx.saved_tensors
+        relu, p, layer, B, T = ctx.meta
+        C, K = w.shape[0], w.shape[-1]
+        du = _c(du)
+        dz = empty(z.shape, z)
+        dw = zeros(w.shape, w)
+        db = zeros((C,), z) if bias is not None else None
+        dscale = zeros((C,), z) if scale is not None else None
+        dshift = zeros((C,), z) if scale is not None else None
+        call("tn_dw_bwd", ptr(du), ptr(z), ptr(dz), ptr(w), ptr(dw), ptr(db), ptr(dscale), ptr(dshift), ptr(scale), ptr(shift),
+             int(relu), float(p), ptr(seed), int(layer), B, T, C, K)
+        return dz, dscale, dshift, dw, db, None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------
+# squeeze-excitation + mega-block tail
+# ----------------------------------------------------------------------------
+class SETail(Function):
+    """out = dropout(relu( (s*scale_s+shift_s) + gate * a3 )),  gate = SE(mean_t a3),
+    a3 = dropout(relu(z3*scale3+shift3)).  (src/modules.py:173-189, src/models.py:467-472)"""
+
+    @staticmethod
+    def forward(ctx, z3, sc3, sh3, s, scs, shs, W1, W2, seed, p3: float, layer3: int, p_o: float, layer_o: int, B: int,
+                T: int):
+        z3, sc3, sh3, s, scs, shs, W1, W2 = map(_c, (z3, sc3, sh3, s, scs, shs, W1, W2))
+        C = z3.shape[1]
+        Cr = W1.shape[0]
+        m, gate = empty((B, C), z3), empty((B, C), z3)
+        out = empty(z3.shape, z3)
+        call("tn_se_mean", ptr(z3), ptr(m), ptr(sc3), ptr(sh3), 1, float(p3), ptr(seed), int(layer3), B, T, C)
+        call("tn_se_mlp_fwd", ptr(m), ptr(W1), ptr(W2), ptr(gate), B, C, Cr)
+        call("tn_tail_fwd", ptr(z3), ptr(s), ptr(gate), ptr(out), ptr(sc3), ptr(sh3), float(p3), int(layer3), ptr(scs), ptr(shs),
+             float(p_o), int(layer_o), ptr(seed), B, T, C)
+        ctx.save_for_backward(z3, sc3, sh3, s, scs, shs, W1, W2, seed, m, gate, out)
+        ctx.meta = (p3, layer3, p_o, layer_o, B, T)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z3, sc3, sh3, s, scs, shs, W1, W2, seed, m, gate, out = ctx.saved_tensors
+        p3, layer3, p_o, layer_o, B, T = ctx.meta
+        C, Cr = z3.shape[1], W1.shape[0]
+        dout = _c(dout)
+        dgate = empty((B, C), z3)
+        call("tn_tail_bwd1", ptr(dout), ptr(out), ptr(z3), ptr(dgate), ptr(sc3), ptr(sh3), float(p3), int(layer3), float(p_o),
+             ptr(seed), B, T, C)
+        dm = empty((B, C), z3)
+        dW1, dW2 = zeros(W1.shape, W1), zeros(W2.shape, W2)
+        call("tn_se_mlp_bwd", ptr(dgate), ptr(gate), ptr(m), ptr(W1), ptr(W2), ptr(dm), ptr(dW1), ptr(dW2), B, C, Cr)
+        dz3, ds = empty(z3.shape, z3), empty(z3.shape, z3)
+        red = zeros((4, C), z3)
+        call("tn_tail_bwd2", ptr(dout), ptr(out), ptr(z3), ptr(s), ptr(gate), ptr(dm), ptr(dz3), ptr(ds), red[0].data_ptr(),
+             red[1].data_ptr(), red[2].data_ptr(), red[3].data_ptr(), ptr(sc3), ptr(sh3), float(p3), int(layer3), ptr(scs),
+             ptr(shs), float(p_o), ptr(seed), B, T, C)
+        return dz3, red[0], red[1], ds, red[2], red[3], dW1, dW2, None, None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------
+# attentive statistics pooling
+# ----------------------------------------------------------------------------
+class ASPPool(Function):
+    """pooled[B, 2D] = [sum_t alpha x | sqrt(clamp(sum_t alpha x^2 - mu^2, eps))],
+    alpha = softmax_t(e).  (src/models.py:570-584)"""
+
+    @staticmethod
+    def forward(ctx, e, x, B: int, T: int, eps: float):
+        e, x = _c(e), _c(x)
+        D = e.shape[1]
+        pooled, aux = empty((B, 2 * D), e), empty((B, 2, D), e)
+        call("tn_asp_pool_fwd", ptr(e), ptr(x), ptr(pooled), ptr(aux), B, T, D, float(eps))
+        ctx.save_for_backward(e, x, pooled, aux)
+        ctx.meta = (B, T, eps)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        e, x, pooled, aux = ctx.saved_tensors
+        B, T, eps = ctx.meta
+        D = e.shape[1]
+        de, dx = empty(e.shape, e), empty(x.shape, x)
+        call("tn_asp_pool_bwd", ptr(_c(dpooled)), ptr(pooled), ptr(aux), ptr(e), ptr(x), ptr(de), ptr(dx), B, T, D, float(eps))
+        return de, dx, None, None, None
+
+
+# ----------------------------------------------------------------------------
+# embedding normalisation and loss heads
+# ----------------------------------------------------------------------------
+class L2Norm(Function):
+    """y = x / max(||x||, eps) row-wise (eps = 0: plain division); also returns the norms."""
+
+    @staticmethod
+    def forward(ctx, x, eps: float):
+        x = _c(x)
+        B, E = x.shape
+        y, norms = empty(x.shape, x), empty((B,), x)
+        call("tn_l2norm_fwd", ptr(x), ptr(y), ptr(norms), B, E, float(eps))
+        ctx.save_for_backward(y, norms)
+        ctx.eps = eps
+        return y, norms
+
+    @staticmethod
+    def backward(ctx, dy, dnorms):
+        y, norms = ctx.saved_tensors
+        B, E = y.shape
+        dy = _c(dy) if dy is not None else zeros(y.shape, y)
+        dx = empty(y.shape, y)
+        call("tn_l2norm_bwd", ptr(dy), ptr(y), ptr(norms), ptr(_c(dnorms)) if dnorms is not None else None, ptr(dx), B, E,
+             float(ctx.eps))
+        return dx, None
+
+
+class CrossEntropy(Function):
+    """mean softmax cross-entropy + argmax (F.cross_entropy / torch.argmax; src/losses.py:40-42)."""
+
+    @staticmethod
+    def forward(ctx, logits, targets):
+        logits = _c(logits)
+        require_cuda(targets)
+        targets = targets.to(torch.int64).contiguous()
+        B, Cn = logits.shape
+        loss_row, loss = empty((B,), logits), empty((), logits)
+        preds = empty((B,), logits, torch.int64)
+        call("tn_ce_fwd_bwd", ptr(logits), ptr(targets), ptr(loss_row), ptr(loss), ptr(preds), None, None, B, Cn)
+        ctx.save_for_backward(logits, targets)
+        ctx.mark_non_differentiable(preds)
+        return loss, preds
+
+    @staticmethod
+    def backward(ctx, dloss, _dpreds):
+        logits, targets = ctx.saved_tensors
+        B, Cn = logits.shape
+        loss_row, loss = empty((B,), logits), empty((), logits)
+        preds = empty((B,), logits, torch.int64)
+        dlogits = empty(logits.shape, logits)
+        call("tn_ce_fwd_bwd", ptr(logits), ptr(targets), ptr(loss_row), ptr(loss), ptr(preds), ptr(dlogits), ptr(_c(dloss)), B, Cn)
+        return dlogits, None
+
+
+class AngularMargin(Function):
+    """loss = -mean(num - log(exp(num) + sum_{j != y} exp(s c_j) + eps)),
+    num = s (cos(m1 acos(c_y) + m2) - m3), c = clamp(raw, -1, 1)  (src/losses.py:101-130)."""
+
+    @staticmethod
+    def forward(ctx, raw, norms, targets, scale, m1: float, m2: float, m3: float, eps: float):
+        raw = _c(raw)
+        norms = _c(norms)
+        require_cuda(targets)
+        targets = targets.to(torch.int64).contiguous()
+        B, Cn = raw.shape
+        loss_row, loss = empty((B,), raw), empty((), raw)
+        preds = empty((B,), raw, torch.int64)
+        use_norm = scale is None
+        call("tn_margin_fwd_bwd", ptr(raw), ptr(norms), ptr(targets), ptr(loss_row), ptr(loss), ptr(preds), None, None, None, B, Cn,
+             0.0 if use_norm else float(scale), int(use_norm), float(m1), float(m2), float(m3), float(eps))
+        ctx.save_for_backward(raw, norms, targets)
+        ctx.meta = (scale, m1, m2, m3, eps)
+        ctx.mark_non_differentiable(preds)
+        return loss, preds
+
+    @staticmethod
+    def backward(ctx, dloss, _dpreds):
+        raw, norms, targets = ctx.saved_tensors
+        scale, m1, m2, m3, eps = ctx.meta
+        B, Cn = raw.shape
+        use_norm = scale is None
+        loss_row, loss = empty((B,), raw), empty((), raw)
+        preds = empty((B,), raw, torch.int64)
+        draw = empty(raw.shape, raw)
+        dnorm = empty((B,), raw) if use_norm else None
+        call("tn_margin_fwd_bwd", ptr(raw), ptr(norms), ptr(targets), ptr(loss_row), ptr(loss), ptr(preds), ptr(draw), ptr(dnorm),
+             ptr(_c(dloss)), B, Cn, 0.0 if use_norm else float(scale), int(use_norm), float(m1), float(m2), float(m3), float(eps))
+        return draw, dnorm, None, None, None, None, None, None
+
+
+def rownorm_(w: Tensor, eps: float = 1e-12) -> Tensor:
+    """In-place F.normalize(w, dim=1) outside autograd (src/losses.py:86)."""
+    require_cuda(w)
+    assert w.is_contiguous() and w.dtype == torch.float32
+    call("tn_rownorm_inplace", ptr(w), w.shape[0], w.shape[1], float(eps))
+    return w
+
+
+# ----------------------------------------------------------------------------
+# mel front end (no gradient)
+# ----------------------------------------------------------------------------
+def mel_forward(wave: Tensor, lengths: Optional[Tensor], window: Tensor, fb: Tensor, band_lo: Tensor, band_hi: Tensor,
+                n_fft: int, hop: int, n_mels: int, T_out: Optional[int] = None, nwc: bool = False) -> Tensor:
+    """wave [B, L] -> [B, n_mels, T] (or [B, T, n_mels] when nwc)."""
+    wave = _c(wave)
+    B, L = wave.shape
+    if T_out is None:
+        T_out = 1 + L // hop
+    if lengths is not None:
+        require_cuda(lengths)
+        lengths = lengths.to(torch.int32).contiguous()
+    out = empty((B, T_out, n_mels) if nwc else (B, n_mels, T_out), wave)
+    call("tn_mel_fwd", ptr(wave), ptr(lengths), ptr(window), ptr(fb), ptr(band_lo), ptr(band_hi), ptr(out), B, L, L, T_out, n_fft,
+         hop, n_mels, int(nwc))
+    return out

@@ -1,0 +1,200 @@
+// Shared device/host helpers for libtitanet_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "titanet_b200.h"
+
+void tn_set_error(const char* fmt, ...);
+
+#define TN_REQUIRE(cond, ...)                      \
+  do {                                             \
+    if (!(cond)) {                                 \
+      tn_set_error(__VA_ARGS__);                   \
+      return TN_EINVAL;                            \
+    }                                              \
+  } while (0)
+
+#define TN_UNSUPPORTED(cond, ...)                  \
+  do {                                             \
+    if (cond) {                                    \
+      tn_set_error(__VA_ARGS__);                   \
+      return TN_EUNSUPPORTED;                      \
+    }                                              \
+  } while (0)
+
+#define TN_CUDA(expr)                                                          \
+  do {                                                                         \
+    cudaError_t e__ = (expr);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      tn_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),    \
+                   __FILE__, __LINE__);                                        \
+      return (int)e__;                                                         \
+    }                                                                          \
+  } while (0)
+
+#define TN_LAUNCH_CHECK(name)                                                  \
+  do {                                                                         \
+    cudaError_t e__ = cudaGetLastError();                                      \
+    if (e__ != cudaSuccess) {                                                  \
+      tn_set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));  \
+      return (int)e__;                                                         \
+    }                                                                          \
+  } while (0)
+
+static inline bool tn_aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+static inline int tn_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+int tn_num_sms();
+
+// ---------------------------------------------------------------------------
+// "lazy activation": a = dropout(relu(z * scale[c] + shift[c]))
+// A tensor travels through the encoder as its pre-BatchNorm values z plus the
+// per-channel affine (scale, shift) folded from the BatchNorm statistics; the
+// consumer kernel applies affine + ReLU + dropout while loading.  scale==nullptr
+// means "plain tensor" (identity).
+// ---------------------------------------------------------------------------
+struct TnAct {
+  const float* scale;   // [C] or nullptr
+  const float* shift;   // [C]
+  int relu;
+  float inv_keep;       // 1/(1-p), 1 when no dropout
+  uint32_t thresh;      // drop when rand < thresh ; 0 => no dropout
+  const unsigned long long* seed_ptr;   // device scalar: the step's dropout seed (CUDA-graph safe)
+  uint32_t seed_lo, seed_hi, layer;     // seed_lo/hi are filled on the device by tn_act_init
+};
+
+static inline TnAct tn_make_act(const float* scale, const float* shift, int relu, float p,
+                                const unsigned long long* seed, unsigned int layer) {
+  TnAct a;
+  a.scale = scale; a.shift = shift; a.relu = relu;
+  if (p > 0.f) {
+    double t = (double)p * 4294967296.0;
+    a.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    a.inv_keep = 1.0f / (1.0f - p);
+  } else {
+    a.thresh = 0; a.inv_keep = 1.0f;
+  }
+  if (seed == nullptr) { a.thresh = 0; a.inv_keep = 1.0f; }   // no seed => no dropout (callers validate)
+  a.seed_ptr = seed; a.seed_lo = 0; a.seed_hi = 0; a.layer = layer;
+  return a;
+}
+
+#ifdef __CUDACC__
+// Philox4x32-10 counter RNG (Salmon et al. 2011): stateless, so forward and
+// backward regenerate the same dropout mask from (seed, layer, element index).
+__device__ __forceinline__ uint4 tn_philox(uint32_t k0, uint32_t k1, uint4 c) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// load the step seed once per thread (kernel parameters are read-only: work on a copy)
+__device__ __forceinline__ TnAct tn_act_init(TnAct a) {
+  if (a.thresh != 0) {
+    const unsigned long long s = __ldg(a.seed_ptr);
+    a.seed_lo = (uint32_t)s; a.seed_hi = (uint32_t)(s >> 32);
+  }
+  return a;
+}
+
+// keep-multipliers (0 or inv_keep) for the 4 consecutive elements of quad `qidx`
+__device__ __forceinline__ float4 tn_drop4(const TnAct& a, unsigned long long qidx) {
+  if (a.thresh == 0) return make_float4(1.f, 1.f, 1.f, 1.f);
+  uint4 r = tn_philox(a.seed_lo, a.seed_hi, make_uint4((uint32_t)qidx, (uint32_t)(qidx >> 32), a.layer, 0x7174u));
+  return make_float4(r.x >= a.thresh ? a.inv_keep : 0.f, r.y >= a.thresh ? a.inv_keep : 0.f,
+                     r.z >= a.thresh ? a.inv_keep : 0.f, r.w >= a.thresh ? a.inv_keep : 0.f);
+}
+
+// a = act(z) for one channel quad; `mult` (optional) receives d a / d pre, i.e. the
+// factor the backward pass multiplies by (before the extra *scale[c]).
+__device__ __forceinline__ float4 tn_act4(const TnAct& a, float4 z, int c, unsigned long long qidx, float4* mult) {
+  if (a.scale == nullptr) {
+    if (mult) *mult = make_float4(1.f, 1.f, 1.f, 1.f);
+    return z;
+  }
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + c));
+  const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + c));
+  float4 v = make_float4(fmaf(z.x, sc.x, sh.x), fmaf(z.y, sc.y, sh.y), fmaf(z.z, sc.z, sh.z), fmaf(z.w, sc.w, sh.w));
+  float4 m = tn_drop4(a, qidx);
+  if (a.relu) {
+    m.x = v.x > 0.f ? m.x : 0.f; m.y = v.y > 0.f ? m.y : 0.f;
+    m.z = v.z > 0.f ? m.z : 0.f; m.w = v.w > 0.f ? m.w : 0.f;
+  }
+  if (mult) *mult = m;
+  return make_float4(v.x * m.x, v.y * m.y, v.z * m.z, v.w * m.w);
+}
+
+__device__ __forceinline__ float tn_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float tn_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float4 tn_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void tn_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float b) { return make_float4(a.x * b, a.y * b, a.z * b, a.w * b); }
+__device__ __forceinline__ float4 tn_fma4(float4 a, float4 b, float4 c) {
+  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+__device__ __forceinline__ float4 tn_zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// ---------------------------------------------------------------------------
+// Row-tiled channel-quad work distribution shared by the HBM-bound NWC kernels.
+// A block of TN_EW_THREADS threads owns `rows_per_block` consecutive rows of an
+// [R, C] tensor.  Thread -> (quad q, lane l): quads are consecutive across
+// threads (coalesced float4), lanes stride over rows.  Per-channel partial sums
+// are combined across lanes in shared memory and leave the block as one atomic
+// per channel.
+// ---------------------------------------------------------------------------
+#define TN_EW_THREADS 256
+
+struct TnTile {
+  int Q;        // quads per row (C/4)
+  int qpb;      // quads handled per pass by the block = min(Q, TN_EW_THREADS)
+  int lanes;    // row lanes = TN_EW_THREADS / qpb
+  int q0;       // this thread's first quad
+  int lane;     // this thread's lane
+  bool active;
+};
+
+__device__ __forceinline__ TnTile tn_tile(int C) {
+  TnTile t;
+  t.Q = C >> 2;
+  t.qpb = t.Q < TN_EW_THREADS ? t.Q : TN_EW_THREADS;
+  t.lanes = TN_EW_THREADS / t.qpb;
+  t.q0 = threadIdx.x % t.qpb;
+  t.lane = threadIdx.x / t.qpb;
+  t.active = t.lane < t.lanes;
+  return t;
+}
+
+// Sum `v` (a per-thread partial for channel quad q) over the lanes of the block and
+// atomically add the result to dst[4q..4q+3].  `red` is TN_EW_THREADS float4s of
+// shared memory.  Must be called by all threads of the block the same number of times.
+template <typename DstT>
+__device__ __forceinline__ void tn_lane_reduce_atomic(const TnTile& t, float4 v, int q, DstT* dst, float4* red, float mul = 1.f) {
+  __syncthreads();
+  red[threadIdx.x] = t.active ? v : tn_zero4();
+  __syncthreads();
+  if (t.lane == 0 && q < t.Q) {
+    float4 s = red[threadIdx.x];
+    for (int l = 1; l < t.lanes; ++l) s = s + red[threadIdx.x + l * t.qpb];
+    atomicAdd(dst + 4 * q + 0, (DstT)(s.x * mul));
+    atomicAdd(dst + 4 * q + 1, (DstT)(s.y * mul));
+    atomicAdd(dst + 4 * q + 2, (DstT)(s.z * mul));
+    atomicAdd(dst + 4 * q + 3, (DstT)(s.w * mul));
+  }
+}
+#endif  // __CUDACC__

@@ -1,0 +1,373 @@
+// HBM-bound NWC kernels: layout transposes, lazy-activation materialise / backward,
+// BatchNorm statistics -> (scale, shift) folding and its backward, small row ops.
+// Reference semantics: nn.BatchNorm1d / nn.ReLU / nn.Dropout inside ConvBlock1d
+// (src/modules.py:119-134), skip-connection BN (src/models.py:452-455), decoder BNs
+// (src/models.py:504-513), F.normalize (src/models.py:333, src/losses.py:43).
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void tn_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* tn_last_error(void) { return g_err; }
+extern "C" int tn_version(void) { return 100; }
+
+static int g_num_sms = 0;
+int tn_num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+extern "C" int tn_device_check(void) {
+  int dev = 0, major = 0, minor = 0;
+  TN_CUDA(cudaGetDevice(&dev));
+  TN_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  TN_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  TN_UNSUPPORTED(major != 10, "libtitanet_sm100 needs an sm_100a device, found sm_%d%d", major, minor);
+  return TN_OK;
+}
+
+extern "C" int tn_zero(void* p, size_t bytes, void* stream) {
+  TN_CUDA(cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream));
+  return TN_OK;
+}
+
+// rows per block for the row-tiled kernels: aim at >= 4 waves of 8 blocks/SM
+static int rows_per_block(long long R) {
+  long long target = (long long)tn_num_sms() * 16;
+  long long rpb = (R + target - 1) / target;
+  if (rpb < 16) rpb = 16;
+  if (rpb > 128) rpb = 128;
+  return (int)rpb;
+}
+
+// ---------------------------------------------------------------------------
+// [B, C, T] <-> [B, T, C]
+// ---------------------------------------------------------------------------
+__global__ void transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int rows, int cols) {
+  // per batch item: x is [rows, cols] -> y is [cols, rows]
+  __shared__ float tile[32][33];
+  const float* xb = x + (size_t)blockIdx.z * rows * cols;
+  float* yb = y + (size_t)blockIdx.z * rows * cols;
+  int c = blockIdx.x * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int r = blockIdx.y * 32 + j;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? xb[(size_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  int r2 = blockIdx.y * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int c2 = blockIdx.x * 32 + j;
+    if (r2 < rows && c2 < cols) yb[(size_t)c2 * rows + r2] = tile[threadIdx.x][j];
+  }
+}
+
+static int launch_transpose(const float* x, float* y, int B, int rows, int cols, void* stream) {
+  TN_REQUIRE(B > 0 && rows > 0 && cols > 0 && B <= 65535, "transpose: bad shape B=%d rows=%d cols=%d", B, rows, cols);
+  dim3 grid(tn_cdiv(cols, 32), tn_cdiv(rows, 32), B), block(32, 8);
+  transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, rows, cols);
+  TN_LAUNCH_CHECK("transpose_kernel");
+  return TN_OK;
+}
+extern "C" int tn_ncw_to_nwc(const float* x, float* y, int B, int C, int T, void* stream) {
+  return launch_transpose(x, y, B, C, T, stream);
+}
+extern "C" int tn_nwc_to_ncw(const float* x, float* y, int B, int C, int T, void* stream) {
+  return launch_transpose(x, y, B, T, C, stream);
+}
+
+// ---------------------------------------------------------------------------
+// materialise a lazy activation / its backward
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TN_EW_THREADS) act_fwd_kernel(const float* __restrict__ z, float* __restrict__ y,
+                                                                TnAct act, int R, int C, int rpb) {
+  act = tn_act_init(act);
+  TnTile tl = tn_tile(C);
+  int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    int q = qb + tl.q0;
+    if (!tl.active || q >= tl.Q) continue;
+    for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
+      size_t off = (size_t)r * C + 4 * q;
+      tn_st4(y + off, tn_act4(act, tn_ld4(z + off), 4 * q, off >> 2, nullptr));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TN_EW_THREADS) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                                float* __restrict__ dz, float* __restrict__ dscale,
+                                                                float* __restrict__ dshift, TnAct act, int R, int C, int rpb) {
+  act = tn_act_init(act);
+  __shared__ float4 red[TN_EW_THREADS];
+  TnTile tl = tn_tile(C);
+  int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    int q = qb + tl.q0;
+    float4 a_sc = tn_zero4(), a_sh = tn_zero4();
+    if (tl.active && q < tl.Q) {
+      const float4 sc = tn_ld4(act.scale + 4 * q);
+      for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
+        size_t off = (size_t)r * C + 4 * q;
+        float4 zz = tn_ld4(z + off), m;
+        tn_act4(act, zz, 4 * q, off >> 2, &m);
+        float4 g = tn_ld4(dy + off) * m;
+        a_sc = tn_fma4(g, zz, a_sc);
+        a_sh = a_sh + g;
+        tn_st4(dz + off, g * sc);
+      }
+    }
+    tn_lane_reduce_atomic(tl, a_sc, q, dscale, red);
+    tn_lane_reduce_atomic(tl, a_sh, q, dshift, red);
+  }
+}
+
+extern "C" int tn_act_fwd(const float* z, float* y, const float* scale, const float* shift, int relu, float drop_p,
+                          const unsigned long long* seed, unsigned int layer, int R, int C, void* stream) {
+  TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0, "act_fwd: need C %% 4 == 0 (R=%d C=%d)", R, C);
+  TN_REQUIRE(scale && shift, "act_fwd: scale/shift are required");
+  TN_REQUIRE(tn_aligned16(z) && tn_aligned16(y) && tn_aligned16(scale) && tn_aligned16(shift), "act_fwd: pointers must be 16B aligned");
+  int rpb = rows_per_block(R);
+  act_fwd_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(z, y, tn_make_act(scale, shift, relu, drop_p, seed, layer), R, C, rpb);
+  TN_LAUNCH_CHECK("act_fwd_kernel");
+  return TN_OK;
+}
+
+// dz = dy * act'(z) * scale ; dscale += sum dy*act'*z ; dshift += sum dy*act'   (accumulating)
+extern "C" int tn_act_bwd(const float* dy, const float* z, float* dz, float* dscale, float* dshift, const float* scale,
+                          const float* shift, int relu, float drop_p, const unsigned long long* seed, unsigned int layer, int R,
+                          int C, void* stream) {
+  TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0, "act_bwd: need C %% 4 == 0 (R=%d C=%d)", R, C);
+  TN_REQUIRE(scale && shift && dscale && dshift, "act_bwd: scale/shift/dscale/dshift are required");
+  TN_REQUIRE(tn_aligned16(z) && tn_aligned16(dy) && tn_aligned16(dz) && tn_aligned16(scale) && tn_aligned16(shift), "act_bwd: pointers must be 16B aligned");
+  int rpb = rows_per_block(R);
+  act_bwd_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(dy, z, dz, dscale, dshift, tn_make_act(scale, shift, relu, drop_p, seed, layer), R, C, rpb);
+  TN_LAUNCH_CHECK("act_bwd_kernel");
+  return TN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// per-channel sum / sum of squares of an [R, C] tensor (fp64 accumulators)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TN_EW_THREADS) colstats_kernel(const float* __restrict__ x, double* __restrict__ stats, int R, int C, int rpb) {
+  __shared__ float4 red[TN_EW_THREADS];
+  TnTile tl = tn_tile(C);
+  int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    int q = qb + tl.q0;
+    float4 s1 = tn_zero4(), s2 = tn_zero4();
+    if (tl.active && q < tl.Q)
+      for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
+        float4 v = tn_ld4(x + (size_t)r * C + 4 * q);
+        s1 = s1 + v;
+        s2 = tn_fma4(v, v, s2);
+      }
+    tn_lane_reduce_atomic(tl, s1, q, stats, red);
+    tn_lane_reduce_atomic(tl, s2, q, stats + C, red);
+  }
+}
+extern "C" int tn_colstats(const float* x, double* stats, int R, int C, void* stream) {
+  TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0 && tn_aligned16(x), "colstats: need C %% 4 == 0 and aligned x (R=%d C=%d)", R, C);
+  int rpb = rows_per_block(R);
+  colstats_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(x, stats, R, C, rpb);
+  TN_LAUNCH_CHECK("colstats_kernel");
+  return TN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// BatchNorm folding: statistics -> (scale, shift) [+ running-stat update]
+// ---------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double n, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
+                                   long long* __restrict__ nbt, float momentum, float eps, int training,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && nbt) *nbt += 1;
+  if (c >= C) return;
+  float mean, invstd;
+  if (training) {
+    double m = stats[c] / n;
+    double var = stats[C + c] / n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (rmean) {
+      double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+      rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+    }
+  } else {
+    mean = rmean[c];
+    invstd = 1.0f / sqrtf(rvar[c] + eps);
+  }
+  float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  mean_out[c] = mean;
+  invstd_out[c] = invstd;
+}
+
+extern "C" int tn_bn_finalize(const double* stats, double n, const float* gamma, const float* beta, float* running_mean,
+                              float* running_var, long long* num_batches_tracked, float momentum, float eps, int training,
+                              float* scale, float* shift, float* mean, float* invstd, int C, void* stream) {
+  TN_REQUIRE(C > 0 && gamma && beta && scale && shift && mean && invstd, "bn_finalize: null argument");
+  TN_REQUIRE(training ? (stats != nullptr && n >= 1.0) : (running_mean && running_var), "bn_finalize: missing statistics");
+  bn_finalize_kernel<<<tn_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(stats, n, gamma, beta, running_mean, running_var,
+                                                                         num_batches_tracked, momentum, eps, training, scale,
+                                                                         shift, mean, invstd, C);
+  TN_LAUNCH_CHECK("bn_finalize_kernel");
+  return TN_OK;
+}
+
+// Backward of the folding.  Given dL/dscale, dL/dshift it returns dgamma, dbeta and the
+// gradient w.r.t. the statistics, dstats = [dL/dS1 | dL/dS2] (fp64, like stats), so that
+// the producer of z adds dL/dz_i += dS1[c] + 2 z_i dS2[c]  (tn_stats_bwd).
+__global__ void bn_bwd_coef_kernel(const float* __restrict__ dscale, const float* __restrict__ dshift,
+                                   const float* __restrict__ mean, const float* __restrict__ invstd,
+                                   const float* __restrict__ gamma, double n, int training, float* __restrict__ dgamma,
+                                   float* __restrict__ dbeta, double* __restrict__ dstats, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double dsc = dscale[c], dsh = dshift[c], mu = mean[c], r = invstd[c], g = gamma[c];
+  double t = dsc - mu * dsh;               // dL/d(invstd) / gamma
+  dgamma[c] = (float)(r * t);
+  dbeta[c] = (float)dsh;
+  if (training && dstats) {
+    double dvar = -0.5 * g * t * r * r * r;
+    double dmu = -dsh * g * r - 2.0 * mu * dvar;
+    dstats[c] = dmu / n;
+    dstats[C + c] = dvar / n;
+  }
+}
+extern "C" int tn_bn_bwd_coef(const float* dscale, const float* dshift, const float* mean, const float* invstd,
+                              const float* gamma, double n, int training, float* dgamma, float* dbeta, double* dstats,
+                              int C, void* stream) {
+  TN_REQUIRE(C > 0 && dscale && dshift && mean && invstd && gamma && dgamma && dbeta, "bn_bwd_coef: null argument");
+  TN_REQUIRE(!training || dstats, "bn_bwd_coef: training mode needs dstats");
+  bn_bwd_coef_kernel<<<tn_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(dscale, dshift, mean, invstd, gamma, n, training, dgamma, dbeta, dstats, C);
+  TN_LAUNCH_CHECK("bn_bwd_coef_kernel");
+  return TN_OK;
+}
+
+// out = (dz_direct or 0) + dS1[c] + 2 * z * dS2[c]   -- the statistics path of the BatchNorm
+// backward (and the whole backward of tn_colstats when dz_direct == NULL).  out may alias dz_direct.
+__global__ void __launch_bounds__(TN_EW_THREADS) stats_bwd_kernel(const float* __restrict__ dzd, const float* __restrict__ z,
+                                                                  const double* __restrict__ dstats, float* __restrict__ out,
+                                                                  size_t n4, int Q) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  const int C = 4 * Q;
+  for (; i < n4; i += stride) {
+    int c = 4 * (int)(i % Q);
+    float4 a = make_float4((float)dstats[c], (float)dstats[c + 1], (float)dstats[c + 2], (float)dstats[c + 3]);
+    float4 b = make_float4((float)(2.0 * dstats[C + c]), (float)(2.0 * dstats[C + c + 1]), (float)(2.0 * dstats[C + c + 2]),
+                           (float)(2.0 * dstats[C + c + 3]));
+    float4 v = tn_fma4(b, tn_ld4(z + 4 * i), a);
+    if (dzd) v = v + tn_ld4(dzd + 4 * i);
+    tn_st4(out + 4 * i, v);
+  }
+}
+extern "C" int tn_stats_bwd(const float* dz_direct, const float* z, const double* dstats, float* out, int R, int C, void* stream) {
+  TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0 && z && dstats && out && tn_aligned16(out) && tn_aligned16(z) && (!dz_direct || tn_aligned16(dz_direct)),
+             "stats_bwd: need C %% 4 == 0 and aligned tensors (R=%d C=%d)", R, C);
+  size_t n4 = (size_t)R * C / 4;
+  int blocks = (int)((n4 + TN_EW_THREADS - 1) / TN_EW_THREADS);
+  int cap = tn_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  stats_bwd_kernel<<<blocks, TN_EW_THREADS, 0, (cudaStream_t)stream>>>(dz_direct, z, dstats, out, n4, C / 4);
+  TN_LAUNCH_CHECK("stats_bwd_kernel");
+  return TN_OK;
+}
+
+// advance the dropout seed state (splitmix64) and publish the new step seed
+__global__ void seed_next_kernel(unsigned long long* state, unsigned long long* out) {
+  unsigned long long z = (*state += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  *out = z ^ (z >> 31);
+}
+extern "C" int tn_seed_next(unsigned long long* state, unsigned long long* out, void* stream) {
+  TN_REQUIRE(state && out, "seed_next: null argument");
+  seed_next_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, out);
+  TN_LAUNCH_CHECK("seed_next_kernel");
+  return TN_OK;
+}
+
+// out = dh * (1 - h^2)
+__global__ void tanh_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ h, float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float hv = h[i];
+    out[i] = dh[i] * (1.f - hv * hv);
+  }
+}
+extern "C" int tn_tanh_bwd(const float* dh, const float* h, float* out, long long n, void* stream) {
+  TN_REQUIRE(n > 0, "tanh_bwd: empty");
+  int blocks = (int)((n + 255) / 256);
+  int cap = tn_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  tanh_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dh, h, out, (size_t)n);
+  TN_LAUNCH_CHECK("tanh_bwd_kernel");
+  return TN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// row L2 normalisation:  y = x / max(||x||, eps)   (eps = 0: plain division)
+// ---------------------------------------------------------------------------
+__global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ norms, int B, int E, float eps) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* xr = x + (size_t)row * E;
+  float s = 0.f;
+  for (int i = lane; i < E; i += 32) s = fmaf(xr[i], xr[i], s);
+  float nrm = sqrtf(tn_warp_sum(s));
+  float d = eps > 0.f ? fmaxf(nrm, eps) : nrm;
+  for (int i = lane; i < E; i += 32) y[(size_t)row * E + i] = xr[i] / d;
+  if (lane == 0 && norms) norms[row] = nrm;
+}
+// dx = (dy - y * <y, dy>) / max(norm, eps) + dnorm * y      (dnorm optional: grad w.r.t. the returned norm)
+__global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ norms,
+                                  const float* __restrict__ dnorm, float* __restrict__ dx, int B, int E, float eps) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* yr = y + (size_t)row * E;
+  const float* gr = dy + (size_t)row * E;
+  float s = 0.f;
+  for (int i = lane; i < E; i += 32) s = fmaf(yr[i], gr[i], s);
+  s = tn_warp_sum(s);
+  float nrm = norms[row];
+  bool clamped = eps > 0.f && nrm < eps;          // F.normalize: denominator is the constant eps
+  float d = eps > 0.f ? fmaxf(nrm, eps) : nrm;
+  float dn = dnorm ? dnorm[row] : 0.f;
+  for (int i = lane; i < E; i += 32) {
+    float v = clamped ? gr[i] / d : (gr[i] - yr[i] * s) / d;
+    dx[(size_t)row * E + i] = fmaf(dn, yr[i], v);
+  }
+}
+extern "C" int tn_l2norm_fwd(const float* x, float* y, float* norms, int B, int E, float eps, void* stream) {
+  TN_REQUIRE(B > 0 && E > 0 && x && y, "l2norm_fwd: bad arguments");
+  l2norm_fwd_kernel<<<tn_cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(x, y, norms, B, E, eps);
+  TN_LAUNCH_CHECK("l2norm_fwd_kernel");
+  return TN_OK;
+}
+extern "C" int tn_l2norm_bwd(const float* dy, const float* y, const float* norms, const float* dnorm, float* dx, int B, int E,
+                             float eps, void* stream) {
+  TN_REQUIRE(B > 0 && E > 0 && dy && y && norms && dx, "l2norm_bwd: bad arguments");
+  l2norm_bwd_kernel<<<tn_cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(dy, y, norms, dnorm, dx, B, E, eps);
+  TN_LAUNCH_CHECK("l2norm_bwd_kernel");
+  return TN_OK;
+}

@@ -1,0 +1,219 @@
+// fp32 CUDA-core conv-as-GEMM kernels on NWC activations.  These are the exact-fp32
+// path for the shapes the tcgen05 kernel (gemm_tc.cu) does not take: the K-tap prolog
+// conv (80 -> H, k=3), the decoder / loss-head linears (few rows, 251 classes), odd
+// channel counts, and every weight-gradient that is not tile aligned.
+//
+//   fwd  : Z[r, co]  = bias[co] + sum_{k, ci} X[r + k - pad, ci] * W[co, ci, k]
+//   dgrad: same kernel with transpose_w = 1 (reads W[ci', co', K-1-k]): dX from dZ
+//   wgrad: dW[co, ci, k] += sum_r dZ[r, co] * X[r + k - pad, ci],  db[co] += sum_r dZ[r, co]
+//
+// Rows are b*T + t; taps never cross an utterance boundary (zero "same" padding).
+// Reference: Conv1dSamePadding (src/modules.py:14-40), nn.Conv1d k=1 in the skip
+// connection (src/models.py:452-455), nn.Linear in ASP / decoder / loss heads
+// (src/models.py:549-551, 510-513; src/losses.py:30, 70).
+#include "common.cuh"
+
+#define GM 64   // rows per tile
+#define GN 64   // output channels per tile
+#define GK 16   // reduction chunk
+
+
+__global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict__ X, const float* __restrict__ W,
+                                                        const float* __restrict__ bias, float* __restrict__ Z,
+                                                        double* __restrict__ stats, int R, int T, int Ci, int Co, int K,
+                                                        int transpose_w, int flags) {
+  __shared__ float As[GK][GM + 4];
+  __shared__ float Bs[GK][GN + 4];
+  __shared__ float red1[16][GN], red2[16][GN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int r0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
+  const int pad = K / 2;
+  const int KK = K * Ci;                // reduction length; kk = tap * Ci + ci
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int lk = tid & 15;              // reduction index inside the chunk handled by this thread's loads
+  const int lr = tid >> 4;              // row / column group
+  for (int kk0 = 0; kk0 < KK; kk0 += GK) {
+    const int kk = kk0 + lk;
+    const int tap = kk < KK ? kk / Ci : 0;
+    const int ci = kk < KK ? kk - tap * Ci : 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      // A tile: rows r0 + lr + 16p
+      const int m = lr + 16 * p;
+      const int r = r0 + m;
+      float v = 0.f;
+      if (kk < KK && r < R) {
+        const int t = r % T;
+        const int tt = t + tap - pad;
+        if (tt >= 0 && tt < T) v = __ldg(X + (size_t)(r + tap - pad) * Ci + ci);
+      }
+      As[lk][m] = v;
+      // B tile: output channels n0 + lr + 16p
+      const int n = n0 + m;
+      float wv = 0.f;
+      if (kk < KK && n < Co) {
+        wv = transpose_w ? __ldg(W + ((size_t)ci * Co + n) * K + (K - 1 - tap))   // W is [Ci(red), Co(out), K]
+                         : __ldg(W + ((size_t)n * Ci + ci) * K + tap);            // W is [Co(out), Ci(red), K]
+      }
+      Bs[lk][m] = wv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty * 4 + i;
+    if (r >= R) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= Co) continue;
+      float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+      if (flags & TN_EPI_TANH) v = tanhf(v);
+      float* zp = Z + (size_t)r * Co + n;
+      if (flags & TN_EPI_ACCUM) v += *zp;
+      *zp = v;
+      s1[j] += v;
+      s2[j] = fmaf(v, v, s2[j]);
+    }
+  }
+  if (stats) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red1[ty][tx * 4 + j] = s1[j]; red2[ty][tx * 4 + j] = s2[j]; }
+    __syncthreads();
+    if (tid < GN) {
+      const int n = n0 + tid;
+      if (n < Co) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int y = 0; y < 16; ++y) { a += red1[y][tid]; b += red2[y][tid]; }
+        atomicAdd(stats + n, (double)a);
+        atomicAdd(stats + Co + n, (double)b);
+      }
+    }
+  }
+}
+
+// dW[co, ci, k] += sum_r dZ[r, co] * X[r + k - pad, ci]; rows split over blockIdx.z
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ dZ, const float* __restrict__ X,
+                                                         float* __restrict__ dW, float* __restrict__ dbias, int R, int T,
+                                                         int Ci, int Co, int K, int rows_per_split) {
+  __shared__ float As[GK][GM + 4];   // As[row][co]
+  __shared__ float Bs[GK][GN + 4];   // Bs[row][kk]
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * GM;    // co tile
+  const int n0 = blockIdx.y * GN;    // kk tile (kk = tap * Ci + ci)
+  const int pad = K / 2;
+  const int KK = K * Ci;
+  const int ra = blockIdx.z * rows_per_split;
+  const int rb = min(R, ra + rows_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+
+  const int lc = tid & 63;           // column (co or kk) handled by this thread's loads
+  const int lr = tid >> 6;           // 0..3
+  const int co_l = m0 + lc;
+  const int kk_l = n0 + lc;
+  const int tap = kk_l < KK ? kk_l / Ci : 0;
+  const int ci = kk_l < KK ? kk_l - tap * Ci : 0;
+  for (int rr = ra; rr < rb; rr += GK) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int k = lr + 4 * p;
+      const int r = rr + k;
+      float a = 0.f, b = 0.f;
+      if (r < rb) {
+        if (co_l < Co) a = __ldg(dZ + (size_t)r * Co + co_l);
+        if (kk_l < KK) {
+          const int tt = (r % T) + tap - pad;
+          if (tt >= 0 && tt < T) b = __ldg(X + (size_t)(r + tap - pad) * Ci + ci);
+        }
+      }
+      As[k][lc] = a;
+      Bs[k][lc] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        bsum[i] += av[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = m0 + ty * 4 + i;
+    if (co >= Co) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kk = n0 + tx * 4 + j;
+      if (kk >= KK) continue;
+      const int tp = kk / Ci, c2 = kk - tp * Ci;
+      atomicAdd(dW + ((size_t)co * Ci + c2) * K + tp, acc[i][j]);
+    }
+    if (dbias && blockIdx.y == 0 && tx == 0) atomicAdd(dbias + co, bsum[i]);
+  }
+}
+
+extern "C" int tn_conv_gemm_simt(const float* X, const float* W, const float* bias, float* Z, double* stats, int B, int T,
+                                 int Ci, int Co, int K, int transpose_w, int flags, void* stream) {
+  TN_REQUIRE(B > 0 && T > 0 && Ci > 0 && Co > 0 && K > 0 && (K & 1), "conv_gemm: bad shape B=%d T=%d Ci=%d Co=%d K=%d (odd K only)", B, T, Ci, Co, K);
+  TN_REQUIRE(X && W && Z, "conv_gemm: null tensor");
+  long long R = (long long)B * T;
+  TN_REQUIRE(R < (1ll << 31) && tn_cdiv(Co, GN) <= 65535, "conv_gemm: shape too large");
+  dim3 grid(tn_cdiv(R, GM), tn_cdiv(Co, GN));
+  conv_gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, W, bias, Z, stats, (int)R, T, Ci, Co, K, transpose_w, flags);
+  TN_LAUNCH_CHECK("conv_gemm_kernel");
+  return TN_OK;
+}
+
+extern "C" int tn_conv_wgrad_simt(const float* dZ, const float* X, float* dW, float* dbias, int B, int T, int Ci, int Co, int K,
+                                  void* stream) {
+  TN_REQUIRE(B > 0 && T > 0 && Ci > 0 && Co > 0 && K > 0 && (K & 1), "conv_wgrad: bad shape B=%d T=%d Ci=%d Co=%d K=%d (odd K only)", B, T, Ci, Co, K);
+  TN_REQUIRE(dZ && X && dW, "conv_wgrad: null tensor");
+  long long R = (long long)B * T;
+  TN_REQUIRE(R < (1ll << 31), "conv_wgrad: shape too large");
+  int tiles = tn_cdiv(Co, GM) * tn_cdiv((long long)K * Ci, GN);
+  long long want = ((long long)tn_num_sms() * 4 + tiles - 1) / tiles;     // ~4 blocks per SM in total
+  long long max_split = (R + GK * 4 - 1) / (GK * 4);
+  long long split = want < 1 ? 1 : (want > max_split ? max_split : want);
+  if (split > 65535) split = 65535;
+  int rps = (int)((R + split - 1) / split);
+  rps = ((rps + GK - 1) / GK) * GK;
+  split = (R + rps - 1) / rps;
+  dim3 grid(tn_cdiv(Co, GM), tn_cdiv((long long)K * Ci, GN), (unsigned)split);
+  TN_REQUIRE(grid.y <= 65535, "conv_wgrad: K*Ci too large");
+  conv_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dZ, X, dW, dbias, (int)R, T, Ci, Co, K, rps);
+  TN_LAUNCH_CHECK("conv_wgrad_kernel");
+  return TN_OK;
+}

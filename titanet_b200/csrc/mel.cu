@@ -1,0 +1,149 @@
+// Waveform -> normalised log-mel spectrogram, one kernel.
+//   STFT (center=True reflect padding n_fft/2, window zero-padded to n_fft, one-sided,
+//   un-normalised) -> |.|^2 -> mel filterbank -> 10*log10(clamp(., 1e-10)) ->
+//   L2 normalisation over the mel axis (eps 1e-12).
+// Reference: transforms.MelSpectrogram.__call__ (src/transforms.py:158-184) with
+// torchaudio Spectrogram(power=None) / MelScale / AmplitudeToDB (lines 134-144); the
+// batched form reproduces datasets.collate_fn's zero padding of frames past each
+// utterance's own length (src/datasets.py:48-73).
+//
+// One block transforms a tile of MEL_FT consecutive frames of one utterance.  Two real
+// frames share one complex radix-2 FFT in shared memory (frame A in the real lane,
+// frame B in the imaginary lane), the spectra are separated with the conjugate-symmetry
+// identity, and the tile is written out in one coalesced pass in either layout.
+#include "common.cuh"
+
+#define MEL_FT 16
+#define MEL_THREADS 256
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+__global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
+                                                          const float* __restrict__ window, const float* __restrict__ fb,
+                                                          const int* __restrict__ band_lo, const int* __restrict__ band_hi,
+                                                          float* __restrict__ out, int L_stride, int L_full, int T_out,
+                                                          int N, int log2N, int hop, int n_mels, int nwc) {
+  extern __shared__ float smem[];
+  const int NF = N / 2 + 1;
+  float2* buf = reinterpret_cast<float2*>(smem);             // N complex
+  float2* tw = buf + N;                                      // N/2 twiddles
+  float* win = reinterpret_cast<float*>(tw + N / 2);         // N
+  float* pw = win + N;                                       // 2 * NF
+  float* melv = pw + 2 * NF;                                 // MEL_FT * (n_mels + 1)
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * MEL_FT;
+  const int L = lengths ? lengths[b] : L_full;
+  const int T_valid = 1 + L / hop;
+  const float* x = wave + (size_t)b * L_stride;
+  const int half = N / 2;
+
+  for (int i = tid; i < half; i += MEL_THREADS) {
+    float s, c;
+    sincospif(-(float)i / (float)half, &s, &c);
+    tw[i] = make_float2(c, s);
+  }
+  for (int i = tid; i < N; i += MEL_THREADS) win[i] = window[i];
+  __syncthreads();
+
+  for (int jp = 0; jp < MEL_FT; jp += 2) {
+    const int ta = t0 + jp, tb = ta + 1;
+    const bool va = ta < T_valid && ta < T_out, vb = tb < T_valid && tb < T_out;
+    if (!va && !vb) {
+      for (int i = tid; i < 2 * n_mels; i += MEL_THREADS) melv[(jp + i / n_mels) * (n_mels + 1) + i % n_mels] = 0.f;
+      continue;        // uniform across the block
+    }
+    // windowed frames, bit-reversed order
+    for (int n = tid; n < N; n += MEL_THREADS) {
+      float w = win[n];
+      int sa = ta * hop + n - half, sb = sa + hop;
+      sa = sa < 0 ? -sa : (sa >= L ? 2 * (L - 1) - sa : sa);
+      sb = sb < 0 ? -sb : (sb >= L ? 2 * (L - 1) - sb : sb);
+      float xa = (va && w != 0.f) ? x[sa] * w : 0.f;
+      float xb = (vb && w != 0.f) ? x[sb] * w : 0.f;
+      buf[__brev((unsigned)n) >> (32 - log2N)] = make_float2(xa, xb);
+    }
+    __syncthreads();
+    for (int s = 0; s < log2N; ++s) {
+      const int h = 1 << s;
+      for (int i = tid; i < half; i += MEL_THREADS) {
+        const int pos = i & (h - 1);
+        const int i0 = ((i >> s) << (s + 1)) + pos, i1 = i0 + h;
+        const float2 w = tw[pos * (half >> s)];
+        const float2 a = buf[i0], t = cmul(w, buf[i1]);
+        buf[i0] = make_float2(a.x + t.x, a.y + t.y);
+        buf[i1] = make_float2(a.x - t.x, a.y - t.y);
+      }
+      __syncthreads();
+    }
+    // split the two real spectra, take |.|^2
+    for (int k = tid; k < NF; k += MEL_THREADS) {
+      const float2 zk = buf[k], zc = buf[(N - k) & (N - 1)];
+      const float ar = 0.5f * (zk.x + zc.x), ai = 0.5f * (zk.y - zc.y);     // X_A = (Z[k] + conj Z[N-k]) / 2
+      const float br = 0.5f * (zk.y + zc.y), bi = -0.5f * (zk.x - zc.x);    // X_B = (Z[k] - conj Z[N-k]) / (2i)
+      pw[k] = ar * ar + ai * ai;
+      pw[NF + k] = br * br + bi * bi;
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * n_mels; i += MEL_THREADS) {
+      const int j = i / n_mels, m = i - j * n_mels;
+      const bool valid = j == 0 ? va : vb;
+      float acc = 0.f;
+      const float* p = pw + j * NF;
+      const int lo = band_lo[m], hi = band_hi[m];
+      for (int f = lo; f < hi; ++f) acc = fmaf(p[f], __ldg(fb + (size_t)f * n_mels + m), acc);
+      melv[(jp + j) * (n_mels + 1) + m] = valid ? 10.0f * log10f(fmaxf(acc, 1e-10f)) : 0.f;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  // L2-normalise every frame of the tile over the mel axis (warp per frame)
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int j = warp; j < MEL_FT; j += MEL_THREADS / 32) {
+    float* row = melv + j * (n_mels + 1);
+    float s = 0.f;
+    for (int m = lane; m < n_mels; m += 32) s = fmaf(row[m], row[m], s);
+    s = tn_warp_sum(s);
+    const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+    for (int m = lane; m < n_mels; m += 32) row[m] *= inv;
+  }
+  __syncthreads();
+  const int total = MEL_FT * n_mels;
+  if (nwc) {
+    for (int i = tid; i < total; i += MEL_THREADS) {
+      const int j = i / n_mels, m = i - j * n_mels;
+      if (t0 + j < T_out) out[((size_t)b * T_out + t0 + j) * n_mels + m] = melv[j * (n_mels + 1) + m];
+    }
+  } else {
+    for (int i = tid; i < total; i += MEL_THREADS) {
+      const int m = i / MEL_FT, j = i - m * MEL_FT;
+      if (t0 + j < T_out) out[((size_t)b * n_mels + m) * T_out + t0 + j] = melv[j * (n_mels + 1) + m];
+    }
+  }
+}
+
+// wave [B, L_stride] (utterance b uses its first lengths[b] samples, or L_full when
+// lengths == NULL) -> out [B, n_mels, T_out] (nwc = 0) or [B, T_out, n_mels] (nwc = 1).
+// window: [n_fft] (already zero-padded); fb: [n_fft/2+1, n_mels]; band_lo/hi: [n_mels]
+// half-open ranges of non-zero filterbank rows.  Frames >= 1 + L_b/hop are zero filled.
+extern "C" int tn_mel_fwd(const float* wave, const int* lengths, const float* window, const float* fb, const int* band_lo,
+                          const int* band_hi, float* out, int B, int L_stride, int L_full, int T_out, int n_fft, int hop,
+                          int n_mels, int nwc, void* stream) {
+  TN_REQUIRE(wave && window && fb && band_lo && band_hi && out, "mel_fwd: null tensor");
+  TN_REQUIRE(B > 0 && B <= 65535 && T_out > 0 && hop > 0 && n_mels > 0 && n_mels <= 256, "mel_fwd: bad shape B=%d T_out=%d hop=%d n_mels=%d", B, T_out, hop, n_mels);
+  int log2N = 0;
+  while ((1 << log2N) < n_fft) ++log2N;
+  TN_UNSUPPORTED((1 << log2N) != n_fft || n_fft < 64 || n_fft > 4096, "mel_fwd: n_fft=%d must be a power of two in [64, 4096]", n_fft);
+  TN_REQUIRE(lengths || L_full > n_fft / 2, "mel_fwd: reflect padding needs more than n_fft/2 samples (L=%d)", L_full);
+  TN_REQUIRE(L_full <= L_stride, "mel_fwd: L_full > L_stride");
+  const int NF = n_fft / 2 + 1;
+  size_t smem = sizeof(float) * ((size_t)2 * n_fft + n_fft + n_fft + 2 * NF + (size_t)MEL_FT * (n_mels + 1));
+  if (smem > 48 * 1024) {
+    TN_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  dim3 grid(tn_cdiv(T_out, MEL_FT), B);
+  mel_kernel<<<grid, MEL_THREADS, smem, (cudaStream_t)stream>>>(wave, lengths, window, fb, band_lo, band_hi, out, L_stride,
+                                                                 L_full, T_out, n_fft, log2N, hop, n_mels, nwc);
+  TN_LAUNCH_CHECK("mel_kernel");
+  return TN_OK;
+}

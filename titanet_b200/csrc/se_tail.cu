@@ -1,0 +1,292 @@
+// Squeeze-and-excitation and the mega-block tail, NWC layout.
+//   m[b,c]    = mean_t a3[b,t,c]                          (a3 = lazy activation of sub-block 3)
+//   gate[b,:] = sigmoid(W2 relu(W1 m[b,:]))               (no biases)
+//   out       = dropout(relu( (s*scale_s + shift_s) + gate[b,c] * a3 ))
+// Reference: modules.SqueezeExcitation.forward (src/modules.py:173-189) fed by the
+// post-ReLU/dropout output of sub-block 3 (src/models.py:435-449), and
+// MegaBlock.forward (src/models.py:467-472).
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------
+// squeeze: mean over time of the lazy activation
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TN_EW_THREADS) se_mean_kernel(const float* __restrict__ z, float* __restrict__ m, TnAct act,
+                                                                int T, int C, int tpb, float inv_T) {
+  act = tn_act_init(act);
+  __shared__ float4 red[TN_EW_THREADS];
+  TnTile tl = tn_tile(C);
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * tpb, t1 = min(T, t0 + tpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    const int q = qb + tl.q0;
+    float4 s = tn_zero4();
+    if (tl.active && q < tl.Q)
+      for (int t = t0 + tl.lane; t < t1; t += tl.lanes) {
+        size_t off = ((size_t)b * T + t) * C + 4 * q;
+        s = s + tn_act4(act, tn_ld4(z + off), 4 * q, off >> 2, nullptr);
+      }
+    tn_lane_reduce_atomic(tl, s, q, m + (size_t)b * C, red, inv_T);
+  }
+}
+
+// excitation MLP, one block per batch item.  smem: m[C] + h[Cr]
+__global__ void __launch_bounds__(256) se_mlp_fwd_kernel(const float* __restrict__ m, const float* __restrict__ W1,
+                                                         const float* __restrict__ W2, float* __restrict__ gate, int C, int Cr) {
+  extern __shared__ float sm[];
+  float* ms = sm;
+  float* hs = sm + C;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) ms[c] = m[(size_t)b * C + c];
+  __syncthreads();
+  for (int j = warp; j < Cr; j += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(__ldg(W1 + (size_t)j * C + c), ms[c], s);
+    s = tn_warp_sum(s);
+    if (lane == 0) hs[j] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < Cr; ++j) s = fmaf(__ldg(W2 + (size_t)c * Cr + j), hs[j], s);
+    gate[(size_t)b * C + c] = 1.f / (1.f + expf(-s));
+  }
+}
+
+// backward of the MLP: dgate -> dm, dW1 +=, dW2 +=.  smem: m[C] + h[Cr] + dh[Cr] + dp[C]
+__global__ void __launch_bounds__(256) se_mlp_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ gate,
+                                                         const float* __restrict__ m, const float* __restrict__ W1,
+                                                         const float* __restrict__ W2, float* __restrict__ dm,
+                                                         float* __restrict__ dW1, float* __restrict__ dW2, int C, int Cr) {
+  extern __shared__ float sm[];
+  float* ms = sm;
+  float* hs = ms + C;
+  float* dh = hs + Cr;
+  float* dp = dh + Cr;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    ms[c] = m[(size_t)b * C + c];
+    float g = gate[(size_t)b * C + c];
+    dp[c] = dgate[(size_t)b * C + c] * g * (1.f - g);
+  }
+  __syncthreads();
+  for (int j = warp; j < Cr; j += nw) {       // recompute h and dh = W2^T dp
+    float s = 0.f, d = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      s = fmaf(__ldg(W1 + (size_t)j * C + c), ms[c], s);
+      d = fmaf(__ldg(W2 + (size_t)c * Cr + j), dp[c], d);
+    }
+    s = tn_warp_sum(s);
+    d = tn_warp_sum(d);
+    if (lane == 0) { hs[j] = fmaxf(s, 0.f); dh[j] = s > 0.f ? d : 0.f; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    const float dpc = dp[c], mc = ms[c];
+    for (int j = 0; j < Cr; ++j) {
+      s = fmaf(__ldg(W1 + (size_t)j * C + c), dh[j], s);
+      atomicAdd(dW2 + (size_t)c * Cr + j, dpc * hs[j]);
+      atomicAdd(dW1 + (size_t)j * C + c, dh[j] * mc);
+    }
+    dm[(size_t)b * C + c] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// tail forward
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TN_EW_THREADS) tail_fwd_kernel(const float* __restrict__ z3, const float* __restrict__ s,
+                                                                 const float* __restrict__ gate, float* __restrict__ out,
+                                                                 TnAct act3, TnAct act_s, TnAct act_o, int R, int T, int C, int rpb) {
+  act3 = tn_act_init(act3);
+  act_o = tn_act_init(act_o);
+  TnTile tl = tn_tile(C);
+  const int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    const int q = qb + tl.q0;
+    if (!tl.active || q >= tl.Q) continue;
+    const float4 ssc = tn_ld4(act_s.scale + 4 * q), ssh = tn_ld4(act_s.shift + 4 * q);
+    for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
+      const int b = r / T;
+      size_t off = (size_t)r * C + 4 * q;
+      float4 a3 = tn_act4(act3, tn_ld4(z3 + off), 4 * q, off >> 2, nullptr);
+      float4 g = tn_ld4(gate + (size_t)b * C + 4 * q);
+      float4 v = tn_fma4(g, a3, tn_fma4(tn_ld4(s + off), ssc, ssh));
+      float4 keep = tn_drop4(act_o, off >> 2);
+      v.x = v.x > 0.f ? v.x * keep.x : 0.f; v.y = v.y > 0.f ? v.y * keep.y : 0.f;
+      v.z = v.z > 0.f ? v.z * keep.z : 0.f; v.w = v.w > 0.f ? v.w * keep.w : 0.f;
+      tn_st4(out + off, v);
+    }
+  }
+}
+
+// g = dout * d out / d pre  (pre > 0 and kept  <=>  out > 0)
+__device__ __forceinline__ float4 tail_gout(float4 dout, float4 o, float inv_keep) {
+  return make_float4(o.x > 0.f ? dout.x * inv_keep : 0.f, o.y > 0.f ? dout.y * inv_keep : 0.f,
+                     o.z > 0.f ? dout.z * inv_keep : 0.f, o.w > 0.f ? dout.w * inv_keep : 0.f);
+}
+
+// pass 1: dgate[b,c] += sum_t g * a3
+__global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd1_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                                  const float* __restrict__ z3, float* __restrict__ dgate,
+                                                                  TnAct act3, float inv_keep_o, int T, int C, int tpb) {
+  act3 = tn_act_init(act3);
+  __shared__ float4 red[TN_EW_THREADS];
+  TnTile tl = tn_tile(C);
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * tpb, t1 = min(T, t0 + tpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    const int q = qb + tl.q0;
+    float4 acc = tn_zero4();
+    if (tl.active && q < tl.Q)
+      for (int t = t0 + tl.lane; t < t1; t += tl.lanes) {
+        size_t off = ((size_t)b * T + t) * C + 4 * q;
+        float4 g = tail_gout(tn_ld4(dout + off), tn_ld4(out + off), inv_keep_o);
+        float4 a3 = tn_act4(act3, tn_ld4(z3 + off), 4 * q, off >> 2, nullptr);
+        acc = tn_fma4(g, a3, acc);
+      }
+    tn_lane_reduce_atomic(tl, acc, q, dgate + (size_t)b * C, red);
+  }
+}
+
+// pass 2: dz3, ds and the four per-channel reductions
+__global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd2_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                                  const float* __restrict__ z3, const float* __restrict__ s,
+                                                                  const float* __restrict__ gate, const float* __restrict__ dm,
+                                                                  float* __restrict__ dz3, float* __restrict__ ds,
+                                                                  float* __restrict__ dsc3, float* __restrict__ dsh3,
+                                                                  float* __restrict__ dscs, float* __restrict__ dshs,
+                                                                  TnAct act3, TnAct act_s, float inv_keep_o, float inv_T, int R,
+                                                                  int T, int C, int rpb) {
+  act3 = tn_act_init(act3);
+  __shared__ float4 red[TN_EW_THREADS];
+  TnTile tl = tn_tile(C);
+  const int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    const int q = qb + tl.q0;
+    float4 a1 = tn_zero4(), a2 = tn_zero4(), a3s = tn_zero4(), a4 = tn_zero4();
+    if (tl.active && q < tl.Q) {
+      const float4 sc3 = tn_ld4(act3.scale + 4 * q), scs = tn_ld4(act_s.scale + 4 * q);
+      for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
+        const int b = r / T;
+        size_t off = (size_t)r * C + 4 * q;
+        float4 g = tail_gout(tn_ld4(dout + off), tn_ld4(out + off), inv_keep_o);
+        float4 zz = tn_ld4(z3 + off), mult;
+        tn_act4(act3, zz, 4 * q, off >> 2, &mult);
+        float4 gt = tn_ld4(gate + (size_t)b * C + 4 * q);
+        float4 dmean = tn_ld4(dm + (size_t)b * C + 4 * q) * inv_T;
+        float4 da = tn_fma4(g, gt, dmean) * mult;          // dL/d pre3
+        a1 = tn_fma4(da, zz, a1);
+        a2 = a2 + da;
+        tn_st4(dz3 + off, da * sc3);
+        float4 sv = tn_ld4(s + off);
+        a3s = tn_fma4(g, sv, a3s);
+        a4 = a4 + g;
+        tn_st4(ds + off, g * scs);
+      }
+    }
+    tn_lane_reduce_atomic(tl, a1, q, dsc3, red);
+    tn_lane_reduce_atomic(tl, a2, q, dsh3, red);
+    tn_lane_reduce_atomic(tl, a3s, q, dscs, red);
+    tn_lane_reduce_atomic(tl, a4, q, dshs, red);
+  }
+}
+
+static int tail_rows_per_block(long long R) {
+  long long target = (long long)tn_num_sms() * 16;
+  long long rpb = (R + target - 1) / target;
+  if (rpb < 16) rpb = 16;
+  if (rpb > 128) rpb = 128;
+  return (int)rpb;
+}
+static int time_per_block(int B, int T) {
+  // blocks = B * ceil(T / tpb); aim at >= 8 blocks per SM
+  long long target = (long long)tn_num_sms() * 8;
+  long long chunks = (target + B - 1) / B;
+  if (chunks < 1) chunks = 1;
+  long long tpb = (T + chunks - 1) / chunks;
+  if (tpb < 16) tpb = 16;
+  return (int)tpb;
+}
+
+#define SE_COMMON_CHECK(name)                                                                                   \
+  TN_REQUIRE(B > 0 && T > 0 && C > 0 && C % 4 == 0 && B <= 65535, name ": need C %% 4 == 0, B <= 65535 (B=%d T=%d C=%d)", B, T, C)
+
+extern "C" int tn_se_mean(const float* z3, float* m, const float* scale, const float* shift, int relu, float drop_p,
+                          const unsigned long long* seed, unsigned int layer, int B, int T, int C, void* stream) {
+  SE_COMMON_CHECK("se_mean");
+  TN_REQUIRE(z3 && m && scale && shift, "se_mean: null tensor");
+  TN_CUDA(cudaMemsetAsync(m, 0, sizeof(float) * (size_t)B * C, (cudaStream_t)stream));
+  int tpb = time_per_block(B, T);
+  dim3 grid(tn_cdiv(T, tpb), B);
+  se_mean_kernel<<<grid, TN_EW_THREADS, 0, (cudaStream_t)stream>>>(z3, m, tn_make_act(scale, shift, relu, drop_p, seed, layer), T, C, tpb, 1.0f / (float)T);
+  TN_LAUNCH_CHECK("se_mean_kernel");
+  return TN_OK;
+}
+
+extern "C" int tn_se_mlp_fwd(const float* m, const float* W1, const float* W2, float* gate, int B, int C, int Cr, void* stream) {
+  TN_REQUIRE(B > 0 && C > 0 && Cr > 0 && m && W1 && W2 && gate, "se_mlp_fwd: bad arguments");
+  size_t smem = sizeof(float) * (size_t)(C + Cr);
+  TN_REQUIRE(smem <= 48 * 1024, "se_mlp_fwd: C too large");
+  se_mlp_fwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(m, W1, W2, gate, C, Cr);
+  TN_LAUNCH_CHECK("se_mlp_fwd_kernel");
+  return TN_OK;
+}
+
+extern "C" int tn_se_mlp_bwd(const float* dgate, const float* gate, const float* m, const float* W1, const float* W2, float* dm,
+                             float* dW1, float* dW2, int B, int C, int Cr, void* stream) {
+  TN_REQUIRE(B > 0 && C > 0 && Cr > 0 && dgate && gate && m && W1 && W2 && dm && dW1 && dW2, "se_mlp_bwd: bad arguments");
+  size_t smem = sizeof(float) * (size_t)(2 * C + 2 * Cr);
+  TN_REQUIRE(smem <= 48 * 1024, "se_mlp_bwd: C too large");
+  se_mlp_bwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(dgate, gate, m, W1, W2, dm, dW1, dW2, C, Cr);
+  TN_LAUNCH_CHECK("se_mlp_bwd_kernel");
+  return TN_OK;
+}
+
+extern "C" int tn_tail_fwd(const float* z3, const float* s, const float* gate, float* out, const float* scale3,
+                           const float* shift3, float drop3, unsigned int layer3, const float* scale_s, const float* shift_s,
+                           float drop_o, unsigned int layer_o, const unsigned long long* seed, int B, int T, int C, void* stream) {
+  SE_COMMON_CHECK("tail_fwd");
+  TN_REQUIRE(z3 && s && gate && out && scale3 && shift3 && scale_s && shift_s, "tail_fwd: null tensor");
+  long long R = (long long)B * T;
+  TN_REQUIRE(R < (1ll << 31), "tail_fwd: B*T too large");
+  int rpb = tail_rows_per_block(R);
+  tail_fwd_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(
+      z3, s, gate, out, tn_make_act(scale3, shift3, 1, drop3, seed, layer3), tn_make_act(scale_s, shift_s, 0, 0.f, seed, 0),
+      tn_make_act(scale_s, shift_s, 1, drop_o, seed, layer_o), (int)R, T, C, rpb);
+  TN_LAUNCH_CHECK("tail_fwd_kernel");
+  return TN_OK;
+}
+
+extern "C" int tn_tail_bwd1(const float* dout, const float* out, const float* z3, float* dgate, const float* scale3,
+                            const float* shift3, float drop3, unsigned int layer3, float drop_o, const unsigned long long* seed, int B,
+                            int T, int C, void* stream) {
+  SE_COMMON_CHECK("tail_bwd1");
+  TN_REQUIRE(dout && out && z3 && dgate && scale3 && shift3, "tail_bwd1: null tensor");
+  TN_CUDA(cudaMemsetAsync(dgate, 0, sizeof(float) * (size_t)B * C, (cudaStream_t)stream));
+  int tpb = time_per_block(B, T);
+  dim3 grid(tn_cdiv(T, tpb), B);
+  float inv_keep_o = drop_o > 0.f ? 1.f / (1.f - drop_o) : 1.f;
+  tail_bwd1_kernel<<<grid, TN_EW_THREADS, 0, (cudaStream_t)stream>>>(dout, out, z3, dgate, tn_make_act(scale3, shift3, 1, drop3, seed, layer3), inv_keep_o, T, C, tpb);
+  TN_LAUNCH_CHECK("tail_bwd1_kernel");
+  return TN_OK;
+}
+
+// dsc3/dsh3/dscs/dshs are ACCUMULATED into (caller zeroes them)
+extern "C" int tn_tail_bwd2(const float* dout, const float* out, const float* z3, const float* s, const float* gate,
+                            const float* dm, float* dz3, float* ds, float* dsc3, float* dsh3, float* dscs, float* dshs,
+                            const float* scale3, const float* shift3, float drop3, unsigned int layer3, const float* scale_s,
+                            const float* shift_s, float drop_o, const unsigned long long* seed, int B, int T, int C, void* stream) {
+  SE_COMMON_CHECK("tail_bwd2");
+  TN_REQUIRE(dout && out && z3 && s && gate && dm && dz3 && ds && dsc3 && dsh3 && dscs && dshs && scale3 && shift3 && scale_s && shift_s,
+             "tail_bwd2: null tensor");
+  long long R = (long long)B * T;
+  TN_REQUIRE(R < (1ll << 31), "tail_bwd2: B*T too large");
+  int rpb = tail_rows_per_block(R);
+  float inv_keep_o = drop_o > 0.f ? 1.f / (1.f - drop_o) : 1.f;
+  tail_bwd2_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(
+      dout, out, z3, s, gate, dm, dz3, ds, dsc3, dsh3, dscs, dshs, tn_make_act(scale3, shift3, 1, drop3, seed, layer3),
+      tn_make_act(scale_s, shift_s, 0, 0.f, seed, 0), inv_keep_o, 1.0f / (float)T, (int)R, T, C, rpb);
+  TN_LAUNCH_CHECK("tail_bwd2_kernel");
+  return TN_OK;
+}

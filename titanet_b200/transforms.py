@@ -1,0 +1,168 @@
+"""Drop-in for the mel front end of the reference's ``src/transforms.py``.
+
+``MelSpectrogram`` keeps the reference's constructor signature and its
+example-dict call contract (src/transforms.py:111-203) and adds a batched entry point
+(``batch``) that turns ``[B, L]`` waveforms (+ per-utterance lengths) into the padded
+``[B, n_mels, T]`` tensor ``datasets.collate_fn`` would build (src/datasets.py:48-73).
+The arithmetic is one CUDA kernel (csrc/mel.cu).  The window and the HTK filterbank
+are small host-side constants computed here with the formulas torchaudio uses
+(``torch.hann_window``; ``torchaudio.functional.melscale_fbanks``, htk, norm=None).
+
+Out of the accelerated path (DESIGN.md "scope"): SpecAugment (time stretch + masks,
+SURVEY §8f rank 2), ``SpeedPerturbation``, ``Reverb``; ``Resample`` only accepts inputs
+already at the target rate.
+"""
+from __future__ import annotations
+
+import math
+import random
+
+import torch
+
+from . import _ops as ops
+
+
+def copy_example(example):
+    """Copy a dataset example, cloning its tensors (reference: src/transforms.py:12-22)."""
+    return {k: (torch.clone(v) if isinstance(v, torch.Tensor) else v) for k, v in example.items()}
+
+
+def _htk_filterbank(n_freqs: int, n_mels: int, sample_rate: int) -> torch.Tensor:
+    """[n_freqs, n_mels] triangular HTK mel filters over 0 .. sample_rate/2, no area norm."""
+    freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    mel_max = 2595.0 * math.log10(1.0 + float(sample_rate // 2) / 700.0)
+    mel_pts = torch.linspace(0.0, mel_max, n_mels + 2)
+    hz_pts = 700.0 * (10.0 ** (mel_pts / 2595.0) - 1.0)
+    width = hz_pts[1:] - hz_pts[:-1]
+    dist = hz_pts.unsqueeze(0) - freqs.unsqueeze(1)
+    rising = (-1.0 * dist[:, :-2]) / width[:-1]
+    falling = dist[:, 2:] / width[1:]
+    return torch.clamp(torch.minimum(rising, falling), min=0.0)
+
+
+class MelSpectrogram:
+    """Waveform -> L2-normalised log-mel spectrogram (reference: src/transforms.py:111-203)."""
+
+    def __init__(self, sample_rate, n_fft=400, win_length=None, hop_length=None, n_mels=128, specaugment_min_speed=0.95,
+                 specaugment_max_speed=1.05, specaugment_freq_mask_ratio=0.35, specaugment_freq_mask_num=1,
+                 specaugment_time_mask_ratio=0.15, specaugment_time_mask_num=1, specaugment_probability=1.0):
+        self.sample_rate = sample_rate
+        self.n_fft = n_fft
+        self.win_length = win_length if win_length is not None else n_fft          # torchaudio defaults
+        self.hop_length = hop_length if hop_length is not None else self.win_length // 2
+        self.n_mels = n_mels
+        self.specaugment_min_speed = specaugment_min_speed
+        self.specaugment_max_speed = specaugment_max_speed
+        self.specaugment_freq_mask_ratio = specaugment_freq_mask_ratio
+        self.specaugment_freq_mask_num = specaugment_freq_mask_num
+        self.specaugment_time_mask_ratio = specaugment_time_mask_ratio
+        self.specaugment_time_mask_num = specaugment_time_mask_num
+        self.specaugment_probability = specaugment_probability
+        if self.n_fft & (self.n_fft - 1) or not 64 <= self.n_fft <= 4096:
+            raise NotImplementedError(f"n_fft={n_fft}: the CUDA STFT needs a power of two in [64, 4096] "
+                                      "(the reference's training configuration uses 512)")
+        if self.win_length > self.n_fft:
+            raise ValueError("win_length must be <= n_fft")
+        # host-side constants
+        window = torch.zeros(self.n_fft)
+        off = (self.n_fft - self.win_length) // 2
+        window[off:off + self.win_length] = torch.hann_window(self.win_length, periodic=True)
+        fb = _htk_filterbank(self.n_fft // 2 + 1, n_mels, sample_rate)
+        nz = fb > 0
+        lo = torch.where(nz.any(0), nz.float().argmax(0), torch.zeros(n_mels, dtype=torch.long))
+        hi = torch.where(nz.any(0), fb.shape[0] - nz.flip(0).float().argmax(0), torch.zeros(n_mels, dtype=torch.long))
+        self._host = (window, fb.contiguous(), lo.to(torch.int32), hi.to(torch.int32))
+        self._dev = {}
+
+    def _consts(self, device):
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = tuple(t.to(device) for t in self._host)
+        return self._dev[key]
+
+    def n_frames(self, n_samples: int) -> int:
+        return 1 + n_samples // self.hop_length
+
+    def batch(self, waveforms: torch.Tensor, lengths: torch.Tensor | None = None, channels_last: bool = False) -> torch.Tensor:
+        """``[B, L]`` CUDA waveforms -> ``[B, n_mels, T]`` with ``T = 1 + L // hop``.  With
+        ``lengths`` (samples per utterance) each utterance is transformed on its own length
+        (own reflect padding) and frames past it are zero, like ``collate_fn``."""
+        if waveforms.dim() != 2:
+            raise ValueError("expected [B, L] waveforms")
+        if lengths is None and waveforms.shape[1] <= self.n_fft // 2:
+            raise ValueError("waveform shorter than n_fft // 2 + 1 samples (reflect padding)")
+        window, fb, lo, hi = self._consts(waveforms.device)
+        return ops.mel_forward(waveforms, lengths, window, fb, lo, hi, self.n_fft, self.hop_length, self.n_mels,
+                               nwc=channels_last)
+
+    def __call__(self, example):
+        assert isinstance(example, dict) and "waveform" in example, "Wrong input structure"
+        new_example = copy_example(example)
+        apply_specaugment = random.random() < self.specaugment_probability
+        if apply_specaugment:
+            raise NotImplementedError("SpecAugment (time stretch / frequency / time masks) is not part of the CUDA mel "
+                                      "path yet; construct with specaugment_probability=0.0 (the reference's default "
+                                      "training configuration does, parameters.yml:87-91)")
+        wave = new_example["waveform"]
+        src_device = wave.device
+        if wave.dim() == 1:
+            wave = wave.unsqueeze(0)
+        dev = src_device if src_device.type == "cuda" else torch.device("cuda")
+        spec = self.batch(wave.to(device=dev, dtype=torch.float32))                # [C, n_mels, T]
+        new_example["spectrogram"] = spec.to(src_device)
+        return new_example
+
+
+class RandomChunk:
+    """Random crop of utterances longer than ``max_length`` seconds (reference:
+    src/transforms.py:206-233); slicing only, no kernel."""
+
+    def __init__(self, max_length, lengths):
+        self.max_length = max_length
+        self.lengths = lengths
+
+    def __call__(self, example):
+        assert isinstance(example, dict) and "waveform" in example and "sample_rate" in example, "Wrong input structure"
+        new_example = copy_example(example)
+        num_samples = new_example["waveform"].size(-1)
+        if num_samples / new_example["sample_rate"] > self.max_length:
+            length = random.choice(self.lengths)
+            samples = int(length * new_example["sample_rate"])
+            start = random.randint(0, num_samples - samples)
+            new_example["waveform"] = new_example["waveform"][:, start:start + samples]
+        return new_example
+
+
+class Resample:
+    """Identity for inputs already at the target rate; anything else is out of scope."""
+
+    def __init__(self, target_sample_rate):
+        self.target_sample_rate = target_sample_rate
+
+    def __call__(self, example):
+        assert isinstance(example, dict) and "waveform" in example and "sample_rate" in example, "Wrong input structure"
+        if example["sample_rate"] != self.target_sample_rate:
+            raise NotImplementedError("resampling is outside the titanet_b200 hot path; feed 16 kHz audio")
+        return copy_example(example)
+
+
+def get_transforms(enabled, rir_corpora_path, max_length=3, chunk_lengths=[1.5, 2, 3], min_speed=0.95, max_speed=1.05,
+                   sample_rate=16000, n_fft=512, win_length=25, hop_length=10, n_mels=80, freq_mask_ratio=0.35,
+                   freq_mask_num=1, time_mask_ratio=0.15, time_mask_num=1, probability=1.0, device="cpu", training=True):
+    """Transformation list of the TitaNet paper (reference: src/transforms.py:25-75)."""
+    if enabled is None:
+        enabled = []
+    transformations = [Resample(sample_rate)]
+    if "chunk" in enabled:
+        transformations += [RandomChunk(max_length, chunk_lengths)]
+    if "reverb" in enabled and training:
+        raise NotImplementedError("Reverb augmentation is outside the titanet_b200 hot path")
+    transformations += [
+        MelSpectrogram(sample_rate, n_fft=n_fft, win_length=int(win_length / 1000 * sample_rate),
+                       hop_length=int(hop_length / 1000 * sample_rate), n_mels=n_mels, specaugment_min_speed=min_speed,
+                       specaugment_max_speed=max_speed, specaugment_freq_mask_ratio=freq_mask_ratio,
+                       specaugment_freq_mask_num=freq_mask_num, specaugment_time_mask_ratio=time_mask_ratio,
+                       specaugment_time_mask_num=time_mask_num,
+                       specaugment_probability=(probability if "specaugment" in enabled and training else 0.0))
+    ]
+    return transformations
