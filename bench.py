@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Headline benchmark: utterances/s of the TitaNet hot path, forward + backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one batch of synthetic utterances:
+raw waveform -> mel (CUDA) -> TitaNet-S/17 encoder + decoder -> CE loss -> backward
+(gradients for every parameter; N>1: + one NCCL all-reduce of the gradients).  The
+workload is BASELINE.json configs[1] (TitaNet-S, CE loss, batch 64 per GPU, 3 s @ 16 kHz
+synthetic waveforms, dropout 0.1 as parameters.yml:57).
+
+One JSON line on stdout (rank 0).  ``value`` is device-resident throughput (inputs already
+in HBM), ``e2e`` the same metric through the public module API with pinned host buffers
+(H2D of the step's waveforms + labels and a D2H read of the loss inside the timed region).
+``--impl reference`` times the CPU implementation of the same path (the oracle port of
+the reference's modules; torch CPU ops with all host threads) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+SAMPLE_RATE, N_CLASSES = 16000, 251
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="utterances per GPU per step")
+    ap.add_argument("--seconds", type=float, default=3.0)
+    ap.add_argument("--model", default="s")
+    ap.add_argument("--blocks", type=int, default=17)
+    ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--cpu-batch", type=int, default=8, help="utterances per step of the CPU arm / CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (torch CPU ops, all host threads)
+# ----------------------------------------------------------------------------
+def cpu_step_factory(args, batch):
+    import titanet_oracle as O
+    spec = O.TitaNetSpec.named(args.model, args.blocks, dropout=args.dropout)
+    sd = O.synth_state_dict(spec, "ce", N_CLASSES)
+    wave, labels = O.synthetic_batch(batch, seconds=args.seconds, n_classes=N_CLASSES, seed=42)
+
+    def step():
+        # per-utterance mel loop + collate, like datasets.py:292-293 / 48-73, then fwd + bwd
+        x, _ = O.collate_pad([O.mel_spectrogram(w.view(1, -1)) for w in wave])
+        out = O.titanet_step(sd, spec, x, labels, "ce", training=True)
+        return float(out[2])
+
+    return step
+
+
+def time_cpu(args, batch, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_step_factory(args, batch)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return batch / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = args.cpu_batch
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 1))
+    value, dt = time_cpu(args, batch, steps, warmup)
+    cores = os.cpu_count() or 1
+    sample = f"{steps} steps of {batch} utterances x {args.seconds:g} s (mel + fwd + bwd), {warmup} warm-up, torch CPU ops"
+    line = {
+        "impl": "reference", "metric": "utterances/sec (TitaNet-S fwd+bwd, 3s@16kHz)", "value": round(value, 3),
+        "unit": "utterances/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(dt * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, batch),
+        "cpu_baseline": {"value": round(value, 3), "unit": "utterances/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch):
+    return {"workload": f"TitaNet-{args.model.upper()}/{args.blocks} fwd+bwd, CE loss ({N_CLASSES} classes), "
+                        f"batch {batch}/GPU, {args.seconds:g}s@16kHz synthetic waveform, mel on device, dropout {args.dropout}",
+            "batch_per_gpu": batch, "seconds": args.seconds, "frames": 1 + int(args.seconds * SAMPLE_RATE) // 160,
+            "l2": "per-step working set (~2 GB of activations) >> 126 MB L2; no explicit flush"}
+
+
+# ----------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------
+def gemm_work(tag: str):
+    """(flops, bytes) of one conv-GEMM launch from its profile tag 'kind R.. Ci.. Co.. K..'."""
+    f = dict((t[0] if t[0] != "C" else t[:2], int(t[1:] if t[0] != "C" else t[2:])) for t in tag.split()[1:])
+    R, Ci, Co, K = f["R"], f["Ci"], f["Co"], f["K"]
+    return 2.0 * R * Ci * Co * K, 4.0 * (R * Ci + R * Co + Co * Ci * K)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from titanet_b200 import _lib, losses, models, transforms
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(42)
+    B, L = args.batch, int(args.seconds * SAMPLE_RATE)
+    model = models.TitaNet.get_titanet(192, 80, args.blocks, args.model, loss_function=losses.CELoss(192, N_CLASSES),
+                                       dropout=args.dropout, device=dev).train()
+    mel = transforms.MelSpectrogram(SAMPLE_RATE, n_fft=512, win_length=400, hop_length=160, n_mels=80, specaugment_probability=0.0)
+    params = [p for p in model.parameters()]
+    g = torch.Generator().manual_seed(42 + rank)
+    wave_h = (0.1 * torch.randn(B, L, generator=g)).pin_memory()
+    labels_h = torch.randint(0, N_CLASSES, (B,), generator=g).pin_memory()
+    wave_d, labels_d = wave_h.to(dev), labels_h.to(dev)
+
+    def allreduce_grads():
+        if world == 1:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        dist.all_reduce(flat)
+        flat.mul_(1.0 / world)
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p))
+            off += n
+
+    def step(wave, labels):
+        for p in params:
+            p.grad = None
+        emb, preds, loss = model(mel.batch(wave), speakers=labels)
+        loss.backward()
+        allreduce_grads()
+        return loss
+
+    def step_e2e():
+        w = wave_h.to(dev, non_blocking=True)
+        y = labels_h.to(dev, non_blocking=True)
+        return float(step(w, y))          # D2H read of the loss (synchronises)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for _ in range(max(3, args.warmup)):
+        step(wave_d, labels_d)
+    sampler = ClockSampler(local) if rank == 0 else None
+    _lib.COUNTS.clear()
+    ms_step = timed(lambda: step(wave_d, labels_d), args.steps)
+    launches = _lib.kernel_launches() // args.steps
+    clocks = sampler.stop() if sampler else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # per-kernel device time: a separate pass with CUDA events around every launch
+    roof = None
+    if rank == 0:
+        pk = peaks()
+        _lib.profile_start()
+        prof_steps = min(args.steps, 5)
+        for _ in range(prof_steps):
+            step(wave_d, labels_d)
+        prof = _lib.profile_stop()
+        total_ms = sum(ms for _, ms in prof.values())
+        groups = {}
+        for key, (n, ms) in prof.items():
+            name = key.split("[")[0]
+            gn, gms = groups.get(name, (0, 0.0))
+            groups[name] = (gn + n, gms + ms)
+        top = sorted(prof.items(), key=lambda kv: -kv[1][1])
+        top_gemm = next(((k, v) for k, v in top if k.startswith("tn_conv_gemm") or k.startswith("tn_gemm")), None)
+        if top_gemm is not None:
+            key, (n, ms) = top_gemm
+            flops, byts = gemm_work(key[key.index("[") + 1:-1])
+            per_launch_s = ms / n * 1e-3
+            tf32_peak = pk["bf16_tflops"] / 2.0
+            ach_tf = flops / per_launch_s / 1e12
+            ach_gb = byts / per_launch_s / 1e9
+            tensor_bound = (flops / byts) > (tf32_peak * 1e12 / 3.0) / (pk["hbm_gbs"] * 1e9)
+            roof = {"kernel": key, "launches_per_step": n // prof_steps, "us_per_launch": round(per_launch_s * 1e6, 2),
+                    "share_of_step": round(ms / total_ms, 4),
+                    "bound": "tensor" if tensor_bound else "hbm",
+                    "achieved": round(ach_tf if tensor_bound else ach_gb, 3),
+                    "peak": round(tf32_peak if tensor_bound else pk["hbm_gbs"], 1),
+                    "unit": "TFLOP/s" if tensor_bound else "GB/s",
+                    "frac": round((ach_tf / tf32_peak) if tensor_bound else (ach_gb / pk["hbm_gbs"]), 4),
+                    "traffic": None,
+                    "peak_source": pk["source"] + (" (dense TF32 = measured sustained bf16 / 2)" if tensor_bound else ""),
+                    "algorithmic_gb_s": round(ach_gb, 1), "algorithmic_tflop_s": round(ach_tf, 2),
+                    "by_kernel_ms_per_step": {k: round(v[1] / prof_steps, 3) for k, v in sorted(groups.items(), key=lambda kv: -kv[1][1])}}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * B / (ms_step * 1e-3)
+    e2e = world * B / (ms_e2e * 1e-3)
+    line = {
+        "metric": "utterances/sec (TitaNet-S fwd+bwd, 3s@16kHz)", "value": round(value, 1), "unit": "utterances/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, B),
+        "e2e": {"value": round(e2e, 1), "unit": "utterances/s", "h2d_bytes_per_step": B * L * 4 + B * 8, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e, 3)},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        v, dt = time_cpu(args, args.cpu_batch, 2, 1)
+        line["cpu_baseline"] = {"value": round(v, 3), "unit": "utterances/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": f"2 steps of {args.cpu_batch} utterances x {args.seconds:g} s (mel + fwd + bwd) after 1 warm-up, "
+                                          "oracle port of the reference modules on torch CPU ops, all host threads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

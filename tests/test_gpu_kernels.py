@@ -67,11 +67,12 @@ def test_conv_gemm_fwd_bwd(ops, B, T, Ci, Co, K):
     xg = nwc(x).float().to(dev()).requires_grad_(True)
     wg = w.float().to(dev()).requires_grad_(True)
     bg = b.float().to(dev()).requires_grad_(True)
-    z, stats = ops.conv_gemm(xg, wg, bg, B, T, want_stats=True)
+    z, stats = ops.conv_gemm(xg, wg, bg, B, T, want_stats=Co % 4 == 0)     # BatchNorm'd channel counts are multiples of 4
     assert rel(ncw(z, B, T), yr) < 1e-5
-    s1 = yr.sum(dim=(0, 2))
-    s2 = (yr ** 2).sum(dim=(0, 2))
-    assert rel(stats[:Co], s1, floor=1e-3) < 1e-5 and rel(stats[Co:], s2) < 1e-5
+    if stats is not None:
+        s1 = yr.sum(dim=(0, 2))
+        s2 = (yr ** 2).sum(dim=(0, 2))
+        assert rel(stats[:Co], s1, floor=1e-3) < 1e-5 and rel(stats[Co:], s2) < 1e-5
     z.backward(nwc(gy).float().to(dev()))
     assert rel(ncw(xg.grad, B, T), xr.grad) < 1e-5
     assert rel(wg.grad, wr.grad) < 1e-5
@@ -169,7 +170,7 @@ def test_bn_fold_act_chain(ops, training):
     assert rel(wg.grad, wr.grad) < 5e-5
     assert rel(bn.weight.grad, gr.grad) < 5e-5 and rel(bn.bias.grad, ber.grad) < 5e-5
     if training:
-        assert rel(bg.grad, br.grad, floor=1e-3) < 1e-4          # mathematically zero
+        assert float(bg.grad.abs().max()) < 1e-4 * float(wr.grad.abs().max())   # mathematically zero: rounding noise only
         assert rel(bn.running_mean, rm_r) < 1e-5 and rel(bn.running_var, rv_r) < 1e-5
         assert int(bn.num_batches_tracked) == 1
     else:

@@ -124,5 +124,40 @@ def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name: str, *args):
+# launch accounting (bench.py reads these): ABI calls and, optionally, per-call device time
+COUNTS: Dict[str, int] = {}
+KERNELS_PER_CALL = {"tn_zero": 0, "tn_ce_fwd_bwd": 2, "tn_margin_fwd_bwd": 2}
+_profile = None          # list of (key, start_event, stop_event) while profiling
+
+
+def profile_start():
+    global _profile
+    _profile = []
+
+
+def profile_stop() -> Dict[str, Tuple[int, float]]:
+    """key -> (launches, total milliseconds); synchronises the device."""
+    global _profile
+    rec, _profile = _profile or [], None
+    torch.cuda.synchronize()
+    out: Dict[str, Tuple[int, float]] = {}
+    for key, e0, e1 in rec:
+        n, ms = out.get(key, (0, 0.0))
+        out[key] = (n + 1, ms + e0.elapsed_time(e1))
+    return out
+
+
+def kernel_launches() -> int:
+    return sum(n * KERNELS_PER_CALL.get(k, 1) for k, n in COUNTS.items())
+
+
+def call(name: str, *args, tag: str = ""):
+    COUNTS[name] = COUNTS.get(name, 0) + 1
+    if _profile is None:
+        LIB.call(name, *args, stream())
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     LIB.call(name, *args, stream())
+    e1.record()
+    _profile.append((f"{name}[{tag}]" if tag else name, e0, e1))

@@ -94,14 +94,16 @@ def nwc_to_ncw(x: Tensor) -> Tensor:
 def _gemm_fwd(x, w3, bias, z, stats, B, T, transpose_w, flags):
     Co, Ci, K = w3.shape
     if transpose_w:
-        call("tn_conv_gemm_simt", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), B, T, Co, Ci, K, 1, flags)
+        call("tn_conv_gemm_simt", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), B, T, Co, Ci, K, 1, flags,
+             tag=f"dgrad R{B * T} Ci{Co} Co{Ci} K{K}")
     else:
-        call("tn_conv_gemm_simt", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), B, T, Ci, Co, K, 0, flags)
+        call("tn_conv_gemm_simt", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), B, T, Ci, Co, K, 0, flags,
+             tag=f"fwd R{B * T} Ci{Ci} Co{Co} K{K}")
 
 
 def _gemm_wgrad(dz, x, dw3, dbias, B, T):
     Co, Ci, K = dw3.shape
-    call("tn_conv_wgrad_simt", ptr(dz), ptr(x), ptr(dw3), ptr(dbias), B, T, Ci, Co, K)
+    call("tn_conv_wgrad_simt", ptr(dz), ptr(x), ptr(dw3), ptr(dbias), B, T, Ci, Co, K, tag=f"wgrad R{B * T} Ci{Ci} Co{Co} K{K}")
 
 
 class ConvGemm(Function):
