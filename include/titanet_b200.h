@@ -70,6 +70,15 @@ int tn_conv_gemm_simt(const float* X, const float* W, const float* bias, float* 
 int tn_conv_wgrad_simt(const float* dZ, const float* X, float* dW, float* dbias, int B, int T, int Ci, int Co, int K,
                        void* stream);
 
+/* Tensor-core path for the 1x1 convs / linears (tcgen05 + TMEM + TMA, 3xTF32 = fp32-equivalent):
+ * Z[R,M] = bias + X[R,Kd] W[M,Kd]^T.  ws = split weights [2, M, Kd] from tn_split_tf32
+ * (transpose = 1 reads W as [Kd, M]: the data-gradient GEMM).  nsplit: 3 (hi*hi+lo*hi+hi*lo)
+ * or 1 (plain TF32).  Needs Kd %% 32 == 0 and M %% 128 == 0 (tn_gemm_tc_supported). */
+int tn_gemm_tc_supported(int R, int Kd, int M);
+int tn_split_tf32(const float* W, float* ws, int M, int Kd, int transpose, void* stream);
+int tn_gemm_tc(const float* X, const float* ws, const float* bias, float* Z, double* stats, int R, int Kd, int M, int flags,
+               int nsplit, void* stream);
+
 /* ---- depthwise conv with fused lazy-activation prologue:
  *      DepthwiseConv1d's first conv (src/modules.py:64-75) after BN/ReLU/Dropout
  *      (src/modules.py:128-133) ---------------------------------------------------- */

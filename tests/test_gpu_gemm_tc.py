@@ -1,0 +1,83 @@
+"""tcgen05 (tensor-core) GEMM against an fp64 CPU product, through the C ABI."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def run_tc(x, w, bias, nsplit, transpose=False, want_stats=True, flags=0, z0=None):
+    from titanet_b200._lib import call, ptr
+    R, Kd = x.shape
+    M = w.shape[1] if transpose else w.shape[0]
+    ws = torch.empty(2, M, Kd, device="cuda")
+    call("tn_split_tf32", ptr(w), ptr(ws), M, Kd, int(transpose))
+    z = torch.empty(R, M, device="cuda") if z0 is None else z0
+    stats = torch.zeros(2 * M, device="cuda", dtype=torch.float64) if want_stats else None
+    call("tn_gemm_tc", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), R, Kd, M, flags, nsplit)
+    torch.cuda.synchronize()
+    return z, stats, ws
+
+
+@pytest.mark.parametrize("R,Kd,M", [(19264, 256, 256), (301, 256, 256), (1000, 128, 1536), (777, 1536, 128), (4096, 512, 512),
+                                     (2000, 256, 1536), (515, 64, 384)])
+def test_gemm_tc_3xtf32_matches_fp64(R, Kd, M):
+    g = torch.Generator().manual_seed(R + Kd + M)
+    x = torch.randn(R, Kd, generator=g)
+    w = torch.randn(M, Kd, generator=g) / math.sqrt(Kd)
+    b = torch.randn(M, generator=g)
+    ref = x.double() @ w.double().t() + b.double()
+    z, stats, ws = run_tc(x.cuda(), w.cuda(), b.cuda(), 3)
+    # split is exact to ~2^-22: hi + lo reproduces w
+    assert rel(ws[0] + ws[1], w) < 1e-6
+    assert rel(z, ref) < 1e-5, "3xTF32 must be fp32-equivalent (tensor-core accumulation leaves ~2^-19)"
+    assert rel(stats[:M], ref.sum(0)) < 1e-4 * max(1.0, float(ref.abs().sum(0).max() / ref.sum(0).abs().max()))
+    assert rel(stats[M:], (ref ** 2).sum(0)) < 1e-5
+
+
+def test_gemm_tc_plain_tf32_and_transpose_and_flags():
+    R, Kd, M = 3000, 256, 256
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(R, Kd, generator=g)
+    w = torch.randn(Kd, M, generator=g) / math.sqrt(Kd)          # stored [Kd, M]: the dgrad layout
+    ref = x.double() @ w.double()
+    z1, _, _ = run_tc(x.cuda(), w.cuda(), None, 1, transpose=True, want_stats=False)
+    assert 1e-5 < rel(z1, ref) < 3e-3, "plain TF32: ~1e-3 accurate"
+    z3, _, _ = run_tc(x.cuda(), w.cuda(), None, 3, transpose=True, want_stats=False)
+    assert rel(z3, ref) < 1e-5
+    # accumulate + tanh epilogues
+    z0 = torch.randn(R, M, generator=g)
+    za, _, _ = run_tc(x.cuda(), w.cuda(), None, 3, transpose=True, want_stats=False, flags=2, z0=z0.cuda().clone())
+    assert rel(za, ref + z0.double()) < 1e-5
+    zt, _, _ = run_tc(x.cuda(), w.cuda(), None, 3, transpose=True, want_stats=False, flags=1)
+    assert rel(zt, torch.tanh(ref)) < 1e-5
+
+
+def test_conv_gemm_op_uses_tensor_cores_and_matches_simt():
+    from titanet_b200 import _ops as ops
+    from titanet_b200 import _lib
+    B, T, Ci, Co = 8, 301, 256, 256
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(B * T, Ci, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(Co, Ci, 1, generator=g) / 16).cuda().requires_grad_(True)
+    b = torch.randn(Co, generator=g).cuda().requires_grad_(True)
+    gy = torch.randn(B * T, Co, generator=g).cuda()
+    outs = []
+    for enabled in (True, False):
+        ops.TC_ENABLED = enabled
+        _lib.COUNTS.clear()
+        for t in (x, w, b):
+            t.grad = None
+        z, st = ops.conv_gemm(x, w, b, B, T, want_stats=True)
+        z.backward(gy)
+        assert (_lib.COUNTS.get("tn_gemm_tc", 0) > 0) == enabled
+        outs.append((z.detach().clone(), st.clone(), x.grad.clone(), w.grad.clone(), b.grad.clone()))
+    ops.TC_ENABLED = True
+    for a, c in zip(*outs):
+        assert rel(a, c) < 1e-5

@@ -91,8 +91,33 @@ def nwc_to_ncw(x: Tensor) -> Tensor:
 # ----------------------------------------------------------------------------
 # conv / linear as GEMM  (+ BatchNorm statistics in the epilogue)
 # ----------------------------------------------------------------------------
+# Tensor-core (tcgen05) path for the 1x1 convs / linears.  TC_FWD_NSPLIT / TC_BWD_NSPLIT:
+# 3 = fp32-equivalent 3xTF32, 1 = plain TF32.  TC_ENABLED exists for A/B tests against the
+# exact-fp32 CUDA-core kernel, not as a runtime fallback (unsupported shapes always take the
+# CUDA-core kernel: K-tap convs, channel counts that are not multiples of 128 / 32).
+TC_ENABLED = True
+TC_FWD_NSPLIT = 3
+TC_BWD_NSPLIT = 3
+TC_MIN_ROWS = 256
+
+
+def _tc_ok(R: int, Kd: int, M: int, K: int) -> bool:
+    return TC_ENABLED and K == 1 and R >= TC_MIN_ROWS and Kd % 32 == 0 and M % 128 == 0
+
+
+def _gemm_tc(x, w2, bias, z, stats, R, Kd, M, transpose, flags, nsplit, tag):
+    ws = torch.empty((2, M, Kd), device=x.device, dtype=torch.float32)
+    call("tn_split_tf32", ptr(w2), ptr(ws), M, Kd, int(transpose))
+    call("tn_gemm_tc", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), R, Kd, M, flags, nsplit, tag=tag)
+
+
 def _gemm_fwd(x, w3, bias, z, stats, B, T, transpose_w, flags):
     Co, Ci, K = w3.shape
+    R = B * T
+    if transpose_w and _tc_ok(R, Co, Ci, K):
+        return _gemm_tc(x, w3, bias, z, stats, R, Co, Ci, 1, flags, TC_BWD_NSPLIT, f"dgrad R{R} Ci{Co} Co{Ci} K1")
+    if not transpose_w and _tc_ok(R, Ci, Co, K):
+        return _gemm_tc(x, w3, bias, z, stats, R, Ci, Co, 0, flags, TC_FWD_NSPLIT, f"fwd R{R} Ci{Ci} Co{Co} K1")
     if transpose_w:
         call("tn_conv_gemm_simt", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), B, T, Co, Ci, K, 1, flags,
              tag=f"dgrad R{B * T} Ci{Co} Co{Ci} K{K}")

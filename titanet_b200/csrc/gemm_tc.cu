@@ -1,0 +1,379 @@
+// 1x1-convolution / linear layers on the 5th-generation tensor cores (tcgen05 + TMEM),
+// operands staged by TMA, fp32-equivalent "3xTF32" arithmetic.
+//
+//   Z[r, co] = bias[co] + sum_ci X[r, ci] * W[co, ci]          X: [R, Kd]  W: [M, Kd]  Z: [R, M]
+//
+// Orientation: the output channels are the MMA's M (TMEM lanes), the activation rows are
+// its N (TMEM columns), both operands K-major in shared memory:
+//     D[co, r] (TMEM) += A[co, k] (= W, smem) * B[r, k] (= X, smem)
+// so in the epilogue one thread owns one output channel: the bias is a scalar, the
+// BatchNorm statistics (sum z, sum z^2 per channel) are thread-local sums, and for a
+// fixed row the 32 lanes of a warp write 32 consecutive floats (one 128 B line).
+//
+// Precision: fp32 operands are split hi = rna_tf32(x), lo = rna_tf32(x - hi); three MMAs
+// hi*hi + lo*hi + hi*lo accumulate into the same fp32 TMEM tile (error ~2^-21 per
+// product, like an fp32 FMA chain; SURVEY.md §7 hard part 1 shows plain TF32 breaks the
+// 1e-3 parity contract through train-mode BatchNorm).  The weight split is precomputed
+// (tn_split_tf32, tiny); the activation tile is split in shared memory by the four
+// transform warps between the TMA arrival and the MMA issue.  nsplit = 1 skips the
+// split (the tensor core truncates fp32 to tf32) for the backward GEMMs.
+//
+// Warp roles (192 threads, 1 CTA / SM): warp 0 TMA producer, warp 1 TMEM allocator +
+// MMA issuer, warps 2-5 operand transform then epilogue (TMEM -> registers -> global).
+// Reference ops replaced: the pointwise Conv1dSamePadding(C, C', 1) of DepthwiseConv1d
+// (src/modules.py:76-78), the skip nn.Conv1d (src/models.py:452-455), the epilog conv
+// (src/models.py:384) and the ASP linears (src/models.py:549-551).
+#include "common.cuh"
+#include <cuda.h>
+
+#define TC_THREADS 192
+#define TC_BK 32              // fp32 elements per K chunk = one 128-byte swizzle row
+#define TC_MAX_STAGES 4
+#define TC_SMEM_LIMIT (227 * 1024)
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if (spins == 1024) t0 = clock64();
+    if (spins > 1024 && (spins & 1023) == 0 && clock64() - t0 > 4000000000ll) {   // ~2 s: a protocol bug, not a slow GPU
+      printf("gemm_tc: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct TcParams {
+  const float* bias;
+  float* Z;
+  double* stats;
+  int R, Kd, M_total, BN, stages, nsplit, flags, tmem_cols;
+};
+
+// ---------------------------------------------------------------------------
+// kernel: MT = number of 128-row output-channel tiles per CTA (1 or 2)
+// ---------------------------------------------------------------------------
+template <int MT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 1];
+  __shared__ uint32_t tmem_base_slot;
+
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = p.BN, S = p.stages;
+  const int n0 = blockIdx.x * BN;                    // first activation row of this CTA
+  const int m0 = blockIdx.y * (128 * MT);            // first output channel of this CTA
+  const int num_kc = p.Kd / TC_BK;
+  const bool split = p.nsplit == 3;
+
+  const uint32_t a_tile = 128 * TC_BK * 4;           // 16 KiB per 128-channel weight tile
+  const uint32_t b_tile = (uint32_t)BN * TC_BK * 4;
+  const uint32_t stage_bytes = (split ? 2 : 1) * (MT * a_tile + b_tile);
+  const uint32_t tx_bytes = (split ? 2 : 1) * MT * a_tile + b_tile;      // B_lo is written by the transform warps, not TMA
+  // stage layout: A_hi[MT] | B_hi | (A_lo[MT] | B_lo)
+  auto a_hi = [&](int s, int mt) { return smem + (size_t)s * stage_bytes + mt * a_tile; };
+  auto b_hi = [&](int s) { return smem + (size_t)s * stage_bytes + MT * a_tile; };
+  auto a_lo = [&](int s, int mt) { return smem + (size_t)s * stage_bytes + MT * a_tile + b_tile + mt * a_tile; };
+  auto b_lo = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * MT * a_tile + b_tile; };
+  const uint32_t full0 = smem_u32(&bars[0]), ready0 = smem_u32(&bars[TC_MAX_STAGES]), empty0 = smem_u32(&bars[2 * TC_MAX_STAGES]);
+  const uint32_t accum_bar = smem_u32(&bars[3 * TC_MAX_STAGES]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(ready0 + 8 * s, 128);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kc = 0; kc < num_kc; ++kc) {
+        const int s = kc % S;
+        if (kc >= S) mbar_wait(empty0 + 8 * s, ((kc / S) - 1) & 1);
+        const uint32_t fb = full0 + 8 * s;
+        mbar_expect_tx(fb, tx_bytes);
+        const int k0 = kc * TC_BK;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          tma_load_2d(smem_u32(a_hi(s, mt)), &tmA_hi, fb, k0, m0 + mt * 128);
+          if (split) tma_load_2d(smem_u32(a_lo(s, mt)), &tmA_lo, fb, k0, m0 + mt * 128);
+        }
+        tma_load_2d(smem_u32(b_hi(s)), &tmB, fb, k0, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+      for (int kc = 0; kc < num_kc; ++kc) {
+        const int s = kc % S;
+        const uint32_t ph = (kc / S) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        if (split) mbar_wait(ready0 + 8 * s, ph);
+        tc_fence_after();
+        const uint64_t dbh = umma_desc_k128(smem_u32(b_hi(s)));
+        const uint64_t dbl = split ? umma_desc_k128(smem_u32(b_lo(s))) : 0;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint64_t dah = umma_desc_k128(smem_u32(a_hi(s, mt)));
+          const uint64_t dal = split ? umma_desc_k128(smem_u32(a_lo(s, mt))) : 0;
+          const uint32_t d = tmem_base + (uint32_t)(mt * 256);
+#pragma unroll
+          for (int kk = 0; kk < TC_BK / 8; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 2);       // 8 tf32 = 32 bytes = 2 x 16-byte units
+            const uint32_t acc = (kc > 0 || kk > 0) ? 1u : 0u;
+            if (split) {
+              tc_mma_tf32(d, dal + adv, dbh + adv, idesc, acc);
+              tc_mma_tf32(d, dah + adv, dbl + adv, idesc, 1u);
+              tc_mma_tf32(d, dah + adv, dbh + adv, idesc, 1u);
+            } else {
+              tc_mma_tf32(d, dah + adv, dbh + adv, idesc, acc);
+            }
+          }
+        }
+        tc_commit(empty0 + 8 * s);           // stage free once these MMAs have read it
+      }
+      tc_commit(accum_bar);                  // accumulators complete
+    }
+  } else {
+    // ===== transform warps (split only), then epilogue =====
+    const int tid = threadIdx.x - 64;        // 0..127
+    if (split) {
+      const int n4 = BN * TC_BK / 4;
+      for (int kc = 0; kc < num_kc; ++kc) {
+        const int s = kc % S;
+        mbar_wait(full0 + 8 * s, (kc / S) & 1);
+        float4* hi = reinterpret_cast<float4*>(b_hi(s));
+        float4* lo = reinterpret_cast<float4*>(b_lo(s));
+        for (int i = tid; i < n4; i += 128) {
+          const float4 v = hi[i];
+          uint4 h, l;
+          h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+          l.x = rna_tf32(v.x - __uint_as_float(h.x)); l.y = rna_tf32(v.y - __uint_as_float(h.y));
+          l.z = rna_tf32(v.z - __uint_as_float(h.z)); l.w = rna_tf32(v.w - __uint_as_float(h.w));
+          reinterpret_cast<uint4*>(hi)[i] = h;
+          reinterpret_cast<uint4*>(lo)[i] = l;
+        }
+        fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(ready0 + 8 * s);
+      }
+    }
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int quad = warp & 3;               // TMEM lanes 32*quad .. 32*quad+31 belong to this warp
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int co = m0 + mt * 128 + quad * 32 + lane;
+      const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
+      float s1 = 0.f, s2 = 0.f;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 256 + c0), v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int r = n0 + c0 + j;
+          if (r < p.R) {
+            float x = v[j] + bv;
+            if (p.flags & TN_EPI_TANH) x = tanhf(x);
+            float* zp = p.Z + (size_t)r * p.M_total + co;
+            if (p.flags & TN_EPI_ACCUM) x += *zp;
+            *zp = x;
+            s1 += x;
+            s2 = fmaf(x, x, s2);
+          }
+        }
+      }
+      if (p.stats) {
+        atomicAdd(p.stats + co, (double)s1);
+        atomicAdd(p.stats + p.M_total + co, (double)s2);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// weight split: ws[0] = rna_tf32(W), ws[1] = rna_tf32(W - ws[0]); optional transpose
+// ---------------------------------------------------------------------------
+__global__ void split_tf32_kernel(const float* __restrict__ W, float* __restrict__ hi, float* __restrict__ lo, int M, int Kd, int transpose) {
+  // output [M, Kd]; input [M, Kd] or (transpose) [Kd, M]
+  const size_t n = (size_t)M * Kd;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / Kd), k = (int)(i - (size_t)m * Kd);
+    const float x = transpose ? W[(size_t)k * M + m] : W[i];
+    const float h = __uint_as_float(rna_tf32(x));
+    hi[i] = h;
+    lo[i] = __uint_as_float(rna_tf32(x - h));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+static int get_encoder() {
+  if (g_encode) return TN_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  TN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  TN_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+  g_encode = (PFN_encodeTiled)fn;
+  return TN_OK;
+}
+
+// 2-D fp32 row-major [rows, cols] tensor, box = [box_rows, 32 cols], 128-byte swizzle
+static int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for [%lld, %lld] box %d", (int)r, rows, cols, box_rows);
+  return TN_OK;
+}
+
+extern "C" int tn_gemm_tc_supported(int R, int Kd, int M) {
+  return (R > 0 && Kd >= TC_BK && Kd % TC_BK == 0 && M >= 128 && M % 128 == 0) ? 1 : 0;
+}
+
+extern "C" int tn_split_tf32(const float* W, float* ws, int M, int Kd, int transpose, void* stream) {
+  TN_REQUIRE(W && ws && M > 0 && Kd > 0, "split_tf32: bad arguments");
+  size_t n = (size_t)M * Kd;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > tn_num_sms() * 8) blocks = tn_num_sms() * 8;
+  split_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, ws, ws + n, M, Kd, transpose);
+  TN_LAUNCH_CHECK("split_tf32_kernel");
+  return TN_OK;
+}
+
+static int pick_bn(long long R, int groups, int per_row_stage_bytes, int fixed_stage_bytes, int* stages_out) {
+  const int sms = tn_num_sms();
+  int best = 0;
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= 32; bn -= 16) {
+    long long stage = (long long)fixed_stage_bytes + (long long)bn * per_row_stage_bytes;
+    int stages = (int)((TC_SMEM_LIMIT - 2048) / stage);
+    if (stages < 2) continue;
+    long long ctas = ((R + bn - 1) / bn) * groups;
+    long long waves = (ctas + sms - 1) / sms;
+    double cost = (double)waves * (bn + 24);
+    if (cost < best_cost) { best_cost = cost; best = bn; *stages_out = stages > TC_MAX_STAGES ? TC_MAX_STAGES : stages; }
+  }
+  return best;
+}
+
+// ws: the split weights from tn_split_tf32 (hi | lo), [2, M, Kd].  nsplit 3 = fp32-equivalent, 1 = plain TF32.
+extern "C" int tn_gemm_tc(const float* X, const float* ws, const float* bias, float* Z, double* stats, int R, int Kd, int M,
+                          int flags, int nsplit, void* stream) {
+  TN_REQUIRE(X && ws && Z, "gemm_tc: null tensor");
+  TN_REQUIRE(tn_gemm_tc_supported(R, Kd, M), "gemm_tc: unsupported shape R=%d K=%d M=%d (need K %% 32 == 0, M %% 128 == 0)", R, Kd, M);
+  TN_REQUIRE(nsplit == 1 || nsplit == 3, "gemm_tc: nsplit must be 1 or 3");
+  TN_REQUIRE(tn_aligned16(X) && tn_aligned16(ws), "gemm_tc: operands must be 16B aligned");
+  int rc = get_encoder();
+  if (rc != TN_OK) return rc;
+  const int MT = (M % 256 == 0) ? 2 : 1;
+  const int groups = M / (128 * MT);
+  const int mult = nsplit == 3 ? 2 : 1;
+  int stages = 2;
+  const int bn = pick_bn(R, groups, mult * TC_BK * 4, mult * MT * 128 * TC_BK * 4, &stages);
+  TN_REQUIRE(bn >= 32, "gemm_tc: no tile configuration fits shared memory");
+  CUtensorMap mA_hi, mA_lo, mB;
+  if ((rc = make_map(&mA_hi, ws, M, Kd, 128)) != TN_OK) return rc;
+  if ((rc = make_map(&mA_lo, ws + (size_t)M * Kd, M, Kd, 128)) != TN_OK) return rc;
+  if ((rc = make_map(&mB, X, R, Kd, bn)) != TN_OK) return rc;
+  TcParams p;
+  p.bias = bias; p.Z = Z; p.stats = stats; p.R = R; p.Kd = Kd; p.M_total = M; p.BN = bn; p.stages = stages; p.nsplit = nsplit;
+  p.flags = flags;
+  int cols = MT == 2 ? 512 : 32;
+  while (MT == 1 && cols < bn) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t stage_bytes = (size_t)mult * (MT * 128 * TC_BK * 4 + (size_t)bn * TC_BK * 4);
+  const size_t smem = stage_bytes * stages + 1024;
+  dim3 grid(tn_cdiv(R, bn), groups);
+  if (MT == 2) {
+    TN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_tc_kernel<2><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB, p);
+  } else {
+    TN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_tc_kernel<1><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB, p);
+  }
+  TN_LAUNCH_CHECK("gemm_tc_kernel");
+  return TN_OK;
+}
