@@ -78,6 +78,10 @@ int tn_gemm_tc_supported(int R, int Kd, int M);
 int tn_split_tf32(const float* W, float* ws, int M, int Kd, int transpose, void* stream);
 int tn_gemm_tc(const float* X, const float* ws, const float* bias, float* Z, double* stats, int R, int Kd, int M, int flags,
                int nsplit, void* stream);
+/* dW[Co,Ci] += dZ[R,Co]^T U[R,Ci] on the tensor cores (split-K over rows, MN-major operands; ACCUMULATED) */
+int tn_wgrad_tc_supported(int R, int Ci, int Co);
+int tn_wgrad_tc(const float* dZ, const float* U, float* dW, int R, int Ci, int Co, void* stream);
+int tn_colsum(const float* x, float* out, int R, int C, void* stream);                /* out[c] += sum_r x[r,c] */
 
 /* ---- depthwise conv with fused lazy-activation prologue:
  *      DepthwiseConv1d's first conv (src/modules.py:64-75) after BN/ReLU/Dropout

@@ -79,5 +79,26 @@ def test_conv_gemm_op_uses_tensor_cores_and_matches_simt():
         assert (_lib.COUNTS.get("tn_gemm_tc", 0) > 0) == enabled
         outs.append((z.detach().clone(), st.clone(), x.grad.clone(), w.grad.clone(), b.grad.clone()))
     ops.TC_ENABLED = True
-    for a, c in zip(*outs):
-        assert rel(a, c) < 1e-5
+    names = ("z", "stats", "dx", "dw", "db")
+    for n, a, c in zip(names, *outs):
+        # forward / dgrad run fp32-equivalent 3xTF32; the weight gradient uses plain TF32 operands
+        assert rel(a, c) < (2e-3 if n == "dw" else 1e-5), n
+
+
+@pytest.mark.parametrize("R,Ci,Co", [(19264, 256, 256), (1000, 256, 256), (2000, 256, 1536), (3000, 1536, 128), (777, 128, 1536),
+                                      (5000, 512, 512), (64, 64, 128)])
+def test_wgrad_tc_matches_fp64(R, Ci, Co):
+    from titanet_b200._lib import call, ptr
+    g = torch.Generator().manual_seed(R + Ci + Co)
+    dz = torch.randn(R, Co, generator=g)
+    u = torch.randn(R, Ci, generator=g)
+    ref = dz.double().t() @ u.double()
+    dw = torch.zeros(Co, Ci, device="cuda")
+    dz_d, u_d = dz.cuda(), u.cuda()
+    call("tn_wgrad_tc", ptr(dz_d), ptr(u_d), ptr(dw), R, Ci, Co)
+    call("tn_wgrad_tc", ptr(dz_d), ptr(u_d), ptr(dw), R, Ci, Co)        # accumulates
+    torch.cuda.synchronize()
+    assert rel(dw, 2 * ref) < 2e-3, "plain-TF32 operands: ~1e-3"
+    db = torch.zeros(Co, device="cuda")
+    call("tn_colsum", ptr(dz_d), ptr(db), R, Co)
+    assert rel(db, dz.double().sum(0)) < 1e-5

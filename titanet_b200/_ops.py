@@ -98,6 +98,7 @@ def nwc_to_ncw(x: Tensor) -> Tensor:
 TC_ENABLED = True
 TC_FWD_NSPLIT = 3
 TC_BWD_NSPLIT = 3
+TC_WGRAD = True
 TC_MIN_ROWS = 256
 
 
@@ -128,6 +129,12 @@ def _gemm_fwd(x, w3, bias, z, stats, B, T, transpose_w, flags):
 
 def _gemm_wgrad(dz, x, dw3, dbias, B, T):
     Co, Ci, K = dw3.shape
+    R = B * T
+    if TC_ENABLED and TC_WGRAD and K == 1 and R >= TC_MIN_ROWS and Ci % 32 == 0 and Co % 128 == 0:
+        call("tn_wgrad_tc", ptr(dz), ptr(x), ptr(dw3), R, Ci, Co, tag=f"wgrad R{R} Ci{Ci} Co{Co} K1")
+        if dbias is not None:
+            call("tn_colsum", ptr(dz), ptr(dbias), R, Co)
+        return
     call("tn_conv_wgrad_simt", ptr(dz), ptr(x), ptr(dw3), ptr(dbias), B, T, Ci, Co, K, tag=f"wgrad R{B * T} Ci{Ci} Co{Co} K{K}")
 
 

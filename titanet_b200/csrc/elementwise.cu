@@ -186,6 +186,27 @@ extern "C" int tn_colstats(const float* x, double* stats, int R, int C, void* st
   return TN_OK;
 }
 
+// per-channel column sums in fp32 (bias gradients): out[c] += sum_r x[r, c]
+__global__ void __launch_bounds__(TN_EW_THREADS) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int R, int C, int rpb) {
+  __shared__ float4 red[TN_EW_THREADS];
+  TnTile tl = tn_tile(C);
+  int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    int q = qb + tl.q0;
+    float4 s1 = tn_zero4();
+    if (tl.active && q < tl.Q)
+      for (int r = r0 + tl.lane; r < r1; r += tl.lanes) s1 = s1 + tn_ld4(x + (size_t)r * C + 4 * q);
+    tn_lane_reduce_atomic(tl, s1, q, out, red);
+  }
+}
+extern "C" int tn_colsum(const float* x, float* out, int R, int C, void* stream) {
+  TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0 && tn_aligned16(x) && out, "colsum: need C %% 4 == 0 and aligned x (R=%d C=%d)", R, C);
+  int rpb = rows_per_block(R);
+  colsum_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(x, out, R, C, rpb);
+  TN_LAUNCH_CHECK("colsum_kernel");
+  return TN_OK;
+}
+
 // ---------------------------------------------------------------------------
 // BatchNorm folding: statistics -> (scale, shift) [+ running-stat update]
 // ---------------------------------------------------------------------------

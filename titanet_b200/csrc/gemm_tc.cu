@@ -159,10 +159,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int s = kc % S;
         if (kc >= S) mbar_wait(empty0 + 8 * s, ((kc / S) - 1) & 1);
         const uint32_t fb = full0 + 8 * s;
-        mbar_expect_tx(fb, tx_bytes);
+        const bool skip_a = (p.flags & 1024) != 0;      // debug knob: measure the B feed alone
+        mbar_expect_tx(fb, skip_a ? b_tile : tx_bytes);
         const int k0 = kc * TC_BK;
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
+        for (int mt = 0; mt < MT && !skip_a; ++mt) {
           tma_load_2d(smem_u32(a_hi(s, mt)), &tmA_hi, fb, k0, m0 + mt * 128);
           if (split) tma_load_2d(smem_u32(a_lo(s, mt)), &tmA_lo, fb, k0, m0 + mt * 128);
         }
@@ -186,6 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint64_t dah = umma_desc_k128(smem_u32(a_hi(s, mt)));
           const uint64_t dal = split ? umma_desc_k128(smem_u32(a_lo(s, mt))) : 0;
           const uint32_t d = tmem_base + (uint32_t)(mt * 256);
+          if (p.flags & 256) continue;                     // debug knob: no MMA issue
 #pragma unroll
           for (int kk = 0; kk < TC_BK / 8; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 2);       // 8 tf32 = 32 bytes = 2 x 16-byte units
@@ -240,7 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int r = n0 + c0 + j;
-          if (r < p.R) {
+          if (r < p.R && !(p.flags & 512)) {               // (512: debug knob, no stores)
             float x = v[j] + bv;
             if (p.flags & TN_EPI_TANH) x = tanhf(x);
             float* zp = p.Z + (size_t)r * p.M_total + co;
@@ -306,6 +308,186 @@ static int make_map(CUtensorMap* map, const float* base, long long rows, long lo
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for [%lld, %lld] box %d", (int)r, rows, cols, box_rows);
+  return TN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// weight gradient on the tensor cores:  dW[co, ci] += sum_r dZ[r, co] * U[r, ci]
+// The reduction runs over the rows, so both operands are "MN-major" in shared memory
+// (the contiguous global dimension is M resp. N): a 3-D TMA box {32 channels, WG_BK rows,
+// channel blocks} lands as [channel block][row][32 floats] = 4 KiB slabs of 128-byte
+// swizzled rows, which is the canonical MN-major SWIZZLE_128B layout (LBO = slab stride,
+// one 8-row group per UMMA_K = 8).  Split-K over row ranges: each CTA reduces its rows into
+// a [128*MT, NB] fp32 TMEM tile and adds it to dW with vectorised red.global.add.v4.f32.
+// ---------------------------------------------------------------------------
+#define WG_BK 32                         // rows per chunk
+
+// MN-major tf32 operands only exist in the SWIZZLE_128B_BASE32B shared-memory layout (32-byte
+// swizzle chunks, 4-row period: byte-address bits [5,7) ^= bits [7,9)); the matching TMA mode is
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  LBO = stride between 32-channel blocks, SBO = stride
+// between 4-row groups along K (512 B for densely packed 128-byte rows).
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+struct WgParams {
+  float* dW;
+  int R, Co, Ci, NB, stages, rows_per_split, tmem_cols;
+};
+
+template <int MT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 1];
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages, NB = p.NB;
+  const int co0 = blockIdx.x * (128 * MT);
+  const int ci0 = blockIdx.y * NB;
+  const int ra = blockIdx.z * p.rows_per_split;
+  const int rb = min(p.R, ra + p.rows_per_split);
+  const int num_kc = (rb - ra + WG_BK - 1) / WG_BK;
+  const uint32_t slab = WG_BK * 128;                               // one 32-channel block: WG_BK rows x 128 B
+  const uint32_t a_bytes = MT * 4 * slab, b_bytes = (uint32_t)(NB / 32) * slab;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_STAGES]), accum_bar = smem_u32(&bars[2 * TC_MAX_STAGES]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (num_kc > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int kc = 0; kc < num_kc; ++kc) {
+          const int s = kc % S;
+          if (kc >= S) mbar_wait(empty0 + 8 * s, ((kc / S) - 1) & 1);
+          const uint32_t fb = full0 + 8 * s;
+          mbar_expect_tx(fb, stage_bytes);
+          const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+          tma_load_3d(base, &tmA, fb, 0, ra + kc * WG_BK, co0 / 32);
+          tma_load_3d(base + a_bytes, &tmB, fb, 0, ra + kc * WG_BK, ci0 / 32);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // tf32, fp32 accumulate, A and B MN-major (bits 15, 16), M = 128, N = NB
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
+        for (int kc = 0; kc < num_kc; ++kc) {
+          const int s = kc % S;
+          mbar_wait(full0 + 8 * s, (kc / S) & 1);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+            for (int k8 = 0; k8 < WG_BK / 8; ++k8) {
+              const uint64_t da = umma_desc_mn128(base + mt * 4 * slab + k8 * 1024, slab);
+              const uint64_t db = umma_desc_mn128(base + a_bytes + k8 * 1024, slab);
+              tc_mma_tf32(tmem_base + (uint32_t)(mt * 256), da, db, idesc, (kc > 0 || k8 > 0) ? 1u : 0u);
+            }
+          }
+          tc_commit(empty0 + 8 * s);
+        }
+        tc_commit(accum_bar);
+      }
+    } else {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+      const int quad = warp & 3;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int co = co0 + mt * 128 + quad * 32 + lane;
+        float* row = p.dW + (size_t)co * p.Ci + ci0;
+        for (int c0 = 0; c0 < NB; c0 += 16) {
+          float v[16];
+          tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 256 + c0), v);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(row + c0 + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// 3-D view of a row-major fp32 [rows, cols] tensor as {32, rows, cols/32}; box {32, WG_BK, nblk}
+static int make_map_mn(CUtensorMap* map, const float* base, long long rows, long long cols, int nblk) {
+  cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * sizeof(float), 32 * sizeof(float)};
+  cuuint32_t box[3] = {32, WG_BK, (cuuint32_t)nblk};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed (%d) for [%lld, %lld] nblk %d", (int)r, rows, cols, nblk);
+  return TN_OK;
+}
+
+extern "C" int tn_wgrad_tc_supported(int R, int Ci, int Co) {
+  return (R >= 32 && Ci >= 32 && Ci % 32 == 0 && Co >= 128 && Co % 128 == 0) ? 1 : 0;
+}
+
+// dW[Co, Ci] += dZ[R, Co]^T U[R, Ci]   (plain TF32 operands, fp32 accumulation; ACCUMULATED)
+extern "C" int tn_wgrad_tc(const float* dZ, const float* U, float* dW, int R, int Ci, int Co, void* stream) {
+  TN_REQUIRE(dZ && U && dW, "wgrad_tc: null tensor");
+  TN_REQUIRE(tn_wgrad_tc_supported(R, Ci, Co), "wgrad_tc: unsupported shape R=%d Ci=%d Co=%d", R, Ci, Co);
+  TN_REQUIRE(tn_aligned16(dZ) && tn_aligned16(U) && tn_aligned16(dW), "wgrad_tc: operands must be 16B aligned");
+  int rc = get_encoder();
+  if (rc != TN_OK) return rc;
+  const int MT = (Co % 256 == 0) ? 2 : 1;
+  int NB = 256;
+  while (Ci % NB != 0) NB -= 32;                     // largest multiple of 32 <= 256 that divides Ci
+  TN_REQUIRE(NB % 16 == 0 && NB >= 32, "wgrad_tc: no N tile for Ci=%d", Ci);
+  const int co_groups = Co / (128 * MT), ci_blocks = Ci / NB;
+  const size_t stage_bytes = (size_t)WG_BK * 128 * (MT * 4 + NB / 32);
+  int stages = (int)((TC_SMEM_LIMIT - 2048) / stage_bytes);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  TN_REQUIRE(stages >= 2, "wgrad_tc: tile does not fit shared memory");
+  long long chunks = ((long long)R + WG_BK - 1) / WG_BK;
+  long long want = tn_num_sms() / (co_groups * ci_blocks);
+  if (want < 1) want = 1;
+  if (want > chunks) want = chunks;
+  long long cps = (chunks + want - 1) / want;        // chunks per split
+  int splits = (int)((chunks + cps - 1) / cps);
+  CUtensorMap mA, mB;
+  if ((rc = make_map_mn(&mA, dZ, R, Co, MT * 4)) != TN_OK) return rc;
+  if ((rc = make_map_mn(&mB, U, R, Ci, NB / 32)) != TN_OK) return rc;
+  WgParams p;
+  p.dW = dW; p.R = R; p.Co = Co; p.Ci = Ci; p.NB = NB; p.stages = stages; p.rows_per_split = (int)cps * WG_BK;
+  int cols = MT == 2 ? 512 : 32;
+  while (MT == 1 && cols < NB) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t smem = stage_bytes * stages + 1024;
+  dim3 grid(co_groups, ci_blocks, splits);
+  if (MT == 2) {
+    TN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad_tc_kernel<2><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mA, mB, p);
+  } else {
+    TN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad_tc_kernel<1><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mA, mB, p);
+  }
+  TN_LAUNCH_CHECK("wgrad_tc_kernel");
   return TN_OK;
 }
 
