@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--cpu-batch", type=int, default=8, help="utterances per step of the CPU arm / CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -196,30 +197,21 @@ def run_ours(args):
     labels_h = torch.randint(0, N_CLASSES, (B,), generator=g).pin_memory()
     wave_d, labels_d = wave_h.to(dev), labels_h.to(dev)
 
-    def allreduce_grads():
-        if world == 1:
-            return
-        flat = torch.cat([p.grad.reshape(-1) for p in params])
-        dist.all_reduce(flat)
-        flat.mul_(1.0 / world)
-        off = 0
-        for p in params:
-            n = p.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p))
-            off += n
+    from titanet_b200.engine import GradAllReduce, GraphedTrainStep
+    allreduce = GradAllReduce(params, world)
+    gts = GraphedTrainStep(model, mel, B, L, dev, use_graph=not args.no_graph, warmup=max(3, args.warmup))
 
-    def step(wave, labels):
-        for p in params:
-            p.grad = None
-        emb, preds, loss = model(mel.batch(wave), speakers=labels)
-        loss.backward()
-        allreduce_grads()
+    def step_resident():
+        gts.load(wave_d, labels_d)        # device -> device: inputs are already in HBM
+        loss = gts.run()
+        allreduce()
         return loss
 
     def step_e2e():
-        w = wave_h.to(dev, non_blocking=True)
-        y = labels_h.to(dev, non_blocking=True)
-        return float(step(w, y))          # D2H read of the loss (synchronises)
+        gts.load(wave_h, labels_h)        # pinned host -> device copies inside the timed region
+        loss = gts.run()
+        allreduce()
+        return float(loss.detach())       # D2H read of the loss (synchronises)
 
     def barrier():
         if world > 1:
@@ -240,15 +232,19 @@ def run_ours(args):
         return float(ms) / steps
 
     for _ in range(max(3, args.warmup)):
-        step(wave_d, labels_d)
+        step_resident()
     sampler = ClockSampler(local) if rank == 0 else None
-    _lib.COUNTS.clear()
-    ms_step = timed(lambda: step(wave_d, labels_d), args.steps)
-    launches = _lib.kernel_launches() // args.steps
+    ms_step = timed(step_resident, args.steps)
+    launches = gts.launches_per_step
     clocks = sampler.stop() if sampler else None
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+
+    def step(wave, labels):               # eager body for the per-kernel profile below
+        gts.wave.copy_(wave)
+        gts.labels.copy_(labels)
+        gts._body()
 
     # per-kernel device time: a separate pass with CUDA events around every launch
     roof = None
@@ -300,7 +296,7 @@ def run_ours(args):
         "config": workload_config(args, B),
         "e2e": {"value": round(e2e, 1), "unit": "utterances/s", "h2d_bytes_per_step": B * L * 4 + B * 8, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e, 3)},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        "gpu_launches": launches, "cuda_graph": not args.no_graph, "clocks": clocks, "roofline": roof,
     }
     if not args.no_cpu_baseline and world == 1:
         v, dt = time_cpu(args, args.cpu_batch, 2, 1)

@@ -102,8 +102,10 @@ int tn_bn_finalize(const double* stats, double n, const float* gamma, const floa
                    float* scale, float* shift, float* mean, float* invstd, int C, void* stream);
 int tn_bn_bwd_coef(const float* dscale, const float* dshift, const float* mean, const float* invstd, const float* gamma,
                    double n, int training, float* dgamma, float* dbeta, double* dstats, int C, void* stream);
-/* out = (dz_direct or 0) + dstats[c] + 2 z dstats[C+c]: gradient of the statistics w.r.t. their tensor */
-int tn_stats_bwd(const float* dz_direct, const float* z, const double* dstats, float* out, int R, int C, void* stream);
+/* out = (dz_direct or 0) + dstats[c] + 2 z dstats[C+c]: gradient of the statistics w.r.t. their tensor;
+ * dbias (optional, ACCUMULATED) += column sums of out (the conv-bias gradient, same pass) */
+int tn_stats_bwd(const float* dz_direct, const float* z, const double* dstats, float* out, float* dbias, int R, int C,
+                 void* stream);
 /* dropout seed stream: state = splitmix64 step, *out = this step's seed (device scalars) */
 int tn_seed_next(unsigned long long* state, unsigned long long* out, void* stream);
 int tn_act_fwd(const float* z, float* y, const float* scale, const float* shift, int relu, float drop_p,

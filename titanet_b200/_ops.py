@@ -170,17 +170,18 @@ class ConvGemm(Function):
             g = empty(dz.shape, dz)
             call("tn_tanh_bwd", ptr(dz), ptr(z), ptr(g), dz.numel())
             dz = g
+        db = zeros(bias.shape, bias) if bias is not None else None
+        db_done = False
         if want_stats and dstats is not None:
             g = empty(dz.shape, dz)
-            call("tn_stats_bwd", ptr(dz), ptr(z), ptr(dstats.contiguous()), ptr(g), B * T, Co)
-            dz = g
+            call("tn_stats_bwd", ptr(dz), ptr(z), ptr(dstats.contiguous()), ptr(g), ptr(db), B * T, Co)   # + bias gradient
+            dz, db_done = g, True
         dx = None
         if ctx.needs_input_grad[0]:
             dx = empty((B * T, Ci), x)
             _gemm_fwd(dz, w3, None, dx, None, B, T, 1, 0)
         dw = zeros(w.shape, w)
-        db = zeros(bias.shape, bias) if bias is not None else None
-        _gemm_wgrad(dz, x, dw if dw.dim() == 3 else dw.unsqueeze(-1), db, B, T)
+        _gemm_wgrad(dz, x, dw if dw.dim() == 3 else dw.unsqueeze(-1), None if db_done else db, B, T)
         return dx, dw, db, None, None, None, None
 
 
@@ -204,7 +205,7 @@ class ColStats(Function):
     def backward(ctx, dstats):
         (x,) = ctx.saved_tensors
         dx = empty(x.shape, x)
-        call("tn_stats_bwd", None, ptr(x), ptr(dstats.contiguous()), ptr(dx), x.shape[0], x.shape[1])
+        call("tn_stats_bwd", None, ptr(x), ptr(dstats.contiguous()), ptr(dx), None, x.shape[0], x.shape[1])
         return dx
 
 

@@ -185,16 +185,19 @@ __device__ __forceinline__ TnTile tn_tile(int C) {
 // shared memory.  Must be called by all threads of the block the same number of times.
 template <typename DstT>
 __device__ __forceinline__ void tn_lane_reduce_atomic(const TnTile& t, float4 v, int q, DstT* dst, float4* red, float mul = 1.f) {
+  // Same-line atomics serialise in the L2 slice (~27 cycles per warp-level visit of a 128-byte
+  // line), so the block leaves with ONE visit per line: consecutive threads own consecutive
+  // channels (32 floats = one line per warp instruction) instead of 4 strided scalars per thread.
   __syncthreads();
   red[threadIdx.x] = t.active ? v : tn_zero4();
   __syncthreads();
-  if (t.lane == 0 && q < t.Q) {
-    float4 s = red[threadIdx.x];
-    for (int l = 1; l < t.lanes; ++l) s = s + red[threadIdx.x + l * t.qpb];
-    atomicAdd(dst + 4 * q + 0, (DstT)(s.x * mul));
-    atomicAdd(dst + 4 * q + 1, (DstT)(s.y * mul));
-    atomicAdd(dst + 4 * q + 2, (DstT)(s.z * mul));
-    atomicAdd(dst + 4 * q + 3, (DstT)(s.w * mul));
+  const float* rf = reinterpret_cast<const float*>(red);
+  const int qb = q - t.q0;                       // first quad of this pass (block-uniform)
+  const int nch = min(4 * t.qpb, 4 * (t.Q - qb));
+  for (int ch = threadIdx.x; ch < nch; ch += TN_EW_THREADS) {
+    float s = rf[ch];
+    for (int l = 1; l < t.lanes; ++l) s += rf[ch + l * 4 * t.qpb];
+    atomicAdd(dst + 4 * qb + ch, (DstT)(s * mul));
   }
 }
 #endif  // __CUDACC__

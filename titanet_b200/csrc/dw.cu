@@ -127,19 +127,18 @@ __global__ void __launch_bounds__(DW_THREADS) dw_bwd_kernel(const float* __restr
       tn_lane_reduce_atomic(tl, a_sc, q, dscale, red);
       tn_lane_reduce_atomic(tl, a_sh, q, dshift, red);
     }
-    // dw is [C, K]: one lane-reduction per tap
+    // dw is [C, K]: one lane-reduction per tap (consecutive threads -> consecutive channels)
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       __syncthreads();
       red[threadIdx.x] = tl.active ? a_w[j] : tn_zero4();
       __syncthreads();
-      if (tl.lane == 0 && q < tl.Q) {
-        float4 s = red[threadIdx.x];
-        for (int l = 1; l < tl.lanes; ++l) s = s + red[threadIdx.x + l * tl.qpb];
-        atomicAdd(dw + (c + 0) * K + j, s.x);
-        atomicAdd(dw + (c + 1) * K + j, s.y);
-        atomicAdd(dw + (c + 2) * K + j, s.z);
-        atomicAdd(dw + (c + 3) * K + j, s.w);
+      const float* rf = reinterpret_cast<const float*>(red);
+      const int nch = min(4 * tl.qpb, 4 * (tl.Q - qb));
+      for (int ch = threadIdx.x; ch < nch; ch += DW_THREADS) {
+        float s = rf[ch];
+        for (int l = 1; l < tl.lanes; ++l) s += rf[ch + l * 4 * tl.qpb];
+        atomicAdd(dw + (size_t)(4 * qb + ch) * K + j, s);
       }
     }
   }
@@ -147,7 +146,7 @@ __global__ void __launch_bounds__(DW_THREADS) dw_bwd_kernel(const float* __restr
 
 static int dw_rows_per_block(int C, int K) {
   int Q = C / 4, qpb = Q < DW_THREADS ? Q : DW_THREADS, lanes = DW_THREADS / qpb;
-  int run = K <= 5 ? 8 : 16;
+  int run = K <= 5 ? 16 : 32;
   return lanes * run;
 }
 

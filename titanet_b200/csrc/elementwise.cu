@@ -47,10 +47,10 @@ extern "C" int tn_zero(void* p, size_t bytes, void* stream) {
 
 // rows per block for the row-tiled kernels: aim at >= 4 waves of 8 blocks/SM
 static int rows_per_block(long long R) {
-  long long target = (long long)tn_num_sms() * 16;
+  long long target = (long long)tn_num_sms() * 4;      // few, fat blocks: every block ends in per-channel atomics
   long long rpb = (R + target - 1) / target;
-  if (rpb < 16) rpb = 16;
-  if (rpb > 128) rpb = 128;
+  if (rpb < 32) rpb = 32;
+  if (rpb > 256) rpb = 256;
   return (int)rpb;
 }
 
@@ -284,31 +284,41 @@ extern "C" int tn_bn_bwd_coef(const float* dscale, const float* dshift, const fl
 }
 
 // out = (dz_direct or 0) + dS1[c] + 2 * z * dS2[c]   -- the statistics path of the BatchNorm
-// backward (and the whole backward of tn_colstats when dz_direct == NULL).  out may alias dz_direct.
+// backward (and the whole backward of tn_colstats when dz_direct == NULL).  out may alias
+// dz_direct.  dbias (optional, ACCUMULATED) receives the column sums of out: the gradient of the
+// conv bias in front of the BatchNorm, for free in the same pass.
 __global__ void __launch_bounds__(TN_EW_THREADS) stats_bwd_kernel(const float* __restrict__ dzd, const float* __restrict__ z,
                                                                   const double* __restrict__ dstats, float* __restrict__ out,
-                                                                  size_t n4, int Q) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  const int C = 4 * Q;
-  for (; i < n4; i += stride) {
-    int c = 4 * (int)(i % Q);
-    float4 a = make_float4((float)dstats[c], (float)dstats[c + 1], (float)dstats[c + 2], (float)dstats[c + 3]);
-    float4 b = make_float4((float)(2.0 * dstats[C + c]), (float)(2.0 * dstats[C + c + 1]), (float)(2.0 * dstats[C + c + 2]),
-                           (float)(2.0 * dstats[C + c + 3]));
-    float4 v = tn_fma4(b, tn_ld4(z + 4 * i), a);
-    if (dzd) v = v + tn_ld4(dzd + 4 * i);
-    tn_st4(out + 4 * i, v);
+                                                                  float* __restrict__ dbias, int R, int C, int rpb) {
+  __shared__ float4 red[TN_EW_THREADS];
+  TnTile tl = tn_tile(C);
+  const int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    const int q = qb + tl.q0;
+    float4 acc = tn_zero4();
+    if (tl.active && q < tl.Q) {
+      const int c = 4 * q;
+      const float4 a = make_float4((float)dstats[c], (float)dstats[c + 1], (float)dstats[c + 2], (float)dstats[c + 3]);
+      const float4 b = make_float4((float)(2.0 * dstats[C + c]), (float)(2.0 * dstats[C + c + 1]), (float)(2.0 * dstats[C + c + 2]),
+                                   (float)(2.0 * dstats[C + c + 3]));
+#pragma unroll 4
+      for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
+        const size_t off = (size_t)r * C + c;
+        float4 v = tn_fma4(b, tn_ld4(z + off), a);
+        if (dzd) v = v + tn_ld4(dzd + off);
+        tn_st4(out + off, v);
+        acc = acc + v;
+      }
+    }
+    if (dbias) tn_lane_reduce_atomic(tl, acc, q, dbias, red);
   }
 }
-extern "C" int tn_stats_bwd(const float* dz_direct, const float* z, const double* dstats, float* out, int R, int C, void* stream) {
+extern "C" int tn_stats_bwd(const float* dz_direct, const float* z, const double* dstats, float* out, float* dbias, int R, int C,
+                            void* stream) {
   TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0 && z && dstats && out && tn_aligned16(out) && tn_aligned16(z) && (!dz_direct || tn_aligned16(dz_direct)),
              "stats_bwd: need C %% 4 == 0 and aligned tensors (R=%d C=%d)", R, C);
-  size_t n4 = (size_t)R * C / 4;
-  int blocks = (int)((n4 + TN_EW_THREADS - 1) / TN_EW_THREADS);
-  int cap = tn_num_sms() * 16;
-  if (blocks > cap) blocks = cap;
-  stats_bwd_kernel<<<blocks, TN_EW_THREADS, 0, (cudaStream_t)stream>>>(dz_direct, z, dstats, out, n4, C / 4);
+  int rpb = rows_per_block(R);
+  stats_bwd_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(dz_direct, z, dstats, out, dbias, R, C, rpb);
   TN_LAUNCH_CHECK("stats_bwd_kernel");
   return TN_OK;
 }

@@ -193,19 +193,19 @@ __global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd2_kernel(const float* _
 }
 
 static int tail_rows_per_block(long long R) {
-  long long target = (long long)tn_num_sms() * 16;
+  long long target = (long long)tn_num_sms() * 4;      // few, fat blocks: every block ends in per-channel atomics
   long long rpb = (R + target - 1) / target;
-  if (rpb < 16) rpb = 16;
-  if (rpb > 128) rpb = 128;
+  if (rpb < 32) rpb = 32;
+  if (rpb > 256) rpb = 256;
   return (int)rpb;
 }
 static int time_per_block(int B, int T) {
   // blocks = B * ceil(T / tpb); aim at >= 8 blocks per SM
-  long long target = (long long)tn_num_sms() * 8;
+  long long target = (long long)tn_num_sms() * 4;
   long long chunks = (target + B - 1) / B;
   if (chunks < 1) chunks = 1;
   long long tpb = (T + chunks - 1) / chunks;
-  if (tpb < 16) tpb = 16;
+  if (tpb < 32) tpb = 32;
   return (int)tpb;
 }
 
