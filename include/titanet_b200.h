@@ -75,6 +75,7 @@ int tn_conv_wgrad_simt(const float* dZ, const float* X, float* dW, float* dbias,
  * (transpose = 1 reads W as [Kd, M]: the data-gradient GEMM).  nsplit: 3 (hi*hi+lo*hi+hi*lo)
  * or 1 (plain TF32).  Needs Kd %% 32 == 0 and M %% 128 == 0 (tn_gemm_tc_supported). */
 int tn_gemm_tc_supported(int R, int Kd, int M);
+int tn_gemm_tc_set_trace(long long* buf);      /* debug: clock64 timeline of two CTAs (256 int64), NULL = off */
 int tn_split_tf32(const float* W, float* ws, int M, int Kd, int transpose, void* stream);
 int tn_gemm_tc(const float* X, const float* ws, const float* bias, float* Z, double* stats, int R, int Kd, int M, int flags,
                int nsplit, void* stream);

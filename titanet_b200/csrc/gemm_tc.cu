@@ -85,6 +85,20 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// issue a 16-column TMEM load without waiting; tc_ld_wait() makes the registers valid.  The
+// "+f" constraints on the wait tie the data dependence so the compiler cannot hoist uses above it.
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, float* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+                 "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait(float* v, int n) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i < n) asm volatile("" : "+f"(v[i]));
+}
 __device__ __forceinline__ uint32_t rna_tf32(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -101,7 +115,10 @@ struct TcParams {
   float* Z;
   double* stats;
   int R, Kd, M_total, BN, stages, nsplit, flags, tmem_cols;
+  long long* trace;      // optional timeline buffer (debug): 128 slots per traced CTA
 };
+#define TC_TRACE(slot) do { if (p.trace && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && blockIdx.y == 0) \
+    p.trace[(blockIdx.x == 0 ? 0 : 128) + (slot)] = clock64(); } while (0)
 
 // ---------------------------------------------------------------------------
 // kernel: MT = number of 128-row output-channel tiles per CTA (1 or 2)
@@ -116,6 +133,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { TC_TRACE(110); if (p.trace && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) {
+      unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[(blockIdx.x == 0 ? 0 : 128) + 111] = (long long)gt; } }
   const int BN = p.BN, S = p.stages;
   const int n0 = blockIdx.x * BN;                    // first activation row of this CTA
   const int m0 = blockIdx.y * (128 * MT);            // first output channel of this CTA
@@ -151,6 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  if (threadIdx.x == 0) TC_TRACE(0);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -160,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (kc >= S) mbar_wait(empty0 + 8 * s, ((kc / S) - 1) & 1);
         const uint32_t fb = full0 + 8 * s;
         const bool skip_a = (p.flags & 1024) != 0;      // debug knob: measure the B feed alone
+        TC_TRACE(1 + kc);
         mbar_expect_tx(fb, skip_a ? b_tile : tx_bytes);
         const int k0 = kc * TC_BK;
 #pragma unroll
@@ -178,7 +199,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int s = kc % S;
         const uint32_t ph = (kc / S) & 1;
         mbar_wait(full0 + 8 * s, ph);
+        TC_TRACE(40 + kc);
         if (split) mbar_wait(ready0 + 8 * s, ph);
+        TC_TRACE(60 + kc);
         tc_fence_after();
         const uint64_t dbh = umma_desc_k128(smem_u32(b_hi(s)));
         const uint64_t dbl = split ? umma_desc_k128(smem_u32(b_lo(s))) : 0;
@@ -202,6 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
         }
         tc_commit(empty0 + 8 * s);           // stage free once these MMAs have read it
+        TC_TRACE(80 + kc);
       }
       tc_commit(accum_bar);                  // accumulators complete
     }
@@ -226,30 +250,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(ready0 + 8 * s);
+        if (tid == 0) TC_TRACE(20 + kc);
       }
     }
     mbar_wait(accum_bar, 0);
+    if (tid == 0) TC_TRACE(100);
     tc_fence_after();
     const int quad = warp & 3;               // TMEM lanes 32*quad .. 32*quad+31 belong to this warp
+    const bool fast = (p.flags == 0) && (n0 + BN <= p.R);      // full tile, plain epilogue: no per-element branches
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       const int co = m0 + mt * 128 + quad * 32 + lane;
       const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
+      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 256);
       float s1 = 0.f, s2 = 0.f;
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 256 + c0), v);
+      if (fast) {
+        float* zp = p.Z + (size_t)n0 * p.M_total + co;
+        const size_t ld = (size_t)p.M_total;
+        int c0 = 0;
+        for (; c0 + 32 <= BN; c0 += 32) {            // two x16 loads in flight per wait
+          float v[32];
+          tc_ld16_issue(tbase + c0, v);
+          tc_ld16_issue(tbase + c0 + 16, v + 16);
+          tc_ld_wait(v, 32);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int r = n0 + c0 + j;
-          if (r < p.R && !(p.flags & 512)) {               // (512: debug knob, no stores)
-            float x = v[j] + bv;
-            if (p.flags & TN_EPI_TANH) x = tanhf(x);
-            float* zp = p.Z + (size_t)r * p.M_total + co;
-            if (p.flags & TN_EPI_ACCUM) x += *zp;
-            *zp = x;
+          for (int j = 0; j < 32; ++j) {
+            const float x = v[j] + bv;
+            zp[(size_t)(c0 + j) * ld] = x;
             s1 += x;
             s2 = fmaf(x, x, s2);
+          }
+        }
+        for (; c0 < BN; c0 += 16) {
+          float v[16];
+          tc_ld16_issue(tbase + c0, v);
+          tc_ld_wait(v, 16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = v[j] + bv;
+            zp[(size_t)(c0 + j) * ld] = x;
+            s1 += x;
+            s2 = fmaf(x, x, s2);
+          }
+        }
+      } else {
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          tc_ld16(tbase + c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int r = n0 + c0 + j;
+            if (r < p.R && !(p.flags & 512)) {               // (512: debug knob, no stores)
+              float x = v[j] + bv;
+              if (p.flags & TN_EPI_TANH) x = tanhf(x);
+              float* zq = p.Z + (size_t)r * p.M_total + co;
+              if (p.flags & TN_EPI_ACCUM) x += *zq;
+              *zq = x;
+              s1 += x;
+              s2 = fmaf(x, x, s2);
+            }
           }
         }
       }
@@ -259,11 +318,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   }
+  if (threadIdx.x == 64) TC_TRACE(101);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
+  if (threadIdx.x == 0) { TC_TRACE(102); if (p.trace && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) {
+      unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[(blockIdx.x == 0 ? 0 : 128) + 112] = (long long)gt; } }
 }
 
 // ---------------------------------------------------------------------------
@@ -284,6 +346,10 @@ __global__ void split_tf32_kernel(const float* __restrict__ W, float* __restrict
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+static long long* g_trace = nullptr;
+// debug: device buffer of 256 int64 receiving a clock64() timeline of two CTAs of the next tn_gemm_tc launches
+extern "C" int tn_gemm_tc_set_trace(long long* buf) { g_trace = buf; return TN_OK; }
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -543,6 +609,7 @@ extern "C" int tn_gemm_tc(const float* X, const float* ws, const float* bias, fl
   TcParams p;
   p.bias = bias; p.Z = Z; p.stats = stats; p.R = R; p.Kd = Kd; p.M_total = M; p.BN = bn; p.stages = stages; p.nsplit = nsplit;
   p.flags = flags;
+  p.trace = g_trace;
   int cols = MT == 2 ? 512 : 32;
   while (MT == 1 && cols < bn) cols <<= 1;
   p.tmem_cols = cols;
