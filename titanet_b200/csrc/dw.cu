@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(DW_THREADS) dw_fwd_kernel(const float* __restr
 #pragma unroll
     for (int j = 0; j < K - 1; ++j) win[j] = load(ra - PAD + j);
     int t = ra % T;
+#pragma unroll 4
     for (int r = ra; r < rb; ++r) {
       win[K - 1] = load(r + PAD);
       float4 acc = b4;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(DW_THREADS) dw_fwd_kernel(const float* __restr
 
 // backward: da = dw^T(du); dz = da * act'(z) * scale; accumulates dscale, dshift, dw, dbias
 template <int K>
-__global__ void __launch_bounds__(DW_THREADS) dw_bwd_kernel(const float* __restrict__ du, const float* __restrict__ z,
+__global__ void __launch_bounds__(DW_THREADS, (K <= 5 ? 2 : 1)) dw_bwd_kernel(const float* __restrict__ du, const float* __restrict__ z,
                                                             float* __restrict__ dz, const float* __restrict__ w,
                                                             float* __restrict__ dw, float* __restrict__ dbias,
                                                             float* __restrict__ dscale, float* __restrict__ dshift,
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(DW_THREADS) dw_bwd_kernel(const float* __restr
 #pragma unroll
       for (int j = 0; j < K - 1; ++j) { aw[j] = load_a(ra - PAD + j); gw[j] = load_g(ra - PAD + j); }
       int t = ra % T;
+#pragma unroll 2
       for (int r = ra; r < rb; ++r) {
         aw[K - 1] = load_a(r + PAD);
         gw[K - 1] = load_g(r + PAD);
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(DW_THREADS) dw_bwd_kernel(const float* __restr
 
 static int dw_rows_per_block(int C, int K) {
   int Q = C / 4, qpb = Q < DW_THREADS ? Q : DW_THREADS, lanes = DW_THREADS / qpb;
-  int run = K <= 5 ? 16 : 32;
+  int run = K <= 5 ? 8 : 16;
   return lanes * run;
 }
 

@@ -21,7 +21,7 @@
 __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict__ X, const float* __restrict__ W,
                                                         const float* __restrict__ bias, float* __restrict__ Z,
                                                         double* __restrict__ stats, int R, int T, int Ci, int Co, int K,
-                                                        int transpose_w, int flags) {
+                                                        int transpose_w, int flags, int kk_per_split) {
   __shared__ float As[GK][GM + 4];
   __shared__ float Bs[GK][GN + 4];
   __shared__ float red1[16][GN], red2[16][GN];
@@ -30,6 +30,10 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
   const int r0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
   const int pad = K / 2;
   const int KK = K * Ci;                // reduction length; kk = tap * Ci + ci
+  // split-K (skinny problems, e.g. the decoder's [B, 3072] x [3072, 192]): blockIdx.z owns a slice of the
+  // reduction and adds its partial tile to a zero-initialised Z with atomics (flags == 0, no stats).
+  const bool splitk = gridDim.z > 1;
+  const int kk_begin = blockIdx.z * kk_per_split, kk_end = min(KK, kk_begin + kk_per_split);
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -38,17 +42,17 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
 
   const int lk = tid & 15;              // reduction index inside the chunk handled by this thread's loads
   const int lr = tid >> 4;              // row / column group
-  for (int kk0 = 0; kk0 < KK; kk0 += GK) {
+  for (int kk0 = kk_begin; kk0 < kk_end; kk0 += GK) {
     const int kk = kk0 + lk;
-    const int tap = kk < KK ? kk / Ci : 0;
-    const int ci = kk < KK ? kk - tap * Ci : 0;
+    const int tap = kk < kk_end ? kk / Ci : 0;
+    const int ci = kk < kk_end ? kk - tap * Ci : 0;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       // A tile: rows r0 + lr + 16p
       const int m = lr + 16 * p;
       const int r = r0 + m;
       float v = 0.f;
-      if (kk < KK && r < R) {
+      if (kk < kk_end && r < R) {
         const int t = r % T;
         const int tt = t + tap - pad;
         if (tt >= 0 && tt < T) v = __ldg(X + (size_t)(r + tap - pad) * Ci + ci);
@@ -57,7 +61,7 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
       // B tile: output channels n0 + lr + 16p
       const int n = n0 + m;
       float wv = 0.f;
-      if (kk < KK && n < Co) {
+      if (kk < kk_end && n < Co) {
         wv = transpose_w ? __ldg(W + ((size_t)ci * Co + n) * K + (K - 1 - tap))   // W is [Ci(red), Co(out), K]
                          : __ldg(W + ((size_t)n * Ci + ci) * K + tap);            // W is [Co(out), Ci(red), K]
       }
@@ -86,16 +90,17 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= Co) continue;
-      float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
-      if (flags & TN_EPI_TANH) v = tanhf(v);
+      float v = acc[i][j] + ((bias && blockIdx.z == 0) ? __ldg(bias + n) : 0.f);
       float* zp = Z + (size_t)r * Co + n;
+      if (splitk) { atomicAdd(zp, v); continue; }
+      if (flags & TN_EPI_TANH) v = tanhf(v);
       if (flags & TN_EPI_ACCUM) v += *zp;
       *zp = v;
       s1[j] += v;
       s2[j] = fmaf(v, v, s2[j]);
     }
   }
-  if (stats) {
+  if (stats && !splitk) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) { red1[ty][tx * 4 + j] = s1[j]; red2[ty][tx * 4 + j] = s2[j]; }
     __syncthreads();
@@ -192,8 +197,20 @@ extern "C" int tn_conv_gemm_simt(const float* X, const float* W, const float* bi
   long long R = (long long)B * T;
   TN_REQUIRE(R < (1ll << 31) && tn_cdiv(Co, GN) <= 65535, "conv_gemm: shape too large");
   dim3 grid(tn_cdiv(R, GM), tn_cdiv(Co, GN));
-  conv_gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, W, bias, Z, stats, (int)R, T, Ci, Co, K, transpose_w, flags);
+  const long long KK = (long long)K * Ci;
+  int splits = 1;
+  if (flags == 0 && KK >= 1024 && (long long)grid.x * grid.y * 4 <= tn_num_sms()) {
+    splits = tn_num_sms() / (int)(grid.x * grid.y);
+    if (splits > KK / 128) splits = (int)(KK / 128);
+    if (splits < 1) splits = 1;
+  }
+  int kps = (int)(((KK + splits - 1) / splits + GK - 1) / GK * GK);
+  splits = (int)((KK + kps - 1) / kps);
+  grid.z = splits;
+  if (splits > 1) TN_CUDA(cudaMemsetAsync(Z, 0, sizeof(float) * (size_t)R * Co, (cudaStream_t)stream));
+  conv_gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, W, bias, Z, stats, (int)R, T, Ci, Co, K, transpose_w, flags, kps);
   TN_LAUNCH_CHECK("conv_gemm_kernel");
+  if (splits > 1 && stats) return tn_colstats(Z, stats, (int)R, Co, stream);   // split-K: statistics from the finished tensor
   return TN_OK;
 }
 

@@ -110,6 +110,35 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// Epilogue of one 128-channel accumulator tile: TMEM -> registers -> (+bias, tanh, +=) -> global.
+// This thread owns output channel `zp[0]`; column j of the tile is activation row j (stride ld).
+// Rows >= nvalid (tail tile) are masked by predication, not branches.
+template <bool TANH, bool ACCUM, bool FULL>
+__device__ __forceinline__ void tc_epilogue(uint32_t tbase, float* __restrict__ zp, size_t ld, int BN, int nvalid, float bv,
+                                            float& s1, float& s2) {
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    float v[32];
+    const bool two = c0 + 16 < BN;                   // BN is a multiple of 16
+    tc_ld16_issue(tbase + c0, v);
+    if (two) tc_ld16_issue(tbase + c0 + 16, v + 16);
+    tc_ld_wait(v, 32);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j >= 16 && !two) break;
+      const bool ok = FULL || (c0 + j < nvalid);
+      float x = v[j] + bv;
+      if (TANH) x = tanhf(x);
+      float* q = zp + (size_t)(c0 + j) * ld;
+      if (ACCUM) x += ok ? *q : 0.f;
+      if (ok) {
+        *q = x;
+        s1 += x;
+        s2 = fmaf(x, x, s2);
+      }
+    }
+  }
+}
+
 struct TcParams {
   const float* bias;
   float* Z;
@@ -135,6 +164,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) { TC_TRACE(110); if (p.trace && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) {
       unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[(blockIdx.x == 0 ? 0 : 128) + 111] = (long long)gt; } }
+  if (threadIdx.x == 0 && p.trace && blockIdx.y == 0 && blockIdx.x < 256) {
+    unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[256 + 2 * blockIdx.x] = (long long)gt; }
   const int BN = p.BN, S = p.stages;
   const int n0 = blockIdx.x * BN;                    // first activation row of this CTA
   const int m0 = blockIdx.y * (128 * MT);            // first output channel of this CTA
@@ -257,60 +288,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (tid == 0) TC_TRACE(100);
     tc_fence_after();
     const int quad = warp & 3;               // TMEM lanes 32*quad .. 32*quad+31 belong to this warp
-    const bool fast = (p.flags == 0) && (n0 + BN <= p.R);      // full tile, plain epilogue: no per-element branches
+    const int nvalid = min(BN, p.R - n0);                       // rows of this tile inside the tensor
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       const int co = m0 + mt * 128 + quad * 32 + lane;
       const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 256);
+      float* zp = p.Z + (size_t)n0 * p.M_total + co;
       float s1 = 0.f, s2 = 0.f;
-      if (fast) {
-        float* zp = p.Z + (size_t)n0 * p.M_total + co;
-        const size_t ld = (size_t)p.M_total;
-        int c0 = 0;
-        for (; c0 + 32 <= BN; c0 += 32) {            // two x16 loads in flight per wait
-          float v[32];
-          tc_ld16_issue(tbase + c0, v);
-          tc_ld16_issue(tbase + c0 + 16, v + 16);
-          tc_ld_wait(v, 32);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = v[j] + bv;
-            zp[(size_t)(c0 + j) * ld] = x;
-            s1 += x;
-            s2 = fmaf(x, x, s2);
-          }
-        }
-        for (; c0 < BN; c0 += 16) {
-          float v[16];
-          tc_ld16_issue(tbase + c0, v);
-          tc_ld_wait(v, 16);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float x = v[j] + bv;
-            zp[(size_t)(c0 + j) * ld] = x;
-            s1 += x;
-            s2 = fmaf(x, x, s2);
-          }
-        }
-      } else {
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          float v[16];
-          tc_ld16(tbase + c0, v);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int r = n0 + c0 + j;
-            if (r < p.R && !(p.flags & 512)) {               // (512: debug knob, no stores)
-              float x = v[j] + bv;
-              if (p.flags & TN_EPI_TANH) x = tanhf(x);
-              float* zq = p.Z + (size_t)r * p.M_total + co;
-              if (p.flags & TN_EPI_ACCUM) x += *zq;
-              *zq = x;
-              s1 += x;
-              s2 = fmaf(x, x, s2);
-            }
-          }
-        }
+      switch ((p.flags & 3) | (nvalid == BN ? 4 : 0)) {          // warp-uniform: one specialised, branch-free loop each
+        case 4: tc_epilogue<false, false, true>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2); break;
+        case 0: tc_epilogue<false, false, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2); break;
+        case TN_EPI_TANH: case TN_EPI_TANH | 4: tc_epilogue<true, false, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2); break;
+        case TN_EPI_ACCUM: case TN_EPI_ACCUM | 4: tc_epilogue<false, true, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2); break;
+        default: tc_epilogue<true, true, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2); break;
       }
       if (p.stats) {
         atomicAdd(p.stats + co, (double)s1);
@@ -324,6 +315,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
+  if (threadIdx.x == 0 && p.trace && blockIdx.y == 0 && blockIdx.x < 256) {
+    unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[257 + 2 * blockIdx.x] = (long long)gt; }
   if (threadIdx.x == 0) { TC_TRACE(102); if (p.trace && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) {
       unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[(blockIdx.x == 0 ? 0 : 128) + 112] = (long long)gt; } }
 }

@@ -6,7 +6,7 @@ from titanet_b200._lib import LIB, call, ptr
 R, K, M, nsplit = (int(v) for v in (sys.argv[1:5] + ["19264", "256", "256", "3"][len(sys.argv) - 1:]))
 x = torch.randn(R, K, device="cuda"); w = torch.randn(M, K, device="cuda") / math.sqrt(K)
 z = torch.empty(R, M, device="cuda"); ws = torch.empty(2, M, K, device="cuda")
-tr = torch.zeros(256, dtype=torch.int64, device="cuda")
+tr = torch.zeros(1024, dtype=torch.int64, device="cuda")
 call("tn_split_tf32", ptr(w), ptr(ws), M, K, 0)
 for _ in range(3): call("tn_gemm_tc", ptr(x), ptr(ws), None, ptr(z), None, R, K, M, 0, nsplit)
 torch.cuda.synchronize()
@@ -27,3 +27,9 @@ for base, name in ((0, "CTA 0"), (128, "CTA mid")):
               f"ready_seen {us(t[base+60+kc]):6.2f}  mma_issued {us(t[base+80+kc]):6.2f}")
     print(f" kernel entry {us(t[base+110]):6.2f} (prologue = {-us(t[base+110]):.2f} us); globaltimer entry->exit {(t[base+112]-t[base+111])/1e3:.2f} us")
     print(f" accum_seen {us(t[base+100]):6.2f}  epilogue_done {us(t[base+101]):6.2f}  exit {us(t[base+102]):6.2f}")
+
+import statistics
+ent = [t[256 + 2 * i] for i in range(256) if t[256 + 2 * i]]; ext = [t[257 + 2 * i] for i in range(256) if t[257 + 2 * i]]
+e0_ = min(ent)
+print(f"CTAs traced {len(ent)}: entry spread {(max(ent)-e0_)/1e3:.2f} us (median {(statistics.median(ent)-e0_)/1e3:.2f}); last exit at {(max(ext)-e0_)/1e3:.2f} us; "
+      f"lifetime median {statistics.median([b-a for a,b in zip(ent,ext)])/1e3:.2f} max {max(b-a for a,b in zip(ent,ext))/1e3:.2f} us")
