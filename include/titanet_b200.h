@@ -21,7 +21,7 @@
  *    its pre-BN values z; consumers receive (scale, shift, relu, drop_p, seed, layer)
  *    and compute a = dropout(relu(z*scale[c] + shift[c])) on load.  scale == NULL
  *    means the tensor is already an activation.  Dropout masks come from a
- *    counter-based Philox4x32-10 keyed by (seed, layer, element index), so the
+ *    counter-based hash (seeded multiply-xorshift) of (seed, layer, element index), so the
  *    backward pass regenerates them.
  *  - "ACCUMULATED" outputs are added to (atomically); the caller zeroes them.
  */
@@ -79,6 +79,15 @@ int tn_gemm_tc_set_trace(long long* buf);      /* debug: clock64 timeline of two
 int tn_split_tf32(const float* W, float* ws, int M, int Kd, int transpose, void* stream);
 int tn_gemm_tc(const float* X, const float* ws, const float* bias, float* Z, double* stats, int R, int Kd, int M, int flags,
                int nsplit, void* stream);
+/* Data gradient of a depthwise-separable block in ONE kernel: du = dZ[R,Co] W[Co,C] on the tensor
+ * cores (ws = tn_split_tf32(W, transpose = 1)), then, in the epilogue, the transposed depthwise conv,
+ * the BN/ReLU/dropout backward of the previous layer and all per-channel reductions:
+ * dzprev, dw += , dbias +=, dscale +=, dshift +=  (= tn_gemm_tc(dgrad) + tn_dw_bwd without du in HBM).
+ * Autograd of DepthwiseConv1d + ConvBlock1d (src/modules.py:64-79, 119-134) under loss.backward(). */
+int tn_gemm_tc_dwbwd(const float* dZ, const float* ws, const float* zprev, float* dzprev, const float* dw_w, float* g_dw,
+                     float* g_dbias, float* g_dscale, float* g_dshift, const float* scale, const float* shift, int relu,
+                     float drop_p, const unsigned long long* seed, unsigned int layer, int B, int T, int Co, int C, int K,
+                     int nsplit, void* stream);
 /* dW[Co,Ci] += dZ[R,Co]^T U[R,Ci] on the tensor cores (split-K over rows, MN-major operands; ACCUMULATED) */
 int tn_wgrad_tc_supported(int R, int Ci, int Co);
 int tn_wgrad_tc(const float* dZ, const float* U, float* dW, int R, int Ci, int Co, void* stream);

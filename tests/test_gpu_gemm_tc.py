@@ -102,3 +102,43 @@ def test_wgrad_tc_matches_fp64(R, Ci, Co):
     db = torch.zeros(Co, device="cuda")
     call("tn_colsum", ptr(dz_d), ptr(db), R, Co)
     assert rel(db, dz.double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("B,T,C,Co,K,lazy,p", [(8, 301, 256, 256, 3, True, 0.0), (5, 77, 128, 256, 7, True, 0.0), (3, 120, 256, 128, 11, True, 0.0),
+                                                (8, 301, 256, 256, 3, False, 0.0), (4, 100, 128, 128, 1, True, 0.0), (6, 301, 256, 256, 3, True, 0.1)])
+def test_fused_dgrad_depthwise_backward(B, T, C, Co, K, lazy, p):
+    """DwPw (depthwise-separable block): fused tensor-core backward == unfused kernels == fp64 torch."""
+    import torch.nn.functional as F
+    from titanet_b200 import _ops as ops
+    g = torch.Generator().manual_seed(B * T + C + K)
+    R = B * T
+    z = torch.randn(R, C, generator=g)
+    sc, sh = 0.5 + torch.rand(C, generator=g), 0.3 * torch.randn(C, generator=g)
+    dw_w, dw_b = torch.randn(C, 1, K, generator=g) / math.sqrt(K), torch.randn(C, generator=g)
+    pw_w, pw_b = torch.randn(Co, C, 1, generator=g) / math.sqrt(C), torch.randn(Co, generator=g)
+    gy = torch.randn(R, Co, generator=g)
+    seed = torch.tensor([77], dtype=torch.int64, device="cuda")
+    res = []
+    for fused in (True, False):
+        ops.TC_FUSE_DWBWD = fused
+        t = [x.clone().cuda().requires_grad_(True) for x in (z, sc, sh, dw_w, dw_b, pw_w, pw_b)]
+        zo, st = ops.DwPw.apply(t[0], t[1] if lazy else None, t[2] if lazy else None, t[3], t[4], t[5], t[6], seed if p > 0 else None,
+                                True, p, 5, B, T, True)
+        (zo * gy.cuda()).sum().backward()
+        res.append([zo.detach()] + [x.grad for x in t if x.grad is not None])
+    ops.TC_FUSE_DWBWD = True
+    for a, b in zip(*res):
+        assert rel(a, b) < 2e-3           # weight gradients use plain-TF32 operands in both paths; the rest agrees to ~1e-5
+    for i in (0, 1):                      # z_out and dz_prev: 3xTF32 in both paths
+        assert rel(res[0][i], res[1][i]) < 2e-5
+    if p == 0.0:
+        zr, scr, shr, dwr, dbr, pwr, pbr = (x.double().clone().requires_grad_(True) for x in (z, sc, sh, dw_w, dw_b, pw_w, pw_b))
+        zz = zr.view(B, T, C).permute(0, 2, 1)
+        a = torch.relu(zz * scr.view(1, -1, 1) + shr.view(1, -1, 1)) if lazy else zz
+        u = F.conv1d(F.pad(a, (K // 2, K // 2)), dwr, dbr, groups=C)
+        zo_r = F.conv1d(u, pwr, pbr).permute(0, 2, 1).reshape(R, Co)
+        (zo_r * gy.double()).sum().backward()
+        ref = [zo_r.detach(), zr.grad] + ([scr.grad, shr.grad] if lazy else []) + [dwr.grad, dbr.grad, pwr.grad, pbr.grad]
+        tols = [1e-5, 2e-5] + ([1e-4, 1e-4] if lazy else []) + [1e-4, 1e-4, 2e-3, 1e-4]
+        for a_, r_, tol in zip(res[0], ref, tols):
+            assert rel(a_, r_) < tol

@@ -315,6 +315,67 @@ class Depthwise(Function):
         return dz, dscale, dshift, dw, db, None, None, None, None, None, None
 
 
+TC_FUSE_DWBWD = True
+
+
+class DwPw(Function):
+    """Depthwise-separable convolution on a lazy activation, with the following BatchNorm's
+    statistics:  z_out = pointwise(depthwise_K(act(z)) + b_dw) + b_pw  (modules.DepthwiseConv1d,
+    src/modules.py:64-79).  Backward runs the pointwise data-gradient GEMM and the whole depthwise /
+    BN-ReLU-dropout backward of the previous layer as ONE tensor-core kernel (tn_gemm_tc_dwbwd)."""
+
+    @staticmethod
+    def forward(ctx, z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, relu: bool, p: float, layer: int, B: int, T: int,
+                want_stats: bool):
+        z, scale, shift, dw_w, dw_b, pw_w, pw_b = map(_c, (z, scale, shift, dw_w, dw_b, pw_w, pw_b))
+        C, K = dw_w.shape[0], dw_w.shape[-1]
+        Co = pw_w.shape[0]
+        assert z.shape == (B * T, C)
+        u = empty(z.shape, z)
+        call("tn_dw_fwd", ptr(z), ptr(u), ptr(dw_w), ptr(dw_b), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer),
+             B, T, C, K)
+        zo = empty((B * T, Co), z)
+        stats = zeros((2 * Co,), z, torch.float64) if want_stats else None
+        _gemm_fwd(u, pw_w if pw_w.dim() == 3 else pw_w.unsqueeze(-1), pw_b, zo, stats, B, T, 0, 0)
+        ctx.save_for_backward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, u, zo if want_stats else None)
+        ctx.meta = (relu, p, layer, B, T, want_stats)
+        return zo, stats
+
+    @staticmethod
+    def backward(ctx, dzo, dstats):
+        z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, u, zo = ctx.saved_tensors
+        relu, p, layer, B, T, want_stats = ctx.meta
+        C, K = dw_w.shape[0], dw_w.shape[-1]
+        pw3 = pw_w if pw_w.dim() == 3 else pw_w.unsqueeze(-1)
+        Co, R = pw3.shape[0], B * T
+        dz = _c(dzo) if dzo is not None else zeros((R, Co), z)
+        db_pw = zeros((Co,), z) if pw_b is not None else None
+        db_done = False
+        if want_stats and dstats is not None:
+            g = empty(dz.shape, dz)
+            call("tn_stats_bwd", ptr(dz), ptr(zo), ptr(dstats.contiguous()), ptr(g), ptr(db_pw), R, Co)
+            dz, db_done = g, True
+        dpw = zeros(pw_w.shape, pw_w)
+        _gemm_wgrad(dz, u, dpw if dpw.dim() == 3 else dpw.unsqueeze(-1), None if db_done else db_pw, B, T)
+        dzp = empty(z.shape, z)
+        ddw = zeros(dw_w.shape, dw_w)
+        ddb = zeros((C,), z) if dw_b is not None else None
+        dscale = zeros((C,), z) if scale is not None else None
+        dshift = zeros((C,), z) if scale is not None else None
+        if TC_ENABLED and TC_FUSE_DWBWD and R >= TC_MIN_ROWS and Co % 32 == 0 and C % 128 == 0 and K % 2 == 1 and K <= 15:
+            ws = torch.empty((2, C, Co), device=z.device, dtype=torch.float32)
+            call("tn_split_tf32", ptr(pw3), ptr(ws), C, Co, 1)
+            call("tn_gemm_tc_dwbwd", ptr(dz), ptr(ws), ptr(z), ptr(dzp), ptr(dw_w), ptr(ddw), ptr(ddb), ptr(dscale), ptr(dshift),
+                 ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer), B, T, Co, C, K, TC_BWD_NSPLIT,
+                 tag=f"dgrad+dwbwd R{R} Ci{Co} Co{C} K1")
+        else:
+            du = empty(z.shape, z)
+            _gemm_fwd(dz, pw3, None, du, None, B, T, 1, 0)
+            call("tn_dw_bwd", ptr(du), ptr(z), ptr(dzp), ptr(dw_w), ptr(ddw), ptr(ddb), ptr(dscale), ptr(dshift), ptr(scale),
+                 ptr(shift), int(relu), float(p), ptr(seed), int(layer), B, T, C, K)
+        return dzp, dscale, dshift, ddw, ddb, dpw, db_pw, None, None, None, None, None, None, None
+
+
 # ----------------------------------------------------------------------------
 # squeeze-excitation + mega-block tail
 # ----------------------------------------------------------------------------

@@ -80,18 +80,20 @@ static inline TnAct tn_make_act(const float* scale, const float* shift, int relu
 }
 
 #ifdef __CUDACC__
-// Philox4x32-10 counter RNG (Salmon et al. 2011): stateless, so forward and
-// backward regenerate the same dropout mask from (seed, layer, element index).
-__device__ __forceinline__ uint4 tn_philox(uint32_t k0, uint32_t k1, uint4 c) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  return c;
+// Counter-based dropout RNG: one 32-bit hash per ELEMENT of (step seed, layer id, element
+// index) -- a seeded multiply-xorshift finaliser ("lowbias32").  Stateless, so forward and
+// backward regenerate the same mask, and any thread can ask for any element (the tensor-core
+// epilogues own one channel per thread, the row-tiled kernels four).
+__device__ __forceinline__ uint32_t tn_hash_elem(uint32_t seed_lo, uint32_t seed_hi, uint32_t layer, unsigned long long idx) {
+  uint32_t h = (uint32_t)idx * 0x9E3779B1u ^ seed_lo;
+  h ^= (uint32_t)(idx >> 32) * 0xC2B2AE3Du + layer * 0x85EBCA77u + seed_hi;
+  h ^= h >> 16; h *= 0x21F0AAADu;
+  h ^= h >> 15; h *= 0x735A2D97u;
+  h ^= h >> 15;
+  return h;
 }
+// keep-multiplier (0 or inv_keep) of element `idx` (= row * C + channel)
+__device__ __forceinline__ float tn_drop1(const struct TnAct& a, unsigned long long idx);
 
 // load the step seed once per thread (kernel parameters are read-only: work on a copy)
 __device__ __forceinline__ TnAct tn_act_init(TnAct a) {
@@ -105,9 +107,24 @@ __device__ __forceinline__ TnAct tn_act_init(TnAct a) {
 // keep-multipliers (0 or inv_keep) for the 4 consecutive elements of quad `qidx`
 __device__ __forceinline__ float4 tn_drop4(const TnAct& a, unsigned long long qidx) {
   if (a.thresh == 0) return make_float4(1.f, 1.f, 1.f, 1.f);
-  uint4 r = tn_philox(a.seed_lo, a.seed_hi, make_uint4((uint32_t)qidx, (uint32_t)(qidx >> 32), a.layer, 0x7174u));
-  return make_float4(r.x >= a.thresh ? a.inv_keep : 0.f, r.y >= a.thresh ? a.inv_keep : 0.f,
-                     r.z >= a.thresh ? a.inv_keep : 0.f, r.w >= a.thresh ? a.inv_keep : 0.f);
+  const unsigned long long e = qidx << 2;
+  return make_float4(tn_hash_elem(a.seed_lo, a.seed_hi, a.layer, e) >= a.thresh ? a.inv_keep : 0.f,
+                     tn_hash_elem(a.seed_lo, a.seed_hi, a.layer, e + 1) >= a.thresh ? a.inv_keep : 0.f,
+                     tn_hash_elem(a.seed_lo, a.seed_hi, a.layer, e + 2) >= a.thresh ? a.inv_keep : 0.f,
+                     tn_hash_elem(a.seed_lo, a.seed_hi, a.layer, e + 3) >= a.thresh ? a.inv_keep : 0.f);
+}
+__device__ __forceinline__ float tn_drop1(const TnAct& a, unsigned long long idx) {
+  if (a.thresh == 0) return 1.f;
+  return tn_hash_elem(a.seed_lo, a.seed_hi, a.layer, idx) >= a.thresh ? a.inv_keep : 0.f;
+}
+// scalar lazy activation of element (row, c): returns a, *mult = d a / d pre
+__device__ __forceinline__ float tn_act1(const TnAct& a, float z, int c, unsigned long long idx, float* mult) {
+  if (a.scale == nullptr) { *mult = 1.f; return z; }
+  const float v = fmaf(z, __ldg(a.scale + c), __ldg(a.shift + c));
+  float m = tn_drop1(a, idx);
+  if (a.relu && !(v > 0.f)) m = 0.f;
+  *mult = m;
+  return v * m;
 }
 
 // a = act(z) for one channel quad; `mult` (optional) receives d a / d pre, i.e. the

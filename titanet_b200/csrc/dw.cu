@@ -146,9 +146,11 @@ __global__ void __launch_bounds__(DW_THREADS, (K <= 5 ? 2 : 1)) dw_bwd_kernel(co
   }
 }
 
+#include <stdlib.h>
 static int dw_rows_per_block(int C, int K) {
   int Q = C / 4, qpb = Q < DW_THREADS ? Q : DW_THREADS, lanes = DW_THREADS / qpb;
   int run = K <= 5 ? 8 : 16;
+  if (const char* e = getenv("TN_DW_RUN")) run = atoi(e) > 0 ? atoi(e) : run;      // tuning knob
   return lanes * run;
 }
 

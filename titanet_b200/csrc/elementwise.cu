@@ -46,7 +46,9 @@ extern "C" int tn_zero(void* p, size_t bytes, void* stream) {
 }
 
 // rows per block for the row-tiled kernels: aim at >= 4 waves of 8 blocks/SM
+#include <stdlib.h>
 static int rows_per_block(long long R) {
+  if (const char* e = getenv("TN_EW_RPB")) if (atoi(e) > 0) return atoi(e);             // tuning knob
   long long target = (long long)tn_num_sms() * 4;      // few, fat blocks: every block ends in per-channel atomics
   long long rpb = (R + target - 1) / target;
   if (rpb < 32) rpb = 32;

@@ -25,6 +25,7 @@
 // (src/models.py:384) and the ASP linears (src/models.py:549-551).
 #include "common.cuh"
 #include <cuda.h>
+#include <string.h>
 
 #define TC_THREADS 192
 #define TC_BK 32              // fp32 elements per K chunk = one 128-byte swizzle row
@@ -145,7 +146,92 @@ struct TcParams {
   double* stats;
   int R, Kd, M_total, BN, stages, nsplit, flags, tmem_cols;
   long long* trace;      // optional timeline buffer (debug): 128 slots per traced CTA
+  // fused depthwise-backward epilogue (dw_K > 0): this GEMM is the data gradient of a pointwise conv
+  // whose input was depthwise_K(act(zprev)); the epilogue turns du (in TMEM) into dzprev directly.
+  int dw_K, dw_T, BNo;   // taps, frames per utterance, output rows per CTA (BN = BNo + halo)
+  const float* dw_w;     // [C, K]
+  const float* zprev;    // [R, C]
+  float* dzprev;         // [R, C]
+  float* g_dw;           // [C, K]   ACCUMULATED
+  float* g_db;           // [C]      ACCUMULATED
+  float* g_dscale;       // [C]      ACCUMULATED (act only)
+  float* g_dshift;       // [C]      ACCUMULATED (act only)
+  TnAct act;
 };
+
+// Epilogue for the fused depthwise backward.  The accumulator tile holds du[c, j] for the rows
+// n0 + j (n0 = first output row - PAD: the tile carries a PAD-row halo on both sides, recomputed
+// by the neighbouring CTAs).  One thread owns channel c, so the transposed depthwise conv walks
+// along its own TMEM columns and every per-channel reduction (d scale, d shift, d dw weights,
+// d dw bias) is a thread-local sum; z of the previous layer is read once, coalesced across lanes.
+// Reference: autograd of DepthwiseConv1d's first conv + BatchNorm/ReLU/Dropout
+// (src/modules.py:64-75, 128-133) as reached by loss.backward() (src/learn.py:117).
+template <int K>
+__device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams& p, const TnAct& act, int c, int n0) {
+  constexpr int PAD = K / 2;
+  const int C = p.M_total, T = p.dw_T, R = p.R;
+  float w[K], a_w[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { w[k] = __ldg(p.dw_w + (size_t)c * K + k); a_w[k] = 0.f; }
+  const float sc = act.scale ? __ldg(act.scale + c) : 1.f;
+  float a_sc = 0.f, a_sh = 0.f, a_b = 0.f;
+  const int r_first = n0 + PAD;
+  const int nout = min(p.BNo, R - r_first);
+  for (int o0 = 0; o0 < p.BNo; o0 += 16) {
+    float v[32];
+    tc_ld16_issue(tbase + o0, v);
+    if (PAD > 0) tc_ld16_issue(tbase + o0 + 16, v + 16);
+    // activation window of the previous layer: rows n0 + o0 + jj, jj in [0, 16 + 2 PAD)
+    float av[16 + 2 * PAD], zc[16], mv[16];
+#pragma unroll
+    for (int jj = 0; jj < 16 + 2 * PAD; ++jj) {
+      const int row = n0 + o0 + jj;
+      const bool valid = row >= 0 && row < R;
+      const size_t idx = (size_t)(valid ? row : 0) * C + c;
+      const float zz = valid ? __ldg(p.zprev + idx) : 0.f;
+      float m;
+      const float a = tn_act1(act, zz, c, idx, &m);
+      av[jj] = valid ? a : 0.f;
+      if (jj >= PAD && jj < PAD + 16) { zc[jj - PAD] = zz; mv[jj - PAD] = m; }
+    }
+    tc_ld_wait(v, 32);
+    const int t0 = (r_first + o0) % T;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const bool ok = o0 + i < nout;
+      int t = t0 + i;
+      t = t >= T ? t % T : t;
+      const float g0 = v[i + PAD];
+      float da = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        // forward: u[r'] += w[k] * a[r' + k - PAD]  =>  a[r] feeds u[r + PAD - k]
+        const int tu = t + PAD - k;
+        if (tu >= 0 && tu < T) da = fmaf(w[k], v[i + 2 * PAD - k], da);
+        const int ta = t + k - PAD;
+        if (ok && ta >= 0 && ta < T) a_w[k] = fmaf(g0, av[i + k], a_w[k]);
+      }
+      if (ok) {
+        a_b += g0;
+        float out = da;
+        if (act.scale) {
+          const float g = da * mv[i];
+          a_sc = fmaf(g, zc[i], a_sc);
+          a_sh += g;
+          out = g * sc;
+        }
+        p.dzprev[(size_t)(r_first + o0 + i) * C + c] = out;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) atomicAdd(p.g_dw + (size_t)c * K + k, a_w[k]);
+  if (p.g_db) atomicAdd(p.g_db + c, a_b);
+  if (act.scale) {
+    atomicAdd(p.g_dscale + c, a_sc);
+    atomicAdd(p.g_dshift + c, a_sh);
+  }
+}
 #define TC_TRACE(slot) do { if (p.trace && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && blockIdx.y == 0) \
     p.trace[(blockIdx.x == 0 ? 0 : 128) + (slot)] = clock64(); } while (0)
 
@@ -167,7 +253,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (threadIdx.x == 0 && p.trace && blockIdx.y == 0 && blockIdx.x < 256) {
     unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[256 + 2 * blockIdx.x] = (long long)gt; }
   const int BN = p.BN, S = p.stages;
-  const int n0 = blockIdx.x * BN;                    // first activation row of this CTA
+  // first activation row of this CTA's tile (fused depthwise backward: the tile starts PAD rows early;
+  // TMA zero-fills rows < 0 and >= R)
+  const int n0 = p.dw_K > 0 ? blockIdx.x * p.BNo - (p.dw_K >> 1) : blockIdx.x * BN;
   const int m0 = blockIdx.y * (128 * MT);            // first output channel of this CTA
   const int num_kc = p.Kd / TC_BK;
   const bool split = p.nsplit == 3;
@@ -289,6 +377,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     tc_fence_after();
     const int quad = warp & 3;               // TMEM lanes 32*quad .. 32*quad+31 belong to this warp
     const int nvalid = min(BN, p.R - n0);                       // rows of this tile inside the tensor
+    if (p.dw_K > 0) {
+      const TnAct act = tn_act_init(p.act);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int c = m0 + mt * 128 + quad * 32 + lane;
+        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 256);
+        switch (p.dw_K) {
+          case 1: tc_epilogue_dwbwd<1>(tbase, p, act, c, n0); break;
+          case 3: tc_epilogue_dwbwd<3>(tbase, p, act, c, n0); break;
+          case 5: tc_epilogue_dwbwd<5>(tbase, p, act, c, n0); break;
+          case 7: tc_epilogue_dwbwd<7>(tbase, p, act, c, n0); break;
+          case 9: tc_epilogue_dwbwd<9>(tbase, p, act, c, n0); break;
+          case 11: tc_epilogue_dwbwd<11>(tbase, p, act, c, n0); break;
+          case 13: tc_epilogue_dwbwd<13>(tbase, p, act, c, n0); break;
+          default: tc_epilogue_dwbwd<15>(tbase, p, act, c, n0); break;
+        }
+      }
+    } else
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       const int co = m0 + mt * 128 + quad * 32 + lane;
@@ -564,26 +670,27 @@ extern "C" int tn_split_tf32(const float* W, float* ws, int M, int Kd, int trans
   return TN_OK;
 }
 
-static int pick_bn(long long R, int groups, int per_row_stage_bytes, int fixed_stage_bytes, int* stages_out) {
+// rows of output per CTA: the multiple of 16 that minimises waves * (tile rows + fixed cost).
+// `halo` extra MMA columns ride along (fused depthwise backward).
+static int pick_bn(long long R, int groups, int per_row_stage_bytes, int fixed_stage_bytes, int halo, int* stages_out) {
   const int sms = tn_num_sms();
   int best = 0;
   double best_cost = 1e30;
-  for (int bn = 256; bn >= 32; bn -= 16) {
-    long long stage = (long long)fixed_stage_bytes + (long long)bn * per_row_stage_bytes;
+  for (int bn = 256 - halo; bn >= 32; bn -= 16) {
+    long long stage = (long long)fixed_stage_bytes + (long long)(bn + halo) * per_row_stage_bytes;
     int stages = (int)((TC_SMEM_LIMIT - 2048) / stage);
     if (stages < 2) continue;
     long long ctas = ((R + bn - 1) / bn) * groups;
     long long waves = (ctas + sms - 1) / sms;
-    double cost = (double)waves * (bn + 24);
+    double cost = (double)waves * (bn + halo + 24);
     if (cost < best_cost) { best_cost = cost; best = bn; *stages_out = stages > TC_MAX_STAGES ? TC_MAX_STAGES : stages; }
   }
   return best;
 }
 
-// ws: the split weights from tn_split_tf32 (hi | lo), [2, M, Kd].  nsplit 3 = fp32-equivalent, 1 = plain TF32.
-extern "C" int tn_gemm_tc(const float* X, const float* ws, const float* bias, float* Z, double* stats, int R, int Kd, int M,
-                          int flags, int nsplit, void* stream) {
-  TN_REQUIRE(X && ws && Z, "gemm_tc: null tensor");
+// common launcher: p carries the epilogue configuration; shapes / tiles / maps are filled here
+static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, int Kd, int M, int nsplit, void* stream) {
+  TN_REQUIRE(X && ws, "gemm_tc: null tensor");
   TN_REQUIRE(tn_gemm_tc_supported(R, Kd, M), "gemm_tc: unsupported shape R=%d K=%d M=%d (need K %% 32 == 0, M %% 128 == 0)", R, Kd, M);
   TN_REQUIRE(nsplit == 1 || nsplit == 3, "gemm_tc: nsplit must be 1 or 3");
   TN_REQUIRE(tn_aligned16(X) && tn_aligned16(ws), "gemm_tc: operands must be 16B aligned");
@@ -592,23 +699,23 @@ extern "C" int tn_gemm_tc(const float* X, const float* ws, const float* bias, fl
   const int MT = (M % 256 == 0) ? 2 : 1;
   const int groups = M / (128 * MT);
   const int mult = nsplit == 3 ? 2 : 1;
+  const int halo = p.dw_K > 1 ? 16 : 0;              // 2 * PAD <= 14 rows of halo, rounded to the MMA's N granularity
   int stages = 2;
-  const int bn = pick_bn(R, groups, mult * TC_BK * 4, mult * MT * 128 * TC_BK * 4, &stages);
-  TN_REQUIRE(bn >= 32, "gemm_tc: no tile configuration fits shared memory");
+  const int bno = pick_bn(R, groups, mult * TC_BK * 4, mult * MT * 128 * TC_BK * 4, halo, &stages);
+  TN_REQUIRE(bno >= 32, "gemm_tc: no tile configuration fits shared memory");
+  const int bn = bno + halo;
   CUtensorMap mA_hi, mA_lo, mB;
   if ((rc = make_map(&mA_hi, ws, M, Kd, 128)) != TN_OK) return rc;
   if ((rc = make_map(&mA_lo, ws + (size_t)M * Kd, M, Kd, 128)) != TN_OK) return rc;
   if ((rc = make_map(&mB, X, R, Kd, bn)) != TN_OK) return rc;
-  TcParams p;
-  p.bias = bias; p.Z = Z; p.stats = stats; p.R = R; p.Kd = Kd; p.M_total = M; p.BN = bn; p.stages = stages; p.nsplit = nsplit;
-  p.flags = flags;
+  p.R = R; p.Kd = Kd; p.M_total = M; p.BN = bn; p.BNo = bno; p.stages = stages; p.nsplit = nsplit;
   p.trace = g_trace;
   int cols = MT == 2 ? 512 : 32;
   while (MT == 1 && cols < bn) cols <<= 1;
   p.tmem_cols = cols;
   const size_t stage_bytes = (size_t)mult * (MT * 128 * TC_BK * 4 + (size_t)bn * TC_BK * 4);
   const size_t smem = stage_bytes * stages + 1024;
-  dim3 grid(tn_cdiv(R, bn), groups);
+  dim3 grid(tn_cdiv(R, bno), groups);
   if (MT == 2) {
     TN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm_tc_kernel<2><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB, p);
@@ -618,4 +725,37 @@ extern "C" int tn_gemm_tc(const float* X, const float* ws, const float* bias, fl
   }
   TN_LAUNCH_CHECK("gemm_tc_kernel");
   return TN_OK;
+}
+
+// ws: the split weights from tn_split_tf32 (hi | lo), [2, M, Kd].  nsplit 3 = fp32-equivalent, 1 = plain TF32.
+extern "C" int tn_gemm_tc(const float* X, const float* ws, const float* bias, float* Z, double* stats, int R, int Kd, int M,
+                          int flags, int nsplit, void* stream) {
+  TN_REQUIRE(Z, "gemm_tc: null output");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = bias; p.Z = Z; p.stats = stats; p.flags = flags;
+  return launch_gemm_tc(X, ws, p, R, Kd, M, nsplit, stream);
+}
+
+// Data gradient of a depthwise-separable conv block in one kernel:
+//   du = dZ[R, Co] W[Co, C]            (tensor cores; ws = tn_split_tf32(W, transpose = 1), [2, C, Co])
+//   dzprev = act'(zprev) * scale * depthwise_K^T(du),   dw += ..., dbias += ..., dscale += ..., dshift += ...
+// i.e. tn_gemm_tc(dgrad) followed by tn_dw_bwd, without du ever leaving the SM.  scale == NULL: zprev is
+// already the activation (first sub-block of a mega-block) and dzprev is the gradient w.r.t. it.
+extern "C" int tn_gemm_tc_dwbwd(const float* dZ, const float* ws, const float* zprev, float* dzprev, const float* dw_w,
+                                float* g_dw, float* g_dbias, float* g_dscale, float* g_dshift, const float* scale,
+                                const float* shift, int relu, float drop_p, const unsigned long long* seed,
+                                unsigned int layer, int B, int T, int Co, int C, int K, int nsplit, void* stream) {
+  TN_REQUIRE(zprev && dzprev && dw_w && g_dw, "gemm_tc_dwbwd: null tensor");
+  TN_REQUIRE(K >= 1 && K <= 15 && (K & 1), "gemm_tc_dwbwd: unsupported depthwise kernel size %d (odd sizes 1..15)", K);
+  TN_REQUIRE(!scale || (shift && g_dscale && g_dshift), "gemm_tc_dwbwd: scale given without shift/dscale/dshift");
+  TN_REQUIRE(drop_p <= 0.f || seed, "gemm_tc_dwbwd: dropout needs a seed");
+  long long R = (long long)B * T;
+  TN_REQUIRE(B > 0 && T > 0 && R < (1ll << 31), "gemm_tc_dwbwd: bad B/T");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.dw_K = K; p.dw_T = T; p.dw_w = dw_w; p.zprev = zprev; p.dzprev = dzprev;
+  p.g_dw = g_dw; p.g_db = g_dbias; p.g_dscale = g_dscale; p.g_dshift = g_dshift;
+  p.act = tn_make_act(scale, shift, relu, drop_p, seed, layer);
+  return launch_gemm_tc(dZ, ws, p, (int)R, Co, C, nsplit, stream);
 }

@@ -139,8 +139,8 @@ class DepthwiseConv1d(nn.Module):
     def _fwd(self, x: Lazy, want_stats: bool = False):
         dw, pw = self.conv[0], self.conv[1]
         _check_conv_supported(dw)
-        u = ops.Depthwise.apply(x.z, x.scale, x.shift, dw.weight, dw.bias, x.seed, x.relu, x.p, x.layer, x.B, x.T)
-        return ops.conv_gemm(u, pw.weight, pw.bias, x.B, x.T, want_stats=want_stats)
+        return ops.DwPw.apply(x.z, x.scale, x.shift, dw.weight, dw.bias, pw.weight, pw.bias, x.seed, x.relu, x.p, x.layer,
+                              x.B, x.T, want_stats)
 
     def forward(self, inputs):
         x = Lazy.from_ncw(inputs)
