@@ -27,7 +27,9 @@
 #include <cuda.h>
 #include <string.h>
 
-#define TC_THREADS 192
+#define TC_THREADS 192        // wgrad kernel: TMA + MMA + 4 epilogue warps
+#define TC_GEMM_THREADS 320   // GEMM kernel: TMA + MMA + 8 transform/epilogue warps (two per TMEM lane quadrant)
+#define TC_EPI_THREADS 256
 #define TC_BK 32              // fp32 elements per K chunk = one 128-byte swizzle row
 #define TC_MAX_STAGES 4
 #define TC_SMEM_LIMIT (227 * 1024)
@@ -116,8 +118,8 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
 // Rows >= nvalid (tail tile) are masked by predication, not branches.
 template <bool TANH, bool ACCUM, bool FULL>
 __device__ __forceinline__ void tc_epilogue(uint32_t tbase, float* __restrict__ zp, size_t ld, int BN, int nvalid, float bv,
-                                            float& s1, float& s2) {
-  for (int c0 = 0; c0 < BN; c0 += 32) {
+                                            float& s1, float& s2, int half) {
+  for (int c0 = 32 * half; c0 < BN; c0 += 64) {      // the two warps of a lane quadrant alternate 32-column chunks
     float v[32];
     const bool two = c0 + 16 < BN;                   // BN is a multiple of 16
     tc_ld16_issue(tbase + c0, v);
@@ -167,35 +169,80 @@ struct TcParams {
 // Reference: autograd of DepthwiseConv1d's first conv + BatchNorm/ReLU/Dropout
 // (src/modules.py:64-75, 128-133) as reached by loss.backward() (src/learn.py:117).
 template <int K>
-__device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams& p, const TnAct& act, int c, int n0) {
+__device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams& p, const TnAct& act, int c, int n0, int half) {
   constexpr int PAD = K / 2;
   const int C = p.M_total, T = p.dw_T, R = p.R;
   float w[K], a_w[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) { w[k] = __ldg(p.dw_w + (size_t)c * K + k); a_w[k] = 0.f; }
-  const float sc = act.scale ? __ldg(act.scale + c) : 1.f;
+  const bool lazy = act.scale != nullptr;
+  const float sc = lazy ? __ldg(act.scale + c) : 1.f;
+  const float sh = lazy ? __ldg(act.shift + c) : 0.f;
   float a_sc = 0.f, a_sh = 0.f, a_b = 0.f;
   const int r_first = n0 + PAD;
   const int nout = min(p.BNo, R - r_first);
-  for (int o0 = 0; o0 < p.BNo; o0 += 16) {
+  constexpr int W = 16 + 2 * PAD;                    // rows of the previous layer needed per 16 outputs
+  // z window of the previous layer: rows n0 + o0 + jj.  All loads of a chunk are issued back to back
+  // (no control flow in between) and the next chunk's window is prefetched while this one is
+  // processed: only four warps run this epilogue, so the latency has to be hidden by ILP.
+  float zn[W];
+  auto load_window = [&](int o0) {
+#pragma unroll
+    for (int jj = 0; jj < W; ++jj) {
+      const int row = n0 + o0 + jj;
+      const bool valid = row >= 0 && row < R && o0 < p.BNo;
+      zn[jj] = valid ? __ldg(p.zprev + (size_t)row * C + c) : 0.f;
+    }
+  };
+  load_window(16 * half);
+  for (int o0 = 16 * half; o0 < p.BNo; o0 += 32) {   // the two warps of a lane quadrant alternate 16-row chunks
     float v[32];
     tc_ld16_issue(tbase + o0, v);
     if (PAD > 0) tc_ld16_issue(tbase + o0 + 16, v + 16);
-    // activation window of the previous layer: rows n0 + o0 + jj, jj in [0, 16 + 2 PAD)
-    float av[16 + 2 * PAD], zc[16], mv[16];
+    float zw[W];
 #pragma unroll
-    for (int jj = 0; jj < 16 + 2 * PAD; ++jj) {
+    for (int jj = 0; jj < W; ++jj) zw[jj] = zn[jj];
+    load_window(o0 + 32);                            // prefetch (predicated off past the last chunk)
+    float av[W], zc[16], mv[16];
+#pragma unroll
+    for (int jj = 0; jj < W; ++jj) {
       const int row = n0 + o0 + jj;
       const bool valid = row >= 0 && row < R;
-      const size_t idx = (size_t)(valid ? row : 0) * C + c;
-      const float zz = valid ? __ldg(p.zprev + idx) : 0.f;
-      float m;
-      const float a = tn_act1(act, zz, c, idx, &m);
+      float a = zw[jj], m = 1.f;
+      if (lazy) {
+        const float pre = fmaf(zw[jj], sc, sh);
+        m = tn_drop1(act, (unsigned long long)(valid ? row : 0) * C + c);
+        m = (act.relu && !(pre > 0.f)) ? 0.f : m;
+        a = pre * m;
+      }
       av[jj] = valid ? a : 0.f;
-      if (jj >= PAD && jj < PAD + 16) { zc[jj - PAD] = zz; mv[jj - PAD] = m; }
+      if (jj >= PAD && jj < PAD + 16) { zc[jj - PAD] = zw[jj]; mv[jj - PAD] = m; }
     }
     tc_ld_wait(v, 32);
     const int t0 = (r_first + o0) % T;
+    if (t0 >= PAD && t0 + 15 + PAD < T && o0 + 16 <= nout) {
+      // the whole chunk lies inside one utterance and inside the tensor: no boundary tests
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float g0 = v[i + PAD];
+        float da = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          da = fmaf(w[k], v[i + 2 * PAD - k], da);
+          a_w[k] = fmaf(g0, av[i + k], a_w[k]);
+        }
+        a_b += g0;
+        float out = da;
+        if (lazy) {
+          const float g = da * mv[i];
+          a_sc = fmaf(g, zc[i], a_sc);
+          a_sh += g;
+          out = g * sc;
+        }
+        p.dzprev[(size_t)(r_first + o0 + i) * C + c] = out;
+      }
+      continue;
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const bool ok = o0 + i < nout;
@@ -239,7 +286,7 @@ __device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams
 // kernel: MT = number of 128-row output-channel tiles per CTA (1 or 2)
 // ---------------------------------------------------------------------------
 template <int MT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -275,7 +322,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full0 + 8 * s, 1);
-      mbar_init(ready0 + 8 * s, 128);
+      mbar_init(ready0 + 8 * s, TC_EPI_THREADS);
       mbar_init(empty0 + 8 * s, 1);
     }
     mbar_init(accum_bar, 1);
@@ -350,7 +397,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else {
     // ===== transform warps (split only), then epilogue =====
-    const int tid = threadIdx.x - 64;        // 0..127
+    const int tid = threadIdx.x - 64;        // 0..255
     if (split) {
       const int n4 = BN * TC_BK / 4;
       for (int kc = 0; kc < num_kc; ++kc) {
@@ -358,7 +405,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait(full0 + 8 * s, (kc / S) & 1);
         float4* hi = reinterpret_cast<float4*>(b_hi(s));
         float4* lo = reinterpret_cast<float4*>(b_lo(s));
-        for (int i = tid; i < n4; i += 128) {
+        for (int i = tid; i < n4; i += TC_EPI_THREADS) {
           const float4 v = hi[i];
           uint4 h, l;
           h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
@@ -376,6 +423,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (tid == 0) TC_TRACE(100);
     tc_fence_after();
     const int quad = warp & 3;               // TMEM lanes 32*quad .. 32*quad+31 belong to this warp
+    const int half = (warp - 2) >> 2;        // 0 / 1: which of the two warps of this quadrant
     const int nvalid = min(BN, p.R - n0);                       // rows of this tile inside the tensor
     if (p.dw_K > 0) {
       const TnAct act = tn_act_init(p.act);
@@ -384,14 +432,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int c = m0 + mt * 128 + quad * 32 + lane;
         const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 256);
         switch (p.dw_K) {
-          case 1: tc_epilogue_dwbwd<1>(tbase, p, act, c, n0); break;
-          case 3: tc_epilogue_dwbwd<3>(tbase, p, act, c, n0); break;
-          case 5: tc_epilogue_dwbwd<5>(tbase, p, act, c, n0); break;
-          case 7: tc_epilogue_dwbwd<7>(tbase, p, act, c, n0); break;
-          case 9: tc_epilogue_dwbwd<9>(tbase, p, act, c, n0); break;
-          case 11: tc_epilogue_dwbwd<11>(tbase, p, act, c, n0); break;
-          case 13: tc_epilogue_dwbwd<13>(tbase, p, act, c, n0); break;
-          default: tc_epilogue_dwbwd<15>(tbase, p, act, c, n0); break;
+          case 1: tc_epilogue_dwbwd<1>(tbase, p, act, c, n0, half); break;
+          case 3: tc_epilogue_dwbwd<3>(tbase, p, act, c, n0, half); break;
+          case 5: tc_epilogue_dwbwd<5>(tbase, p, act, c, n0, half); break;
+          case 7: tc_epilogue_dwbwd<7>(tbase, p, act, c, n0, half); break;
+          case 9: tc_epilogue_dwbwd<9>(tbase, p, act, c, n0, half); break;
+          case 11: tc_epilogue_dwbwd<11>(tbase, p, act, c, n0, half); break;
+          case 13: tc_epilogue_dwbwd<13>(tbase, p, act, c, n0, half); break;
+          default: tc_epilogue_dwbwd<15>(tbase, p, act, c, n0, half); break;
         }
       }
     } else
@@ -403,11 +451,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       float* zp = p.Z + (size_t)n0 * p.M_total + co;
       float s1 = 0.f, s2 = 0.f;
       switch ((p.flags & 3) | (nvalid == BN ? 4 : 0)) {          // warp-uniform: one specialised, branch-free loop each
-        case 4: tc_epilogue<false, false, true>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2); break;
-        case 0: tc_epilogue<false, false, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2); break;
-        case TN_EPI_TANH: case TN_EPI_TANH | 4: tc_epilogue<true, false, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2); break;
-        case TN_EPI_ACCUM: case TN_EPI_ACCUM | 4: tc_epilogue<false, true, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2); break;
-        default: tc_epilogue<true, true, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2); break;
+        case 4: tc_epilogue<false, false, true>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
+        case 0: tc_epilogue<false, false, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
+        case TN_EPI_TANH: case TN_EPI_TANH | 4: tc_epilogue<true, false, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
+        case TN_EPI_ACCUM: case TN_EPI_ACCUM | 4: tc_epilogue<false, true, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
+        default: tc_epilogue<true, true, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
       }
       if (p.stats) {
         atomicAdd(p.stats + co, (double)s1);
@@ -718,10 +766,10 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   dim3 grid(tn_cdiv(R, bno), groups);
   if (MT == 2) {
     TN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<2><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB, p);
+    gemm_tc_kernel<2><<<grid, TC_GEMM_THREADS, smem, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB, p);
   } else {
     TN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<1><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB, p);
+    gemm_tc_kernel<1><<<grid, TC_GEMM_THREADS, smem, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB, p);
   }
   TN_LAUNCH_CHECK("gemm_tc_kernel");
   return TN_OK;
