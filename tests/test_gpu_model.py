@@ -68,12 +68,20 @@ def test_train_step_matches_reference(golden_dir, name):
     xg = x.cuda().requires_grad_(True)
     emb, preds, lval = model(xg, speakers=y.cuda())
     lval.backward()
-    assert rel(emb, g["emb"]) < 1e-3, "embeddings vs reference"
+    sd64 = O.synth_state_dict(spec, loss, nc, dtype=torch.float64)
+    r64 = O.titanet_step(sd64, spec, x.double(), y, loss, scale=scale, margin=margin, input_grad=True)
+    if spec.n_mega_blocks > 4:
+        # S/17 at batch 4 (my stress case, not a BASELINE config): 72 train-mode BatchNorms over a tiny batch amplify
+        # fp32 rounding so much that the reference's own fp32 forward sits ~6e-4 from its fp64 run.  Two independent
+        # fp32 evaluations can therefore differ by ~1e-3; judge against fp64 with the reference's error as yard-stick.
+        ref_err = rel(g["emb"], r64[0])
+        assert rel(emb, r64[0]) <= max(1e-3, 2.0 * ref_err), "embeddings vs fp64 oracle"
+        assert rel(emb, g["emb"]) < 2e-3, "embeddings vs reference"
+    else:
+        assert rel(emb, g["emb"]) < 1e-3, "embeddings vs reference"
     assert abs(float(lval) - float(g["loss"])) <= 1e-3 * abs(float(g["loss"])), "loss vs reference"
     assert np.array_equal(preds.cpu().numpy(), g["preds"])
     # gradients: fp64 oracle as truth, fp32 reference (golden) error as the yard-stick
-    sd64 = O.synth_state_dict(spec, loss, nc, dtype=torch.float64)
-    r64 = O.titanet_step(sd64, spec, x.double(), y, loss, scale=scale, margin=margin, input_grad=True)
     grads64, dx64 = r64[3], r64[5]
     gmax = max(float(v.abs().max()) for v in grads64.values())
     worst_ours, worst_ref = 0.0, 0.0
