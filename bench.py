@@ -172,6 +172,51 @@ def gemm_work(tag: str):
     return 2.0 * R * Ci * Co * K, 4.0 * (R * Ci + R * Co + Co * Ci * K)
 
 
+def graph_time_kernel(kind: str, R: int, Ci: int, Co: int, B: int, dropout: float, dev, reps: int = 20) -> float:
+    """Microseconds per launch of one tensor-core kernel shape, replayed back to back from a CUDA graph."""
+    import math
+    from titanet_b200._lib import call, ptr
+    T = R // B
+    rnd = lambda *s: torch.randn(*s, device=dev)
+    x, out = rnd(R, Ci), torch.empty(R, Co, device=dev)
+    w = rnd(Co, Ci) / math.sqrt(Ci)
+    ws = torch.empty(2, Co, Ci, device=dev)
+    if kind == "tn_wgrad_tc":
+        dz, dw = rnd(R, Co), torch.zeros(Co, Ci, device=dev)
+        fn = lambda: call("tn_wgrad_tc", ptr(dz), ptr(x), ptr(dw), R, Ci, Co)
+    elif kind == "tn_gemm_tc_dwbwd":
+        # tag convention: Ci = channels of dZ (reduction), Co = channels of the depthwise input
+        call("tn_split_tf32", ptr(rnd(Ci, Co) / math.sqrt(Ci)), ptr(ws), Co, Ci, 1)
+        zp, dzp = rnd(R, Co), torch.empty(R, Co, device=dev)
+        dww, ddw = rnd(Co, 1, 3), torch.zeros(Co, 3, device=dev)
+        acc = torch.zeros(3, Co, device=dev)
+        sc, sh = torch.rand(Co, device=dev) + 0.5, 0.1 * rnd(Co)
+        seed = torch.tensor([1], dtype=torch.int64, device=dev)
+        fn = lambda: call("tn_gemm_tc_dwbwd", ptr(x), ptr(ws), ptr(zp), ptr(dzp), ptr(dww), ptr(ddw), acc[0].data_ptr(),
+                          acc[1].data_ptr(), acc[2].data_ptr(), ptr(sc), ptr(sh), 1, float(dropout),
+                          ptr(seed) if dropout > 0 else None, 3, B, T, Ci, Co, 3, 3)
+    else:
+        call("tn_split_tf32", ptr(w), ptr(ws), Co, Ci, 0)
+        bias, st = rnd(Co), torch.zeros(2 * Co, dtype=torch.float64, device=dev)
+        fn = lambda: call("tn_gemm_tc", ptr(x), ptr(ws), ptr(bias), ptr(out), ptr(st), R, Ci, Co, 0, 3)
+    fn()
+    torch.cuda.synchronize()
+    g, side = torch.cuda.CUDAGraph(), torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps
+
+
 def run_ours(args):
     import torch.distributed as dist
     from titanet_b200 import _lib, losses, models, transforms
@@ -261,27 +306,34 @@ def run_ours(args):
             name = key.split("[")[0]
             gn, gms = groups.get(name, (0, 0.0))
             groups[name] = (gn + n, gms + ms)
-        top = sorted(prof.items(), key=lambda kv: -kv[1][1])
-        top_gemm = next(((k, v) for k, v in top if k.startswith("tn_conv_gemm") or k.startswith("tn_gemm")), None)
-        if top_gemm is not None:
-            key, (n, ms) = top_gemm
-            flops, byts = gemm_work(key[key.index("[") + 1:-1])
-            per_launch_s = ms / n * 1e-3
+        # The eager pass above ranks the kernels (its per-launch times include host launch gaps).  The dominant
+        # tensor-core kernel shape is then timed live WITHOUT host gaps: 20 back-to-back launches replayed from
+        # a CUDA graph, CUDA events around the replay, on the launching stream.
+        gemm_keys = [(k, v) for k, v in prof.items() if k.startswith(("tn_gemm_tc", "tn_wgrad_tc"))]
+        if gemm_keys:
+            key, (n, _) = max(gemm_keys, key=lambda kv: kv[1][1])
+            kind, tag = key.split("[")[0], key[key.index("[") + 1:-1]
+            flops, byts = gemm_work(tag)
+            f = dict((t[0] if t[0] != "C" else t[:2], int(t[1:] if t[0] != "C" else t[2:])) for t in tag.split()[1:])
+            per_launch_s = graph_time_kernel(kind, f["R"], f["Ci"], f["Co"], B, args.dropout, dev) * 1e-6
+            if kind == "tn_gemm_tc_dwbwd":          # reads dZ and z_prev, writes dz_prev (+ weights); du never leaves the SM
+                byts = 4.0 * (f["R"] * f["Ci"] + 2 * f["R"] * f["Co"] + f["Ci"] * f["Co"])
             tf32_peak = pk["bf16_tflops"] / 2.0
             ach_tf = flops / per_launch_s / 1e12
             ach_gb = byts / per_launch_s / 1e9
-            tensor_bound = (flops / byts) > (tf32_peak * 1e12 / 3.0) / (pk["hbm_gbs"] * 1e9)
-            roof = {"kernel": key, "launches_per_step": n // prof_steps, "us_per_launch": round(per_launch_s * 1e6, 2),
-                    "share_of_step": round(ms / total_ms, 4),
-                    "bound": "tensor" if tensor_bound else "hbm",
-                    "achieved": round(ach_tf if tensor_bound else ach_gb, 3),
-                    "peak": round(tf32_peak if tensor_bound else pk["hbm_gbs"], 1),
-                    "unit": "TFLOP/s" if tensor_bound else "GB/s",
-                    "frac": round((ach_tf / tf32_peak) if tensor_bound else (ach_gb / pk["hbm_gbs"]), 4),
-                    "traffic": None,
-                    "peak_source": pk["source"] + (" (dense TF32 = measured sustained bf16 / 2)" if tensor_bound else ""),
-                    "algorithmic_gb_s": round(ach_gb, 1), "algorithmic_tflop_s": round(ach_tf, 2),
-                    "by_kernel_ms_per_step": {k: round(v[1] / prof_steps, 3) for k, v in sorted(groups.items(), key=lambda kv: -kv[1][1])}}
+            launches_per_step = n // prof_steps
+            roof = {"kernel": key, "launches_per_step": launches_per_step, "us_per_launch": round(per_launch_s * 1e6, 2),
+                    "share_of_step": round(launches_per_step * per_launch_s * 1e3 / ms_step, 4),
+                    # TitaNet-S: AI = 2*R*Ci*Co / bytes ~ 64 FLOP/B < the TF32 ridge (~104 FLOP/B) -> HBM is the roofline
+                    # of the algorithm; the fp32-equivalent 3xTF32 arithmetic issues 3 MMAs per algorithmic MAC.
+                    "bound": "hbm", "achieved": round(ach_gb, 1), "peak": round(pk["hbm_gbs"], 1), "unit": "GB/s",
+                    "frac": round(ach_gb / pk["hbm_gbs"], 4), "traffic": None, "peak_source": pk["source"],
+                    "algorithmic_bytes_per_launch": byts, "algorithmic_flops_per_launch": flops,
+                    "algorithmic_tflop_s": round(ach_tf, 2), "tf32_peak_tflop_s": round(tf32_peak, 1),
+                    "tensor_frac_of_tf32_peak": round(ach_tf / tf32_peak, 4), "mma_issue_factor": 3,
+                    "timing": "CUDA events around a CUDA graph of 20 back-to-back launches of this shape",
+                    "eager_ms_per_step_by_entry_point": {k: round(v[1] / prof_steps, 3) for k, v in
+                                                         sorted(groups.items(), key=lambda kv: -kv[1][1])}}
 
     if rank != 0:
         if world > 1:

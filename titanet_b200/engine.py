@@ -48,6 +48,10 @@ class GraphedTrainStep:
             self.after_backward()
 
     def _capture(self, warmup: int):
+        try:    # warm-up runs on a side stream by design; the AccumulateGrad stream-mismatch warning is noise here
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except AttributeError:
+            pass
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
