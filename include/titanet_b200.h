@@ -93,6 +93,46 @@ int tn_wgrad_tc_supported(int R, int Ci, int Co);
 int tn_wgrad_tc(const float* dZ, const float* U, float* dW, int R, int Ci, int Co, void* stream);
 int tn_colsum(const float* x, float* out, int R, int C, void* stream);                /* out[c] += sum_r x[r,c] */
 
+/* ---- train-mode BatchNorm folded INTO its producer / consumer kernels --------------------------
+ * tn_bn_fold describes the nn.BatchNorm1d that follows a conv (src/modules.py:128, src/models.py:454,
+ * 512).  The *_bn GEMM entry points accumulate the statistics of Z in their epilogue as before; the
+ * last CTA to finish (device-wide ticket in `counter`, which must be zero on entry and is reset to zero)
+ * folds them into (scale, shift), stores (mean, invstd) for the backward pass and updates the running
+ * statistics (momentum, unbiased variance) and num_batches_tracked -- i.e. tn_bn_finalize without its
+ * launch.  n = samples per channel (B*T). */
+typedef struct tn_bn_fold {
+  const float* gamma;              /* [C] BatchNorm weight                      */
+  const float* beta;               /* [C] BatchNorm bias                        */
+  float* running_mean;             /* [C] or NULL (track_running_stats=False)   */
+  float* running_var;              /* [C] or NULL                               */
+  long long* num_batches_tracked;  /* scalar or NULL                            */
+  float momentum, eps;
+  double n;
+  float* scale;                    /* [C] out: gamma * invstd                   */
+  float* shift;                    /* [C] out: beta - mean * scale              */
+  float* mean;                     /* [C] out (saved for backward)              */
+  float* invstd;                   /* [C] out (saved for backward)              */
+  unsigned int* counter;           /* device scalar, zero on entry              */
+} tn_bn_fold;
+int tn_gemm_tc_bn(const float* X, const float* ws, const float* bias, float* Z, double* stats, const tn_bn_fold* bn, int R,
+                  int Kd, int M, int flags, int nsplit, void* stream);
+int tn_conv_gemm_simt_bn(const float* X, const float* W, const float* bias, float* Z, double* stats, const tn_bn_fold* bn,
+                         int B, int T, int Ci, int Co, int K, int flags, void* stream);
+/* Backward of conv -> train-mode BatchNorm fold in one pass over the tensor (tn_bn_bwd_coef + tn_stats_bwd):
+ * from dL/dscale, dL/dshift and the saved (mean, invstd) compute, per channel, dgamma, dbeta and the
+ * statistics-path coefficients, then out = dz_direct + a[c] + b[c] * z and dbias[c] += sum_r out
+ * (dbias ACCUMULATED; dz_direct may be NULL = 0; out may alias dz_direct). */
+int tn_bn_stats_bwd(const float* dz_direct, const float* z, const float* dscale, const float* dshift, const float* mean,
+                    const float* invstd, const float* gamma, double n, float* out, float* dbias, float* dgamma,
+                    float* dbeta, int R, int C, void* stream);
+/* every weight split of a step in ONE launch: jobs (device array) = {W, ws, M, Kd, transpose} like tn_split_tf32 */
+typedef struct tn_split_job {
+  const float* W;
+  float* ws;
+  int M, Kd, transpose, pad_;
+} tn_split_job;
+int tn_split_tf32_batch(const tn_split_job* jobs_dev, int njobs, int max_elems, void* stream);
+
 /* ---- depthwise conv with fused lazy-activation prologue:
  *      DepthwiseConv1d's first conv (src/modules.py:64-75) after BN/ReLU/Dropout
  *      (src/modules.py:128-133) ---------------------------------------------------- */

@@ -99,6 +99,21 @@ class _Lib:
             raise TitanetLibraryError(f"{name} failed (code {rc}): {self.last_error()}")
 
 
+class TnBnFold(ctypes.Structure):
+    """``tn_bn_fold`` of include/titanet_b200.h (train-mode BatchNorm folded by its producer kernel)."""
+    _fields_ = [("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p), ("running_mean", ctypes.c_void_p),
+                ("running_var", ctypes.c_void_p), ("num_batches_tracked", ctypes.c_void_p),
+                ("momentum", ctypes.c_float), ("eps", ctypes.c_float), ("n", ctypes.c_double),
+                ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p), ("mean", ctypes.c_void_p),
+                ("invstd", ctypes.c_void_p), ("counter", ctypes.c_void_p)]
+
+
+class TnSplitJob(ctypes.Structure):
+    """``tn_split_job`` of include/titanet_b200.h."""
+    _fields_ = [("W", ctypes.c_void_p), ("ws", ctypes.c_void_p), ("M", ctypes.c_int), ("Kd", ctypes.c_int),
+                ("transpose", ctypes.c_int), ("pad_", ctypes.c_int)]
+
+
 LIB = _Lib()
 _checked_device = False
 

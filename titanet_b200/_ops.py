@@ -17,7 +17,10 @@ from typing import Optional
 import torch
 from torch.autograd import Function
 
-from ._lib import LIB, call, ptr, require_cuda, stream
+import ctypes
+import weakref
+
+from ._lib import LIB, TnBnFold, TnSplitJob, call, ptr, require_cuda, stream
 
 Tensor = torch.Tensor
 EPI_TANH, EPI_ACCUM = 1, 2
@@ -40,11 +43,83 @@ def empty(shape, ref: Tensor, dtype=torch.float32) -> Tensor:
     return torch.empty(shape, device=ref.device, dtype=dtype)
 
 
+class ZeroArena:
+    """One zero-filled device buffer per step for every accumulator the kernels add into (BatchNorm
+    statistics, per-channel reductions, every parameter gradient): ``reset()`` is ONE memset, ``take``
+    carves 256-byte aligned views.  A TitaNet-S step has ~500 such buffers; as separate memset nodes
+    they cost more than the arithmetic they serve.  Used by ``engine.GraphedTrainStep`` (fixed shapes,
+    so the carve-up is identical on every step); outside an arena ``zeros`` is a plain per-tensor memset.
+
+    ``grads_only`` views handed out by ``gempty`` (fully overwritten gradients) live in the same buffer,
+    so after backward every ``p.grad`` is a view of ``self.buf`` and the data-parallel exchange can
+    all-reduce the arena in place."""
+
+    ALIGN = 256
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:      # tensors report an explicit index
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.buf: Optional[Tensor] = None
+        self.offset = 0
+        self.high_water = 0
+        self.measuring = True
+
+    def begin_step(self):
+        """Start a step: zero the arena (allocated after the first, measuring, step)."""
+        if self.buf is None and self.high_water > 0 and not self.measuring:
+            self.buf = torch.empty(self.high_water, device=self.device, dtype=torch.uint8)
+        self.offset = 0
+        if self.buf is not None:
+            LIB.call("tn_zero", self.buf.data_ptr(), self.buf.numel(), stream())
+
+    def finish_measuring(self):
+        self.measuring = False
+
+    def take(self, shape, dtype) -> Optional[Tensor]:
+        n = 1
+        for d in (shape if isinstance(shape, (tuple, list, torch.Size)) else (shape,)):
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        start = self.offset
+        self.offset = (start + nbytes + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if self.buf is None:
+            self.high_water = max(self.high_water, self.offset)
+            return None
+        if self.offset > self.buf.numel():
+            raise RuntimeError("ZeroArena overflow: the step's shapes changed after the arena was sized")
+        return self.buf[start:start + nbytes].view(dtype).view(shape)
+
+
+_ARENA: Optional[ZeroArena] = None
+
+
+def set_arena(arena: Optional[ZeroArena]) -> Optional[ZeroArena]:
+    """Install (or remove, with None) the arena ``zeros`` / ``gempty`` carve from; returns the previous one."""
+    global _ARENA
+    prev, _ARENA = _ARENA, arena
+    return prev
+
+
 def zeros(shape, ref: Tensor, dtype=torch.float32) -> Tensor:
+    if _ARENA is not None and ref.device == _ARENA.device:
+        t = _ARENA.take(shape, dtype)
+        if t is not None:
+            return t
     t = torch.empty(shape, device=ref.device, dtype=dtype)
     if t.numel():
         LIB.call("tn_zero", t.data_ptr(), t.numel() * t.element_size(), stream())
     return t
+
+
+def gempty(shape, ref: Tensor, dtype=torch.float32) -> Tensor:
+    """Uninitialised storage for a parameter gradient the kernel fully overwrites (inside the arena when
+    one is active, so that all gradients share one buffer)."""
+    if _ARENA is not None and ref.device == _ARENA.device:
+        t = _ARENA.take(shape, dtype)
+        if t is not None:
+            return t
+    return torch.empty(shape, device=ref.device, dtype=dtype)
 
 
 def seed_next(state: Tensor) -> Tensor:
@@ -106,22 +181,92 @@ def _tc_ok(R: int, Kd: int, M: int, K: int) -> bool:
     return TC_ENABLED and K == 1 and R >= TC_MIN_ROWS and Kd % 32 == 0 and M % 128 == 0
 
 
-def _gemm_tc(x, w2, bias, z, stats, R, Kd, M, transpose, flags, nsplit, tag):
-    ws = torch.empty((2, M, Kd), device=x.device, dtype=torch.float32)
-    call("tn_split_tf32", ptr(w2), ptr(ws), M, Kd, int(transpose))
-    call("tn_gemm_tc", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), R, Kd, M, flags, nsplit, tag=tag)
+class SplitCache:
+    """The tf32 (hi | lo) splits of every tensor-core weight of a model, both orientations, produced by
+    ONE kernel per step (``tn_split_tf32_batch``) into a persistent buffer instead of one tiny launch in
+    front of every GEMM (142 per TitaNet-S step).  ``refresh()`` is called at the top of the model's
+    forward; ``lookup`` is valid for weights whose ``_version`` has not moved since."""
+
+    def __init__(self, weights):
+        self.weights = [w for w in weights]
+        dev = self.weights[0].device
+        self.ptrs = [w.data_ptr() for w in self.weights]
+        jobs, self.views, off = [], {}, 0
+        total = sum(4 * w.numel() for w in self.weights)
+        self.buf = torch.empty(total, device=dev, dtype=torch.float32)
+        for i, w in enumerate(self.weights):
+            Co, Ci = w.shape[0], w.shape[1]
+            n = Co * Ci
+            fwd = self.buf[off:off + 2 * n].view(2, Co, Ci)
+            bwd = self.buf[off + 2 * n:off + 4 * n].view(2, Ci, Co)
+            off += 4 * n
+            jobs.append(TnSplitJob(w.data_ptr(), fwd.data_ptr(), Co, Ci, 0, 0))
+            jobs.append(TnSplitJob(w.data_ptr(), bwd.data_ptr(), Ci, Co, 1, 0))
+            self.views[id(w)] = (i, fwd, bwd)
+        arr = (TnSplitJob * len(jobs))(*jobs)
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.jobs = raw.to(dev)
+        self.njobs = len(jobs)
+        self.max_elems = max(w.numel() for w in self.weights)
+        self.versions = [-1] * len(self.weights)
+
+    def stale(self) -> bool:
+        return any(w.data_ptr() != p for w, p in zip(self.weights, self.ptrs))
+
+    def refresh(self):
+        call("tn_split_tf32_batch", ptr(self.jobs), self.njobs, self.max_elems)
+        self.versions = [w._version for w in self.weights]
+        for w in self.weights:
+            _SPLITS[id(w)] = self
+
+    def lookup(self, w: Tensor):
+        ent = self.views.get(id(w))
+        if ent is None or self.weights[ent[0]] is not w or self.versions[ent[0]] != w._version \
+                or self.ptrs[ent[0]] != w.data_ptr():
+            return None
+        return ent[1], ent[2]
 
 
-def _gemm_fwd(x, w3, bias, z, stats, B, T, transpose_w, flags):
+# id(parameter) -> its SplitCache.  Weak values: the cache is owned by the model (which also keeps the parameters, and
+# with them their ids, alive), so entries vanish with the model instead of pinning its buffers.
+_SPLITS = weakref.WeakValueDictionary()
+
+
+def cached_splits(w: Tensor):
+    """(ws_fwd [2, Co, Ci], ws_dgrad [2, Ci, Co]) of a weight refreshed this step, else None."""
+    cache = _SPLITS.get(id(w))
+    return cache.lookup(w) if cache is not None else None
+
+
+def make_bn_fold(gamma, beta, rm, rv, nbt, momentum, eps, n, scale, shift, mean, invstd, counter_ptr) -> TnBnFold:
+    return TnBnFold(ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(nbt), float(momentum), float(eps), float(n), ptr(scale),
+                    ptr(shift), ptr(mean), ptr(invstd), counter_ptr)
+
+
+def _gemm_tc(x, w2, bias, z, stats, R, Kd, M, transpose, flags, nsplit, tag, ws=None, bn=None):
+    if ws is None:
+        ws = torch.empty((2, M, Kd), device=x.device, dtype=torch.float32)
+        call("tn_split_tf32", ptr(w2), ptr(ws), M, Kd, int(transpose))
+    if bn is not None:
+        call("tn_gemm_tc_bn", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), ctypes.byref(bn), R, Kd, M, flags, nsplit, tag=tag)
+    else:
+        call("tn_gemm_tc", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), R, Kd, M, flags, nsplit, tag=tag)
+
+
+def _gemm_fwd(x, w3, bias, z, stats, B, T, transpose_w, flags, ws=None, bn=None):
+    """ws: pre-split weights for this orientation (SplitCache) or None; bn: TnBnFold to fuse (forward only)."""
     Co, Ci, K = w3.shape
     R = B * T
     if transpose_w and _tc_ok(R, Co, Ci, K):
-        return _gemm_tc(x, w3, bias, z, stats, R, Co, Ci, 1, flags, TC_BWD_NSPLIT, f"dgrad R{R} Ci{Co} Co{Ci} K1")
+        return _gemm_tc(x, w3, bias, z, stats, R, Co, Ci, 1, flags, TC_BWD_NSPLIT, f"dgrad R{R} Ci{Co} Co{Ci} K1", ws=ws)
     if not transpose_w and _tc_ok(R, Ci, Co, K):
-        return _gemm_tc(x, w3, bias, z, stats, R, Ci, Co, 0, flags, TC_FWD_NSPLIT, f"fwd R{R} Ci{Ci} Co{Co} K1")
+        return _gemm_tc(x, w3, bias, z, stats, R, Ci, Co, 0, flags, TC_FWD_NSPLIT, f"fwd R{R} Ci{Ci} Co{Co} K1", ws=ws, bn=bn)
     if transpose_w:
         call("tn_conv_gemm_simt", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), B, T, Co, Ci, K, 1, flags,
              tag=f"dgrad R{B * T} Ci{Co} Co{Ci} K{K}")
+    elif bn is not None:
+        call("tn_conv_gemm_simt_bn", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), ctypes.byref(bn), B, T, Ci, Co, K, flags,
+             tag=f"fwd R{B * T} Ci{Ci} Co{Co} K{K}")
     else:
         call("tn_conv_gemm_simt", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), B, T, Ci, Co, K, 0, flags,
              tag=f"fwd R{B * T} Ci{Ci} Co{Co} K{K}")
@@ -150,7 +295,9 @@ class ConvGemm(Function):
         assert x.shape == (B * T, Ci), (x.shape, B, T, Ci)
         z = empty((B * T, Co), x)
         stats = zeros((2 * Co,), x, torch.float64) if want_stats else None
-        _gemm_fwd(x, w3, bias, z, stats, B, T, 0, EPI_TANH if tanh else 0)
+        sp = cached_splits(w)
+        _gemm_fwd(x, w3, bias, z, stats, B, T, 0, EPI_TANH if tanh else 0, ws=sp[0] if sp else None)
+        ctx.ws_t = sp[1] if sp else None
         ctx.save_for_backward(x, w, bias, z if (want_stats or tanh) else None)
         ctx.meta = (B, T, want_stats, tanh)
         if want_stats:
@@ -179,7 +326,7 @@ class ConvGemm(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = empty((B * T, Ci), x)
-            _gemm_fwd(dz, w3, None, dx, None, B, T, 1, 0)
+            _gemm_fwd(dz, w3, None, dx, None, B, T, 1, 0, ws=ctx.ws_t)
         dw = zeros(w.shape, w)
         _gemm_wgrad(dz, x, dw if dw.dim() == 3 else dw.unsqueeze(-1), None if db_done else db, B, T)
         return dx, dw, db, None, None, None, None
@@ -187,6 +334,79 @@ class ConvGemm(Function):
 
 def conv_gemm(x, w, bias, B, T, want_stats=False, tanh=False):
     return ConvGemm.apply(x, w, bias, B, T, want_stats, tanh)
+
+
+def _bn_forward_buffers(Co: int, ref: Tensor):
+    """(stats+ticket fp64 [2Co+1], fold [4, Co] = scale | shift | mean | invstd)."""
+    stats = zeros((2 * Co + 1,), ref, torch.float64)
+    fold = empty((4, Co), ref)
+    return stats, fold
+
+
+def _bn_backward(dz, z, dscale, dshift, fold, gamma, n, bias, R, Co):
+    """tn_bn_stats_bwd: returns (g = full gradient w.r.t. z, dbias, dgamma, dbeta)."""
+    dscale = _c(dscale) if dscale is not None else zeros((Co,), z)
+    dshift = _c(dshift) if dshift is not None else zeros((Co,), z)
+    g = empty(z.shape, z)
+    db = zeros((Co,), z) if bias is not None else None
+    dgamma, dbeta = gempty((Co,), z), gempty((Co,), z)
+    call("tn_bn_stats_bwd", ptr(_c(dz)) if dz is not None else None, ptr(z), ptr(dscale), ptr(dshift), fold[2].data_ptr(),
+         fold[3].data_ptr(), ptr(gamma), float(n), ptr(g), ptr(db), ptr(dgamma), ptr(dbeta), R, Co)
+    return g, db, dgamma, dbeta
+
+
+class ConvGemmBN(Function):
+    """conv (as GEMM) followed by a TRAIN-mode BatchNorm1d, folded: returns the pre-BN tensor ``z`` and the
+    per-channel ``(scale, shift)``.  The GEMM epilogue accumulates the statistics and its last CTA folds them
+    (and updates running_mean / running_var / num_batches_tracked), so there is no separate BatchNorm launch;
+    backward is one pass (tn_bn_stats_bwd) + dgrad + wgrad.  (src/modules.py:119-131, src/models.py:452-455)"""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, gamma, beta, rm, rv, nbt, momentum: float, eps: float, B: int, T: int):
+        x, w, bias, gamma, beta = _c(x), _c(w), _c(bias), _c(gamma), _c(beta)
+        w3 = w if w.dim() == 3 else w.unsqueeze(-1)
+        Co, Ci, K = w3.shape
+        assert x.shape == (B * T, Ci), (x.shape, B, T, Ci)
+        z = empty((B * T, Co), x)
+        stats, fold = _bn_forward_buffers(Co, x)
+        n = float(B * T)
+        bn = make_bn_fold(gamma, beta, rm, rv, nbt, momentum, eps, n, fold[0], fold[1], fold[2], fold[3],
+                          stats.data_ptr() + 16 * Co)
+        sp = cached_splits(w)
+        _gemm_fwd(x, w3, bias, z, stats, B, T, 0, 0, ws=sp[0] if sp else None, bn=bn)
+        ctx.ws_t = sp[1] if sp else None
+        ctx.save_for_backward(x, w, bias, z, gamma, fold)
+        ctx.meta = (B, T, n)
+        return z, fold[0], fold[1]
+
+    @staticmethod
+    def backward(ctx, dz, dscale, dshift):
+        x, w, bias, z, gamma, fold = ctx.saved_tensors
+        B, T, n = ctx.meta
+        w3 = w if w.dim() == 3 else w.unsqueeze(-1)
+        Co, Ci, K = w3.shape
+        g, db, dgamma, dbeta = _bn_backward(dz, z, dscale, dshift, fold, gamma, n, bias, B * T, Co)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = empty((B * T, Ci), x)
+            _gemm_fwd(g, w3, None, dx, None, B, T, 1, 0, ws=ctx.ws_t)
+        dw = zeros(w.shape, w)
+        _gemm_wgrad(g, x, dw if dw.dim() == 3 else dw.unsqueeze(-1), None, B, T)
+        return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def _bn_trainable(bn: torch.nn.BatchNorm1d) -> bool:
+    return (bn.training or bn.running_mean is None) and bn.momentum is not None and bn.affine
+
+
+def conv_gemm_bn(x, w, bias, bn: torch.nn.BatchNorm1d, B: int, T: int):
+    """(z, scale, shift) of ``bn(conv(x))``: fused in train mode, conv + running-statistics fold in eval mode."""
+    if _bn_trainable(bn):
+        return ConvGemmBN.apply(x, w, bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                                bn.momentum, bn.eps, B, T)
+    z, stats = conv_gemm(x, w, bias, B, T, want_stats=bn.training)
+    scale, shift = bn_fold(stats, bn, float(B * T))
+    return z, scale, shift
 
 
 class ColStats(Function):
@@ -237,7 +457,7 @@ class BNFold(Function):
         C = gamma.numel()
         dscale = _c(dscale) if dscale is not None else zeros((C,), gamma)
         dshift = _c(dshift) if dshift is not None else zeros((C,), gamma)
-        dgamma, dbeta = empty((C,), gamma), empty((C,), gamma)
+        dgamma, dbeta = gempty((C,), gamma), gempty((C,), gamma)
         dstats = empty((2 * C,), gamma, torch.float64) if (training and has_stats) else None
         call("tn_bn_bwd_coef", ptr(dscale), ptr(dshift), ptr(mean), ptr(invstd), ptr(gamma), n, 1 if dstats is not None else 0,
              ptr(dgamma), ptr(dbeta), ptr(dstats), C)
@@ -336,7 +556,9 @@ class DwPw(Function):
              B, T, C, K)
         zo = empty((B * T, Co), z)
         stats = zeros((2 * Co,), z, torch.float64) if want_stats else None
-        _gemm_fwd(u, pw_w if pw_w.dim() == 3 else pw_w.unsqueeze(-1), pw_b, zo, stats, B, T, 0, 0)
+        sp = cached_splits(pw_w)
+        _gemm_fwd(u, pw_w if pw_w.dim() == 3 else pw_w.unsqueeze(-1), pw_b, zo, stats, B, T, 0, 0, ws=sp[0] if sp else None)
+        ctx.ws_t = sp[1] if sp else None
         ctx.save_for_backward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, u, zo if want_stats else None)
         ctx.meta = (relu, p, layer, B, T, want_stats)
         return zo, stats
@@ -357,23 +579,76 @@ class DwPw(Function):
             dz, db_done = g, True
         dpw = zeros(pw_w.shape, pw_w)
         _gemm_wgrad(dz, u, dpw if dpw.dim() == 3 else dpw.unsqueeze(-1), None if db_done else db_pw, B, T)
-        dzp = empty(z.shape, z)
-        ddw = zeros(dw_w.shape, dw_w)
-        ddb = zeros((C,), z) if dw_b is not None else None
-        dscale = zeros((C,), z) if scale is not None else None
-        dshift = zeros((C,), z) if scale is not None else None
-        if TC_ENABLED and TC_FUSE_DWBWD and R >= TC_MIN_ROWS and Co % 32 == 0 and C % 128 == 0 and K % 2 == 1 and K <= 15:
+        dzp, dscale, dshift, ddw, ddb = _dwpw_dgrad(dz, pw3, ctx.ws_t, z, scale, shift, dw_w, dw_b, seed, relu, p, layer, B, T)
+        return dzp, dscale, dshift, ddw, ddb, dpw, db_pw, None, None, None, None, None, None, None
+
+
+def _dwpw_dgrad(dz, pw3, ws_t, z, scale, shift, dw_w, dw_b, seed, relu, p, layer, B, T):
+    """Data gradient of pointwise(depthwise(act(z))): one fused tensor-core kernel when the shape allows."""
+    C, K = dw_w.shape[0], dw_w.shape[-1]
+    Co, R = pw3.shape[0], B * T
+    dzp = empty(z.shape, z)
+    ddw = zeros(dw_w.shape, dw_w)
+    ddb = zeros((C,), z) if dw_b is not None else None
+    dscale = zeros((C,), z) if scale is not None else None
+    dshift = zeros((C,), z) if scale is not None else None
+    if (TC_ENABLED and TC_FUSE_DWBWD and R >= TC_MIN_ROWS and Co % 32 == 0 and C % 128 == 0 and K % 2 == 1 and K <= 11
+            and (R + 16) * C < 2 ** 32):
+        ws = ws_t
+        if ws is None:
             ws = torch.empty((2, C, Co), device=z.device, dtype=torch.float32)
             call("tn_split_tf32", ptr(pw3), ptr(ws), C, Co, 1)
-            call("tn_gemm_tc_dwbwd", ptr(dz), ptr(ws), ptr(z), ptr(dzp), ptr(dw_w), ptr(ddw), ptr(ddb), ptr(dscale), ptr(dshift),
-                 ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer), B, T, Co, C, K, TC_BWD_NSPLIT,
-                 tag=f"dgrad+dwbwd R{R} Ci{Co} Co{C} K1")
-        else:
-            du = empty(z.shape, z)
-            _gemm_fwd(dz, pw3, None, du, None, B, T, 1, 0)
-            call("tn_dw_bwd", ptr(du), ptr(z), ptr(dzp), ptr(dw_w), ptr(ddw), ptr(ddb), ptr(dscale), ptr(dshift), ptr(scale),
-                 ptr(shift), int(relu), float(p), ptr(seed), int(layer), B, T, C, K)
-        return dzp, dscale, dshift, ddw, ddb, dpw, db_pw, None, None, None, None, None, None, None
+        call("tn_gemm_tc_dwbwd", ptr(dz), ptr(ws), ptr(z), ptr(dzp), ptr(dw_w), ptr(ddw), ptr(ddb), ptr(dscale), ptr(dshift),
+             ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer), B, T, Co, C, K, TC_BWD_NSPLIT,
+             tag=f"dgrad+dwbwd R{R} Ci{Co} Co{C} K1")
+    else:
+        du = empty(z.shape, z)
+        _gemm_fwd(dz, pw3, None, du, None, B, T, 1, 0, ws=ws_t)
+        call("tn_dw_bwd", ptr(du), ptr(z), ptr(dzp), ptr(dw_w), ptr(ddw), ptr(ddb), ptr(dscale), ptr(dshift), ptr(scale),
+             ptr(shift), int(relu), float(p), ptr(seed), int(layer), B, T, C, K)
+    return dzp, dscale, dshift, ddw, ddb
+
+
+class DwPwBN(Function):
+    """``DwPw`` followed by a TRAIN-mode BatchNorm1d folded by the GEMM's last CTA (see ``ConvGemmBN``):
+    returns (z_out, scale_out, shift_out).  One ConvBlock1d(depthwise=True) of a mega-block
+    (src/modules.py:119-134) = tn_dw_fwd + tn_gemm_tc_bn forward, tn_bn_stats_bwd + tn_wgrad_tc +
+    tn_gemm_tc_dwbwd backward."""
+
+    @staticmethod
+    def forward(ctx, z, scale, shift, dw_w, dw_b, pw_w, pw_b, gamma, beta, rm, rv, nbt, momentum: float, eps: float, seed,
+                relu: bool, p: float, layer: int, B: int, T: int):
+        z, scale, shift, dw_w, dw_b, pw_w, pw_b, gamma, beta = map(_c, (z, scale, shift, dw_w, dw_b, pw_w, pw_b, gamma, beta))
+        C, K = dw_w.shape[0], dw_w.shape[-1]
+        Co = pw_w.shape[0]
+        assert z.shape == (B * T, C)
+        u = empty(z.shape, z)
+        call("tn_dw_fwd", ptr(z), ptr(u), ptr(dw_w), ptr(dw_b), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer),
+             B, T, C, K)
+        zo = empty((B * T, Co), z)
+        stats, fold = _bn_forward_buffers(Co, z)
+        n = float(B * T)
+        bn = make_bn_fold(gamma, beta, rm, rv, nbt, momentum, eps, n, fold[0], fold[1], fold[2], fold[3],
+                          stats.data_ptr() + 16 * Co)
+        sp = cached_splits(pw_w)
+        _gemm_fwd(u, pw_w if pw_w.dim() == 3 else pw_w.unsqueeze(-1), pw_b, zo, stats, B, T, 0, 0, ws=sp[0] if sp else None, bn=bn)
+        ctx.ws_t = sp[1] if sp else None
+        ctx.save_for_backward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, u, zo, gamma, fold)
+        ctx.meta = (relu, p, layer, B, T, n)
+        return zo, fold[0], fold[1]
+
+    @staticmethod
+    def backward(ctx, dzo, dscale_o, dshift_o):
+        z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, u, zo, gamma, fold = ctx.saved_tensors
+        relu, p, layer, B, T, n = ctx.meta
+        pw3 = pw_w if pw_w.dim() == 3 else pw_w.unsqueeze(-1)
+        Co = pw3.shape[0]
+        g, db_pw, dgamma, dbeta = _bn_backward(dzo, zo, dscale_o, dshift_o, fold, gamma, n, pw_b, B * T, Co)
+        dpw = zeros(pw_w.shape, pw_w)
+        _gemm_wgrad(g, u, dpw if dpw.dim() == 3 else dpw.unsqueeze(-1), None, B, T)
+        dzp, dscale, dshift, ddw, ddb = _dwpw_dgrad(g, pw3, ctx.ws_t, z, scale, shift, dw_w, dw_b, seed, relu, p, layer, B, T)
+        return (dzp, dscale, dshift, ddw, ddb, dpw, db_pw, dgamma, dbeta, None, None, None, None, None, None, None, None,
+                None, None, None)
 
 
 # ----------------------------------------------------------------------------

@@ -92,6 +92,18 @@ __device__ __forceinline__ uint32_t tn_hash_elem(uint32_t seed_lo, uint32_t seed
   h ^= h >> 15;
   return h;
 }
+// The same hash for element indices below 2^32: the high-word term is a per-launch constant, so the
+// caller folds it into `key = tn_hash_key32(...)` once and pays one multiply + the finaliser per element.
+__device__ __forceinline__ uint32_t tn_hash_key32(uint32_t seed_lo, uint32_t seed_hi, uint32_t layer) {
+  return seed_lo ^ (layer * 0x85EBCA77u + seed_hi);
+}
+__device__ __forceinline__ uint32_t tn_hash_elem32(uint32_t key, uint32_t idx) {
+  uint32_t h = idx * 0x9E3779B1u ^ key;
+  h ^= h >> 16; h *= 0x21F0AAADu;
+  h ^= h >> 15; h *= 0x735A2D97u;
+  h ^= h >> 15;
+  return h;
+}
 // keep-multiplier (0 or inv_keep) of element `idx` (= row * C + channel)
 __device__ __forceinline__ float tn_drop1(const struct TnAct& a, unsigned long long idx);
 
@@ -166,6 +178,46 @@ __device__ __forceinline__ float4 tn_fma4(float4 a, float4 b, float4 c) {
   return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
 }
 __device__ __forceinline__ float4 tn_zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// ---------------------------------------------------------------------------
+// Train-mode BatchNorm fold performed by the LAST block of the kernel that produced the statistics
+// (device-wide ticket).  Every thread of every block calls this after its statistics atomics were
+// issued.  nn.BatchNorm1d semantics (biased variance for normalisation, unbiased for running_var).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tn_bn_fold_last(const tn_bn_fold& f, const double* stats, int C, unsigned int total_blocks) {
+  __shared__ unsigned int s_is_last;
+  __threadfence();                                   // this thread's atomics before the block's ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(f.counter, 1u);
+    s_is_last = (t == total_blocks - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  const double n = f.n;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double m = __ldcg(stats + c) / n;
+    double var = __ldcg(stats + C + c) / n - m * m;
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)m;
+    const float invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+    if (f.running_mean) {
+      const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+      f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
+      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+    }
+    const float sc = __ldg(f.gamma + c) * invstd;
+    f.scale[c] = sc;
+    f.shift[c] = __ldg(f.beta + c) - mean * sc;
+    f.mean[c] = mean;
+    f.invstd[c] = invstd;
+  }
+  if (threadIdx.x == 0) {
+    *f.counter = 0u;                                 // ready for the next launch / graph replay
+    if (f.num_batches_tracked) *f.num_batches_tracked += 1;
+  }
+}
 
 // ---------------------------------------------------------------------------
 // Row-tiled channel-quad work distribution shared by the HBM-bound NWC kernels.

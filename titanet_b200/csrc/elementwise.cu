@@ -325,6 +325,63 @@ extern "C" int tn_stats_bwd(const float* dz_direct, const float* z, const double
   return TN_OK;
 }
 
+// tn_bn_bwd_coef + tn_stats_bwd in one pass: the per-channel coefficients are recomputed by every
+// thread for its own four channels (a handful of fp64 operations), block 0 also writes dgamma / dbeta.
+__global__ void __launch_bounds__(TN_EW_THREADS) bn_stats_bwd_kernel(const float* __restrict__ dzd, const float* __restrict__ z,
+                                                                     const float* __restrict__ dscale, const float* __restrict__ dshift,
+                                                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                     const float* __restrict__ gamma, double n, float* __restrict__ out,
+                                                                     float* __restrict__ dbias, float* __restrict__ dgamma,
+                                                                     float* __restrict__ dbeta, int R, int C, int rpb) {
+  __shared__ float4 red[TN_EW_THREADS];
+  TnTile tl = tn_tile(C);
+  const int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    const int q = qb + tl.q0;
+    float4 acc = tn_zero4();
+    if (tl.active && q < tl.Q) {
+      const int c = 4 * q;
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double dsc = dscale[c + i], dsh = dshift[c + i], mu = mean[c + i], r = invstd[c + i], g = gamma[c + i];
+        const double t = dsc - mu * dsh;               // dL/d(invstd) / gamma
+        const double dvar = -0.5 * g * t * r * r * r;
+        const double dmu = -dsh * g * r - 2.0 * mu * dvar;
+        av[i] = (float)(dmu / n);
+        bv[i] = (float)(2.0 * dvar / n);
+        if (blockIdx.x == 0 && tl.lane == 0) {
+          dgamma[c + i] = (float)(r * t);
+          dbeta[c + i] = (float)dsh;
+        }
+      }
+      const float4 a = make_float4(av[0], av[1], av[2], av[3]);
+      const float4 b = make_float4(bv[0], bv[1], bv[2], bv[3]);
+#pragma unroll 4
+      for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
+        const size_t off = (size_t)r * C + c;
+        float4 v = tn_fma4(b, tn_ld4(z + off), a);
+        if (dzd) v = v + tn_ld4(dzd + off);
+        tn_st4(out + off, v);
+        acc = acc + v;
+      }
+    }
+    if (dbias) tn_lane_reduce_atomic(tl, acc, q, dbias, red);
+  }
+}
+extern "C" int tn_bn_stats_bwd(const float* dz_direct, const float* z, const float* dscale, const float* dshift, const float* mean,
+                               const float* invstd, const float* gamma, double n, float* out, float* dbias, float* dgamma,
+                               float* dbeta, int R, int C, void* stream) {
+  TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0 && z && out && tn_aligned16(out) && tn_aligned16(z) && (!dz_direct || tn_aligned16(dz_direct)),
+             "bn_stats_bwd: need C %% 4 == 0 and aligned tensors (R=%d C=%d)", R, C);
+  TN_REQUIRE(dscale && dshift && mean && invstd && gamma && dgamma && dbeta && n >= 1.0, "bn_stats_bwd: null argument");
+  int rpb = rows_per_block(R);
+  bn_stats_bwd_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(dz_direct, z, dscale, dshift, mean, invstd, gamma, n,
+                                                                                    out, dbias, dgamma, dbeta, R, C, rpb);
+  TN_LAUNCH_CHECK("bn_stats_bwd_kernel");
+  return TN_OK;
+}
+
 // advance the dropout seed state (splitmix64) and publish the new step seed
 __global__ void seed_next_kernel(unsigned long long* state, unsigned long long* out) {
   unsigned long long z = (*state += 0x9E3779B97F4A7C15ull);

@@ -12,6 +12,7 @@
 // connection (src/models.py:452-455), nn.Linear in ASP / decoder / loss heads
 // (src/models.py:549-551, 510-513; src/losses.py:30, 70).
 #include "common.cuh"
+#include <string.h>
 
 #define GM 64   // rows per tile
 #define GN 64   // output channels per tile
@@ -21,7 +22,7 @@
 __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict__ X, const float* __restrict__ W,
                                                         const float* __restrict__ bias, float* __restrict__ Z,
                                                         double* __restrict__ stats, int R, int T, int Ci, int Co, int K,
-                                                        int transpose_w, int flags, int kk_per_split) {
+                                                        int transpose_w, int flags, int kk_per_split, tn_bn_fold bn, int has_bn) {
   __shared__ float As[GK][GM + 4];
   __shared__ float Bs[GK][GN + 4];
   __shared__ float red1[16][GN], red2[16][GN];
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
       }
     }
   }
+  if (has_bn) tn_bn_fold_last(bn, stats, Co, gridDim.x * gridDim.y);   // never with split-K (the host folds separately)
 }
 
 // dW[co, ci, k] += sum_r dZ[r, co] * X[r + k - pad, ci]; rows split over blockIdx.z
@@ -190,8 +192,8 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
   }
 }
 
-extern "C" int tn_conv_gemm_simt(const float* X, const float* W, const float* bias, float* Z, double* stats, int B, int T,
-                                 int Ci, int Co, int K, int transpose_w, int flags, void* stream) {
+static int conv_gemm_launch(const float* X, const float* W, const float* bias, float* Z, double* stats, const tn_bn_fold* bn,
+                            int B, int T, int Ci, int Co, int K, int transpose_w, int flags, void* stream) {
   TN_REQUIRE(B > 0 && T > 0 && Ci > 0 && Co > 0 && K > 0 && (K & 1), "conv_gemm: bad shape B=%d T=%d Ci=%d Co=%d K=%d (odd K only)", B, T, Ci, Co, K);
   TN_REQUIRE(X && W && Z, "conv_gemm: null tensor");
   long long R = (long long)B * T;
@@ -208,10 +210,32 @@ extern "C" int tn_conv_gemm_simt(const float* X, const float* W, const float* bi
   splits = (int)((KK + kps - 1) / kps);
   grid.z = splits;
   if (splits > 1) TN_CUDA(cudaMemsetAsync(Z, 0, sizeof(float) * (size_t)R * Co, (cudaStream_t)stream));
-  conv_gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, W, bias, Z, stats, (int)R, T, Ci, Co, K, transpose_w, flags, kps);
+  tn_bn_fold f;
+  memset(&f, 0, sizeof(f));
+  const int fuse_bn = (bn && splits == 1) ? 1 : 0;
+  if (fuse_bn) f = *bn;
+  conv_gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, W, bias, Z, stats, (int)R, T, Ci, Co, K, transpose_w, flags, kps, f, fuse_bn);
   TN_LAUNCH_CHECK("conv_gemm_kernel");
-  if (splits > 1 && stats) return tn_colstats(Z, stats, (int)R, Co, stream);   // split-K: statistics from the finished tensor
+  if (splits > 1 && stats) {                       // split-K: statistics (and the fold) from the finished tensor
+    int rc = tn_colstats(Z, stats, (int)R, Co, stream);
+    if (rc != TN_OK) return rc;
+    if (bn) return tn_bn_finalize(stats, bn->n, bn->gamma, bn->beta, bn->running_mean, bn->running_var, bn->num_batches_tracked,
+                                  bn->momentum, bn->eps, 1, bn->scale, bn->shift, bn->mean, bn->invstd, Co, stream);
+  }
   return TN_OK;
+}
+
+extern "C" int tn_conv_gemm_simt(const float* X, const float* W, const float* bias, float* Z, double* stats, int B, int T,
+                                 int Ci, int Co, int K, int transpose_w, int flags, void* stream) {
+  return conv_gemm_launch(X, W, bias, Z, stats, nullptr, B, T, Ci, Co, K, transpose_w, flags, stream);
+}
+
+extern "C" int tn_conv_gemm_simt_bn(const float* X, const float* W, const float* bias, float* Z, double* stats,
+                                    const tn_bn_fold* bn, int B, int T, int Ci, int Co, int K, int flags, void* stream) {
+  TN_REQUIRE(bn && stats, "conv_gemm_simt_bn: the fold needs the statistics buffer");
+  TN_REQUIRE(bn->gamma && bn->beta && bn->scale && bn->shift && bn->mean && bn->invstd && bn->counter && bn->n >= 1.0,
+             "conv_gemm_simt_bn: incomplete tn_bn_fold");
+  return conv_gemm_launch(X, W, bias, Z, stats, bn, B, T, Ci, Co, K, 0, flags, stream);
 }
 
 extern "C" int tn_conv_wgrad_simt(const float* dZ, const float* X, float* dW, float* dbias, int B, int T, int Ci, int Co, int K,

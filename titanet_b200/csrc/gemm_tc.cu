@@ -152,7 +152,12 @@ struct TcParams {
   // fused depthwise-backward epilogue (dw_K > 0): this GEMM is the data gradient of a pointwise conv
   // whose input was depthwise_K(act(zprev)); the epilogue turns du (in TMEM) into dzprev directly.
   int dw_K, dw_T, BNo;   // taps, frames per utterance, output rows per CTA (BN = BNo + halo)
+  int z_early;           // z tiles may be requested while the last chunks are still in the tensor core (2 stages)
+  uint32_t z_off1;       // byte offset of the second z tile in the (freed) pipeline memory when !z_early
+  uint32_t red_off;      // byte offset of the per-channel reduction staging buffer (behind the pipeline stages)
   const float* dw_w;     // [C, K]
+  tn_bn_fold bn;         // has_bn: the last CTA folds the statistics into (scale, shift) (tn_bn_fold_last)
+  int has_bn;
   const float* zprev;    // [R, C]
   float* dzprev;         // [R, C]
   float* g_dw;           // [C, K]   ACCUMULATED
@@ -169,116 +174,180 @@ struct TcParams {
 // d dw bias) is a thread-local sum; z of the previous layer is read once, coalesced across lanes.
 // Reference: autograd of DepthwiseConv1d's first conv + BatchNorm/ReLU/Dropout
 // (src/modules.py:64-75, 128-133) as reached by loss.backward() (src/learn.py:117).
+// tcgen05.ld of 4 accumulator columns, issue only (tc_ld_wait makes the registers valid)
+__device__ __forceinline__ void tc_ld4_issue(uint32_t taddr, float* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(taddr));
+}
+
+// The epilogue is a ROLLED loop over groups of four output rows with the depthwise window carried in
+// registers (the first version unrolled 16 rows: 21 KB of straight-line code per chunk, and the ncu source
+// view showed the eight epilogue warps stalled on instruction fetch, stall_no_inst, on nearly every line).
+// Per group: four new accumulator columns (tcgen05.ld.x4, issued one group ahead), four new z rows of the
+// previous layer (coalesced 128-byte lines, issued two groups ahead), their activation / dropout mask, four
+// outputs.  The two warps of a lane quadrant own the two halves of the tile's rows.
 template <int K>
-__device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams& p, const TnAct& act, int c, int n0, int half) {
+__device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams& p, const TnAct& act, int c, int n0, int half,
+                                                  const uint8_t* zs, float* red) {
   constexpr int PAD = K / 2;
+  constexpr int WW = 4 + 2 * PAD;                    // window: tile columns o .. o + 3 + 2 PAD for outputs o .. o + 3
   const int C = p.M_total, T = p.dw_T, R = p.R;
   float w[K], a_w[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) { w[k] = __ldg(p.dw_w + (size_t)c * K + k); a_w[k] = 0.f; }
   const bool lazy = act.scale != nullptr;
+  const bool drop = act.thresh != 0;
   const float sc = lazy ? __ldg(act.scale + c) : 1.f;
   const float sh = lazy ? __ldg(act.shift + c) : 0.f;
+  const uint32_t key = tn_hash_key32(act.seed_lo, act.seed_hi, act.layer);   // R * C < 2^32 (checked by the launcher)
   float a_sc = 0.f, a_sh = 0.f, a_b = 0.f;
-  const int r_first = n0 + PAD;
+  const int r_first = n0 + PAD;                      // global row of output 0 (tile column j <-> global row n0 + j)
   const int nout = min(p.BNo, R - r_first);
-  constexpr int W = 16 + 2 * PAD;                    // rows of the previous layer needed per 16 outputs
-  // z window of the previous layer: rows n0 + o0 + jj.  All loads of a chunk are issued back to back
-  // (no control flow in between) and the next chunk's window is prefetched while this one is
-  // processed: only four warps run this epilogue, so the latency has to be hidden by ILP.
-  float zn[W];
-  auto load_window = [&](int o0) {
-#pragma unroll
-    for (int jj = 0; jj < W; ++jj) {
-      const int row = n0 + o0 + jj;
-      const bool valid = row >= 0 && row < R && o0 < p.BNo;
-      zn[jj] = valid ? __ldg(p.zprev + (size_t)row * C + c) : 0.f;
-    }
+  const int hsplit = p.BNo >> 1;                     // BNo is a multiple of 16
+  const int oa = half ? hsplit : 0;
+  const int ob = min(half ? p.BNo : hsplit, nout);   // this warp's outputs: [oa, ob)
+  const bool traced = p.trace && threadIdx.x == 64 && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2);
+  long long* tr = traced ? p.trace + (blockIdx.x == 0 ? 0 : 128) + 113 + (c >= 128 ? 4 : 0) : nullptr;
+  if (tr) tr[0] = clock64();
+  if (oa < ob) {
+  float* dzcol = p.dzprev + c;
+  // z of the previous layer for this CTA's rows was brought into shared memory by TMA (128-byte swizzled rows of
+  // 32 channels; rows outside the tensor arrive as zeros): `zs` is this thread's 32-channel block, tile row j is
+  // global row n0 + j.  A warp reads one 128-byte row: conflict-free.  (Per-thread global loads could not keep
+  // enough bytes in flight: eight warps x 4 B left the epilogue latency-bound at ~8 GB/s per SM.)
+  const uint32_t lane = threadIdx.x & 31;
+  auto load_zt = [&](int j) -> float {
+    const uint32_t off = (uint32_t)j * 128u + ((((lane >> 2) ^ ((uint32_t)j & 7u)) << 4) | ((lane & 3u) << 2));
+    return *reinterpret_cast<const float*>(zs + off);
   };
-  load_window(16 * half);
-  for (int o0 = 16 * half; o0 < p.BNo; o0 += 32) {   // the two warps of a lane quadrant alternate 16-row chunks
-    float v[32];
-    tc_ld16_issue(tbase + o0, v);
-    if (PAD > 0) tc_ld16_issue(tbase + o0 + 16, v + 16);
-    float zw[W];
+  // activation of window row `row` from its z (0 for rows outside the tensor); m = d a / d pre
+  auto actf = [&](float zv, int row, float& m) -> float {
+    m = 1.f;
+    if (!lazy) return zv;
+    const float pre = fmaf(zv, sc, sh);
+    if (drop) m = tn_hash_elem32(key, (uint32_t)row * (uint32_t)C + (uint32_t)c) >= act.thresh ? act.inv_keep : 0.f;
+    if (act.relu && !(pre > 0.f)) m = 0.f;
+    return (row >= 0 && row < R) ? pre * m : 0.f;
+  };
+  float g[WW], a[WW], zc[PAD + 4], mc[PAD + 4];
+  // prime window positions [0, 2 PAD)
+  if (PAD > 0) {
+    float tmp[16];
+    tc_ld16(tbase + oa, tmp);
 #pragma unroll
-    for (int jj = 0; jj < W; ++jj) zw[jj] = zn[jj];
-    load_window(o0 + 32);                            // prefetch (predicated off past the last chunk)
-    float av[W], zc[16], mv[16];
-#pragma unroll
-    for (int jj = 0; jj < W; ++jj) {
-      const int row = n0 + o0 + jj;
-      const bool valid = row >= 0 && row < R;
-      float a = zw[jj], m = 1.f;
-      if (lazy) {
-        const float pre = fmaf(zw[jj], sc, sh);
-        m = tn_drop1(act, (unsigned long long)(valid ? row : 0) * C + c);
-        m = (act.relu && !(pre > 0.f)) ? 0.f : m;
-        a = pre * m;
-      }
-      av[jj] = valid ? a : 0.f;
-      if (jj >= PAD && jj < PAD + 16) { zc[jj - PAD] = zw[jj]; mv[jj - PAD] = m; }
+    for (int j = 0; j < 2 * PAD; ++j) {
+      const int row = n0 + oa + j;
+      const float zv = load_zt(oa + j);
+      float m;
+      g[j] = tmp[j];
+      a[j] = actf(zv, row, m);
+      if (j >= PAD) { zc[j - PAD] = zv; mc[j - PAD] = m; }
     }
-    tc_ld_wait(v, 32);
-    const int t0 = (r_first + o0) % T;
-    if (t0 >= PAD && t0 + 15 + PAD < T && o0 + 16 <= nout) {
-      // the whole chunk lies inside one utterance and inside the tensor: no boundary tests
+  }
+  float gq[4];
+  if (tr) tr[1] = clock64();
+  tc_ld4_issue(tbase + oa + 2 * PAD, gq);
+  int t0 = (r_first + oa) % T;
+#pragma unroll 1
+  for (int o = oa; o < ob; o += 4) {
+    tc_ld_wait(gq, 4);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float g0 = v[i + PAD];
+    for (int i = 0; i < 4; ++i) g[2 * PAD + i] = gq[i];
+    if (o + 4 < ob) tc_ld4_issue(tbase + o + 4 + 2 * PAD, gq);       // warp-uniform
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float m;
+      const float zv = load_zt(o + 2 * PAD + i);
+      a[2 * PAD + i] = actf(zv, n0 + o + 2 * PAD + i, m);
+      zc[PAD + i] = zv;
+      mc[PAD + i] = m;
+    }
+    const int cnt = ob - o;
+    float* dq = dzcol + (size_t)((uint32_t)(r_first + o) * (uint32_t)C);
+    if (t0 >= PAD && t0 + 3 + PAD < T && cnt >= 4) {
+      // the group and its taps lie inside one utterance and inside the tensor: no boundary tests
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float g0 = g[i + PAD];
         float da = 0.f;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          da = fmaf(w[k], v[i + 2 * PAD - k], da);
-          a_w[k] = fmaf(g0, av[i + k], a_w[k]);
+          da = fmaf(w[k], g[i + 2 * PAD - k], da);
+          a_w[k] = fmaf(g0, a[i + k], a_w[k]);
         }
         a_b += g0;
         float out = da;
         if (lazy) {
-          const float g = da * mv[i];
-          a_sc = fmaf(g, zc[i], a_sc);
-          a_sh += g;
-          out = g * sc;
+          const float gg = da * mc[i];
+          a_sc = fmaf(gg, zc[i], a_sc);
+          a_sh += gg;
+          out = gg * sc;
         }
-        p.dzprev[(size_t)(r_first + o0 + i) * C + c] = out;
+        dq[(uint32_t)(i * C)] = out;
       }
-      continue;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool ok = i < cnt;
+        const int t = (t0 + i) % T;
+        const float g0 = g[i + PAD];
+        float da = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          // forward: u[r'] += w[k] * a[r' + k - PAD]  =>  a[r] feeds u[r + PAD - k]
+          const int tu = t + PAD - k;
+          if (tu >= 0 && tu < T) da = fmaf(w[k], g[i + 2 * PAD - k], da);
+          const int ta = t + k - PAD;
+          if (ok && ta >= 0 && ta < T) a_w[k] = fmaf(g0, a[i + k], a_w[k]);
+        }
+        if (ok) {
+          a_b += g0;
+          float out = da;
+          if (lazy) {
+            const float gg = da * mc[i];
+            a_sc = fmaf(gg, zc[i], a_sc);
+            a_sh += gg;
+            out = gg * sc;
+          }
+          dq[(uint32_t)(i * C)] = out;
+        }
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const bool ok = o0 + i < nout;
-      int t = t0 + i;
-      t = t >= T ? t % T : t;
-      const float g0 = v[i + PAD];
-      float da = 0.f;
+    for (int j = 0; j < 2 * PAD; ++j) { g[j] = g[j + 4]; a[j] = a[j + 4]; }
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        // forward: u[r'] += w[k] * a[r' + k - PAD]  =>  a[r] feeds u[r + PAD - k]
-        const int tu = t + PAD - k;
-        if (tu >= 0 && tu < T) da = fmaf(w[k], v[i + 2 * PAD - k], da);
-        const int ta = t + k - PAD;
-        if (ok && ta >= 0 && ta < T) a_w[k] = fmaf(g0, av[i + k], a_w[k]);
-      }
-      if (ok) {
-        a_b += g0;
-        float out = da;
-        if (act.scale) {
-          const float g = da * mv[i];
-          a_sc = fmaf(g, zc[i], a_sc);
-          a_sh += g;
-          out = g * sc;
-        }
-        p.dzprev[(size_t)(r_first + o0 + i) * C + c] = out;
-      }
-    }
+    for (int j = 0; j < PAD; ++j) { zc[j] = zc[j + 4]; mc[j] = mc[j + 4]; }
+    t0 += 4;
+    if (t0 >= T) t0 %= T;
   }
+  }
+  if (tr) tr[2] = clock64();
+  // Per-channel sums leave the CTA through shared memory: the two warps of a lane quadrant are combined and the
+  // atomics are issued with consecutive threads on consecutive addresses, i.e. ONE visit per 128-byte line per CTA
+  // (same-line atomics serialise in the L2 slice; one thread per channel with stride-K addresses made 96 line
+  // visits per CTA and the backlog stalled the next channel half for ~4 us).
+  constexpr int F = K + 3;
+  const int chl = (int)(threadIdx.x & 127u);              // (warp & 3) * 32 + lane: channel inside this 128-channel half
+  float* mine = red + ((size_t)half * 128 + chl) * F;
 #pragma unroll
-  for (int k = 0; k < K; ++k) atomicAdd(p.g_dw + (size_t)c * K + k, a_w[k]);
-  if (p.g_db) atomicAdd(p.g_db + c, a_b);
-  if (act.scale) {
-    atomicAdd(p.g_dscale + c, a_sc);
-    atomicAdd(p.g_dshift + c, a_sh);
+  for (int k = 0; k < K; ++k) mine[k] = a_w[k];
+  mine[K] = a_b; mine[K + 1] = a_sc; mine[K + 2] = a_sh;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  const int tid = (int)threadIdx.x - 64;
+  const int cbase = c - chl;
+  for (int L = tid; L < 128 * K; L += 256) {
+    const int ch = L / K, k = L - ch * K;
+    atomicAdd(p.g_dw + (size_t)cbase * K + L, red[ch * F + k] + red[(128 + ch) * F + k]);
   }
+  if (tid < 128) {
+    if (p.g_db) atomicAdd(p.g_db + cbase + tid, red[tid * F + K] + red[(128 + tid) * F + K]);
+  } else if (lazy) {
+    const int ch = tid - 128;
+    atomicAdd(p.g_dscale + cbase + ch, red[ch * F + K + 1] + red[(128 + ch) * F + K + 1]);
+    atomicAdd(p.g_dshift + cbase + ch, red[ch * F + K + 2] + red[(128 + ch) * F + K + 2]);
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");          // `red` is reused by the next channel half
+  if (tr) tr[3] = clock64();
 }
 #define TC_TRACE(slot) do { if (p.trace && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && blockIdx.y == 0) \
     p.trace[(blockIdx.x == 0 ? 0 : 128) + (slot)] = clock64(); } while (0)
@@ -289,9 +358,9 @@ __device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams
 template <int MT>
 __global__ void __launch_bounds__(TC_GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-               const __grid_constant__ CUtensorMap tmB, TcParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 1 + 2];
   __shared__ uint32_t tmem_base_slot;
 
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -319,6 +388,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   auto b_lo = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * MT * a_tile + b_tile; };
   const uint32_t full0 = smem_u32(&bars[0]), ready0 = smem_u32(&bars[TC_MAX_STAGES]), empty0 = smem_u32(&bars[2 * TC_MAX_STAGES]);
   const uint32_t accum_bar = smem_u32(&bars[3 * TC_MAX_STAGES]);
+  const uint32_t z_bar0 = smem_u32(&bars[3 * TC_MAX_STAGES + 1]);     // fused depthwise backward: z tile of output-channel half mt
+  // z tile mt (128 channels = 4 blocks of [BN rows x 128 B]) lands in pipeline memory the mainloop no longer needs
+  const uint32_t z_blk = (uint32_t)BN * 128u;
+  auto z_off = [&](int mt) -> uint32_t {
+    if (p.z_early) return (uint32_t)(((num_kc - 2 + mt) % S)) * stage_bytes;     // the stage of the (mt+1)-th last-but-one chunk
+    return mt ? p.z_off1 : 0u;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -327,6 +403,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(empty0 + 8 * s, 1);
     }
     mbar_init(accum_bar, 1);
+    mbar_init(z_bar0, 1);
+    mbar_init(z_bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -356,6 +434,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (split) tma_load_2d(smem_u32(a_lo(s, mt)), &tmA_lo, fb, k0, m0 + mt * 128);
         }
         tma_load_2d(smem_u32(b_hi(s)), &tmB, fb, k0, n0);
+      }
+      if (p.dw_K > 0) {
+        // z tiles of the previous layer for the fused epilogue: wait until the tensor core has finished with the
+        // pipeline stage(s) a tile overwrites (the MMA warp's commit on `empty` of the stage's last chunk)
+        auto wait_stage_free = [&](int s) {
+          if (s >= num_kc) return;                                   // stage never used
+          const int kc_last = ((num_kc - 1 - s) / S) * S + s;         // last chunk that occupied stage s
+          mbar_wait(empty0 + 8 * s, (uint32_t)(kc_last / S) & 1u);
+        };
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          if (p.z_early) wait_stage_free((num_kc - 2 + mt) % S);
+          else if (mt == 0) for (int s = 0; s < S; ++s) wait_stage_free(s);
+          const uint32_t zb = z_bar0 + 8 * mt;
+          mbar_expect_tx(zb, 4u * z_blk);
+          const uint32_t dst = smem_u32(smem) + z_off(mt);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) tma_load_2d(dst + b * z_blk, &tmZ, zb, m0 + mt * 128 + b * 32, n0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -432,15 +529,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       for (int mt = 0; mt < MT; ++mt) {
         const int c = m0 + mt * 128 + quad * 32 + lane;
         const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 256);
+        mbar_wait(z_bar0 + 8 * mt, 0);
+        const uint8_t* zs = smem + z_off(mt) + (uint32_t)quad * z_blk;
+        float* red = reinterpret_cast<float*>(smem + p.red_off);
         switch (p.dw_K) {
-          case 1: tc_epilogue_dwbwd<1>(tbase, p, act, c, n0, half); break;
-          case 3: tc_epilogue_dwbwd<3>(tbase, p, act, c, n0, half); break;
-          case 5: tc_epilogue_dwbwd<5>(tbase, p, act, c, n0, half); break;
-          case 7: tc_epilogue_dwbwd<7>(tbase, p, act, c, n0, half); break;
-          case 9: tc_epilogue_dwbwd<9>(tbase, p, act, c, n0, half); break;
-          case 11: tc_epilogue_dwbwd<11>(tbase, p, act, c, n0, half); break;
-          case 13: tc_epilogue_dwbwd<13>(tbase, p, act, c, n0, half); break;
-          default: tc_epilogue_dwbwd<15>(tbase, p, act, c, n0, half); break;
+          case 1: tc_epilogue_dwbwd<1>(tbase, p, act, c, n0, half, zs, red); break;
+          case 3: tc_epilogue_dwbwd<3>(tbase, p, act, c, n0, half, zs, red); break;
+          case 5: tc_epilogue_dwbwd<5>(tbase, p, act, c, n0, half, zs, red); break;
+          case 7: tc_epilogue_dwbwd<7>(tbase, p, act, c, n0, half, zs, red); break;
+          case 9: tc_epilogue_dwbwd<9>(tbase, p, act, c, n0, half, zs, red); break;
+          default: tc_epilogue_dwbwd<11>(tbase, p, act, c, n0, half, zs, red); break;
         }
       }
     } else
@@ -459,8 +557,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         default: tc_epilogue<true, true, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
       }
       if (p.stats) {
-        atomicAdd(p.stats + co, (double)s1);
-        atomicAdd(p.stats + p.M_total + co, (double)s2);
+        // combine the two warps of each lane quadrant in shared memory, then one pass of atomics with consecutive
+        // threads on consecutive channels: one visit per 128-byte line per CTA (same-line atomics serialise in L2)
+        float* red = reinterpret_cast<float*>(smem + p.red_off);          // [2 halves][2 sums][128 channels]
+        const int chl = (int)(threadIdx.x & 127u);
+        red[(half * 2 + 0) * 128 + chl] = s1;
+        red[(half * 2 + 1) * 128 + chl] = s2;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int which = tid >> 7, ch = tid & 127;                        // threads 0-127: sum, 128-255: sum of squares
+        atomicAdd(p.stats + (size_t)which * p.M_total + (co - chl) + ch, (double)red[which * 128 + ch] + (double)red[(2 + which) * 128 + ch]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");                    // `red` is reused by the next channel half
       }
     }
   }
@@ -470,6 +576,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
+  if (p.has_bn) tn_bn_fold_last(p.bn, p.stats, p.M_total, gridDim.x * gridDim.y);
   if (threadIdx.x == 0 && p.trace && blockIdx.y == 0 && blockIdx.x < 256) {
     unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[257 + 2 * blockIdx.x] = (long long)gt; }
   if (threadIdx.x == 0) { TC_TRACE(102); if (p.trace && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) {
@@ -723,15 +830,37 @@ extern "C" int tn_split_tf32(const float* W, float* ws, int M, int Kd, int trans
   return TN_OK;
 }
 
+__global__ void split_tf32_batch_kernel(const tn_split_job* __restrict__ jobs) {
+  const tn_split_job j = jobs[blockIdx.y];
+  const size_t n = (size_t)j.M * j.Kd;
+  float* hi = j.ws;
+  float* lo = j.ws + n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / j.Kd), k = (int)(i - (size_t)m * j.Kd);
+    const float x = j.transpose ? j.W[(size_t)k * j.M + m] : j.W[i];
+    const float h = __uint_as_float(rna_tf32(x));
+    hi[i] = h;
+    lo[i] = __uint_as_float(rna_tf32(x - h));
+  }
+}
+extern "C" int tn_split_tf32_batch(const tn_split_job* jobs_dev, int njobs, int max_elems, void* stream) {
+  TN_REQUIRE(jobs_dev && njobs > 0 && njobs <= 65535 && max_elems > 0, "split_tf32_batch: bad arguments");
+  int bx = (max_elems + 255) / 256;
+  if (bx > 64) bx = 64;
+  split_tf32_batch_kernel<<<dim3(bx, njobs), 256, 0, (cudaStream_t)stream>>>(jobs_dev);
+  TN_LAUNCH_CHECK("split_tf32_batch_kernel");
+  return TN_OK;
+}
+
 // rows of output per CTA: the multiple of 16 that minimises waves * (tile rows + fixed cost).
 // `halo` extra MMA columns ride along (fused depthwise backward).
-static int pick_bn(long long R, int groups, int per_row_stage_bytes, int fixed_stage_bytes, int halo, int* stages_out) {
+static int pick_bn(long long R, int groups, int per_row_stage_bytes, int fixed_stage_bytes, int halo, int reserve, int* stages_out) {
   const int sms = tn_num_sms();
   int best = 0;
   double best_cost = 1e30;
   for (int bn = 256 - halo; bn >= 32; bn -= 16) {
     long long stage = (long long)fixed_stage_bytes + (long long)(bn + halo) * per_row_stage_bytes;
-    int stages = (int)((TC_SMEM_LIMIT - 2048) / stage);
+    int stages = (int)((TC_SMEM_LIMIT - 2048 - reserve) / stage);
     if (stages < 2) continue;
     long long ctas = ((R + bn - 1) / bn) * groups;
     long long waves = (ctas + sms - 1) / sms;
@@ -754,7 +883,9 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   const int mult = nsplit == 3 ? 2 : 1;
   const int halo = p.dw_K > 1 ? 16 : 0;              // 2 * PAD <= 14 rows of halo, rounded to the MMA's N granularity
   int stages = 2;
-  const int bno = pick_bn(R, groups, mult * TC_BK * 4, mult * MT * 128 * TC_BK * 4, halo, &stages);
+  // fused depthwise backward: [2 halves][128 channels][K + 3 sums] of staging behind the pipeline stages
+  const int red_bytes = p.dw_K > 0 ? (2 * 128 * (p.dw_K + 3) * 4 + 1023) / 1024 * 1024 : (p.stats ? 2048 : 0);
+  const int bno = pick_bn(R, groups, mult * TC_BK * 4, mult * MT * 128 * TC_BK * 4, halo, red_bytes, &stages);
   TN_REQUIRE(bno >= 32, "gemm_tc: no tile configuration fits shared memory");
   const int bn = bno + halo;
   CUtensorMap mA_hi, mA_lo, mB;
@@ -767,14 +898,25 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   while (MT == 1 && cols < bn) cols <<= 1;
   p.tmem_cols = cols;
   const size_t stage_bytes = (size_t)mult * (MT * 128 * TC_BK * 4 + (size_t)bn * TC_BK * 4);
-  const size_t smem = stage_bytes * stages + 1024;
+  const size_t smem = stage_bytes * stages + red_bytes + 1024;
+  p.red_off = (uint32_t)(stage_bytes * stages);
+  CUtensorMap mZ = mB;
+  if (p.dw_K > 0) {
+    // z tiles of the fused epilogue reuse the pipeline memory: one tile = 128 channels x bn rows = 4 blocks of bn x 128 B
+    if ((rc = make_map(&mZ, p.zprev, R, M, bn)) != TN_OK) return rc;
+    const size_t ztile = (size_t)4 * bn * 128;
+    p.z_early = (stages == 2 && Kd / TC_BK >= 2 && ztile <= stage_bytes) ? 1 : 0;
+    p.z_off1 = (uint32_t)(((ztile > stage_bytes ? ztile : stage_bytes) + 1023) / 1024 * 1024);
+    TN_REQUIRE(MT == 1 || p.z_early || p.z_off1 + ztile <= stage_bytes * stages, "gemm_tc_dwbwd: z tiles do not fit the pipeline memory");
+    TN_REQUIRE(ztile <= stage_bytes * stages, "gemm_tc_dwbwd: z tile does not fit the pipeline memory");
+  }
   dim3 grid(tn_cdiv(R, bno), groups);
   if (MT == 2) {
     TN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<2><<<grid, TC_GEMM_THREADS, smem, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB, p);
+    gemm_tc_kernel<2><<<grid, TC_GEMM_THREADS, smem, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB, mZ, p);
   } else {
     TN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<1><<<grid, TC_GEMM_THREADS, smem, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB, p);
+    gemm_tc_kernel<1><<<grid, TC_GEMM_THREADS, smem, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB, mZ, p);
   }
   TN_LAUNCH_CHECK("gemm_tc_kernel");
   return TN_OK;
@@ -790,6 +932,26 @@ extern "C" int tn_gemm_tc(const float* X, const float* ws, const float* bias, fl
   return launch_gemm_tc(X, ws, p, R, Kd, M, nsplit, stream);
 }
 
+static int check_bn(const tn_bn_fold* bn, const double* stats) {
+  TN_REQUIRE(bn && stats, "bn fold needs the statistics buffer");
+  TN_REQUIRE(bn->gamma && bn->beta && bn->scale && bn->shift && bn->mean && bn->invstd && bn->counter, "bn fold: null field");
+  TN_REQUIRE(bn->n >= 1.0, "bn fold: n must be >= 1");
+  TN_REQUIRE((bn->running_mean == nullptr) == (bn->running_var == nullptr), "bn fold: running_mean/var must come together");
+  return TN_OK;
+}
+
+extern "C" int tn_gemm_tc_bn(const float* X, const float* ws, const float* bias, float* Z, double* stats, const tn_bn_fold* bn,
+                             int R, int Kd, int M, int flags, int nsplit, void* stream) {
+  TN_REQUIRE(Z, "gemm_tc_bn: null output");
+  int rc = check_bn(bn, stats);
+  if (rc != TN_OK) return rc;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = bias; p.Z = Z; p.stats = stats; p.flags = flags;
+  p.bn = *bn; p.has_bn = 1;
+  return launch_gemm_tc(X, ws, p, R, Kd, M, nsplit, stream);
+}
+
 // Data gradient of a depthwise-separable conv block in one kernel:
 //   du = dZ[R, Co] W[Co, C]            (tensor cores; ws = tn_split_tf32(W, transpose = 1), [2, C, Co])
 //   dzprev = act'(zprev) * scale * depthwise_K^T(du),   dw += ..., dbias += ..., dscale += ..., dshift += ...
@@ -800,11 +962,12 @@ extern "C" int tn_gemm_tc_dwbwd(const float* dZ, const float* ws, const float* z
                                 const float* shift, int relu, float drop_p, const unsigned long long* seed,
                                 unsigned int layer, int B, int T, int Co, int C, int K, int nsplit, void* stream) {
   TN_REQUIRE(zprev && dzprev && dw_w && g_dw, "gemm_tc_dwbwd: null tensor");
-  TN_REQUIRE(K >= 1 && K <= 15 && (K & 1), "gemm_tc_dwbwd: unsupported depthwise kernel size %d (odd sizes 1..15)", K);
+  TN_REQUIRE(K >= 1 && K <= 11 && (K & 1), "gemm_tc_dwbwd: unsupported depthwise kernel size %d (odd sizes 1..11)", K);
   TN_REQUIRE(!scale || (shift && g_dscale && g_dshift), "gemm_tc_dwbwd: scale given without shift/dscale/dshift");
   TN_REQUIRE(drop_p <= 0.f || seed, "gemm_tc_dwbwd: dropout needs a seed");
   long long R = (long long)B * T;
   TN_REQUIRE(B > 0 && T > 0 && R < (1ll << 31), "gemm_tc_dwbwd: bad B/T");
+  TN_REQUIRE((R + 16) * C < (1ll << 32), "gemm_tc_dwbwd: R * C must stay below 2^32 (32-bit element offsets)");
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.dw_K = K; p.dw_T = T; p.dw_w = dw_w; p.zprev = zprev; p.dzprev = dzprev;

@@ -15,6 +15,7 @@ from typing import Callable, Optional
 import torch
 
 from . import _lib
+from . import _ops as ops
 
 
 class GraphedTrainStep:
@@ -27,7 +28,7 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model: torch.nn.Module, mel, batch: int, n_samples: int, device, use_graph: bool = True,
-                 warmup: int = 3, after_backward: Optional[Callable[[], None]] = None):
+                 warmup: int = 3, after_backward: Optional[Callable[[], None]] = None, use_arena: bool = True):
         self.model, self.mel, self.device = model, mel, torch.device(device)
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.wave = torch.zeros(batch, n_samples, device=self.device)
@@ -36,16 +37,27 @@ class GraphedTrainStep:
         self.loss = self.emb = self.preds = None
         self.graph = None
         self.launches_per_step = 0
+        # every zero-initialised accumulator and every parameter gradient of a step lives in one buffer that a
+        # single memset clears (ops.ZeroArena): the first (measuring) step sizes it
+        self.arena = ops.ZeroArena(self.device) if use_arena else None
         if use_graph:
             self._capture(warmup)
 
     def _body(self):
-        for p in self.params:
-            p.grad = None
-        self.emb, self.preds, self.loss = self.model(self.mel.batch(self.wave), speakers=self.labels)
-        self.loss.backward()
-        if self.after_backward is not None:
-            self.after_backward()
+        prev = ops.set_arena(self.arena)
+        try:
+            if self.arena is not None:
+                self.arena.begin_step()
+            for p in self.params:
+                p.grad = None
+            self.emb, self.preds, self.loss = self.model(self.mel.batch(self.wave), speakers=self.labels)
+            self.loss.backward()
+            if self.arena is not None and self.arena.measuring:
+                self.arena.finish_measuring()
+            if self.after_backward is not None:
+                self.after_backward()
+        finally:
+            ops.set_arena(prev)
 
     def _capture(self, warmup: int):
         try:    # warm-up runs on a side stream by design; the AccumulateGrad stream-mismatch warning is noise here
@@ -55,7 +67,7 @@ class GraphedTrainStep:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):
+            for _ in range(max(2, warmup)):
                 self._body()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
@@ -95,11 +107,36 @@ class GradAllReduce:
         self.group = group
         self.flat = None
 
+    def _arena_span(self, grads):
+        """The slice of the active ZeroArena that holds every gradient, as one fp32 tensor (or None)."""
+        arena = ops._ARENA
+        if arena is None or arena.buf is None:
+            return None
+        base, size = arena.buf.data_ptr(), arena.buf.numel()
+        lo, hi = size, 0
+        for g in grads:
+            off = g.data_ptr() - base
+            if off < 0 or off + g.numel() * g.element_size() > size or g.dtype != torch.float32 or not g.is_contiguous():
+                return None
+            lo, hi = min(lo, off), max(hi, off + g.numel() * 4)
+        lo -= lo % 16
+        hi += (-hi) % 16
+        return arena.buf[lo:min(hi, size)].view(torch.float32)
+
     def __call__(self):
         if self.world <= 1:
             return
         import torch.distributed as dist
         grads = [p.grad for p in self.params]
+        span = self._arena_span(grads)
+        if span is not None:
+            # gradients already share one buffer: exchange it in place (no pack / unpack copies)
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(span, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(span, group=self.group)
+                span.mul_(1.0 / self.world)
+            return
         if self.flat is None:
             self.flat = torch.empty(sum(g.numel() for g in grads), device=grads[0].device, dtype=grads[0].dtype)
         torch._foreach_copy_(list(self.flat.split([g.numel() for g in grads])), [g.reshape(-1) for g in grads])

@@ -35,6 +35,29 @@ class TitaNet(nn.Module):
         self._dropout = float(dropout)
         self.to(device)
 
+    def _tc_weights(self):
+        """Weights of the 1x1 convs / linears that run on the tensor cores (pointwise, skip, epilog, ASP)."""
+        ws = []
+        for m in self.modules():
+            if isinstance(m, nn.Conv1d) and m.groups == 1 and m.kernel_size[0] == 1:
+                ws.append(m.weight)
+            elif isinstance(m, AttentiveStatsPooling):
+                ws += [m.in_linear.weight, m.out_linear.weight]
+        return [w for w in ws if w.is_cuda and w.shape[0] % 32 == 0 and w.shape[1] % 32 == 0
+                and (w.shape[0] % 128 == 0 or w.shape[1] % 128 == 0)]
+
+    def _refresh_weight_splits(self):
+        """One launch per step for every tf32 weight split (ops.SplitCache)."""
+        if not ops.TC_ENABLED:
+            return
+        cache = self.__dict__.get("_split_cache")
+        if cache is None or (cache and cache.stale()):
+            weights = self._tc_weights()
+            cache = ops.SplitCache(weights) if weights else False
+            self.__dict__["_split_cache"] = cache
+        if cache:
+            cache.refresh()
+
     def get_n_params(self, div=1):
         """Number of trainable parameters, optionally divided (reference: src/models.py:221-228)."""
         return sum([np.prod(p.size()) for p in self.parameters() if p.requires_grad]) / div
@@ -79,6 +102,7 @@ class TitaNet(nn.Module):
         """[B, M, T] spectrograms -> unit-norm embeddings [B, E]; with ``speakers`` the
         loss head's ``(embeddings, preds, loss)`` (reference: src/models.py:318-339)."""
         require_cuda(spectrograms)
+        self._refresh_weight_splits()
         dctx = new_dropout_ctx(spectrograms.device, self.training and self._dropout > 0)
         encodings = self.encoder._fwd(Lazy.from_ncw(spectrograms), dctx)
         embeddings = self.decoder._fwd(encodings)
@@ -137,8 +161,7 @@ class MegaBlock(nn.Module):
         x = x.materialise()
         B, T = x.B, x.T
         skip_conv, skip_bn = self.skip_connection[0], self.skip_connection[1]
-        s, s_stats = ops.conv_gemm(x.z, skip_conv.weight, skip_conv.bias, B, T, want_stats=self.training)
-        scs, shs = ops.bn_fold(s_stats, skip_bn, float(B * T))
+        s, scs, shs = ops.conv_gemm_bn(x.z, skip_conv.weight, skip_conv.bias, skip_bn, B, T)
         y = x
         n_sub = len(self.sub_blocks) - 1
         for j in range(n_sub):
@@ -182,8 +205,7 @@ class Decoder(nn.Module):
         sc1, sh1 = ops.bn_fold(st1, bn1, float(B))
         pooled = ops.Act.apply(pooled, sc1, sh1, None, False, 0.0, 0)
         lin, bn2 = self.linear[0], self.linear[1]
-        z, st2 = ops.conv_gemm(pooled, lin.weight, lin.bias, B, 1, want_stats=bn2.training)
-        sc2, sh2 = ops.bn_fold(st2, bn2, float(B))
+        z, sc2, sh2 = ops.conv_gemm_bn(pooled, lin.weight, lin.bias, bn2, B, 1)
         return ops.Act.apply(z, sc2, sh2, None, False, 0.0, 0)
 
     def forward(self, encodings):

@@ -118,6 +118,16 @@ class Conv1dSamePadding(nn.Conv1d):
             return u, stats
         raise NotImplementedError("grouped convolutions other than depthwise are not supported")
 
+    def _fwd_bn(self, x: Lazy, bn: nn.BatchNorm1d):
+        """Lazy in -> (z, scale, shift) of ``bn(conv(x))`` (BatchNorm folded, see ops.ConvGemmBN)."""
+        _check_conv_supported(self)
+        if self.groups == 1:
+            x = x.materialise()
+            return ops.conv_gemm_bn(x.z, self.weight, self.bias, bn, x.B, x.T)
+        z, stats = self._fwd(x, want_stats=bn.training)
+        scale, shift = ops.bn_fold(stats, bn, float(z.shape[0]))
+        return z, scale, shift
+
     def forward(self, inputs):
         x = Lazy.from_ncw(inputs)
         z, _ = self._fwd(x)
@@ -141,6 +151,17 @@ class DepthwiseConv1d(nn.Module):
         _check_conv_supported(dw)
         return ops.DwPw.apply(x.z, x.scale, x.shift, dw.weight, dw.bias, pw.weight, pw.bias, x.seed, x.relu, x.p, x.layer,
                               x.B, x.T, want_stats)
+
+    def _fwd_bn(self, x: Lazy, bn: nn.BatchNorm1d):
+        dw, pw = self.conv[0], self.conv[1]
+        _check_conv_supported(dw)
+        if ops._bn_trainable(bn):
+            return ops.DwPwBN.apply(x.z, x.scale, x.shift, dw.weight, dw.bias, pw.weight, pw.bias, bn.weight, bn.bias,
+                                    bn.running_mean, bn.running_var, bn.num_batches_tracked, bn.momentum, bn.eps, x.seed,
+                                    x.relu, x.p, x.layer, x.B, x.T)
+        z, stats = self._fwd(x, want_stats=bn.training)
+        scale, shift = ops.bn_fold(stats, bn, float(z.shape[0]))
+        return z, scale, shift
 
     def forward(self, inputs):
         x = Lazy.from_ncw(inputs)
@@ -173,8 +194,7 @@ class ConvBlock1d(nn.Module):
         if self._activation == "tanh":
             raise NotImplementedError("ConvBlock1d(activation='tanh') is not on the TitaNet path and has no kernel")
         conv, bn = self.conv_block[0], self.conv_block[1]
-        z, stats = conv._fwd(x, want_stats=self.training)
-        scale, shift = ops.bn_fold(stats, bn, float(z.shape[0]))
+        z, scale, shift = conv._fwd_bn(x, bn)
         p = self._dropout if self.training else 0.0
         return Lazy(z, x.B, x.T, scale, shift, relu=self._activation == "relu", p=p, seed=dctx.seed if p > 0 else None,
                     layer=dctx.next_layer())

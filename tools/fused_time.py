@@ -26,4 +26,6 @@ for p, lazy in ((0.1, True), (0.0, True), (0.0, False)):
     e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
     LIB.call("tn_gemm_tc_set_trace", tr.data_ptr()); tr.zero_(); run(p, lazy); torch.cuda.synchronize(); LIB.call("tn_gemm_tc_set_trace", None)
     t = tr.cpu().tolist(); us = lambda v: (v - t[0]) / 1.9e3
-    print(f"p={p} lazy={lazy}: {e0.elapsed_time(e1) * 100:.1f} us/launch; CTA0: accum_seen {us(t[100]):.1f} us, epilogue_done {us(t[101]):.1f} us")
+    print(f"p={p} lazy={lazy}: {e0.elapsed_time(e1) * 100:.1f} us/launch; CTA0: accum_seen {us(t[100]):.1f} us, epilogue_done {us(t[101]):.1f} us, "
+          f"kernel_end {us(t[102]):.1f}; warp2 mt0 [z ready {us(t[113]):.1f}, primed {us(t[114]):.1f}, loop done {us(t[115]):.1f}, atomics issued {us(t[116]):.1f}] "
+          f"mt1 [{us(t[117]):.1f}, {us(t[118]):.1f}, {us(t[119]):.1f}, {us(t[120]):.1f}]; globaltimer CTA span {(t[112] - t[111]) / 1e3:.1f} us")
