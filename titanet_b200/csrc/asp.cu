@@ -10,6 +10,7 @@
 // aux[b, 0, c] = log-sum-exp of e over t ; aux[b, 1, c] = sum_t alpha x^2
 __global__ void __launch_bounds__(128) asp_pool_fwd_kernel(const float* __restrict__ e, const float* __restrict__ x,
                                                            float* __restrict__ pooled, float* __restrict__ aux, int T, int D, float eps) {
+  tn_grid_dep_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (c >= D) return;
   const float* ep = e + (size_t)b * T * D + c;
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(128) asp_pool_bwd_kernel(const float* __restri
                                                            const float* __restrict__ aux, const float* __restrict__ e,
                                                            const float* __restrict__ x, float* __restrict__ de,
                                                            float* __restrict__ dx, int T, int D, float eps) {
+  tn_grid_dep_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (c >= D) return;
   const float mu = pooled[(size_t)b * 2 * D + c], sigma = pooled[(size_t)b * 2 * D + D + c];
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(128) asp_pool_bwd_kernel(const float* __restri
 extern "C" int tn_asp_pool_fwd(const float* e, const float* x, float* pooled, float* aux, int B, int T, int D, float eps, void* stream) {
   TN_REQUIRE(e && x && pooled && aux && B > 0 && B <= 65535 && T > 0 && D > 0, "asp_pool_fwd: bad arguments (B=%d T=%d D=%d)", B, T, D);
   dim3 grid(tn_cdiv(D, 128), B);
-  asp_pool_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(e, x, pooled, aux, T, D, eps);
+  tn_launch(asp_pool_fwd_kernel, grid, 128, 0, stream, e, x, pooled, aux, T, D, eps);
   TN_LAUNCH_CHECK("asp_pool_fwd_kernel");
   return TN_OK;
 }
@@ -72,7 +74,7 @@ extern "C" int tn_asp_pool_bwd(const float* dpooled, const float* pooled, const 
                                float* de, float* dx, int B, int T, int D, float eps, void* stream) {
   TN_REQUIRE(dpooled && pooled && aux && e && x && de && dx && B > 0 && B <= 65535 && T > 0 && D > 0, "asp_pool_bwd: bad arguments (B=%d T=%d D=%d)", B, T, D);
   dim3 grid(tn_cdiv(D, 128), B);
-  asp_pool_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(dpooled, pooled, aux, e, x, de, dx, T, D, eps);
+  tn_launch(asp_pool_bwd_kernel, grid, 128, 0, stream, dpooled, pooled, aux, e, x, de, dx, T, D, eps);
   TN_LAUNCH_CHECK("asp_pool_bwd_kernel");
   return TN_OK;
 }

@@ -10,6 +10,7 @@ template <int K>
 __global__ void __launch_bounds__(DW_THREADS) dw_fwd_kernel(const float* __restrict__ z, float* __restrict__ u,
                                                             const float* __restrict__ w, const float* __restrict__ bias,
                                                             TnAct act, int R, int C, int T, int rpb) {
+  tn_grid_dep_sync();
   constexpr int PAD = K / 2;
   act = tn_act_init(act);
   TnTile tl = tn_tile(C);
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(DW_THREADS, (K <= 5 ? 2 : 1)) dw_bwd_kernel(co
                                                             float* __restrict__ dw, float* __restrict__ dbias,
                                                             float* __restrict__ dscale, float* __restrict__ dshift,
                                                             TnAct act, int R, int C, int T, int rpb) {
+  tn_grid_dep_sync();
   constexpr int PAD = K / 2;
   act = tn_act_init(act);
   __shared__ float4 red[DW_THREADS];
@@ -181,7 +183,7 @@ extern "C" int tn_dw_fwd(const float* z, float* u, const float* w, const float* 
   TN_REQUIRE(R < (1ll << 31), "dw_fwd: B*T too large");
   int rpb = dw_rows_per_block(C, K);
   TnAct act = tn_make_act(scale, shift, relu, drop_p, seed, layer);
-  DW_DISPATCH(K, (dw_fwd_kernel<KK><<<tn_cdiv(R, rpb), DW_THREADS, 0, (cudaStream_t)stream>>>(z, u, w, bias, act, (int)R, C, T, rpb)));
+  DW_DISPATCH(K, (tn_launch(dw_fwd_kernel<KK>, tn_cdiv(R, rpb), DW_THREADS, 0, stream, z, u, w, bias, act, (int)R, C, T, rpb)));
   TN_LAUNCH_CHECK("dw_fwd_kernel");
   return TN_OK;
 }
@@ -199,7 +201,7 @@ extern "C" int tn_dw_bwd(const float* du, const float* z, float* dz, const float
   TN_REQUIRE(R < (1ll << 31), "dw_bwd: B*T too large");
   int rpb = dw_rows_per_block(C, K);
   TnAct act = tn_make_act(scale, shift, relu, drop_p, seed, layer);
-  DW_DISPATCH(K, (dw_bwd_kernel<KK><<<tn_cdiv(R, rpb), DW_THREADS, 0, (cudaStream_t)stream>>>(du, z, dz, w, dw, dbias, dscale, dshift, act, (int)R, C, T, rpb)));
+  DW_DISPATCH(K, (tn_launch(dw_bwd_kernel<KK>, tn_cdiv(R, rpb), DW_THREADS, 0, stream, du, z, dz, w, dw, dbias, dscale, dshift, act, (int)R, C, T, rpb)));
   TN_LAUNCH_CHECK("dw_bwd_kernel");
   return TN_OK;
 }

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 // ---------------------------------------------------------------------------
 // error plumbing
@@ -29,6 +30,15 @@ int tn_num_sms() {
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   return g_num_sms;
+}
+
+static int g_pdl = -1;
+bool tn_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("TN_PDL");
+    g_pdl = (e && atoi(e) != 0) ? 1 : 0;      // measured: no gain on the graph-replayed step (the kernels cannot co-reside), so off by default
+  }
+  return g_pdl != 0;
 }
 
 extern "C" int tn_device_check(void) {
@@ -60,6 +70,7 @@ static int rows_per_block(long long R) {
 // [B, C, T] <-> [B, T, C]
 // ---------------------------------------------------------------------------
 __global__ void transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int rows, int cols) {
+  tn_grid_dep_sync();
   // per batch item: x is [rows, cols] -> y is [cols, rows]
   __shared__ float tile[32][33];
   const float* xb = x + (size_t)blockIdx.z * rows * cols;
@@ -80,7 +91,7 @@ __global__ void transpose_kernel(const float* __restrict__ x, float* __restrict_
 static int launch_transpose(const float* x, float* y, int B, int rows, int cols, void* stream) {
   TN_REQUIRE(B > 0 && rows > 0 && cols > 0 && B <= 65535, "transpose: bad shape B=%d rows=%d cols=%d", B, rows, cols);
   dim3 grid(tn_cdiv(cols, 32), tn_cdiv(rows, 32), B), block(32, 8);
-  transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, rows, cols);
+  tn_launch(transpose_kernel, grid, block, 0, stream, x, y, rows, cols);
   TN_LAUNCH_CHECK("transpose_kernel");
   return TN_OK;
 }
@@ -96,6 +107,7 @@ extern "C" int tn_nwc_to_ncw(const float* x, float* y, int B, int C, int T, void
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(TN_EW_THREADS) act_fwd_kernel(const float* __restrict__ z, float* __restrict__ y,
                                                                 TnAct act, int R, int C, int rpb) {
+  tn_grid_dep_sync();
   act = tn_act_init(act);
   TnTile tl = tn_tile(C);
   int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
@@ -112,6 +124,7 @@ __global__ void __launch_bounds__(TN_EW_THREADS) act_fwd_kernel(const float* __r
 __global__ void __launch_bounds__(TN_EW_THREADS) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                                 float* __restrict__ dz, float* __restrict__ dscale,
                                                                 float* __restrict__ dshift, TnAct act, int R, int C, int rpb) {
+  tn_grid_dep_sync();
   act = tn_act_init(act);
   __shared__ float4 red[TN_EW_THREADS];
   TnTile tl = tn_tile(C);
@@ -142,7 +155,7 @@ extern "C" int tn_act_fwd(const float* z, float* y, const float* scale, const fl
   TN_REQUIRE(scale && shift, "act_fwd: scale/shift are required");
   TN_REQUIRE(tn_aligned16(z) && tn_aligned16(y) && tn_aligned16(scale) && tn_aligned16(shift), "act_fwd: pointers must be 16B aligned");
   int rpb = rows_per_block(R);
-  act_fwd_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(z, y, tn_make_act(scale, shift, relu, drop_p, seed, layer), R, C, rpb);
+  tn_launch(act_fwd_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, z, y, tn_make_act(scale, shift, relu, drop_p, seed, layer), R, C, rpb);
   TN_LAUNCH_CHECK("act_fwd_kernel");
   return TN_OK;
 }
@@ -155,7 +168,7 @@ extern "C" int tn_act_bwd(const float* dy, const float* z, float* dz, float* dsc
   TN_REQUIRE(scale && shift && dscale && dshift, "act_bwd: scale/shift/dscale/dshift are required");
   TN_REQUIRE(tn_aligned16(z) && tn_aligned16(dy) && tn_aligned16(dz) && tn_aligned16(scale) && tn_aligned16(shift), "act_bwd: pointers must be 16B aligned");
   int rpb = rows_per_block(R);
-  act_bwd_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(dy, z, dz, dscale, dshift, tn_make_act(scale, shift, relu, drop_p, seed, layer), R, C, rpb);
+  tn_launch(act_bwd_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, dy, z, dz, dscale, dshift, tn_make_act(scale, shift, relu, drop_p, seed, layer), R, C, rpb);
   TN_LAUNCH_CHECK("act_bwd_kernel");
   return TN_OK;
 }
@@ -164,6 +177,7 @@ extern "C" int tn_act_bwd(const float* dy, const float* z, float* dz, float* dsc
 // per-channel sum / sum of squares of an [R, C] tensor (fp64 accumulators)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(TN_EW_THREADS) colstats_kernel(const float* __restrict__ x, double* __restrict__ stats, int R, int C, int rpb) {
+  tn_grid_dep_sync();
   __shared__ float4 red[TN_EW_THREADS];
   TnTile tl = tn_tile(C);
   int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
@@ -183,13 +197,14 @@ __global__ void __launch_bounds__(TN_EW_THREADS) colstats_kernel(const float* __
 extern "C" int tn_colstats(const float* x, double* stats, int R, int C, void* stream) {
   TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0 && tn_aligned16(x), "colstats: need C %% 4 == 0 and aligned x (R=%d C=%d)", R, C);
   int rpb = rows_per_block(R);
-  colstats_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(x, stats, R, C, rpb);
+  tn_launch(colstats_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, x, stats, R, C, rpb);
   TN_LAUNCH_CHECK("colstats_kernel");
   return TN_OK;
 }
 
 // per-channel column sums in fp32 (bias gradients): out[c] += sum_r x[r, c]
 __global__ void __launch_bounds__(TN_EW_THREADS) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int R, int C, int rpb) {
+  tn_grid_dep_sync();
   __shared__ float4 red[TN_EW_THREADS];
   TnTile tl = tn_tile(C);
   int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
@@ -204,7 +219,7 @@ __global__ void __launch_bounds__(TN_EW_THREADS) colsum_kernel(const float* __re
 extern "C" int tn_colsum(const float* x, float* out, int R, int C, void* stream) {
   TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0 && tn_aligned16(x) && out, "colsum: need C %% 4 == 0 and aligned x (R=%d C=%d)", R, C);
   int rpb = rows_per_block(R);
-  colsum_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(x, out, R, C, rpb);
+  tn_launch(colsum_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, x, out, R, C, rpb);
   TN_LAUNCH_CHECK("colsum_kernel");
   return TN_OK;
 }
@@ -217,6 +232,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double n, c
                                    long long* __restrict__ nbt, float momentum, float eps, int training,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out, int C) {
+  tn_grid_dep_sync();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && training && nbt) *nbt += 1;
   if (c >= C) return;
@@ -248,7 +264,7 @@ extern "C" int tn_bn_finalize(const double* stats, double n, const float* gamma,
                               float* scale, float* shift, float* mean, float* invstd, int C, void* stream) {
   TN_REQUIRE(C > 0 && gamma && beta && scale && shift && mean && invstd, "bn_finalize: null argument");
   TN_REQUIRE(training ? (stats != nullptr && n >= 1.0) : (running_mean && running_var), "bn_finalize: missing statistics");
-  bn_finalize_kernel<<<tn_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(stats, n, gamma, beta, running_mean, running_var,
+  tn_launch(bn_finalize_kernel, tn_cdiv(C, 128), 128, 0, stream, stats, n, gamma, beta, running_mean, running_var,
                                                                          num_batches_tracked, momentum, eps, training, scale,
                                                                          shift, mean, invstd, C);
   TN_LAUNCH_CHECK("bn_finalize_kernel");
@@ -262,6 +278,7 @@ __global__ void bn_bwd_coef_kernel(const float* __restrict__ dscale, const float
                                    const float* __restrict__ mean, const float* __restrict__ invstd,
                                    const float* __restrict__ gamma, double n, int training, float* __restrict__ dgamma,
                                    float* __restrict__ dbeta, double* __restrict__ dstats, int C) {
+  tn_grid_dep_sync();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double dsc = dscale[c], dsh = dshift[c], mu = mean[c], r = invstd[c], g = gamma[c];
@@ -280,7 +297,7 @@ extern "C" int tn_bn_bwd_coef(const float* dscale, const float* dshift, const fl
                               int C, void* stream) {
   TN_REQUIRE(C > 0 && dscale && dshift && mean && invstd && gamma && dgamma && dbeta, "bn_bwd_coef: null argument");
   TN_REQUIRE(!training || dstats, "bn_bwd_coef: training mode needs dstats");
-  bn_bwd_coef_kernel<<<tn_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(dscale, dshift, mean, invstd, gamma, n, training, dgamma, dbeta, dstats, C);
+  tn_launch(bn_bwd_coef_kernel, tn_cdiv(C, 128), 128, 0, stream, dscale, dshift, mean, invstd, gamma, n, training, dgamma, dbeta, dstats, C);
   TN_LAUNCH_CHECK("bn_bwd_coef_kernel");
   return TN_OK;
 }
@@ -292,6 +309,7 @@ extern "C" int tn_bn_bwd_coef(const float* dscale, const float* dshift, const fl
 __global__ void __launch_bounds__(TN_EW_THREADS) stats_bwd_kernel(const float* __restrict__ dzd, const float* __restrict__ z,
                                                                   const double* __restrict__ dstats, float* __restrict__ out,
                                                                   float* __restrict__ dbias, int R, int C, int rpb) {
+  tn_grid_dep_sync();
   __shared__ float4 red[TN_EW_THREADS];
   TnTile tl = tn_tile(C);
   const int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
@@ -320,7 +338,7 @@ extern "C" int tn_stats_bwd(const float* dz_direct, const float* z, const double
   TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0 && z && dstats && out && tn_aligned16(out) && tn_aligned16(z) && (!dz_direct || tn_aligned16(dz_direct)),
              "stats_bwd: need C %% 4 == 0 and aligned tensors (R=%d C=%d)", R, C);
   int rpb = rows_per_block(R);
-  stats_bwd_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(dz_direct, z, dstats, out, dbias, R, C, rpb);
+  tn_launch(stats_bwd_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, dz_direct, z, dstats, out, dbias, R, C, rpb);
   TN_LAUNCH_CHECK("stats_bwd_kernel");
   return TN_OK;
 }
@@ -333,6 +351,7 @@ __global__ void __launch_bounds__(TN_EW_THREADS) bn_stats_bwd_kernel(const float
                                                                      const float* __restrict__ gamma, double n, float* __restrict__ out,
                                                                      float* __restrict__ dbias, float* __restrict__ dgamma,
                                                                      float* __restrict__ dbeta, int R, int C, int rpb) {
+  tn_grid_dep_sync();
   __shared__ float4 red[TN_EW_THREADS];
   TnTile tl = tn_tile(C);
   const int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
@@ -376,7 +395,7 @@ extern "C" int tn_bn_stats_bwd(const float* dz_direct, const float* z, const flo
              "bn_stats_bwd: need C %% 4 == 0 and aligned tensors (R=%d C=%d)", R, C);
   TN_REQUIRE(dscale && dshift && mean && invstd && gamma && dgamma && dbeta && n >= 1.0, "bn_stats_bwd: null argument");
   int rpb = rows_per_block(R);
-  bn_stats_bwd_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(dz_direct, z, dscale, dshift, mean, invstd, gamma, n,
+  tn_launch(bn_stats_bwd_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, dz_direct, z, dscale, dshift, mean, invstd, gamma, n,
                                                                                     out, dbias, dgamma, dbeta, R, C, rpb);
   TN_LAUNCH_CHECK("bn_stats_bwd_kernel");
   return TN_OK;
@@ -384,6 +403,7 @@ extern "C" int tn_bn_stats_bwd(const float* dz_direct, const float* z, const flo
 
 // advance the dropout seed state (splitmix64) and publish the new step seed
 __global__ void seed_next_kernel(unsigned long long* state, unsigned long long* out) {
+  tn_grid_dep_sync();
   unsigned long long z = (*state += 0x9E3779B97F4A7C15ull);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
@@ -391,13 +411,14 @@ __global__ void seed_next_kernel(unsigned long long* state, unsigned long long* 
 }
 extern "C" int tn_seed_next(unsigned long long* state, unsigned long long* out, void* stream) {
   TN_REQUIRE(state && out, "seed_next: null argument");
-  seed_next_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, out);
+  tn_launch(seed_next_kernel, 1, 1, 0, stream, state, out);
   TN_LAUNCH_CHECK("seed_next_kernel");
   return TN_OK;
 }
 
 // out = dh * (1 - h^2)
 __global__ void tanh_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ h, float* __restrict__ out, size_t n) {
+  tn_grid_dep_sync();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -410,7 +431,7 @@ extern "C" int tn_tanh_bwd(const float* dh, const float* h, float* out, long lon
   int blocks = (int)((n + 255) / 256);
   int cap = tn_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  tanh_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dh, h, out, (size_t)n);
+  tn_launch(tanh_bwd_kernel, blocks, 256, 0, stream, dh, h, out, (size_t)n);
   TN_LAUNCH_CHECK("tanh_bwd_kernel");
   return TN_OK;
 }
@@ -419,6 +440,7 @@ extern "C" int tn_tanh_bwd(const float* dh, const float* h, float* out, long lon
 // row L2 normalisation:  y = x / max(||x||, eps)   (eps = 0: plain division)
 // ---------------------------------------------------------------------------
 __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ norms, int B, int E, float eps) {
+  tn_grid_dep_sync();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= B) return;
   const float* xr = x + (size_t)row * E;
@@ -432,6 +454,7 @@ __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict
 // dx = (dy - y * <y, dy>) / max(norm, eps) + dnorm * y      (dnorm optional: grad w.r.t. the returned norm)
 __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ norms,
                                   const float* __restrict__ dnorm, float* __restrict__ dx, int B, int E, float eps) {
+  tn_grid_dep_sync();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= B) return;
   const float* yr = y + (size_t)row * E;
@@ -450,14 +473,14 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __r
 }
 extern "C" int tn_l2norm_fwd(const float* x, float* y, float* norms, int B, int E, float eps, void* stream) {
   TN_REQUIRE(B > 0 && E > 0 && x && y, "l2norm_fwd: bad arguments");
-  l2norm_fwd_kernel<<<tn_cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(x, y, norms, B, E, eps);
+  tn_launch(l2norm_fwd_kernel, tn_cdiv(B, 4), 128, 0, stream, x, y, norms, B, E, eps);
   TN_LAUNCH_CHECK("l2norm_fwd_kernel");
   return TN_OK;
 }
 extern "C" int tn_l2norm_bwd(const float* dy, const float* y, const float* norms, const float* dnorm, float* dx, int B, int E,
                              float eps, void* stream) {
   TN_REQUIRE(B > 0 && E > 0 && dy && y && norms && dx, "l2norm_bwd: bad arguments");
-  l2norm_bwd_kernel<<<tn_cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(dy, y, norms, dnorm, dx, B, E, eps);
+  tn_launch(l2norm_bwd_kernel, tn_cdiv(B, 4), 128, 0, stream, dy, y, norms, dnorm, dx, B, E, eps);
   TN_LAUNCH_CHECK("l2norm_bwd_kernel");
   return TN_OK;
 }

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
                                                         const float* __restrict__ bias, float* __restrict__ Z,
                                                         double* __restrict__ stats, int R, int T, int Ci, int Co, int K,
                                                         int transpose_w, int flags, int kk_per_split, tn_bn_fold bn, int has_bn) {
+  tn_grid_dep_sync();
   __shared__ float As[GK][GM + 4];
   __shared__ float Bs[GK][GN + 4];
   __shared__ float red1[16][GN], red2[16][GN];
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ dZ, const float* __restrict__ X,
                                                          float* __restrict__ dW, float* __restrict__ dbias, int R, int T,
                                                          int Ci, int Co, int K, int rows_per_split) {
+  tn_grid_dep_sync();
   __shared__ float As[GK][GM + 4];   // As[row][co]
   __shared__ float Bs[GK][GN + 4];   // Bs[row][kk]
   const int tid = threadIdx.x;
@@ -214,7 +216,7 @@ static int conv_gemm_launch(const float* X, const float* W, const float* bias, f
   memset(&f, 0, sizeof(f));
   const int fuse_bn = (bn && splits == 1) ? 1 : 0;
   if (fuse_bn) f = *bn;
-  conv_gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, W, bias, Z, stats, (int)R, T, Ci, Co, K, transpose_w, flags, kps, f, fuse_bn);
+  tn_launch(conv_gemm_kernel, grid, 256, 0, stream, X, W, bias, Z, stats, (int)R, T, Ci, Co, K, transpose_w, flags, kps, f, fuse_bn);
   TN_LAUNCH_CHECK("conv_gemm_kernel");
   if (splits > 1 && stats) {                       // split-K: statistics (and the fold) from the finished tensor
     int rc = tn_colstats(Z, stats, (int)R, Co, stream);
@@ -254,7 +256,7 @@ extern "C" int tn_conv_wgrad_simt(const float* dZ, const float* X, float* dW, fl
   split = (R + rps - 1) / rps;
   dim3 grid(tn_cdiv(Co, GM), tn_cdiv((long long)K * Ci, GN), (unsigned)split);
   TN_REQUIRE(grid.y <= 65535, "conv_wgrad: K*Ci too large");
-  conv_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dZ, X, dW, dbias, (int)R, T, Ci, Co, K, rps);
+  tn_launch(conv_wgrad_kernel, grid, 256, 0, stream, dZ, X, dW, dbias, (int)R, T, Ci, Co, K, rps);
   TN_LAUNCH_CHECK("conv_wgrad_kernel");
   return TN_OK;
 }

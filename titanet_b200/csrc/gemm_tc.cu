@@ -31,8 +31,13 @@
 #define TC_THREADS 192        // wgrad kernel: TMA + MMA + 4 epilogue warps
 #define TC_GEMM_THREADS 320   // GEMM kernel: TMA + MMA + 8 transform/epilogue warps (two per TMEM lane quadrant)
 #define TC_EPI_THREADS 256
-#define TC_BK 32              // fp32 elements per K chunk = one 128-byte swizzle row
-#define TC_MAX_STAGES 4
+// fp32 elements per K chunk: 32 = 128-byte swizzled rows, 2 stages of ~100 KB; 16 = 64-byte rows, 4 stages of ~50 KB.
+// Measured at R=19264, 256x256 (tools/trace_gemm.py): BK=32 delivers a chunk (84 KB) every 1.41 us against 1.06 us of MMA,
+// mainloop 12.8 us; BK=16 delivers 42 KB every 0.95 us (64-byte rows use the TMA unit worse), mainloop 15.9 us.  Both sit
+// at the per-SM TMA rate (~45-60 GB/s), most of it weight tiles re-streamed by every CTA; multicasting the weights
+// across a 2-CTA cluster (TN_TC_CLUSTER=1) is functional but changes nothing (L2 already de-duplicates neighbours).
+#define TC_BK 32
+#define TC_MAX_STAGES 6
 #define TC_SMEM_LIMIT (227 * 1024)
 
 // ---------------------------------------------------------------------------
@@ -66,6 +71,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// multicast variants for a 2-CTA cluster: the tile (and its complete_tx) lands at the same offsets in every CTA of
+// `mask`; the commit arrives on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -109,9 +132,14 @@ __device__ __forceinline__ uint32_t rna_tf32(float x) {
   return u;
 }
 
-// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
+// shared-memory matrix descriptor, K-major operand tile of TC_BK fp32 per row:
+// 128-byte rows: SWIZZLE_128B (layout 2), 8-row groups 1024 B apart; 64-byte rows: SWIZZLE_64B (layout 4), 512 B apart
 __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
+#if TC_BK == 32
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+#else
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+#endif
 }
 
 // Epilogue of one 128-channel accumulator tile: TMEM -> registers -> (+bias, tanh, +=) -> global.
@@ -148,6 +176,7 @@ struct TcParams {
   float* Z;
   double* stats;
   int R, Kd, M_total, BN, stages, nsplit, flags, tmem_cols;
+  int cluster2;          // launched as 2-CTA clusters along x: the two CTAs share (multicast) the weight tiles
   long long* trace;      // optional timeline buffer (debug): 128 slots per traced CTA
   // fused depthwise-backward epilogue (dw_K > 0): this GEMM is the data gradient of a pointwise conv
   // whose input was depthwise_K(act(zprev)); the epilogue turns du (in TMEM) into dzprev directly.
@@ -359,6 +388,7 @@ template <int MT>
 __global__ void __launch_bounds__(TC_GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ, TcParams p) {
+  tn_grid_dep_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 1 + 2];
   __shared__ uint32_t tmem_base_slot;
@@ -391,8 +421,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint32_t z_bar0 = smem_u32(&bars[3 * TC_MAX_STAGES + 1]);     // fused depthwise backward: z tile of output-channel half mt
   // z tile mt (128 channels = 4 blocks of [BN rows x 128 B]) lands in pipeline memory the mainloop no longer needs
   const uint32_t z_blk = (uint32_t)BN * 128u;
+  // z_early: the last S chunks sit in stages 0 .. S-1 in order (num_kc % S == 0), tile mt takes stages [mt S/2, (mt+1) S/2)
   auto z_off = [&](int mt) -> uint32_t {
-    if (p.z_early) return (uint32_t)(((num_kc - 2 + mt) % S)) * stage_bytes;     // the stage of the (mt+1)-th last-but-one chunk
+    if (p.z_early) return (uint32_t)(mt * (S >> 1)) * stage_bytes;
     return mt ? p.z_off1 : 0u;
   };
 
@@ -400,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     for (int s = 0; s < S; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(ready0 + 8 * s, TC_EPI_THREADS);
-      mbar_init(empty0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, p.cluster2 ? 2 : 1);     // cluster: both CTAs' tensor cores must be done with the stage
     }
     mbar_init(accum_bar, 1);
     mbar_init(z_bar0, 1);
@@ -412,9 +443,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (p.cluster2) cluster_sync_all();        // the peer's barriers must be initialised before anything is multicast to them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t cta_rank = p.cluster2 ? cluster_cta_rank() : 0u;
   if (threadIdx.x == 0) TC_TRACE(0);
 
   if (warp == 0) {
@@ -428,10 +461,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         TC_TRACE(1 + kc);
         mbar_expect_tx(fb, skip_a ? b_tile : tx_bytes);
         const int k0 = kc * TC_BK;
+        if (MT == 2 && p.cluster2) {
+          // each CTA of the pair fetches ONE of the two 128-channel weight tiles and multicasts it to both: the weights
+          // are identical for every row tile, and re-streaming them per CTA made the mainloop L2-bandwidth bound
+          const int mt = (int)cta_rank;
+          tma_load_2d_mc(smem_u32(a_hi(s, mt)), &tmA_hi, fb, k0, m0 + mt * 128, (uint16_t)3);
+          if (split) tma_load_2d_mc(smem_u32(a_lo(s, mt)), &tmA_lo, fb, k0, m0 + mt * 128, (uint16_t)3);
+        } else {
 #pragma unroll
-        for (int mt = 0; mt < MT && !skip_a; ++mt) {
-          tma_load_2d(smem_u32(a_hi(s, mt)), &tmA_hi, fb, k0, m0 + mt * 128);
-          if (split) tma_load_2d(smem_u32(a_lo(s, mt)), &tmA_lo, fb, k0, m0 + mt * 128);
+          for (int mt = 0; mt < MT && !skip_a; ++mt) {
+            tma_load_2d(smem_u32(a_hi(s, mt)), &tmA_hi, fb, k0, m0 + mt * 128);
+            if (split) tma_load_2d(smem_u32(a_lo(s, mt)), &tmA_lo, fb, k0, m0 + mt * 128);
+          }
         }
         tma_load_2d(smem_u32(b_hi(s)), &tmB, fb, k0, n0);
       }
@@ -445,7 +486,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         };
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          if (p.z_early) wait_stage_free((num_kc - 2 + mt) % S);
+          if (p.z_early) wait_stage_free((mt + 1) * (S >> 1) - 1);      // commits complete in order: the lower stages are free too
           else if (mt == 0) for (int s = 0; s < S; ++s) wait_stage_free(s);
           const uint32_t zb = z_bar0 + 8 * mt;
           mbar_expect_tx(zb, 4u * z_blk);
@@ -488,7 +529,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
         }
-        tc_commit(empty0 + 8 * s);           // stage free once these MMAs have read it
+        if (p.cluster2) tc_commit_mc(empty0 + 8 * s, (uint16_t)3);   // stage free (in both CTAs) once these MMAs have read it
+        else tc_commit(empty0 + 8 * s);
         TC_TRACE(80 + kc);
       }
       tc_commit(accum_bar);                  // accumulators complete
@@ -576,6 +618,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
+  if (p.cluster2) cluster_sync_all();        // the peer may still signal this CTA's barriers until its MMAs have drained
   if (p.has_bn) tn_bn_fold_last(p.bn, p.stats, p.M_total, gridDim.x * gridDim.y);
   if (threadIdx.x == 0 && p.trace && blockIdx.y == 0 && blockIdx.x < 256) {
     unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[257 + 2 * blockIdx.x] = (long long)gt; }
@@ -587,6 +630,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // weight split: ws[0] = rna_tf32(W), ws[1] = rna_tf32(W - ws[0]); optional transpose
 // ---------------------------------------------------------------------------
 __global__ void split_tf32_kernel(const float* __restrict__ W, float* __restrict__ hi, float* __restrict__ lo, int M, int Kd, int transpose) {
+  tn_grid_dep_sync();
   // output [M, Kd]; input [M, Kd] or (transpose) [Kd, M]
   const size_t n = (size_t)M * Kd;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -620,14 +664,16 @@ static int get_encoder() {
   return TN_OK;
 }
 
-// 2-D fp32 row-major [rows, cols] tensor, box = [box_rows, 32 cols], 128-byte swizzle
-static int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, int box_rows) {
+// 2-D fp32 row-major [rows, cols] tensor, box = [box_rows, box_cols]: 32 columns -> 128-byte swizzle, 16 -> 64-byte swizzle
+static int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, int box_rows, int box_cols = TC_BK) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
-  cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TN_REQUIRE(box_cols == 32 || box_cols == 16, "make_map: box of %d columns", box_cols);
   TN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for [%lld, %lld] box %d", (int)r, rows, cols, box_rows);
   return TN_OK;
 }
@@ -663,6 +709,7 @@ struct WgParams {
 template <int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, WgParams p) {
+  tn_grid_dep_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 1];
   __shared__ uint32_t tmem_base_slot;
@@ -807,10 +854,10 @@ extern "C" int tn_wgrad_tc(const float* dZ, const float* U, float* dW, int R, in
   dim3 grid(co_groups, ci_blocks, splits);
   if (MT == 2) {
     TN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wgrad_tc_kernel<2><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mA, mB, p);
+    tn_launch(wgrad_tc_kernel<2>, grid, TC_THREADS, smem, stream, mA, mB, p);
   } else {
     TN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wgrad_tc_kernel<1><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mA, mB, p);
+    tn_launch(wgrad_tc_kernel<1>, grid, TC_THREADS, smem, stream, mA, mB, p);
   }
   TN_LAUNCH_CHECK("wgrad_tc_kernel");
   return TN_OK;
@@ -825,12 +872,13 @@ extern "C" int tn_split_tf32(const float* W, float* ws, int M, int Kd, int trans
   size_t n = (size_t)M * Kd;
   int blocks = (int)((n + 255) / 256);
   if (blocks > tn_num_sms() * 8) blocks = tn_num_sms() * 8;
-  split_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, ws, ws + n, M, Kd, transpose);
+  tn_launch(split_tf32_kernel, blocks, 256, 0, stream, W, ws, ws + n, M, Kd, transpose);
   TN_LAUNCH_CHECK("split_tf32_kernel");
   return TN_OK;
 }
 
 __global__ void split_tf32_batch_kernel(const tn_split_job* __restrict__ jobs) {
+  tn_grid_dep_sync();
   const tn_split_job j = jobs[blockIdx.y];
   const size_t n = (size_t)j.M * j.Kd;
   float* hi = j.ws;
@@ -847,7 +895,7 @@ extern "C" int tn_split_tf32_batch(const tn_split_job* jobs_dev, int njobs, int 
   TN_REQUIRE(jobs_dev && njobs > 0 && njobs <= 65535 && max_elems > 0, "split_tf32_batch: bad arguments");
   int bx = (max_elems + 255) / 256;
   if (bx > 64) bx = 64;
-  split_tf32_batch_kernel<<<dim3(bx, njobs), 256, 0, (cudaStream_t)stream>>>(jobs_dev);
+  tn_launch(split_tf32_batch_kernel, dim3(bx, njobs), 256, 0, stream, jobs_dev);
   TN_LAUNCH_CHECK("split_tf32_batch_kernel");
   return TN_OK;
 }
@@ -903,20 +951,30 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   CUtensorMap mZ = mB;
   if (p.dw_K > 0) {
     // z tiles of the fused epilogue reuse the pipeline memory: one tile = 128 channels x bn rows = 4 blocks of bn x 128 B
-    if ((rc = make_map(&mZ, p.zprev, R, M, bn)) != TN_OK) return rc;
+    if ((rc = make_map(&mZ, p.zprev, R, M, bn, 32)) != TN_OK) return rc;
     const size_t ztile = (size_t)4 * bn * 128;
-    p.z_early = (stages == 2 && Kd / TC_BK >= 2 && ztile <= stage_bytes) ? 1 : 0;
+    const int num_kc = Kd / TC_BK;
+    p.z_early = (stages % 2 == 0 && num_kc % stages == 0 && ztile <= stage_bytes * (stages / 2)) ? 1 : 0;
     p.z_off1 = (uint32_t)(((ztile > stage_bytes ? ztile : stage_bytes) + 1023) / 1024 * 1024);
     TN_REQUIRE(MT == 1 || p.z_early || p.z_off1 + ztile <= stage_bytes * stages, "gemm_tc_dwbwd: z tiles do not fit the pipeline memory");
     TN_REQUIRE(ztile <= stage_bytes * stages, "gemm_tc_dwbwd: z tile does not fit the pipeline memory");
   }
   dim3 grid(tn_cdiv(R, bno), groups);
-  if (MT == 2) {
+  static int use_cluster = -1;
+  if (use_cluster < 0) { const char* e = getenv("TN_TC_CLUSTER"); use_cluster = (e && atoi(e) != 0) ? 1 : 0; }   // no gain measured: opt-in
+  if (MT == 2 && use_cluster && grid.x >= 2) {
+    // pairs of row tiles share the weight tiles by TMA multicast; an odd grid gets one idle tile (rows >= R: zero-filled loads,
+    // nothing stored)
+    grid.x = (grid.x + 1) & ~1u;
+    p.cluster2 = 1;
     TN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<2><<<grid, TC_GEMM_THREADS, smem, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB, mZ, p);
+    tn_launch_cluster(gemm_tc_kernel<2>, grid, TC_GEMM_THREADS, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
+  } else if (MT == 2) {
+    TN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tn_launch(gemm_tc_kernel<2>, grid, TC_GEMM_THREADS, smem, stream, mA_hi, mA_lo, mB, mZ, p);
   } else {
     TN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<1><<<grid, TC_GEMM_THREADS, smem, (cudaStream_t)stream>>>(mA_hi, mA_lo, mB, mZ, p);
+    tn_launch(gemm_tc_kernel<1>, grid, TC_GEMM_THREADS, smem, stream, mA_hi, mA_lo, mB, mZ, p);
   }
   TN_LAUNCH_CHECK("gemm_tc_kernel");
   return TN_OK;

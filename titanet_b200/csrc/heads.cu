@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(128) ce_kernel(const float* __restrict__ logit
                                                  float* __restrict__ loss_row, long long* __restrict__ preds,
                                                  float* __restrict__ dlogits, const float* __restrict__ gout, int B, int Cn,
                                                  float inv_B) {
+  tn_grid_dep_sync();
   if (gout) inv_B *= __ldg(gout);
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= B) return;
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(128) margin_kernel(const float* __restrict__ r
                                                      float* __restrict__ dnorm, const float* __restrict__ gout, int B, int Cn,
                                                      float scale, int use_norm_scale, float m1, float m2, float m3, float eps,
                                                      float inv_B) {
+  tn_grid_dep_sync();
   if (gout) inv_B *= __ldg(gout);
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= B) return;
@@ -103,6 +105,7 @@ __global__ void __launch_bounds__(128) margin_kernel(const float* __restrict__ r
 
 // deterministic mean of the per-row losses
 __global__ void loss_mean_kernel(const float* __restrict__ loss_row, float* __restrict__ loss, int B) {
+  tn_grid_dep_sync();
   __shared__ float sh[32];
   float s = 0.f;
   for (int i = threadIdx.x; i < B; i += blockDim.x) s += loss_row[i];
@@ -118,6 +121,7 @@ __global__ void loss_mean_kernel(const float* __restrict__ loss_row, float* __re
 
 // W[row, :] /= max(||W[row, :]||, eps)   in place (F.normalize(dim=1))
 __global__ void __launch_bounds__(128) rownorm_kernel(float* __restrict__ W, int rows, int cols, float eps) {
+  tn_grid_dep_sync();
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   float* w = W + (size_t)row * cols;
@@ -130,9 +134,9 @@ __global__ void __launch_bounds__(128) rownorm_kernel(float* __restrict__ W, int
 extern "C" int tn_ce_fwd_bwd(const float* logits, const long long* targets, float* loss_row, float* loss, long long* preds,
                              float* dlogits, const float* gout, int B, int Cn, void* stream) {
   TN_REQUIRE(logits && targets && loss_row && loss && preds && B > 0 && Cn > 0, "ce_fwd_bwd: bad arguments");
-  ce_kernel<<<tn_cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(logits, targets, loss_row, preds, dlogits, gout, B, Cn, 1.0f / (float)B);
+  tn_launch(ce_kernel, tn_cdiv(B, 4), 128, 0, stream, logits, targets, loss_row, preds, dlogits, gout, B, Cn, 1.0f / (float)B);
   TN_LAUNCH_CHECK("ce_kernel");
-  loss_mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(loss_row, loss, B);
+  tn_launch(loss_mean_kernel, 1, 256, 0, stream, loss_row, loss, B);
   TN_LAUNCH_CHECK("loss_mean_kernel");
   return TN_OK;
 }
@@ -142,17 +146,17 @@ extern "C" int tn_margin_fwd_bwd(const float* raw_cos, const float* norms, const
                                  float scale, int use_norm_scale, float m1, float m2, float m3, float eps, void* stream) {
   TN_REQUIRE(raw_cos && targets && loss_row && loss && preds && B > 0 && Cn > 0, "margin_fwd_bwd: bad arguments");
   TN_REQUIRE(!use_norm_scale || norms, "margin_fwd_bwd: scale=None needs the input norms");
-  margin_kernel<<<tn_cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(raw_cos, norms, targets, loss_row, preds, draw, dnorm, gout, B,
+  tn_launch(margin_kernel, tn_cdiv(B, 4), 128, 0, stream, raw_cos, norms, targets, loss_row, preds, draw, dnorm, gout, B,
                                                                   Cn, scale, use_norm_scale, m1, m2, m3, eps, 1.0f / (float)B);
   TN_LAUNCH_CHECK("margin_kernel");
-  loss_mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(loss_row, loss, B);
+  tn_launch(loss_mean_kernel, 1, 256, 0, stream, loss_row, loss, B);
   TN_LAUNCH_CHECK("loss_mean_kernel");
   return TN_OK;
 }
 
 extern "C" int tn_rownorm_inplace(float* W, int rows, int cols, float eps, void* stream) {
   TN_REQUIRE(W && rows > 0 && cols > 0, "rownorm_inplace: bad arguments");
-  rownorm_kernel<<<tn_cdiv(rows, 4), 128, 0, (cudaStream_t)stream>>>(W, rows, cols, eps);
+  tn_launch(rownorm_kernel, tn_cdiv(rows, 4), 128, 0, stream, W, rows, cols, eps);
   TN_LAUNCH_CHECK("rownorm_kernel");
   return TN_OK;
 }

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float* __restric
                                                           const int* __restrict__ band_lo, const int* __restrict__ band_hi,
                                                           float* __restrict__ out, int L_stride, int L_full, int T_out,
                                                           int N, int log2N, int hop, int n_mels, int nwc) {
+  tn_grid_dep_sync();
   extern __shared__ float smem[];
   const int NF = N / 2 + 1;
   float2* buf = reinterpret_cast<float2*>(smem);             // N complex
@@ -142,7 +143,7 @@ extern "C" int tn_mel_fwd(const float* wave, const int* lengths, const float* wi
     TN_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   dim3 grid(tn_cdiv(T_out, MEL_FT), B);
-  mel_kernel<<<grid, MEL_THREADS, smem, (cudaStream_t)stream>>>(wave, lengths, window, fb, band_lo, band_hi, out, L_stride,
+  tn_launch(mel_kernel, grid, MEL_THREADS, smem, stream, wave, lengths, window, fb, band_lo, band_hi, out, L_stride,
                                                                  L_full, T_out, n_fft, log2N, hop, n_mels, nwc);
   TN_LAUNCH_CHECK("mel_kernel");
   return TN_OK;

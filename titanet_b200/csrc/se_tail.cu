@@ -12,6 +12,7 @@
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(TN_EW_THREADS) se_mean_kernel(const float* __restrict__ z, float* __restrict__ m, TnAct act,
                                                                 int T, int C, int tpb, float inv_T) {
+  tn_grid_dep_sync();
   act = tn_act_init(act);
   __shared__ float4 red[TN_EW_THREADS];
   TnTile tl = tn_tile(C);
@@ -32,6 +33,7 @@ __global__ void __launch_bounds__(TN_EW_THREADS) se_mean_kernel(const float* __r
 // excitation MLP, one block per batch item.  smem: m[C] + h[Cr]
 __global__ void __launch_bounds__(256) se_mlp_fwd_kernel(const float* __restrict__ m, const float* __restrict__ W1,
                                                          const float* __restrict__ W2, float* __restrict__ gate, int C, int Cr) {
+  tn_grid_dep_sync();
   extern __shared__ float sm[];
   float* ms = sm;
   float* hs = sm + C;
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(256) se_mlp_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ m, const float* __restrict__ W1,
                                                          const float* __restrict__ W2, float* __restrict__ dm,
                                                          float* __restrict__ dW1, float* __restrict__ dW2, int C, int Cr) {
+  tn_grid_dep_sync();
   extern __shared__ float sm[];
   float* ms = sm;
   float* hs = ms + C;
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(256) se_mlp_bwd_kernel(const float* __restrict
 __global__ void __launch_bounds__(TN_EW_THREADS) tail_fwd_kernel(const float* __restrict__ z3, const float* __restrict__ s,
                                                                  const float* __restrict__ gate, float* __restrict__ out,
                                                                  TnAct act3, TnAct act_s, TnAct act_o, int R, int T, int C, int rpb) {
+  tn_grid_dep_sync();
   act3 = tn_act_init(act3);
   act_o = tn_act_init(act_o);
   TnTile tl = tn_tile(C);
@@ -130,6 +134,7 @@ __device__ __forceinline__ float4 tail_gout(float4 dout, float4 o, float inv_kee
 __global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd1_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                                                   const float* __restrict__ z3, float* __restrict__ dgate,
                                                                   TnAct act3, float inv_keep_o, int T, int C, int tpb) {
+  tn_grid_dep_sync();
   act3 = tn_act_init(act3);
   __shared__ float4 red[TN_EW_THREADS];
   TnTile tl = tn_tile(C);
@@ -158,6 +163,7 @@ __global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd2_kernel(const float* _
                                                                   float* __restrict__ dscs, float* __restrict__ dshs,
                                                                   TnAct act3, TnAct act_s, float inv_keep_o, float inv_T, int R,
                                                                   int T, int C, int rpb) {
+  tn_grid_dep_sync();
   act3 = tn_act_init(act3);
   __shared__ float4 red[TN_EW_THREADS];
   TnTile tl = tn_tile(C);
@@ -219,7 +225,7 @@ extern "C" int tn_se_mean(const float* z3, float* m, const float* scale, const f
   TN_CUDA(cudaMemsetAsync(m, 0, sizeof(float) * (size_t)B * C, (cudaStream_t)stream));
   int tpb = time_per_block(B, T);
   dim3 grid(tn_cdiv(T, tpb), B);
-  se_mean_kernel<<<grid, TN_EW_THREADS, 0, (cudaStream_t)stream>>>(z3, m, tn_make_act(scale, shift, relu, drop_p, seed, layer), T, C, tpb, 1.0f / (float)T);
+  tn_launch(se_mean_kernel, grid, TN_EW_THREADS, 0, stream, z3, m, tn_make_act(scale, shift, relu, drop_p, seed, layer), T, C, tpb, 1.0f / (float)T);
   TN_LAUNCH_CHECK("se_mean_kernel");
   return TN_OK;
 }
@@ -228,7 +234,7 @@ extern "C" int tn_se_mlp_fwd(const float* m, const float* W1, const float* W2, f
   TN_REQUIRE(B > 0 && C > 0 && Cr > 0 && m && W1 && W2 && gate, "se_mlp_fwd: bad arguments");
   size_t smem = sizeof(float) * (size_t)(C + Cr);
   TN_REQUIRE(smem <= 48 * 1024, "se_mlp_fwd: C too large");
-  se_mlp_fwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(m, W1, W2, gate, C, Cr);
+  tn_launch(se_mlp_fwd_kernel, B, 256, smem, stream, m, W1, W2, gate, C, Cr);
   TN_LAUNCH_CHECK("se_mlp_fwd_kernel");
   return TN_OK;
 }
@@ -238,7 +244,7 @@ extern "C" int tn_se_mlp_bwd(const float* dgate, const float* gate, const float*
   TN_REQUIRE(B > 0 && C > 0 && Cr > 0 && dgate && gate && m && W1 && W2 && dm && dW1 && dW2, "se_mlp_bwd: bad arguments");
   size_t smem = sizeof(float) * (size_t)(2 * C + 2 * Cr);
   TN_REQUIRE(smem <= 48 * 1024, "se_mlp_bwd: C too large");
-  se_mlp_bwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(dgate, gate, m, W1, W2, dm, dW1, dW2, C, Cr);
+  tn_launch(se_mlp_bwd_kernel, B, 256, smem, stream, dgate, gate, m, W1, W2, dm, dW1, dW2, C, Cr);
   TN_LAUNCH_CHECK("se_mlp_bwd_kernel");
   return TN_OK;
 }
@@ -251,7 +257,7 @@ extern "C" int tn_tail_fwd(const float* z3, const float* s, const float* gate, f
   long long R = (long long)B * T;
   TN_REQUIRE(R < (1ll << 31), "tail_fwd: B*T too large");
   int rpb = tail_rows_per_block(R);
-  tail_fwd_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(
+  tn_launch(tail_fwd_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, 
       z3, s, gate, out, tn_make_act(scale3, shift3, 1, drop3, seed, layer3), tn_make_act(scale_s, shift_s, 0, 0.f, seed, 0),
       tn_make_act(scale_s, shift_s, 1, drop_o, seed, layer_o), (int)R, T, C, rpb);
   TN_LAUNCH_CHECK("tail_fwd_kernel");
@@ -267,7 +273,7 @@ extern "C" int tn_tail_bwd1(const float* dout, const float* out, const float* z3
   int tpb = time_per_block(B, T);
   dim3 grid(tn_cdiv(T, tpb), B);
   float inv_keep_o = drop_o > 0.f ? 1.f / (1.f - drop_o) : 1.f;
-  tail_bwd1_kernel<<<grid, TN_EW_THREADS, 0, (cudaStream_t)stream>>>(dout, out, z3, dgate, tn_make_act(scale3, shift3, 1, drop3, seed, layer3), inv_keep_o, T, C, tpb);
+  tn_launch(tail_bwd1_kernel, grid, TN_EW_THREADS, 0, stream, dout, out, z3, dgate, tn_make_act(scale3, shift3, 1, drop3, seed, layer3), inv_keep_o, T, C, tpb);
   TN_LAUNCH_CHECK("tail_bwd1_kernel");
   return TN_OK;
 }
@@ -284,7 +290,7 @@ extern "C" int tn_tail_bwd2(const float* dout, const float* out, const float* z3
   TN_REQUIRE(R < (1ll << 31), "tail_bwd2: B*T too large");
   int rpb = tail_rows_per_block(R);
   float inv_keep_o = drop_o > 0.f ? 1.f / (1.f - drop_o) : 1.f;
-  tail_bwd2_kernel<<<tn_cdiv(R, rpb), TN_EW_THREADS, 0, (cudaStream_t)stream>>>(
+  tn_launch(tail_bwd2_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, 
       dout, out, z3, s, gate, dm, dz3, ds, dsc3, dsh3, dscs, dshs, tn_make_act(scale3, shift3, 1, drop3, seed, layer3),
       tn_make_act(scale_s, shift_s, 0, 0.f, seed, 0), inv_keep_o, 1.0f / (float)T, (int)R, T, C, rpb);
   TN_LAUNCH_CHECK("tail_bwd2_kernel");

@@ -19,6 +19,8 @@ fns = {
  "dw_fwd": lambda: call("tn_dw_fwd", ptr(z), ptr(u), ptr(w), ptr(b), ptr(sc), ptr(sh), 1, P, ptr(seed), 3, B, T, C, K),
  "dw_bwd": lambda: call("tn_dw_bwd", ptr(du), ptr(z), ptr(dz), ptr(w), ptr(dw), ptr(db), ptr(dsc), ptr(dsh), ptr(sc), ptr(sh), 1, P, ptr(seed), 3, B, T, C, K),
  "stats_bwd": lambda: call("tn_stats_bwd", ptr(du), ptr(z), ptr(dst), ptr(dz), ptr(db), R, C),
+ "bn_stats_bwd": lambda: call("tn_bn_stats_bwd", ptr(du), ptr(z), ptr(dsc), ptr(dsh), ptr(sh), ptr(sc), ptr(sc), float(R), ptr(dz), ptr(db), ptr(dsc), ptr(dsh), R, C),
+ "tail_bwd1": lambda: call("tn_tail_bwd1", ptr(dout), ptr(out), ptr(z), ptr(dm), ptr(sc), ptr(sh), P, 3, P, ptr(seed), B, T, C),
  "tail_fwd": lambda: call("tn_tail_fwd", ptr(z), ptr(s_), ptr(gate), ptr(out), ptr(sc), ptr(sh), P, 3, ptr(sc), ptr(sh), P, 4, ptr(seed), B, T, C),
  "tail_bwd2": lambda: call("tn_tail_bwd2", ptr(dout), ptr(out), ptr(z), ptr(s_), ptr(gate), ptr(dm), ptr(dz), ptr(du), red[0].data_ptr(), red[1].data_ptr(), red[2].data_ptr(), red[3].data_ptr(), ptr(sc), ptr(sh), P, 3, ptr(sc), ptr(sh), P, ptr(seed), B, T, C),
  "se_mean": lambda: call("tn_se_mean", ptr(z), ptr(gate), ptr(sc), ptr(sh), 1, P, ptr(seed), 3, B, T, C),
