@@ -243,8 +243,8 @@ def run_ours(args):
     wave_d, labels_d = wave_h.to(dev), labels_h.to(dev)
 
     from titanet_b200.engine import GradAllReduce, GraphedTrainStep
-    allreduce = GradAllReduce(params, world)
     gts = GraphedTrainStep(model, mel, B, L, dev, use_graph=not args.no_graph, warmup=max(3, args.warmup))
+    allreduce = GradAllReduce(params, world, arena=gts.arena)     # every gradient lives in the step's arena: one in-place NCCL call
 
     def step_resident():
         gts.load(wave_d, labels_d)        # device -> device: inputs are already in HBM

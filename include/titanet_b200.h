@@ -167,6 +167,7 @@ int tn_tanh_bwd(const float* dh, const float* h, float* out, long long n, void* 
 
 /* ---- squeeze-excitation + mega-block tail: SqueezeExcitation.forward
  *      (src/modules.py:173-189), MegaBlock.forward (src/models.py:467-472) ----------- */
+/* m[b,c] += mean_t act(z3)[b,t,c]  (ACCUMULATED: the caller zeroes m; scale == NULL: z3 is already the activation) */
 int tn_se_mean(const float* z3, float* m, const float* scale, const float* shift, int relu, float drop_p,
                const unsigned long long* seed, unsigned int layer, int B, int T, int C, void* stream);
 int tn_se_mlp_fwd(const float* m, const float* W1, const float* W2, float* gate, int B, int C, int Cr, void* stream);
@@ -175,6 +176,7 @@ int tn_se_mlp_bwd(const float* dgate, const float* gate, const float* m, const f
 int tn_tail_fwd(const float* z3, const float* s, const float* gate, float* out, const float* scale3, const float* shift3,
                 float drop3, unsigned int layer3, const float* scale_s, const float* shift_s, float drop_o,
                 unsigned int layer_o, const unsigned long long* seed, int B, int T, int C, void* stream);
+/* dgate is ACCUMULATED (the caller zeroes it) */
 int tn_tail_bwd1(const float* dout, const float* out, const float* z3, float* dgate, const float* scale3,
                  const float* shift3, float drop3, unsigned int layer3, float drop_o, const unsigned long long* seed, int B, int T,
                  int C, void* stream);
@@ -182,6 +184,14 @@ int tn_tail_bwd2(const float* dout, const float* out, const float* z3, const flo
                  float* dz3, float* ds, float* dsc3, float* dsh3, float* dscs, float* dshs, const float* scale3,
                  const float* shift3, float drop3, unsigned int layer3, const float* scale_s, const float* shift_s,
                  float drop_o, const unsigned long long* seed, int B, int T, int C, void* stream);
+
+/* stand-alone SE gate multiply (SqueezeExcitation.forward outside a MegaBlock, src/modules.py:187-189):
+ * out = x * gate[b,c];  backward: dx = dout * gate, dgate[b,c] += sum_t dout * x  (dgate ACCUMULATED) */
+int tn_gate_mul_fwd(const float* x, const float* gate, float* out, int B, int T, int C, void* stream);
+int tn_gate_mul_bwd(const float* dout, const float* x, const float* gate, float* dx, float* dgate, int B, int T, int C,
+                    void* stream);
+/* out[b*T+t, c] = v[b,c] * mul: backward of a mean over time (nn.AdaptiveAvgPool1d(1), src/modules.py:165, src/models.py:498) */
+int tn_bcast_rows(const float* v, float* out, float mul, int B, int T, int C, void* stream);
 
 /* ---- attentive statistics pooling: AttentiveStatsPooling.forward (src/models.py:570-584) */
 int tn_asp_pool_fwd(const float* e, const float* x, float* pooled, float* aux, int B, int T, int D, float eps,

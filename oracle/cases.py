@@ -8,6 +8,8 @@ TINY = dict(
     tiny_k3=TitaNetSpec(hidden=64, kernel=3, n_mega_blocks=2, enc_out=96, attn_hidden=32, emb=48),
     tiny_k7=TitaNetSpec(hidden=32, kernel=7, n_mega_blocks=1, enc_out=64, attn_hidden=16, emb=32),
     tiny_k11=TitaNetSpec(hidden=32, kernel=11, n_mega_blocks=1, enc_out=64, attn_hidden=16, emb=32),
+    # Decoder(simple_pool=True): average pooling + Linear instead of attentive statistics (models.py:497-502)
+    tiny_k3_simple=TitaNetSpec(hidden=64, kernel=3, n_mega_blocks=1, enc_out=96, attn_hidden=32, emb=48, simple_pool=True),
 )
 
 # name -> (spec, loss, n_classes, B, T, scale, margin, full_grads)
@@ -18,6 +20,7 @@ TRAIN_CASES = {
     "tiny_k3_arc_noscale": (TINY["tiny_k3"], "arc", 10, 4, 37, None, 0.2, True),
     "tiny_k7_ce": (TINY["tiny_k7"], "ce", 7, 3, 33, None, 0.0, True),
     "tiny_k11_arc": (TINY["tiny_k11"], "arc", 7, 3, 64, 30, 0.2, True),
+    "tiny_k3_simple_ce": (TINY["tiny_k3_simple"], "ce", 10, 4, 41, None, 0.0, True),
     "s17_ce_b4": (TitaNetSpec.named("s", 17), "ce", 251, 4, 101, None, 0.0, False),
 }
 

@@ -131,9 +131,14 @@ def case_eval_input_grad():
 
 
 if __name__ == "__main__":
-    case_mel()
-    case_cfg1()
+    only = set(sys.argv[1:])            # optional: regenerate just the named train cases
+    if not only:
+        case_mel()
+        case_cfg1()
     for name, (spec, loss, nc, B, T, scale, margin, full) in TRAIN_CASES.items():
+        if only and name not in only:
+            continue
         train_case(name, spec, loss, nc, B, T, scale if loss != "ce" else None,
                    margin if loss != "ce" else None, full)
-    case_eval_input_grad()
+    if not only:
+        case_eval_input_grad()

@@ -342,3 +342,26 @@ def test_dropout_statistics_and_mask_replay(ops):
     seed2 = ops.seed_next(state)
     y3 = ops.Act.apply(z.detach(), sc, sh, seed2, True, p, 3)      # next step -> another mask
     assert not torch.equal(y3 > 0, y > 0)
+
+
+def test_standalone_squeeze_excitation_matches_fp64():
+    """modules.SqueezeExcitation.forward outside a MegaBlock (src/modules.py:173-189): [B, C, W] -> [B, C, W]."""
+    from titanet_b200 import modules
+    B, C, T = 5, 64, 77
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, C, T, generator=g)
+    gy = torch.randn(B, C, T, generator=g)
+    se = modules.SqueezeExcitation(C, reduction=16)
+    W1, W2 = se.excitation[0].weight.detach().clone(), se.excitation[2].weight.detach().clone()
+    xr, w1r, w2r = x.double().requires_grad_(True), W1.double().requires_grad_(True), W2.double().requires_grad_(True)
+    gate = torch.sigmoid(torch.relu(xr.mean(dim=2) @ w1r.t()) @ w2r.t())
+    yr = xr * gate.unsqueeze(-1)
+    yr.backward(gy.double())
+    se = se.to(dev())
+    xg = x.to(dev()).requires_grad_(True)
+    y = se(xg)
+    y.backward(gy.to(dev()))
+    assert y.shape == (B, C, T)
+    assert rel(y, yr) < 1e-5
+    assert rel(xg.grad, xr.grad) < 1e-4
+    assert rel(se.excitation[0].weight.grad, w1r.grad) < 1e-4 and rel(se.excitation[2].weight.grad, w2r.grad) < 1e-4

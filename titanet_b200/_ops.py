@@ -664,7 +664,7 @@ class SETail(Function):
         z3, sc3, sh3, s, scs, shs, W1, W2 = map(_c, (z3, sc3, sh3, s, scs, shs, W1, W2))
         C = z3.shape[1]
         Cr = W1.shape[0]
-        m, gate = empty((B, C), z3), empty((B, C), z3)
+        m, gate = zeros((B, C), z3), empty((B, C), z3)
         out = empty(z3.shape, z3)
         call("tn_se_mean", ptr(z3), ptr(m), ptr(sc3), ptr(sh3), 1, float(p3), ptr(seed), int(layer3), B, T, C)
         call("tn_se_mlp_fwd", ptr(m), ptr(W1), ptr(W2), ptr(gate), B, C, Cr)
@@ -680,7 +680,7 @@ class SETail(Function):
         p3, layer3, p_o, layer_o, B, T = ctx.meta
         C, Cr = z3.shape[1], W1.shape[0]
         dout = _c(dout)
-        dgate = empty((B, C), z3)
+        dgate = zeros((B, C), z3)
         call("tn_tail_bwd1", ptr(dout), ptr(out), ptr(z3), ptr(dgate), ptr(sc3), ptr(sh3), float(p3), int(layer3), float(p_o),
              ptr(seed), B, T, C)
         dm = empty((B, C), z3)
@@ -692,6 +692,73 @@ class SETail(Function):
              red[1].data_ptr(), red[2].data_ptr(), red[3].data_ptr(), ptr(sc3), ptr(sh3), float(p3), int(layer3), ptr(scs),
              ptr(shs), float(p_o), ptr(seed), B, T, C)
         return dz3, red[0], red[1], ds, red[2], red[3], dW1, dW2, None, None, None, None, None, None, None
+
+
+class MeanT(Function):
+    """m[B, C] = mean over time of a plain [B*T, C] tensor (nn.AdaptiveAvgPool1d(1): src/modules.py:165,
+    src/models.py:498); backward broadcasts dm / T over the frames."""
+
+    @staticmethod
+    def forward(ctx, x, B: int, T: int):
+        x = _c(x)
+        C = x.shape[1]
+        m = zeros((B, C), x)
+        call("tn_se_mean", ptr(x), ptr(m), None, None, 0, 0.0, None, 0, B, T, C)
+        ctx.meta = (B, T, C)
+        return m
+
+    @staticmethod
+    def backward(ctx, dm):
+        B, T, C = ctx.meta
+        dm = _c(dm)
+        dx = empty((B * T, C), dm)
+        call("tn_bcast_rows", ptr(dm), ptr(dx), 1.0 / T, B, T, C)
+        return dx, None, None
+
+
+class SEMlp(Function):
+    """gate = sigmoid(W2 relu(W1 m)), no biases (SqueezeExcitation.excitation, src/modules.py:166-171)."""
+
+    @staticmethod
+    def forward(ctx, m, W1, W2):
+        m, W1, W2 = _c(m), _c(W1), _c(W2)
+        B, C = m.shape
+        gate = empty((B, C), m)
+        call("tn_se_mlp_fwd", ptr(m), ptr(W1), ptr(W2), ptr(gate), B, C, W1.shape[0])
+        ctx.save_for_backward(m, W1, W2, gate)
+        return gate
+
+    @staticmethod
+    def backward(ctx, dgate):
+        m, W1, W2, gate = ctx.saved_tensors
+        B, C = m.shape
+        dm = empty((B, C), m)
+        dW1, dW2 = zeros(W1.shape, W1), zeros(W2.shape, W2)
+        call("tn_se_mlp_bwd", ptr(_c(dgate)), ptr(gate), ptr(m), ptr(W1), ptr(W2), ptr(dm), ptr(dW1), ptr(dW2), B, C, W1.shape[0])
+        return dm, dW1, dW2
+
+
+class GateMul(Function):
+    """out[b, t, c] = x[b, t, c] * gate[b, c]  (src/modules.py:187-189)."""
+
+    @staticmethod
+    def forward(ctx, x, gate, B: int, T: int):
+        x, gate = _c(x), _c(gate)
+        C = x.shape[1]
+        out = empty(x.shape, x)
+        call("tn_gate_mul_fwd", ptr(x), ptr(gate), ptr(out), B, T, C)
+        ctx.save_for_backward(x, gate)
+        ctx.meta = (B, T, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, gate = ctx.saved_tensors
+        B, T, C = ctx.meta
+        dx = empty(x.shape, x)
+        dgate = zeros((B, C), x)
+        call("tn_gate_mul_bwd", ptr(_c(dout)), ptr(x), ptr(gate), ptr(dx), ptr(dgate), B, T, C)
+        return dx, dgate, None, None
 
 
 # ----------------------------------------------------------------------------

@@ -221,8 +221,7 @@ static int time_per_block(int B, int T) {
 extern "C" int tn_se_mean(const float* z3, float* m, const float* scale, const float* shift, int relu, float drop_p,
                           const unsigned long long* seed, unsigned int layer, int B, int T, int C, void* stream) {
   SE_COMMON_CHECK("se_mean");
-  TN_REQUIRE(z3 && m && scale && shift, "se_mean: null tensor");
-  TN_CUDA(cudaMemsetAsync(m, 0, sizeof(float) * (size_t)B * C, (cudaStream_t)stream));
+  TN_REQUIRE(z3 && m && (scale == nullptr) == (shift == nullptr), "se_mean: null tensor");
   int tpb = time_per_block(B, T);
   dim3 grid(tn_cdiv(T, tpb), B);
   tn_launch(se_mean_kernel, grid, TN_EW_THREADS, 0, stream, z3, m, tn_make_act(scale, shift, relu, drop_p, seed, layer), T, C, tpb, 1.0f / (float)T);
@@ -269,7 +268,6 @@ extern "C" int tn_tail_bwd1(const float* dout, const float* out, const float* z3
                             int T, int C, void* stream) {
   SE_COMMON_CHECK("tail_bwd1");
   TN_REQUIRE(dout && out && z3 && dgate && scale3 && shift3, "tail_bwd1: null tensor");
-  TN_CUDA(cudaMemsetAsync(dgate, 0, sizeof(float) * (size_t)B * C, (cudaStream_t)stream));
   int tpb = time_per_block(B, T);
   dim3 grid(tn_cdiv(T, tpb), B);
   float inv_keep_o = drop_o > 0.f ? 1.f / (1.f - drop_o) : 1.f;
@@ -294,5 +292,93 @@ extern "C" int tn_tail_bwd2(const float* dout, const float* out, const float* z3
       dout, out, z3, s, gate, dm, dz3, ds, dsc3, dsh3, dscs, dshs, tn_make_act(scale3, shift3, 1, drop3, seed, layer3),
       tn_make_act(scale_s, shift_s, 0, 0.f, seed, 0), inv_keep_o, 1.0f / (float)T, (int)R, T, C, rpb);
   TN_LAUNCH_CHECK("tail_bwd2_kernel");
+  return TN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// stand-alone squeeze-excitation gate (modules.SqueezeExcitation.forward outside a MegaBlock,
+// src/modules.py:173-189) and the broadcast that is the backward of a mean over time
+// (nn.AdaptiveAvgPool1d(1) in SqueezeExcitation and in Decoder(simple_pool=True), src/models.py:497-502)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TN_EW_THREADS) gate_mul_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gate,
+                                                                     float* __restrict__ out, int R, int T, int C, int rpb) {
+  tn_grid_dep_sync();
+  TnTile tl = tn_tile(C);
+  const int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    const int q = qb + tl.q0;
+    if (!tl.active || q >= tl.Q) continue;
+    for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
+      const size_t off = (size_t)r * C + 4 * q;
+      tn_st4(out + off, tn_ld4(x + off) * tn_ld4(gate + (size_t)(r / T) * C + 4 * q));
+    }
+  }
+}
+// dx = dout * gate ; dgate[b, c] += sum_t dout * x   (one utterance per blockIdx.y so the reduction stays per batch item)
+__global__ void __launch_bounds__(TN_EW_THREADS) gate_mul_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x,
+                                                                     const float* __restrict__ gate, float* __restrict__ dx,
+                                                                     float* __restrict__ dgate, int T, int C, int tpb) {
+  tn_grid_dep_sync();
+  __shared__ float4 red[TN_EW_THREADS];
+  TnTile tl = tn_tile(C);
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * tpb, t1 = min(T, t0 + tpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    const int q = qb + tl.q0;
+    float4 s = tn_zero4();
+    if (tl.active && q < tl.Q) {
+      const float4 g = tn_ld4(gate + (size_t)b * C + 4 * q);
+      for (int t = t0 + tl.lane; t < t1; t += tl.lanes) {
+        const size_t off = ((size_t)b * T + t) * C + 4 * q;
+        const float4 d = tn_ld4(dout + off);
+        s = tn_fma4(d, tn_ld4(x + off), s);
+        tn_st4(dx + off, d * g);
+      }
+    }
+    tn_lane_reduce_atomic(tl, s, q, dgate + (size_t)b * C, red);
+  }
+}
+// out[b*T + t, c] = v[b, c] * mul
+__global__ void __launch_bounds__(TN_EW_THREADS) bcast_rows_kernel(const float* __restrict__ v, float* __restrict__ out, float mul,
+                                                                   int R, int T, int C, int rpb) {
+  tn_grid_dep_sync();
+  TnTile tl = tn_tile(C);
+  const int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    const int q = qb + tl.q0;
+    if (!tl.active || q >= tl.Q) continue;
+    for (int r = r0 + tl.lane; r < r1; r += tl.lanes)
+      tn_st4(out + (size_t)r * C + 4 * q, tn_ld4(v + (size_t)(r / T) * C + 4 * q) * mul);
+  }
+}
+
+extern "C" int tn_gate_mul_fwd(const float* x, const float* gate, float* out, int B, int T, int C, void* stream) {
+  SE_COMMON_CHECK("gate_mul_fwd");
+  TN_REQUIRE(x && gate && out, "gate_mul_fwd: null tensor");
+  long long R = (long long)B * T;
+  TN_REQUIRE(R < (1ll << 31), "gate_mul_fwd: B*T too large");
+  int rpb = tail_rows_per_block(R);
+  tn_launch(gate_mul_fwd_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, x, gate, out, (int)R, T, C, rpb);
+  TN_LAUNCH_CHECK("gate_mul_fwd_kernel");
+  return TN_OK;
+}
+extern "C" int tn_gate_mul_bwd(const float* dout, const float* x, const float* gate, float* dx, float* dgate, int B, int T, int C,
+                               void* stream) {
+  SE_COMMON_CHECK("gate_mul_bwd");
+  TN_REQUIRE(dout && x && gate && dx && dgate, "gate_mul_bwd: null tensor");
+  int tpb = time_per_block(B, T);
+  dim3 grid(tn_cdiv(T, tpb), B);
+  tn_launch(gate_mul_bwd_kernel, grid, TN_EW_THREADS, 0, stream, dout, x, gate, dx, dgate, T, C, tpb);
+  TN_LAUNCH_CHECK("gate_mul_bwd_kernel");
+  return TN_OK;
+}
+extern "C" int tn_bcast_rows(const float* v, float* out, float mul, int B, int T, int C, void* stream) {
+  SE_COMMON_CHECK("bcast_rows");
+  TN_REQUIRE(v && out, "bcast_rows: null tensor");
+  long long R = (long long)B * T;
+  TN_REQUIRE(R < (1ll << 31), "bcast_rows: B*T too large");
+  int rpb = tail_rows_per_block(R);
+  tn_launch(bcast_rows_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, v, out, mul, (int)R, T, C, rpb);
+  TN_LAUNCH_CHECK("bcast_rows_kernel");
   return TN_OK;
 }

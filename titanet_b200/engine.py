@@ -101,15 +101,16 @@ class GradAllReduce:
     buffer holding every parameter gradient (24.6 MB for TitaNet-S), NCCL over NVLink.
     BatchNorm statistics stay per replica (DDP semantics)."""
 
-    def __init__(self, params, world_size: int, group=None):
+    def __init__(self, params, world_size: int, group=None, arena=None):
         self.params = list(params)
         self.world = world_size
         self.group = group
+        self.arena = arena          # the step's ops.ZeroArena (GraphedTrainStep.arena): gradients are exchanged in place
         self.flat = None
 
     def _arena_span(self, grads):
         """The slice of the active ZeroArena that holds every gradient, as one fp32 tensor (or None)."""
-        arena = ops._ARENA
+        arena = self.arena if self.arena is not None else ops._ARENA
         if arena is None or arena.buf is None:
             return None
         base, size = arena.buf.data_ptr(), arena.buf.numel()

@@ -198,12 +198,16 @@ class Decoder(nn.Module):
     def _fwd(self, enc: Lazy) -> torch.Tensor:
         B = enc.B
         if self._simple_pool:
-            raise NotImplementedError("Decoder(simple_pool=True) has no titanet_b200 kernel yet (see DESIGN.md)")
-        pooled = self.pool[0]._fwd(enc)
-        bn1 = self.pool[1]
-        st1 = ops.ColStats.apply(pooled) if bn1.training else None
-        sc1, sh1 = ops.bn_fold(st1, bn1, float(B))
-        pooled = ops.Act.apply(pooled, sc1, sh1, None, False, 0.0, 0)
+            # AdaptiveAvgPool1d(1) -> Squeeze -> Linear(D, 2D)   (reference: src/models.py:497-502)
+            x = enc.materialise()
+            lin0 = self.pool[2]
+            pooled, _ = ops.conv_gemm(ops.MeanT.apply(x.z, x.B, x.T), lin0.weight, lin0.bias, B, 1)
+        else:
+            pooled = self.pool[0]._fwd(enc)
+            bn1 = self.pool[1]
+            st1 = ops.ColStats.apply(pooled) if bn1.training else None
+            sc1, sh1 = ops.bn_fold(st1, bn1, float(B))
+            pooled = ops.Act.apply(pooled, sc1, sh1, None, False, 0.0, 0)
         lin, bn2 = self.linear[0], self.linear[1]
         z, sc2, sh2 = ops.conv_gemm_bn(pooled, lin.weight, lin.bias, bn2, B, 1)
         return ops.Act.apply(z, sc2, sh2, None, False, 0.0, 0)

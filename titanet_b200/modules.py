@@ -220,9 +220,14 @@ class SqueezeExcitation(nn.Module):
         )
 
     def forward(self, inputs):
-        raise NotImplementedError(
-            "standalone SqueezeExcitation.forward: use it through models.MegaBlock (the fused SE + residual tail kernel); "
-            "a stand-alone gate-multiply kernel is not built yet")
+        """[B, C, W] -> [B, C, W] (reference: src/modules.py:173-189): mean over time, two-layer gate, multiply."""
+        lin1, lin2 = self.excitation[0], self.excitation[2]
+        if lin1.bias is not None or lin2.bias is not None:
+            raise NotImplementedError("SqueezeExcitation kernels have no bias terms (the reference uses bias=False)")
+        x = Lazy.from_ncw(inputs)
+        m = ops.MeanT.apply(x.z, x.B, x.T)
+        gate = ops.SEMlp.apply(m, lin1.weight, lin2.weight)
+        return Lazy(ops.GateMul.apply(x.z, gate, x.B, x.T), x.B, x.T).to_ncw()
 
 
 class Squeeze(nn.Module):
