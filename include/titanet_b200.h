@@ -170,6 +170,16 @@ int tn_tanh_bwd(const float* dh, const float* h, float* out, long long n, void* 
 /* m[b,c] += mean_t act(z3)[b,t,c]  (ACCUMULATED: the caller zeroes m; scale == NULL: z3 is already the activation) */
 int tn_se_mean(const float* z3, float* m, const float* scale, const float* shift, int relu, float drop_p,
                const unsigned long long* seed, unsigned int layer, int B, int T, int C, void* stream);
+/* tn_se_mean + tn_se_mlp_fwd in one launch: the last block of each utterance's mean runs its MLP.  m ACCUMULATED (caller zeroes),
+ * counters: B zeroed unsigned ints (device-wide tickets, reset by the kernel). */
+int tn_se_squeeze_excite(const float* z3, float* m, float* gate, unsigned int* counters, const float* W1, const float* W2,
+                         const float* scale, const float* shift, int relu, float drop_p, const unsigned long long* seed,
+                         unsigned int layer, int B, int T, int C, int Cr, void* stream);
+/* tn_tail_bwd1 + tn_se_mlp_bwd in one launch (dgate, dW1, dW2 ACCUMULATED; counters as above) */
+int tn_tail_bwd1_mlp(const float* dout, const float* out, const float* z3, float* dgate, unsigned int* counters,
+                     const float* gate, const float* m, const float* W1, const float* W2, float* dm, float* dW1, float* dW2,
+                     const float* scale3, const float* shift3, float drop3, unsigned int layer3, float drop_o,
+                     const unsigned long long* seed, int B, int T, int C, int Cr, void* stream);
 int tn_se_mlp_fwd(const float* m, const float* W1, const float* W2, float* gate, int B, int C, int Cr, void* stream);
 int tn_se_mlp_bwd(const float* dgate, const float* gate, const float* m, const float* W1, const float* W2, float* dm,
                   float* dW1, float* dW2, int B, int C, int Cr, void* stream);       /* dW1/dW2 ACCUMULATED */

@@ -159,3 +159,32 @@ def test_model_step_uses_one_split_launch_and_arena_matches():
         for k, gref in results[0][1].items():
             err = float((grads[k] - gref).abs().max()) / max(float(gref.abs().max()), 1e-2 * gmax)
             assert err < 5e-2, (k, err)
+
+
+def test_optional_launch_fusions_match_default():
+    """TN_FUSE_BLOCK_ENTRY / TN_FUSE_SE_MLP (off by default: measured slower) compute the same step."""
+    import titanet_oracle as O
+    from titanet_b200 import _lib, _ops as ops, losses, models
+    from cases import train_inputs
+    spec = O.TitaNetSpec.named("s", 2)
+    sd = O.synth_state_dict(spec, "ce", 251)
+    x, y = train_inputs(spec, 251, 4, 101)
+    res = []
+    try:
+        for fused in (False, True):
+            ops.FUSE_BLOCK_ENTRY = ops.FUSE_SE_MLP = fused
+            model = models.TitaNet.get_titanet(192, 80, 2, "s", loss_function=losses.CELoss(192, 251), dropout=0.0)
+            model.load_state_dict(sd, strict=True)
+            model = model.cuda().train()
+            _lib.COUNTS.clear()
+            emb, preds, loss = model(x.cuda(), speakers=y.cuda())
+            loss.backward()
+            assert (_lib.COUNTS.get("tn_se_squeeze_excite", 0) > 0) == fused and (_lib.COUNTS.get("tn_tail_bwd1_mlp", 0) > 0) == fused
+            res.append((float(loss), emb.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}))
+    finally:
+        ops.FUSE_BLOCK_ENTRY = ops.FUSE_SE_MLP = False
+    assert abs(res[0][0] - res[1][0]) < 1e-4 * abs(res[0][0]) and rel(res[1][1], res[0][1]) < 1e-3   # atomics order x BatchNorm at batch 4
+    gmax = max(float(v.abs().max()) for v in res[0][2].values())
+    for k, gref in res[0][2].items():
+        err = float((res[1][2][k] - gref).abs().max()) / max(float(gref.abs().max()), 1e-2 * gmax)
+        assert err < 5e-2, (k, err)

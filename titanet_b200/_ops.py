@@ -536,6 +536,14 @@ class Depthwise(Function):
 
 
 TC_FUSE_DWBWD = True
+# Two launch fusions, measured on the graph-replayed TitaNet-S step and OFF by default because they lose:
+#   TN_FUSE_BLOCK_ENTRY=1  first sub-block + skip branch as one autograd node, the skip data gradient accumulated in the GEMM
+#                          epilogue (red.global.add) instead of an add kernel:   10.21 -> 10.24 ms
+#   TN_FUSE_SE_MLP=1       SE MLP forward / backward run by the last block of se_mean / tail_bwd1 (-34 launches): 10.21 -> 10.32 ms
+# (inside a CUDA graph a launch boundary costs less than the serial tail the fused kernels add)
+import os as _os
+FUSE_BLOCK_ENTRY = _os.environ.get("TN_FUSE_BLOCK_ENTRY", "0") == "1"
+FUSE_SE_MLP = _os.environ.get("TN_FUSE_SE_MLP", "0") == "1"
 
 
 class DwPw(Function):
@@ -651,6 +659,64 @@ class DwPwBN(Function):
                 None, None, None)
 
 
+class BlockEntryBN(Function):
+    """The two consumers of a mega-block's input in ONE autograd node (train mode): the first sub-block
+    (depthwise-separable conv + BatchNorm, ``DwPwBN``) and the skip branch (1x1 conv + BatchNorm, ``ConvGemmBN``)
+    (src/models.py:435-455, 467-469).  Forward is the same kernels; in backward the skip branch's data-gradient GEMM
+    accumulates straight into the gradient the fused depthwise backward wrote (TN_EPI_ACCUM), so autograd has no
+    ``dx_a + dx_b`` kernel to run on the 17 block inputs.  ``z`` is a plain activation (the previous block's output)."""
+
+    @staticmethod
+    def forward(ctx, z, dw_w, dw_b, pw_w, pw_b, g1, b1, rm1, rv1, nbt1, mom1: float, eps1: float,
+                sk_w, sk_b, gs, bs, rms, rvs, nbts, moms: float, epss: float, B: int, T: int):
+        z, dw_w, dw_b, pw_w, pw_b, g1, b1, sk_w, sk_b, gs, bs = map(_c, (z, dw_w, dw_b, pw_w, pw_b, g1, b1, sk_w, sk_b, gs, bs))
+        C, K = dw_w.shape[0], dw_w.shape[-1]
+        Co, Cs = pw_w.shape[0], sk_w.shape[0]
+        R = B * T
+        assert z.shape == (R, C)
+        n = float(R)
+        # skip branch first, like the reference's forward (src/models.py:469)
+        s = empty((R, Cs), z)
+        st_s, fold_s = _bn_forward_buffers(Cs, z)
+        bn_s = make_bn_fold(gs, bs, rms, rvs, nbts, moms, epss, n, fold_s[0], fold_s[1], fold_s[2], fold_s[3],
+                            st_s.data_ptr() + 16 * Cs)
+        sp_s = cached_splits(sk_w)
+        sk3 = sk_w if sk_w.dim() == 3 else sk_w.unsqueeze(-1)
+        _gemm_fwd(z, sk3, sk_b, s, st_s, B, T, 0, 0, ws=sp_s[0] if sp_s else None, bn=bn_s)
+        u = empty(z.shape, z)
+        call("tn_dw_fwd", ptr(z), ptr(u), ptr(dw_w), ptr(dw_b), None, None, 0, 0.0, None, 0, B, T, C, K)
+        zo = empty((R, Co), z)
+        st_1, fold_1 = _bn_forward_buffers(Co, z)
+        bn_1 = make_bn_fold(g1, b1, rm1, rv1, nbt1, mom1, eps1, n, fold_1[0], fold_1[1], fold_1[2], fold_1[3],
+                            st_1.data_ptr() + 16 * Co)
+        sp_1 = cached_splits(pw_w)
+        _gemm_fwd(u, pw_w if pw_w.dim() == 3 else pw_w.unsqueeze(-1), pw_b, zo, st_1, B, T, 0, 0, ws=sp_1[0] if sp_1 else None, bn=bn_1)
+        ctx.ws_t1 = sp_1[1] if sp_1 else None
+        ctx.ws_ts = sp_s[1] if sp_s else None
+        ctx.save_for_backward(z, dw_w, dw_b, pw_w, pw_b, g1, sk_w, sk_b, gs, u, zo, s, fold_1, fold_s)
+        ctx.meta = (B, T, n)
+        return zo, fold_1[0], fold_1[1], s, fold_s[0], fold_s[1]
+
+    @staticmethod
+    def backward(ctx, dzo, dsc1, dsh1, ds, dscs, dshs):
+        z, dw_w, dw_b, pw_w, pw_b, g1, sk_w, sk_b, gs, u, zo, s, fold_1, fold_s = ctx.saved_tensors
+        B, T, n = ctx.meta
+        R = B * T
+        pw3 = pw_w if pw_w.dim() == 3 else pw_w.unsqueeze(-1)
+        sk3 = sk_w if sk_w.dim() == 3 else sk_w.unsqueeze(-1)
+        Co, Cs = pw3.shape[0], sk3.shape[0]
+        ga, db_pw, dg1, db1 = _bn_backward(dzo, zo, dsc1, dsh1, fold_1, g1, n, pw_b, R, Co)
+        dpw = zeros(pw_w.shape, pw_w)
+        _gemm_wgrad(ga, u, dpw if dpw.dim() == 3 else dpw.unsqueeze(-1), None, B, T)
+        dz, _, _, ddw, ddb = _dwpw_dgrad(ga, pw3, ctx.ws_t1, z, None, None, dw_w, dw_b, None, False, 0.0, 0, B, T)
+        gb, db_s, dgs, dbs = _bn_backward(ds, s, dscs, dshs, fold_s, gs, n, sk_b, R, Cs)
+        dws = zeros(sk_w.shape, sk_w)
+        _gemm_wgrad(gb, z, dws if dws.dim() == 3 else dws.unsqueeze(-1), None, B, T)
+        _gemm_fwd(gb, sk3, None, dz, None, B, T, 1, EPI_ACCUM, ws=ctx.ws_ts)          # dz += gb W_skip
+        return (dz, ddw, ddb, dpw, db_pw, dg1, db1, None, None, None, None, None,
+                dws, db_s, dgs, dbs, None, None, None, None, None, None, None)
+
+
 # ----------------------------------------------------------------------------
 # squeeze-excitation + mega-block tail
 # ----------------------------------------------------------------------------
@@ -666,8 +732,13 @@ class SETail(Function):
         Cr = W1.shape[0]
         m, gate = zeros((B, C), z3), empty((B, C), z3)
         out = empty(z3.shape, z3)
-        call("tn_se_mean", ptr(z3), ptr(m), ptr(sc3), ptr(sh3), 1, float(p3), ptr(seed), int(layer3), B, T, C)
-        call("tn_se_mlp_fwd", ptr(m), ptr(W1), ptr(W2), ptr(gate), B, C, Cr)
+        if FUSE_SE_MLP:
+            tickets = zeros((B,), z3, torch.int32)
+            call("tn_se_squeeze_excite", ptr(z3), ptr(m), ptr(gate), ptr(tickets), ptr(W1), ptr(W2), ptr(sc3), ptr(sh3), 1, float(p3),
+                 ptr(seed), int(layer3), B, T, C, Cr)
+        else:
+            call("tn_se_mean", ptr(z3), ptr(m), ptr(sc3), ptr(sh3), 1, float(p3), ptr(seed), int(layer3), B, T, C)
+            call("tn_se_mlp_fwd", ptr(m), ptr(W1), ptr(W2), ptr(gate), B, C, Cr)
         call("tn_tail_fwd", ptr(z3), ptr(s), ptr(gate), ptr(out), ptr(sc3), ptr(sh3), float(p3), int(layer3), ptr(scs), ptr(shs),
              float(p_o), int(layer_o), ptr(seed), B, T, C)
         ctx.save_for_backward(z3, sc3, sh3, s, scs, shs, W1, W2, seed, m, gate, out)
@@ -681,11 +752,16 @@ class SETail(Function):
         C, Cr = z3.shape[1], W1.shape[0]
         dout = _c(dout)
         dgate = zeros((B, C), z3)
-        call("tn_tail_bwd1", ptr(dout), ptr(out), ptr(z3), ptr(dgate), ptr(sc3), ptr(sh3), float(p3), int(layer3), float(p_o),
-             ptr(seed), B, T, C)
         dm = empty((B, C), z3)
         dW1, dW2 = zeros(W1.shape, W1), zeros(W2.shape, W2)
-        call("tn_se_mlp_bwd", ptr(dgate), ptr(gate), ptr(m), ptr(W1), ptr(W2), ptr(dm), ptr(dW1), ptr(dW2), B, C, Cr)
+        if FUSE_SE_MLP:
+            tickets = zeros((B,), z3, torch.int32)
+            call("tn_tail_bwd1_mlp", ptr(dout), ptr(out), ptr(z3), ptr(dgate), ptr(tickets), ptr(gate), ptr(m), ptr(W1), ptr(W2), ptr(dm),
+                 ptr(dW1), ptr(dW2), ptr(sc3), ptr(sh3), float(p3), int(layer3), float(p_o), ptr(seed), B, T, C, Cr)
+        else:
+            call("tn_tail_bwd1", ptr(dout), ptr(out), ptr(z3), ptr(dgate), ptr(sc3), ptr(sh3), float(p3), int(layer3), float(p_o),
+                 ptr(seed), B, T, C)
+            call("tn_se_mlp_bwd", ptr(dgate), ptr(gate), ptr(m), ptr(W1), ptr(W2), ptr(dm), ptr(dW1), ptr(dW2), B, C, Cr)
         dz3, ds = empty(z3.shape, z3), empty(z3.shape, z3)
         red = zeros((4, C), z3)
         call("tn_tail_bwd2", ptr(dout), ptr(out), ptr(z3), ptr(s), ptr(gate), ptr(dm), ptr(dz3), ptr(ds), red[0].data_ptr(),

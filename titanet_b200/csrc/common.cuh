@@ -112,8 +112,11 @@ static inline TnAct tn_make_act(const float* scale, const float* shift, int relu
   TnAct a;
   a.scale = scale; a.shift = shift; a.relu = relu;
   if (p > 0.f) {
-    double t = (double)p * 4294967296.0;
-    a.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    // 16-bit drop threshold: one 32-bit hash decides TWO elements (its low / high half), so the drop probability is
+    // p rounded to 1/65536 (|error| < 8e-6; inv_keep stays the nominal 1/(1-p))
+    double t = (double)p * 65536.0 + 0.5;
+    a.thresh = t >= 65535.0 ? 65535u : (uint32_t)t;
+    if (a.thresh == 0) a.thresh = 1;
     a.inv_keep = 1.0f / (1.0f - p);
   } else {
     a.thresh = 0; a.inv_keep = 1.0f;
@@ -124,10 +127,12 @@ static inline TnAct tn_make_act(const float* scale, const float* shift, int relu
 }
 
 #ifdef __CUDACC__
-// Counter-based dropout RNG: one 32-bit hash per ELEMENT of (step seed, layer id, element
-// index) -- a seeded multiply-xorshift finaliser ("lowbias32").  Stateless, so forward and
-// backward regenerate the same mask, and any thread can ask for any element (the tensor-core
-// epilogues own one channel per thread, the row-tiled kernels four).
+// Counter-based dropout RNG: one 32-bit hash per PAIR of consecutive elements of (step seed, layer id,
+// pair index = element index >> 1) -- a seeded multiply-xorshift finaliser ("lowbias32"); the even element
+// compares the low 16 bits with the threshold, the odd one the high 16 bits.  Stateless, so forward and
+// backward regenerate the same mask, and any thread can ask for any element (the tensor-core epilogues own
+// one channel per thread, the row-tiled kernels four = two hashes).  Measured: with one hash per element the
+// hash was 30-50 % of the HBM-bound kernels' time (se_mean 10.3 us with dropout, 5.4 us without).
 __device__ __forceinline__ uint32_t tn_hash_elem(uint32_t seed_lo, uint32_t seed_hi, uint32_t layer, unsigned long long idx) {
   uint32_t h = (uint32_t)idx * 0x9E3779B1u ^ seed_lo;
   h ^= (uint32_t)(idx >> 32) * 0xC2B2AE3Du + layer * 0x85EBCA77u + seed_hi;
@@ -163,15 +168,15 @@ __device__ __forceinline__ TnAct tn_act_init(TnAct a) {
 // keep-multipliers (0 or inv_keep) for the 4 consecutive elements of quad `qidx`
 __device__ __forceinline__ float4 tn_drop4(const TnAct& a, unsigned long long qidx) {
   if (a.thresh == 0) return make_float4(1.f, 1.f, 1.f, 1.f);
-  const unsigned long long e = qidx << 2;
-  return make_float4(tn_hash_elem(a.seed_lo, a.seed_hi, a.layer, e) >= a.thresh ? a.inv_keep : 0.f,
-                     tn_hash_elem(a.seed_lo, a.seed_hi, a.layer, e + 1) >= a.thresh ? a.inv_keep : 0.f,
-                     tn_hash_elem(a.seed_lo, a.seed_hi, a.layer, e + 2) >= a.thresh ? a.inv_keep : 0.f,
-                     tn_hash_elem(a.seed_lo, a.seed_hi, a.layer, e + 3) >= a.thresh ? a.inv_keep : 0.f);
+  const uint32_t h0 = tn_hash_elem(a.seed_lo, a.seed_hi, a.layer, qidx << 1);          // elements 4q, 4q+1
+  const uint32_t h1 = tn_hash_elem(a.seed_lo, a.seed_hi, a.layer, (qidx << 1) | 1ull);  // elements 4q+2, 4q+3
+  return make_float4((h0 & 0xFFFFu) >= a.thresh ? a.inv_keep : 0.f, (h0 >> 16) >= a.thresh ? a.inv_keep : 0.f,
+                     (h1 & 0xFFFFu) >= a.thresh ? a.inv_keep : 0.f, (h1 >> 16) >= a.thresh ? a.inv_keep : 0.f);
 }
 __device__ __forceinline__ float tn_drop1(const TnAct& a, unsigned long long idx) {
   if (a.thresh == 0) return 1.f;
-  return tn_hash_elem(a.seed_lo, a.seed_hi, a.layer, idx) >= a.thresh ? a.inv_keep : 0.f;
+  const uint32_t h = tn_hash_elem(a.seed_lo, a.seed_hi, a.layer, idx >> 1);
+  return ((idx & 1ull) ? (h >> 16) : (h & 0xFFFFu)) >= a.thresh ? a.inv_keep : 0.f;
 }
 // scalar lazy activation of element (row, c): returns a, *mult = d a / d pre
 __device__ __forceinline__ float tn_act1(const TnAct& a, float z, int c, unsigned long long idx, float* mult) {

@@ -161,8 +161,11 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tbase, float* __restrict__ 
       float x = v[j] + bv;
       if (TANH) x = tanhf(x);
       float* q = zp + (size_t)(c0 + j) * ld;
-      if (ACCUM) x += ok ? *q : 0.f;
-      if (ok) {
+      if (ACCUM) {
+        // Z += x as a fire-and-forget reduction (red.global.add.f32, one 128-byte line per warp): a load-add-store here
+        // put 4-byte global loads on the eight epilogue warps' critical path (+60 us per launch, measured)
+        if (ok) atomicAdd(q, x);
+      } else if (ok) {
         *q = x;
         s1 += x;
         s2 = fmaf(x, x, s2);
@@ -254,7 +257,11 @@ __device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams
     m = 1.f;
     if (!lazy) return zv;
     const float pre = fmaf(zv, sc, sh);
-    if (drop) m = tn_hash_elem32(key, (uint32_t)row * (uint32_t)C + (uint32_t)c) >= act.thresh ? act.inv_keep : 0.f;
+    if (drop) {
+      const uint32_t idx = (uint32_t)row * (uint32_t)C + (uint32_t)c;                 // same pairing as tn_drop1 / tn_drop4
+      const uint32_t h = tn_hash_elem32(key, idx >> 1);
+      m = ((idx & 1u) ? (h >> 16) : (h & 0xFFFFu)) >= act.thresh ? act.inv_keep : 0.f;
+    }
     if (act.relu && !(pre > 0.f)) m = 0.f;
     return (row >= 0 && row < R) ? pre * m : 0.f;
   };
@@ -595,7 +602,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         case 4: tc_epilogue<false, false, true>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
         case 0: tc_epilogue<false, false, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
         case TN_EPI_TANH: case TN_EPI_TANH | 4: tc_epilogue<true, false, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
-        case TN_EPI_ACCUM: case TN_EPI_ACCUM | 4: tc_epilogue<false, true, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
+        case TN_EPI_ACCUM | 4: tc_epilogue<false, true, true>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
+        case TN_EPI_ACCUM: tc_epilogue<false, true, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
         default: tc_epilogue<true, true, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
       }
       if (p.stats) {
@@ -984,6 +992,7 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
 extern "C" int tn_gemm_tc(const float* X, const float* ws, const float* bias, float* Z, double* stats, int R, int Kd, int M,
                           int flags, int nsplit, void* stream) {
   TN_REQUIRE(Z, "gemm_tc: null output");
+  TN_REQUIRE(!(flags & TN_EPI_ACCUM) || !stats, "gemm_tc: statistics of an accumulated output are not available");
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.bias = bias; p.Z = Z; p.stats = stats; p.flags = flags;

@@ -30,15 +30,19 @@ __global__ void __launch_bounds__(TN_EW_THREADS) se_mean_kernel(const float* __r
   }
 }
 
-// excitation MLP, one block per batch item.  smem: m[C] + h[Cr]
-__global__ void __launch_bounds__(256) se_mlp_fwd_kernel(const float* __restrict__ m, const float* __restrict__ W1,
-                                                         const float* __restrict__ W2, float* __restrict__ gate, int C, int Cr) {
-  tn_grid_dep_sync();
-  extern __shared__ float sm[];
+// squeeze + excitation in one launch: the last block to finish batch item b's mean runs b's MLP
+__global__ void __launch_bounds__(TN_EW_THREADS) se_squeeze_excite_kernel(const float* __restrict__ z, float* __restrict__ m,
+                                                                          float* __restrict__ gate, unsigned int* __restrict__ counters,
+                                                                          const float* __restrict__ W1, const float* __restrict__ W2,
+                                                                          TnAct act, int T, int C, int Cr, int tpb, float inv_T);
+// excitation MLP of batch item b by one block.  sm: m[C] + h[Cr].  m is read with ld.cg: in the fused kernels it was
+// just accumulated by other blocks' atomics (performed in L2).
+__device__ __forceinline__ void se_mlp_fwd_block(float* sm, int b, const float* __restrict__ m, const float* __restrict__ W1,
+                                                 const float* __restrict__ W2, float* __restrict__ gate, int C, int Cr) {
   float* ms = sm;
   float* hs = sm + C;
-  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) ms[c] = m[(size_t)b * C + c];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) ms[c] = __ldcg(m + (size_t)b * C + c);
   __syncthreads();
   for (int j = warp; j < Cr; j += nw) {
     float s = 0.f;
@@ -53,23 +57,43 @@ __global__ void __launch_bounds__(256) se_mlp_fwd_kernel(const float* __restrict
     gate[(size_t)b * C + c] = 1.f / (1.f + expf(-s));
   }
 }
-
-// backward of the MLP: dgate -> dm, dW1 +=, dW2 +=.  smem: m[C] + h[Cr] + dh[Cr] + dp[C]
-__global__ void __launch_bounds__(256) se_mlp_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ gate,
-                                                         const float* __restrict__ m, const float* __restrict__ W1,
-                                                         const float* __restrict__ W2, float* __restrict__ dm,
-                                                         float* __restrict__ dW1, float* __restrict__ dW2, int C, int Cr) {
+__global__ void __launch_bounds__(256) se_mlp_fwd_kernel(const float* __restrict__ m, const float* __restrict__ W1,
+                                                         const float* __restrict__ W2, float* __restrict__ gate, int C, int Cr) {
   tn_grid_dep_sync();
   extern __shared__ float sm[];
+  se_mlp_fwd_block(sm, blockIdx.x, m, W1, W2, gate, C, Cr);
+}
+
+// device-wide "last block of batch item b" test: every thread of the block calls it after its atomics were issued;
+// `counter` (zero on entry) is reset by the last block, so CUDA-graph replays start clean.
+__device__ __forceinline__ bool tn_last_block_of(unsigned int* counter, unsigned int blocks) {
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == blocks - 1) ? 1u : 0u;
+    if (s_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0u;
+}
+
+// backward of the MLP for batch item b by one block: dgate -> dm, dW1 +=, dW2 +=.  sm: m[C] + h[Cr] + dh[Cr] + dp[C]
+__device__ __forceinline__ void se_mlp_bwd_block(float* sm, int b, const float* __restrict__ dgate, const float* __restrict__ gate,
+                                                 const float* __restrict__ m, const float* __restrict__ W1,
+                                                 const float* __restrict__ W2, float* __restrict__ dm,
+                                                 float* __restrict__ dW1, float* __restrict__ dW2, int C, int Cr) {
   float* ms = sm;
   float* hs = ms + C;
   float* dh = hs + Cr;
   float* dp = dh + Cr;
-  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     ms[c] = m[(size_t)b * C + c];
     float g = gate[(size_t)b * C + c];
-    dp[c] = dgate[(size_t)b * C + c] * g * (1.f - g);
+    dp[c] = __ldcg(dgate + (size_t)b * C + c) * g * (1.f - g);
   }
   __syncthreads();
   for (int j = warp; j < Cr; j += nw) {       // recompute h and dh = W2^T dp
@@ -93,6 +117,38 @@ __global__ void __launch_bounds__(256) se_mlp_bwd_kernel(const float* __restrict
     }
     dm[(size_t)b * C + c] = s;
   }
+}
+__global__ void __launch_bounds__(256) se_mlp_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ gate,
+                                                         const float* __restrict__ m, const float* __restrict__ W1,
+                                                         const float* __restrict__ W2, float* __restrict__ dm,
+                                                         float* __restrict__ dW1, float* __restrict__ dW2, int C, int Cr) {
+  tn_grid_dep_sync();
+  extern __shared__ float sm[];
+  se_mlp_bwd_block(sm, blockIdx.x, dgate, gate, m, W1, W2, dm, dW1, dW2, C, Cr);
+}
+
+__global__ void __launch_bounds__(TN_EW_THREADS) se_squeeze_excite_kernel(const float* __restrict__ z, float* __restrict__ m,
+                                                                          float* __restrict__ gate, unsigned int* __restrict__ counters,
+                                                                          const float* __restrict__ W1, const float* __restrict__ W2,
+                                                                          TnAct act, int T, int C, int Cr, int tpb, float inv_T) {
+  tn_grid_dep_sync();
+  act = tn_act_init(act);
+  __shared__ float4 red[TN_EW_THREADS];
+  extern __shared__ float sm[];
+  TnTile tl = tn_tile(C);
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * tpb, t1 = min(T, t0 + tpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    const int q = qb + tl.q0;
+    float4 s = tn_zero4();
+    if (tl.active && q < tl.Q)
+      for (int t = t0 + tl.lane; t < t1; t += tl.lanes) {
+        size_t off = ((size_t)b * T + t) * C + 4 * q;
+        s = s + tn_act4(act, tn_ld4(z + off), 4 * q, off >> 2, nullptr);
+      }
+    tn_lane_reduce_atomic(tl, s, q, m + (size_t)b * C, red, inv_T);
+  }
+  if (tn_last_block_of(counters + b, gridDim.x)) se_mlp_fwd_block(sm, b, m, W1, W2, gate, C, Cr);
 }
 
 // ---------------------------------------------------------------------------
@@ -152,6 +208,36 @@ __global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd1_kernel(const float* _
       }
     tn_lane_reduce_atomic(tl, acc, q, dgate + (size_t)b * C, red);
   }
+}
+
+// pass 1 + the excitation MLP's backward: the last block of batch item b turns dgate[b] into dm[b], dW1 +=, dW2 +=
+__global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd1_mlp_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                                      const float* __restrict__ z3, float* __restrict__ dgate,
+                                                                      unsigned int* __restrict__ counters, const float* __restrict__ gate,
+                                                                      const float* __restrict__ m, const float* __restrict__ W1,
+                                                                      const float* __restrict__ W2, float* __restrict__ dm,
+                                                                      float* __restrict__ dW1, float* __restrict__ dW2, TnAct act3,
+                                                                      float inv_keep_o, int T, int C, int Cr, int tpb) {
+  tn_grid_dep_sync();
+  act3 = tn_act_init(act3);
+  __shared__ float4 red[TN_EW_THREADS];
+  extern __shared__ float sm[];
+  TnTile tl = tn_tile(C);
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * tpb, t1 = min(T, t0 + tpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    const int q = qb + tl.q0;
+    float4 acc = tn_zero4();
+    if (tl.active && q < tl.Q)
+      for (int t = t0 + tl.lane; t < t1; t += tl.lanes) {
+        size_t off = ((size_t)b * T + t) * C + 4 * q;
+        float4 g = tail_gout(tn_ld4(dout + off), tn_ld4(out + off), inv_keep_o);
+        float4 a3 = tn_act4(act3, tn_ld4(z3 + off), 4 * q, off >> 2, nullptr);
+        acc = tn_fma4(g, a3, acc);
+      }
+    tn_lane_reduce_atomic(tl, acc, q, dgate + (size_t)b * C, red);
+  }
+  if (tn_last_block_of(counters + b, gridDim.x)) se_mlp_bwd_block(sm, b, dgate, gate, m, W1, W2, dm, dW1, dW2, C, Cr);
 }
 
 // pass 2: dz3, ds and the four per-channel reductions
@@ -229,6 +315,22 @@ extern "C" int tn_se_mean(const float* z3, float* m, const float* scale, const f
   return TN_OK;
 }
 
+// m (ACCUMULATED) and counters (B zeroed uints, self-resetting) are provided zeroed by the caller
+extern "C" int tn_se_squeeze_excite(const float* z3, float* m, float* gate, unsigned int* counters, const float* W1, const float* W2,
+                                    const float* scale, const float* shift, int relu, float drop_p, const unsigned long long* seed,
+                                    unsigned int layer, int B, int T, int C, int Cr, void* stream) {
+  SE_COMMON_CHECK("se_squeeze_excite");
+  TN_REQUIRE(z3 && m && gate && counters && W1 && W2 && Cr > 0 && (scale == nullptr) == (shift == nullptr), "se_squeeze_excite: null tensor");
+  size_t smem = sizeof(float) * (size_t)(C + Cr);
+  TN_REQUIRE(smem <= 40 * 1024, "se_squeeze_excite: C too large");
+  int tpb = time_per_block(B, T);
+  dim3 grid(tn_cdiv(T, tpb), B);
+  tn_launch(se_squeeze_excite_kernel, grid, TN_EW_THREADS, smem, stream, z3, m, gate, counters, W1, W2,
+            tn_make_act(scale, shift, relu, drop_p, seed, layer), T, C, Cr, tpb, 1.0f / (float)T);
+  TN_LAUNCH_CHECK("se_squeeze_excite_kernel");
+  return TN_OK;
+}
+
 extern "C" int tn_se_mlp_fwd(const float* m, const float* W1, const float* W2, float* gate, int B, int C, int Cr, void* stream) {
   TN_REQUIRE(B > 0 && C > 0 && Cr > 0 && m && W1 && W2 && gate, "se_mlp_fwd: bad arguments");
   size_t smem = sizeof(float) * (size_t)(C + Cr);
@@ -273,6 +375,25 @@ extern "C" int tn_tail_bwd1(const float* dout, const float* out, const float* z3
   float inv_keep_o = drop_o > 0.f ? 1.f / (1.f - drop_o) : 1.f;
   tn_launch(tail_bwd1_kernel, grid, TN_EW_THREADS, 0, stream, dout, out, z3, dgate, tn_make_act(scale3, shift3, 1, drop3, seed, layer3), inv_keep_o, T, C, tpb);
   TN_LAUNCH_CHECK("tail_bwd1_kernel");
+  return TN_OK;
+}
+
+// tn_tail_bwd1 + tn_se_mlp_bwd in one launch; dgate, dW1, dW2 ACCUMULATED, counters: B zeroed uints (self-resetting)
+extern "C" int tn_tail_bwd1_mlp(const float* dout, const float* out, const float* z3, float* dgate, unsigned int* counters,
+                                const float* gate, const float* m, const float* W1, const float* W2, float* dm, float* dW1,
+                                float* dW2, const float* scale3, const float* shift3, float drop3, unsigned int layer3, float drop_o,
+                                const unsigned long long* seed, int B, int T, int C, int Cr, void* stream) {
+  SE_COMMON_CHECK("tail_bwd1_mlp");
+  TN_REQUIRE(dout && out && z3 && dgate && counters && gate && m && W1 && W2 && dm && dW1 && dW2 && scale3 && shift3 && Cr > 0,
+             "tail_bwd1_mlp: null tensor");
+  size_t smem = sizeof(float) * (size_t)(2 * C + 2 * Cr);
+  TN_REQUIRE(smem <= 40 * 1024, "tail_bwd1_mlp: C too large");
+  int tpb = time_per_block(B, T);
+  dim3 grid(tn_cdiv(T, tpb), B);
+  float inv_keep_o = drop_o > 0.f ? 1.f / (1.f - drop_o) : 1.f;
+  tn_launch(tail_bwd1_mlp_kernel, grid, TN_EW_THREADS, smem, stream, dout, out, z3, dgate, counters, gate, m, W1, W2, dm, dW1, dW2,
+            tn_make_act(scale3, shift3, 1, drop3, seed, layer3), inv_keep_o, T, C, Cr, tpb);
+  TN_LAUNCH_CHECK("tail_bwd1_mlp_kernel");
   return TN_OK;
 }
 

@@ -161,10 +161,25 @@ class MegaBlock(nn.Module):
         x = x.materialise()
         B, T = x.B, x.T
         skip_conv, skip_bn = self.skip_connection[0], self.skip_connection[1]
-        s, scs, shs = ops.conv_gemm_bn(x.z, skip_conv.weight, skip_conv.bias, skip_bn, B, T)
-        y = x
         n_sub = len(self.sub_blocks) - 1
-        for j in range(n_sub):
+        first = self.sub_blocks[0] if n_sub > 0 else None
+        fused_entry = (ops.FUSE_BLOCK_ENTRY and first is not None and isinstance(first.conv_block[0], modules.DepthwiseConv1d)
+                       and first._activation == "relu" and ops._bn_trainable(first.conv_block[1]) and ops._bn_trainable(skip_bn)
+                       and skip_conv.bias is not None and first.conv_block[0].conv[0].bias is not None)
+        if fused_entry:
+            # first sub-block + skip branch as one autograd node (ops.BlockEntryBN): no gradient-sum kernel on the block input
+            dw, pw, bn1 = first.conv_block[0].conv[0], first.conv_block[0].conv[1], first.conv_block[1]
+            modules._check_conv_supported(dw)
+            z1, sc1, sh1, s, scs, shs = ops.BlockEntryBN.apply(
+                x.z, dw.weight, dw.bias, pw.weight, pw.bias, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var,
+                bn1.num_batches_tracked, bn1.momentum, bn1.eps, skip_conv.weight, skip_conv.bias, skip_bn.weight, skip_bn.bias,
+                skip_bn.running_mean, skip_bn.running_var, skip_bn.num_batches_tracked, skip_bn.momentum, skip_bn.eps, B, T)
+            p1 = first._dropout if self.training else 0.0
+            y = Lazy(z1, B, T, sc1, sh1, relu=True, p=p1, seed=dctx.seed if p1 > 0 else None, layer=dctx.next_layer())
+        else:
+            s, scs, shs = ops.conv_gemm_bn(x.z, skip_conv.weight, skip_conv.bias, skip_bn, B, T)
+            y = x
+        for j in range(1 if fused_entry else 0, n_sub):
             y = self.sub_blocks[j]._fwd(y, dctx)
         if n_sub == 0 or y.scale is None:
             raise NotImplementedError("MegaBlock needs at least one sub-block")
