@@ -195,6 +195,16 @@ def graph_time_kernel(kind: str, R: int, Ci: int, Co: int, B: int, dropout: floa
         fn = lambda: call("tn_gemm_tc_dwbwd", ptr(x), ptr(ws), ptr(zp), ptr(dzp), ptr(dww), ptr(ddw), acc[0].data_ptr(),
                           acc[1].data_ptr(), acc[2].data_ptr(), ptr(sc), ptr(sh), 1, float(dropout),
                           ptr(seed) if dropout > 0 else None, 3, B, T, Ci, Co, 3, 3)
+    elif kind == "tn_gemm_tc_dwfwd":
+        # depthwise conv (+ BN/ReLU/dropout on load) as the GEMM's operand producer: reads z, writes u (side output) and Z
+        call("tn_split_tf32", ptr(w), ptr(ws), Co, Ci, 0)
+        u = torch.empty(R, Ci, device=dev)
+        dww, dwb, bias = rnd(Ci, 1, 3), rnd(Ci), rnd(Co)
+        sc, sh = torch.rand(Ci, device=dev) + 0.5, 0.1 * rnd(Ci)
+        seed = torch.tensor([1], dtype=torch.int64, device=dev)
+        st = torch.zeros(2 * Co, dtype=torch.float64, device=dev)
+        fn = lambda: call("tn_gemm_tc_dwfwd", ptr(x), ptr(ws), ptr(dww), ptr(dwb), ptr(sc), ptr(sh), 1, float(dropout),
+                          ptr(seed) if dropout > 0 else None, 3, ptr(bias), ptr(u), ptr(out), ptr(st), None, B, T, Ci, Co, 3)
     else:
         call("tn_split_tf32", ptr(w), ptr(ws), Co, Ci, 0)
         bias, st = rnd(Co), torch.zeros(2 * Co, dtype=torch.float64, device=dev)
@@ -318,6 +328,14 @@ def run_ours(args):
             per_launch_s = graph_time_kernel(kind, f["R"], f["Ci"], f["Co"], B, args.dropout, dev) * 1e-6
             if kind == "tn_gemm_tc_dwbwd":          # reads dZ and z_prev, writes dz_prev (+ weights); du never leaves the SM
                 byts = 4.0 * (f["R"] * f["Ci"] + 2 * f["R"] * f["Co"] + f["Ci"] * f["Co"])
+            if kind == "tn_gemm_tc_dwfwd":          # reads z, writes u (kept for the backward wgrad) and Z (+ weights)
+                byts = 4.0 * (2 * f["R"] * f["Ci"] + f["R"] * f["Co"] + f["Ci"] * f["Co"])
+            traffic = None                          # DRAM bytes per launch of this kernel from the committed ncu --set full capture
+            try:
+                with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as fh:
+                    traffic = json.load(fh).get(kind)
+            except (OSError, ValueError):
+                pass
             tf32_peak = pk["bf16_tflops"] / 2.0
             ach_tf = flops / per_launch_s / 1e12
             ach_gb = byts / per_launch_s / 1e9
@@ -327,7 +345,7 @@ def run_ours(args):
                     # TitaNet-S: AI = 2*R*Ci*Co / bytes ~ 64 FLOP/B < the TF32 ridge (~104 FLOP/B) -> HBM is the roofline
                     # of the algorithm; the fp32-equivalent 3xTF32 arithmetic issues 3 MMAs per algorithmic MAC.
                     "bound": "hbm", "achieved": round(ach_gb, 1), "peak": round(pk["hbm_gbs"], 1), "unit": "GB/s",
-                    "frac": round(ach_gb / pk["hbm_gbs"], 4), "traffic": None, "peak_source": pk["source"],
+                    "frac": round(ach_gb / pk["hbm_gbs"], 4), "traffic": traffic, "peak_source": pk["source"],
                     "algorithmic_bytes_per_launch": byts, "algorithmic_flops_per_launch": flops,
                     "algorithmic_tflop_s": round(ach_tf, 2), "tf32_peak_tflop_s": round(tf32_peak, 1),
                     "tensor_frac_of_tf32_peak": round(ach_tf / tf32_peak, 4), "mma_issue_factor": 3,

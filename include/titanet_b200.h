@@ -116,6 +116,15 @@ typedef struct tn_bn_fold {
 } tn_bn_fold;
 int tn_gemm_tc_bn(const float* X, const float* ws, const float* bias, float* Z, double* stats, const tn_bn_fold* bn, int R,
                   int Kd, int M, int flags, int nsplit, void* stream);
+/* Forward of a depthwise-separable block (+ the following train-mode BatchNorm's statistics / fold) in ONE kernel:
+ * the GEMM's transform warps build the operand u = depthwise_K(act(z)) + b_dw from the raw z tile (BN/ReLU/dropout on load,
+ * K-tap FIR, tf32 split) instead of reading a u tensor written by tn_dw_fwd; u_out (optional) receives u for the backward
+ * weight gradient.  Z = u W^T + b_pw (3xTF32).  bn may be NULL (statistics only, or none when stats is NULL too).
+ * DepthwiseConv1d.forward + the BatchNorm1d of ConvBlock1d (src/modules.py:64-93, 119-134). */
+int tn_gemm_tc_dwfwd(const float* z, const float* ws, const float* dw_w, const float* dw_b, const float* scale,
+                     const float* shift, int relu, float drop_p, const unsigned long long* seed, unsigned int layer,
+                     const float* pw_bias, float* u_out, float* Z, double* stats, const tn_bn_fold* bn, int B, int T, int C,
+                     int Co, int K, void* stream);
 int tn_conv_gemm_simt_bn(const float* X, const float* W, const float* bias, float* Z, double* stats, const tn_bn_fold* bn,
                          int B, int T, int Ci, int Co, int K, int flags, void* stream);
 /* Backward of conv -> train-mode BatchNorm fold in one pass over the tensor (tn_bn_bwd_coef + tn_stats_bwd):
@@ -222,6 +231,21 @@ int tn_margin_fwd_bwd(const float* raw_cos, const float* norms, const long long*
                       long long* preds, float* draw, float* dnorm, const float* gout, int B, int Cn, float scale,
                       int use_norm_scale, float m1, float m2, float m3, float eps, void* stream);
 int tn_rownorm_inplace(float* W, int rows, int cols, float eps, void* stream);
+
+/* ---- the step after the path: torch.optim.Adam over every parameter in ONE launch
+ *      (src/train.py:130-136: Adam, lr 1e-3, weight_decay 0).  hyper (device, 10 floats) =
+ *      {lr, beta1, beta2, eps, weight_decay, step, 1 - beta1^step, 1 - beta2^step, 1 - beta1, 1 - beta2}; tn_adam_tick advances
+ *      step and the two bias corrections on the device, so a captured step replays correctly.
+ *      g' = g + wd p;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;  p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps) */
+typedef struct tn_adam_job {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long long n;
+} tn_adam_job;
+int tn_adam_tick(float* hyper_dev, void* stream);
+int tn_adam_multi(const tn_adam_job* jobs_dev, int njobs, long long max_n, const float* hyper_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -188,3 +188,39 @@ def test_optional_launch_fusions_match_default():
     for k, gref in res[0][2].items():
         err = float((res[1][2][k] - gref).abs().max()) / max(float(gref.abs().max()), 1e-2 * gmax)
         assert err < 5e-2, (k, err)
+
+
+@pytest.mark.parametrize("B,T,C,Co,K,lazy,p", [(8, 301, 256, 256, 3, True, 0.0), (8, 301, 256, 256, 3, True, 0.1), (5, 77, 128, 256, 7, True, 0.1),
+                                                (64, 301, 256, 256, 3, False, 0.0), (3, 97, 64, 128, 5, True, 0.0), (2, 150, 256, 384, 1, True, 0.1)])
+def test_depthwise_fused_into_gemm_operand(B, T, C, Co, K, lazy, p):
+    """tn_gemm_tc_dwfwd (depthwise conv + BN/ReLU/dropout as the GEMM's operand producer) == tn_dw_fwd + tn_gemm_tc:
+    same dropout masks (same counter-based hash), same u side output, same statistics; and == fp64 torch when p = 0."""
+    from titanet_b200 import _ops as ops
+    g = torch.Generator().manual_seed(B * T + C + K)
+    R = B * T
+    z = torch.randn(R, C, generator=g)
+    sc, sh = 0.5 + torch.rand(C, generator=g), 0.3 * torch.randn(C, generator=g)
+    dw_w, dw_b = torch.randn(C, 1, K, generator=g) / math.sqrt(K), torch.randn(C, generator=g)
+    pw_w, pw_b = torch.randn(Co, C, 1, generator=g) / math.sqrt(C), torch.randn(Co, generator=g)
+    seed = torch.tensor([91], dtype=torch.int64, device="cuda")
+    outs = []
+    try:
+        for fused in (True, False):
+            ops.TC_FUSE_DWFWD = fused
+            stats = torch.zeros(2 * Co, dtype=torch.float64, device="cuda")
+            u, zo, _ = ops._dw_pw_forward(z.cuda(), sc.cuda() if lazy else None, sh.cuda() if lazy else None, dw_w.cuda(), dw_b.cuda(),
+                                          pw_w.cuda(), pw_b.cuda(), seed if p > 0 else None, True, p, 7, B, T, stats, None)
+            torch.cuda.synchronize()
+            outs.append((u.clone(), zo.clone(), stats.clone()))
+    finally:
+        ops.TC_FUSE_DWFWD = True
+    assert rel(outs[0][0], outs[1][0]) < 1e-6, "u side output"
+    assert rel(outs[0][1], outs[1][1]) < 1e-5, "pointwise output"
+    assert rel(outs[0][2][Co:], outs[1][2][Co:]) < 1e-5, "sum of squares"
+    if p == 0.0:
+        zz = z.double().view(B, T, C).permute(0, 2, 1)
+        a = torch.relu(zz * sc.double().view(1, -1, 1) + sh.double().view(1, -1, 1)) if lazy else zz
+        ur = F.conv1d(F.pad(a, (K // 2, K // 2)), dw_w.double(), dw_b.double(), groups=C)
+        zr = F.conv1d(ur, pw_w.double(), pw_b.double()).permute(0, 2, 1).reshape(R, Co)
+        assert rel(outs[0][0], ur.permute(0, 2, 1).reshape(R, C)) < 1e-5
+        assert rel(outs[0][1], zr) < 1e-5

@@ -365,3 +365,29 @@ def test_standalone_squeeze_excitation_matches_fp64():
     assert rel(y, yr) < 1e-5
     assert rel(xg.grad, xr.grad) < 1e-4
     assert rel(se.excitation[0].weight.grad, w1r.grad) < 1e-4 and rel(se.excitation[2].weight.grad, w2r.grad) < 1e-4
+
+
+def test_fused_adam_matches_torch_adam():
+    """optim.FusedAdam == torch.optim.Adam (src/train.py:130-136) over several steps, incl. weight decay and an LR change."""
+    from titanet_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(3)
+    shapes = [(64, 32, 3), (64,), (7, 5), (1,), (1000, 33)]
+    ref_p = [torch.randn(s, generator=g, dtype=torch.float64).requires_grad_(True) for s in shapes]
+    our_p = [p.detach().float().to(dev()).requires_grad_(True) for p in ref_p]
+    for wd in (0.0, 0.01):
+        ref = torch.optim.Adam(ref_p, lr=1e-3, weight_decay=wd)
+        ours = FusedAdam(our_p, lr=1e-3, weight_decay=wd)
+        for it in range(4):
+            if it == 2:
+                for o in (ref, ours):
+                    o.param_groups[0]["lr"] = 5e-4
+            for pr, po in zip(ref_p, our_p):
+                gr = torch.randn(pr.shape, generator=g, dtype=torch.float64)
+                pr.grad = gr.clone()
+                po.grad = gr.float().to(dev())
+            ref.step()
+            ours.step()
+        for pr, po in zip(ref_p, our_p):
+            assert rel(po, pr) < 2e-6
+        assert rel(ours.state[our_p[0]]["exp_avg"], ref.state[ref_p[0]]["exp_avg"]) < 1e-5
+        assert rel(ours.state[our_p[0]]["exp_avg_sq"], ref.state[ref_p[0]]["exp_avg_sq"]) < 1e-5

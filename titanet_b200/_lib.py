@@ -114,6 +114,12 @@ class TnSplitJob(ctypes.Structure):
                 ("transpose", ctypes.c_int), ("pad_", ctypes.c_int)]
 
 
+class TnAdamJob(ctypes.Structure):
+    """``tn_adam_job`` of include/titanet_b200.h."""
+    _fields_ = [("p", ctypes.c_void_p), ("g", ctypes.c_void_p), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p),
+                ("n", ctypes.c_longlong)]
+
+
 LIB = _Lib()
 _checked_device = False
 

@@ -546,6 +546,34 @@ FUSE_BLOCK_ENTRY = _os.environ.get("TN_FUSE_BLOCK_ENTRY", "0") == "1"
 FUSE_SE_MLP = _os.environ.get("TN_FUSE_SE_MLP", "0") == "1"
 
 
+TC_FUSE_DWFWD = _os.environ.get("TN_FUSE_DWFWD", "1") != "0"
+
+
+def _dw_pw_forward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, relu, p, layer, B, T, stats, bn):
+    """u = depthwise(act(z)) + b_dw ; zo = pointwise(u) + b_pw (+ statistics / BatchNorm fold of zo).  One tensor-core kernel
+    (tn_gemm_tc_dwfwd: the depthwise conv is the GEMM's operand producer) when the shape allows, else tn_dw_fwd + GEMM.
+    Returns (u, zo, ws_dgrad)."""
+    C, K = dw_w.shape[0], dw_w.shape[-1]
+    pw3 = pw_w if pw_w.dim() == 3 else pw_w.unsqueeze(-1)
+    Co, R = pw3.shape[0], B * T
+    u = empty(z.shape, z)
+    zo = empty((R, Co), z)
+    sp = cached_splits(pw_w)
+    if (TC_FUSE_DWFWD and TC_FWD_NSPLIT == 3 and _tc_ok(R, C, Co, pw3.shape[2]) and K % 2 == 1 and K <= 7 and (R + 16) * C < 2 ** 32):
+        ws = sp[0] if sp else None
+        if ws is None:
+            ws = torch.empty((2, Co, C), device=z.device, dtype=torch.float32)
+            call("tn_split_tf32", ptr(pw3), ptr(ws), Co, C, 0)
+        call("tn_gemm_tc_dwfwd", ptr(z), ptr(ws), ptr(dw_w), ptr(dw_b), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed),
+             int(layer), ptr(pw_b), ptr(u), ptr(zo), ptr(stats), ctypes.byref(bn) if bn is not None else None, B, T, C, Co, K,
+             tag=f"dw+fwd R{R} Ci{C} Co{Co} K1")
+    else:
+        call("tn_dw_fwd", ptr(z), ptr(u), ptr(dw_w), ptr(dw_b), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer),
+             B, T, C, K)
+        _gemm_fwd(u, pw3, pw_b, zo, stats, B, T, 0, 0, ws=sp[0] if sp else None, bn=bn)
+    return u, zo, (sp[1] if sp else None)
+
+
 class DwPw(Function):
     """Depthwise-separable convolution on a lazy activation, with the following BatchNorm's
     statistics:  z_out = pointwise(depthwise_K(act(z)) + b_dw) + b_pw  (modules.DepthwiseConv1d,
@@ -559,14 +587,8 @@ class DwPw(Function):
         C, K = dw_w.shape[0], dw_w.shape[-1]
         Co = pw_w.shape[0]
         assert z.shape == (B * T, C)
-        u = empty(z.shape, z)
-        call("tn_dw_fwd", ptr(z), ptr(u), ptr(dw_w), ptr(dw_b), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer),
-             B, T, C, K)
-        zo = empty((B * T, Co), z)
         stats = zeros((2 * Co,), z, torch.float64) if want_stats else None
-        sp = cached_splits(pw_w)
-        _gemm_fwd(u, pw_w if pw_w.dim() == 3 else pw_w.unsqueeze(-1), pw_b, zo, stats, B, T, 0, 0, ws=sp[0] if sp else None)
-        ctx.ws_t = sp[1] if sp else None
+        u, zo, ctx.ws_t = _dw_pw_forward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, relu, p, layer, B, T, stats, None)
         ctx.save_for_backward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, u, zo if want_stats else None)
         ctx.meta = (relu, p, layer, B, T, want_stats)
         return zo, stats
@@ -630,17 +652,11 @@ class DwPwBN(Function):
         C, K = dw_w.shape[0], dw_w.shape[-1]
         Co = pw_w.shape[0]
         assert z.shape == (B * T, C)
-        u = empty(z.shape, z)
-        call("tn_dw_fwd", ptr(z), ptr(u), ptr(dw_w), ptr(dw_b), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer),
-             B, T, C, K)
-        zo = empty((B * T, Co), z)
         stats, fold = _bn_forward_buffers(Co, z)
         n = float(B * T)
         bn = make_bn_fold(gamma, beta, rm, rv, nbt, momentum, eps, n, fold[0], fold[1], fold[2], fold[3],
                           stats.data_ptr() + 16 * Co)
-        sp = cached_splits(pw_w)
-        _gemm_fwd(u, pw_w if pw_w.dim() == 3 else pw_w.unsqueeze(-1), pw_b, zo, stats, B, T, 0, 0, ws=sp[0] if sp else None, bn=bn)
-        ctx.ws_t = sp[1] if sp else None
+        u, zo, ctx.ws_t = _dw_pw_forward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, relu, p, layer, B, T, stats, bn)
         ctx.save_for_backward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, u, zo, gamma, fold)
         ctx.meta = (relu, p, layer, B, T, n)
         return zo, fold[0], fold[1]
@@ -683,15 +699,10 @@ class BlockEntryBN(Function):
         sp_s = cached_splits(sk_w)
         sk3 = sk_w if sk_w.dim() == 3 else sk_w.unsqueeze(-1)
         _gemm_fwd(z, sk3, sk_b, s, st_s, B, T, 0, 0, ws=sp_s[0] if sp_s else None, bn=bn_s)
-        u = empty(z.shape, z)
-        call("tn_dw_fwd", ptr(z), ptr(u), ptr(dw_w), ptr(dw_b), None, None, 0, 0.0, None, 0, B, T, C, K)
-        zo = empty((R, Co), z)
         st_1, fold_1 = _bn_forward_buffers(Co, z)
         bn_1 = make_bn_fold(g1, b1, rm1, rv1, nbt1, mom1, eps1, n, fold_1[0], fold_1[1], fold_1[2], fold_1[3],
                             st_1.data_ptr() + 16 * Co)
-        sp_1 = cached_splits(pw_w)
-        _gemm_fwd(u, pw_w if pw_w.dim() == 3 else pw_w.unsqueeze(-1), pw_b, zo, st_1, B, T, 0, 0, ws=sp_1[0] if sp_1 else None, bn=bn_1)
-        ctx.ws_t1 = sp_1[1] if sp_1 else None
+        u, zo, ctx.ws_t1 = _dw_pw_forward(z, None, None, dw_w, dw_b, pw_w, pw_b, None, False, 0.0, 0, B, T, st_1, bn_1)
         ctx.ws_ts = sp_s[1] if sp_s else None
         ctx.save_for_backward(z, dw_w, dw_b, pw_w, pw_b, g1, sk_w, sk_b, gs, u, zo, s, fold_1, fold_s)
         ctx.meta = (B, T, n)

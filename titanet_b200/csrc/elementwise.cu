@@ -484,3 +484,44 @@ extern "C" int tn_l2norm_bwd(const float* dy, const float* y, const float* norms
   TN_LAUNCH_CHECK("l2norm_bwd_kernel");
   return TN_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Adam over all parameters in one launch (torch.optim.Adam semantics; src/train.py:130-136)
+// ---------------------------------------------------------------------------
+__global__ void adam_tick_kernel(float* hyper) {
+  tn_grid_dep_sync();
+  const float step = hyper[5] + 1.f;
+  hyper[5] = step;
+  hyper[6] = (float)(1.0 - pow((double)hyper[1], (double)step));      // double: 1 - 0.999^1 cancels badly in fp32
+  hyper[7] = (float)(1.0 - pow((double)hyper[2], (double)step));
+}
+__global__ void __launch_bounds__(256) adam_multi_kernel(const tn_adam_job* __restrict__ jobs, const float* __restrict__ hyper) {
+  tn_grid_dep_sync();
+  const tn_adam_job j = jobs[blockIdx.y];
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+  const float step_size = lr / hyper[6], inv_sqrt_bc2 = rsqrtf(hyper[7]);
+  const float omb1 = hyper[8], omb2 = hyper[9];        // 1 - beta, rounded once from double by the host (1.f - 0.999f is 1e-5 off)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < j.n; i += (long long)gridDim.x * blockDim.x) {
+    const float p = j.p[i];
+    const float g = fmaf(wd, p, j.g[i]);
+    const float m = fmaf(b1, j.m[i], omb1 * g);
+    const float v = fmaf(b2, j.v[i], omb2 * g * g);
+    j.m[i] = m;
+    j.v[i] = v;
+    j.p[i] = p - step_size * m / (sqrtf(v) * inv_sqrt_bc2 + eps);
+  }
+}
+extern "C" int tn_adam_tick(float* hyper_dev, void* stream) {
+  TN_REQUIRE(hyper_dev, "adam_tick: null state");
+  tn_launch(adam_tick_kernel, 1, 1, 0, stream, hyper_dev);
+  TN_LAUNCH_CHECK("adam_tick_kernel");
+  return TN_OK;
+}
+extern "C" int tn_adam_multi(const tn_adam_job* jobs_dev, int njobs, long long max_n, const float* hyper_dev, void* stream) {
+  TN_REQUIRE(jobs_dev && hyper_dev && njobs > 0 && njobs <= 65535 && max_n > 0, "adam_multi: bad arguments");
+  long long bx = (max_n + 256 * 8 - 1) / (256 * 8);
+  if (bx > 64) bx = 64;
+  tn_launch(adam_multi_kernel, dim3((unsigned)bx, (unsigned)njobs), 256, 0, stream, jobs_dev, hyper_dev);
+  TN_LAUNCH_CHECK("adam_multi_kernel");
+  return TN_OK;
+}

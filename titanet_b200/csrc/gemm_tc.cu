@@ -184,6 +184,13 @@ struct TcParams {
   // fused depthwise-backward epilogue (dw_K > 0): this GEMM is the data gradient of a pointwise conv
   // whose input was depthwise_K(act(zprev)); the epilogue turns du (in TMEM) into dzprev directly.
   int dw_K, dw_T, BNo;   // taps, frames per utterance, output rows per CTA (BN = BNo + halo)
+  // fused depthwise FORWARD (fdw_K > 0): the B operand is u = depthwise_K(act(z)) + b, produced by the transform warps from
+  // the raw z tile TMA delivers (act = p.act); u is also written to fdw_u for the weight-gradient GEMM of the backward pass
+  int fdw_K, fdw_T;
+  const float* fdw_w;    // [Kd, K]
+  const float* fdw_b;    // [Kd] or NULL
+  float* fdw_u;          // [R, Kd] or NULL
+  uint32_t par_off;      // byte offset of the per-channel parameter table [3 + K][Kd] behind the pipeline stages
   int z_early;           // z tiles may be requested while the last chunks are still in the tensor core (2 stages)
   uint32_t z_off1;       // byte offset of the second z tile in the (freed) pipeline memory when !z_early
   uint32_t red_off;      // byte offset of the per-channel reduction staging buffer (behind the pipeline stages)
@@ -385,13 +392,128 @@ __device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams
   asm volatile("bar.sync 1, 256;" ::: "memory");          // `red` is reused by the next channel half
   if (tr) tr[3] = clock64();
 }
+
+// Fused depthwise-forward operand producer (the transform warps' mainloop when fdw_K > 0).  Per K chunk (32 channels)
+// TMA delivers the RAW z tile into the B_hi region: raw row r <-> global row n0 - PAD + r (rows outside the tensor are
+// zero-filled), 128-byte swizzled rows.  Thread (q = channel quad 0..7, row lane 0..31) owns up to RP consecutive output
+// rows j0 .. j0+rp-1: phase 1 pulls its window of RP + 2 PAD raw float4s into registers, a named barrier lets every thread
+// finish reading, phase 2 applies BN/ReLU/dropout, the K-tap FIR and the tf32 hi/lo split and writes the operand rows in
+// place (hi) and to B_lo.  Per-channel parameters (scale, shift, bias, taps) sit in shared memory as [field][channel].
+// Reference ops: nn.BatchNorm1d/ReLU/Dropout of the previous ConvBlock1d + DepthwiseConv1d's first conv
+// (src/modules.py:64-75, 128-133).
+template <int K, int RP>
+__device__ __forceinline__ void tc_dw_mainloop(const TcParams& p, uint8_t* smem, uint32_t stage_bytes, uint32_t bh_off, uint32_t bl_off,
+                                               uint32_t full0, uint32_t ready0, int S, int num_kc, int n0, int BN, const float* par,
+                                               int tid) {
+  constexpr int PAD = K / 2;
+  constexpr int W = RP + 2 * PAD;
+  const TnAct act = tn_act_init(p.act);
+  const int C = p.Kd, T = p.fdw_T, R = p.R;
+  const bool lazy = act.scale != nullptr;
+  const bool drop = act.thresh != 0;
+  const uint32_t key = tn_hash_key32(act.seed_lo, act.seed_hi, act.layer);
+  const uint32_t q = (uint32_t)tid & 7u;
+  const int rpa = (BN + 31) >> 5;                            // rows per lane actually used (<= RP)
+  const int j0 = (tid >> 3) * rpa;
+  const int rp = min(rpa, BN - j0);                          // may be <= 0 for the last lanes
+  const int t0 = (int)(((long long)n0 + j0) % T);
+  const bool interior = rp > 0 && t0 - PAD >= 0 && t0 + rp - 1 + PAD < T;   // every tap of every row inside one utterance
+  // validity of the window rows (global row n0 - PAD + j0 + i inside the tensor) as a bit mask
+  uint32_t vmask = 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const int grow = n0 - PAD + j0 + i;
+    if (grow >= 0 && grow < R) vmask |= 1u << i;
+  }
+  for (int kc = 0; kc < num_kc; ++kc) {
+    const int s = kc % S;
+    uint8_t* bh = smem + (size_t)s * stage_bytes + bh_off;
+    uint8_t* bl = smem + (size_t)s * stage_bytes + bl_off;
+    const int c = kc * TC_BK + 4 * (int)q;
+    // per-channel parameters of this thread's four channels
+    const float4 sc4 = *reinterpret_cast<const float4*>(par + c);
+    const float4 sh4 = *reinterpret_cast<const float4*>(par + C + c);
+    const float4 b4 = *reinterpret_cast<const float4*>(par + 2 * C + c);
+    mbar_wait(full0 + 8 * s, (kc / S) & 1);
+    float4 win[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const uint32_t r = (uint32_t)(j0 + i);
+      if (i < rp + 2 * PAD) win[i] = *reinterpret_cast<const float4*>(bh + r * 128u + ((q ^ (r & 7u)) << 4));
+      else win[i] = tn_zero4();
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");        // every thread has its window: the raw tile may be overwritten
+    if (rp > 0) {
+      if (lazy) {
+        // 32-bit element indices (the launcher guarantees (R + 16) * C < 2^32); pair p = idx >> 1 feeds one hash for two
+        // elements, exactly like tn_drop4 (common.cuh)
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+          float4 v = make_float4(fmaf(win[i].x, sc4.x, sh4.x), fmaf(win[i].y, sc4.y, sh4.y), fmaf(win[i].z, sc4.z, sh4.z),
+                                 fmaf(win[i].w, sc4.w, sh4.w));
+          float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (drop) {
+            const uint32_t pr = ((uint32_t)(n0 - PAD + j0 + i) * (uint32_t)C + (uint32_t)c) >> 1;   // rows < 0 wrap: masked below
+            const uint32_t h0 = tn_hash_elem32(key, pr), h1 = tn_hash_elem32(key, pr + 1u);
+            m = make_float4((h0 & 0xFFFFu) >= act.thresh ? act.inv_keep : 0.f, (h0 >> 16) >= act.thresh ? act.inv_keep : 0.f,
+                            (h1 & 0xFFFFu) >= act.thresh ? act.inv_keep : 0.f, (h1 >> 16) >= act.thresh ? act.inv_keep : 0.f);
+          }
+          if (act.relu) {
+            m.x = v.x > 0.f ? m.x : 0.f; m.y = v.y > 0.f ? m.y : 0.f;
+            m.z = v.z > 0.f ? m.z : 0.f; m.w = v.w > 0.f ? m.w : 0.f;
+          }
+          win[i] = make_float4(v.x * m.x, v.y * m.y, v.z * m.z, v.w * m.w);
+        }
+        if (vmask != (1u << W) - 1u) {                      // tensor edge: rows outside contribute nothing
+#pragma unroll
+          for (int i = 0; i < W; ++i)
+            if (!((vmask >> i) & 1u)) win[i] = tn_zero4();
+        }
+      }
+      float4 wk[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) wk[k] = *reinterpret_cast<const float4*>(par + (3 + k) * C + c);
+#pragma unroll
+      for (int i = 0; i < RP; ++i) {
+        if (i < rp) {
+          const int j = j0 + i;
+          float4 acc = b4;
+          if (interior) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc = tn_fma4(wk[k], win[i + k], acc);
+          } else {
+            const int t = (t0 + i) % T;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+              const int tt = t + k - PAD;
+              if (tt >= 0 && tt < T) acc = tn_fma4(wk[k], win[i + k], acc);
+            }
+          }
+          if (p.fdw_u && n0 + j < R) tn_st4(p.fdw_u + (size_t)(n0 + j) * C + c, acc);
+          uint4 h, l;
+          h.x = rna_tf32(acc.x); h.y = rna_tf32(acc.y); h.z = rna_tf32(acc.z); h.w = rna_tf32(acc.w);
+          l.x = rna_tf32(acc.x - __uint_as_float(h.x)); l.y = rna_tf32(acc.y - __uint_as_float(h.y));
+          l.z = rna_tf32(acc.z - __uint_as_float(h.z)); l.w = rna_tf32(acc.w - __uint_as_float(h.w));
+          const uint32_t o = (uint32_t)j * 128u + ((q ^ ((uint32_t)j & 7u)) << 4);
+          *reinterpret_cast<uint4*>(bh + o) = h;
+          *reinterpret_cast<uint4*>(bl + o) = l;
+        }
+      }
+    }
+    fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
+    mbar_arrive(ready0 + 8 * s);
+  }
+}
 #define TC_TRACE(slot) do { if (p.trace && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && blockIdx.y == 0) \
     p.trace[(blockIdx.x == 0 ? 0 : 128) + (slot)] = clock64(); } while (0)
 
 // ---------------------------------------------------------------------------
 // kernel: MT = number of 128-row output-channel tiles per CTA (1 or 2)
 // ---------------------------------------------------------------------------
-template <int MT>
+// MODE: 0 plain GEMM epilogue, 1 fused depthwise-BACKWARD epilogue (dw_K > 0), 2 fused depthwise-FORWARD operand producer
+// (fdw_K > 0).  A template parameter, not a runtime branch: one instantiation carrying all three costs the plain GEMM ~1.5 us
+// per launch (registers / instruction cache), measured.
+template <int MT, int MODE>
 __global__ void __launch_bounds__(TC_GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ, TcParams p) {
@@ -409,20 +531,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int BN = p.BN, S = p.stages;
   // first activation row of this CTA's tile (fused depthwise backward: the tile starts PAD rows early;
   // TMA zero-fills rows < 0 and >= R)
-  const int n0 = p.dw_K > 0 ? blockIdx.x * p.BNo - (p.dw_K >> 1) : blockIdx.x * BN;
+  const int n0 = MODE == 1 ? blockIdx.x * p.BNo - (p.dw_K >> 1) : blockIdx.x * BN;
   const int m0 = blockIdx.y * (128 * MT);            // first output channel of this CTA
   const int num_kc = p.Kd / TC_BK;
   const bool split = p.nsplit == 3;
 
   const uint32_t a_tile = 128 * TC_BK * 4;           // 16 KiB per 128-channel weight tile
   const uint32_t b_tile = (uint32_t)BN * TC_BK * 4;
-  const uint32_t stage_bytes = (split ? 2 : 1) * (MT * a_tile + b_tile);
-  const uint32_t tx_bytes = (split ? 2 : 1) * MT * a_tile + b_tile;      // B_lo is written by the transform warps, not TMA
-  // stage layout: A_hi[MT] | B_hi | (A_lo[MT] | B_lo)
+  // fused depthwise forward: TMA delivers the RAW z tile with 16 extra rows (halo of the K-tap FIR) into the B_hi region
+  const uint32_t b_raw = b_tile + (MODE == 2 ? 16u * TC_BK * 4 : 0u);
+  const uint32_t nA = (split ? 2u : 1u) * MT;
+  const uint32_t stage_bytes = nA * a_tile + b_raw + (split ? b_tile : 0u);
+  const uint32_t tx_bytes = nA * a_tile + b_raw;                         // B_lo is written by the transform warps, not TMA
+  // stage layout: A_hi[MT] | A_lo[MT] | B_hi (raw tile) | B_lo
   auto a_hi = [&](int s, int mt) { return smem + (size_t)s * stage_bytes + mt * a_tile; };
-  auto b_hi = [&](int s) { return smem + (size_t)s * stage_bytes + MT * a_tile; };
-  auto a_lo = [&](int s, int mt) { return smem + (size_t)s * stage_bytes + MT * a_tile + b_tile + mt * a_tile; };
-  auto b_lo = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * MT * a_tile + b_tile; };
+  auto a_lo = [&](int s, int mt) { return smem + (size_t)s * stage_bytes + (MT + mt) * a_tile; };
+  auto b_hi = [&](int s) { return smem + (size_t)s * stage_bytes + nA * a_tile; };
+  auto b_lo = [&](int s) { return smem + (size_t)s * stage_bytes + nA * a_tile + b_raw; };
   const uint32_t full0 = smem_u32(&bars[0]), ready0 = smem_u32(&bars[TC_MAX_STAGES]), empty0 = smem_u32(&bars[2 * TC_MAX_STAGES]);
   const uint32_t accum_bar = smem_u32(&bars[3 * TC_MAX_STAGES]);
   const uint32_t z_bar0 = smem_u32(&bars[3 * TC_MAX_STAGES + 1]);     // fused depthwise backward: z tile of output-channel half mt
@@ -466,7 +591,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const uint32_t fb = full0 + 8 * s;
         const bool skip_a = (p.flags & 1024) != 0;      // debug knob: measure the B feed alone
         TC_TRACE(1 + kc);
-        mbar_expect_tx(fb, skip_a ? b_tile : tx_bytes);
+        mbar_expect_tx(fb, skip_a ? b_raw : tx_bytes);
         const int k0 = kc * TC_BK;
         if (MT == 2 && p.cluster2) {
           // each CTA of the pair fetches ONE of the two 128-channel weight tiles and multicasts it to both: the weights
@@ -481,9 +606,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (split) tma_load_2d(smem_u32(a_lo(s, mt)), &tmA_lo, fb, k0, m0 + mt * 128);
           }
         }
-        tma_load_2d(smem_u32(b_hi(s)), &tmB, fb, k0, n0);
+        tma_load_2d(smem_u32(b_hi(s)), &tmB, fb, k0, n0 - (MODE == 2 ? (p.fdw_K >> 1) : 0));     // fused depthwise forward: PAD rows of halo in front
       }
-      if (p.dw_K > 0) {
+      if (MODE == 1) {
         // z tiles of the previous layer for the fused epilogue: wait until the tensor core has finished with the
         // pipeline stage(s) a tile overwrites (the MMA warp's commit on `empty` of the stage's last chunk)
         auto wait_stage_free = [&](int s) {
@@ -545,7 +670,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else {
     // ===== transform warps (split only), then epilogue =====
     const int tid = threadIdx.x - 64;        // 0..255
-    if (split) {
+    if (MODE == 2) {
+      // fused depthwise forward: per-channel parameters to shared memory ([scale | shift | bias | tap 0 | ... ] x Kd), then the
+      // operand-producing mainloop (tc_dw_mainloop)
+      float* par = reinterpret_cast<float*>(smem + p.par_off);
+      const int Kd = p.Kd, Kt = p.fdw_K;
+      for (int idx = tid; idx < Kd * (3 + Kt); idx += TC_EPI_THREADS) {
+        const int f = idx / Kd, ch = idx - f * Kd;
+        float v;
+        if (f == 0) v = p.act.scale ? __ldg(p.act.scale + ch) : 1.f;
+        else if (f == 1) v = p.act.scale ? __ldg(p.act.shift + ch) : 0.f;
+        else if (f == 2) v = p.fdw_b ? __ldg(p.fdw_b + ch) : 0.f;
+        else v = __ldg(p.fdw_w + (size_t)ch * Kt + (f - 3));
+        par[idx] = v;
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      const uint32_t bh_off = nA * a_tile, bl_off = nA * a_tile + b_raw;
+      const bool small = ((BN + 31) >> 5) <= 5;
+#define TC_DW_CALL(KK, RR) tc_dw_mainloop<KK, RR>(p, smem, stage_bytes, bh_off, bl_off, full0, ready0, S, num_kc, n0, BN, par, tid)
+      switch (p.fdw_K) {
+        case 1: if (small) TC_DW_CALL(1, 5); else TC_DW_CALL(1, 8); break;
+        case 3: if (small) TC_DW_CALL(3, 5); else TC_DW_CALL(3, 8); break;
+        case 5: if (small) TC_DW_CALL(5, 5); else TC_DW_CALL(5, 8); break;
+        default: if (small) TC_DW_CALL(7, 5); else TC_DW_CALL(7, 8); break;
+      }
+#undef TC_DW_CALL
+    } else if (split) {
       const int n4 = BN * TC_BK / 4;
       for (int kc = 0; kc < num_kc; ++kc) {
         const int s = kc % S;
@@ -572,7 +722,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int quad = warp & 3;               // TMEM lanes 32*quad .. 32*quad+31 belong to this warp
     const int half = (warp - 2) >> 2;        // 0 / 1: which of the two warps of this quadrant
     const int nvalid = min(BN, p.R - n0);                       // rows of this tile inside the tensor
-    if (p.dw_K > 0) {
+    if (MODE == 1) {
       const TnAct act = tn_act_init(p.act);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
@@ -926,6 +1076,25 @@ static int pick_bn(long long R, int groups, int per_row_stage_bytes, int fixed_s
   return best;
 }
 
+template <int MT, int MODE>
+static cudaError_t launch_inst(bool cluster, dim3 grid, size_t smem, void* stream, const CUtensorMap& a, const CUtensorMap& b,
+                               const CUtensorMap& c, const CUtensorMap& d, const TcParams& p) {
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (cluster) tn_launch_cluster(gemm_tc_kernel<MT, MODE>, grid, TC_GEMM_THREADS, smem, stream, 2, a, b, c, d, p);
+  else tn_launch(gemm_tc_kernel<MT, MODE>, grid, TC_GEMM_THREADS, smem, stream, a, b, c, d, p);
+  return cudaSuccess;
+}
+template <int MT>
+static cudaError_t launch_mode(int mode, bool cluster, dim3 grid, size_t smem, void* stream, const CUtensorMap& a, const CUtensorMap& b,
+                               const CUtensorMap& c, const CUtensorMap& d, const TcParams& p) {
+  switch (mode) {
+    case 1: return launch_inst<MT, 1>(cluster, grid, smem, stream, a, b, c, d, p);
+    case 2: return launch_inst<MT, 2>(cluster, grid, smem, stream, a, b, c, d, p);
+    default: return launch_inst<MT, 0>(cluster, grid, smem, stream, a, b, c, d, p);
+  }
+}
+
 // common launcher: p carries the epilogue configuration; shapes / tiles / maps are filled here
 static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, int Kd, int M, int nsplit, void* stream) {
   TN_REQUIRE(X && ws, "gemm_tc: null tensor");
@@ -940,22 +1109,25 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   const int halo = p.dw_K > 1 ? 16 : 0;              // 2 * PAD <= 14 rows of halo, rounded to the MMA's N granularity
   int stages = 2;
   // fused depthwise backward: [2 halves][128 channels][K + 3 sums] of staging behind the pipeline stages
-  const int red_bytes = p.dw_K > 0 ? (2 * 128 * (p.dw_K + 3) * 4 + 1023) / 1024 * 1024 : (p.stats ? 2048 : 0);
-  const int bno = pick_bn(R, groups, mult * TC_BK * 4, mult * MT * 128 * TC_BK * 4, halo, red_bytes, &stages);
+  const int par_bytes = p.fdw_K > 0 ? (Kd * (3 + p.fdw_K) * 4 + 1023) / 1024 * 1024 : 0;
+  const int red_bytes = (p.dw_K > 0 ? (2 * 128 * (p.dw_K + 3) * 4 + 1023) / 1024 * 1024 : (p.stats ? 2048 : 0)) + par_bytes;
+  const int fdw_extra = p.fdw_K > 0 ? 16 * TC_BK * 4 : 0;       // raw-tile halo rows of the fused depthwise forward
+  const int bno = pick_bn(R, groups, mult * TC_BK * 4, mult * MT * 128 * TC_BK * 4 + fdw_extra, halo, red_bytes, &stages);
   TN_REQUIRE(bno >= 32, "gemm_tc: no tile configuration fits shared memory");
   const int bn = bno + halo;
   CUtensorMap mA_hi, mA_lo, mB;
   if ((rc = make_map(&mA_hi, ws, M, Kd, 128)) != TN_OK) return rc;
   if ((rc = make_map(&mA_lo, ws + (size_t)M * Kd, M, Kd, 128)) != TN_OK) return rc;
-  if ((rc = make_map(&mB, X, R, Kd, bn)) != TN_OK) return rc;
+  if ((rc = make_map(&mB, X, R, Kd, bn + (p.fdw_K > 0 ? 16 : 0))) != TN_OK) return rc;
   p.R = R; p.Kd = Kd; p.M_total = M; p.BN = bn; p.BNo = bno; p.stages = stages; p.nsplit = nsplit;
   p.trace = g_trace;
   int cols = MT == 2 ? 512 : 32;
   while (MT == 1 && cols < bn) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t stage_bytes = (size_t)mult * (MT * 128 * TC_BK * 4 + (size_t)bn * TC_BK * 4);
+  const size_t stage_bytes = (size_t)mult * (MT * 128 * TC_BK * 4 + (size_t)bn * TC_BK * 4) + fdw_extra;
   const size_t smem = stage_bytes * stages + red_bytes + 1024;
   p.red_off = (uint32_t)(stage_bytes * stages);
+  p.par_off = (uint32_t)(stage_bytes * stages + red_bytes - par_bytes);
   CUtensorMap mZ = mB;
   if (p.dw_K > 0) {
     // z tiles of the fused epilogue reuse the pipeline memory: one tile = 128 channels x bn rows = 4 blocks of bn x 128 B
@@ -968,6 +1140,7 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
     TN_REQUIRE(ztile <= stage_bytes * stages, "gemm_tc_dwbwd: z tile does not fit the pipeline memory");
   }
   dim3 grid(tn_cdiv(R, bno), groups);
+  const int mode = p.dw_K > 0 ? 1 : (p.fdw_K > 0 ? 2 : 0);
   static int use_cluster = -1;
   if (use_cluster < 0) { const char* e = getenv("TN_TC_CLUSTER"); use_cluster = (e && atoi(e) != 0) ? 1 : 0; }   // no gain measured: opt-in
   if (MT == 2 && use_cluster && grid.x >= 2) {
@@ -975,14 +1148,11 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
     // nothing stored)
     grid.x = (grid.x + 1) & ~1u;
     p.cluster2 = 1;
-    TN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tn_launch_cluster(gemm_tc_kernel<2>, grid, TC_GEMM_THREADS, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
+    TN_CUDA(launch_mode<2>(mode, true, grid, smem, stream, mA_hi, mA_lo, mB, mZ, p));
   } else if (MT == 2) {
-    TN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tn_launch(gemm_tc_kernel<2>, grid, TC_GEMM_THREADS, smem, stream, mA_hi, mA_lo, mB, mZ, p);
+    TN_CUDA(launch_mode<2>(mode, false, grid, smem, stream, mA_hi, mA_lo, mB, mZ, p));
   } else {
-    TN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tn_launch(gemm_tc_kernel<1>, grid, TC_GEMM_THREADS, smem, stream, mA_hi, mA_lo, mB, mZ, p);
+    TN_CUDA(launch_mode<1>(mode, false, grid, smem, stream, mA_hi, mA_lo, mB, mZ, p));
   }
   TN_LAUNCH_CHECK("gemm_tc_kernel");
   return TN_OK;
@@ -1017,6 +1187,34 @@ extern "C" int tn_gemm_tc_bn(const float* X, const float* ws, const float* bias,
   p.bias = bias; p.Z = Z; p.stats = stats; p.flags = flags;
   p.bn = *bn; p.has_bn = 1;
   return launch_gemm_tc(X, ws, p, R, Kd, M, nsplit, stream);
+}
+
+// Forward of a depthwise-separable conv block + train-mode BatchNorm fold in ONE kernel:
+//   u = depthwise_K(act(z)) + b_dw  (transform warps, from the raw z tile)   [also written to u_out for the backward wgrad]
+//   Z = u W^T + b_pw  (tensor cores, 3xTF32), statistics of Z, BatchNorm fold by the last CTA (bn may be NULL: stats only / none)
+extern "C" int tn_gemm_tc_dwfwd(const float* z, const float* ws, const float* dw_w, const float* dw_b, const float* scale,
+                                const float* shift, int relu, float drop_p, const unsigned long long* seed, unsigned int layer,
+                                const float* pw_bias, float* u_out, float* Z, double* stats, const tn_bn_fold* bn, int B, int T,
+                                int C, int Co, int K, void* stream) {
+  TN_REQUIRE(z && dw_w && Z, "gemm_tc_dwfwd: null tensor");
+  TN_REQUIRE(K >= 1 && K <= 7 && (K & 1), "gemm_tc_dwfwd: unsupported depthwise kernel size %d (odd sizes 1..7; wider windows do not fit the register file)", K);
+  TN_REQUIRE((scale == nullptr) == (shift == nullptr), "gemm_tc_dwfwd: scale and shift come together");
+  TN_REQUIRE(drop_p <= 0.f || seed, "gemm_tc_dwfwd: dropout needs a seed");
+  long long R = (long long)B * T;
+  TN_REQUIRE(B > 0 && T > 0 && R < (1ll << 31), "gemm_tc_dwfwd: bad B/T");
+  TN_REQUIRE(tn_aligned16(dw_b ? (const void*)dw_b : (const void*)z) && (!u_out || tn_aligned16(u_out)) && (!scale || (tn_aligned16(scale) && tn_aligned16(shift))),
+             "gemm_tc_dwfwd: pointers must be 16B aligned");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = pw_bias; p.Z = Z; p.stats = stats;
+  if (bn) {
+    int rc = check_bn(bn, stats);
+    if (rc != TN_OK) return rc;
+    p.bn = *bn; p.has_bn = 1;
+  }
+  p.fdw_K = K; p.fdw_T = T; p.fdw_w = dw_w; p.fdw_b = dw_b; p.fdw_u = u_out;
+  p.act = tn_make_act(scale, shift, relu, drop_p, seed, layer);
+  return launch_gemm_tc(z, ws, p, (int)R, C, Co, 3, stream);
 }
 
 // Data gradient of a depthwise-separable conv block in one kernel:

@@ -1,0 +1,82 @@
+"""The step after the hot path: ``torch.optim.Adam`` as ONE kernel launch.
+
+The reference builds ``torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0)``
+(src/train.py:130-136); on a 426-tensor TitaNet-S that is hundreds of small launches per step.
+``FusedAdam`` keeps the same constructor, ``param_groups`` / ``state_dict`` round trip and arithmetic
+(bias-corrected, L2 weight decay folded into the gradient, no amsgrad) and updates every parameter in one
+``tn_adam_multi`` launch; the step counter and bias corrections live on the device (``tn_adam_tick``), so the
+update can be captured in a CUDA graph behind the backward pass.  LR schedulers work unchanged: the learning
+rate is read from ``param_groups`` on every ``step()``.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+
+from ._lib import TnAdamJob, call, ptr, require_cuda
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False):
+        if amsgrad:
+            raise NotImplementedError("FusedAdam: amsgrad is not supported")
+        if not 0.0 <= lr or not 0.0 <= eps or not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0 or not 0.0 <= weight_decay:
+            raise ValueError("FusedAdam: invalid hyper-parameter")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False))
+        self._plans = {}
+
+    def _plan(self, gi: int, group):
+        """Device job table + flat moment buffers of one param group (rebuilt when a pointer moves)."""
+        ps: List[torch.Tensor] = [p for p in group["params"] if p.grad is not None]
+        if not ps:
+            return None
+        require_cuda(*ps)
+        for p in ps:
+            if p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous() or p.grad.dtype != torch.float32:
+                raise TypeError("FusedAdam needs contiguous fp32 parameters and gradients")
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+        plan = self._plans.get(gi)
+        if plan is not None and plan["key"] == key:
+            return plan
+        dev = ps[0].device
+        if plan is None or plan["ids"] != [id(p) for p in ps]:
+            total = sum(p.numel() for p in ps)
+            plan = dict(m=torch.zeros(total, device=dev), v=torch.zeros(total, device=dev), ids=[id(p) for p in ps],
+                        hyper=torch.zeros(10, device=dev), lr=None)
+            b1, b2 = group["betas"]
+            plan["hyper"].copy_(torch.tensor([group["lr"], b1, b2, group["eps"], group["weight_decay"], 0.0, 1.0, 1.0, 1.0 - b1, 1.0 - b2]))
+            plan["lr"] = group["lr"]
+            off = 0
+            for p in ps:          # expose the moments the way torch.optim.Adam does (views of the flat buffers)
+                st = self.state[p]
+                st["exp_avg"] = plan["m"][off:off + p.numel()].view_as(p)
+                st["exp_avg_sq"] = plan["v"][off:off + p.numel()].view_as(p)
+                off += p.numel()
+        jobs, off = [], 0
+        for p in ps:
+            n = p.numel()
+            jobs.append(TnAdamJob(p.data_ptr(), p.grad.data_ptr(), plan["m"].data_ptr() + 4 * off, plan["v"].data_ptr() + 4 * off, n))
+            off += n
+        arr = (TnAdamJob * len(jobs))(*jobs)
+        plan["jobs"] = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        plan["njobs"], plan["max_n"], plan["key"] = len(jobs), max(p.numel() for p in ps), key
+        self._plans[gi] = plan
+        return plan
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            plan = self._plan(gi, group)
+            if plan is None:
+                continue
+            if plan["lr"] != group["lr"]:                       # LR schedulers write param_groups[i]["lr"]
+                plan["hyper"][0:1].copy_(torch.tensor([group["lr"]]), non_blocking=True)
+                plan["lr"] = group["lr"]
+            call("tn_adam_tick", ptr(plan["hyper"]))
+            call("tn_adam_multi", ptr(plan["jobs"]), plan["njobs"], plan["max_n"], ptr(plan["hyper"]))
+        return loss
