@@ -105,7 +105,7 @@ def run_reference(args):
         "impl": "reference", "metric": "utterances/sec (TitaNet-S fwd+bwd, 3s@16kHz)", "value": round(value, 3),
         "unit": "utterances/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(dt * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, batch),
+        "config": workload_config(args, args.batch),      # our arm's workload; each CPU step is a bounded sample of it (see `sample`)
         "cpu_baseline": {"value": round(value, 3), "unit": "utterances/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 3), "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
