@@ -204,6 +204,7 @@ def test_depthwise_fused_into_gemm_operand(B, T, C, Co, K, lazy, p):
     pw_w, pw_b = torch.randn(Co, C, 1, generator=g) / math.sqrt(C), torch.randn(Co, generator=g)
     seed = torch.tensor([91], dtype=torch.int64, device="cuda")
     outs = []
+    default = ops.TC_FUSE_DWFWD
     try:
         for fused in (True, False):
             ops.TC_FUSE_DWFWD = fused
@@ -213,7 +214,7 @@ def test_depthwise_fused_into_gemm_operand(B, T, C, Co, K, lazy, p):
             torch.cuda.synchronize()
             outs.append((u.clone(), zo.clone(), stats.clone()))
     finally:
-        ops.TC_FUSE_DWFWD = True
+        ops.TC_FUSE_DWFWD = default
     assert rel(outs[0][0], outs[1][0]) < 1e-6, "u side output"
     assert rel(outs[0][1], outs[1][1]) < 1e-5, "pointwise output"
     assert rel(outs[0][2][Co:], outs[1][2][Co:]) < 1e-5, "sum of squares"

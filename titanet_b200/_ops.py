@@ -546,7 +546,10 @@ FUSE_BLOCK_ENTRY = _os.environ.get("TN_FUSE_BLOCK_ENTRY", "0") == "1"
 FUSE_SE_MLP = _os.environ.get("TN_FUSE_SE_MLP", "0") == "1"
 
 
-TC_FUSE_DWFWD = _os.environ.get("TN_FUSE_DWFWD", "1") != "0"
+# TN_FUSE_DWFWD=1: the depthwise conv as the pointwise GEMM's operand producer (tn_gemm_tc_dwfwd).  Parity-green and 1.3 us
+# faster per sub-block than tn_dw_fwd + GEMM in isolation (33.4 vs 34.7 us), but transform-bound, and on the whole graph-replayed
+# step it measures slower (10.18 vs 10.00 ms, same box), so it is opt-in until the producer keeps up with the tensor pipe.
+TC_FUSE_DWFWD = _os.environ.get("TN_FUSE_DWFWD", "0") == "1"
 
 
 def _dw_pw_forward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, relu, p, layer, B, T, stats, bn):
