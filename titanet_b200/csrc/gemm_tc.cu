@@ -785,6 +785,188 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------
+// Pair kernel: the same GEMM issued as tcgen05.mma.cta_group::2 by 2-CTA clusters.
+//
+// A pair of CTAs (one cluster) owns M = 256 output channels x 2 x BN2 rows.  CTA r holds HALF of every operand:
+// weight rows [128 r, 128 r + 128) (hi + lo) and, of each of the two BN2-row tiles, rows [r BN2/2, (r+1) BN2/2).  One
+// thread of the even ("leader") CTA issues M = 256 MMAs that read both CTAs' shared memory and write both CTAs' TMEM
+// (each CTA ends up with its 128 channels x all 2 BN2 rows).  Per SM that is 50 KB of TMA traffic per K chunk instead
+// of 84 KB (the single-CTA kernel re-streams the whole 64 KB weight chunk into every SM and is paced by the per-SM TMA
+// rate), and the 68 KB stage leaves room for three stages instead of two.
+//
+// Barriers (same offsets in both CTAs): fullA (leader's is used: both CTAs' weight loads complete_tx on it through the
+// .cta_group::2 TMA form), fullB (local: this CTA's activation rows, waited by the local transform warps), ready
+// (leader's: one arrival per transform warp of BOTH CTAs, remote arrivals through mapa), empty and accum (local,
+// signalled in both CTAs by the leader's multicast tcgen05.commit).
+// ---------------------------------------------------------------------------
+#define TC2_STAGES 3
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_leader, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_local_addr, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar_local_addr), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_GEMM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  tn_grid_dep_sync();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[5 * TC2_STAGES + 1];
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN2 = p.BN, HB = BN2 >> 1;                 // rows per N tile, rows of it held by this CTA
+  constexpr int S = TC2_STAGES;
+  const uint32_t rank = cluster_cta_rank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int n0 = pair * 2 * BN2;                        // first row of the pair's tile
+  const int m0 = blockIdx.y * 256;                      // first output channel of the pair
+  const int num_kc = p.Kd / TC_BK;
+  const uint32_t a_tile = 128 * TC_BK * 4;              // 16 KiB: this CTA's 128 weight rows
+  const uint32_t b_half = (uint32_t)HB * TC_BK * 4;     // this CTA's rows of one N tile
+  const uint32_t stage_bytes = 2 * a_tile + 4 * b_half; // A_hi | A_lo | B_hi[2] | B_lo[2]
+  auto a_hi = [&](int s) { return smem + (size_t)s * stage_bytes; };
+  auto a_lo = [&](int s) { return smem + (size_t)s * stage_bytes + a_tile; };
+  auto b_hi = [&](int s, int t) { return smem + (size_t)s * stage_bytes + 2 * a_tile + t * b_half; };
+  auto b_lo = [&](int s, int t) { return smem + (size_t)s * stage_bytes + 2 * a_tile + (2 + t) * b_half; };
+  const uint32_t fullA0 = smem_u32(&bars[0]), fullB0 = smem_u32(&bars[S]), ready0 = smem_u32(&bars[2 * S]),
+                 empty0 = smem_u32(&bars[3 * S]), accum_bar = smem_u32(&bars[4 * S]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(fullA0 + 8 * s, 1);
+      mbar_init(fullB0 + 8 * s, 1);
+      mbar_init(ready0 + 8 * s, 16);                    // 8 transform warps of each CTA
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      uint32_t fullA_leader0;                                       // the same barrier in the even (leader) CTA of the pair
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(fullA_leader0) : "r"(fullA0), "r"(0u));
+      for (int kc = 0; kc < num_kc; ++kc) {
+        const int s = kc % S;
+        if (kc >= S) mbar_wait(empty0 + 8 * s, ((kc / S) - 1) & 1);
+        const int k0 = kc * TC_BK;
+        if (leader) mbar_expect_tx(fullA0 + 8 * s, 4 * a_tile);   // both CTAs' hi + lo weight tiles
+        tma_load_2d_2sm(smem_u32(a_hi(s)), &tmA_hi, fullA_leader0 + 8 * s, k0, m0 + (int)rank * 128);
+        tma_load_2d_2sm(smem_u32(a_lo(s)), &tmA_lo, fullA_leader0 + 8 * s, k0, m0 + (int)rank * 128);
+        mbar_expect_tx(fullB0 + 8 * s, 2 * b_half);
+        tma_load_2d(smem_u32(b_hi(s, 0)), &tmB, fullB0 + 8 * s, k0, n0 + (int)rank * HB);
+        tma_load_2d(smem_u32(b_hi(s, 1)), &tmB, fullB0 + 8 * s, k0, n0 + BN2 + (int)rank * HB);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (leader && lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((256u >> 4) << 24);
+      for (int kc = 0; kc < num_kc; ++kc) {
+        const int s = kc % S;
+        const uint32_t ph = (kc / S) & 1;
+        mbar_wait(fullA0 + 8 * s, ph);
+        mbar_wait(ready0 + 8 * s, ph);
+        tc_fence_after();
+        const uint64_t dah = umma_desc_k128(smem_u32(a_hi(s))), dal = umma_desc_k128(smem_u32(a_lo(s)));
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const uint64_t dbh = umma_desc_k128(smem_u32(b_hi(s, t))), dbl = umma_desc_k128(smem_u32(b_lo(s, t)));
+          const uint32_t d = tmem_base + (uint32_t)(t * 256);
+#pragma unroll
+          for (int kk = 0; kk < TC_BK / 8; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 2);
+            const uint32_t acc = (kc > 0 || kk > 0) ? 1u : 0u;
+            tc_mma_tf32_2sm(d, dal + adv, dbh + adv, idesc, acc);
+            tc_mma_tf32_2sm(d, dah + adv, dbl + adv, idesc, 1u);
+            tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, 1u);
+          }
+        }
+        tc_commit_2sm(empty0 + 8 * s, (uint16_t)3);       // stage free in both CTAs once these MMAs have read it
+      }
+      tc_commit_2sm(accum_bar, (uint16_t)3);              // accumulators complete (both CTAs)
+    }
+  } else {
+    // ===== transform warps (hi / lo split of this CTA's activation rows), then epilogue =====
+    const int tid = threadIdx.x - 64;
+    const int n4 = 2 * HB * TC_BK / 4;                    // both N tiles are contiguous: B_hi[0] | B_hi[1]
+    for (int kc = 0; kc < num_kc; ++kc) {
+      const int s = kc % S;
+      mbar_wait(fullB0 + 8 * s, (kc / S) & 1);
+      float4* hi = reinterpret_cast<float4*>(b_hi(s, 0));
+      float4* lo = reinterpret_cast<float4*>(b_lo(s, 0));
+      for (int i = tid; i < n4; i += TC_EPI_THREADS) {
+        const float4 v = hi[i];
+        uint4 h, l;
+        h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+        l.x = rna_tf32(v.x - __uint_as_float(h.x)); l.y = rna_tf32(v.y - __uint_as_float(h.y));
+        l.z = rna_tf32(v.z - __uint_as_float(h.z)); l.w = rna_tf32(v.w - __uint_as_float(h.w));
+        reinterpret_cast<uint4*>(hi)[i] = h;
+        reinterpret_cast<uint4*>(lo)[i] = l;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(ready0 + 8 * s, 0u);     // one arrival per warp on the LEADER's barrier
+    }
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int co = m0 + (int)rank * 128 + quad * 32 + lane;
+    const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int r0 = n0 + t * BN2;
+      const int nvalid = min(BN2, p.R - r0);
+      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * 256);
+      float* zp = p.Z + (size_t)r0 * p.M_total + co;
+      if (nvalid == BN2) tc_epilogue<false, false, true>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, s1, s2, half);
+      else if (nvalid > 0) tc_epilogue<false, false, false>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, s1, s2, half);
+    }
+    if (p.stats) {
+      float* red = reinterpret_cast<float*>(smem + p.red_off);          // [2 halves][2 sums][128 channels]
+      const int chl = (int)(threadIdx.x & 127u);
+      red[(half * 2 + 0) * 128 + chl] = s1;
+      red[(half * 2 + 1) * 128 + chl] = s2;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int which = tid >> 7, ch = tid & 127;
+      atomicAdd(p.stats + (size_t)which * p.M_total + (co - chl) + ch, (double)red[which * 128 + ch] + (double)red[(2 + which) * 128 + ch]);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                                     // the peer reads this CTA's smem / signals its barriers until its MMAs drained
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+  if (p.has_bn) tn_bn_fold_last(p.bn, p.stats, p.M_total, gridDim.x * gridDim.y);
+}
+
+// ---------------------------------------------------------------------------
 // weight split: ws[0] = rna_tf32(W), ws[1] = rna_tf32(W - ws[0]); optional transpose
 // ---------------------------------------------------------------------------
 __global__ void split_tf32_kernel(const float* __restrict__ W, float* __restrict__ hi, float* __restrict__ lo, int M, int Kd, int transpose) {
@@ -1103,6 +1285,36 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   TN_REQUIRE(tn_aligned16(X) && tn_aligned16(ws), "gemm_tc: operands must be 16B aligned");
   int rc = get_encoder();
   if (rc != TN_OK) return rc;
+  static int use_pair = -1;
+  if (use_pair < 0) { const char* e = getenv("TN_TC_PAIR"); use_pair = (e && atoi(e) == 0) ? 0 : 1; }   // measured: 9.99 -> 9.48 ms per step
+  if (use_pair && p.dw_K == 0 && p.fdw_K == 0 && nsplit == 3 && M % 256 == 0 && !(p.flags & 3) && R >= 512) {
+    // cta_group::2 pair kernel: rows per pair = 2 * BN2, chosen like pick_bn (one wave of pairs, smallest tile that achieves it)
+    const int sms = tn_num_sms();
+    int best = 0; double best_cost = 1e30;
+    for (int bn2 = 256; bn2 >= 32; bn2 -= 16) {
+      const long long stage = 2ll * 128 * TC_BK * 4 + 4ll * (bn2 / 2) * TC_BK * 4;
+      if (stage * TC2_STAGES + 4096 > TC_SMEM_LIMIT) continue;
+      const long long ctas = 2 * (((long long)R + 2 * bn2 - 1) / (2 * bn2)) * (M / 256);
+      const long long waves = (ctas + sms - 1) / sms;
+      const double cost = (double)waves * (2 * bn2 + 48);
+      if (cost < best_cost) { best_cost = cost; best = bn2; }
+    }
+    if (best > 0) {
+      CUtensorMap mA_hi, mA_lo, mB;
+      if ((rc = make_map(&mA_hi, ws, M, Kd, 128)) != TN_OK) return rc;
+      if ((rc = make_map(&mA_lo, ws + (size_t)M * Kd, M, Kd, 128)) != TN_OK) return rc;
+      if ((rc = make_map(&mB, X, R, Kd, best / 2)) != TN_OK) return rc;
+      p.R = R; p.Kd = Kd; p.M_total = M; p.BN = best; p.nsplit = 3;
+      const size_t stage_bytes = 2ull * 128 * TC_BK * 4 + 4ull * (best / 2) * TC_BK * 4;
+      p.red_off = (uint32_t)(stage_bytes * TC2_STAGES);
+      const size_t smem = stage_bytes * TC2_STAGES + 2048 + 1024;
+      dim3 grid(2 * (unsigned)tn_cdiv(R, 2 * best), M / 256);
+      TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tn_launch_cluster(gemm_tc2_kernel, grid, TC_GEMM_THREADS, smem, stream, 2, mA_hi, mA_lo, mB, p);
+      TN_LAUNCH_CHECK("gemm_tc2_kernel");
+      return TN_OK;
+    }
+  }
   const int MT = (M % 256 == 0) ? 2 : 1;
   const int groups = M / (128 * MT);
   const int mult = nsplit == 3 ? 2 : 1;
