@@ -213,6 +213,10 @@ struct TcParams {
 // d dw bias) is a thread-local sum; z of the previous layer is read once, coalesced across lanes.
 // Reference: autograd of DepthwiseConv1d's first conv + BatchNorm/ReLU/Dropout
 // (src/modules.py:64-75, 128-133) as reached by loss.backward() (src/learn.py:117).
+// tcgen05.ld of 2 accumulator columns, issue only (tc_ld_wait makes the registers valid)
+__device__ __forceinline__ void tc_ld2_issue(uint32_t taddr, float* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(taddr));
+}
 // tcgen05.ld of 4 accumulator columns, issue only (tc_ld_wait makes the registers valid)
 __device__ __forceinline__ void tc_ld4_issue(uint32_t taddr, float* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
@@ -227,7 +231,11 @@ __device__ __forceinline__ void tc_ld4_issue(uint32_t taddr, float* v) {
 // outputs.  The two warps of a lane quadrant own the two halves of the tile's rows.
 template <int K>
 __device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams& p, const TnAct& act, int c, int n0, int half,
-                                                  const uint8_t* zs, float* red) {
+                                                  const uint8_t* zs, float* red, int bn2 = 0x7fffffff, const uint8_t* zs2 = nullptr) {
+  // Tile geometry.  Single-CTA kernel: tile column j is TMEM column tbase + j and z row j of `zs`.  Pair kernel
+  // (cta_group::2): the tile is two N tiles of bn2 columns; columns >= bn2 live at TMEM column 256 + (j - bn2) and in
+  // the second z box `zs2`.  All accesses below are in aligned pairs / single rows, so they never straddle the seam.
+  auto tcol = [&](int j) -> uint32_t { return tbase + (uint32_t)(j >= bn2 ? j - bn2 + 256 : j); };
   constexpr int PAD = K / 2;
   constexpr int WW = 4 + 2 * PAD;                    // window: tile columns o .. o + 3 + 2 PAD for outputs o .. o + 3
   const int C = p.M_total, T = p.dw_T, R = p.R;
@@ -256,8 +264,10 @@ __device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams
   // enough bytes in flight: eight warps x 4 B left the epilogue latency-bound at ~8 GB/s per SM.)
   const uint32_t lane = threadIdx.x & 31;
   auto load_zt = [&](int j) -> float {
-    const uint32_t off = (uint32_t)j * 128u + ((((lane >> 2) ^ ((uint32_t)j & 7u)) << 4) | ((lane & 3u) << 2));
-    return *reinterpret_cast<const float*>(zs + off);
+    const uint8_t* base = j >= bn2 ? zs2 : zs;
+    const uint32_t jr = (uint32_t)(j >= bn2 ? j - bn2 : j);
+    const uint32_t off = jr * 128u + ((((lane >> 2) ^ (jr & 7u)) << 4) | ((lane & 3u) << 2));
+    return *reinterpret_cast<const float*>(base + off);
   };
   // activation of window row `row` from its z (0 for rows outside the tensor); m = d a / d pre
   auto actf = [&](float zv, int row, float& m) -> float {
@@ -275,8 +285,10 @@ __device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams
   float g[WW], a[WW], zc[PAD + 4], mc[PAD + 4];
   // prime window positions [0, 2 PAD)
   if (PAD > 0) {
-    float tmp[16];
-    tc_ld16(tbase + oa, tmp);
+    float tmp[2 * PAD + 1];
+#pragma unroll
+    for (int jj = 0; jj < PAD; ++jj) tc_ld2_issue(tcol(oa + 2 * jj), tmp + 2 * jj);
+    tc_ld_wait(tmp, 2 * PAD);
 #pragma unroll
     for (int j = 0; j < 2 * PAD; ++j) {
       const int row = n0 + oa + j;
@@ -289,14 +301,18 @@ __device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams
   }
   float gq[4];
   if (tr) tr[1] = clock64();
-  tc_ld4_issue(tbase + oa + 2 * PAD, gq);
+  tc_ld2_issue(tcol(oa + 2 * PAD), gq);
+  tc_ld2_issue(tcol(oa + 2 * PAD + 2), gq + 2);
   int t0 = (r_first + oa) % T;
 #pragma unroll 1
   for (int o = oa; o < ob; o += 4) {
     tc_ld_wait(gq, 4);
 #pragma unroll
     for (int i = 0; i < 4; ++i) g[2 * PAD + i] = gq[i];
-    if (o + 4 < ob) tc_ld4_issue(tbase + o + 4 + 2 * PAD, gq);       // warp-uniform
+    if (o + 4 < ob) {                                                 // warp-uniform
+      tc_ld2_issue(tcol(o + 4 + 2 * PAD), gq);
+      tc_ld2_issue(tcol(o + 6 + 2 * PAD), gq + 2);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float m;
@@ -820,12 +836,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_local_addr, uin
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
+template <int MODE>      // 0: plain epilogue (+ statistics / BatchNorm fold), 1: fused depthwise-backward epilogue
 __global__ void __launch_bounds__(TC_GEMM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                const __grid_constant__ CUtensorMap tmB, TcParams p) {
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ, TcParams p) {
   tn_grid_dep_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[5 * TC2_STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[5 * TC2_STAGES + 1 + TC2_STAGES];
   __shared__ uint32_t tmem_base_slot;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -834,7 +851,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const uint32_t rank = cluster_cta_rank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
-  const int n0 = pair * 2 * BN2;                        // first row of the pair's tile
+  // first row of the pair's tile; fused depthwise backward: BNo output rows per pair, the tile starts PAD rows early
+  const int n0 = MODE == 1 ? pair * p.BNo - (p.dw_K >> 1) : pair * 2 * BN2;
   const int m0 = blockIdx.y * 256;                      // first output channel of the pair
   const int num_kc = p.Kd / TC_BK;
   const uint32_t a_tile = 128 * TC_BK * 4;              // 16 KiB: this CTA's 128 weight rows
@@ -845,7 +863,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   auto b_hi = [&](int s, int t) { return smem + (size_t)s * stage_bytes + 2 * a_tile + t * b_half; };
   auto b_lo = [&](int s, int t) { return smem + (size_t)s * stage_bytes + 2 * a_tile + (2 + t) * b_half; };
   const uint32_t fullA0 = smem_u32(&bars[0]), fullB0 = smem_u32(&bars[S]), ready0 = smem_u32(&bars[2 * S]),
-                 empty0 = smem_u32(&bars[3 * S]), accum_bar = smem_u32(&bars[4 * S]);
+                 empty0 = smem_u32(&bars[3 * S]), accum_bar = smem_u32(&bars[4 * S]), zbar0 = smem_u32(&bars[4 * S + 1]);
+  // fused depthwise backward: the z tile of this CTA's 128 channels = 8 boxes [BN2 rows x 32 channels] (box b = 2 * channel
+  // block + N tile), loaded into pipeline stages in the order the mainloop releases them: `zcap` boxes per stage, group g
+  // of boxes -> stage (num_kc - S + g) % S, one barrier per group
+  const uint32_t z_box = (uint32_t)BN2 * 128u;
+  const int zcap = (int)(stage_bytes / z_box);
+  auto z_stage = [&](int g) { return num_kc >= S ? (num_kc - S + g) % S : g; };
+  auto z_ptr = [&](int b) { return smem + (size_t)z_stage(b / zcap) * stage_bytes + (size_t)(b % zcap) * z_box; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -855,6 +880,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       mbar_init(empty0 + 8 * s, 1);
     }
     mbar_init(accum_bar, 1);
+    for (int g = 0; g < S; ++g) mbar_init(zbar0 + 8 * g, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -881,6 +907,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         mbar_expect_tx(fullB0 + 8 * s, 2 * b_half);
         tma_load_2d(smem_u32(b_hi(s, 0)), &tmB, fullB0 + 8 * s, k0, n0 + (int)rank * HB);
         tma_load_2d(smem_u32(b_hi(s, 1)), &tmB, fullB0 + 8 * s, k0, n0 + BN2 + (int)rank * HB);
+      }
+      if (MODE == 1) {
+        // z boxes of the previous layer for the fused epilogue, group by group as the tensor core releases the stages
+        // (this CTA's `empty` barriers are signalled by the leader's multicast commit)
+        const int ngroups = (8 + zcap - 1) / zcap;
+        for (int g = 0; g < ngroups; ++g) {
+          if (num_kc >= S) {
+            const int st = z_stage(g);
+            const int kc_last = ((num_kc - 1 - st) / S) * S + st;
+            mbar_wait(empty0 + 8 * st, (uint32_t)(kc_last / S) & 1u);
+          } else if (g == 0) {
+            for (int st = 0; st < num_kc; ++st) mbar_wait(empty0 + 8 * st, 0u);
+          }
+          const int b0 = g * zcap, b1 = min(8, b0 + zcap);
+          mbar_expect_tx(zbar0 + 8 * g, (uint32_t)(b1 - b0) * z_box);
+          for (int b = b0; b < b1; ++b)
+            tma_load_2d(smem_u32(z_ptr(b)), &tmZ, zbar0 + 8 * g, m0 + (int)rank * 128 + (b >> 1) * 32, n0 + (b & 1) * BN2);
+        }
       }
     }
   } else if (warp == 1) {
@@ -937,6 +981,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     tc_fence_after();
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int co = m0 + (int)rank * 128 + quad * 32 + lane;
+    if (MODE == 1) {
+      const TnAct act = tn_act_init(p.act);
+      const int ba = 2 * quad, bb = 2 * quad + 1;                      // this channel block's two z boxes
+      mbar_wait(zbar0 + 8 * (ba / zcap), 0);
+      mbar_wait(zbar0 + 8 * (bb / zcap), 0);
+      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16);
+      float* red = reinterpret_cast<float*>(smem + p.red_off);
+      switch (p.dw_K) {
+        case 1: tc_epilogue_dwbwd<1>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb)); break;
+        case 3: tc_epilogue_dwbwd<3>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb)); break;
+        case 5: tc_epilogue_dwbwd<5>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb)); break;
+        case 7: tc_epilogue_dwbwd<7>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb)); break;
+        case 9: tc_epilogue_dwbwd<9>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb)); break;
+        default: tc_epilogue_dwbwd<11>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb)); break;
+      }
+    } else {
     const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -956,6 +1016,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int which = tid >> 7, ch = tid & 127;
       atomicAdd(p.stats + (size_t)which * p.M_total + (co - chl) + ch, (double)red[which * 128 + ch] + (double)red[(2 + which) * 128 + ch]);
+    }
     }
   }
   tc_fence_before();
@@ -1287,14 +1348,23 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   if (rc != TN_OK) return rc;
   static int use_pair = -1;
   if (use_pair < 0) { const char* e = getenv("TN_TC_PAIR"); use_pair = (e && atoi(e) == 0) ? 0 : 1; }   // measured: 9.99 -> 9.48 ms per step
-  if (use_pair && p.dw_K == 0 && p.fdw_K == 0 && nsplit == 3 && M % 256 == 0 && !(p.flags & 3) && R >= 512) {
-    // cta_group::2 pair kernel: rows per pair = 2 * BN2, chosen like pick_bn (one wave of pairs, smallest tile that achieves it)
+  static int use_pair_dw = -1;
+  if (use_pair_dw < 0) { const char* e = getenv("TN_TC_PAIR_DW"); use_pair_dw = (e && atoi(e) == 0) ? 0 : 1; }
+  if (use_pair && (p.dw_K == 0 || use_pair_dw) && p.fdw_K == 0 && nsplit == 3 && M % 256 == 0 && !(p.flags & 3) && R >= 512) {
+    // cta_group::2 pair kernel: rows per pair = 2 * BN2 (minus the halo of the fused depthwise backward), chosen like pick_bn
+    // (one wave of pairs, smallest tile that achieves it)
     const int sms = tn_num_sms();
+    const int halo2 = p.dw_K > 1 ? 16 : 0;
+    const int red2 = p.dw_K > 0 ? (2 * 128 * (p.dw_K + 3) * 4 + 1023) / 1024 * 1024 : 2048;
     int best = 0; double best_cost = 1e30;
     for (int bn2 = 256; bn2 >= 32; bn2 -= 16) {
       const long long stage = 2ll * 128 * TC_BK * 4 + 4ll * (bn2 / 2) * TC_BK * 4;
-      if (stage * TC2_STAGES + 4096 > TC_SMEM_LIMIT) continue;
-      const long long ctas = 2 * (((long long)R + 2 * bn2 - 1) / (2 * bn2)) * (M / 256);
+      if (stage * TC2_STAGES + red2 + 2048 > TC_SMEM_LIMIT) continue;
+      if (p.dw_K > 0) {                                  // the 8 z boxes must fit the released stages
+        const long long cap = stage / ((long long)bn2 * 128);
+        if (cap < 1 || (8 + cap - 1) / cap > TC2_STAGES) continue;
+      }
+      const long long ctas = 2 * (((long long)R + (2 * bn2 - halo2) - 1) / (2 * bn2 - halo2)) * (M / 256);
       const long long waves = (ctas + sms - 1) / sms;
       const double cost = (double)waves * (2 * bn2 + 48);
       if (cost < best_cost) { best_cost = cost; best = bn2; }
@@ -1304,13 +1374,20 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
       if ((rc = make_map(&mA_hi, ws, M, Kd, 128)) != TN_OK) return rc;
       if ((rc = make_map(&mA_lo, ws + (size_t)M * Kd, M, Kd, 128)) != TN_OK) return rc;
       if ((rc = make_map(&mB, X, R, Kd, best / 2)) != TN_OK) return rc;
-      p.R = R; p.Kd = Kd; p.M_total = M; p.BN = best; p.nsplit = 3;
+      CUtensorMap mZ = mB;
+      if (p.dw_K > 0 && (rc = make_map(&mZ, p.zprev, R, M, best, 32)) != TN_OK) return rc;
+      p.R = R; p.Kd = Kd; p.M_total = M; p.BN = best; p.BNo = 2 * best - halo2; p.nsplit = 3;
       const size_t stage_bytes = 2ull * 128 * TC_BK * 4 + 4ull * (best / 2) * TC_BK * 4;
       p.red_off = (uint32_t)(stage_bytes * TC2_STAGES);
-      const size_t smem = stage_bytes * TC2_STAGES + 2048 + 1024;
-      dim3 grid(2 * (unsigned)tn_cdiv(R, 2 * best), M / 256);
-      TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      tn_launch_cluster(gemm_tc2_kernel, grid, TC_GEMM_THREADS, smem, stream, 2, mA_hi, mA_lo, mB, p);
+      const size_t smem = stage_bytes * TC2_STAGES + red2 + 1024;
+      dim3 grid(2 * (unsigned)tn_cdiv(R, p.BNo), M / 256);
+      if (p.dw_K > 0) {
+        TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tn_launch_cluster(gemm_tc2_kernel<1>, grid, TC_GEMM_THREADS, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
+      } else {
+        TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tn_launch_cluster(gemm_tc2_kernel<0>, grid, TC_GEMM_THREADS, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
+      }
       TN_LAUNCH_CHECK("gemm_tc2_kernel");
       return TN_OK;
     }
