@@ -1180,17 +1180,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(accum_bar, 0);
       tc_fence_after();
       const int quad = warp & 3;
+      // Epilogue through shared memory (the pipeline stages are free now): TMEM hands each thread one output channel
+      // (row of dW), so a direct red.global.add.v4 would touch 32 different 128-byte lines per warp instruction; staged,
+      // each warp instruction adds 512 contiguous bytes of one row.  Rows are padded to NB + 4 floats (conflict-free).
+      float* stg = reinterpret_cast<float*>(smem) + (size_t)(quad * 32) * (NB + 4);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const int co = co0 + mt * 128 + quad * 32 + lane;
-        float* row = p.dW + (size_t)co * p.Ci + ci0;
         for (int c0 = 0; c0 < NB; c0 += 16) {
           float v[16];
           tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 256 + c0), v);
+          float4* dst = reinterpret_cast<float4*>(stg + (size_t)lane * (NB + 4) + c0);
 #pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(row + c0 + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+          for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
+        __syncwarp();                                 // each warp stages and drains its own 32 rows
+        for (int r = 0; r < 32; ++r) {
+          float* grow = p.dW + (size_t)(co0 + mt * 128 + quad * 32 + r) * p.Ci + ci0;
+          for (int c = 4 * lane; c < NB; c += 128) {
+            const float4 x = *reinterpret_cast<const float4*>(stg + (size_t)r * (NB + 4) + c);
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(grow + c), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+          }
+        }
+        __syncwarp();
       }
     }
   }
@@ -1198,6 +1209,110 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// Pair (cta_group::2) variant of the weight-gradient kernel: a 2-CTA cluster reduces a row range into a [256, NB2] tile.
+// CTA r loads dZ[rows, 128 r .. 128 r + 128) and U[rows, r NB2/2 .. (r+1) NB2/2): 32 KB per 32-row chunk for a 256 x 256
+// tile, where the single-CTA kernel spends 32 KB per 128 x 128 tile -- half the TMA bytes per SM, which is what paces it.
+// Each CTA ends with its 128 output channels x NB2 columns in TMEM; eight epilogue warps add them to dW (red.global.add.v4).
+__global__ void __launch_bounds__(TC_GEMM_THREADS, 1)
+wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, WgParams p) {
+  tn_grid_dep_sync();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 1];
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages, NB2 = p.NB, HN = NB2 >> 1;
+  const uint32_t rank = cluster_cta_rank();
+  const bool leader = rank == 0;
+  const int co0 = blockIdx.z * 256 + (int)rank * 128;     // this CTA's output channels
+  const int ci0 = blockIdx.y * NB2;                        // the pair's input-channel block
+  const int split = blockIdx.x >> 1;                       // gridDim.x = 2 * splits: the cluster spans x
+  const int ra = split * p.rows_per_split;
+  const int rb = min(p.R, ra + p.rows_per_split);
+  const int num_kc = (rb - ra + WG_BK - 1) / WG_BK;
+  const uint32_t slab = WG_BK * 128;
+  const uint32_t a_bytes = 4 * slab, b_bytes = (uint32_t)(HN / 32) * slab;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_MAX_STAGES]), accum_bar = smem_u32(&bars[2 * TC_MAX_STAGES]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (num_kc > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        uint32_t full_leader0;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(full_leader0) : "r"(full0), "r"(0u));
+        for (int kc = 0; kc < num_kc; ++kc) {
+          const int s = kc % S;
+          if (kc >= S) mbar_wait(empty0 + 8 * s, ((kc / S) - 1) & 1);
+          if (leader) mbar_expect_tx(full0 + 8 * s, 2 * stage_bytes);      // both CTAs' tiles
+          const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+          asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                       ::"r"(base), "l"(&tmA), "r"(full_leader0 + 8 * s), "r"(0), "r"(ra + kc * WG_BK), "r"(co0 / 32) : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                       ::"r"(base + a_bytes), "l"(&tmB), "r"(full_leader0 + 8 * s), "r"(0), "r"(ra + kc * WG_BK), "r"((ci0 + (int)rank * HN) / 32) : "memory");
+        }
+      }
+    } else if (warp == 1) {
+      if (leader && lane == 0) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NB2 >> 3) << 17) | ((256u >> 4) << 24);
+        for (int kc = 0; kc < num_kc; ++kc) {
+          const int s = kc % S;
+          mbar_wait(full0 + 8 * s, (kc / S) & 1);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+#pragma unroll
+          for (int k8 = 0; k8 < WG_BK / 8; ++k8) {
+            const uint64_t da = umma_desc_mn128(base + k8 * 1024, slab);
+            const uint64_t db = umma_desc_mn128(base + a_bytes + k8 * 1024, slab);
+            tc_mma_tf32_2sm(tmem_base, da, db, idesc, (kc > 0 || k8 > 0) ? 1u : 0u);
+          }
+          tc_commit_2sm(empty0 + 8 * s, (uint16_t)3);
+        }
+        tc_commit_2sm(accum_bar, (uint16_t)3);
+      }
+    } else {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+      const int quad = warp & 3, half = (warp - 2) >> 2;
+      // staged through the (free) pipeline memory so that every red.global.add.v4 instruction covers 512 contiguous bytes
+      float* stg = reinterpret_cast<float*>(smem) + (size_t)(quad * 32) * (NB2 + 4);
+      for (int c0 = 16 * half; c0 < NB2; c0 += 32) {       // the two warps of a lane quadrant alternate 16-column groups
+        float v[16];
+        tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+        float4* dst = reinterpret_cast<float4*>(stg + (size_t)lane * (NB2 + 4) + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int r = half; r < 32; r += 2) {
+        float* grow = p.dW + (size_t)(co0 + quad * 32 + r) * p.Ci + ci0;
+        for (int c = 4 * lane; c < NB2; c += 128) {
+          const float4 x = *reinterpret_cast<const float4*>(stg + (size_t)r * (NB2 + 4) + c);
+          asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(grow + c), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -1224,10 +1339,46 @@ extern "C" int tn_wgrad_tc(const float* dZ, const float* U, float* dW, int R, in
   TN_REQUIRE(tn_aligned16(dZ) && tn_aligned16(U) && tn_aligned16(dW), "wgrad_tc: operands must be 16B aligned");
   int rc = get_encoder();
   if (rc != TN_OK) return rc;
+  static int wg_pair = -1;
+  if (wg_pair < 0) { const char* e = getenv("TN_WG_PAIR"); wg_pair = (e && atoi(e) != 0) ? 1 : 0; }   // measured slower (16.1 vs 14.5 us): opt-in
+  if (wg_pair && Co % 256 == 0 && Ci % 64 == 0 && R >= 1024) {
+    int NB2 = 256;
+    if (const char* e = getenv("TN_WG_NB2")) NB2 = atoi(e) >= 64 ? atoi(e) : NB2;     // tuning knob
+    while (Ci % NB2 != 0) NB2 -= 64;                 // largest multiple of 64 <= 256 that divides Ci
+    const int co_groups = Co / 256, ci_blocks = Ci / NB2;
+    const size_t stage_bytes2 = (size_t)WG_BK * 128 * (4 + NB2 / 64);
+    int stages2 = (int)((TC_SMEM_LIMIT - 2048) / stage_bytes2);
+    if (stages2 > TC_MAX_STAGES) stages2 = TC_MAX_STAGES;
+    const long long chunks = ((long long)R + WG_BK - 1) / WG_BK;
+    long long want = (tn_num_sms() / 2) / (co_groups * ci_blocks);
+    if (want < 1) want = 1;
+    if (want > chunks) want = chunks;
+    const long long cps = (chunks + want - 1) / want;
+    const int splits = (int)((chunks + cps - 1) / cps);
+    if (stages2 >= 2 && co_groups <= 65535) {
+      CUtensorMap mA, mB;
+      if ((rc = make_map_mn(&mA, dZ, R, Co, 4)) != TN_OK) return rc;
+      if ((rc = make_map_mn(&mB, U, R, Ci, NB2 / 64)) != TN_OK) return rc;
+      WgParams p;
+      p.dW = dW; p.R = R; p.Co = Co; p.Ci = Ci; p.NB = NB2; p.stages = stages2; p.rows_per_split = (int)cps * WG_BK;
+      int cols = 32;
+      while (cols < NB2) cols <<= 1;
+      p.tmem_cols = cols;
+      const size_t smem = stage_bytes2 * stages2 + 1024;
+      // CTAs (2 s, y, z) and (2 s + 1, y, z) form the pair of row split s
+      dim3 grid(2 * splits, ci_blocks, co_groups);
+      TN_CUDA(cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tn_launch_cluster(wgrad_tc2_kernel, grid, TC_GEMM_THREADS, smem, stream, 2, mA, mB, p);
+      TN_LAUNCH_CHECK("wgrad_tc2_kernel");
+      return TN_OK;
+    }
+  }
   // 128 x 128 output tiles: the epilogue (TMEM -> red.global) is a fixed cost per CTA, so small tiles with long
   // row ranges win over 256 x 256 tiles with short ones (measured 14.6 us vs 25.8 us at R=19264, 256 x 256)
+  // (with the epilogue staged through shared memory, 128 x 256 tiles measure best: 12.9 us against 15.3 us for 128 x 128
+  //  and 19.6 us for 256 x 256 at R=19264, 256 x 256; the pair kernel above reaches 12.8 us)
   int MT = 1;
-  int NB = 128;
+  int NB = 256;
   if (const char* e = getenv("TN_WG_MT")) MT = (atoi(e) == 1 || Co % 256 != 0) ? 1 : 2;      // tuning knobs
   if (const char* e = getenv("TN_WG_NB")) NB = atoi(e) >= 32 ? atoi(e) : NB;
   while (Ci % NB != 0) NB -= 32;                     // largest multiple of 32 <= 256 that divides Ci
@@ -1237,6 +1388,7 @@ extern "C" int tn_wgrad_tc(const float* dZ, const float* U, float* dW, int R, in
   int stages = (int)((TC_SMEM_LIMIT - 2048) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   TN_REQUIRE(stages >= 2, "wgrad_tc: tile does not fit shared memory");
+  TN_REQUIRE(stage_bytes * stages >= (size_t)128 * (NB + 4) * 4, "wgrad_tc: epilogue staging does not fit the pipeline memory");
   long long chunks = ((long long)R + WG_BK - 1) / WG_BK;
   long long want = tn_num_sms() / (co_groups * ci_blocks);
   if (want < 1) want = 1;
