@@ -304,7 +304,7 @@ __device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams
   tc_ld2_issue(tcol(oa + 2 * PAD), gq);
   tc_ld2_issue(tcol(oa + 2 * PAD + 2), gq + 2);
   int t0 = (r_first + oa) % T;
-#pragma unroll 1
+#pragma unroll 2
   for (int o = oa; o < ob; o += 4) {
     tc_ld_wait(gq, 4);
 #pragma unroll
