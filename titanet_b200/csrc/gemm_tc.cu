@@ -231,7 +231,10 @@ __device__ __forceinline__ void tc_ld4_issue(uint32_t taddr, float* v) {
 // outputs.  The two warps of a lane quadrant own the two halves of the tile's rows.
 template <int K>
 __device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams& p, const TnAct& act, int c, int n0, int half,
-                                                  const uint8_t* zs, float* red, int bn2 = 0x7fffffff, const uint8_t* zs2 = nullptr) {
+                                                  const uint8_t* zs, float* red, int bn2 = 0x7fffffff, const uint8_t* zs2 = nullptr,
+                                                  int nparts = 2, int nthreads = 256) {
+  // `half` = which of the `nparts` warps of this lane quadrant (each owns a contiguous range of the tile's output rows);
+  // `nthreads` = epilogue threads of the CTA (named barrier 1, cooperative atomics)
   // Tile geometry.  Single-CTA kernel: tile column j is TMEM column tbase + j and z row j of `zs`.  Pair kernel
   // (cta_group::2): the tile is two N tiles of bn2 columns; columns >= bn2 live at TMEM column 256 + (j - bn2) and in
   // the second z box `zs2`.  All accesses below are in aligned pairs / single rows, so they never straddle the seam.
@@ -250,9 +253,9 @@ __device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams
   float a_sc = 0.f, a_sh = 0.f, a_b = 0.f;
   const int r_first = n0 + PAD;                      // global row of output 0 (tile column j <-> global row n0 + j)
   const int nout = min(p.BNo, R - r_first);
-  const int hsplit = p.BNo >> 1;                     // BNo is a multiple of 16
-  const int oa = half ? hsplit : 0;
-  const int ob = min(half ? p.BNo : hsplit, nout);   // this warp's outputs: [oa, ob)
+  const int hsplit = ((p.BNo + nparts - 1) / nparts + 7) & ~7;   // rows per part, a multiple of 8 (BNo is a multiple of 16)
+  const int oa = half * hsplit;
+  const int ob = min(min((half + 1) * hsplit, p.BNo), nout);     // this warp's outputs: [oa, ob)
   const bool traced = p.trace && threadIdx.x == 64 && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2);
   long long* tr = traced ? p.trace + (blockIdx.x == 0 ? 0 : 128) + 113 + (c >= 128 ? 4 : 0) : nullptr;
   if (tr) tr[0] = clock64();
@@ -391,21 +394,26 @@ __device__ __forceinline__ void tc_epilogue_dwbwd(uint32_t tbase, const TcParams
 #pragma unroll
   for (int k = 0; k < K; ++k) mine[k] = a_w[k];
   mine[K] = a_b; mine[K + 1] = a_sc; mine[K + 2] = a_sh;
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
   const int tid = (int)threadIdx.x - 64;
   const int cbase = c - chl;
-  for (int L = tid; L < 128 * K; L += 256) {
+  auto rsum = [&](int ch, int f) -> float {
+    float v = red[ch * F + f];
+    for (int pp = 1; pp < nparts; ++pp) v += red[(pp * 128 + ch) * F + f];
+    return v;
+  };
+  for (int L = tid; L < 128 * K; L += nthreads) {
     const int ch = L / K, k = L - ch * K;
-    atomicAdd(p.g_dw + (size_t)cbase * K + L, red[ch * F + k] + red[(128 + ch) * F + k]);
+    atomicAdd(p.g_dw + (size_t)cbase * K + L, rsum(ch, k));
   }
   if (tid < 128) {
-    if (p.g_db) atomicAdd(p.g_db + cbase + tid, red[tid * F + K] + red[(128 + tid) * F + K]);
-  } else if (lazy) {
+    if (p.g_db) atomicAdd(p.g_db + cbase + tid, rsum(tid, K));
+  } else if (lazy && tid < 256) {
     const int ch = tid - 128;
-    atomicAdd(p.g_dscale + cbase + ch, red[ch * F + K + 1] + red[(128 + ch) * F + K + 1]);
-    atomicAdd(p.g_dshift + cbase + ch, red[ch * F + K + 2] + red[(128 + ch) * F + K + 2]);
+    atomicAdd(p.g_dscale + cbase + ch, rsum(ch, K + 1));
+    atomicAdd(p.g_dshift + cbase + ch, rsum(ch, K + 2));
   }
-  asm volatile("bar.sync 1, 256;" ::: "memory");          // `red` is reused by the next channel half
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");   // `red` is reused by the next channel half
   if (tr) tr[3] = clock64();
 }
 
@@ -836,8 +844,10 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_local_addr, uin
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-template <int MODE>      // 0: plain epilogue (+ statistics / BatchNorm fold), 1: fused depthwise-backward epilogue
-__global__ void __launch_bounds__(TC_GEMM_THREADS, 1)
+// MODE 0: plain epilogue (+ statistics / BatchNorm fold), 1: fused depthwise-backward epilogue.  EW = transform / epilogue
+// warps (8, or 12 for the fused backward with K <= 3: its epilogue is issue-bound with two warps per scheduler).
+template <int MODE, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ, TcParams p) {
   tn_grid_dep_sync();
@@ -876,7 +886,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     for (int s = 0; s < S; ++s) {
       mbar_init(fullA0 + 8 * s, 1);
       mbar_init(fullB0 + 8 * s, 1);
-      mbar_init(ready0 + 8 * s, 16);                    // 8 transform warps of each CTA
+      mbar_init(ready0 + 8 * s, 2 * EW);                // the transform warps of both CTAs
       mbar_init(empty0 + 8 * s, 1);
     }
     mbar_init(accum_bar, 1);
@@ -964,7 +974,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       mbar_wait(fullB0 + 8 * s, (kc / S) & 1);
       float4* hi = reinterpret_cast<float4*>(b_hi(s, 0));
       float4* lo = reinterpret_cast<float4*>(b_lo(s, 0));
-      for (int i = tid; i < n4; i += TC_EPI_THREADS) {
+      for (int i = tid; i < n4; i += 32 * EW) {
         const float4 v = hi[i];
         uint4 h, l;
         h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
@@ -988,13 +998,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       mbar_wait(zbar0 + 8 * (bb / zcap), 0);
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16);
       float* red = reinterpret_cast<float*>(smem + p.red_off);
-      switch (p.dw_K) {
-        case 1: tc_epilogue_dwbwd<1>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb)); break;
-        case 3: tc_epilogue_dwbwd<3>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb)); break;
-        case 5: tc_epilogue_dwbwd<5>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb)); break;
-        case 7: tc_epilogue_dwbwd<7>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb)); break;
-        case 9: tc_epilogue_dwbwd<9>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb)); break;
-        default: tc_epilogue_dwbwd<11>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb)); break;
+      constexpr int NP = EW / 4, NT = 32 * EW;
+      if (EW > 8) {                                           // 128-register budget: narrow windows only (host: K <= 3)
+        if (p.dw_K == 1) tc_epilogue_dwbwd<1>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT);
+        else tc_epilogue_dwbwd<3>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT);
+      } else switch (p.dw_K) {
+        case 1: tc_epilogue_dwbwd<1>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT); break;
+        case 3: tc_epilogue_dwbwd<3>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT); break;
+        case 5: tc_epilogue_dwbwd<5>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT); break;
+        case 7: tc_epilogue_dwbwd<7>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT); break;
+        case 9: tc_epilogue_dwbwd<9>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT); break;
+        default: tc_epilogue_dwbwd<11>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT); break;
       }
     } else {
     const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
@@ -1507,7 +1521,15 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
     // (one wave of pairs, smallest tile that achieves it)
     const int sms = tn_num_sms();
     const int halo2 = p.dw_K > 1 ? 16 : 0;
-    const int red2 = p.dw_K > 0 ? (2 * 128 * (p.dw_K + 3) * 4 + 1023) / 1024 * 1024 : 2048;
+    static int ew_sel = -1;                                    // epilogue warps of the fused backward for K <= 3: 8, 12 or 16
+    if (ew_sel < 0) {                                          // measured at R=19264, 256x256, K=3: 34.4 / 32.1 / 31.5 us
+      const char* e = getenv("TN_TC_EW");
+      const int v = e ? atoi(e) : 16;
+      ew_sel = (v == 8 || v == 12) ? v : 16;
+    }
+    const int ew = (p.dw_K > 0 && p.dw_K <= 3) ? ew_sel : 8;
+    const bool wide = ew > 8;
+    const int red2 = p.dw_K > 0 ? ((ew / 4) * 128 * (p.dw_K + 3) * 4 + 1023) / 1024 * 1024 : 2048;
     int best = 0; double best_cost = 1e30;
     for (int bn2 = 256; bn2 >= 32; bn2 -= 16) {
       const long long stage = 2ll * 128 * TC_BK * 4 + 4ll * (bn2 / 2) * TC_BK * 4;
@@ -1533,12 +1555,18 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
       p.red_off = (uint32_t)(stage_bytes * TC2_STAGES);
       const size_t smem = stage_bytes * TC2_STAGES + red2 + 1024;
       dim3 grid(2 * (unsigned)tn_cdiv(R, p.BNo), M / 256);
-      if (p.dw_K > 0) {
-        TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tn_launch_cluster(gemm_tc2_kernel<1>, grid, TC_GEMM_THREADS, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
+      if (wide && ew == 16) {
+        TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tn_launch_cluster(gemm_tc2_kernel<1, 16>, grid, 64 + 32 * 16, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
+      } else if (wide) {
+        TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tn_launch_cluster(gemm_tc2_kernel<1, 12>, grid, 64 + 32 * 12, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
+      } else if (p.dw_K > 0) {
+        TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tn_launch_cluster(gemm_tc2_kernel<1, 8>, grid, TC_GEMM_THREADS, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
       } else {
-        TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tn_launch_cluster(gemm_tc2_kernel<0>, grid, TC_GEMM_THREADS, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
+        TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tn_launch_cluster(gemm_tc2_kernel<0, 8>, grid, TC_GEMM_THREADS, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
       }
       TN_LAUNCH_CHECK("gemm_tc2_kernel");
       return TN_OK;
