@@ -147,8 +147,8 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
 // Rows >= nvalid (tail tile) are masked by predication, not branches.
 template <bool TANH, bool ACCUM, bool FULL>
 __device__ __forceinline__ void tc_epilogue(uint32_t tbase, float* __restrict__ zp, size_t ld, int BN, int nvalid, float bv,
-                                            float& s1, float& s2, int half) {
-  for (int c0 = 32 * half; c0 < BN; c0 += 64) {      // the two warps of a lane quadrant alternate 32-column chunks
+                                            float& s1, float& s2, int half, int nparts = 2) {
+  for (int c0 = 32 * half; c0 < BN; c0 += 32 * nparts) {   // the `nparts` warps of a lane quadrant alternate 32-column chunks
     float v[32];
     const bool two = c0 + 16 < BN;                   // BN is a multiple of 16
     tc_ld16_issue(tbase + c0, v);
@@ -844,15 +844,131 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_local_addr, uin
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-// MODE 0: plain epilogue (+ statistics / BatchNorm fold), 1: fused depthwise-backward epilogue.  EW = transform / epilogue
-// warps (8, or 12 for the fused backward with K <= 3: its epilogue is issue-bound with two warps per scheduler).
+// Fused depthwise-forward operand producer of the pair kernel (MODE 2, 16 transform warps = 512 threads): like
+// tc_dw_mainloop, but this CTA holds HB = BN2/2 rows of each of the two N tiles.  Per K chunk TMA delivers, per tile, the raw z
+// rows [first row - PAD, + HB + 8) into the B_hi buffer; thread (q = channel quad, tile t, row lane 0..31) owns RP consecutive
+// rows of tile t.  Same two phases (window to registers | barrier | BN/ReLU/dropout, FIR, u side output, hi/lo split in place).
+template <int K, int RP>
+__device__ __forceinline__ void tc2_dw_mainloop(const TcParams& p, uint8_t* smem, uint32_t stage_bytes, uint32_t bh_off, uint32_t bh_tile,
+                                                uint32_t bl_off, uint32_t bl_tile, uint32_t fullB0, uint32_t ready0, int num_kc,
+                                                int row_base, int BN2, int HB, const float* par, int tid, int lane) {
+  constexpr int PAD = K / 2;
+  constexpr int W = RP + 2 * PAD;
+  constexpr int S = TC2_STAGES;
+  const TnAct act = tn_act_init(p.act);
+  const int C = p.Kd, T = p.fdw_T, R = p.R;
+  const bool lazy = act.scale != nullptr;
+  const bool drop = act.thresh != 0;
+  const uint32_t key = tn_hash_key32(act.seed_lo, act.seed_hi, act.layer);
+  const uint32_t q = (uint32_t)tid & 7u;
+  const int rl = tid >> 3;                                   // 0..63
+  const int t = rl >> 5;                                     // N tile
+  const int rpa = (HB + 31) >> 5;                            // rows per lane actually used (<= RP)
+  const int j0 = (rl & 31) * rpa;
+  const int rp = min(rpa, HB - j0);                          // may be <= 0 for the last lanes
+  const int g0 = row_base + t * BN2 + j0;                    // global row of this thread's first output row
+  const int t0 = (int)(((long long)g0 % T + T) % T);
+  const bool interior = rp > 0 && g0 >= 0 && t0 - PAD >= 0 && t0 + rp - 1 + PAD < T;
+  uint32_t vmask = 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const int grow = g0 - PAD + i;
+    if (grow >= 0 && grow < R) vmask |= 1u << i;
+  }
+  for (int kc = 0; kc < num_kc; ++kc) {
+    const int s = kc % S;
+    uint8_t* bh = smem + (size_t)s * stage_bytes + bh_off + (size_t)t * bh_tile;
+    uint8_t* bl = smem + (size_t)s * stage_bytes + bl_off + (size_t)t * bl_tile;
+    const int c = kc * TC_BK + 4 * (int)q;
+    const float4 sc4 = *reinterpret_cast<const float4*>(par + c);
+    const float4 sh4 = *reinterpret_cast<const float4*>(par + C + c);
+    const float4 b4 = *reinterpret_cast<const float4*>(par + 2 * C + c);
+    mbar_wait(fullB0 + 8 * s, (kc / S) & 1);
+    float4 win[W], uo[RP];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const uint32_t r = (uint32_t)(j0 + i);                 // raw row r <-> global row (tile's first row) - PAD + r
+      if (i < rp + 2 * PAD) win[i] = *reinterpret_cast<const float4*>(bh + r * 128u + ((q ^ (r & 7u)) << 4));
+      else win[i] = tn_zero4();
+    }
+    asm volatile("bar.sync 2, 512;" ::: "memory");          // every thread has its window: the raw tiles may be overwritten
+    if (rp > 0) {
+      if (lazy) {
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+          float4 v = make_float4(fmaf(win[i].x, sc4.x, sh4.x), fmaf(win[i].y, sc4.y, sh4.y), fmaf(win[i].z, sc4.z, sh4.z),
+                                 fmaf(win[i].w, sc4.w, sh4.w));
+          float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (drop) {
+            const uint32_t pr = ((uint32_t)(g0 - PAD + i) * (uint32_t)C + (uint32_t)c) >> 1;   // rows < 0 wrap: masked below
+            const uint32_t h0 = tn_hash_elem32(key, pr), h1 = tn_hash_elem32(key, pr + 1u);
+            m = make_float4((h0 & 0xFFFFu) >= act.thresh ? act.inv_keep : 0.f, (h0 >> 16) >= act.thresh ? act.inv_keep : 0.f,
+                            (h1 & 0xFFFFu) >= act.thresh ? act.inv_keep : 0.f, (h1 >> 16) >= act.thresh ? act.inv_keep : 0.f);
+          }
+          if (act.relu) {
+            m.x = v.x > 0.f ? m.x : 0.f; m.y = v.y > 0.f ? m.y : 0.f;
+            m.z = v.z > 0.f ? m.z : 0.f; m.w = v.w > 0.f ? m.w : 0.f;
+          }
+          win[i] = make_float4(v.x * m.x, v.y * m.y, v.z * m.z, v.w * m.w);
+        }
+        if (vmask != (1u << W) - 1u) {
+#pragma unroll
+          for (int i = 0; i < W; ++i)
+            if (!((vmask >> i) & 1u)) win[i] = tn_zero4();
+        }
+      }
+      float4 wk[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) wk[k] = *reinterpret_cast<const float4*>(par + (3 + k) * C + c);
+#pragma unroll
+      for (int i = 0; i < RP; ++i) {
+        if (i < rp) {
+          const int j = j0 + i;
+          float4 acc = b4;
+          if (interior) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc = tn_fma4(wk[k], win[i + k], acc);
+          } else {
+            const int tt0 = (t0 + i) % T;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+              const int tt = tt0 + k - PAD;
+              if (tt >= 0 && tt < T) acc = tn_fma4(wk[k], win[i + k], acc);
+            }
+          }
+          uo[i] = acc;
+          uint4 h, l;
+          h.x = rna_tf32(acc.x); h.y = rna_tf32(acc.y); h.z = rna_tf32(acc.z); h.w = rna_tf32(acc.w);
+          l.x = rna_tf32(acc.x - __uint_as_float(h.x)); l.y = rna_tf32(acc.y - __uint_as_float(h.y));
+          l.z = rna_tf32(acc.z - __uint_as_float(h.z)); l.w = rna_tf32(acc.w - __uint_as_float(h.w));
+          const uint32_t o = (uint32_t)j * 128u + ((q ^ ((uint32_t)j & 7u)) << 4);
+          *reinterpret_cast<uint4*>(bh + o) = h;
+          *reinterpret_cast<uint4*>(bl + o) = l;
+        }
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ready0 + 8 * s);               // one arrival per warp on this CTA's barrier
+    // the u side output leaves after the arrival, off the critical path of the chunk
+    if (p.fdw_u && rp > 0) {
+#pragma unroll
+      for (int i = 0; i < RP; ++i)
+        if (i < rp && g0 + i >= 0 && g0 + i < R) tn_st4(p.fdw_u + (size_t)(g0 + i) * C + c, uo[i]);
+    }
+  }
+}
+
+// MODE 0: plain epilogue (+ statistics / BatchNorm fold), 1: fused depthwise-backward epilogue, 2: fused depthwise-forward
+// operand producer (plain epilogue).  EW = transform / epilogue warps: 8, or 12 / 16 for the fused modes with K <= 3 (their
+// epilogue / producer loops are issue-bound with two warps per scheduler).
 template <int MODE, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ, TcParams p) {
   tn_grid_dep_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[5 * TC2_STAGES + 1 + TC2_STAGES];
+  __shared__ __align__(8) uint64_t bars[5 * TC2_STAGES + 1 + 2 * TC2_STAGES];
   __shared__ uint32_t tmem_base_slot;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -867,13 +983,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const int num_kc = p.Kd / TC_BK;
   const uint32_t a_tile = 128 * TC_BK * 4;              // 16 KiB: this CTA's 128 weight rows
   const uint32_t b_half = (uint32_t)HB * TC_BK * 4;     // this CTA's rows of one N tile
-  const uint32_t stage_bytes = 2 * a_tile + 4 * b_half; // A_hi | A_lo | B_hi[2] | B_lo[2]
+  // MODE 2: TMA delivers the RAW z rows with 8 extra rows (halo of the K-tap FIR) into the B_hi buffers
+  const uint32_t b_raw = b_half + (MODE == 2 ? 8u * TC_BK * 4 : 0u);
+  const uint32_t stage_bytes = 2 * a_tile + 2 * b_raw + 2 * b_half;   // A_hi | A_lo | B_hi[2] (raw) | B_lo[2]
   auto a_hi = [&](int s) { return smem + (size_t)s * stage_bytes; };
   auto a_lo = [&](int s) { return smem + (size_t)s * stage_bytes + a_tile; };
-  auto b_hi = [&](int s, int t) { return smem + (size_t)s * stage_bytes + 2 * a_tile + t * b_half; };
-  auto b_lo = [&](int s, int t) { return smem + (size_t)s * stage_bytes + 2 * a_tile + (2 + t) * b_half; };
+  auto b_hi = [&](int s, int t) { return smem + (size_t)s * stage_bytes + 2 * a_tile + t * b_raw; };
+  auto b_lo = [&](int s, int t) { return smem + (size_t)s * stage_bytes + 2 * a_tile + 2 * b_raw + t * b_half; };
   const uint32_t fullA0 = smem_u32(&bars[0]), fullB0 = smem_u32(&bars[S]), ready0 = smem_u32(&bars[2 * S]),
-                 empty0 = smem_u32(&bars[3 * S]), accum_bar = smem_u32(&bars[4 * S]), zbar0 = smem_u32(&bars[4 * S + 1]);
+                 empty0 = smem_u32(&bars[3 * S]), accum_bar = smem_u32(&bars[4 * S]), zbar0 = smem_u32(&bars[4 * S + 1]),
+                 readyP0 = smem_u32(&bars[5 * S + 1]);
+  // `ready` collects the LOCAL transform warps (cheap cta-scope arrivals).  The peer's otherwise idle warp 1 forwards its CTA's
+  // completion with ONE remote arrival per chunk on the leader's `readyP`: a remote arrive carries a gpu-scope release fence
+  // (MEMBAR.ALL.GPU in SASS, profiled as stall_membar), which must stay off the transform warps' critical path.
   // fused depthwise backward: the z tile of this CTA's 128 channels = 8 boxes [BN2 rows x 32 channels] (box b = 2 * channel
   // block + N tile), loaded into pipeline stages in the order the mainloop releases them: `zcap` boxes per stage, group g
   // of boxes -> stage (num_kc - S + g) % S, one barrier per group
@@ -886,7 +1008,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     for (int s = 0; s < S; ++s) {
       mbar_init(fullA0 + 8 * s, 1);
       mbar_init(fullB0 + 8 * s, 1);
-      mbar_init(ready0 + 8 * s, 2 * EW);                // the transform warps of both CTAs
+      mbar_init(ready0 + 8 * s, EW);                    // this CTA's transform warps
+      mbar_init(readyP0 + 8 * s, 1);                    // leader only: the peer's forwarded completion
       mbar_init(empty0 + 8 * s, 1);
     }
     mbar_init(accum_bar, 1);
@@ -914,9 +1037,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         if (leader) mbar_expect_tx(fullA0 + 8 * s, 4 * a_tile);   // both CTAs' hi + lo weight tiles
         tma_load_2d_2sm(smem_u32(a_hi(s)), &tmA_hi, fullA_leader0 + 8 * s, k0, m0 + (int)rank * 128);
         tma_load_2d_2sm(smem_u32(a_lo(s)), &tmA_lo, fullA_leader0 + 8 * s, k0, m0 + (int)rank * 128);
-        mbar_expect_tx(fullB0 + 8 * s, 2 * b_half);
-        tma_load_2d(smem_u32(b_hi(s, 0)), &tmB, fullB0 + 8 * s, k0, n0 + (int)rank * HB);
-        tma_load_2d(smem_u32(b_hi(s, 1)), &tmB, fullB0 + 8 * s, k0, n0 + BN2 + (int)rank * HB);
+        const int padr = MODE == 2 ? (p.fdw_K >> 1) : 0;           // fused depthwise forward: PAD rows of halo in front
+        mbar_expect_tx(fullB0 + 8 * s, 2 * b_raw);
+        tma_load_2d(smem_u32(b_hi(s, 0)), &tmB, fullB0 + 8 * s, k0, n0 + (int)rank * HB - padr);
+        tma_load_2d(smem_u32(b_hi(s, 1)), &tmB, fullB0 + 8 * s, k0, n0 + BN2 + (int)rank * HB - padr);
       }
       if (MODE == 1) {
         // z boxes of the previous layer for the fused epilogue, group by group as the tensor core releases the stages
@@ -946,6 +1070,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const uint32_t ph = (kc / S) & 1;
         mbar_wait(fullA0 + 8 * s, ph);
         mbar_wait(ready0 + 8 * s, ph);
+        mbar_wait(readyP0 + 8 * s, ph);
         tc_fence_after();
         const uint64_t dah = umma_desc_k128(smem_u32(a_hi(s))), dal = umma_desc_k128(smem_u32(a_lo(s)));
 #pragma unroll
@@ -964,11 +1089,36 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tc_commit_2sm(empty0 + 8 * s, (uint16_t)3);       // stage free in both CTAs once these MMAs have read it
       }
       tc_commit_2sm(accum_bar, (uint16_t)3);              // accumulators complete (both CTAs)
+    } else if (!leader && lane == 0) {
+      for (int kc = 0; kc < num_kc; ++kc) {               // forward this CTA's operand-ready events to the leader
+        const int s = kc % S;
+        mbar_wait(ready0 + 8 * s, (kc / S) & 1);
+        mbar_arrive_cluster(readyP0 + 8 * s, 0u);
+      }
     }
   } else {
     // ===== transform warps (hi / lo split of this CTA's activation rows), then epilogue =====
     const int tid = threadIdx.x - 64;
     const int n4 = 2 * HB * TC_BK / 4;                    // both N tiles are contiguous: B_hi[0] | B_hi[1]
+    if (MODE == 2) {
+      // fused depthwise forward: per-channel parameters to shared memory, then the operand-producing mainloop
+      float* par = reinterpret_cast<float*>(smem + p.par_off);
+      const int Kd = p.Kd, Kt = p.fdw_K;
+      for (int idx = tid; idx < Kd * (3 + Kt); idx += 32 * EW) {
+        const int f = idx / Kd, ch = idx - f * Kd;
+        float v;
+        if (f == 0) v = p.act.scale ? __ldg(p.act.scale + ch) : 1.f;
+        else if (f == 1) v = p.act.scale ? __ldg(p.act.shift + ch) : 0.f;
+        else if (f == 2) v = p.fdw_b ? __ldg(p.fdw_b + ch) : 0.f;
+        else v = __ldg(p.fdw_w + (size_t)ch * Kt + (f - 3));
+        par[idx] = v;
+      }
+      asm volatile("bar.sync 2, 512;" ::: "memory");
+      const uint32_t bh_off = 2 * a_tile, bl_off = 2 * a_tile + 2 * b_raw;
+      const int row_base = n0 + (int)rank * HB;
+      if (p.fdw_K == 1) tc2_dw_mainloop<1, 4>(p, smem, stage_bytes, bh_off, b_raw, bl_off, b_half, fullB0, ready0, num_kc, row_base, BN2, HB, par, tid, lane);
+      else tc2_dw_mainloop<3, 4>(p, smem, stage_bytes, bh_off, b_raw, bl_off, b_half, fullB0, ready0, num_kc, row_base, BN2, HB, par, tid, lane);
+    } else
     for (int kc = 0; kc < num_kc; ++kc) {
       const int s = kc % S;
       mbar_wait(fullB0 + 8 * s, (kc / S) & 1);
@@ -985,7 +1135,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(ready0 + 8 * s, 0u);     // one arrival per warp on the LEADER's barrier
+      if (lane == 0) mbar_arrive(ready0 + 8 * s);                 // one arrival per warp on this CTA's barrier
     }
     mbar_wait(accum_bar, 0);
     tc_fence_after();
@@ -1019,17 +1169,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const int nvalid = min(BN2, p.R - r0);
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * 256);
       float* zp = p.Z + (size_t)r0 * p.M_total + co;
-      if (nvalid == BN2) tc_epilogue<false, false, true>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, s1, s2, half);
-      else if (nvalid > 0) tc_epilogue<false, false, false>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, s1, s2, half);
+      if (nvalid == BN2) tc_epilogue<false, false, true>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, s1, s2, half, EW / 4);
+      else if (nvalid > 0) tc_epilogue<false, false, false>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, s1, s2, half, EW / 4);
     }
     if (p.stats) {
-      float* red = reinterpret_cast<float*>(smem + p.red_off);          // [2 halves][2 sums][128 channels]
+      float* red = reinterpret_cast<float*>(smem + p.red_off);          // [EW/4 parts][2 sums][128 channels]
       const int chl = (int)(threadIdx.x & 127u);
       red[(half * 2 + 0) * 128 + chl] = s1;
       red[(half * 2 + 1) * 128 + chl] = s2;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int which = tid >> 7, ch = tid & 127;
-      atomicAdd(p.stats + (size_t)which * p.M_total + (co - chl) + ch, (double)red[which * 128 + ch] + (double)red[(2 + which) * 128 + ch]);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
+      if (tid < 256) {
+        const int which = tid >> 7, ch = tid & 127;
+        double acc = 0.0;
+#pragma unroll
+        for (int pp = 0; pp < EW / 4; ++pp) acc += (double)red[(pp * 2 + which) * 128 + ch];
+        atomicAdd(p.stats + (size_t)which * p.M_total + (co - chl) + ch, acc);
+      }
     }
     }
   }
@@ -1516,7 +1671,7 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   if (use_pair < 0) { const char* e = getenv("TN_TC_PAIR"); use_pair = (e && atoi(e) == 0) ? 0 : 1; }   // measured: 9.99 -> 9.48 ms per step
   static int use_pair_dw = -1;
   if (use_pair_dw < 0) { const char* e = getenv("TN_TC_PAIR_DW"); use_pair_dw = (e && atoi(e) == 0) ? 0 : 1; }
-  if (use_pair && (p.dw_K == 0 || use_pair_dw) && p.fdw_K == 0 && nsplit == 3 && M % 256 == 0 && !(p.flags & 3) && R >= 512) {
+  if (use_pair && (p.dw_K == 0 || use_pair_dw) && (p.fdw_K == 0 || p.fdw_K <= 3) && nsplit == 3 && M % 256 == 0 && !(p.flags & 3) && R >= 512) {
     // cta_group::2 pair kernel: rows per pair = 2 * BN2 (minus the halo of the fused depthwise backward), chosen like pick_bn
     // (one wave of pairs, smallest tile that achieves it)
     const int sms = tn_num_sms();
@@ -1529,11 +1684,14 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
     }
     const int ew = (p.dw_K > 0 && p.dw_K <= 3) ? ew_sel : 8;
     const bool wide = ew > 8;
-    const int red2 = p.dw_K > 0 ? ((ew / 4) * 128 * (p.dw_K + 3) * 4 + 1023) / 1024 * 1024 : 2048;
+    const int par2 = p.fdw_K > 0 ? (Kd * (3 + p.fdw_K) * 4 + 1023) / 1024 * 1024 : 0;
+    const int raw2 = p.fdw_K > 0 ? 2 * 8 * TC_BK * 4 : 0;      // halo rows of the two raw tiles per stage
+    const int red2 = (p.dw_K > 0 ? ((ew / 4) * 128 * (p.dw_K + 3) * 4 + 1023) / 1024 * 1024 : (p.fdw_K > 0 ? 4096 : 2048)) + par2;
     int best = 0; double best_cost = 1e30;
     for (int bn2 = 256; bn2 >= 32; bn2 -= 16) {
-      const long long stage = 2ll * 128 * TC_BK * 4 + 4ll * (bn2 / 2) * TC_BK * 4;
+      const long long stage = 2ll * 128 * TC_BK * 4 + 4ll * (bn2 / 2) * TC_BK * 4 + raw2;
       if (stage * TC2_STAGES + red2 + 2048 > TC_SMEM_LIMIT) continue;
+      if (p.fdw_K > 0 && bn2 > 256 - 0) continue;
       if (p.dw_K > 0) {                                  // the 8 z boxes must fit the released stages
         const long long cap = stage / ((long long)bn2 * 128);
         if (cap < 1 || (8 + cap - 1) / cap > TC2_STAGES) continue;
@@ -1547,15 +1705,19 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
       CUtensorMap mA_hi, mA_lo, mB;
       if ((rc = make_map(&mA_hi, ws, M, Kd, 128)) != TN_OK) return rc;
       if ((rc = make_map(&mA_lo, ws + (size_t)M * Kd, M, Kd, 128)) != TN_OK) return rc;
-      if ((rc = make_map(&mB, X, R, Kd, best / 2)) != TN_OK) return rc;
+      if ((rc = make_map(&mB, X, R, Kd, best / 2 + (p.fdw_K > 0 ? 8 : 0))) != TN_OK) return rc;
       CUtensorMap mZ = mB;
       if (p.dw_K > 0 && (rc = make_map(&mZ, p.zprev, R, M, best, 32)) != TN_OK) return rc;
       p.R = R; p.Kd = Kd; p.M_total = M; p.BN = best; p.BNo = 2 * best - halo2; p.nsplit = 3;
-      const size_t stage_bytes = 2ull * 128 * TC_BK * 4 + 4ull * (best / 2) * TC_BK * 4;
+      const size_t stage_bytes = 2ull * 128 * TC_BK * 4 + 4ull * (best / 2) * TC_BK * 4 + raw2;
       p.red_off = (uint32_t)(stage_bytes * TC2_STAGES);
+      p.par_off = (uint32_t)(stage_bytes * TC2_STAGES + red2 - par2);
       const size_t smem = stage_bytes * TC2_STAGES + red2 + 1024;
       dim3 grid(2 * (unsigned)tn_cdiv(R, p.BNo), M / 256);
-      if (wide && ew == 16) {
+      if (p.fdw_K > 0) {
+        TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tn_launch_cluster(gemm_tc2_kernel<2, 16>, grid, 64 + 32 * 16, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
+      } else if (wide && ew == 16) {
         TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tn_launch_cluster(gemm_tc2_kernel<1, 16>, grid, 64 + 32 * 16, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
       } else if (wide) {
