@@ -247,6 +247,23 @@ typedef struct tn_adam_job {
 int tn_adam_tick(float* hyper_dev, void* stream);
 int tn_adam_multi(const tn_adam_job* jobs_dev, int njobs, long long max_n, const float* hyper_dev, void* stream);
 
+/* ---- the consumer of the eval-mode forward: trial scoring and detection metrics ----------------
+ * tn_cosine_scores: scores[i*N+j] = F.cosine_similarity(e_i, e_j) (eps 1e-8) for every ORDERED pair, i.e. the
+ * itertools.product order of SpeakerDataset.get_sample_pairs (src/datasets.py:165-183) as consumed by learn.test
+ * (src/learn.py:428-439); labels[i*N+j] = (speakers[i] == speakers[j]) (labels / speakers may be NULL).
+ * tn_det_metrics: utils.compute_error_rates / compute_mindcf / compute_eer (src/utils.py:294-367) over n trials
+ * (fp32 scores, 0/1 byte labels): stable ascending sort, cumulative target / non-target counts, fnrs / fprs (optional
+ * fp64 [n] outputs in sorted order), out8 (device, 8 doubles) = {min c_det (before the division by c_def + eps), EER,
+ * targets, non-targets, fpr0, tpr0, fpr1, tpr1 (the ROC segment crossing tpr = 1 - fpr)}.  sorted_keys (optional u64 [n]):
+ * low 32 bits = trial index at each sorted position.  workspace: 256-byte aligned, tn_det_workspace_bytes(n) bytes
+ * (bytes_out is a HOST pointer).  EER is NaN when all trials carry one label. */
+int tn_cosine_scores(const float* E, const long long* speakers, float* scores, unsigned char* labels, int N, int D,
+                     float eps, void* stream);
+int tn_det_workspace_bytes(long long n, long long* bytes_out);
+int tn_det_metrics(const float* scores, const unsigned char* labels, long long n, double p_target, double c_fa,
+                   double c_miss, double eps, void* workspace, long long workspace_bytes, double* out8, double* fnrs,
+                   double* fprs, unsigned long long* sorted_keys, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
