@@ -56,6 +56,14 @@ int tn_nwc_to_ncw(const float* x, float* y, int B, int C, int T, void* stream);
 int tn_mel_fwd(const float* wave, const int* lengths, const float* window, const float* fb, const int* band_lo,
                const int* band_hi, float* out, int B, int L_stride, int L_full, int T_out, int n_fft, int hop,
                int n_mels, int nwc, void* stream);
+/* The same with SpecAugment for given per-utterance draws (src/transforms.py:168-175: torchaudio TimeStretch at a
+ * random rate, 187-201: mask_along_axis over the mel axis and the time axis, value 0.0).  rates [B] fp64 (1.0 = bypass)
+ * and frames [B] = ceil(T_b / rate_b), both NULL = no stretching; masks [B, n_fmask + n_tmask, 2] int32 half-open
+ * (start, end) ranges, frequency masks first (NULL = none).  Frames >= frames[b] are zero filled. */
+int tn_mel_specaug_fwd(const float* wave, const int* lengths, const float* window, const float* fb, const int* band_lo,
+                       const int* band_hi, const double* rates, const int* frames, const int* masks, int n_fmask,
+                       int n_tmask, float* out, int B, int L_stride, int L_full, int T_out, int n_fft, int hop, int n_mels,
+                       int nwc, void* stream);
 
 /* ---- convolutions as GEMMs ------------------------------------------------------
  * Z[r,co] = bias[co] + sum_{k,ci} X[r+k-K/2, ci] * W[co,ci,k]  (taps stay inside an

@@ -43,3 +43,13 @@ def mel_inputs():
 def eval_dx_inputs():
     g = torch.Generator().manual_seed(5)
     return torch.randn(3, 80, 40, generator=g)
+
+
+# SpecAugment cases: (samples, seed for ``random`` and ``torch``); the waveform comes from ``specaug_wave``
+SPECAUG_CASES = [(16000, 101), (48000, 102), (12345, 103), (30001, 104), (20000, 105)]
+SPECAUG_KW = dict(freq_mask_num=2, time_mask_num=2)          # the fifth case uses two masks per axis
+
+
+def specaug_wave(samples, seed):
+    g = torch.Generator().manual_seed(seed)
+    return 0.1 * torch.randn(1, samples, generator=g)

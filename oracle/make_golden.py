@@ -74,6 +74,24 @@ def case_mel():
     save("mel_1s", mel=mels, **extra)
 
 
+def case_specaugment():
+    """``MelSpectrogram.__call__`` with SpecAugment (src/transforms.py:165-201) under fixed ``random`` / ``torch`` seeds:
+    the draws come out of the reference's own code, so the stored spectrograms pin the arithmetic AND the order /
+    source of the random numbers."""
+    import random
+    from cases import SPECAUG_CASES, SPECAUG_KW, specaug_wave
+    out = {}
+    for i, (samples, seed) in enumerate(SPECAUG_CASES):
+        kw = dict(specaugment_probability=1.0)
+        if i == len(SPECAUG_CASES) - 1:
+            kw.update(specaugment_freq_mask_num=SPECAUG_KW["freq_mask_num"], specaugment_time_mask_num=SPECAUG_KW["time_mask_num"])
+        t = transforms.MelSpectrogram(16000, n_fft=512, win_length=400, hop_length=160, n_mels=80, **kw)
+        random.seed(seed)
+        torch.manual_seed(seed)
+        out[f"specaug_{samples}_{seed}"] = t({"waveform": specaug_wave(samples, seed), "sample_rate": 16000})["spectrogram"][0]
+    save("mel_specaug", **out)
+
+
 def case_cfg1():
     """BASELINE.json configs[0]: TitaNet-S eval forward, batch 2, 1 s synthetic waveform."""
     spec = O.TitaNetSpec.named("s", 17, dropout=0.1)
@@ -132,8 +150,12 @@ def case_eval_input_grad():
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])            # optional: regenerate just the named train cases
+    if only == {"specaug"}:
+        case_specaugment()
+        sys.exit(0)
     if not only:
         case_mel()
+        case_specaugment()
         case_cfg1()
     for name, (spec, loss, nc, B, T, scale, margin, full) in TRAIN_CASES.items():
         if only and name not in only:

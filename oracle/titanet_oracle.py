@@ -212,6 +212,68 @@ def mel_spectrogram(waveform: Tensor, sample_rate: int = 16000, n_fft: int = 512
     return db / db.norm(p=2, dim=1, keepdim=True).clamp_min(1e-12)
 
 
+def specaugment_draw(n_mels: int, n_frames: int, min_speed: float = 0.95, max_speed: float = 1.05,
+                     freq_mask_ratio: float = 0.35, freq_mask_num: int = 1, time_mask_ratio: float = 0.15,
+                     time_mask_num: int = 1, probability: float = 1.0):
+    """The random draws of one ``MelSpectrogram.__call__`` with SpecAugment, in the reference's order and from the
+    same generators (src/transforms.py:168-173: ``random.random()``, ``random.uniform``; 187-201 ->
+    ``torchaudio.functional.mask_along_axis``: two ``torch.rand(1)`` per mask, ``value = rand * mask_param``,
+    ``start = long(rand * (size - value))``, ``end = start + long(value)``; a mask_param < 1 draws nothing).
+    Returns None (not applied) or ``(rate, stretched_frames, [(f0, f1), ...], [(t0, t1), ...])``."""
+    import random
+    if not (random.random() < probability):
+        return None
+    rate = random.uniform(min_speed, max_speed)
+    frames = n_frames if rate == 1.0 else int(math.ceil(n_frames / rate))      # len(torch.arange(0, T, rate))
+
+    def draw(mask_param, size):
+        if mask_param < 1:
+            return None
+        value = torch.rand(1) * mask_param
+        min_value = torch.rand(1) * (size - value)
+        start = int(min_value.long())
+        return start, start + int(value.long())
+
+    fm = [m for m in (draw(freq_mask_ratio * n_mels, n_mels) for _ in range(freq_mask_num)) if m is not None]
+    tm = [m for m in (draw(time_mask_ratio * frames, frames) for _ in range(time_mask_num)) if m is not None]
+    return rate, frames, fm, tm
+
+
+def mel_spectrogram_specaugment(waveform: Tensor, rate: float, freq_masks=(), time_masks=(), sample_rate: int = 16000,
+                                n_fft: int = 512, win_length: int = 400, hop_length: int = 160, n_mels: int = 80) -> Tensor:
+    """``transforms.MelSpectrogram.__call__`` WITH SpecAugment for given draws (src/transforms.py:165-201).
+
+    ``torchaudio.transforms.TimeStretch`` (phase vocoder, torchaudio 0.13 ``functional.phase_vocoder``) resamples the
+    complex STFT at ``time_steps = arange(0, T, rate)``: magnitude ``alpha |X[i+1]| + (1 - alpha) |X[i]|`` with
+    ``alpha = time_steps % 1`` and two zero frames appended, phase accumulated separately.  Line 178 takes
+    ``abs().pow(2)`` right after, so the phase never reaches the mel spectrogram: only the interpolated magnitude does.
+    Then mel / dB / L2-normalise as without augmentation, then the masks set rows [f0, f1) and frames [t0, t1) to 0."""
+    w = waveform if waveform.dim() == 2 else waveform.unsqueeze(0)
+    pad = n_fft // 2
+    x = F.pad(w.unsqueeze(1), (pad, pad), mode="reflect").squeeze(1)
+    frames = x.unfold(-1, n_fft, hop_length)
+    win = torch.zeros(n_fft, dtype=w.dtype)
+    off = (n_fft - win_length) // 2
+    win[off:off + win_length] = hann_window_periodic(win_length, w.dtype)
+    spec = torch.fft.rfft(frames * win, dim=-1)                            # [C, T, F]
+    mag = spec.abs()
+    if rate != 1.0:
+        T = mag.shape[1]
+        steps = torch.arange(0, T, rate, dtype=w.dtype)
+        alphas = (steps % 1.0).view(1, -1, 1)
+        mag = F.pad(mag, (0, 0, 0, 2))
+        mag = alphas * mag.index_select(1, (steps + 1).long()) + (1 - alphas) * mag.index_select(1, steps.long())
+    power = mag ** 2
+    fb = mel_filterbank(n_fft // 2 + 1, n_mels, sample_rate).to(w.dtype)
+    db = 10.0 * torch.log10(torch.clamp(power @ fb, min=1e-10)).transpose(1, 2)
+    out = db / db.norm(p=2, dim=1, keepdim=True).clamp_min(1e-12)
+    for f0, f1 in freq_masks:
+        out[:, f0:f1, :] = 0.0
+    for t0, t1 in time_masks:
+        out[:, :, t0:t1] = 0.0
+    return out
+
+
 def collate_pad(mels) -> Tuple[Tensor, Tensor]:
     """``datasets.collate_fn`` (src/datasets.py:48-73): zero-pad ``[1, M, T_i]`` mels
     to the batch max T; returns (``[B, M, Tmax]``, lengths)."""

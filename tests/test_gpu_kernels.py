@@ -322,6 +322,50 @@ def test_mel_against_golden_and_oracle(golden_dir):
     assert float(got[2, :, 26:].abs().max()) == 0.0
 
 
+def test_mel_specaugment_against_golden_and_oracle(golden_dir):
+    """SpecAugment inside the mel kernel (tn_mel_specaug_fwd): the example-dict call under the reference's seeds vs the
+    reference-generated golden; a ragged batch with per-utterance draws vs the oracle + collate zero padding."""
+    import random
+    from titanet_b200 import transforms
+    from cases import SPECAUG_CASES, SPECAUG_KW, specaug_wave
+    gold = np.load(os.path.join(golden_dir, "mel_specaug.npz"))
+    for i, (samples, seed) in enumerate(SPECAUG_CASES):
+        kw = {}
+        if i == len(SPECAUG_CASES) - 1:
+            kw = dict(specaugment_freq_mask_num=SPECAUG_KW["freq_mask_num"], specaugment_time_mask_num=SPECAUG_KW["time_mask_num"])
+        mel = transforms.MelSpectrogram(16000, n_fft=512, win_length=400, hop_length=160, n_mels=80, **kw)   # probability 1.0
+        random.seed(seed)
+        torch.manual_seed(seed)
+        ex = mel({"waveform": specaug_wave(samples, seed), "sample_rate": 16000})
+        want = torch.from_numpy(gold[f"specaug_{samples}_{seed}"])
+        assert ex["spectrogram"].shape == (1,) + want.shape
+        assert rel(ex["spectrogram"][0], want) < 2e-5, (samples, seed)
+        assert torch.equal(ex["spectrogram"][0] == 0, want == 0)                  # identical masks
+    # ragged batch: utterance 1 not augmented, utterance 3 stretched only, others stretched + masked
+    mel = transforms.MelSpectrogram(16000, n_fft=512, win_length=400, hop_length=160, n_mels=80)
+    g = torch.Generator().manual_seed(13)
+    lens = [16000, 12345, 48000, 30001]
+    waves = [0.1 * torch.randn(n, generator=g) for n in lens]
+    batch = torch.zeros(len(lens), max(lens))
+    for i, w in enumerate(waves):
+        batch[i, : len(w)] = w
+    SD = transforms.SpecAugmentDraw
+    fr = [mel.n_frames(n) for n in lens]
+    draws = [SD(0.95, transforms.stretched_frames(fr[0], 0.95), [(3, 20)], [(10, 25)]), None,
+             SD(1.05, transforms.stretched_frames(fr[2], 1.05), [(70, 80), (0, 2)], [(0, 7)]),
+             SD(1.0123456789, transforms.stretched_frames(fr[3], 1.0123456789))]
+    got = mel.batch(batch.to(dev()), torch.tensor(lens).to(dev()), augment=draws)
+    each = [O.mel_spectrogram(w.view(1, -1)) if d is None else
+            O.mel_spectrogram_specaugment(w.view(1, -1), d.rate, d.freq_masks, d.time_masks) for w, d in zip(waves, draws)]
+    want, _ = O.collate_pad(each)
+    assert got.shape == want.shape and rel(got, want) < 2e-5
+    got_cl = mel.batch(batch.to(dev()), torch.tensor(lens).to(dev()), channels_last=True, augment=draws)
+    assert torch.equal(got_cl.permute(0, 2, 1).contiguous(), got)
+    auto = mel.batch(batch.to(dev()), torch.tensor(lens).to(dev()), augment=True)       # host draws, probability 1.0
+    assert auto.shape[:2] == (4, 80) and bool(torch.isfinite(auto).all())
+    assert float((auto == 0).float().mean()) > 0.02                                      # some masked / padded cells
+
+
 def test_dropout_statistics_and_mask_replay(ops):
     """dropout>0 cannot match torch's RNG stream; check keep-rate, 1/(1-p) scaling, and that
     backward regenerates the forward mask."""

@@ -103,13 +103,24 @@ def test_constructor_signatures_match_reference_contract():
 
 
 def test_mel_host_constants_match_torchaudio_formula():
-    from titanet_b200 import transforms
+    from titanet_b200 import TitanetLibraryError, transforms
     assert torch.equal(transforms._htk_filterbank(257, 80, 16000), O.mel_filterbank())
     with pytest.raises(NotImplementedError):
         transforms.MelSpectrogram(16000)          # n_fft=400 default is not a power of two
     mel = transforms.MelSpectrogram(16000, n_fft=512, win_length=400, hop_length=160, n_mels=80)
-    with pytest.raises(NotImplementedError):      # SpecAugment (default probability 1.0) is not built
+    with pytest.raises(TitanetLibraryError):      # no CPU path (this test runs without a GPU)
         mel({"waveform": torch.zeros(1, 16000), "sample_rate": 16000})
+    # SpecAugment draws: same generators, same order as the reference (pinned through the oracle's golden test)
+    import random
+    for seed, frames in ((101, 101), (7, 301)):
+        random.seed(seed); torch.manual_seed(seed)
+        d = mel.draw_specaugment(frames)
+        random.seed(seed); torch.manual_seed(seed)
+        rate, fr, fm, tm = O.specaugment_draw(80, frames)
+        assert (d.rate, d.frames, d.freq_masks, d.time_masks) == (rate, fr, fm, tm)
+        assert 0.95 <= d.rate <= 1.05 and d.frames == transforms.stretched_frames(frames, d.rate)
+    off = transforms.MelSpectrogram(16000, n_fft=512, win_length=400, hop_length=160, n_mels=80, specaugment_probability=0.0)
+    assert off.draw_specaugment(101) is None
     ts = transforms.get_transforms(["chunk"], None)
     assert [type(t).__name__ for t in ts] == ["Resample", "RandomChunk", "MelSpectrogram"]
     assert ts[-1].specaugment_probability == 0.0 and ts[-1].hop_length == 160 and ts[-1].win_length == 400

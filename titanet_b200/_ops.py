@@ -980,8 +980,11 @@ def rownorm_(w: Tensor, eps: float = 1e-12) -> Tensor:
 # mel front end (no gradient)
 # ----------------------------------------------------------------------------
 def mel_forward(wave: Tensor, lengths: Optional[Tensor], window: Tensor, fb: Tensor, band_lo: Tensor, band_hi: Tensor,
-                n_fft: int, hop: int, n_mels: int, T_out: Optional[int] = None, nwc: bool = False) -> Tensor:
-    """wave [B, L] -> [B, n_mels, T] (or [B, T, n_mels] when nwc)."""
+                n_fft: int, hop: int, n_mels: int, T_out: Optional[int] = None, nwc: bool = False,
+                rates: Optional[Tensor] = None, frames: Optional[Tensor] = None, masks: Optional[Tensor] = None,
+                n_fmask: int = 0, n_tmask: int = 0) -> Tensor:
+    """wave [B, L] -> [B, n_mels, T] (or [B, T, n_mels] when nwc).  rates / frames / masks: SpecAugment draws
+    (``tn_mel_specaug_fwd``: fp64 [B], int32 [B], int32 [B, n_fmask + n_tmask, 2])."""
     wave = _c(wave)
     B, L = wave.shape
     if T_out is None:
@@ -990,6 +993,17 @@ def mel_forward(wave: Tensor, lengths: Optional[Tensor], window: Tensor, fb: Ten
         require_cuda(lengths)
         lengths = lengths.to(torch.int32).contiguous()
     out = empty((B, T_out, n_mels) if nwc else (B, n_mels, T_out), wave)
-    call("tn_mel_fwd", ptr(wave), ptr(lengths), ptr(window), ptr(fb), ptr(band_lo), ptr(band_hi), ptr(out), B, L, L, T_out, n_fft,
-         hop, n_mels, int(nwc))
+    if rates is None and masks is None:
+        call("tn_mel_fwd", ptr(wave), ptr(lengths), ptr(window), ptr(fb), ptr(band_lo), ptr(band_hi), ptr(out), B, L, L, T_out,
+             n_fft, hop, n_mels, int(nwc))
+        return out
+    require_cuda(rates, frames, masks)
+    if rates is not None and (rates.dtype != torch.float64 or frames.dtype != torch.int32 or rates.numel() != B or frames.numel() != B):
+        raise TypeError("rates must be fp64 [B] and frames int32 [B]")
+    if masks is not None and (masks.dtype != torch.int32 or tuple(masks.shape) != (B, n_fmask + n_tmask, 2)):
+        raise TypeError("masks must be int32 [B, n_fmask + n_tmask, 2]")
+    call("tn_mel_specaug_fwd", ptr(wave), ptr(lengths), ptr(window), ptr(fb), ptr(band_lo), ptr(band_hi),
+         ptr(rates.contiguous() if rates is not None else None), ptr(frames.contiguous() if frames is not None else None),
+         ptr(masks.contiguous() if masks is not None else None), n_fmask, n_tmask, ptr(out), B, L, L, T_out, n_fft, hop,
+         n_mels, int(nwc))
     return out

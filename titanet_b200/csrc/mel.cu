@@ -16,13 +16,26 @@
 #define MEL_FT 16
 #define MEL_THREADS 256
 
+// SpecAugment (src/transforms.py:168-175, 187-201) for given per-utterance draws; all pointers NULL = off.
+//  - time stretch (torchaudio TimeStretch = phase vocoder, then .abs().pow(2): the accumulated phase never reaches the
+//    power spectrogram, so only its magnitude interpolation alpha |X[i+1]| + (1 - alpha) |X[i]| at the fractional frame
+//    positions arange(0, T, rate) is computed); an output frame then needs TWO source frames, which ride in the real
+//    and imaginary lanes of one FFT.  rate == 1 is torchaudio's bypass.
+//  - masks: n_fmask ranges over the mel axis then n_tmask ranges over the (stretched) time axis, value 0.0.
+struct TnSpecAug {
+  const double* rates;       // [B]
+  const int* frames;         // [B] stretched frame count ceil(T_b / rate_b)
+  const int* masks;          // [B, n_fmask + n_tmask, 2] half-open (start, end)
+  int n_fmask, n_tmask;
+};
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
 __global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
                                                           const float* __restrict__ window, const float* __restrict__ fb,
                                                           const int* __restrict__ band_lo, const int* __restrict__ band_hi,
                                                           float* __restrict__ out, int L_stride, int L_full, int T_out,
-                                                          int N, int log2N, int hop, int n_mels, int nwc) {
+                                                          int N, int log2N, int hop, int n_mels, int nwc, TnSpecAug aug) {
   tn_grid_dep_sync();
   extern __shared__ float smem[];
   const int NF = N / 2 + 1;
@@ -35,7 +48,11 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float* __restric
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * MEL_FT;
   const int L = lengths ? lengths[b] : L_full;
-  const int T_valid = 1 + L / hop;
+  const int T_src = 1 + L / hop;                             // frames of the (unstretched) spectrogram
+  const double rate = aug.rates ? aug.rates[b] : 1.0;
+  const bool stretch = rate != 1.0;
+  const int T_valid = stretch ? aug.frames[b] : T_src;       // frames this utterance produces; later ones are zero
+  const int step = stretch ? 1 : 2;                          // output frames per FFT
   const float* x = wave + (size_t)b * L_stride;
   const int half = N / 2;
 
@@ -47,12 +64,19 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float* __restric
   for (int i = tid; i < N; i += MEL_THREADS) win[i] = window[i];
   __syncthreads();
 
-  for (int jp = 0; jp < MEL_FT; jp += 2) {
-    const int ta = t0 + jp, tb = ta + 1;
-    const bool va = ta < T_valid && ta < T_out, vb = tb < T_valid && tb < T_out;
+  for (int jp = 0; jp < MEL_FT; jp += step) {
+    int ta = t0 + jp, tb = ta + 1;                            // source frames in the two FFT lanes
+    bool va = ta < T_valid && ta < T_out, vb = tb < T_valid && tb < T_out;
+    float alpha = 0.f;
     if (!va && !vb) {
-      for (int i = tid; i < 2 * n_mels; i += MEL_THREADS) melv[(jp + i / n_mels) * (n_mels + 1) + i % n_mels] = 0.f;
+      for (int i = tid; i < step * n_mels; i += MEL_THREADS) melv[(jp + i / n_mels) * (n_mels + 1) + i % n_mels] = 0.f;
       continue;        // uniform across the block
+    }
+    if (stretch) {     // output frame t0 + jp sits at time_steps[t0 + jp] = fp32(rate * index), like torch.arange
+      const float pos = (float)(rate * (double)(t0 + jp));
+      ta = (int)pos; tb = (int)(pos + 1.0f);
+      alpha = pos - floorf(pos);
+      va = ta < T_src; vb = tb < T_src;                       // frames past the end are the vocoder's zero padding
     }
     // windowed frames, bit-reversed order
     for (int n = tid; n < N; n += MEL_THREADS) {
@@ -82,13 +106,19 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float* __restric
       const float2 zk = buf[k], zc = buf[(N - k) & (N - 1)];
       const float ar = 0.5f * (zk.x + zc.x), ai = 0.5f * (zk.y - zc.y);     // X_A = (Z[k] + conj Z[N-k]) / 2
       const float br = 0.5f * (zk.y + zc.y), bi = -0.5f * (zk.x - zc.x);    // X_B = (Z[k] - conj Z[N-k]) / (2i)
-      pw[k] = ar * ar + ai * ai;
-      pw[NF + k] = br * br + bi * bi;
+      const float pa = ar * ar + ai * ai, pb = br * br + bi * bi;
+      if (stretch) {
+        const float mg = alpha * sqrtf(pb) + (1.f - alpha) * sqrtf(pa);
+        pw[k] = mg * mg;
+      } else {
+        pw[k] = pa;
+        pw[NF + k] = pb;
+      }
     }
     __syncthreads();
-    for (int i = tid; i < 2 * n_mels; i += MEL_THREADS) {
+    for (int i = tid; i < step * n_mels; i += MEL_THREADS) {
       const int j = i / n_mels, m = i - j * n_mels;
-      const bool valid = j == 0 ? va : vb;
+      const bool valid = stretch ? true : (j == 0 ? va : vb);
       float acc = 0.f;
       const float* p = pw + j * NF;
       const int lo = band_lo[m], hi = band_hi[m];
@@ -109,6 +139,17 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float* __restric
     for (int m = lane; m < n_mels; m += 32) row[m] *= inv;
   }
   __syncthreads();
+  if (aug.masks) {
+    const int* mk = aug.masks + (size_t)b * (aug.n_fmask + aug.n_tmask) * 2;
+    for (int i = tid; i < MEL_FT * n_mels; i += MEL_THREADS) {
+      const int j = i / n_mels, m = i - j * n_mels, t = t0 + j;
+      bool hit = false;
+      for (int q = 0; q < aug.n_fmask; ++q) hit |= (m >= mk[2 * q] && m < mk[2 * q + 1]);
+      for (int q = aug.n_fmask; q < aug.n_fmask + aug.n_tmask; ++q) hit |= (t >= mk[2 * q] && t < mk[2 * q + 1]);
+      if (hit) melv[j * (n_mels + 1) + m] = 0.f;
+    }
+    __syncthreads();
+  }
   const int total = MEL_FT * n_mels;
   if (nwc) {
     for (int i = tid; i < total; i += MEL_THREADS) {
@@ -127,9 +168,9 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float* __restric
 // lengths == NULL) -> out [B, n_mels, T_out] (nwc = 0) or [B, T_out, n_mels] (nwc = 1).
 // window: [n_fft] (already zero-padded); fb: [n_fft/2+1, n_mels]; band_lo/hi: [n_mels]
 // half-open ranges of non-zero filterbank rows.  Frames >= 1 + L_b/hop are zero filled.
-extern "C" int tn_mel_fwd(const float* wave, const int* lengths, const float* window, const float* fb, const int* band_lo,
-                          const int* band_hi, float* out, int B, int L_stride, int L_full, int T_out, int n_fft, int hop,
-                          int n_mels, int nwc, void* stream) {
+static int mel_launch(const float* wave, const int* lengths, const float* window, const float* fb, const int* band_lo,
+                      const int* band_hi, float* out, int B, int L_stride, int L_full, int T_out, int n_fft, int hop, int n_mels,
+                      int nwc, TnSpecAug aug, void* stream) {
   TN_REQUIRE(wave && window && fb && band_lo && band_hi && out, "mel_fwd: null tensor");
   TN_REQUIRE(B > 0 && B <= 65535 && T_out > 0 && hop > 0 && n_mels > 0 && n_mels <= 256, "mel_fwd: bad shape B=%d T_out=%d hop=%d n_mels=%d", B, T_out, hop, n_mels);
   int log2N = 0;
@@ -144,7 +185,34 @@ extern "C" int tn_mel_fwd(const float* wave, const int* lengths, const float* wi
   }
   dim3 grid(tn_cdiv(T_out, MEL_FT), B);
   tn_launch(mel_kernel, grid, MEL_THREADS, smem, stream, wave, lengths, window, fb, band_lo, band_hi, out, L_stride,
-                                                                 L_full, T_out, n_fft, log2N, hop, n_mels, nwc);
+                                                                 L_full, T_out, n_fft, log2N, hop, n_mels, nwc, aug);
   TN_LAUNCH_CHECK("mel_kernel");
   return TN_OK;
+}
+
+// wave [B, L_stride] (utterance b uses its first lengths[b] samples, or L_full when
+// lengths == NULL) -> out [B, n_mels, T_out] (nwc = 0) or [B, T_out, n_mels] (nwc = 1).
+// window: [n_fft] (already zero-padded); fb: [n_fft/2+1, n_mels]; band_lo/hi: [n_mels]
+// half-open ranges of non-zero filterbank rows.  Frames >= 1 + L_b/hop are zero filled.
+extern "C" int tn_mel_fwd(const float* wave, const int* lengths, const float* window, const float* fb, const int* band_lo,
+                          const int* band_hi, float* out, int B, int L_stride, int L_full, int T_out, int n_fft, int hop,
+                          int n_mels, int nwc, void* stream) {
+  TnSpecAug aug = {nullptr, nullptr, nullptr, 0, 0};
+  return mel_launch(wave, lengths, window, fb, band_lo, band_hi, out, B, L_stride, L_full, T_out, n_fft, hop, n_mels, nwc, aug,
+                    stream);
+}
+
+// The same with SpecAugment for given draws: rates [B] fp64 (1.0 = not stretched) and frames [B] = ceil(T_b / rate_b)
+// (both NULL = no stretching); masks [B, n_fmask + n_tmask, 2] int32 half-open ranges (NULL = no masks; an empty range
+// masks nothing).  Frames >= frames[b] are zero filled.
+extern "C" int tn_mel_specaug_fwd(const float* wave, const int* lengths, const float* window, const float* fb,
+                                  const int* band_lo, const int* band_hi, const double* rates, const int* frames,
+                                  const int* masks, int n_fmask, int n_tmask, float* out, int B, int L_stride, int L_full,
+                                  int T_out, int n_fft, int hop, int n_mels, int nwc, void* stream) {
+  TN_REQUIRE((rates == nullptr) == (frames == nullptr), "mel_specaug_fwd: rates and frames go together");
+  TN_REQUIRE(n_fmask >= 0 && n_tmask >= 0 && n_fmask + n_tmask <= 64, "mel_specaug_fwd: bad mask counts %d / %d", n_fmask, n_tmask);
+  TN_REQUIRE(masks != nullptr || n_fmask + n_tmask == 0, "mel_specaug_fwd: mask counts without masks");
+  TnSpecAug aug = {rates, frames, (n_fmask + n_tmask) ? masks : nullptr, n_fmask, n_tmask};
+  return mel_launch(wave, lengths, window, fb, band_lo, band_hi, out, B, L_stride, L_full, T_out, n_fft, hop, n_mels, nwc, aug,
+                    stream);
 }

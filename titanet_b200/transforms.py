@@ -8,9 +8,13 @@ The arithmetic is one CUDA kernel (csrc/mel.cu).  The window and the HTK filterb
 are small host-side constants computed here with the formulas torchaudio uses
 (``torch.hann_window``; ``torchaudio.functional.melscale_fbanks``, htk, norm=None).
 
-Out of the accelerated path (DESIGN.md "scope"): SpecAugment (time stretch + masks,
-SURVEY §8f rank 2), ``SpeedPerturbation``, ``Reverb``; ``Resample`` only accepts inputs
-already at the target rate.
+SpecAugment (src/transforms.py:168-175, 187-201) runs inside the same
+kernel: the random draws (apply?, stretch rate, mask ranges) are made on the host from the
+generators the reference uses (``random`` and ``torch.rand``) in the reference's order, so
+equal seeds give equal augmentations; the kernel receives them as per-utterance arrays.
+
+Out of the accelerated path (DESIGN.md "scope"): ``SpeedPerturbation``, ``Reverb``;
+``Resample`` only accepts inputs already at the target rate.
 """
 from __future__ import annotations
 
@@ -20,11 +24,41 @@ import random
 import torch
 
 from . import _ops as ops
+from ._lib import TitanetLibraryError
 
 
 def copy_example(example):
     """Copy a dataset example, cloning its tensors (reference: src/transforms.py:12-22)."""
     return {k: (torch.clone(v) if isinstance(v, torch.Tensor) else v) for k, v in example.items()}
+
+
+class SpecAugmentDraw:
+    """The random draws of one augmented utterance: stretch ``rate``, stretched frame count, frequency masks and
+    time masks as half-open ``(start, end)`` ranges."""
+
+    __slots__ = ("rate", "frames", "freq_masks", "time_masks")
+
+    def __init__(self, rate: float, frames: int, freq_masks=(), time_masks=()):
+        self.rate, self.frames = float(rate), int(frames)
+        self.freq_masks, self.time_masks = list(freq_masks), list(time_masks)
+
+    def __repr__(self):
+        return f"SpecAugmentDraw(rate={self.rate}, frames={self.frames}, freq={self.freq_masks}, time={self.time_masks})"
+
+
+def stretched_frames(n_frames: int, rate: float) -> int:
+    """Frames after ``torchaudio.transforms.TimeStretch``: ``len(torch.arange(0, n_frames, rate))`` (bypass at rate 1)."""
+    return n_frames if rate == 1.0 else int(math.ceil(n_frames / rate))
+
+
+def _draw_mask(mask_param: float, size: int):
+    """``torchaudio.functional.mask_along_axis``' draws (two ``torch.rand(1)``); nothing is drawn when mask_param < 1."""
+    if mask_param < 1:
+        return None
+    value = torch.rand(1) * mask_param
+    min_value = torch.rand(1) * (size - value)
+    start = int(min_value.long())
+    return start, start + int(value.long())
 
 
 def _htk_filterbank(n_freqs: int, n_mels: int, sample_rate: int) -> torch.Tensor:
@@ -83,32 +117,77 @@ class MelSpectrogram:
     def n_frames(self, n_samples: int) -> int:
         return 1 + n_samples // self.hop_length
 
-    def batch(self, waveforms: torch.Tensor, lengths: torch.Tensor | None = None, channels_last: bool = False) -> torch.Tensor:
+    def draw_specaugment(self, n_frames: int):
+        """One utterance's SpecAugment draws, from the generators and in the order the reference consumes them
+        (src/transforms.py:168-173 ``random.random()`` / ``random.uniform``; 187-201 ``torch.rand`` inside
+        ``mask_along_axis``).  Returns ``None`` when the coin flip says "no augmentation"."""
+        if not (random.random() < self.specaugment_probability):
+            return None
+        rate = random.uniform(self.specaugment_min_speed, self.specaugment_max_speed)
+        frames = stretched_frames(n_frames, rate)
+        fm = [_draw_mask(self.specaugment_freq_mask_ratio * self.n_mels, self.n_mels)
+              for _ in range(self.specaugment_freq_mask_num)]
+        tm = [_draw_mask(self.specaugment_time_mask_ratio * frames, frames) for _ in range(self.specaugment_time_mask_num)]
+        return SpecAugmentDraw(rate, frames, [m for m in fm if m], [m for m in tm if m])
+
+    def batch(self, waveforms: torch.Tensor, lengths: torch.Tensor | None = None, channels_last: bool = False,
+              augment=None) -> torch.Tensor:
         """``[B, L]`` CUDA waveforms -> ``[B, n_mels, T]`` with ``T = 1 + L // hop``.  With
         ``lengths`` (samples per utterance) each utterance is transformed on its own length
-        (own reflect padding) and frames past it are zero, like ``collate_fn``."""
+        (own reflect padding) and frames past it are zero, like ``collate_fn``.
+
+        ``augment``: ``None`` (no SpecAugment), ``True`` (draw per utterance with ``draw_specaugment``) or a list of
+        B ``SpecAugmentDraw`` / ``None``.  Stretched utterances have ``ceil(T_b / rate_b)`` frames; T becomes the
+        batch maximum and shorter utterances are zero padded, again like ``collate_fn``."""
         if waveforms.dim() != 2:
             raise ValueError("expected [B, L] waveforms")
         if lengths is None and waveforms.shape[1] <= self.n_fft // 2:
             raise ValueError("waveform shorter than n_fft // 2 + 1 samples (reflect padding)")
         window, fb, lo, hi = self._consts(waveforms.device)
+        if augment is None:
+            return ops.mel_forward(waveforms, lengths, window, fb, lo, hi, self.n_fft, self.hop_length, self.n_mels,
+                                   nwc=channels_last)
+        B, L = waveforms.shape
+        lens = [L] * B if lengths is None else [int(v) for v in lengths.tolist()]
+        src_frames = [self.n_frames(v) for v in lens]
+        if augment is True:
+            augment = [self.draw_specaugment(t) for t in src_frames]
+        if len(augment) != B:
+            raise ValueError("augment must hold one entry per utterance")
+        nf = max([len(d.freq_masks) for d in augment if d is not None] + [0])
+        nt = max([len(d.time_masks) for d in augment if d is not None] + [0])
+        rates = torch.ones(B, dtype=torch.float64)
+        frames = torch.tensor(src_frames, dtype=torch.int32)
+        masks = torch.zeros(B, max(nf + nt, 1), 2, dtype=torch.int32)
+        for b, d in enumerate(augment):
+            if d is None:
+                continue
+            if d.frames != stretched_frames(src_frames[b], d.rate):
+                raise ValueError(f"utterance {b}: draw made for another length ({d.frames} frames)")
+            rates[b], frames[b] = d.rate, d.frames
+            for q, m in enumerate(d.freq_masks):
+                masks[b, q] = torch.tensor(m, dtype=torch.int32)
+            for q, m in enumerate(d.time_masks):
+                masks[b, nf + q] = torch.tensor(m, dtype=torch.int32)
+        dev = waveforms.device
         return ops.mel_forward(waveforms, lengths, window, fb, lo, hi, self.n_fft, self.hop_length, self.n_mels,
-                               nwc=channels_last)
+                               T_out=int(frames.max()), nwc=channels_last, rates=rates.to(dev), frames=frames.to(dev),
+                               masks=masks.to(dev) if nf + nt else None, n_fmask=nf, n_tmask=nt)
 
     def __call__(self, example):
         assert isinstance(example, dict) and "waveform" in example, "Wrong input structure"
         new_example = copy_example(example)
-        apply_specaugment = random.random() < self.specaugment_probability
-        if apply_specaugment:
-            raise NotImplementedError("SpecAugment (time stretch / frequency / time masks) is not part of the CUDA mel "
-                                      "path yet; construct with specaugment_probability=0.0 (the reference's default "
-                                      "training configuration does, parameters.yml:87-91)")
         wave = new_example["waveform"]
         src_device = wave.device
         if wave.dim() == 1:
             wave = wave.unsqueeze(0)
+        if src_device.type != "cuda" and not torch.cuda.is_available():
+            raise TitanetLibraryError("titanet_b200.transforms.MelSpectrogram runs on NVIDIA B200 (sm_100a) only: no CUDA "
+                                      "device is visible and there is no CPU fallback")
         dev = src_device if src_device.type == "cuda" else torch.device("cuda")
-        spec = self.batch(wave.to(device=dev, dtype=torch.float32))                # [C, n_mels, T]
+        draw = self.draw_specaugment(self.n_frames(wave.shape[-1]))                 # one draw per example, like the reference
+        spec = self.batch(wave.to(device=dev, dtype=torch.float32),
+                          augment=None if draw is None else [draw] * wave.shape[0])  # [C, n_mels, T]
         new_example["spectrogram"] = spec.to(src_device)
         return new_example
 
