@@ -102,7 +102,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     sample = f"{steps} steps of {batch} utterances x {args.seconds:g} s (mel + fwd + bwd), {warmup} warm-up, torch CPU ops"
     line = {
-        "impl": "reference", "metric": "utterances/sec (TitaNet-S fwd+bwd, 3s@16kHz)", "value": round(value, 3),
+        "impl": "reference", "metric": metric_name(args), "value": round(value, 3),
         "unit": "utterances/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(dt * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.batch),      # our arm's workload; each CPU step is a bounded sample of it (see `sample`)
@@ -225,6 +225,11 @@ def graph_time_kernel(kind: str, R: int, Ci: int, Co: int, B: int, dropout: floa
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e3 / reps
+
+
+def metric_name(args) -> str:
+    """BASELINE.json's metric for the default workload; other --model / --seconds runs (parity-test configurations) say so."""
+    return f"utterances/sec (TitaNet-{args.model.upper()} fwd+bwd, {args.seconds:g}s@16kHz)"
 
 
 def run_ours(args):
@@ -360,13 +365,14 @@ def run_ours(args):
     value = world * B / (ms_step * 1e-3)
     e2e = world * B / (ms_e2e * 1e-3)
     line = {
-        "metric": "utterances/sec (TitaNet-S fwd+bwd, 3s@16kHz)", "value": round(value, 1), "unit": "utterances/s",
+        "metric": metric_name(args), "value": round(value, 1), "unit": "utterances/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, B),
         "e2e": {"value": round(e2e, 1), "unit": "utterances/s", "h2d_bytes_per_step": B * L * 4 + B * 8, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e, 3)},
-        "gpu_launches": launches, "cuda_graph": not args.no_graph, "clocks": clocks, "roofline": roof,
+        "gpu_launches": launches, "cuda_graph": not args.no_graph,
+        "hbm_peak_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2), "clocks": clocks, "roofline": roof,
     }
     if not args.no_cpu_baseline and world == 1:
         v, dt = time_cpu(args, args.cpu_batch, 2, 1)
