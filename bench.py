@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--blocks", type=int, default=17)
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--cpu-batch", type=int, default=8, help="utterances per step of the CPU arm / CPU baseline")
+    ap.add_argument("--loss", default="ce", choices=["ce", "arc"], help="ce: CELoss (configs[1]); arc: ArcFaceLoss s=30 m=0.2 (configs[2], [3])")
+    ap.add_argument("--ragged", action="store_true",
+                    help="configs[3]: utterance lengths 1..--seconds s (whole seconds), each mel on its own length, zero padded")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -67,13 +70,15 @@ def peaks():
 def cpu_step_factory(args, batch):
     import titanet_oracle as O
     spec = O.TitaNetSpec.named(args.model, args.blocks, dropout=args.dropout)
-    sd = O.synth_state_dict(spec, "ce", N_CLASSES)
+    sd = O.synth_state_dict(spec, args.loss, N_CLASSES)
     wave, labels = O.synthetic_batch(batch, seconds=args.seconds, n_classes=N_CLASSES, seed=42)
+    lens = ragged_lengths(args, batch, 42).tolist() if args.ragged else [wave.shape[1]] * batch
+    kw = dict(scale=ARC_SCALE, margin=ARC_MARGIN) if args.loss == "arc" else {}
 
     def step():
         # per-utterance mel loop + collate, like datasets.py:292-293 / 48-73, then fwd + bwd
-        x, _ = O.collate_pad([O.mel_spectrogram(w.view(1, -1)) for w in wave])
-        out = O.titanet_step(sd, spec, x, labels, "ce", training=True)
+        x, _ = O.collate_pad([O.mel_spectrogram(w[:n].view(1, -1)) for w, n in zip(wave, lens)])
+        out = O.titanet_step(sd, spec, x, labels, args.loss, training=True, **kw)
         return float(out[2])
 
     return step
@@ -112,9 +117,20 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+ARC_SCALE, ARC_MARGIN = 30, 0.2          # parameters.yml:42-44 / BASELINE.json configs[2]
+
+
+def ragged_lengths(args, batch, seed):
+    """configs[3]: L_i = 16 000 * U{1..seconds} samples."""
+    g = torch.Generator().manual_seed(seed + 7)
+    return SAMPLE_RATE * torch.randint(1, int(args.seconds) + 1, (batch,), generator=g, dtype=torch.int32)
+
+
 def workload_config(args, batch):
-    return {"workload": f"TitaNet-{args.model.upper()}/{args.blocks} fwd+bwd, CE loss ({N_CLASSES} classes), "
-                        f"batch {batch}/GPU, {args.seconds:g}s@16kHz synthetic waveform, mel on device, dropout {args.dropout}",
+    loss = f"CE loss ({N_CLASSES} classes)" if args.loss == "ce" else f"ArcFace loss (s={ARC_SCALE}, m={ARC_MARGIN}, {N_CLASSES} classes)"
+    dur = f"variable 1-{args.seconds:g}s padded to {args.seconds:g}s" if args.ragged else f"{args.seconds:g}s"
+    return {"workload": f"TitaNet-{args.model.upper()}/{args.blocks} fwd+bwd, {loss}, "
+                        f"batch {batch}/GPU, {dur}@16kHz synthetic waveform, mel on device, dropout {args.dropout}",
             "batch_per_gpu": batch, "seconds": args.seconds, "frames": 1 + int(args.seconds * SAMPLE_RATE) // 160,
             "l2": "per-step working set (~2 GB of activations) >> 126 MB L2; no explicit flush"}
 
@@ -248,7 +264,8 @@ def run_ours(args):
 
     torch.manual_seed(42)
     B, L = args.batch, int(args.seconds * SAMPLE_RATE)
-    model = models.TitaNet.get_titanet(192, 80, args.blocks, args.model, loss_function=losses.CELoss(192, N_CLASSES),
+    head = losses.CELoss(192, N_CLASSES) if args.loss == "ce" else losses.ArcFaceLoss(192, N_CLASSES, scale=ARC_SCALE, margin=ARC_MARGIN)
+    model = models.TitaNet.get_titanet(192, 80, args.blocks, args.model, loss_function=head,
                                        dropout=args.dropout, device=dev).train()
     mel = transforms.MelSpectrogram(SAMPLE_RATE, n_fft=512, win_length=400, hop_length=160, n_mels=80, specaugment_probability=0.0)
     params = [p for p in model.parameters()]
@@ -256,19 +273,21 @@ def run_ours(args):
     wave_h = (0.1 * torch.randn(B, L, generator=g)).pin_memory()
     labels_h = torch.randint(0, N_CLASSES, (B,), generator=g).pin_memory()
     wave_d, labels_d = wave_h.to(dev), labels_h.to(dev)
+    lens_h = ragged_lengths(args, B, 42 + rank).pin_memory() if args.ragged else None
+    lens_d = lens_h.to(dev) if args.ragged else None
 
     from titanet_b200.engine import GradAllReduce, GraphedTrainStep
-    gts = GraphedTrainStep(model, mel, B, L, dev, use_graph=not args.no_graph, warmup=max(3, args.warmup))
+    gts = GraphedTrainStep(model, mel, B, L, dev, use_graph=not args.no_graph, warmup=max(3, args.warmup), lengths=lens_d)
     allreduce = GradAllReduce(params, world, arena=gts.arena)     # every gradient lives in the step's arena: one in-place NCCL call
 
     def step_resident():
-        gts.load(wave_d, labels_d)        # device -> device: inputs are already in HBM
+        gts.load(wave_d, labels_d, lens_d)        # device -> device: inputs are already in HBM
         loss = gts.run()
         allreduce()
         return loss
 
     def step_e2e():
-        gts.load(wave_h, labels_h)        # pinned host -> device copies inside the timed region
+        gts.load(wave_h, labels_h, lens_h)        # pinned host -> device copies inside the timed region
         loss = gts.run()
         allreduce()
         return float(loss.detach())       # D2H read of the loss (synchronises)
@@ -369,7 +388,7 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, B),
-        "e2e": {"value": round(e2e, 1), "unit": "utterances/s", "h2d_bytes_per_step": B * L * 4 + B * 8, "d2h_bytes_per_step": 4,
+        "e2e": {"value": round(e2e, 1), "unit": "utterances/s", "h2d_bytes_per_step": B * L * 4 + B * 8 + (B * 4 if args.ragged else 0), "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e, 3)},
         "gpu_launches": launches, "cuda_graph": not args.no_graph,
         "hbm_peak_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2), "clocks": clocks, "roofline": roof,

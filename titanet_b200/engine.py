@@ -28,11 +28,14 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model: torch.nn.Module, mel, batch: int, n_samples: int, device, use_graph: bool = True,
-                 warmup: int = 3, after_backward: Optional[Callable[[], None]] = None, use_arena: bool = True):
+                 warmup: int = 3, after_backward: Optional[Callable[[], None]] = None, use_arena: bool = True,
+                 lengths: Optional[torch.Tensor] = None):
         self.model, self.mel, self.device = model, mel, torch.device(device)
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.wave = torch.zeros(batch, n_samples, device=self.device)
         self.labels = torch.zeros(batch, dtype=torch.int64, device=self.device)
+        # ragged batches (datasets.collate_fn semantics): samples per utterance, a static int32 buffer like the others
+        self.lengths = None if lengths is None else lengths.to(self.device, torch.int32).clone()
         self.after_backward = after_backward
         self.loss = self.emb = self.preds = None
         self.graph = None
@@ -50,7 +53,7 @@ class GraphedTrainStep:
                 self.arena.begin_step()
             for p in self.params:
                 p.grad = None
-            self.emb, self.preds, self.loss = self.model(self.mel.batch(self.wave), speakers=self.labels)
+            self.emb, self.preds, self.loss = self.model(self.mel.batch(self.wave, self.lengths), speakers=self.labels)
             self.loss.backward()
             if self.arena is not None and self.arena.measuring:
                 self.arena.finish_measuring()
@@ -77,9 +80,13 @@ class GraphedTrainStep:
             self._body()
         self.launches_per_step = _lib.kernel_launches() - before
 
-    def load(self, wave: torch.Tensor, labels: torch.Tensor):
+    def load(self, wave: torch.Tensor, labels: torch.Tensor, lengths: Optional[torch.Tensor] = None):
         self.wave.copy_(wave, non_blocking=True)
         self.labels.copy_(labels, non_blocking=True)
+        if lengths is not None:
+            if self.lengths is None:
+                raise ValueError("this step was captured without per-utterance lengths")
+            self.lengths.copy_(lengths, non_blocking=True)
 
     def run(self) -> torch.Tensor:
         """One step on whatever is in the static input buffers."""
