@@ -391,7 +391,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e, 1), "unit": "utterances/s", "h2d_bytes_per_step": B * L * 4 + B * 8 + (B * 4 if args.ragged else 0), "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e, 3)},
         "gpu_launches": launches, "cuda_graph": not args.no_graph,
-        "hbm_peak_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2), "clocks": clocks, "roofline": roof,
+        "hbm_peak_gb": round(torch.cuda.max_memory_reserved(dev) / 2**30, 2), "clocks": clocks, "roofline": roof,
     }
     if not args.no_cpu_baseline and world == 1:
         v, dt = time_cpu(args, args.cpu_batch, 2, 1)

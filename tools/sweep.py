@@ -2,7 +2,8 @@
 
 ``python tools/sweep.py [--model s] [--batches 32,64,...] [--out gpurun_out/sweep.jsonl]`` runs ``bench.py`` once per batch
 size in a fresh process (no CPU baseline; 5 timed steps after 3 warm-up steps) and collects the JSON lines.  A batch is
-skipped when the previous one's peak allocation says it would not fit in HBM (activations grow linearly with the batch).
+skipped when the previous one's peak reservation says it would not fit in HBM (activations grow linearly with the batch;
+TitaNet-S at batch 2048 does not fit: the eager warm-up pool and the CUDA-graph pool each hold a step's ~90 GB).
 """
 import argparse
 import json
@@ -18,7 +19,7 @@ def main():
     ap.add_argument("--model", default="s")
     ap.add_argument("--blocks", type=int, default=17)
     ap.add_argument("--seconds", type=float, default=3.0)
-    ap.add_argument("--batches", default="32,64,128,256,512,1024,2048")
+    ap.add_argument("--batches", default="32,64,128,256,512,1024")
     ap.add_argument("--hbm-gb", type=float, default=150.0, help="skip a batch predicted to need more than this")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
     args = ap.parse_args()
