@@ -10,9 +10,10 @@
 // BatchNorm statistics (sum z, sum z^2 per channel) are thread-local sums, and for a
 // fixed row the 32 lanes of a warp write 32 consecutive floats (one 128 B line).
 //
-// Precision: fp32 operands are split hi = rna_tf32(x), lo = rna_tf32(x - hi); three MMAs
-// hi*hi + lo*hi + hi*lo accumulate into the same fp32 TMEM tile (error ~2^-21 per
-// product, like an fp32 FMA chain; SURVEY.md §7 hard part 1 shows plain TF32 breaks the
+// Precision: fp32 operands are split hi = rna_tf32(x), lo = x - hi.  Default scheme: one kind::tf32 MMA hi*hi plus ONE
+// kind::f16 (bf16) MMA over a doubled K that carries both corrections lo*hi + hi*lo (see tc_store_corr below); the
+// original 3xTF32 scheme (three tf32 MMAs hi*hi + lo*hi + hi*lo, TN_TC_3XTF32=1) is kept for A/B.  Both accumulate into
+// the same fp32 TMEM tile and are fp32-equivalent (SURVEY.md §7 hard part 1 shows plain TF32 breaks the
 // 1e-3 parity contract through train-mode BatchNorm).  The weight split is precomputed
 // (tn_split_tf32, tiny); the activation tile is split in shared memory by the four
 // transform warps between the TMA arrival and the MMA issue.  nsplit = 1 skips the
@@ -25,6 +26,7 @@
 // (src/models.py:384) and the ASP linears (src/models.py:549-551).
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <string.h>
 #include <stdlib.h>
 
@@ -132,6 +134,42 @@ __device__ __forceinline__ uint32_t rna_tf32(float x) {
   return u;
 }
 
+// ---------------------------------------------------------------------------
+// Correction operand of the default split scheme ("TF32 + BF16 corrections", p.corr = 1).
+//   x.w = xh.wh + (xl.wh + xh.wl) + xl.wl,  xh = rna_tf32(x), xl = x - xh (|xl| <= 2^-11 |x|)
+// The bracket is ~2^-11 of the result, so its operands only need ~8 bits: it is issued as ONE kind::f16 (bf16) MMA over a
+// doubled K -- activation row [bf16(xl) x32 | bf16(xh) x32] against weight row [bf16(wh) x32 | bf16(wl) x32] -- next to
+// the kind::tf32 MMA xh.wh.  A bf16 MMA of K = 16 costs what a tf32 MMA of K = 8 costs, and both advance 32 bytes of a
+// 128-byte swizzled row, so a K chunk takes 2 MMA issues per 32 bytes instead of 3 (3xTF32: hi.hi + lo.hi + hi.lo): one
+// third fewer tensor-pipe cycles at an operand-rounding error of ~7e-7 rms (3xTF32 8e-8, torch fp32 2e-7, plain TF32 3e-4;
+// tools/split_precision.py).  The "lo" buffers keep their size and (fp32-typed) TMA maps: 64 bf16 fill the 128 bytes that
+// held 32 tf32.  TN_TC_3XTF32=1 selects the old scheme (weight split and GEMMs alike).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float first, float second) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(first, second);      // .x (low half, lower address) = first
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+// v = four consecutive K elements (logical 16-byte fp32 chunk c = 0..7) of row `row` of a [rows x 32 fp32] SWIZZLE_128B
+// tile, h = their tf32 parts: write bf16(v - h) to K' = 4c.. and bf16(h) to K' = 32 + 4c.. of the bf16 tile at lo_base
+__device__ __forceinline__ void tc_store_corr(uint8_t* lo_base, uint32_t row, uint32_t c, float4 v, uint4 h) {
+  const float hx = __uint_as_float(h.x), hy = __uint_as_float(h.y), hz = __uint_as_float(h.z), hw = __uint_as_float(h.w);
+  const uint2 plo = make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
+  const uint2 phi = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
+  uint8_t* r = lo_base + row * 128u + ((c & 1u) << 3);
+  *reinterpret_cast<uint2*>(r + ((((c >> 1)) ^ (row & 7u)) << 4)) = plo;
+  *reinterpret_cast<uint2*>(r + (((4u + (c >> 1)) ^ (row & 7u)) << 4)) = phi;
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// instruction descriptor of the bf16 correction MMA from the tf32 one: A / B format TF32 (2) -> BF16 (1)
+__device__ __forceinline__ uint32_t tc_idesc_bf16(uint32_t idesc_tf32) {
+  return (idesc_tf32 & ~((7u << 7) | (7u << 10))) | (1u << 7) | (1u << 10);
+}
+
 // shared-memory matrix descriptor, K-major operand tile of TC_BK fp32 per row:
 // 128-byte rows: SWIZZLE_128B (layout 2), 8-row groups 1024 B apart; 64-byte rows: SWIZZLE_64B (layout 4), 512 B apart
 __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
@@ -179,6 +217,7 @@ struct TcParams {
   float* Z;
   double* stats;
   int R, Kd, M_total, BN, stages, nsplit, flags, tmem_cols;
+  int corr;                     // 1: TF32 + BF16-correction split (default), 0: 3xTF32
   int cluster2;          // launched as 2-CTA clusters along x: the two CTAs share (multicast) the weight tiles
   long long* trace;      // optional timeline buffer (debug): 128 slots per traced CTA
   // fused depthwise-backward epilogue (dw_K > 0): this GEMM is the data gradient of a pointwise conv
@@ -520,7 +559,8 @@ __device__ __forceinline__ void tc_dw_mainloop(const TcParams& p, uint8_t* smem,
           l.z = rna_tf32(acc.z - __uint_as_float(h.z)); l.w = rna_tf32(acc.w - __uint_as_float(h.w));
           const uint32_t o = (uint32_t)j * 128u + ((q ^ ((uint32_t)j & 7u)) << 4);
           *reinterpret_cast<uint4*>(bh + o) = h;
-          *reinterpret_cast<uint4*>(bl + o) = l;
+          if (p.corr) tc_store_corr(reinterpret_cast<uint8_t*>(bl), (uint32_t)j, (uint32_t)q, acc, h);
+          else *reinterpret_cast<uint4*>(bl + o) = l;
         }
       }
     }
@@ -676,7 +716,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           for (int kk = 0; kk < TC_BK / 8; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 2);       // 8 tf32 = 32 bytes = 2 x 16-byte units
             const uint32_t acc = (kc > 0 || kk > 0) ? 1u : 0u;
-            if (split) {
+            if (split && p.corr) {
+              tc_mma_tf32(d, dah + adv, dbh + adv, idesc, acc);
+              tc_mma_bf16(d, dal + adv, dbl + adv, tc_idesc_bf16(idesc), 1u);
+            } else if (split) {
               tc_mma_tf32(d, dal + adv, dbh + adv, idesc, acc);
               tc_mma_tf32(d, dah + adv, dbl + adv, idesc, 1u);
               tc_mma_tf32(d, dah + adv, dbh + adv, idesc, 1u);
@@ -733,7 +776,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           l.x = rna_tf32(v.x - __uint_as_float(h.x)); l.y = rna_tf32(v.y - __uint_as_float(h.y));
           l.z = rna_tf32(v.z - __uint_as_float(h.z)); l.w = rna_tf32(v.w - __uint_as_float(h.w));
           reinterpret_cast<uint4*>(hi)[i] = h;
-          reinterpret_cast<uint4*>(lo)[i] = l;
+          if (p.corr) tc_store_corr(reinterpret_cast<uint8_t*>(lo), (uint32_t)i >> 3, ((uint32_t)i & 7u) ^ (((uint32_t)i >> 3) & 7u), v, h);
+          else reinterpret_cast<uint4*>(lo)[i] = l;
         }
         fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(ready0 + 8 * s);
@@ -833,6 +877,13 @@ __device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc
   asm volatile(
       "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
       " tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
 }
 __device__ __forceinline__ void tc_commit_2sm(uint32_t bar, uint16_t mask) {
@@ -943,7 +994,8 @@ __device__ __forceinline__ void tc2_dw_mainloop(const TcParams& p, uint8_t* smem
           l.z = rna_tf32(acc.z - __uint_as_float(h.z)); l.w = rna_tf32(acc.w - __uint_as_float(h.w));
           const uint32_t o = (uint32_t)j * 128u + ((q ^ ((uint32_t)j & 7u)) << 4);
           *reinterpret_cast<uint4*>(bh + o) = h;
-          *reinterpret_cast<uint4*>(bl + o) = l;
+          if (p.corr) tc_store_corr(reinterpret_cast<uint8_t*>(bl), (uint32_t)j, (uint32_t)q, acc, h);
+          else *reinterpret_cast<uint4*>(bl + o) = l;
         }
       }
     }
@@ -1081,9 +1133,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           for (int kk = 0; kk < TC_BK / 8; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 2);
             const uint32_t acc = (kc > 0 || kk > 0) ? 1u : 0u;
-            tc_mma_tf32_2sm(d, dal + adv, dbh + adv, idesc, acc);
-            tc_mma_tf32_2sm(d, dah + adv, dbl + adv, idesc, 1u);
-            tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, 1u);
+            if (p.corr) {
+              tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, acc);
+              tc_mma_bf16_2sm(d, dal + adv, dbl + adv, tc_idesc_bf16(idesc), 1u);
+            } else {
+              tc_mma_tf32_2sm(d, dal + adv, dbh + adv, idesc, acc);
+              tc_mma_tf32_2sm(d, dah + adv, dbl + adv, idesc, 1u);
+              tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, 1u);
+            }
           }
         }
         tc_commit_2sm(empty0 + 8 * s, (uint16_t)3);       // stage free in both CTAs once these MMAs have read it
@@ -1131,7 +1188,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         l.x = rna_tf32(v.x - __uint_as_float(h.x)); l.y = rna_tf32(v.y - __uint_as_float(h.y));
         l.z = rna_tf32(v.z - __uint_as_float(h.z)); l.w = rna_tf32(v.w - __uint_as_float(h.w));
         reinterpret_cast<uint4*>(hi)[i] = h;
-        reinterpret_cast<uint4*>(lo)[i] = l;
+        if (p.corr) tc_store_corr(reinterpret_cast<uint8_t*>(lo), (uint32_t)i >> 3, ((uint32_t)i & 7u) ^ (((uint32_t)i >> 3) & 7u), v, h);
+        else reinterpret_cast<uint4*>(lo)[i] = l;
       }
       fence_proxy_async();
       __syncwarp();
@@ -1196,19 +1254,42 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   if (p.has_bn) tn_bn_fold_last(p.bn, p.stats, p.M_total, gridDim.x * gridDim.y);
 }
 
+// split scheme of the whole library (weight split kernels and GEMMs must agree): 1 = TF32 + BF16 corrections (default),
+// 0 = 3xTF32 (TN_TC_3XTF32=1)
+static int tc_corr_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("TN_TC_3XTF32");
+    mode = (e && e[0] == '1') ? 0 : 1;
+  }
+  return mode;
+}
+
 // ---------------------------------------------------------------------------
-// weight split: ws[0] = rna_tf32(W), ws[1] = rna_tf32(W - ws[0]); optional transpose
+// weight split: ws[0] = rna_tf32(W), ws[1] = rna_tf32(W - ws[0]) (or the packed bf16 correction rows); optional transpose
 // ---------------------------------------------------------------------------
-__global__ void split_tf32_kernel(const float* __restrict__ W, float* __restrict__ hi, float* __restrict__ lo, int M, int Kd, int transpose) {
+// corr = 1: the second half holds, per row and 32-element K chunk, 64 bf16 = [bf16(hi) x32 | bf16(x - hi) x32] in the 128
+// bytes that held 32 tf32 lo values (the weight side of the bf16 correction MMA, see tc_store_corr)
+__device__ __forceinline__ void split_store(float* hi, float* lo, size_t i, int k, float x, int corr) {
+  const float h = __uint_as_float(rna_tf32(x));
+  hi[i] = h;
+  if (corr) {
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(lo + (i - (size_t)(k & 31))) + (k & 31);
+    c[0] = __float2bfloat16_rn(h);
+    c[32] = __float2bfloat16_rn(x - h);
+  } else {
+    lo[i] = __uint_as_float(rna_tf32(x - h));
+  }
+}
+__global__ void split_tf32_kernel(const float* __restrict__ W, float* __restrict__ hi, float* __restrict__ lo, int M, int Kd, int transpose,
+                                  int corr) {
   tn_grid_dep_sync();
   // output [M, Kd]; input [M, Kd] or (transpose) [Kd, M]
   const size_t n = (size_t)M * Kd;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / Kd), k = (int)(i - (size_t)m * Kd);
     const float x = transpose ? W[(size_t)k * M + m] : W[i];
-    const float h = __uint_as_float(rna_tf32(x));
-    hi[i] = h;
-    lo[i] = __uint_as_float(rna_tf32(x - h));
+    split_store(hi, lo, i, k, x, corr);
   }
 }
 
@@ -1594,12 +1675,12 @@ extern "C" int tn_split_tf32(const float* W, float* ws, int M, int Kd, int trans
   size_t n = (size_t)M * Kd;
   int blocks = (int)((n + 255) / 256);
   if (blocks > tn_num_sms() * 8) blocks = tn_num_sms() * 8;
-  tn_launch(split_tf32_kernel, blocks, 256, 0, stream, W, ws, ws + n, M, Kd, transpose);
+  tn_launch(split_tf32_kernel, blocks, 256, 0, stream, W, ws, ws + n, M, Kd, transpose, tc_corr_mode());
   TN_LAUNCH_CHECK("split_tf32_kernel");
   return TN_OK;
 }
 
-__global__ void split_tf32_batch_kernel(const tn_split_job* __restrict__ jobs) {
+__global__ void split_tf32_batch_kernel(const tn_split_job* __restrict__ jobs, int corr) {
   tn_grid_dep_sync();
   const tn_split_job j = jobs[blockIdx.y];
   const size_t n = (size_t)j.M * j.Kd;
@@ -1608,16 +1689,14 @@ __global__ void split_tf32_batch_kernel(const tn_split_job* __restrict__ jobs) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / j.Kd), k = (int)(i - (size_t)m * j.Kd);
     const float x = j.transpose ? j.W[(size_t)k * j.M + m] : j.W[i];
-    const float h = __uint_as_float(rna_tf32(x));
-    hi[i] = h;
-    lo[i] = __uint_as_float(rna_tf32(x - h));
+    split_store(hi, lo, i, k, x, corr);
   }
 }
 extern "C" int tn_split_tf32_batch(const tn_split_job* jobs_dev, int njobs, int max_elems, void* stream) {
   TN_REQUIRE(jobs_dev && njobs > 0 && njobs <= 65535 && max_elems > 0, "split_tf32_batch: bad arguments");
   int bx = (max_elems + 255) / 256;
   if (bx > 64) bx = 64;
-  tn_launch(split_tf32_batch_kernel, dim3(bx, njobs), 256, 0, stream, jobs_dev);
+  tn_launch(split_tf32_batch_kernel, dim3(bx, njobs), 256, 0, stream, jobs_dev, tc_corr_mode());
   TN_LAUNCH_CHECK("split_tf32_batch_kernel");
   return TN_OK;
 }
@@ -1708,7 +1787,7 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
       if ((rc = make_map(&mB, X, R, Kd, best / 2 + (p.fdw_K > 0 ? 8 : 0))) != TN_OK) return rc;
       CUtensorMap mZ = mB;
       if (p.dw_K > 0 && (rc = make_map(&mZ, p.zprev, R, M, best, 32)) != TN_OK) return rc;
-      p.R = R; p.Kd = Kd; p.M_total = M; p.BN = best; p.BNo = 2 * best - halo2; p.nsplit = 3;
+      p.R = R; p.Kd = Kd; p.M_total = M; p.BN = best; p.BNo = 2 * best - halo2; p.nsplit = 3; p.corr = tc_corr_mode();
       const size_t stage_bytes = 2ull * 128 * TC_BK * 4 + 4ull * (best / 2) * TC_BK * 4 + raw2;
       p.red_off = (uint32_t)(stage_bytes * TC2_STAGES);
       p.par_off = (uint32_t)(stage_bytes * TC2_STAGES + red2 - par2);
@@ -1750,7 +1829,7 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   if ((rc = make_map(&mA_hi, ws, M, Kd, 128)) != TN_OK) return rc;
   if ((rc = make_map(&mA_lo, ws + (size_t)M * Kd, M, Kd, 128)) != TN_OK) return rc;
   if ((rc = make_map(&mB, X, R, Kd, bn + (p.fdw_K > 0 ? 16 : 0))) != TN_OK) return rc;
-  p.R = R; p.Kd = Kd; p.M_total = M; p.BN = bn; p.BNo = bno; p.stages = stages; p.nsplit = nsplit;
+  p.R = R; p.Kd = Kd; p.M_total = M; p.BN = bn; p.BNo = bno; p.stages = stages; p.nsplit = nsplit; p.corr = tc_corr_mode();
   p.trace = g_trace;
   int cols = MT == 2 ? 512 : 32;
   while (MT == 1 && cols < bn) cols <<= 1;
