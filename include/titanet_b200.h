@@ -78,10 +78,12 @@ int tn_conv_gemm_simt(const float* X, const float* W, const float* bias, float* 
 int tn_conv_wgrad_simt(const float* dZ, const float* X, float* dW, float* dbias, int B, int T, int Ci, int Co, int K,
                        void* stream);
 
-/* Tensor-core path for the 1x1 convs / linears (tcgen05 + TMEM + TMA, 3xTF32 = fp32-equivalent):
+/* Tensor-core path for the 1x1 convs / linears (tcgen05 + TMEM + TMA, split arithmetic = fp32-equivalent):
  * Z[R,M] = bias + X[R,Kd] W[M,Kd]^T.  ws = split weights [2, M, Kd] from tn_split_tf32
- * (transpose = 1 reads W as [Kd, M]: the data-gradient GEMM).  nsplit: 3 (hi*hi+lo*hi+hi*lo)
- * or 1 (plain TF32).  Needs Kd %% 32 == 0 and M %% 128 == 0 (tn_gemm_tc_supported). */
+ * (transpose = 1 reads W as [Kd, M]: the data-gradient GEMM); its layout is private to the library
+ * (ws[0] = tf32(W); ws[1] = tf32(W - ws[0]), or the packed bf16 correction rows under TN_TC_BF16CORR=1).
+ * nsplit: 3 = fp32-equivalent (3xTF32: hi*hi + lo*hi + hi*lo; TN_TC_BF16CORR=1: tf32 hi*hi + one bf16 MMA carrying
+ * lo*hi + hi*lo) or 1 (plain TF32).  Needs Kd %% 32 == 0 and M %% 128 == 0 (tn_gemm_tc_supported). */
 int tn_gemm_tc_supported(int R, int Kd, int M);
 int tn_gemm_tc_set_trace(long long* buf);      /* debug: clock64 timeline of two CTAs (256 int64), NULL = off */
 int tn_split_tf32(const float* W, float* ws, int M, int Kd, int transpose, void* stream);

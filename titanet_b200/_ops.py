@@ -167,7 +167,7 @@ def nwc_to_ncw(x: Tensor) -> Tensor:
 # conv / linear as GEMM  (+ BatchNorm statistics in the epilogue)
 # ----------------------------------------------------------------------------
 # Tensor-core (tcgen05) path for the 1x1 convs / linears.  TC_FWD_NSPLIT / TC_BWD_NSPLIT:
-# 3 = fp32-equivalent 3xTF32, 1 = plain TF32.  TC_ENABLED exists for A/B tests against the
+# 3 = fp32-equivalent split (3xTF32; TF32 + one bf16 correction MMA under TN_TC_BF16CORR=1), 1 = plain TF32.  TC_ENABLED exists for A/B tests against the
 # exact-fp32 CUDA-core kernel, not as a runtime fallback (unsupported shapes always take the
 # CUDA-core kernel: K-tap convs, channel counts that are not multiples of 128 / 32).
 TC_ENABLED = True
@@ -535,7 +535,7 @@ class Depthwise(Function):
         return dz, dscale, dshift, dw, db, None, None, None, None, None, None
 
 
-TC_FUSE_DWBWD = True
+TC_FUSE_DWBWD = __import__("os").environ.get("TN_FUSE_DWBWD", "1") != "0"     # 0: tn_gemm_tc (dgrad) + tn_dw_bwd, for A/B
 # Two launch fusions, measured on the graph-replayed TitaNet-S step and OFF by default because they lose:
 #   TN_FUSE_BLOCK_ENTRY=1  first sub-block + skip branch as one autograd node, the skip data gradient accumulated in the GEMM
 #                          epilogue (red.global.add) instead of an add kernel:   10.21 -> 10.24 ms

@@ -10,9 +10,9 @@
 // BatchNorm statistics (sum z, sum z^2 per channel) are thread-local sums, and for a
 // fixed row the 32 lanes of a warp write 32 consecutive floats (one 128 B line).
 //
-// Precision: fp32 operands are split hi = rna_tf32(x), lo = x - hi.  Default scheme: one kind::tf32 MMA hi*hi plus ONE
-// kind::f16 (bf16) MMA over a doubled K that carries both corrections lo*hi + hi*lo (see tc_store_corr below); the
-// original 3xTF32 scheme (three tf32 MMAs hi*hi + lo*hi + hi*lo, TN_TC_3XTF32=1) is kept for A/B.  Both accumulate into
+// Precision: fp32 operands are split hi = rna_tf32(x), lo = x - hi.  Default scheme "3xTF32": three tf32 MMAs
+// hi*hi + lo*hi + hi*lo.  Opt-in (TN_TC_BF16CORR=1): one kind::tf32 MMA hi*hi plus ONE kind::f16 (bf16) MMA over a doubled K
+// that carries both corrections lo*hi + hi*lo (see tc_store_corr below).  Both accumulate into
 // the same fp32 TMEM tile and are fp32-equivalent (SURVEY.md §7 hard part 1 shows plain TF32 breaks the
 // 1e-3 parity contract through train-mode BatchNorm).  The weight split is precomputed
 // (tn_split_tf32, tiny); the activation tile is split in shared memory by the four
@@ -135,7 +135,7 @@ __device__ __forceinline__ uint32_t rna_tf32(float x) {
 }
 
 // ---------------------------------------------------------------------------
-// Correction operand of the default split scheme ("TF32 + BF16 corrections", p.corr = 1).
+// Correction operand of the opt-in split scheme ("TF32 + BF16 corrections", TN_TC_BF16CORR=1, p.corr = 1).
 //   x.w = xh.wh + (xl.wh + xh.wl) + xl.wl,  xh = rna_tf32(x), xl = x - xh (|xl| <= 2^-11 |x|)
 // The bracket is ~2^-11 of the result, so its operands only need ~8 bits: it is issued as ONE kind::f16 (bf16) MMA over a
 // doubled K -- activation row [bf16(xl) x32 | bf16(xh) x32] against weight row [bf16(wh) x32 | bf16(wl) x32] -- next to
@@ -143,7 +143,7 @@ __device__ __forceinline__ uint32_t rna_tf32(float x) {
 // 128-byte swizzled row, so a K chunk takes 2 MMA issues per 32 bytes instead of 3 (3xTF32: hi.hi + lo.hi + hi.lo): one
 // third fewer tensor-pipe cycles at an operand-rounding error of ~7e-7 rms (3xTF32 8e-8, torch fp32 2e-7, plain TF32 3e-4;
 // tools/split_precision.py).  The "lo" buffers keep their size and (fp32-typed) TMA maps: 64 bf16 fill the 128 bytes that
-// held 32 tf32.  TN_TC_3XTF32=1 selects the old scheme (weight split and GEMMs alike).
+// held 32 tf32.  The environment variable switches the weight split and the GEMMs alike.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float first, float second) {
   const __nv_bfloat162 t = __floats2bfloat162_rn(first, second);      // .x (low half, lower address) = first
@@ -217,7 +217,7 @@ struct TcParams {
   float* Z;
   double* stats;
   int R, Kd, M_total, BN, stages, nsplit, flags, tmem_cols;
-  int corr;                     // 1: TF32 + BF16-correction split (default), 0: 3xTF32
+  int corr;                     // 1: TF32 + BF16-correction split (TN_TC_BF16CORR=1), 0: 3xTF32 (default)
   int cluster2;          // launched as 2-CTA clusters along x: the two CTAs share (multicast) the weight tiles
   long long* trace;      // optional timeline buffer (debug): 128 slots per traced CTA
   // fused depthwise-backward epilogue (dw_K > 0): this GEMM is the data gradient of a pointwise conv
@@ -1254,13 +1254,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   if (p.has_bn) tn_bn_fold_last(p.bn, p.stats, p.M_total, gridDim.x * gridDim.y);
 }
 
-// split scheme of the whole library (weight split kernels and GEMMs must agree): 1 = TF32 + BF16 corrections (default),
-// 0 = 3xTF32 (TN_TC_3XTF32=1)
+// split scheme of the whole library (weight split kernels and GEMMs must agree): 0 = 3xTF32 (default),
+// 1 = TF32 + BF16 corrections (TN_TC_BF16CORR=1).  The second is 3 % faster on the whole TitaNet-S step and as accurate on
+// every GEMM-level and whole-model check, but one weight gradient of the small smoke() model moved from 1.9e-3 to 2.1e-2 of
+// the fp32 oracle, so it stays opt-in until that is explained.
 static int tc_corr_mode() {
   static int mode = -1;
   if (mode < 0) {
-    const char* e = getenv("TN_TC_3XTF32");
-    mode = (e && e[0] == '1') ? 0 : 1;
+    const char* e = getenv("TN_TC_BF16CORR");
+    mode = (e && e[0] == '1') ? 1 : 0;
   }
   return mode;
 }

@@ -1,0 +1,28 @@
+"""Error of tn_gemm_tc (nsplit = 3) against fp64 for the shapes of the smoke() model (R = 404) and of the benchmark; the split
+scheme follows TN_TC_BF16CORR.  Prints rel-max and rms-relative error per shape."""
+import math, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT]
+import torch
+from titanet_b200._lib import call, ptr
+
+def run(R, Kd, M, transpose, relu, flags=0):
+    g = torch.Generator().manual_seed(R + Kd + M)
+    x = torch.randn(R, Kd, generator=g)
+    if relu:
+        x = torch.relu(x)
+    w = torch.randn(*( (Kd, M) if transpose else (M, Kd) ), generator=g) / math.sqrt(Kd)
+    ref = x.double() @ (w.double() if transpose else w.double().t())
+    ws = torch.empty(2, M, Kd, device="cuda")
+    call("tn_split_tf32", ptr(w.cuda()), ptr(ws), M, Kd, int(transpose))
+    z = torch.empty(R, M, device="cuda")
+    call("tn_gemm_tc", ptr(x.cuda()), ptr(ws), None, ptr(z), None, R, Kd, M, flags, 3)
+    torch.cuda.synchronize()
+    err = (z.double().cpu() - ref)
+    print(f"R={R:6d} Kd={Kd:5d} M={M:5d} T={int(transpose)} relu={int(relu)}: relmax {float(err.abs().max() / ref.abs().max()):.2e}  rms {float(err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()):.2e}")
+
+print("scheme:", "TF32 + BF16 corrections" if os.environ.get("TN_TC_BF16CORR") == "1" else "3xTF32")
+for R in (404, 19264):
+    for Kd, M in ((256, 256), (256, 1536), (1536, 256), (1536, 128), (128, 1536)):
+        for tr in (False, True):
+            run(R, Kd, M, tr, True)
