@@ -31,3 +31,7 @@ print(f"cfg bf16corr={os.environ.get('TN_TC_BF16CORR', '0')} fuse_dwbwd={os.envi
       f"(fp32 oracle {rel(r32[0], r64[0]):.2e})  all grads rel-L2 {l2(grads):.2e} (fp32 oracle {l2(r32[3]):.2e})")
 for e, e32, k in rows[:5]:
     print(f"   {e:.2e} (fp32 oracle {e32:.2e})  {k}")
+k = "encoder.mega_blocks.0.sub_blocks.1.conv_block.0.conv.1.weight"          # the tensor smoke() looks at
+print(f"   smoke tensor: max|g| = {float(r64[3][k].abs().max()) / gmax:.2e} of the model's largest gradient entry; rel-max (own scale) vs fp64: "
+      f"CUDA {rel(grads[k], r64[3][k]):.2e}, fp32 oracle {rel(r32[3][k], r64[3][k]):.2e}; CUDA vs fp32 oracle {rel(grads[k], r32[3][k]):.2e}; "
+      f"rel-L2 vs fp64: CUDA {float((grads[k].double().cpu() - r64[3][k]).norm() / r64[3][k].norm()):.2e}, fp32 oracle {float((r32[3][k].double() - r64[3][k]).norm() / r64[3][k].norm()):.2e}")
