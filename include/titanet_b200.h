@@ -81,9 +81,9 @@ int tn_conv_wgrad_simt(const float* dZ, const float* X, float* dW, float* dbias,
 /* Tensor-core path for the 1x1 convs / linears (tcgen05 + TMEM + TMA, split arithmetic = fp32-equivalent):
  * Z[R,M] = bias + X[R,Kd] W[M,Kd]^T.  ws = split weights [2, M, Kd] from tn_split_tf32
  * (transpose = 1 reads W as [Kd, M]: the data-gradient GEMM); its layout is private to the library
- * (ws[0] = tf32(W); ws[1] = tf32(W - ws[0]), or the packed bf16 correction rows under TN_TC_BF16CORR=1).
- * nsplit: 3 = fp32-equivalent (3xTF32: hi*hi + lo*hi + hi*lo; TN_TC_BF16CORR=1: tf32 hi*hi + one bf16 MMA carrying
- * lo*hi + hi*lo) or 1 (plain TF32).  Needs Kd %% 32 == 0 and M %% 128 == 0 (tn_gemm_tc_supported). */
+ * (ws[0] = tf32(W); ws[1] = the packed bf16 correction rows, or tf32(W - ws[0]) under TN_TC_3XTF32=1).
+ * nsplit: 3 = fp32-equivalent (tf32 hi*hi + one bf16 MMA carrying lo*hi + hi*lo; TN_TC_3XTF32=1: three tf32 MMAs)
+ * or 1 (plain TF32).  Needs Kd %% 32 == 0 and M %% 128 == 0 (tn_gemm_tc_supported). */
 int tn_gemm_tc_supported(int R, int Kd, int M);
 int tn_gemm_tc_set_trace(long long* buf);      /* debug: clock64 timeline of two CTAs (256 int64), NULL = off */
 int tn_split_tf32(const float* W, float* ws, int M, int Kd, int transpose, void* stream);

@@ -36,10 +36,10 @@ def test_gemm_tc_3xtf32_matches_fp64(R, Kd, M):
     ref = x.double() @ w.double().t() + b.double()
     z, stats, ws = run_tc(x.cuda(), w.cuda(), b.cuda(), 3)
     # weight split: ws[0] = tf32(w); ws[1] = per row and 32-wide K chunk, 64 bf16 = [bf16(hi) x32 | bf16(w - hi) x32]
-    # (the weight side of the bf16 correction MMA) under TN_TC_BF16CORR=1, tf32(w - hi) in the default 3xTF32 scheme
+    # (the weight side of the bf16 correction MMA), or tf32(w - hi) under TN_TC_3XTF32=1
     hi = ws[0].cpu()
     assert rel(hi, w) < 6e-4
-    if os.environ.get("TN_TC_BF16CORR") != "1":
+    if os.environ.get("TN_TC_3XTF32") == "1":
         assert rel(ws[0] + ws[1], w) < 1e-6
     else:
         corr = ws[1].cpu().view(torch.bfloat16).view(M, Kd // 32, 64).float()

@@ -167,7 +167,7 @@ def nwc_to_ncw(x: Tensor) -> Tensor:
 # conv / linear as GEMM  (+ BatchNorm statistics in the epilogue)
 # ----------------------------------------------------------------------------
 # Tensor-core (tcgen05) path for the 1x1 convs / linears.  TC_FWD_NSPLIT / TC_BWD_NSPLIT:
-# 3 = fp32-equivalent split (3xTF32; TF32 + one bf16 correction MMA under TN_TC_BF16CORR=1), 1 = plain TF32.  TC_ENABLED exists for A/B tests against the
+# 3 = fp32-equivalent split (TF32 + one bf16 correction MMA; 3xTF32 under TN_TC_3XTF32=1), 1 = plain TF32.  TC_ENABLED exists for A/B tests against the
 # exact-fp32 CUDA-core kernel, not as a runtime fallback (unsupported shapes always take the
 # CUDA-core kernel: K-tap convs, channel counts that are not multiples of 128 / 32).
 TC_ENABLED = True

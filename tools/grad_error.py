@@ -29,7 +29,7 @@ def summarize(name, emb, loss, grads):
     tot = (sum(float((grads[k].double().cpu() - g64[k]).norm() ** 2) for k in g64) / sum(float(g64[k].norm() ** 2) for k in g64)) ** 0.5
     print(f"{name:28s} emb {rel(emb, r64[0], 1e-30):.2e}  loss {abs(float(loss) - float(r64[2])) / float(r64[2]):.2e}  grad worst-tensor relmax {worst:.2e}  global rel-L2 {tot:.2e}")
 summarize("fp32 oracle (CPU)", r32[0], r32[2], r32[3])
-ONLY = os.environ.get("ONLY")          # e.g. ONLY="tc fwd3 dgrad3 wgrad1"; the split scheme itself follows TN_TC_BF16CORR
+ONLY = os.environ.get("ONLY")          # e.g. ONLY="tc fwd3 dgrad3 wgrad1"; the split scheme itself follows TN_TC_3XTF32
 for name, fwd, bwd, wg in [("simt fp32", 0, 0, 0), ("tc fwd3 dgrad3 wgradSIMT", 3, 3, 0), ("tc fwd3 dgrad3 wgrad1", 3, 3, 1), ("tc fwd3 dgrad1 wgrad1", 3, 1, 1), ("tc fwd1 dgrad1 wgrad1", 1, 1, 1)]:
     if ONLY and name != ONLY:
         continue

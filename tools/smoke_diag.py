@@ -1,5 +1,5 @@
 """Per-parameter gradient error of the smoke() model (TitaNet-S/2, batch 4, 1 s, CE, dropout 0) against the fp32 and fp64 CPU
-oracles; env knobs (TN_TC_BF16CORR, TN_FUSE_DWBWD, ...) select the CUDA configuration.  Prints the worst tensors."""
+oracles; env knobs (TN_TC_3XTF32, TN_FUSE_DWBWD, ...) select the CUDA configuration.  Prints the worst tensors."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
@@ -27,7 +27,7 @@ rel = lambda a, b, floor=1e-30: float((a.detach().double().cpu() - b.double()).a
 grads = {k: p.grad for k, p in model.named_parameters()}
 l2 = lambda gs: (sum(float((gs[k].detach().double().cpu() - r64[3][k]).norm() ** 2) for k in r64[3]) / sum(float(r64[3][k].norm() ** 2) for k in r64[3])) ** 0.5
 rows = sorted(((rel(grads[k], r64[3][k], 1e-3 * gmax), rel(r32[3][k], r64[3][k], 1e-3 * gmax), k) for k in grads), reverse=True)
-print(f"cfg bf16corr={os.environ.get('TN_TC_BF16CORR', '0')} fuse_dwbwd={os.environ.get('TN_FUSE_DWBWD', '1')}: emb {rel(emb, r64[0]):.2e} "
+print(f"cfg 3xtf32={os.environ.get('TN_TC_3XTF32', '0')} fuse_dwbwd={os.environ.get('TN_FUSE_DWBWD', '1')}: emb {rel(emb, r64[0]):.2e} "
       f"(fp32 oracle {rel(r32[0], r64[0]):.2e})  all grads rel-L2 {l2(grads):.2e} (fp32 oracle {l2(r32[3]):.2e})")
 for e, e32, k in rows[:5]:
     print(f"   {e:.2e} (fp32 oracle {e32:.2e})  {k}")
