@@ -260,6 +260,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL writes its NCCL_DEBUG lines (the box sets VERSION: "NCCL version 2.28.9+cuda12.9") to stdout; stdout carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(42)
@@ -372,7 +374,7 @@ def run_ours(args):
                     "frac": round(ach_gb / pk["hbm_gbs"], 4), "traffic": traffic, "peak_source": pk["source"],
                     "algorithmic_bytes_per_launch": byts, "algorithmic_flops_per_launch": flops,
                     "algorithmic_tflop_s": round(ach_tf, 2), "tf32_peak_tflop_s": round(tf32_peak, 1),
-                    "tensor_frac_of_tf32_peak": round(ach_tf / tf32_peak, 4), "mma_issue_factor": 3,
+                    "tensor_frac_of_tf32_peak": round(ach_tf / tf32_peak, 4), "mma_issue_factor": 3 if os.environ.get("TN_TC_3XTF32") == "1" else 2,
                     "timing": "CUDA events around a CUDA graph of 20 back-to-back launches of this shape",
                     "eager_ms_per_step_by_entry_point": {k: round(v[1] / prof_steps, 3) for k, v in
                                                          sorted(groups.items(), key=lambda kv: -kv[1][1])}}
