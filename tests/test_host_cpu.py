@@ -124,3 +124,39 @@ def test_mel_host_constants_match_torchaudio_formula():
     ts = transforms.get_transforms(["chunk"], None)
     assert [type(t).__name__ for t in ts] == ["Resample", "RandomChunk", "MelSpectrogram"]
     assert ts[-1].specaugment_probability == 0.0 and ts[-1].hop_length == 160 and ts[-1].win_length == 400
+
+
+def test_evaluation_host_logic_buckets_by_length_and_keeps_order():
+    """``evaluation.embed_utterances`` (the host half of the batched ``learn.test``): utterances are grouped by frame count,
+    each group is forwarded as one batch (never padded together) and the rows come back in the caller's order; Subset /
+    indices handling follows src/learn.py:429-434 and src/datasets.py:171.  Device-free: a torch module stands in for the model."""
+    from titanet_b200 import evaluation as ev
+
+    class Probe(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.ones(1))
+            self.batches = []
+
+        def forward(self, x):                       # [B, 80, T] -> [B, 3]: (mean, first value, T)
+            self.batches.append(tuple(x.shape))
+            return torch.stack([x.mean(dim=(1, 2)), x[:, 0, 0], torch.full((x.shape[0],), float(x.shape[2]))], dim=1) * self.w
+
+    g = torch.Generator().manual_seed(0)
+    frames = [50, 37, 50, 64, 37, 50, 41]
+    specs = [torch.randn(1, 80, t, generator=g) for t in frames]
+    model = Probe().train()
+    emb = ev.embed_utterances(model, specs, max_batch=2)
+    assert not model.training                                            # learn.test puts the model in eval mode (src/learn.py:424)
+    assert sorted(model.batches) == sorted([(2, 80, 37), (1, 80, 41), (2, 80, 50), (1, 80, 50), (1, 80, 64)])
+    want = torch.cat([Probe()(s) for s in specs]).detach()
+    assert torch.allclose(emb, want, atol=1e-6) and emb[:, 2].tolist() == [float(t) for t in frames]
+    assert torch.equal(ev.embed_utterances(model, [s[0] for s in specs]), emb)        # [n_mels, T] inputs are accepted
+    with pytest.raises(ValueError):
+        ev.embed_utterances(model, [torch.randn(2, 80, 10)])
+    data = [{"spectrogram": s, "speaker": i % 3} for i, s in enumerate(specs)]
+    assert [it["speaker"] for it in ev._dataset_items(data, None)] == [0, 1, 2, 0, 1, 2, 0]
+    assert [it["speaker"] for it in ev._dataset_items(data, [4, 0])] == [1, 0]
+    assert [it["speaker"] for it in ev._dataset_items(torch.utils.data.Subset(data, [6, 5]), None)] == [0, 2]
+    with pytest.raises(Exception):                                        # scoring itself has no CPU path
+        ev.cosine_scores(emb)
