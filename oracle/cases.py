@@ -24,6 +24,14 @@ TRAIN_CASES = {
     "s17_ce_b4": (TitaNetSpec.named("s", 17), "ce", 251, 4, 101, None, 0.0, False),
 }
 
+# pinned for the oracle only (CPU): the GPU suite parametrises over TRAIN_CASES
+ORACLE_ONLY_CASES = {
+    # SphereFace: multiplicative angular margin cos(m1 * theta), default margin 3 (src/losses.py:135-149)
+    "tiny_k3_sphere": (TINY["tiny_k3"], "sphere", 10, 4, 43, 30, 3, True),
+    # eval-free train step at the notebook's class count with the loss's default scale (64) and margin (0.5)
+    "tiny_k7_arc_s64": (TINY["tiny_k7"], "arc", 251, 5, 29, 64, 0.5, True),
+}
+
 
 def train_inputs(spec, n_classes, B, T, seed=42):
     g = torch.Generator().manual_seed(seed + 1)

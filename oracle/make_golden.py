@@ -103,7 +103,7 @@ def case_cfg1():
     save("cfg1_s17_eval", emb=emb, n_params=np.int64(m.get_n_params()))
 
 
-from cases import TINY, TRAIN_CASES, train_inputs, mel_inputs, eval_dx_inputs  # noqa: E402
+from cases import TINY, TRAIN_CASES, ORACLE_ONLY_CASES, train_inputs, mel_inputs, eval_dx_inputs  # noqa: E402
 
 
 def train_case(name, spec, loss, n_classes, B, T, scale=None, margin=None, full_grads=True, seed=42,
@@ -157,7 +157,7 @@ if __name__ == "__main__":
         case_mel()
         case_specaugment()
         case_cfg1()
-    for name, (spec, loss, nc, B, T, scale, margin, full) in TRAIN_CASES.items():
+    for name, (spec, loss, nc, B, T, scale, margin, full) in {**TRAIN_CASES, **ORACLE_ONLY_CASES}.items():
         if only and name not in only:
             continue
         train_case(name, spec, loss, nc, B, T, scale if loss != "ce" else None,
