@@ -8,7 +8,7 @@ each scheme against the fp64 oracle next to the fp32 oracle's own error, for the
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tools")]
 import torch
 import torch.nn.functional as F

@@ -1,7 +1,7 @@
 """Gradient error of the CUDA path vs the fp64 oracle for the tensor-core precision settings
 (yard-stick: the fp32 oracle's own error vs fp64)."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
 import torch
 import titanet_oracle as O

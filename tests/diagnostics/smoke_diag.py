@@ -1,7 +1,7 @@
 """Per-parameter gradient error of the smoke() model (TitaNet-S/2, batch 4, 1 s, CE, dropout 0) against the fp32 and fp64 CPU
 oracles; env knobs (TN_TC_3XTF32, TN_FUSE_DWBWD, ...) select the CUDA configuration.  Prints the worst tensors."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import torch
 import titanet_oracle as O
