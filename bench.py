@@ -260,8 +260,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL writes its NCCL_DEBUG lines (the box sets VERSION: "NCCL version 2.28.9+cuda12.9") to stdout; stdout carries ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL writes its NCCL_DEBUG output to stdout (at WARN / VERSION level: "NCCL version 2.28.9+cuda12.9"); stdout carries ONE
+        # JSON line, so the log goes to a per-process file unless the caller chose one
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/titanet_b200_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(42)
