@@ -34,3 +34,30 @@ def test_trial_list_matches_reference_loop(gold):
     assert np.abs(scores - gold["model:scores"]).max() < 5e-7
     assert abs(E.compute_eer(gold["model:scores"], labels) - float(gold["model:eer"])) < 1e-9
     assert E.compute_mindcf(gold["model:scores"], labels) == pytest.approx(float(gold["model:mindcf"]), rel=1e-12)
+
+
+def test_eer_closed_form_matches_sklearn_and_scipy_on_random_trials():
+    """The closed-form crossing of oracle/eval_oracle.compute_eer against the third-party chain the reference calls
+    (sklearn.metrics.roc_curve -> scipy interp1d -> brentq, src/utils.py:294-300) on 60 random trial lists with heavy ties,
+    and compute_error_rates against a literal transcription-free check of its definition (counts at or below each threshold)."""
+    sk = pytest.importorskip("sklearn.metrics")
+    from scipy.interpolate import interp1d
+    from scipy.optimize import brentq
+    rng = np.random.RandomState(2024)
+    for _ in range(60):
+        n = int(rng.randint(8, 400))
+        labels = (rng.rand(n) < rng.uniform(0.1, 0.9)).astype(np.int64)
+        if labels.min() == labels.max():
+            labels[0], labels[1] = 0, 1
+        scores = (rng.randn(n) * 0.3 + rng.uniform(0.0, 0.6) * labels).astype(np.float32)
+        if rng.rand() < 0.7:
+            scores = np.round(scores, int(rng.randint(0, 3))).astype(np.float32)
+        fpr, tpr, _ = sk.roc_curve(labels, scores)
+        want = brentq(lambda x: 1.0 - x - interp1d(fpr, tpr)(x), 0.0, 1.0)
+        assert abs(E.compute_eer(scores, labels) - want) < 1e-9
+        fnrs, fprs, order = E.compute_error_rates(scores, labels)
+        s_sorted, l_sorted = scores[order], labels[order]
+        assert np.all(np.diff(s_sorted) >= 0)
+        i = int(rng.randint(0, n))
+        assert fnrs[i] == l_sorted[: i + 1].sum() / (labels.sum() + 1e-6)
+        assert fprs[i] == 1 - (1 - l_sorted[: i + 1]).sum() / ((1 - labels).sum() + 1e-6)
