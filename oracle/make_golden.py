@@ -137,6 +137,22 @@ def train_case(name, spec, loss, n_classes, B, T, scale=None, margin=None, full_
     return names
 
 
+def case_fp64():
+    """The gradient yard-stick of the GPU tests is the oracle evaluated in fp64; pin THAT against the reference modules run
+    in fp64 (``model.double()``), train mode, CE and ArcFace heads."""
+    for name, loss, scale, margin in (("tiny_k3_ce_fp64", "ce", None, None), ("tiny_k3_arc_fp64", "arc", 30, 0.2)):
+        spec, nc, B, T = TINY["tiny_k3"], 10, 4, 50
+        m = build_ref(spec, loss, nc, scale, margin).double().train()
+        x, y = train_inputs(spec, nc, B, T)
+        x = x.double().requires_grad_(True)
+        emb, preds, lval = m(x, speakers=y)
+        lval.backward()
+        out = dict(emb=emb, preds=preds, loss=lval, dx=x.grad)
+        for k, p in m.named_parameters():
+            out["grad:" + k] = p.grad
+        save(name, **out)
+
+
 def case_eval_input_grad():
     """``utils.chart_dependencies`` (utils.py:451-468): eval-mode forward, backprop one
     sample's outputs, only that sample's input gradient is non-zero."""
@@ -153,6 +169,9 @@ if __name__ == "__main__":
     if only == {"specaug"}:
         case_specaugment()
         sys.exit(0)
+    if only == {"fp64"}:
+        case_fp64()
+        sys.exit(0)
     if not only:
         case_mel()
         case_specaugment()
@@ -164,3 +183,4 @@ if __name__ == "__main__":
                    margin if loss != "ce" else None, full)
     if not only:
         case_eval_input_grad()
+        case_fp64()
