@@ -192,11 +192,12 @@ def graph_time_kernel(kind: str, R: int, Ci: int, Co: int, B: int, dropout: floa
     """Microseconds per launch of one tensor-core kernel shape, replayed back to back from a CUDA graph."""
     import math
     from titanet_b200._lib import call, ptr
+    from titanet_b200._ops import gemm_tc_raw
     T = R // B
     rnd = lambda *s: torch.randn(*s, device=dev)
     x, out = rnd(R, Ci), torch.empty(R, Co, device=dev)
     w = rnd(Co, Ci) / math.sqrt(Ci)
-    ws = torch.empty(2, Co, Ci, device=dev)
+    ws = torch.empty(3, Co, Ci, device=dev)
     if kind == "tn_wgrad_tc":
         dz, dw = rnd(R, Co), torch.zeros(Co, Ci, device=dev)
         fn = lambda: call("tn_wgrad_tc", ptr(dz), ptr(x), ptr(dw), R, Ci, Co)
@@ -218,13 +219,12 @@ def graph_time_kernel(kind: str, R: int, Ci: int, Co: int, B: int, dropout: floa
         dww, dwb, bias = rnd(Ci, 1, 3), rnd(Ci), rnd(Co)
         sc, sh = torch.rand(Ci, device=dev) + 0.5, 0.1 * rnd(Ci)
         seed = torch.tensor([1], dtype=torch.int64, device=dev)
-        st = torch.zeros(2 * Co, dtype=torch.float64, device=dev)
         fn = lambda: call("tn_gemm_tc_dwfwd", ptr(x), ptr(ws), ptr(dww), ptr(dwb), ptr(sc), ptr(sh), 1, float(dropout),
-                          ptr(seed) if dropout > 0 else None, 3, ptr(bias), ptr(u), ptr(out), ptr(st), None, B, T, Ci, Co, 3)
+                          ptr(seed) if dropout > 0 else None, 3, ptr(bias), ptr(u), ptr(out), None, None, B, T, Ci, Co, 3, None)
     else:
         call("tn_split_tf32", ptr(w), ptr(ws), Co, Ci, 0)
         bias, st = rnd(Co), torch.zeros(2 * Co, dtype=torch.float64, device=dev)
-        fn = lambda: call("tn_gemm_tc", ptr(x), ptr(ws), ptr(bias), ptr(out), ptr(st), R, Ci, Co, 0, 3)
+        fn = lambda: gemm_tc_raw(x, ws, bias, out, st, R, Ci, Co, 0, 3)
     fn()
     torch.cuda.synchronize()
     g, side = torch.cuda.CUDAGraph(), torch.cuda.Stream(device=dev)

@@ -41,6 +41,20 @@ extern "C" {
 /* epilogue flags of the conv-GEMM entry points */
 #define TN_EPI_TANH 1   /* z = tanh(z)                       */
 #define TN_EPI_ACCUM 2  /* z += previous contents of Z       */
+#define TN_GEMM_GRAD 8  /* tensor-core GEMMs: this is a gradient GEMM (the cheaper TF32 + bf16-correction split is allowed) */
+
+/* Scratch of the kernels that reduce across thread blocks WITHOUT floating-point atomics (BatchNorm statistics in the GEMM
+ * epilogues, split-K): every block stores its partial result to `parts` and the last block of a group (device-wide ticket)
+ * adds the partials in a fixed order, so a forward pass is reproducible bit for bit.
+ *   parts   uninitialised fp32 workspace of parts_floats elements, 16-byte aligned (tn_*_scratch_floats says how many)
+ *   tickets TN_TICKETS unsigned ints, ZERO on entry and returned to zero by every kernel that uses them: one array per
+ *           stream may be shared by all calls (kernels that run concurrently must not share it) */
+#define TN_TICKETS 64
+typedef struct tn_scratch {
+  float* parts;
+  long long parts_floats;
+  unsigned int* tickets;
+} tn_scratch;
 
 const char* tn_last_error(void);
 int tn_version(void);
@@ -69,26 +83,32 @@ int tn_mel_specaug_fwd(const float* wave, const int* lengths, const float* windo
  * Z[r,co] = bias[co] + sum_{k,ci} X[r+k-K/2, ci] * W[co,ci,k]  (taps stay inside an
  * utterance).  Replaces Conv1dSamePadding.forward (src/modules.py:14-40) for dense convs,
  * the skip nn.Conv1d (src/models.py:452-455) and nn.Linear (src/models.py:549-551,
- * 510-513; src/losses.py:30,70).  stats (fp64 [2*Co], ACCUMULATED) receives the
+ * 510-513; src/losses.py:30,70).  stats (fp64 [2*Co], written; needs Co %% 4 == 0) receives the
  * per-channel sum and sum of squares of Z for the following BatchNorm.
- * transpose_w = 1 computes the data gradient (X := dZ, weight read as W[ci',co',K-1-k]). */
+ * transpose_w = 1 computes the data gradient (X := dZ, weight read as W[ci',co',K-1-k]).
+ * scratch: required when tn_conv_gemm_simt_scratch_floats(...) > 0 (statistics, or a skinny problem run as split-K). */
+long long tn_conv_gemm_simt_scratch_floats(int B, int T, int Ci, int Co, int K, int flags, int with_stats);
 int tn_conv_gemm_simt(const float* X, const float* W, const float* bias, float* Z, double* stats, int B, int T, int Ci,
-                      int Co, int K, int transpose_w, int flags, void* stream);
+                      int Co, int K, int transpose_w, int flags, const tn_scratch* scratch, void* stream);
 /* dW[co,ci,k] += sum_r dZ[r,co] X[r+k-K/2,ci];  dbias[co] += sum_r dZ[r,co]   (ACCUMULATED) */
 int tn_conv_wgrad_simt(const float* dZ, const float* X, float* dW, float* dbias, int B, int T, int Ci, int Co, int K,
                        void* stream);
 
 /* Tensor-core path for the 1x1 convs / linears (tcgen05 + TMEM + TMA, split arithmetic = fp32-equivalent):
- * Z[R,M] = bias + X[R,Kd] W[M,Kd]^T.  ws = split weights [2, M, Kd] from tn_split_tf32
+ * Z[R,M] = bias + X[R,Kd] W[M,Kd]^T.  ws = split weights [3, M, Kd] from tn_split_tf32
  * (transpose = 1 reads W as [Kd, M]: the data-gradient GEMM); its layout is private to the library
- * (ws[0] = tf32(W); ws[1] = the packed bf16 correction rows, or tf32(W - ws[0]) under TN_TC_3XTF32=1).
- * nsplit: 3 = fp32-equivalent (tf32 hi*hi + one bf16 MMA carrying lo*hi + hi*lo; TN_TC_3XTF32=1: three tf32 MMAs)
- * or 1 (plain TF32).  Needs Kd %% 32 == 0 and M %% 128 == 0 (tn_gemm_tc_supported). */
+ * (ws[0] = tf32(W); ws[1] = tf32(W - ws[0]); ws[2] = the packed bf16 correction rows).
+ * nsplit: 3 = fp32-equivalent -- forward GEMMs run 3xTF32 (hi*hi + lo*hi + hi*lo), gradient GEMMs (TN_GEMM_GRAD) tf32
+ * hi*hi + one bf16 MMA carrying both corrections -- or 1 (plain TF32).  When the tile leaves TMEM columns free the main
+ * products of consecutive K ranges and the corrections accumulate in separate TMEM accumulators that the epilogue adds
+ * in fp32 (the tensor core's accumulate truncates).  Needs Kd %% 32 == 0 and M %% 128 == 0 (tn_gemm_tc_supported).
+ * stats (fp64 [2*M], written): per-channel sum / sum of squares of Z; needs scratch (tn_gemm_tc_scratch_floats). */
 int tn_gemm_tc_supported(int R, int Kd, int M);
 int tn_gemm_tc_set_trace(long long* buf);      /* debug: clock64 timeline of two CTAs (256 int64), NULL = off */
 int tn_split_tf32(const float* W, float* ws, int M, int Kd, int transpose, void* stream);
+long long tn_gemm_tc_scratch_floats(int R, int M);
 int tn_gemm_tc(const float* X, const float* ws, const float* bias, float* Z, double* stats, int R, int Kd, int M, int flags,
-               int nsplit, void* stream);
+               int nsplit, const tn_scratch* scratch, void* stream);
 /* Data gradient of a depthwise-separable block in ONE kernel: du = dZ[R,Co] W[Co,C] on the tensor
  * cores (ws = tn_split_tf32(W, transpose = 1)), then, in the epilogue, the transposed depthwise conv,
  * the BN/ReLU/dropout backward of the previous layer and all per-channel reductions:
@@ -105,9 +125,9 @@ int tn_colsum(const float* x, float* out, int R, int C, void* stream);          
 
 /* ---- train-mode BatchNorm folded INTO its producer / consumer kernels --------------------------
  * tn_bn_fold describes the nn.BatchNorm1d that follows a conv (src/modules.py:128, src/models.py:454,
- * 512).  The *_bn GEMM entry points accumulate the statistics of Z in their epilogue as before; the
- * last CTA to finish (device-wide ticket in `counter`, which must be zero on entry and is reset to zero)
- * folds them into (scale, shift), stores (mean, invstd) for the backward pass and updates the running
+ * 512).  The *_bn GEMM entry points produce the statistics of Z in their epilogue as before; the
+ * last CTA of each channel group to finish (device-wide tickets of the tn_scratch) adds the per-tile partial sums in tile
+ * order, folds them into (scale, shift), stores (mean, invstd) for the backward pass and updates the running
  * statistics (momentum, unbiased variance) and num_batches_tracked -- i.e. tn_bn_finalize without its
  * launch.  n = samples per channel (B*T). */
 typedef struct tn_bn_fold {
@@ -122,10 +142,9 @@ typedef struct tn_bn_fold {
   float* shift;                    /* [C] out: beta - mean * scale              */
   float* mean;                     /* [C] out (saved for backward)              */
   float* invstd;                   /* [C] out (saved for backward)              */
-  unsigned int* counter;           /* device scalar, zero on entry              */
 } tn_bn_fold;
 int tn_gemm_tc_bn(const float* X, const float* ws, const float* bias, float* Z, double* stats, const tn_bn_fold* bn, int R,
-                  int Kd, int M, int flags, int nsplit, void* stream);
+                  int Kd, int M, int flags, int nsplit, const tn_scratch* scratch, void* stream);
 /* Forward of a depthwise-separable block (+ the following train-mode BatchNorm's statistics / fold) in ONE kernel:
  * the GEMM's transform warps build the operand u = depthwise_K(act(z)) + b_dw from the raw z tile (BN/ReLU/dropout on load,
  * K-tap FIR, tf32 split) instead of reading a u tensor written by tn_dw_fwd; u_out (optional) receives u for the backward
@@ -134,9 +153,9 @@ int tn_gemm_tc_bn(const float* X, const float* ws, const float* bias, float* Z, 
 int tn_gemm_tc_dwfwd(const float* z, const float* ws, const float* dw_w, const float* dw_b, const float* scale,
                      const float* shift, int relu, float drop_p, const unsigned long long* seed, unsigned int layer,
                      const float* pw_bias, float* u_out, float* Z, double* stats, const tn_bn_fold* bn, int B, int T, int C,
-                     int Co, int K, void* stream);
+                     int Co, int K, const tn_scratch* scratch, void* stream);
 int tn_conv_gemm_simt_bn(const float* X, const float* W, const float* bias, float* Z, double* stats, const tn_bn_fold* bn,
-                         int B, int T, int Ci, int Co, int K, int flags, void* stream);
+                         int B, int T, int Ci, int Co, int K, int flags, const tn_scratch* scratch, void* stream);
 /* Backward of conv -> train-mode BatchNorm fold in one pass over the tensor (tn_bn_bwd_coef + tn_stats_bwd):
  * from dL/dscale, dL/dshift and the saved (mean, invstd) compute, per channel, dgamma, dbeta and the
  * statistics-path coefficients, then out = dz_direct + a[c] + b[c] * z and dbias[c] += sum_r out
@@ -165,7 +184,7 @@ int tn_dw_bwd(const float* du, const float* z, float* dz, const float* w, float*
 /* ---- BatchNorm1d folded into per-channel (scale, shift): nn.BatchNorm1d in
  *      ConvBlock1d (src/modules.py:128), skip (src/models.py:454), decoder
  *      (src/models.py:506,512) ------------------------------------------------------ */
-int tn_colstats(const float* x, double* stats, int R, int C, void* stream);          /* ACCUMULATED */
+int tn_colstats(const float* x, double* stats, int R, int C, void* stream);          /* written (fixed-order reduction) */
 int tn_bn_finalize(const double* stats, double n, const float* gamma, const float* beta, float* running_mean,
                    float* running_var, long long* num_batches_tracked, float momentum, float eps, int training,
                    float* scale, float* shift, float* mean, float* invstd, int C, void* stream);
@@ -186,15 +205,10 @@ int tn_tanh_bwd(const float* dh, const float* h, float* out, long long n, void* 
 
 /* ---- squeeze-excitation + mega-block tail: SqueezeExcitation.forward
  *      (src/modules.py:173-189), MegaBlock.forward (src/models.py:467-472) ----------- */
-/* m[b,c] += mean_t act(z3)[b,t,c]  (ACCUMULATED: the caller zeroes m; scale == NULL: z3 is already the activation) */
+/* m[b,c] = mean_t act(z3)[b,t,c]  (written, fixed-order reduction; scale == NULL: z3 is already the activation) */
 int tn_se_mean(const float* z3, float* m, const float* scale, const float* shift, int relu, float drop_p,
                const unsigned long long* seed, unsigned int layer, int B, int T, int C, void* stream);
-/* tn_se_mean + tn_se_mlp_fwd in one launch: the last block of each utterance's mean runs its MLP.  m ACCUMULATED (caller zeroes),
- * counters: B zeroed unsigned ints (device-wide tickets, reset by the kernel). */
-int tn_se_squeeze_excite(const float* z3, float* m, float* gate, unsigned int* counters, const float* W1, const float* W2,
-                         const float* scale, const float* shift, int relu, float drop_p, const unsigned long long* seed,
-                         unsigned int layer, int B, int T, int C, int Cr, void* stream);
-/* tn_tail_bwd1 + tn_se_mlp_bwd in one launch (dgate, dW1, dW2 ACCUMULATED; counters as above) */
+/* tn_tail_bwd1 + tn_se_mlp_bwd in one launch (dgate, dW1, dW2 ACCUMULATED; counters: B zeroed unsigned ints, device-wide tickets reset by the kernel) */
 int tn_tail_bwd1_mlp(const float* dout, const float* out, const float* z3, float* dgate, unsigned int* counters,
                      const float* gate, const float* m, const float* W1, const float* W2, float* dm, float* dW1, float* dW2,
                      const float* scale3, const float* shift3, float drop3, unsigned int layer3, float drop_o,

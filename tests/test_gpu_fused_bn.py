@@ -162,7 +162,8 @@ def test_model_step_uses_one_split_launch_and_arena_matches():
 
 
 def test_optional_launch_fusions_match_default():
-    """TN_FUSE_BLOCK_ENTRY / TN_FUSE_SE_MLP (off by default: measured slower) compute the same step."""
+    """TN_FUSE_BLOCK_ENTRY / TN_FUSE_SE_MLP (off by default: measured slower) compute the same step (forward bit for bit:
+    the fusions only touch the backward pass and the forward has no floating-point atomics)."""
     import titanet_oracle as O
     from titanet_b200 import _lib, _ops as ops, losses, models
     from cases import train_inputs
@@ -179,7 +180,7 @@ def test_optional_launch_fusions_match_default():
             _lib.COUNTS.clear()
             emb, preds, loss = model(x.cuda(), speakers=y.cuda())
             loss.backward()
-            assert (_lib.COUNTS.get("tn_se_squeeze_excite", 0) > 0) == fused and (_lib.COUNTS.get("tn_tail_bwd1_mlp", 0) > 0) == fused
+            assert (_lib.COUNTS.get("tn_tail_bwd1_mlp", 0) > 0) == fused
             res.append((float(loss), emb.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}))
     finally:
         ops.FUSE_BLOCK_ENTRY = ops.FUSE_SE_MLP = False
@@ -208,7 +209,7 @@ def test_depthwise_fused_into_gemm_operand(B, T, C, Co, K, lazy, p):
     try:
         for fused in (True, False):
             ops.TC_FUSE_DWFWD = fused
-            stats = torch.zeros(2 * Co, dtype=torch.float64, device="cuda")
+            stats = torch.empty(2 * Co, dtype=torch.float64, device="cuda")
             u, zo, _ = ops._dw_pw_forward(z.cuda(), sc.cuda() if lazy else None, sh.cuda() if lazy else None, dw_w.cuda(), dw_b.cuda(),
                                           pw_w.cuda(), pw_b.cuda(), seed if p > 0 else None, True, p, 7, B, T, stats, None)
             torch.cuda.synchronize()

@@ -14,14 +14,17 @@ def rel(a, b):
 
 
 def run_tc(x, w, bias, nsplit, transpose=False, want_stats=True, flags=0, z0=None):
-    from titanet_b200._lib import call, ptr
+    import ctypes
+    from titanet_b200._lib import LIB, call, ptr
+    from titanet_b200._ops import scratch
     R, Kd = x.shape
     M = w.shape[1] if transpose else w.shape[0]
-    ws = torch.empty(2, M, Kd, device="cuda")
+    ws = torch.empty(3, M, Kd, device="cuda")
     call("tn_split_tf32", ptr(w), ptr(ws), M, Kd, int(transpose))
     z = torch.empty(R, M, device="cuda") if z0 is None else z0
-    stats = torch.zeros(2 * M, device="cuda", dtype=torch.float64) if want_stats else None
-    call("tn_gemm_tc", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), R, Kd, M, flags, nsplit)
+    stats = torch.full((2 * M,), float("nan"), device="cuda", dtype=torch.float64) if want_stats else None   # written, not accumulated
+    sc, keep = scratch(x, LIB.query("tn_gemm_tc_scratch_floats", R, M)) if want_stats else (None, None)
+    call("tn_gemm_tc", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), R, Kd, M, flags, nsplit, ctypes.byref(sc) if sc is not None else None)
     torch.cuda.synchronize()
     return z, stats, ws
 
@@ -35,17 +38,21 @@ def test_gemm_tc_3xtf32_matches_fp64(R, Kd, M):
     b = torch.randn(M, generator=g)
     ref = x.double() @ w.double().t() + b.double()
     z, stats, ws = run_tc(x.cuda(), w.cuda(), b.cuda(), 3)
-    # weight split: ws[0] = tf32(w); ws[1] = per row and 32-wide K chunk, 64 bf16 = [bf16(hi) x32 | bf16(w - hi) x32]
-    # (the weight side of the bf16 correction MMA), or tf32(w - hi) under TN_TC_3XTF32=1
+    # weight split: ws[0] = tf32(w); ws[1] = tf32(w - hi) (3xTF32, forward GEMMs); ws[2] = per row and 32-wide K chunk, 64 bf16
+    # = [bf16(hi) x32 | bf16(w - hi) x32] (the weight side of the bf16 correction MMA of the gradient GEMMs)
     hi = ws[0].cpu()
     assert rel(hi, w) < 6e-4
-    if os.environ.get("TN_TC_3XTF32") == "1":
-        assert rel(ws[0] + ws[1], w) < 1e-6
-    else:
-        corr = ws[1].cpu().view(torch.bfloat16).view(M, Kd // 32, 64).float()
-        assert torch.equal(corr[:, :, :32].reshape(M, Kd), hi.bfloat16().float())
-        assert torch.equal(corr[:, :, 32:].reshape(M, Kd), (w - hi).bfloat16().float())
+    assert rel(ws[0] + ws[1], w) < 1e-6
+    corr = ws[2].cpu().view(torch.bfloat16).view(M, Kd // 32, 64).float()
+    assert torch.equal(corr[:, :, :32].reshape(M, Kd), hi.bfloat16().float())
+    assert torch.equal(corr[:, :, 32:].reshape(M, Kd), (w - hi).bfloat16().float())
     assert rel(z, ref) < 1e-5, "the split GEMM must be fp32-equivalent (torch fp32 itself sits at ~5e-7)"
+    # gradient flavour (TF32 + one bf16 correction MMA), same product
+    zg, _, _ = run_tc(x.cuda(), w.cuda(), b.cuda(), 3, want_stats=False, flags=8)
+    assert rel(zg, ref) < 2e-5
+    # bit-for-bit reproducible, statistics included (no floating-point atomics in the forward path)
+    z2, stats2, _ = run_tc(x.cuda(), w.cuda(), b.cuda(), 3)
+    assert torch.equal(z, z2) and torch.equal(stats, stats2)
     assert rel(stats[:M], ref.sum(0)) < 1e-4 * max(1.0, float(ref.abs().sum(0).max() / ref.sum(0).abs().max()))
     assert rel(stats[M:], (ref ** 2).sum(0)) < 1e-5
 

@@ -43,7 +43,7 @@ def parse_header(path: str | None = None) -> Dict[str, Tuple[str, List[Tuple[str
     text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
     text = re.sub(r"//[^\n]*", " ", text)
     protos = {}
-    for m in re.finditer(r"(const char\*|int)\s+(tn_\w+)\s*\(([^)]*)\)\s*;", text):
+    for m in re.finditer(r"(const char\*|long long|int)\s+(tn_\w+)\s*\(([^)]*)\)\s*;", text):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         alist = []
         if args and args != "void":
@@ -80,7 +80,8 @@ class _Lib:
                 fn = getattr(self._dll, name)
             except AttributeError as e:  # pragma: no cover
                 raise TitanetLibraryError(f"{LIB_PATH} does not export {name}") from e
-            fn.restype = ctypes.c_char_p if ret.startswith("const char") else ctypes.c_int
+            fn.restype = (ctypes.c_char_p if ret.startswith("const char") else
+                          ctypes.c_longlong if ret == "long long" else ctypes.c_int)
             fn.argtypes = [_to_ctype(t) for t, _ in args]
             self._fns[name] = fn
         return self
@@ -98,6 +99,14 @@ class _Lib:
         if rc != 0:
             raise TitanetLibraryError(f"{name} failed (code {rc}): {self.last_error()}")
 
+    def query(self, name: str, *args) -> int:
+        """Entry points that return a size (``long long``) instead of a status."""
+        fn = self._fns.get(name)
+        if fn is None:
+            self.load()
+            fn = self._fns[name]
+        return int(fn(*args))
+
 
 class TnBnFold(ctypes.Structure):
     """``tn_bn_fold`` of include/titanet_b200.h (train-mode BatchNorm folded by its producer kernel)."""
@@ -105,7 +114,12 @@ class TnBnFold(ctypes.Structure):
                 ("running_var", ctypes.c_void_p), ("num_batches_tracked", ctypes.c_void_p),
                 ("momentum", ctypes.c_float), ("eps", ctypes.c_float), ("n", ctypes.c_double),
                 ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p), ("mean", ctypes.c_void_p),
-                ("invstd", ctypes.c_void_p), ("counter", ctypes.c_void_p)]
+                ("invstd", ctypes.c_void_p)]
+
+
+class TnScratch(ctypes.Structure):
+    """``tn_scratch`` of include/titanet_b200.h (workspace + tickets of the atomics-free cross-block reductions)."""
+    _fields_ = [("parts", ctypes.c_void_p), ("parts_floats", ctypes.c_longlong), ("tickets", ctypes.c_void_p)]
 
 
 class TnSplitJob(ctypes.Structure):

@@ -20,10 +20,11 @@ from torch.autograd import Function
 import ctypes
 import weakref
 
-from ._lib import LIB, TnBnFold, TnSplitJob, call, ptr, require_cuda, stream
+from ._lib import LIB, TnBnFold, TnScratch, TnSplitJob, call, ptr, require_cuda, stream
 
 Tensor = torch.Tensor
-EPI_TANH, EPI_ACCUM = 1, 2
+EPI_TANH, EPI_ACCUM, GEMM_GRAD = 1, 2, 8
+TN_TICKETS = 64
 
 
 # ----------------------------------------------------------------------------
@@ -130,6 +131,23 @@ def seed_next(state: Tensor) -> Tensor:
     return out
 
 
+_TICKETS = {}
+
+
+def scratch(ref: Tensor, floats: int):
+    """(ctypes ``tn_scratch``, keep-alive tensor): an uninitialised workspace of ``floats`` fp32 elements plus the
+    zero-initialised ticket array of the current stream (kernels return it to zero, so one array serves every call on a
+    stream).  The deterministic statistics / split-K reductions of the conv-GEMM entry points need it."""
+    key = (ref.device, stream())
+    tk = _TICKETS.get(key)
+    if tk is None:
+        tk = torch.empty(TN_TICKETS, device=ref.device, dtype=torch.int32)
+        LIB.call("tn_zero", tk.data_ptr(), tk.numel() * 4, stream())
+        _TICKETS[key] = tk
+    parts = torch.empty(max(int(floats), 4), device=ref.device, dtype=torch.float32)
+    return TnScratch(parts.data_ptr(), parts.numel(), tk.data_ptr()), parts
+
+
 # ----------------------------------------------------------------------------
 # layout
 # ----------------------------------------------------------------------------
@@ -192,14 +210,14 @@ class SplitCache:
         dev = self.weights[0].device
         self.ptrs = [w.data_ptr() for w in self.weights]
         jobs, self.views, off = [], {}, 0
-        total = sum(4 * w.numel() for w in self.weights)
+        total = sum(6 * w.numel() for w in self.weights)
         self.buf = torch.empty(total, device=dev, dtype=torch.float32)
         for i, w in enumerate(self.weights):
             Co, Ci = w.shape[0], w.shape[1]
             n = Co * Ci
-            fwd = self.buf[off:off + 2 * n].view(2, Co, Ci)
-            bwd = self.buf[off + 2 * n:off + 4 * n].view(2, Ci, Co)
-            off += 4 * n
+            fwd = self.buf[off:off + 3 * n].view(3, Co, Ci)
+            bwd = self.buf[off + 3 * n:off + 6 * n].view(3, Ci, Co)
+            off += 6 * n
             jobs.append(TnSplitJob(w.data_ptr(), fwd.data_ptr(), Co, Ci, 0, 0))
             jobs.append(TnSplitJob(w.data_ptr(), bwd.data_ptr(), Ci, Co, 1, 0))
             self.views[id(w)] = (i, fwd, bwd)
@@ -233,24 +251,33 @@ _SPLITS = weakref.WeakValueDictionary()
 
 
 def cached_splits(w: Tensor):
-    """(ws_fwd [2, Co, Ci], ws_dgrad [2, Ci, Co]) of a weight refreshed this step, else None."""
+    """(ws_fwd [3, Co, Ci], ws_dgrad [3, Ci, Co]) of a weight refreshed this step, else None."""
     cache = _SPLITS.get(id(w))
     return cache.lookup(w) if cache is not None else None
 
 
-def make_bn_fold(gamma, beta, rm, rv, nbt, momentum, eps, n, scale, shift, mean, invstd, counter_ptr) -> TnBnFold:
+def make_bn_fold(gamma, beta, rm, rv, nbt, momentum, eps, n, scale, shift, mean, invstd) -> TnBnFold:
     return TnBnFold(ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(nbt), float(momentum), float(eps), float(n), ptr(scale),
-                    ptr(shift), ptr(mean), ptr(invstd), counter_ptr)
+                    ptr(shift), ptr(mean), ptr(invstd))
 
 
 def _gemm_tc(x, w2, bias, z, stats, R, Kd, M, transpose, flags, nsplit, tag, ws=None, bn=None):
     if ws is None:
-        ws = torch.empty((2, M, Kd), device=x.device, dtype=torch.float32)
+        ws = torch.empty((3, M, Kd), device=x.device, dtype=torch.float32)
         call("tn_split_tf32", ptr(w2), ptr(ws), M, Kd, int(transpose))
+    sc, keep = scratch(x, LIB.query("tn_gemm_tc_scratch_floats", R, M)) if stats is not None else (None, None)
+    scp = ctypes.byref(sc) if sc is not None else None
     if bn is not None:
-        call("tn_gemm_tc_bn", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), ctypes.byref(bn), R, Kd, M, flags, nsplit, tag=tag)
+        call("tn_gemm_tc_bn", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), ctypes.byref(bn), R, Kd, M, flags, nsplit, scp, tag=tag)
     else:
-        call("tn_gemm_tc", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), R, Kd, M, flags, nsplit, tag=tag)
+        call("tn_gemm_tc", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), R, Kd, M, flags, nsplit, scp, tag=tag)
+
+
+def gemm_tc_raw(x, ws, bias, z, stats, R, Kd, M, flags, nsplit):
+    """``tn_gemm_tc`` on raw tensors with the scratch it needs (tools / kernel tests)."""
+    sc, keep = scratch(x, LIB.query("tn_gemm_tc_scratch_floats", R, M)) if stats is not None else (None, None)
+    call("tn_gemm_tc", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), R, Kd, M, flags, nsplit,
+         ctypes.byref(sc) if sc is not None else None)
 
 
 def _gemm_fwd(x, w3, bias, z, stats, B, T, transpose_w, flags, ws=None, bn=None):
@@ -258,17 +285,21 @@ def _gemm_fwd(x, w3, bias, z, stats, B, T, transpose_w, flags, ws=None, bn=None)
     Co, Ci, K = w3.shape
     R = B * T
     if transpose_w and _tc_ok(R, Co, Ci, K):
-        return _gemm_tc(x, w3, bias, z, stats, R, Co, Ci, 1, flags, TC_BWD_NSPLIT, f"dgrad R{R} Ci{Co} Co{Ci} K1", ws=ws)
+        return _gemm_tc(x, w3, bias, z, stats, R, Co, Ci, 1, flags | GEMM_GRAD, TC_BWD_NSPLIT, f"dgrad R{R} Ci{Co} Co{Ci} K1", ws=ws)
     if not transpose_w and _tc_ok(R, Ci, Co, K):
         return _gemm_tc(x, w3, bias, z, stats, R, Ci, Co, 0, flags, TC_FWD_NSPLIT, f"fwd R{R} Ci{Ci} Co{Co} K1", ws=ws, bn=bn)
+    co_out, ci_red = (Ci, Co) if transpose_w else (Co, Ci)
+    need = LIB.query("tn_conv_gemm_simt_scratch_floats", B, T, ci_red, co_out, K, flags, 1 if stats is not None else 0)
+    sc, keep = scratch(x, need) if need > 0 else (None, None)
+    scp = ctypes.byref(sc) if sc is not None else None
     if transpose_w:
-        call("tn_conv_gemm_simt", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), B, T, Co, Ci, K, 1, flags,
+        call("tn_conv_gemm_simt", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), B, T, Co, Ci, K, 1, flags, scp,
              tag=f"dgrad R{B * T} Ci{Co} Co{Ci} K{K}")
     elif bn is not None:
-        call("tn_conv_gemm_simt_bn", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), ctypes.byref(bn), B, T, Ci, Co, K, flags,
+        call("tn_conv_gemm_simt_bn", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), ctypes.byref(bn), B, T, Ci, Co, K, flags, scp,
              tag=f"fwd R{B * T} Ci{Ci} Co{Co} K{K}")
     else:
-        call("tn_conv_gemm_simt", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), B, T, Ci, Co, K, 0, flags,
+        call("tn_conv_gemm_simt", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), B, T, Ci, Co, K, 0, flags, scp,
              tag=f"fwd R{B * T} Ci{Ci} Co{Co} K{K}")
 
 
@@ -294,7 +325,7 @@ class ConvGemm(Function):
         Co, Ci, K = w3.shape
         assert x.shape == (B * T, Ci), (x.shape, B, T, Ci)
         z = empty((B * T, Co), x)
-        stats = zeros((2 * Co,), x, torch.float64) if want_stats else None
+        stats = empty((2 * Co,), x, torch.float64) if want_stats else None
         sp = cached_splits(w)
         _gemm_fwd(x, w3, bias, z, stats, B, T, 0, EPI_TANH if tanh else 0, ws=sp[0] if sp else None)
         ctx.ws_t = sp[1] if sp else None
@@ -337,8 +368,8 @@ def conv_gemm(x, w, bias, B, T, want_stats=False, tanh=False):
 
 
 def _bn_forward_buffers(Co: int, ref: Tensor):
-    """(stats+ticket fp64 [2Co+1], fold [4, Co] = scale | shift | mean | invstd)."""
-    stats = zeros((2 * Co + 1,), ref, torch.float64)
+    """(stats fp64 [2Co] (written by the kernel), fold [4, Co] = scale | shift | mean | invstd)."""
+    stats = empty((2 * Co,), ref, torch.float64)
     fold = empty((4, Co), ref)
     return stats, fold
 
@@ -370,8 +401,7 @@ class ConvGemmBN(Function):
         z = empty((B * T, Co), x)
         stats, fold = _bn_forward_buffers(Co, x)
         n = float(B * T)
-        bn = make_bn_fold(gamma, beta, rm, rv, nbt, momentum, eps, n, fold[0], fold[1], fold[2], fold[3],
-                          stats.data_ptr() + 16 * Co)
+        bn = make_bn_fold(gamma, beta, rm, rv, nbt, momentum, eps, n, fold[0], fold[1], fold[2], fold[3])
         sp = cached_splits(w)
         _gemm_fwd(x, w3, bias, z, stats, B, T, 0, 0, ws=sp[0] if sp else None, bn=bn)
         ctx.ws_t = sp[1] if sp else None
@@ -416,7 +446,7 @@ class ColStats(Function):
     def forward(ctx, x):
         x = _c(x)
         R, C = x.shape
-        stats = zeros((2 * C,), x, torch.float64)
+        stats = empty((2 * C,), x, torch.float64)
         call("tn_colstats", ptr(x), ptr(stats), R, C)
         ctx.save_for_backward(x)
         return stats
@@ -539,7 +569,8 @@ TC_FUSE_DWBWD = __import__("os").environ.get("TN_FUSE_DWBWD", "1") != "0"     # 
 # Two launch fusions, measured on the graph-replayed TitaNet-S step and OFF by default because they lose:
 #   TN_FUSE_BLOCK_ENTRY=1  first sub-block + skip branch as one autograd node, the skip data gradient accumulated in the GEMM
 #                          epilogue (red.global.add) instead of an add kernel:   10.21 -> 10.24 ms
-#   TN_FUSE_SE_MLP=1       SE MLP forward / backward run by the last block of se_mean / tail_bwd1 (-34 launches): 10.21 -> 10.32 ms
+#   TN_FUSE_SE_MLP=1       SE MLP backward run by the last block of tail_bwd1 (-17 launches; with the forward twin, removed in
+#                          round 2 because its mean used float atomics: 10.21 -> 10.32 ms)
 # (inside a CUDA graph a launch boundary costs less than the serial tail the fused kernels add)
 import os as _os
 FUSE_BLOCK_ENTRY = _os.environ.get("TN_FUSE_BLOCK_ENTRY", "0") == "1"
@@ -565,11 +596,12 @@ def _dw_pw_forward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, relu, p, layer
     if (TC_FUSE_DWFWD and TC_FWD_NSPLIT == 3 and _tc_ok(R, C, Co, pw3.shape[2]) and K % 2 == 1 and K <= 7 and (R + 16) * C < 2 ** 32):
         ws = sp[0] if sp else None
         if ws is None:
-            ws = torch.empty((2, Co, C), device=z.device, dtype=torch.float32)
+            ws = torch.empty((3, Co, C), device=z.device, dtype=torch.float32)
             call("tn_split_tf32", ptr(pw3), ptr(ws), Co, C, 0)
+        sc, keep = scratch(z, LIB.query("tn_gemm_tc_scratch_floats", R, Co)) if stats is not None else (None, None)
         call("tn_gemm_tc_dwfwd", ptr(z), ptr(ws), ptr(dw_w), ptr(dw_b), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed),
              int(layer), ptr(pw_b), ptr(u), ptr(zo), ptr(stats), ctypes.byref(bn) if bn is not None else None, B, T, C, Co, K,
-             tag=f"dw+fwd R{R} Ci{C} Co{Co} K1")
+             ctypes.byref(sc) if sc is not None else None, tag=f"dw+fwd R{R} Ci{C} Co{Co} K1")
     else:
         call("tn_dw_fwd", ptr(z), ptr(u), ptr(dw_w), ptr(dw_b), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer),
              B, T, C, K)
@@ -590,7 +622,7 @@ class DwPw(Function):
         C, K = dw_w.shape[0], dw_w.shape[-1]
         Co = pw_w.shape[0]
         assert z.shape == (B * T, C)
-        stats = zeros((2 * Co,), z, torch.float64) if want_stats else None
+        stats = empty((2 * Co,), z, torch.float64) if want_stats else None
         u, zo, ctx.ws_t = _dw_pw_forward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, relu, p, layer, B, T, stats, None)
         ctx.save_for_backward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, u, zo if want_stats else None)
         ctx.meta = (relu, p, layer, B, T, want_stats)
@@ -629,7 +661,7 @@ def _dwpw_dgrad(dz, pw3, ws_t, z, scale, shift, dw_w, dw_b, seed, relu, p, layer
             and (R + 16) * C < 2 ** 32):
         ws = ws_t
         if ws is None:
-            ws = torch.empty((2, C, Co), device=z.device, dtype=torch.float32)
+            ws = torch.empty((3, C, Co), device=z.device, dtype=torch.float32)
             call("tn_split_tf32", ptr(pw3), ptr(ws), C, Co, 1)
         call("tn_gemm_tc_dwbwd", ptr(dz), ptr(ws), ptr(z), ptr(dzp), ptr(dw_w), ptr(ddw), ptr(ddb), ptr(dscale), ptr(dshift),
              ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer), B, T, Co, C, K, TC_BWD_NSPLIT,
@@ -657,8 +689,7 @@ class DwPwBN(Function):
         assert z.shape == (B * T, C)
         stats, fold = _bn_forward_buffers(Co, z)
         n = float(B * T)
-        bn = make_bn_fold(gamma, beta, rm, rv, nbt, momentum, eps, n, fold[0], fold[1], fold[2], fold[3],
-                          stats.data_ptr() + 16 * Co)
+        bn = make_bn_fold(gamma, beta, rm, rv, nbt, momentum, eps, n, fold[0], fold[1], fold[2], fold[3])
         u, zo, ctx.ws_t = _dw_pw_forward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, relu, p, layer, B, T, stats, bn)
         ctx.save_for_backward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, u, zo, gamma, fold)
         ctx.meta = (relu, p, layer, B, T, n)
@@ -697,14 +728,12 @@ class BlockEntryBN(Function):
         # skip branch first, like the reference's forward (src/models.py:469)
         s = empty((R, Cs), z)
         st_s, fold_s = _bn_forward_buffers(Cs, z)
-        bn_s = make_bn_fold(gs, bs, rms, rvs, nbts, moms, epss, n, fold_s[0], fold_s[1], fold_s[2], fold_s[3],
-                            st_s.data_ptr() + 16 * Cs)
+        bn_s = make_bn_fold(gs, bs, rms, rvs, nbts, moms, epss, n, fold_s[0], fold_s[1], fold_s[2], fold_s[3])
         sp_s = cached_splits(sk_w)
         sk3 = sk_w if sk_w.dim() == 3 else sk_w.unsqueeze(-1)
         _gemm_fwd(z, sk3, sk_b, s, st_s, B, T, 0, 0, ws=sp_s[0] if sp_s else None, bn=bn_s)
         st_1, fold_1 = _bn_forward_buffers(Co, z)
-        bn_1 = make_bn_fold(g1, b1, rm1, rv1, nbt1, mom1, eps1, n, fold_1[0], fold_1[1], fold_1[2], fold_1[3],
-                            st_1.data_ptr() + 16 * Co)
+        bn_1 = make_bn_fold(g1, b1, rm1, rv1, nbt1, mom1, eps1, n, fold_1[0], fold_1[1], fold_1[2], fold_1[3])
         u, zo, ctx.ws_t1 = _dw_pw_forward(z, None, None, dw_w, dw_b, pw_w, pw_b, None, False, 0.0, 0, B, T, st_1, bn_1)
         ctx.ws_ts = sp_s[1] if sp_s else None
         ctx.save_for_backward(z, dw_w, dw_b, pw_w, pw_b, g1, sk_w, sk_b, gs, u, zo, s, fold_1, fold_s)
@@ -744,15 +773,10 @@ class SETail(Function):
         z3, sc3, sh3, s, scs, shs, W1, W2 = map(_c, (z3, sc3, sh3, s, scs, shs, W1, W2))
         C = z3.shape[1]
         Cr = W1.shape[0]
-        m, gate = zeros((B, C), z3), empty((B, C), z3)
+        m, gate = empty((B, C), z3), empty((B, C), z3)
         out = empty(z3.shape, z3)
-        if FUSE_SE_MLP:
-            tickets = zeros((B,), z3, torch.int32)
-            call("tn_se_squeeze_excite", ptr(z3), ptr(m), ptr(gate), ptr(tickets), ptr(W1), ptr(W2), ptr(sc3), ptr(sh3), 1, float(p3),
-                 ptr(seed), int(layer3), B, T, C, Cr)
-        else:
-            call("tn_se_mean", ptr(z3), ptr(m), ptr(sc3), ptr(sh3), 1, float(p3), ptr(seed), int(layer3), B, T, C)
-            call("tn_se_mlp_fwd", ptr(m), ptr(W1), ptr(W2), ptr(gate), B, C, Cr)
+        call("tn_se_mean", ptr(z3), ptr(m), ptr(sc3), ptr(sh3), 1, float(p3), ptr(seed), int(layer3), B, T, C)
+        call("tn_se_mlp_fwd", ptr(m), ptr(W1), ptr(W2), ptr(gate), B, C, Cr)
         call("tn_tail_fwd", ptr(z3), ptr(s), ptr(gate), ptr(out), ptr(sc3), ptr(sh3), float(p3), int(layer3), ptr(scs), ptr(shs),
              float(p_o), int(layer_o), ptr(seed), B, T, C)
         ctx.save_for_backward(z3, sc3, sh3, s, scs, shs, W1, W2, seed, m, gate, out)
@@ -792,7 +816,7 @@ class MeanT(Function):
     def forward(ctx, x, B: int, T: int):
         x = _c(x)
         C = x.shape[1]
-        m = zeros((B, C), x)
+        m = empty((B, C), x)
         call("tn_se_mean", ptr(x), ptr(m), None, None, 0, 0.0, None, 0, B, T, C)
         ctx.meta = (B, T, C)
         return m

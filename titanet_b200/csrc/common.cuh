@@ -229,43 +229,79 @@ __device__ __forceinline__ float4 tn_fma4(float4 a, float4 b, float4 c) {
 __device__ __forceinline__ float4 tn_zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
 // ---------------------------------------------------------------------------
-// Train-mode BatchNorm fold performed by the LAST block of the kernel that produced the statistics
-// (device-wide ticket).  Every thread of every block calls this after its statistics atomics were
-// issued.  nn.BatchNorm1d semantics (biased variance for normalisation, unbiased for running_var).
+// Deterministic per-channel statistics + train-mode BatchNorm fold by the LAST block of a channel group.
+//
+// Every block of the producing kernel stores its per-channel partial sums (sum z, sum z^2 over ITS rows, fp32, computed in
+// a fixed order) to parts[row tile][which][C_total]; blocks that share a channel range [c0, c0 + nC) form a "group" with
+// one device-wide ticket.  The last block of a group to finish adds the partials of all row tiles IN TILE ORDER (fp64),
+// writes the totals to stats[c] / stats[C_total + c] and, if `f` is given, folds them into (scale, shift), stores
+// (mean, invstd) and updates the running statistics.  No floating-point atomics: the result does not depend on the order
+// in which the blocks ran, so two runs of a forward pass agree bit for bit.  nn.BatchNorm1d semantics (biased variance for
+// normalisation, unbiased for running_var).  Every thread of every block calls this after its partials were stored;
+// `sm` = at least 8 * 2 * nC doubles of shared memory nobody else touches any more.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void tn_bn_fold_last(const tn_bn_fold& f, const double* stats, int C, unsigned int total_blocks) {
+__device__ __forceinline__ void tn_stats_finish(const tn_bn_fold* f, double* stats, const float* parts, int ntiles, int C_total,
+                                                int c0, int nC, unsigned int* ticket, unsigned int blocks_in_group,
+                                                bool bump_nbt, double* sm) {
   __shared__ unsigned int s_is_last;
-  __threadfence();                                   // this thread's atomics before the block's ticket
+  __threadfence();                                   // this thread's partials before the block's ticket
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int t = atomicAdd(f.counter, 1u);
-    s_is_last = (t == total_blocks - 1) ? 1u : 0u;
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_is_last = (t == blocks_in_group - 1) ? 1u : 0u;
+    if (s_is_last) *ticket = 0u;                     // ready for the next launch / graph replay
   }
   __syncthreads();
   if (!s_is_last) return;
   __threadfence();
-  const double n = f.n;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const double m = __ldcg(stats + c) / n;
-    double var = __ldcg(stats + C + c) / n - m * m;
-    if (var < 0.0) var = 0.0;
-    const float mean = (float)m;
-    const float invstd = (float)(1.0 / sqrt(var + (double)f.eps));
-    if (f.running_mean) {
-      const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
-      f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
-      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+  const int nthreads = blockDim.x * blockDim.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nq = nC >> 2, cols = 2 * nq;             // (which, channel quad) columns of the partial table
+  int slices = nthreads / cols;
+  if (slices > 8) slices = 8;
+  if (slices < 1) slices = 1;
+  for (int col = tid; col < cols * slices; col += nthreads) {     // one pass when cols * slices <= nthreads
+    const int slice = col / cols, cc = col - slice * cols;
+    const int which = cc / nq, q = cc - which * nq;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const float* src = parts + (size_t)which * C_total + c0 + 4 * q;
+#pragma unroll 4
+    for (int t = slice; t < ntiles; t += slices) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)t * 2 * C_total));
+      a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
     }
-    const float sc = __ldg(f.gamma + c) * invstd;
-    f.scale[c] = sc;
-    f.shift[c] = __ldg(f.beta + c) - mean * sc;
-    f.mean[c] = mean;
-    f.invstd[c] = invstd;
+    double* dst = sm + ((size_t)slice * 2 + which) * nC + 4 * q;
+    dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
   }
-  if (threadIdx.x == 0) {
-    *f.counter = 0u;                                 // ready for the next launch / graph replay
-    if (f.num_batches_tracked) *f.num_batches_tracked += 1;
+  __syncthreads();
+  for (int cl = tid; cl < nC; cl += nthreads) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int sl = 0; sl < slices; ++sl) {
+      s1 += sm[((size_t)sl * 2 + 0) * nC + cl];
+      s2 += sm[((size_t)sl * 2 + 1) * nC + cl];
+    }
+    const int c = c0 + cl;
+    if (stats) { stats[c] = s1; stats[C_total + c] = s2; }
+    if (f) {
+      const double n = f->n;
+      const double m = s1 / n;
+      double var = s2 / n - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mean = (float)m;
+      const float invstd = (float)(1.0 / sqrt(var + (double)f->eps));
+      if (f->running_mean) {
+        const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+        f->running_mean[c] = (1.f - f->momentum) * f->running_mean[c] + f->momentum * mean;
+        f->running_var[c] = (1.f - f->momentum) * f->running_var[c] + f->momentum * (float)unbiased;
+      }
+      const float sc = __ldg(f->gamma + c) * invstd;
+      f->scale[c] = sc;
+      f->shift[c] = __ldg(f->beta + c) - mean * sc;
+      f->mean[c] = mean;
+      f->invstd[c] = invstd;
+    }
   }
+  if (tid == 0 && f && bump_nbt && f->num_batches_tracked) *f->num_batches_tracked += 1;
 }
 
 // ---------------------------------------------------------------------------

@@ -176,28 +176,40 @@ extern "C" int tn_act_bwd(const float* dy, const float* z, float* dz, float* dsc
 // ---------------------------------------------------------------------------
 // per-channel sum / sum of squares of an [R, C] tensor (fp64 accumulators)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(TN_EW_THREADS) colstats_kernel(const float* __restrict__ x, double* __restrict__ stats, int R, int C, int rpb) {
+// One block owns 64 channels (16 quads x 16 row lanes) and walks ALL rows: the lanes' partial sums are combined in a fixed
+// order, so the statistics are reproducible bit for bit (no atomics, no zero-initialised output).  Used for small R (the
+// decoder's BatchNorms over the batch axis, src/models.py:506,512); the conv outputs get their statistics from the GEMM
+// epilogues (tn_stats_finish).
+__global__ void __launch_bounds__(TN_EW_THREADS) colstats_kernel(const float* __restrict__ x, double* __restrict__ stats, int R, int C) {
   tn_grid_dep_sync();
-  __shared__ float4 red[TN_EW_THREADS];
-  TnTile tl = tn_tile(C);
-  int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
-  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
-    int q = qb + tl.q0;
-    float4 s1 = tn_zero4(), s2 = tn_zero4();
-    if (tl.active && q < tl.Q)
-      for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
-        float4 v = tn_ld4(x + (size_t)r * C + 4 * q);
-        s1 = s1 + v;
-        s2 = tn_fma4(v, v, s2);
-      }
-    tn_lane_reduce_atomic(tl, s1, q, stats, red);
-    tn_lane_reduce_atomic(tl, s2, q, stats + C, red);
+  __shared__ double red[2][16][64];
+  const int q = threadIdx.x & 15, lane = threadIdx.x >> 4;
+  const int c = blockIdx.x * 64 + 4 * q;
+  double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c < C) {
+    for (int r = lane; r < R; r += 16) {
+      const float4 v = tn_ld4(x + (size_t)r * C + c);
+      s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+      s2[0] += (double)v.x * v.x; s2[1] += (double)v.y * v.y; s2[2] += (double)v.z * v.z; s2[3] += (double)v.w * v.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { red[0][lane][4 * q + i] = s1[i]; red[1][lane][4 * q + i] = s2[i]; }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
+    const int cc = blockIdx.x * 64 + ch;
+    if (cc < C) {
+      double a = 0.0;
+#pragma unroll
+      for (int l = 0; l < 16; ++l) a += red[which][l][ch];
+      stats[(size_t)which * C + cc] = a;
+    }
   }
 }
 extern "C" int tn_colstats(const float* x, double* stats, int R, int C, void* stream) {
   TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0 && tn_aligned16(x), "colstats: need C %% 4 == 0 and aligned x (R=%d C=%d)", R, C);
-  int rpb = rows_per_block(R);
-  tn_launch(colstats_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, x, stats, R, C, rpb);
+  tn_launch(colstats_kernel, tn_cdiv(C, 64), TN_EW_THREADS, 0, stream, x, stats, R, C);
   TN_LAUNCH_CHECK("colstats_kernel");
   return TN_OK;
 }

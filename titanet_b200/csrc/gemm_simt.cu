@@ -22,18 +22,22 @@
 __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict__ X, const float* __restrict__ W,
                                                         const float* __restrict__ bias, float* __restrict__ Z,
                                                         double* __restrict__ stats, int R, int T, int Ci, int Co, int K,
-                                                        int transpose_w, int flags, int kk_per_split, tn_bn_fold bn, int has_bn) {
+                                                        int transpose_w, int flags, int kk_per_split, tn_bn_fold bn, int has_bn,
+                                                        float* __restrict__ parts, unsigned int* __restrict__ tickets) {
   tn_grid_dep_sync();
   __shared__ float As[GK][GM + 4];
   __shared__ float Bs[GK][GN + 4];
-  __shared__ float red1[16][GN], red2[16][GN];
+  __shared__ __align__(16) double fin[8 * 2 * GN];      // tn_stats_finish scratch; its head doubles as red1 / red2
+  float (*red1)[GN] = reinterpret_cast<float (*)[GN]>(fin);
+  float (*red2)[GN] = reinterpret_cast<float (*)[GN]>(reinterpret_cast<float*>(fin) + 16 * GN);
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int r0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
   const int pad = K / 2;
   const int KK = K * Ci;                // reduction length; kk = tap * Ci + ci
-  // split-K (skinny problems, e.g. the decoder's [B, 3072] x [3072, 192]): blockIdx.z owns a slice of the
-  // reduction and adds its partial tile to a zero-initialised Z with atomics (flags == 0, no stats).
+  // split-K (skinny problems, e.g. the decoder's [B, 3072] x [3072, 192]): blockIdx.z owns a slice of the reduction and
+  // stores its partial tile to parts[split][R][Co]; the last block of an output tile (ticket) adds the partials in split
+  // order, so the result does not depend on the order the blocks ran in (flags == 0, no stats).
   const bool splitk = gridDim.z > 1;
   const int kk_begin = blockIdx.z * kk_per_split, kk_end = min(KK, kk_begin + kk_per_split);
   float acc[4][4];
@@ -83,6 +87,45 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
     __syncthreads();
   }
 
+  if (splitk) {
+    float* mine = parts + (size_t)blockIdx.z * R * Co;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty * 4 + i;
+      if (r >= R) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        if (n < Co) mine[(size_t)r * Co + n] = acc[i][j];
+      }
+    }
+    __shared__ unsigned int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int* tk = tickets + blockIdx.y * gridDim.x + blockIdx.x;
+      const unsigned int t = atomicAdd(tk, 1u);
+      s_last = (t == gridDim.z - 1) ? 1u : 0u;
+      if (s_last) *tk = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty * 4 + i;
+      if (r >= R) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        if (n >= Co) continue;
+        float v = bias ? __ldg(bias + n) : 0.f;
+        for (unsigned int z = 0; z < gridDim.z; ++z) v += __ldcg(parts + ((size_t)z * R + r) * Co + n);
+        Z[(size_t)r * Co + n] = v;
+      }
+    }
+    return;
+  }
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -92,9 +135,8 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= Co) continue;
-      float v = acc[i][j] + ((bias && blockIdx.z == 0) ? __ldg(bias + n) : 0.f);
+      float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
       float* zp = Z + (size_t)r * Co + n;
-      if (splitk) { atomicAdd(zp, v); continue; }
       if (flags & TN_EPI_TANH) v = tanhf(v);
       if (flags & TN_EPI_ACCUM) v += *zp;
       *zp = v;
@@ -102,22 +144,26 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
       s2[j] = fmaf(v, v, s2[j]);
     }
   }
-  if (stats && !splitk) {
+  if (stats) {
+    // per-channel partial sums of this row tile in a fixed order -> parts[row tile][which][Co]; the last block of this
+    // 64-channel group adds the row tiles in order and (has_bn) folds the BatchNorm (tn_stats_finish)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { red1[ty][tx * 4 + j] = s1[j]; red2[ty][tx * 4 + j] = s2[j]; }
     __syncthreads();
     if (tid < GN) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int y = 0; y < 16; ++y) { a += red1[y][tid]; b += red2[y][tid]; }
       const int n = n0 + tid;
       if (n < Co) {
-        float a = 0.f, b = 0.f;
-#pragma unroll
-        for (int y = 0; y < 16; ++y) { a += red1[y][tid]; b += red2[y][tid]; }
-        atomicAdd(stats + n, (double)a);
-        atomicAdd(stats + Co + n, (double)b);
+        parts[((size_t)blockIdx.x * 2 + 0) * Co + n] = a;
+        parts[((size_t)blockIdx.x * 2 + 1) * Co + n] = b;
       }
     }
+    const int nC = min(GN, Co - n0);
+    tn_stats_finish(has_bn ? &bn : nullptr, stats, parts, (int)gridDim.x, Co, n0, nC, tickets + blockIdx.y, gridDim.x,
+                    blockIdx.y == 0, fin);
   }
-  if (has_bn) tn_bn_fold_last(bn, stats, Co, gridDim.x * gridDim.y);   // never with split-K (the host folds separately)
 }
 
 // dW[co, ci, k] += sum_r dZ[r, co] * X[r + k - pad, ci]; rows split over blockIdx.z
@@ -194,29 +240,54 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
   }
 }
 
+// split-K plan shared by the launcher and the scratch query
+static void conv_gemm_plan(long long R, int Ci, int Co, int K, int flags, int* splits_out, int* kps_out) {
+  const long long tiles = (long long)tn_cdiv(R, GM) * tn_cdiv(Co, GN);
+  const long long KK = (long long)K * Ci;
+  int splits = 1;
+  if (flags == 0 && KK >= 1024 && tiles * 4 <= tn_num_sms() && tiles <= TN_TICKETS) {
+    splits = tn_num_sms() / (int)tiles;
+    if (splits > KK / 128) splits = (int)(KK / 128);
+    if (splits < 1) splits = 1;
+  }
+  int kps = (int)(((KK + splits - 1) / splits + GK - 1) / GK * GK);
+  *splits_out = (int)((KK + kps - 1) / kps);
+  *kps_out = kps;
+}
+
+extern "C" long long tn_conv_gemm_simt_scratch_floats(int B, int T, int Ci, int Co, int K, int flags, int with_stats) {
+  if (B <= 0 || T <= 0 || Ci <= 0 || Co <= 0 || K <= 0) return 0;
+  const long long R = (long long)B * T;
+  int splits, kps;
+  conv_gemm_plan(R, Ci, Co, K, flags, &splits, &kps);
+  long long n = 0;
+  if (splits > 1) n = (long long)splits * R * Co;
+  else if (with_stats) n = (long long)tn_cdiv(R, GM) * 2 * Co;
+  return n;
+}
+
 static int conv_gemm_launch(const float* X, const float* W, const float* bias, float* Z, double* stats, const tn_bn_fold* bn,
-                            int B, int T, int Ci, int Co, int K, int transpose_w, int flags, void* stream) {
+                            int B, int T, int Ci, int Co, int K, int transpose_w, int flags, const tn_scratch* scratch, void* stream) {
   TN_REQUIRE(B > 0 && T > 0 && Ci > 0 && Co > 0 && K > 0 && (K & 1), "conv_gemm: bad shape B=%d T=%d Ci=%d Co=%d K=%d (odd K only)", B, T, Ci, Co, K);
   TN_REQUIRE(X && W && Z, "conv_gemm: null tensor");
   long long R = (long long)B * T;
   TN_REQUIRE(R < (1ll << 31) && tn_cdiv(Co, GN) <= 65535, "conv_gemm: shape too large");
   dim3 grid(tn_cdiv(R, GM), tn_cdiv(Co, GN));
-  const long long KK = (long long)K * Ci;
-  int splits = 1;
-  if (flags == 0 && KK >= 1024 && (long long)grid.x * grid.y * 4 <= tn_num_sms()) {
-    splits = tn_num_sms() / (int)(grid.x * grid.y);
-    if (splits > KK / 128) splits = (int)(KK / 128);
-    if (splits < 1) splits = 1;
-  }
-  int kps = (int)(((KK + splits - 1) / splits + GK - 1) / GK * GK);
-  splits = (int)((KK + kps - 1) / kps);
+  int splits, kps;
+  conv_gemm_plan(R, Ci, Co, K, flags, &splits, &kps);
   grid.z = splits;
-  if (splits > 1) TN_CUDA(cudaMemsetAsync(Z, 0, sizeof(float) * (size_t)R * Co, (cudaStream_t)stream));
+  const long long need = tn_conv_gemm_simt_scratch_floats(B, T, Ci, Co, K, flags, stats != nullptr);
+  if (need > 0) {
+    TN_REQUIRE(scratch && scratch->parts && scratch->tickets && scratch->parts_floats >= need,
+               "conv_gemm: needs a tn_scratch with %lld floats (tn_conv_gemm_simt_scratch_floats) and the ticket array", need);
+    TN_REQUIRE(splits > 1 || (int)grid.y <= TN_TICKETS, "conv_gemm: statistics of more than %d channels are not supported", TN_TICKETS * GN);
+  }
   tn_bn_fold f;
   memset(&f, 0, sizeof(f));
   const int fuse_bn = (bn && splits == 1) ? 1 : 0;
   if (fuse_bn) f = *bn;
-  tn_launch(conv_gemm_kernel, grid, 256, 0, stream, X, W, bias, Z, stats, (int)R, T, Ci, Co, K, transpose_w, flags, kps, f, fuse_bn);
+  tn_launch(conv_gemm_kernel, grid, 256, 0, stream, X, W, bias, Z, splits > 1 ? (double*)nullptr : stats, (int)R, T, Ci, Co, K,
+            transpose_w, flags, kps, f, fuse_bn, scratch ? scratch->parts : (float*)nullptr, scratch ? scratch->tickets : (unsigned int*)nullptr);
   TN_LAUNCH_CHECK("conv_gemm_kernel");
   if (splits > 1 && stats) {                       // split-K: statistics (and the fold) from the finished tensor
     int rc = tn_colstats(Z, stats, (int)R, Co, stream);
@@ -228,16 +299,17 @@ static int conv_gemm_launch(const float* X, const float* W, const float* bias, f
 }
 
 extern "C" int tn_conv_gemm_simt(const float* X, const float* W, const float* bias, float* Z, double* stats, int B, int T,
-                                 int Ci, int Co, int K, int transpose_w, int flags, void* stream) {
-  return conv_gemm_launch(X, W, bias, Z, stats, nullptr, B, T, Ci, Co, K, transpose_w, flags, stream);
+                                 int Ci, int Co, int K, int transpose_w, int flags, const tn_scratch* scratch, void* stream) {
+  return conv_gemm_launch(X, W, bias, Z, stats, nullptr, B, T, Ci, Co, K, transpose_w, flags, scratch, stream);
 }
 
 extern "C" int tn_conv_gemm_simt_bn(const float* X, const float* W, const float* bias, float* Z, double* stats,
-                                    const tn_bn_fold* bn, int B, int T, int Ci, int Co, int K, int flags, void* stream) {
+                                    const tn_bn_fold* bn, int B, int T, int Ci, int Co, int K, int flags, const tn_scratch* scratch,
+                                    void* stream) {
   TN_REQUIRE(bn && stats, "conv_gemm_simt_bn: the fold needs the statistics buffer");
-  TN_REQUIRE(bn->gamma && bn->beta && bn->scale && bn->shift && bn->mean && bn->invstd && bn->counter && bn->n >= 1.0,
+  TN_REQUIRE(bn->gamma && bn->beta && bn->scale && bn->shift && bn->mean && bn->invstd && bn->n >= 1.0,
              "conv_gemm_simt_bn: incomplete tn_bn_fold");
-  return conv_gemm_launch(X, W, bias, Z, stats, bn, B, T, Ci, Co, K, 0, flags, stream);
+  return conv_gemm_launch(X, W, bias, Z, stats, bn, B, T, Ci, Co, K, 0, flags, scratch, stream);
 }
 
 extern "C" int tn_conv_wgrad_simt(const float* dZ, const float* X, float* dW, float* dbias, int B, int T, int Ci, int Co, int K,

@@ -183,15 +183,26 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
 // Epilogue of one 128-channel accumulator tile: TMEM -> registers -> (+bias, tanh, +=) -> global.
 // This thread owns output channel `zp[0]`; column j of the tile is activation row j (stride ld).
 // Rows >= nvalid (tail tile) are masked by predication, not branches.
+// nacc > 1: the tile was accumulated in `nacc` TMEM accumulators `astride` columns apart (K-chunked main products + one
+// accumulator for the small correction products, see the MMA issuer); they are added here in fp32 (round to nearest).
 template <bool TANH, bool ACCUM, bool FULL>
 __device__ __forceinline__ void tc_epilogue(uint32_t tbase, float* __restrict__ zp, size_t ld, int BN, int nvalid, float bv,
-                                            float& s1, float& s2, int half, int nparts = 2) {
+                                            float& s1, float& s2, int half, int nparts = 2, int nacc = 1, int astride = 0) {
   for (int c0 = 32 * half; c0 < BN; c0 += 32 * nparts) {   // the `nparts` warps of a lane quadrant alternate 32-column chunks
     float v[32];
     const bool two = c0 + 16 < BN;                   // BN is a multiple of 16
     tc_ld16_issue(tbase + c0, v);
     if (two) tc_ld16_issue(tbase + c0 + 16, v + 16);
     tc_ld_wait(v, 32);
+    for (int a = 1; a < nacc; ++a) {                 // warp-uniform
+      float w[32];
+      tc_ld16_issue(tbase + a * astride + c0, w);
+      if (two) tc_ld16_issue(tbase + a * astride + c0 + 16, w + 16);
+      tc_ld_wait(w, 32);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < 16 || two) v[j] += w[j];
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       if (j >= 16 && !two) break;
@@ -217,7 +228,10 @@ struct TcParams {
   float* Z;
   double* stats;
   int R, Kd, M_total, BN, stages, nsplit, flags, tmem_cols;
-  int corr;                     // 1: TF32 + BF16-correction split (default), 0: 3xTF32 (TN_TC_3XTF32=1)
+  int corr;                     // 1: TF32 + BF16-correction split (gradient GEMMs), 0: 3xTF32 (forward GEMMs)
+  int nacc;                     // TMEM accumulators per tile (>= 1), BN columns apart: nacc - 1 K-chunked main accumulators + 1 for the corrections
+  float* parts;                 // statistics partials [row tiles][2][M_total] (tn_stats_finish)
+  unsigned int* tickets;        // one per channel group, zero on entry, reset by the kernel
   int cluster2;          // launched as 2-CTA clusters along x: the two CTAs share (multicast) the weight tiles
   long long* trace;      // optional timeline buffer (debug): 128 slots per traced CTA
   // fused depthwise-backward epilogue (dw_K > 0): this GEMM is the data gradient of a pointwise conv
@@ -696,6 +710,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+      // Accumulator plan (p.nacc > 1 when the tile leaves TMEM columns free): the tensor core's fp32 accumulate truncates, an
+      // error that grows with the number of MMAs chained into one accumulator (measured 1.8e-6 rms at K = 256, 1.1e-5 at
+      // K = 1536 for 3 MMAs per 8 of K).  So the main products hi*hi of consecutive K ranges go to nacc - 1 separate
+      // accumulators and the small correction products (2^-11 of the result, their own truncation is negligible) to the last
+      // one; the epilogue adds them in fp32 with round-to-nearest.
+      const int nacc = (split && p.nacc > 1) ? p.nacc : 1, nmain = nacc > 1 ? nacc - 1 : 1;
+      int prev_am = -1;
       for (int kc = 0; kc < num_kc; ++kc) {
         const int s = kc % S;
         const uint32_t ph = (kc / S) & 1;
@@ -706,25 +727,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tc_fence_after();
         const uint64_t dbh = umma_desc_k128(smem_u32(b_hi(s)));
         const uint64_t dbl = split ? umma_desc_k128(smem_u32(b_lo(s))) : 0;
+        const int am = (kc * nmain) / num_kc;              // main accumulator of this K chunk
+        const bool new_main = am != prev_am;
+        prev_am = am;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           const uint64_t dah = umma_desc_k128(smem_u32(a_hi(s, mt)));
           const uint64_t dal = split ? umma_desc_k128(smem_u32(a_lo(s, mt))) : 0;
-          const uint32_t d = tmem_base + (uint32_t)(mt * 256);
+          const uint32_t d = tmem_base + (uint32_t)(mt * 256 + am * BN);
+          const uint32_t dc = tmem_base + (uint32_t)(mt * 256 + (nacc - 1) * BN);
           if (p.flags & 256) continue;                     // debug knob: no MMA issue
 #pragma unroll
           for (int kk = 0; kk < TC_BK / 8; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 2);       // 8 tf32 = 32 bytes = 2 x 16-byte units
-            const uint32_t acc = (kc > 0 || kk > 0) ? 1u : 0u;
-            if (split && p.corr) {
+            const uint32_t acc = (new_main && kk == 0) ? 0u : 1u;
+            const uint32_t accc = (kc > 0 || kk > 0) ? 1u : 0u;
+            if (!split) {
+              tc_mma_tf32(d, dah + adv, dbh + adv, idesc, acc);
+            } else if (nacc > 1) {
+              tc_mma_tf32(d, dah + adv, dbh + adv, idesc, acc);
+              if (p.corr) {
+                tc_mma_bf16(dc, dal + adv, dbl + adv, tc_idesc_bf16(idesc), accc);
+              } else {
+                tc_mma_tf32(dc, dal + adv, dbh + adv, idesc, accc);
+                tc_mma_tf32(dc, dah + adv, dbl + adv, idesc, 1u);
+              }
+            } else if (p.corr) {
               tc_mma_tf32(d, dah + adv, dbh + adv, idesc, acc);
               tc_mma_bf16(d, dal + adv, dbl + adv, tc_idesc_bf16(idesc), 1u);
-            } else if (split) {
+            } else {
               tc_mma_tf32(d, dal + adv, dbh + adv, idesc, acc);
               tc_mma_tf32(d, dah + adv, dbl + adv, idesc, 1u);
               tc_mma_tf32(d, dah + adv, dbh + adv, idesc, 1u);
-            } else {
-              tc_mma_tf32(d, dah + adv, dbh + adv, idesc, acc);
             }
           }
         }
@@ -816,24 +850,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 256);
       float* zp = p.Z + (size_t)n0 * p.M_total + co;
       float s1 = 0.f, s2 = 0.f;
+      const int na = (split && p.nacc > 1) ? p.nacc : 1;
       switch ((p.flags & 3) | (nvalid == BN ? 4 : 0)) {          // warp-uniform: one specialised, branch-free loop each
-        case 4: tc_epilogue<false, false, true>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
-        case 0: tc_epilogue<false, false, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
-        case TN_EPI_TANH: case TN_EPI_TANH | 4: tc_epilogue<true, false, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
-        case TN_EPI_ACCUM | 4: tc_epilogue<false, true, true>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
-        case TN_EPI_ACCUM: tc_epilogue<false, true, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
-        default: tc_epilogue<true, true, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half); break;
+        case 4: tc_epilogue<false, false, true>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half, 2, na, BN); break;
+        case 0: tc_epilogue<false, false, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half, 2, na, BN); break;
+        case TN_EPI_TANH: case TN_EPI_TANH | 4: tc_epilogue<true, false, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half, 2, na, BN); break;
+        case TN_EPI_ACCUM | 4: tc_epilogue<false, true, true>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half, 2, na, BN); break;
+        case TN_EPI_ACCUM: tc_epilogue<false, true, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half, 2, na, BN); break;
+        default: tc_epilogue<true, true, false>(tbase, zp, (size_t)p.M_total, BN, nvalid, bv, s1, s2, half, 2, na, BN); break;
       }
       if (p.stats) {
-        // combine the two warps of each lane quadrant in shared memory, then one pass of atomics with consecutive
-        // threads on consecutive channels: one visit per 128-byte line per CTA (same-line atomics serialise in L2)
+        // the two warps of each lane quadrant are combined in shared memory (fixed order) and the CTA's per-channel partial
+        // sums go to parts[row tile][which][channel]; tn_stats_finish adds the row tiles in order (no atomics)
         float* red = reinterpret_cast<float*>(smem + p.red_off);          // [2 halves][2 sums][128 channels]
         const int chl = (int)(threadIdx.x & 127u);
         red[(half * 2 + 0) * 128 + chl] = s1;
         red[(half * 2 + 1) * 128 + chl] = s2;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int which = tid >> 7, ch = tid & 127;                        // threads 0-127: sum, 128-255: sum of squares
-        atomicAdd(p.stats + (size_t)which * p.M_total + (co - chl) + ch, (double)red[which * 128 + ch] + (double)red[(2 + which) * 128 + ch]);
+        p.parts[((size_t)blockIdx.x * 2 + which) * p.M_total + (co - chl) + ch] = red[which * 128 + ch] + red[(2 + which) * 128 + ch];
         asm volatile("bar.sync 1, 256;" ::: "memory");                    // `red` is reused by the next channel half
       }
     }
@@ -845,7 +880,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
   if (p.cluster2) cluster_sync_all();        // the peer may still signal this CTA's barriers until its MMAs have drained
-  if (p.has_bn) tn_bn_fold_last(p.bn, p.stats, p.M_total, gridDim.x * gridDim.y);
+  if (p.stats)                               // group = this CTA's 128 * MT channels; the pipeline memory is free now
+    tn_stats_finish(p.has_bn ? &p.bn : nullptr, p.stats, p.parts, (int)gridDim.x, p.M_total, m0, 128 * MT, p.tickets + blockIdx.y,
+                    gridDim.x, blockIdx.y == 0, reinterpret_cast<double*>(smem));
   if (threadIdx.x == 0 && p.trace && blockIdx.y == 0 && blockIdx.x < 256) {
     unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[257 + 2 * blockIdx.x] = (long long)gt; }
   if (threadIdx.x == 0) { TC_TRACE(102); if (p.trace && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) {
@@ -1117,6 +1154,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     // ===== MMA issuer (leader CTA only) =====
     if (leader && lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((256u >> 4) << 24);
+      // accumulator plan as in gemm_tc_kernel: nacc - 1 K-chunked main accumulators + one for the corrections, BN2 columns apart
+      const int nacc = (MODE != 1 && p.nacc > 1) ? p.nacc : 1, nmain = nacc > 1 ? nacc - 1 : 1;
+      int prev_am = -1;
       for (int kc = 0; kc < num_kc; ++kc) {
         const int s = kc % S;
         const uint32_t ph = (kc / S) & 1;
@@ -1125,15 +1165,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         mbar_wait(readyP0 + 8 * s, ph);
         tc_fence_after();
         const uint64_t dah = umma_desc_k128(smem_u32(a_hi(s))), dal = umma_desc_k128(smem_u32(a_lo(s)));
+        const int am = (kc * nmain) / num_kc;
+        const bool new_main = am != prev_am;
+        prev_am = am;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const uint64_t dbh = umma_desc_k128(smem_u32(b_hi(s, t))), dbl = umma_desc_k128(smem_u32(b_lo(s, t)));
-          const uint32_t d = tmem_base + (uint32_t)(t * 256);
+          const uint32_t d = tmem_base + (uint32_t)(t * 256 + am * BN2);
+          const uint32_t dc = tmem_base + (uint32_t)(t * 256 + (nacc - 1) * BN2);
 #pragma unroll
           for (int kk = 0; kk < TC_BK / 8; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 2);
-            const uint32_t acc = (kc > 0 || kk > 0) ? 1u : 0u;
-            if (p.corr) {
+            const uint32_t acc = (new_main && kk == 0) ? 0u : 1u;
+            const uint32_t accc = (kc > 0 || kk > 0) ? 1u : 0u;
+            if (nacc > 1) {
+              tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, acc);
+              if (p.corr) {
+                tc_mma_bf16_2sm(dc, dal + adv, dbl + adv, tc_idesc_bf16(idesc), accc);
+              } else {
+                tc_mma_tf32_2sm(dc, dal + adv, dbh + adv, idesc, accc);
+                tc_mma_tf32_2sm(dc, dah + adv, dbl + adv, idesc, 1u);
+              }
+            } else if (p.corr) {
               tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, acc);
               tc_mma_bf16_2sm(d, dal + adv, dbl + adv, tc_idesc_bf16(idesc), 1u);
             } else {
@@ -1227,10 +1280,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const int nvalid = min(BN2, p.R - r0);
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * 256);
       float* zp = p.Z + (size_t)r0 * p.M_total + co;
-      if (nvalid == BN2) tc_epilogue<false, false, true>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, s1, s2, half, EW / 4);
-      else if (nvalid > 0) tc_epilogue<false, false, false>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, s1, s2, half, EW / 4);
+      const int na = p.nacc > 1 ? p.nacc : 1;
+      if (nvalid == BN2) tc_epilogue<false, false, true>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, s1, s2, half, EW / 4, na, BN2);
+      else if (nvalid > 0) tc_epilogue<false, false, false>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, s1, s2, half, EW / 4, na, BN2);
     }
     if (p.stats) {
+      // the warps of each lane quadrant are combined in shared memory in a fixed order; the CTA's per-channel partial sums go
+      // to parts[pair][which][channel] and tn_stats_finish adds the pairs in order (no atomics)
       float* red = reinterpret_cast<float*>(smem + p.red_off);          // [EW/4 parts][2 sums][128 channels]
       const int chl = (int)(threadIdx.x & 127u);
       red[(half * 2 + 0) * 128 + chl] = s1;
@@ -1238,10 +1294,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
       if (tid < 256) {
         const int which = tid >> 7, ch = tid & 127;
-        double acc = 0.0;
+        float acc = 0.f;
 #pragma unroll
-        for (int pp = 0; pp < EW / 4; ++pp) acc += (double)red[(pp * 2 + which) * 128 + ch];
-        atomicAdd(p.stats + (size_t)which * p.M_total + (co - chl) + ch, acc);
+        for (int pp = 0; pp < EW / 4; ++pp) acc += red[(pp * 2 + which) * 128 + ch];
+        p.parts[((size_t)pair * 2 + which) * p.M_total + (co - chl) + ch] = acc;
       }
     }
     }
@@ -1251,46 +1307,51 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
-  if (p.has_bn) tn_bn_fold_last(p.bn, p.stats, p.M_total, gridDim.x * gridDim.y);
+  if (p.stats)                    // group = this CTA's 128 channels over all pairs; the pipeline memory is free now
+    tn_stats_finish(p.has_bn ? &p.bn : nullptr, p.stats, p.parts, (int)(gridDim.x >> 1), p.M_total, m0 + (int)rank * 128, 128,
+                    p.tickets + 2 * blockIdx.y + rank, gridDim.x >> 1, blockIdx.y == 0 && rank == 0, reinterpret_cast<double*>(smem));
 }
 
-// split scheme of the whole library (weight split kernels and GEMMs must agree): 1 = TF32 + BF16 corrections (default),
-// 0 = 3xTF32 (TN_TC_3XTF32=1).  Measured on the device: GEMM error vs fp64 1.4e-6 (K=256) / 7.2e-6 (K=1536) against 1.8e-6 /
-// 1.1e-5 for 3xTF32, whole-model gradients vs the fp64 oracle identical to three digits, 3 % faster step.
-static int tc_corr_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("TN_TC_3XTF32");
-    mode = (e && e[0] == '1') ? 0 : 1;
+// Split scheme per GEMM.  The weight split carries BOTH correction formats (ws = [3, M, Kd]: tf32 hi | tf32 lo | packed bf16
+// correction rows), so the launcher chooses per call:
+//   forward GEMMs  -> 3xTF32 (operand rounding 8e-8 rms, the same as fp32): what reaches the train-mode BatchNorms must be
+//                     fp32-equivalent (S/17 at batch 4, embeddings vs fp64 over 8 runs: 7.0e-4 .. 7.7e-4 with 3xTF32,
+//                     7.3e-4 .. 1.18e-3 with the bf16 correction, 5.8e-4 for the fp32 reference itself)
+//   gradient GEMMs -> TF32 + one bf16 correction MMA (TN_GEMM_GRAD flag / the fused depthwise backward): 6.6e-7 rms, one third
+//                     fewer tensor-pipe cycles; gradients are judged against the fp32 reference's own error (1e-2).
+// TN_TC_FWD_CORR=1 / TN_TC_BWD_CORR=0 override (A/B runs).
+static int tc_corr_for(bool grad) {
+  static int fwd = -1, bwd = -1;
+  if (fwd < 0) {
+    const char* e = getenv("TN_TC_FWD_CORR");
+    fwd = (e && e[0] == '1') ? 1 : 0;
+    e = getenv("TN_TC_BWD_CORR");
+    bwd = (e && e[0] == '0') ? 0 : 1;
   }
-  return mode;
+  return grad ? bwd : fwd;
 }
 
 // ---------------------------------------------------------------------------
-// weight split: ws[0] = rna_tf32(W), ws[1] = rna_tf32(W - ws[0]) (or the packed bf16 correction rows); optional transpose
+// weight split: ws[0] = rna_tf32(W), ws[1] = rna_tf32(W - ws[0]), ws[2] = the packed bf16 correction rows; optional transpose
 // ---------------------------------------------------------------------------
-// corr = 1: the second half holds, per row and 32-element K chunk, 64 bf16 = [bf16(hi) x32 | bf16(x - hi) x32] in the 128
-// bytes that held 32 tf32 lo values (the weight side of the bf16 correction MMA, see tc_store_corr)
-__device__ __forceinline__ void split_store(float* hi, float* lo, size_t i, int k, float x, int corr) {
+// ws[2] holds, per row and 32-element K chunk, 64 bf16 = [bf16(hi) x32 | bf16(x - hi) x32] in the 128 bytes that hold 32 tf32
+// values in the other two planes (the weight side of the bf16 correction MMA, see tc_store_corr)
+__device__ __forceinline__ void split_store(float* hi, float* lo, float* cr, size_t i, int k, float x) {
   const float h = __uint_as_float(rna_tf32(x));
   hi[i] = h;
-  if (corr) {
-    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(lo + (i - (size_t)(k & 31))) + (k & 31);
-    c[0] = __float2bfloat16_rn(h);
-    c[32] = __float2bfloat16_rn(x - h);
-  } else {
-    lo[i] = __uint_as_float(rna_tf32(x - h));
-  }
+  lo[i] = __uint_as_float(rna_tf32(x - h));
+  __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(cr + (i - (size_t)(k & 31))) + (k & 31);
+  c[0] = __float2bfloat16_rn(h);
+  c[32] = __float2bfloat16_rn(x - h);
 }
-__global__ void split_tf32_kernel(const float* __restrict__ W, float* __restrict__ hi, float* __restrict__ lo, int M, int Kd, int transpose,
-                                  int corr) {
+__global__ void split_tf32_kernel(const float* __restrict__ W, float* __restrict__ ws, int M, int Kd, int transpose) {
   tn_grid_dep_sync();
-  // output [M, Kd]; input [M, Kd] or (transpose) [Kd, M]
+  // output [3, M, Kd]; input [M, Kd] or (transpose) [Kd, M]
   const size_t n = (size_t)M * Kd;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / Kd), k = (int)(i - (size_t)m * Kd);
     const float x = transpose ? W[(size_t)k * M + m] : W[i];
-    split_store(hi, lo, i, k, x, corr);
+    split_store(ws, ws + n, ws + 2 * n, i, k, x);
   }
 }
 
@@ -1672,34 +1733,38 @@ extern "C" int tn_gemm_tc_supported(int R, int Kd, int M) {
 }
 
 extern "C" int tn_split_tf32(const float* W, float* ws, int M, int Kd, int transpose, void* stream) {
-  TN_REQUIRE(W && ws && M > 0 && Kd > 0, "split_tf32: bad arguments");
+  TN_REQUIRE(W && ws && M > 0 && Kd > 0 && Kd % 32 == 0, "split_tf32: bad arguments (Kd %% 32 == 0)");
   size_t n = (size_t)M * Kd;
   int blocks = (int)((n + 255) / 256);
   if (blocks > tn_num_sms() * 8) blocks = tn_num_sms() * 8;
-  tn_launch(split_tf32_kernel, blocks, 256, 0, stream, W, ws, ws + n, M, Kd, transpose, tc_corr_mode());
+  tn_launch(split_tf32_kernel, blocks, 256, 0, stream, W, ws, M, Kd, transpose);
   TN_LAUNCH_CHECK("split_tf32_kernel");
   return TN_OK;
 }
 
-__global__ void split_tf32_batch_kernel(const tn_split_job* __restrict__ jobs, int corr) {
+__global__ void split_tf32_batch_kernel(const tn_split_job* __restrict__ jobs) {
   tn_grid_dep_sync();
   const tn_split_job j = jobs[blockIdx.y];
   const size_t n = (size_t)j.M * j.Kd;
-  float* hi = j.ws;
-  float* lo = j.ws + n;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / j.Kd), k = (int)(i - (size_t)m * j.Kd);
     const float x = j.transpose ? j.W[(size_t)k * j.M + m] : j.W[i];
-    split_store(hi, lo, i, k, x, corr);
+    split_store(j.ws, j.ws + n, j.ws + 2 * n, i, k, x);
   }
 }
 extern "C" int tn_split_tf32_batch(const tn_split_job* jobs_dev, int njobs, int max_elems, void* stream) {
   TN_REQUIRE(jobs_dev && njobs > 0 && njobs <= 65535 && max_elems > 0, "split_tf32_batch: bad arguments");
   int bx = (max_elems + 255) / 256;
   if (bx > 64) bx = 64;
-  tn_launch(split_tf32_batch_kernel, dim3(bx, njobs), 256, 0, stream, jobs_dev, tc_corr_mode());
+  tn_launch(split_tf32_batch_kernel, dim3(bx, njobs), 256, 0, stream, jobs_dev);
   TN_LAUNCH_CHECK("split_tf32_batch_kernel");
   return TN_OK;
+}
+
+// upper bound of the statistics partials of the tensor-core GEMMs: row tiles have at least 32 rows
+extern "C" long long tn_gemm_tc_scratch_floats(int R, int M) {
+  if (R <= 0 || M <= 0) return 0;
+  return ((long long)(R + 31) / 32 + 1) * 2 * M;
 }
 
 // rows of output per CTA: the multiple of 16 that minimises waves * (tile rows + fixed cost).
@@ -1740,8 +1805,34 @@ static cudaError_t launch_mode(int mode, bool cluster, dim3 grid, size_t smem, v
 }
 
 // common launcher: p carries the epilogue configuration; shapes / tiles / maps are filled here
-static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, int Kd, int M, int nsplit, void* stream) {
+static int nacc_cap() {
+  static int cap = -1;
+  if (cap < 0) { const char* e = getenv("TN_TC_NACC"); cap = e ? atoi(e) : 8; if (cap < 1) cap = 1; if (cap > 8) cap = 8; }
+  return cap;
+}
+// accumulators per tile: `cols_avail` TMEM columns per tile, `bn` columns per accumulator, at most one main chunk per K chunk
+static int pick_nacc(int cols_avail, int bn, int num_kc, int nsplit) {
+  if (nsplit != 3) return 1;
+  int n = cols_avail / bn;
+  if (n > nacc_cap()) n = nacc_cap();
+  if (n > num_kc + 1) n = num_kc + 1;
+  return n < 2 ? 1 : n;
+}
+
+static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, int Kd, int M, int nsplit, const tn_scratch* scratch,
+                          void* stream) {
   TN_REQUIRE(X && ws, "gemm_tc: null tensor");
+  const bool grad = (p.flags & TN_GEMM_GRAD) != 0 || p.dw_K > 0;
+  p.flags &= ~TN_GEMM_GRAD;
+  p.corr = tc_corr_for(grad);
+  const float* ws_lo = ws + (size_t)(p.corr ? 2 : 1) * M * Kd;
+  if (p.stats) {
+    TN_REQUIRE(scratch && scratch->parts && scratch->tickets && scratch->parts_floats >= tn_gemm_tc_scratch_floats(R, M),
+               "gemm_tc: statistics need a tn_scratch with tn_gemm_tc_scratch_floats(R, M) floats and the ticket array");
+    TN_REQUIRE(M / 128 <= TN_TICKETS, "gemm_tc: statistics of more than %d channels are not supported", TN_TICKETS * 128);
+    TN_REQUIRE(tn_aligned16(scratch->parts), "gemm_tc: scratch must be 16B aligned");
+    p.parts = scratch->parts; p.tickets = scratch->tickets;
+  }
   TN_REQUIRE(tn_gemm_tc_supported(R, Kd, M), "gemm_tc: unsupported shape R=%d K=%d M=%d (need K %% 32 == 0, M %% 128 == 0)", R, Kd, M);
   TN_REQUIRE(nsplit == 1 || nsplit == 3, "gemm_tc: nsplit must be 1 or 3");
   TN_REQUIRE(tn_aligned16(X) && tn_aligned16(ws), "gemm_tc: operands must be 16B aligned");
@@ -1784,11 +1875,12 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
     if (best > 0) {
       CUtensorMap mA_hi, mA_lo, mB;
       if ((rc = make_map(&mA_hi, ws, M, Kd, 128)) != TN_OK) return rc;
-      if ((rc = make_map(&mA_lo, ws + (size_t)M * Kd, M, Kd, 128)) != TN_OK) return rc;
+      if ((rc = make_map(&mA_lo, ws_lo, M, Kd, 128)) != TN_OK) return rc;
       if ((rc = make_map(&mB, X, R, Kd, best / 2 + (p.fdw_K > 0 ? 8 : 0))) != TN_OK) return rc;
       CUtensorMap mZ = mB;
       if (p.dw_K > 0 && (rc = make_map(&mZ, p.zprev, R, M, best, 32)) != TN_OK) return rc;
-      p.R = R; p.Kd = Kd; p.M_total = M; p.BN = best; p.BNo = 2 * best - halo2; p.nsplit = 3; p.corr = tc_corr_mode();
+      p.R = R; p.Kd = Kd; p.M_total = M; p.BN = best; p.BNo = 2 * best - halo2; p.nsplit = 3;
+      p.nacc = p.dw_K > 0 ? 1 : pick_nacc(256, best, Kd / TC_BK, 3);
       const size_t stage_bytes = 2ull * 128 * TC_BK * 4 + 4ull * (best / 2) * TC_BK * 4 + raw2;
       p.red_off = (uint32_t)(stage_bytes * TC2_STAGES);
       p.par_off = (uint32_t)(stage_bytes * TC2_STAGES + red2 - par2);
@@ -1828,12 +1920,13 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   const int bn = bno + halo;
   CUtensorMap mA_hi, mA_lo, mB;
   if ((rc = make_map(&mA_hi, ws, M, Kd, 128)) != TN_OK) return rc;
-  if ((rc = make_map(&mA_lo, ws + (size_t)M * Kd, M, Kd, 128)) != TN_OK) return rc;
+  if ((rc = make_map(&mA_lo, ws_lo, M, Kd, 128)) != TN_OK) return rc;
   if ((rc = make_map(&mB, X, R, Kd, bn + (p.fdw_K > 0 ? 16 : 0))) != TN_OK) return rc;
-  p.R = R; p.Kd = Kd; p.M_total = M; p.BN = bn; p.BNo = bno; p.stages = stages; p.nsplit = nsplit; p.corr = tc_corr_mode();
+  p.R = R; p.Kd = Kd; p.M_total = M; p.BN = bn; p.BNo = bno; p.stages = stages; p.nsplit = nsplit;
+  p.nacc = p.dw_K > 0 ? 1 : pick_nacc(MT == 2 ? 256 : 512, bn, Kd / TC_BK, nsplit);
   p.trace = g_trace;
   int cols = MT == 2 ? 512 : 32;
-  while (MT == 1 && cols < bn) cols <<= 1;
+  while (MT == 1 && cols < bn * p.nacc) cols <<= 1;
   p.tmem_cols = cols;
   const size_t stage_bytes = (size_t)mult * (MT * 128 * TC_BK * 4 + (size_t)bn * TC_BK * 4) + fdw_extra;
   const size_t smem = stage_bytes * stages + red_bytes + 1024;
@@ -1869,27 +1962,27 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   return TN_OK;
 }
 
-// ws: the split weights from tn_split_tf32 (hi | lo), [2, M, Kd].  nsplit 3 = fp32-equivalent, 1 = plain TF32.
+// ws: the split weights from tn_split_tf32, [3, M, Kd].  nsplit 3 = fp32-equivalent, 1 = plain TF32.
 extern "C" int tn_gemm_tc(const float* X, const float* ws, const float* bias, float* Z, double* stats, int R, int Kd, int M,
-                          int flags, int nsplit, void* stream) {
+                          int flags, int nsplit, const tn_scratch* scratch, void* stream) {
   TN_REQUIRE(Z, "gemm_tc: null output");
   TN_REQUIRE(!(flags & TN_EPI_ACCUM) || !stats, "gemm_tc: statistics of an accumulated output are not available");
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.bias = bias; p.Z = Z; p.stats = stats; p.flags = flags;
-  return launch_gemm_tc(X, ws, p, R, Kd, M, nsplit, stream);
+  return launch_gemm_tc(X, ws, p, R, Kd, M, nsplit, scratch, stream);
 }
 
 static int check_bn(const tn_bn_fold* bn, const double* stats) {
   TN_REQUIRE(bn && stats, "bn fold needs the statistics buffer");
-  TN_REQUIRE(bn->gamma && bn->beta && bn->scale && bn->shift && bn->mean && bn->invstd && bn->counter, "bn fold: null field");
+  TN_REQUIRE(bn->gamma && bn->beta && bn->scale && bn->shift && bn->mean && bn->invstd, "bn fold: null field");
   TN_REQUIRE(bn->n >= 1.0, "bn fold: n must be >= 1");
   TN_REQUIRE((bn->running_mean == nullptr) == (bn->running_var == nullptr), "bn fold: running_mean/var must come together");
   return TN_OK;
 }
 
 extern "C" int tn_gemm_tc_bn(const float* X, const float* ws, const float* bias, float* Z, double* stats, const tn_bn_fold* bn,
-                             int R, int Kd, int M, int flags, int nsplit, void* stream) {
+                             int R, int Kd, int M, int flags, int nsplit, const tn_scratch* scratch, void* stream) {
   TN_REQUIRE(Z, "gemm_tc_bn: null output");
   int rc = check_bn(bn, stats);
   if (rc != TN_OK) return rc;
@@ -1897,7 +1990,7 @@ extern "C" int tn_gemm_tc_bn(const float* X, const float* ws, const float* bias,
   memset(&p, 0, sizeof(p));
   p.bias = bias; p.Z = Z; p.stats = stats; p.flags = flags;
   p.bn = *bn; p.has_bn = 1;
-  return launch_gemm_tc(X, ws, p, R, Kd, M, nsplit, stream);
+  return launch_gemm_tc(X, ws, p, R, Kd, M, nsplit, scratch, stream);
 }
 
 // Forward of a depthwise-separable conv block + train-mode BatchNorm fold in ONE kernel:
@@ -1906,7 +1999,7 @@ extern "C" int tn_gemm_tc_bn(const float* X, const float* ws, const float* bias,
 extern "C" int tn_gemm_tc_dwfwd(const float* z, const float* ws, const float* dw_w, const float* dw_b, const float* scale,
                                 const float* shift, int relu, float drop_p, const unsigned long long* seed, unsigned int layer,
                                 const float* pw_bias, float* u_out, float* Z, double* stats, const tn_bn_fold* bn, int B, int T,
-                                int C, int Co, int K, void* stream) {
+                                int C, int Co, int K, const tn_scratch* scratch, void* stream) {
   TN_REQUIRE(z && dw_w && Z, "gemm_tc_dwfwd: null tensor");
   TN_REQUIRE(K >= 1 && K <= 7 && (K & 1), "gemm_tc_dwfwd: unsupported depthwise kernel size %d (odd sizes 1..7; wider windows do not fit the register file)", K);
   TN_REQUIRE((scale == nullptr) == (shift == nullptr), "gemm_tc_dwfwd: scale and shift come together");
@@ -1925,7 +2018,7 @@ extern "C" int tn_gemm_tc_dwfwd(const float* z, const float* ws, const float* dw
   }
   p.fdw_K = K; p.fdw_T = T; p.fdw_w = dw_w; p.fdw_b = dw_b; p.fdw_u = u_out;
   p.act = tn_make_act(scale, shift, relu, drop_p, seed, layer);
-  return launch_gemm_tc(z, ws, p, (int)R, C, Co, 3, stream);
+  return launch_gemm_tc(z, ws, p, (int)R, C, Co, 3, scratch, stream);
 }
 
 // Data gradient of a depthwise-separable conv block in one kernel:
@@ -1949,5 +2042,5 @@ extern "C" int tn_gemm_tc_dwbwd(const float* dZ, const float* ws, const float* z
   p.dw_K = K; p.dw_T = T; p.dw_w = dw_w; p.zprev = zprev; p.dzprev = dzprev;
   p.g_dw = g_dw; p.g_db = g_dbias; p.g_dscale = g_dscale; p.g_dshift = g_dshift;
   p.act = tn_make_act(scale, shift, relu, drop_p, seed, layer);
-  return launch_gemm_tc(dZ, ws, p, (int)R, Co, C, nsplit, stream);
+  return launch_gemm_tc(dZ, ws, p, (int)R, Co, C, nsplit, nullptr, stream);
 }

@@ -10,31 +10,36 @@
 // ---------------------------------------------------------------------------
 // squeeze: mean over time of the lazy activation
 // ---------------------------------------------------------------------------
+// One block owns one utterance and 64 channels (16 quads x 16 row lanes) and walks all T frames; the lanes are combined in
+// a fixed order in shared memory, so m is reproducible bit for bit (the forward pass has no floating-point atomics) and is
+// WRITTEN, not accumulated.
 __global__ void __launch_bounds__(TN_EW_THREADS) se_mean_kernel(const float* __restrict__ z, float* __restrict__ m, TnAct act,
-                                                                int T, int C, int tpb, float inv_T) {
+                                                                int T, int C, float inv_T) {
   tn_grid_dep_sync();
   act = tn_act_init(act);
   __shared__ float4 red[TN_EW_THREADS];
-  TnTile tl = tn_tile(C);
+  const int q = threadIdx.x & 15, lane = threadIdx.x >> 4;
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * tpb, t1 = min(T, t0 + tpb);
-  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
-    const int q = qb + tl.q0;
-    float4 s = tn_zero4();
-    if (tl.active && q < tl.Q)
-      for (int t = t0 + tl.lane; t < t1; t += tl.lanes) {
-        size_t off = ((size_t)b * T + t) * C + 4 * q;
-        s = s + tn_act4(act, tn_ld4(z + off), 4 * q, off >> 2, nullptr);
-      }
-    tn_lane_reduce_atomic(tl, s, q, m + (size_t)b * C, red, inv_T);
+  const int c = blockIdx.x * 64 + 4 * q;
+  float4 s = tn_zero4();
+  if (c < C) {
+    const float* zb = z + (size_t)b * T * C + c;
+#pragma unroll 4
+    for (int t = lane; t < T; t += 16) {
+      const size_t off = ((size_t)b * T + t) * C + c;
+      s = s + tn_act4(act, tn_ld4(zb + (size_t)t * C), c, off >> 2, nullptr);
+    }
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < 16 && c < C) {
+    float4 a = red[q];
+#pragma unroll
+    for (int l = 1; l < 16; ++l) a = a + red[l * 16 + q];
+    tn_st4(m + (size_t)b * C + c, a * inv_T);
   }
 }
 
-// squeeze + excitation in one launch: the last block to finish batch item b's mean runs b's MLP
-__global__ void __launch_bounds__(TN_EW_THREADS) se_squeeze_excite_kernel(const float* __restrict__ z, float* __restrict__ m,
-                                                                          float* __restrict__ gate, unsigned int* __restrict__ counters,
-                                                                          const float* __restrict__ W1, const float* __restrict__ W2,
-                                                                          TnAct act, int T, int C, int Cr, int tpb, float inv_T);
 // excitation MLP of batch item b by one block.  sm: m[C] + h[Cr].  m is read with ld.cg: in the fused kernels it was
 // just accumulated by other blocks' atomics (performed in L2).
 __device__ __forceinline__ void se_mlp_fwd_block(float* sm, int b, const float* __restrict__ m, const float* __restrict__ W1,
@@ -125,30 +130,6 @@ __global__ void __launch_bounds__(256) se_mlp_bwd_kernel(const float* __restrict
   tn_grid_dep_sync();
   extern __shared__ float sm[];
   se_mlp_bwd_block(sm, blockIdx.x, dgate, gate, m, W1, W2, dm, dW1, dW2, C, Cr);
-}
-
-__global__ void __launch_bounds__(TN_EW_THREADS) se_squeeze_excite_kernel(const float* __restrict__ z, float* __restrict__ m,
-                                                                          float* __restrict__ gate, unsigned int* __restrict__ counters,
-                                                                          const float* __restrict__ W1, const float* __restrict__ W2,
-                                                                          TnAct act, int T, int C, int Cr, int tpb, float inv_T) {
-  tn_grid_dep_sync();
-  act = tn_act_init(act);
-  __shared__ float4 red[TN_EW_THREADS];
-  extern __shared__ float sm[];
-  TnTile tl = tn_tile(C);
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * tpb, t1 = min(T, t0 + tpb);
-  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
-    const int q = qb + tl.q0;
-    float4 s = tn_zero4();
-    if (tl.active && q < tl.Q)
-      for (int t = t0 + tl.lane; t < t1; t += tl.lanes) {
-        size_t off = ((size_t)b * T + t) * C + 4 * q;
-        s = s + tn_act4(act, tn_ld4(z + off), 4 * q, off >> 2, nullptr);
-      }
-    tn_lane_reduce_atomic(tl, s, q, m + (size_t)b * C, red, inv_T);
-  }
-  if (tn_last_block_of(counters + b, gridDim.x)) se_mlp_fwd_block(sm, b, m, W1, W2, gate, C, Cr);
 }
 
 // ---------------------------------------------------------------------------
@@ -308,26 +289,9 @@ extern "C" int tn_se_mean(const float* z3, float* m, const float* scale, const f
                           const unsigned long long* seed, unsigned int layer, int B, int T, int C, void* stream) {
   SE_COMMON_CHECK("se_mean");
   TN_REQUIRE(z3 && m && (scale == nullptr) == (shift == nullptr), "se_mean: null tensor");
-  int tpb = time_per_block(B, T);
-  dim3 grid(tn_cdiv(T, tpb), B);
-  tn_launch(se_mean_kernel, grid, TN_EW_THREADS, 0, stream, z3, m, tn_make_act(scale, shift, relu, drop_p, seed, layer), T, C, tpb, 1.0f / (float)T);
+  dim3 grid(tn_cdiv(C, 64), B);
+  tn_launch(se_mean_kernel, grid, TN_EW_THREADS, 0, stream, z3, m, tn_make_act(scale, shift, relu, drop_p, seed, layer), T, C, 1.0f / (float)T);
   TN_LAUNCH_CHECK("se_mean_kernel");
-  return TN_OK;
-}
-
-// m (ACCUMULATED) and counters (B zeroed uints, self-resetting) are provided zeroed by the caller
-extern "C" int tn_se_squeeze_excite(const float* z3, float* m, float* gate, unsigned int* counters, const float* W1, const float* W2,
-                                    const float* scale, const float* shift, int relu, float drop_p, const unsigned long long* seed,
-                                    unsigned int layer, int B, int T, int C, int Cr, void* stream) {
-  SE_COMMON_CHECK("se_squeeze_excite");
-  TN_REQUIRE(z3 && m && gate && counters && W1 && W2 && Cr > 0 && (scale == nullptr) == (shift == nullptr), "se_squeeze_excite: null tensor");
-  size_t smem = sizeof(float) * (size_t)(C + Cr);
-  TN_REQUIRE(smem <= 40 * 1024, "se_squeeze_excite: C too large");
-  int tpb = time_per_block(B, T);
-  dim3 grid(tn_cdiv(T, tpb), B);
-  tn_launch(se_squeeze_excite_kernel, grid, TN_EW_THREADS, smem, stream, z3, m, gate, counters, W1, W2,
-            tn_make_act(scale, shift, relu, drop_p, seed, layer), T, C, Cr, tpb, 1.0f / (float)T);
-  TN_LAUNCH_CHECK("se_squeeze_excite_kernel");
   return TN_OK;
 }
 

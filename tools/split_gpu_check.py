@@ -4,6 +4,7 @@ import math, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT]
 import torch
+from titanet_b200._ops import gemm_tc_raw
 from titanet_b200._lib import call, ptr
 
 def run(R, Kd, M, transpose, relu, flags=0):
@@ -13,10 +14,10 @@ def run(R, Kd, M, transpose, relu, flags=0):
         x = torch.relu(x)
     w = torch.randn(*( (Kd, M) if transpose else (M, Kd) ), generator=g) / math.sqrt(Kd)
     ref = x.double() @ (w.double() if transpose else w.double().t())
-    ws = torch.empty(2, M, Kd, device="cuda")
+    ws = torch.empty(3, M, Kd, device="cuda")
     call("tn_split_tf32", ptr(w.cuda()), ptr(ws), M, Kd, int(transpose))
     z = torch.empty(R, M, device="cuda")
-    call("tn_gemm_tc", ptr(x.cuda()), ptr(ws), None, ptr(z), None, R, Kd, M, flags, 3)
+    gemm_tc_raw(x.cuda(), ws, None, z, None, R, Kd, M, flags, 3)
     torch.cuda.synchronize()
     err = (z.double().cpu() - ref)
     print(f"R={R:6d} Kd={Kd:5d} M={M:5d} T={int(transpose)} relu={int(relu)}: relmax {float(err.abs().max() / ref.abs().max()):.2e}  rms {float(err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()):.2e}")

@@ -2,21 +2,22 @@
 import math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from titanet_b200._ops import gemm_tc_raw
 from titanet_b200._lib import LIB, call, ptr
 B, T, C, Co, K = 64, 301, 256, 256, int(os.environ.get("K", 3))
 P = float(os.environ.get("P", 0.1))
 R = B * T
 g = lambda *s: torch.randn(*s, device="cuda")
 z, u, zo = g(R, C), torch.empty(R, C, device="cuda"), torch.empty(R, Co, device="cuda")
-pw = g(Co, C) / 16; ws = torch.empty(2, Co, C, device="cuda"); call("tn_split_tf32", ptr(pw), ptr(ws), Co, C, 0)
+pw = g(Co, C) / 16; ws = torch.empty(3, Co, C, device="cuda"); call("tn_split_tf32", ptr(pw), ptr(ws), Co, C, 0)
 dw_w, dw_b, pw_b = g(C, 1, K), g(C), g(Co)
 sc, sh = torch.rand(C, device="cuda") + 0.5, g(C) * 0.1
 seed = torch.tensor([5], dtype=torch.int64, device="cuda")
 stats = torch.zeros(2 * Co, dtype=torch.float64, device="cuda")
-def fused(): call("tn_gemm_tc_dwfwd", ptr(z), ptr(ws), ptr(dw_w), ptr(dw_b), ptr(sc), ptr(sh), 1, P, ptr(seed) if P > 0 else None, 3, ptr(pw_b), ptr(u), ptr(zo), ptr(stats), None, B, T, C, Co, K)
+def fused(): call("tn_gemm_tc_dwfwd", ptr(z), ptr(ws), ptr(dw_w), ptr(dw_b), ptr(sc), ptr(sh), 1, P, ptr(seed) if P > 0 else None, 3, ptr(pw_b), ptr(u), ptr(zo), None, None, B, T, C, Co, K, None)
 def unfused():
     call("tn_dw_fwd", ptr(z), ptr(u), ptr(dw_w), ptr(dw_b), ptr(sc), ptr(sh), 1, P, ptr(seed) if P > 0 else None, 3, B, T, C, K)
-    call("tn_gemm_tc", ptr(u), ptr(ws), ptr(pw_b), ptr(zo), ptr(stats), R, C, Co, 0, 3)
+    gemm_tc_raw(u, ws, pw_b, zo, stats, R, C, Co, 0, 3)
 for name, f in (("fused", fused), ("dw_fwd + gemm", unfused)):
     f(); torch.cuda.synchronize()
     gr = torch.cuda.CUDAGraph(); st = torch.cuda.Stream()

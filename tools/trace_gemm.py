@@ -2,18 +2,19 @@
 import math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from titanet_b200._ops import gemm_tc_raw
 from titanet_b200._lib import LIB, call, ptr
 R, K, M, nsplit = (int(v) for v in (sys.argv[1:5] + ["19264", "256", "256", "3"][len(sys.argv) - 1:]))
 x = torch.randn(R, K, device="cuda"); w = torch.randn(M, K, device="cuda") / math.sqrt(K)
-z = torch.empty(R, M, device="cuda"); ws = torch.empty(2, M, K, device="cuda")
+z = torch.empty(R, M, device="cuda"); ws = torch.empty(3, M, K, device="cuda")
 tr = torch.zeros(1024, dtype=torch.int64, device="cuda")
 call("tn_split_tf32", ptr(w), ptr(ws), M, K, 0)
-for _ in range(3): call("tn_gemm_tc", ptr(x), ptr(ws), None, ptr(z), None, R, K, M, 0, nsplit)
+for _ in range(3): gemm_tc_raw(x, ws, None, z, None, R, K, M, 0, nsplit)
 torch.cuda.synchronize()
 LIB.load(); LIB.call("tn_gemm_tc_set_trace", tr.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-call("tn_gemm_tc", ptr(x), ptr(ws), None, ptr(z), None, R, K, M, 0, nsplit)
+gemm_tc_raw(x, ws, None, z, None, R, K, M, 0, nsplit)
 e1.record()
 torch.cuda.synchronize(); LIB.call("tn_gemm_tc_set_trace", None)
 print(f"event-timed launch: {e0.elapsed_time(e1) * 1e3:.1f} us")
