@@ -12,8 +12,8 @@ synthetic waveforms, dropout 0.1 as parameters.yml:57).
 One JSON line on stdout (rank 0).  ``value`` is device-resident throughput (inputs already
 in HBM), ``e2e`` the same metric through the public module API with pinned host buffers
 (H2D of the step's waveforms + labels and a D2H read of the loss inside the timed region).
-``--impl reference`` times the CPU implementation of the same path (the oracle port of
-the reference's modules; torch CPU ops with all host threads) on a bounded sample.
+``--impl reference`` times the reference's own CPU implementation of the same path (the unmodified
+modules from baseline/_ref, all host threads, plus the reference's 2-thread default) on a bounded sample.
 """
 from __future__ import annotations
 
@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--model", default="s")
     ap.add_argument("--blocks", type=int, default=17)
     ap.add_argument("--dropout", type=float, default=0.1)
-    ap.add_argument("--cpu-batch", type=int, default=8, help="utterances per step of the CPU arm / CPU baseline")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="utterances per step of the CPU arm / CPU baseline (0: the stated batch, capped at 64 / 16 / 8 for S / M / L)")
     ap.add_argument("--loss", default="ce", choices=["ce", "arc"], help="ce: CELoss (configs[1]); arc: ArcFaceLoss s=30 m=0.2 (configs[2], [3])")
     ap.add_argument("--ragged", action="store_true",
                     help="configs[3]: utterance lengths 1..--seconds s (whole seconds), each mel on its own length, zero padded")
@@ -58,60 +58,119 @@ def parse():
 
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    out = {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
     if os.path.exists(path):
         d = json.load(open(path))
-        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+        out = {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    # dense TF32 peak measured on this pool's B200 the way MEASURED_PEAKS.json measures bf16 (tools/measure_tf32_peak.py, burst:
+    # the roofline kernel is timed alone); bf16 / 2 only when that file is missing
+    out["tf32_tflops"], out["tf32_source"] = out["bf16_tflops"] / 2.0, "bf16 sustained / 2 (not measured)"
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_tf32_peak.json")))
+        out["tf32_tflops"], out["tf32_source"] = float(t["tf32_tflops"]), "measured (tools/measure_tf32_peak.py, torch.matmul TF32 8192^3, burst)"
+    except (OSError, ValueError, KeyError):
+        pass
+    return out
 
 
 # ----------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path (torch CPU ops, all host threads)
+# CPU arm: the UNMODIFIED reference modules from baseline/_ref (installed by baseline/install_ref.py; git-ignored, shipped to the
+# GPU box by gpurun), driven exactly as the reference drives them: per-utterance transforms.MelSpectrogram (datasets.py:292-293),
+# zero-pad collate (datasets.py:48-73), model(spectrograms, speakers=...) and loss.backward() (learn.py:95-117).  Falls back to
+# the oracle port (oracle/titanet_oracle.py) only when baseline/_ref is absent, and says which in `kind`.
 # ----------------------------------------------------------------------------
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+CPU_BATCH_CAP = {"s": 64, "m": 16, "l": 8}          # utterances per CPU step: S runs the stated batch of 64
+
+
+def reference_available() -> bool:
+    return all(os.path.exists(os.path.join(REF_DIR, f)) for f in ("modules.py", "models.py", "losses.py", "transforms.py"))
+
+
+def cpu_batch(args) -> int:
+    cap = CPU_BATCH_CAP.get(args.model.lower(), 8)
+    if args.seconds > 3.0:
+        cap = max(2, int(cap * 3.0 / args.seconds))
+    return min(args.batch, args.cpu_batch if args.cpu_batch > 0 else cap)
+
+
 def cpu_step_factory(args, batch):
     import titanet_oracle as O
-    spec = O.TitaNetSpec.named(args.model, args.blocks, dropout=args.dropout)
-    sd = O.synth_state_dict(spec, args.loss, N_CLASSES)
     wave, labels = O.synthetic_batch(batch, seconds=args.seconds, n_classes=N_CLASSES, seed=42)
     lens = ragged_lengths(args, batch, 42).tolist() if args.ragged else [wave.shape[1]] * batch
+    if reference_available():
+        import warnings
+        warnings.filterwarnings("ignore")
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        import losses as ref_losses, models as ref_models, transforms as ref_transforms      # the reference's own modules
+        torch.manual_seed(42)                                                                 # utils.set_seed (utils.py:281-291)
+        head = (ref_losses.CELoss(192, N_CLASSES) if args.loss == "ce"
+                else ref_losses.ArcFaceLoss(192, N_CLASSES, scale=ARC_SCALE, margin=ARC_MARGIN))
+        model = ref_models.TitaNet.get_titanet(embedding_size=192, n_mels=80, n_mega_blocks=args.blocks, model_size=args.model,
+                                               loss_function=head, dropout=args.dropout, device="cpu").train()
+        mel = ref_transforms.MelSpectrogram(SAMPLE_RATE, n_fft=512, win_length=400, hop_length=160, n_mels=80,
+                                            specaugment_probability=0.0)
+
+        def step():
+            mels = [mel({"waveform": w[:n].view(1, -1), "sample_rate": SAMPLE_RATE})["spectrogram"] for w, n in zip(wave, lens)]
+            tmax = max(m.shape[-1] for m in mels)
+            x = torch.zeros(batch, 80, tmax)                                                  # collate_fn: zero padding
+            for i, m in enumerate(mels):
+                x[i, :, :m.shape[-1]] = m[0]
+            model.zero_grad()
+            _, _, loss = model(x, speakers=labels)
+            loss.backward()
+            return float(loss)
+
+        return step, "reference"
+    spec = O.TitaNetSpec.named(args.model, args.blocks, dropout=args.dropout)
+    sd = O.synth_state_dict(spec, args.loss, N_CLASSES)
     kw = dict(scale=ARC_SCALE, margin=ARC_MARGIN) if args.loss == "arc" else {}
 
     def step():
-        # per-utterance mel loop + collate, like datasets.py:292-293 / 48-73, then fwd + bwd
         x, _ = O.collate_pad([O.mel_spectrogram(w[:n].view(1, -1)) for w, n in zip(wave, lens)])
         out = O.titanet_step(sd, spec, x, labels, args.loss, training=True, **kw)
         return float(out[2])
 
-    return step
+    return step, "port"
 
 
-def time_cpu(args, batch, steps, warmup):
-    torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_step_factory(args, batch)
+def time_cpu(args, batch, steps, warmup, threads=None):
+    """(utterances/s, seconds per step, kind, threads) of the CPU implementation; best of `steps` after `warmup`."""
+    threads = threads or (os.cpu_count() or 1)
+    torch.set_num_threads(threads)
+    step, kind = cpu_step_factory(args, batch)
     for _ in range(warmup):
         step()
-    t0 = time.perf_counter()
+    best = float("inf")
     for _ in range(steps):
+        t0 = time.perf_counter()
         step()
-    dt = (time.perf_counter() - t0) / steps
-    return batch / dt, dt
+        best = min(best, time.perf_counter() - t0)
+    return batch / best, best, kind, threads
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = args.cpu_batch
-    steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 1))
-    value, dt = time_cpu(args, batch, steps, warmup)
-    cores = os.cpu_count() or 1
-    sample = f"{steps} steps of {batch} utterances x {args.seconds:g} s (mel + fwd + bwd), {warmup} warm-up, torch CPU ops"
+    batch = cpu_batch(args)
+    steps = max(1, min(args.steps, 3))
+    warmup = 1
+    value, dt, kind, threads = time_cpu(args, batch, steps, warmup)
+    v2, dt2, _, _ = time_cpu(args, batch, 1, 0, threads=2)            # the reference's own default: workers = 2 (parameters.yml:74, train.py:21-22)
+    impl = "unmodified reference modules (baseline/_ref)" if kind == "reference" else "oracle port of the reference modules"
+    sample = (f"best of {steps} steps of {batch} utterances x {args.seconds:g} s (per-utterance mel + collate + fwd + bwd), {warmup} warm-up, "
+              f"{impl}, torch CPU, {threads} threads")
     line = {
         "impl": "reference", "metric": metric_name(args), "value": round(value, 3),
         "unit": "utterances/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(dt * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.batch),      # our arm's workload; each CPU step is a bounded sample of it (see `sample`)
-        "cpu_baseline": {"value": round(value, 3), "unit": "utterances/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, batch, device=False),
+        "cpu_baseline": {"value": round(value, 3), "unit": "utterances/s", "cores": threads, "kind": kind, "sample": sample},
+        "reference_default_threads": {"value": round(v2, 3), "unit": "utterances/s", "cores": 2, "ms_per_step": round(dt2 * 1e3, 2),
+                                      "note": "torch.set_num_threads(2), the reference's generic.workers default; 1 step, no warm-up"},
         "e2e": {"value": round(value, 3), "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -126,13 +185,13 @@ def ragged_lengths(args, batch, seed):
     return SAMPLE_RATE * torch.randint(1, int(args.seconds) + 1, (batch,), generator=g, dtype=torch.int32)
 
 
-def workload_config(args, batch):
+def workload_config(args, batch, device=True):
+    """The workload both arms run; identical dicts when the CPU arm runs the stated batch (TitaNet-S: 64)."""
     loss = f"CE loss ({N_CLASSES} classes)" if args.loss == "ce" else f"ArcFace loss (s={ARC_SCALE}, m={ARC_MARGIN}, {N_CLASSES} classes)"
     dur = f"variable 1-{args.seconds:g}s padded to {args.seconds:g}s" if args.ragged else f"{args.seconds:g}s"
-    return {"workload": f"TitaNet-{args.model.upper()}/{args.blocks} fwd+bwd, {loss}, "
-                        f"batch {batch}/GPU, {dur}@16kHz synthetic waveform, mel on device, dropout {args.dropout}",
-            "batch_per_gpu": batch, "seconds": args.seconds, "frames": 1 + int(args.seconds * SAMPLE_RATE) // 160,
-            "l2": "per-step working set (~2 GB of activations) >> 126 MB L2; no explicit flush"}
+    return {"workload": f"TitaNet-{args.model.upper()}/{args.blocks} fwd+bwd, {loss}, batch {batch} per device, {dur}@16kHz synthetic "
+                        f"waveform, mel + encoder + decoder + loss, dropout {args.dropout}",
+            "batch_per_gpu": batch, "seconds": args.seconds, "frames": 1 + int(args.seconds * SAMPLE_RATE) // 160}
 
 
 # ----------------------------------------------------------------------------
@@ -363,7 +422,7 @@ def run_ours(args):
                     traffic = json.load(fh).get(kind)
             except (OSError, ValueError):
                 pass
-            tf32_peak = pk["bf16_tflops"] / 2.0
+            tf32_peak = pk["tf32_tflops"]
             ach_tf = flops / per_launch_s / 1e12
             ach_gb = byts / per_launch_s / 1e9
             launches_per_step = n // prof_steps
@@ -375,7 +434,9 @@ def run_ours(args):
                     "frac": round(ach_gb / pk["hbm_gbs"], 4), "traffic": traffic, "peak_source": pk["source"],
                     "algorithmic_bytes_per_launch": byts, "algorithmic_flops_per_launch": flops,
                     "algorithmic_tflop_s": round(ach_tf, 2), "tf32_peak_tflop_s": round(tf32_peak, 1),
-                    "tensor_frac_of_tf32_peak": round(ach_tf / tf32_peak, 4), "mma_issue_factor": 3 if os.environ.get("TN_TC_3XTF32") == "1" else 2,
+                    "tf32_peak_source": pk["tf32_source"],
+                    "tensor_frac_of_tf32_peak": round(ach_tf / tf32_peak, 4),
+                    "mma_issue_factor": 2 if kind == "tn_gemm_tc_dwbwd" else (1 if kind == "tn_wgrad_tc" else 3),
                     "timing": "CUDA events around a CUDA graph of 20 back-to-back launches of this shape",
                     "eager_ms_per_step_by_entry_point": {k: round(v[1] / prof_steps, 3) for k, v in
                                                          sorted(groups.items(), key=lambda kv: -kv[1][1])}}
@@ -391,16 +452,19 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, B),
+        "l2": "per-step working set (~2 GB of activations) >> 126 MB L2; no explicit flush",
         "e2e": {"value": round(e2e, 1), "unit": "utterances/s", "h2d_bytes_per_step": B * L * 4 + B * 8 + (B * 4 if args.ragged else 0), "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e, 3)},
         "gpu_launches": launches, "cuda_graph": not args.no_graph,
         "hbm_peak_gb": round(torch.cuda.max_memory_reserved(dev) / 2**30, 2), "clocks": clocks, "roofline": roof,
     }
     if not args.no_cpu_baseline and world == 1:
-        v, dt = time_cpu(args, args.cpu_batch, 2, 1)
-        line["cpu_baseline"] = {"value": round(v, 3), "unit": "utterances/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                "sample": f"2 steps of {args.cpu_batch} utterances x {args.seconds:g} s (mel + fwd + bwd) after 1 warm-up, "
-                                          "oracle port of the reference modules on torch CPU ops, all host threads"}
+        cb = cpu_batch(args)
+        v, dt, kind, threads = time_cpu(args, cb, 2, 1)
+        impl = "unmodified reference modules (baseline/_ref)" if kind == "reference" else "oracle port of the reference modules"
+        line["cpu_baseline"] = {"value": round(v, 3), "unit": "utterances/s", "cores": threads, "kind": kind,
+                                "sample": f"best of 2 steps of {cb} utterances x {args.seconds:g} s (per-utterance mel + collate + fwd + bwd) after "
+                                          f"1 warm-up, {impl}, torch CPU, {threads} threads"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

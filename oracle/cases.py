@@ -33,6 +33,29 @@ ORACLE_ONLY_CASES = {
 }
 
 
+# BASELINE.json configs[2] / [3] model families at batches the CPU reference finishes in seconds: TitaNet-M/10 (hidden 512,
+# depthwise K = 7) and TitaNet-L/5 (hidden 1024, K = 11) with the ArcFace head of parameters.yml:42-44 (s = 30, m = 0.2); the
+# L case is "ragged": every utterance has its own number of frames (1..8 s) and zeros behind it, as datasets.collate_fn
+# (src/datasets.py:48-73) leaves a padded batch -- the model never sees the lengths (src/learn.py:88).
+BIG_CASES = {
+    "m10_arc_b8": dict(spec=TitaNetSpec.named("m", 10), loss="arc", nc=251, B=8, T=301, scale=30, margin=0.2, ragged=False),
+    "l5_arc_ragged_b4": dict(spec=TitaNetSpec.named("l", 5), loss="arc", nc=251, B=4, T=801, scale=30, margin=0.2, ragged=True),
+}
+
+
+def big_inputs(case, seed=42):
+    """(x [B, 80, T], labels, frames per utterance) of a BIG_CASES entry."""
+    x, y = train_inputs(case["spec"], case["nc"], case["B"], case["T"], seed)
+    frames = torch.full((case["B"],), case["T"], dtype=torch.int64)
+    if case["ragged"]:
+        g = torch.Generator().manual_seed(seed + 3)
+        frames = 1 + 100 * torch.randint(1, 9, (case["B"],), generator=g)
+        frames[0] = case["T"]                                  # the batch maximum defines T
+        for b in range(case["B"]):
+            x[b, :, int(frames[b]):] = 0.0
+    return x, y, frames
+
+
 def train_inputs(spec, n_classes, B, T, seed=42):
     g = torch.Generator().manual_seed(seed + 1)
     x = 0.3 * torch.randn(B, spec.n_mels, T, generator=g)

@@ -103,7 +103,7 @@ def case_cfg1():
     save("cfg1_s17_eval", emb=emb, n_params=np.int64(m.get_n_params()))
 
 
-from cases import TINY, TRAIN_CASES, ORACLE_ONLY_CASES, train_inputs, mel_inputs, eval_dx_inputs  # noqa: E402
+from cases import TINY, TRAIN_CASES, ORACLE_ONLY_CASES, BIG_CASES, big_inputs, train_inputs, mel_inputs, eval_dx_inputs  # noqa: E402
 
 
 def train_case(name, spec, loss, n_classes, B, T, scale=None, margin=None, full_grads=True, seed=42,
@@ -135,6 +135,60 @@ def train_case(name, spec, loss, n_classes, B, T, scale=None, margin=None, full_
         out["buf:loss_function.fc.weight"] = sd_after["loss_function.fc.weight"]
     save(name, **out)
     return names
+
+
+def big_case(name, case):
+    """TitaNet-M/10 and TitaNet-L/5 (ragged) train steps with the ArcFace head: embeddings, loss, predictions, input gradient,
+    the gradients of every small parameter tensor and the norm of every gradient."""
+    m = build_ref(case["spec"], case["loss"], case["nc"], case["scale"], case["margin"]).train()
+    x, y, frames = big_inputs(case)
+    x.requires_grad_(True)
+    emb, preds, lval = m(x, speakers=y)
+    lval.backward()
+    out = dict(emb=emb, preds=preds, loss=lval, dx=x.grad, frames=frames)
+    out["grad_norms"] = torch.stack([p.grad.norm() for _, p in m.named_parameters()])
+    for k, p in m.named_parameters():
+        if p.numel() <= 2048:
+            out["grad:" + k] = p.grad
+    out["buf:loss_function.fc.weight"] = m.state_dict()["loss_function.fc.weight"]
+    save(name, **out)
+
+
+def case_checkpoint():
+    """A checkpoint written by the reference's own ``save_checkpoint`` (src/learn.py:180-201, extracted with ``ast`` because
+    ``learn`` imports wandb / rich / matplotlib, which are not installed) after two ``torch.optim.Adam`` steps of the
+    reference model (train.py:130-136: lr 1e-3, weight_decay 0; CosineAnnealingLR as train.py:138-144), plus the
+    parameters the reference reaches after a THIRD step on the same batch: what a resumed run must reproduce."""
+    import ast
+    import tempfile
+    src = open(os.path.join(REF, "learn.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "save_checkpoint")
+    ns = {"os": os, "torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "learn.py", "exec"), ns)
+    spec, loss, nc, B, T, scale, margin, _ = TRAIN_CASES["tiny_k3_arc"]
+    m = build_ref(spec, loss, nc, scale, margin).train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=0)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=10)
+    x, y = train_inputs(spec, nc, B, T)
+
+    def step():
+        _, _, lval = m(x, speakers=y)
+        opt.zero_grad()
+        lval.backward()
+        opt.step()
+        return float(lval)
+
+    losses_seen = [step(), step()]
+    sched.step()
+    with tempfile.TemporaryDirectory() as d:
+        ns["save_checkpoint"](2, d, m, opt, lr_scheduler=sched)
+        blob = open(os.path.join(d, "epoch_2.pth"), "rb").read()
+    with open(os.path.join(OUT, "ref_checkpoint_tiny_k3_arc.pth"), "wb") as f:
+        f.write(blob)
+    losses_seen.append(step())
+    after = {"param:" + k: p.detach().clone() for k, p in m.named_parameters()}
+    save("ref_checkpoint_tiny_k3_arc_step3", losses=np.asarray(losses_seen), lr=np.float64(opt.param_groups[0]["lr"]), **after)
+    print("wrote ref_checkpoint_tiny_k3_arc.pth", len(blob), "bytes")
 
 
 def case_fp64():
@@ -172,6 +226,13 @@ if __name__ == "__main__":
     if only == {"fp64"}:
         case_fp64()
         sys.exit(0)
+    if only == {"big"}:
+        for name, case in BIG_CASES.items():
+            big_case(name, case)
+        sys.exit(0)
+    if only == {"checkpoint"}:
+        case_checkpoint()
+        sys.exit(0)
     if not only:
         case_mel()
         case_specaugment()
@@ -184,3 +245,6 @@ if __name__ == "__main__":
     if not only:
         case_eval_input_grad()
         case_fp64()
+        for name, case in BIG_CASES.items():
+            big_case(name, case)
+        case_checkpoint()

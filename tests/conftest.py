@@ -21,6 +21,10 @@ def pytest_collection_modifyitems(config, items):
         has_gpu = torch.cuda.is_available()
     except Exception:  # pragma: no cover
         has_gpu = False
+    # the BASELINE-configuration parity tests (whole model, tensor-core path) run first: under `-x` a failure elsewhere must
+    # not hide them
+    first = ("test_cfg2_baseline_config", "test_big_model_train_step", "test_train_step_matches_reference", "test_cfg1_eval")
+    items.sort(key=lambda it: next((i for i, n in enumerate(first) if n in it.nodeid and "test_gpu_model" in it.nodeid), len(first)))
     if has_gpu:
         return
     skip = pytest.mark.skip(reason="no CUDA device")

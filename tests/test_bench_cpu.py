@@ -24,7 +24,10 @@ def test_reference_arm_prints_one_json_line():
     assert d["metric"] == "utterances/sec (TitaNet-S fwd+bwd, 1s@16kHz)" and d["vs_baseline"] is None and d["dtype"] == "f32"
     assert d["config"]["workload"].startswith("TitaNet-S/1 fwd+bwd, CE loss")
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "utterances" in cb["sample"]
+    have_ref = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "models.py"))      # installed by __graft_entry__.build()
+    assert cb["kind"] == ("reference" if have_ref else "port")
+    assert cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "utterances" in cb["sample"]
+    assert d["config"]["batch_per_gpu"] == 2 and d["reference_default_threads"]["cores"] == 2
     assert d["e2e"] == {"value": d["value"], "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

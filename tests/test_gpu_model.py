@@ -14,7 +14,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 import titanet_oracle as O  # noqa: E402  (checker only)
-from cases import TRAIN_CASES, TINY, train_inputs, eval_dx_inputs  # noqa: E402
+from cases import BIG_CASES, TRAIN_CASES, TINY, big_inputs, train_inputs, eval_dx_inputs  # noqa: E402
 
 
 def rel(a, b, floor=1e-30):
@@ -71,14 +71,13 @@ def test_train_step_matches_reference(golden_dir, name):
     sd64 = O.synth_state_dict(spec, loss, nc, dtype=torch.float64)
     r64 = O.titanet_step(sd64, spec, x.double(), y, loss, scale=scale, margin=margin, input_grad=True)
     if spec.n_mega_blocks > 4:
-        # S/17 at batch 4 (my stress case, not a BASELINE config): 72 train-mode BatchNorms over a tiny batch amplify
-        # fp32 rounding so much that the reference's own fp32 forward sits ~6e-4 from its fp64 run.  Two independent
-        # fp32 evaluations can therefore differ by ~1e-3; judge against fp64 with the reference's error as yard-stick.
+        # S/17 at batch 4 (a stress case, not a BASELINE config): 72 train-mode BatchNorms over 404 samples per channel amplify
+        # fp32 rounding so much that the reference's own fp32 forward sits 5.8e-4 from its fp64 run.  The CUDA path must be
+        # at least as close to fp64 as that (measured 1.5e-4: K-chunked TMEM accumulators + 3xTF32), and within the 1e-3
+        # contract of the reference's fp32 run.
         ref_err = rel(g["emb"], r64[0])
-        assert rel(emb, r64[0]) <= max(1e-3, 2.0 * ref_err), "embeddings vs fp64 oracle"
-        assert rel(emb, g["emb"]) < 2e-3, "embeddings vs reference"
-    else:
-        assert rel(emb, g["emb"]) < 1e-3, "embeddings vs reference"
+        assert rel(emb, r64[0]) <= 2.0 * ref_err, "embeddings vs fp64 oracle"
+    assert rel(emb, g["emb"]) < 1e-3, "embeddings vs reference"
     assert abs(float(lval) - float(g["loss"])) <= 1e-3 * abs(float(g["loss"])), "loss vs reference"
     assert np.array_equal(preds.cpu().numpy(), g["preds"])
     # gradients: fp64 oracle as truth, fp32 reference (golden) error as the yard-stick
@@ -113,12 +112,27 @@ def test_eval_input_gradient_is_per_sample(golden_dir):
     assert bool((x.grad[0] == 0).all()) and bool((x.grad[2] == 0).all()) and bool((x.grad[1] != 0).any())
 
 
-def test_cfg2_shape_against_oracle():
-    """BASELINE.json configs[1] shape (S/17 + CE, 3 s utterances) at a batch the CPU oracle
-    finishes in seconds; dropout 0 for parity."""
+def _grad_report(model, grads64, grads32):
+    """(worst per-tensor rel-max error of the CUDA gradients vs fp64, the same for the fp32 oracle, both global rel-L2)."""
+    gmax = max(float(v.abs().max()) for v in grads64.values())
+    worst, worst32, num, num32, den = 0.0, 0.0, 0.0, 0.0, 0.0
+    for k, p in model.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
+        worst = max(worst, rel(p.grad, grads64[k], floor=1e-3 * gmax))
+        worst32 = max(worst32, rel(grads32[k], grads64[k], floor=1e-3 * gmax))
+        num += float((p.grad.detach().double().cpu() - grads64[k]).norm() ** 2)
+        num32 += float((grads32[k].double() - grads64[k]).norm() ** 2)
+        den += float(grads64[k].norm() ** 2)
+    return worst, worst32, (num / den) ** 0.5, (num32 / den) ** 0.5
+
+
+def test_cfg2_baseline_config_against_oracle():
+    """BASELINE.json configs[1] exactly: TitaNet-S/17 + CE(251), batch 64, 3 s @ 16 kHz synthetic waveforms through the CUDA mel
+    front end, train mode; dropout 0 for parity.  Embeddings / loss within 1e-3 of the fp32 CPU forward, every
+    gradient judged against the fp64 oracle with the fp32 oracle's own error as the yard-stick, and the forward bit-reproducible."""
     from titanet_b200 import transforms
     spec = O.TitaNetSpec.named("s", 17)
-    B = 16
+    B = 64
     wave, labels = O.synthetic_batch(B, seconds=3.0, n_classes=251, seed=42)
     mel = transforms.MelSpectrogram(16000, n_fft=512, win_length=400, hop_length=160, n_mels=80, specaugment_probability=0.0)
     model = build_model(spec, "ce", 251).train()
@@ -131,7 +145,77 @@ def test_cfg2_shape_against_oracle():
     emb_r, preds_r, loss_r, grads_r, _ = O.titanet_step(sd, spec, x_ref, labels, "ce")
     assert rel(emb, emb_r) < 1e-3
     assert abs(float(loss) - float(loss_r)) <= 1e-3 * abs(float(loss_r))
-    assert torch.isfinite(loss) and all(torch.isfinite(p.grad).all() for p in model.parameters())
+    assert int((preds.cpu() != preds_r).sum()) <= 1            # an argmax over 251 near-equal random-init logits may tie-break once
+    r64 = O.titanet_step(O.synth_state_dict(spec, "ce", 251, dtype=torch.float64), spec, x_ref.double(), labels, "ce")
+    assert rel(emb, r64[0]) <= max(2.0 * rel(emb_r, r64[0]), 2e-4), "embeddings vs fp64 oracle"
+    worst, worst32, l2, l2_32 = _grad_report(model, r64[3], grads_r)
+    assert worst <= max(3.0 * worst32, 2e-3), (worst, worst32)
+    assert l2 <= max(3.0 * l2_32, 2e-3), (l2, l2_32)
+    # the forward pass has no floating-point atomics: a second model instance reproduces it bit for bit
+    model2 = build_model(spec, "ce", 251).train()
+    emb2, _, loss2 = model2(x, speakers=labels.cuda())
+    assert torch.equal(emb, emb2) and torch.equal(loss, loss2)
+
+
+@pytest.mark.parametrize("name", list(BIG_CASES))
+def test_big_model_train_step_matches_reference(golden_dir, name):
+    """BASELINE.json configs[2] / [3] model families on the tensor-core path: TitaNet-M/10 (hidden 512, depthwise K = 7, batch 8)
+    and TitaNet-L/5 (hidden 1024, K = 11, batch 4, ragged 1-8 s utterances zero padded to 801 frames), ArcFace(s=30, m=0.2),
+    against the reference's own run (golden) and the fp64 oracle (src/losses.py:77-132, src/datasets.py:48-73)."""
+    case = BIG_CASES[name]
+    spec, loss, nc = case["spec"], case["loss"], case["nc"]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    model = build_model(spec, loss, nc, case["scale"], case["margin"]).train()
+    x, y, frames = big_inputs(case)
+    xg = x.cuda().requires_grad_(True)
+    from titanet_b200 import _lib
+    _lib.COUNTS.clear()
+    emb, preds, lval = model(xg, speakers=y.cuda())
+    lval.backward()
+    assert _lib.COUNTS.get("tn_gemm_tc_bn", 0) > 0 and _lib.COUNTS.get("tn_gemm_tc_dwbwd", 0) > 0 and _lib.COUNTS.get("tn_wgrad_tc", 0) > 0
+    assert rel(emb, g["emb"]) < 1e-3, "embeddings vs reference"
+    assert abs(float(lval) - float(g["loss"])) <= 1e-3 * abs(float(g["loss"])), "loss vs reference"
+    assert np.array_equal(preds.cpu().numpy(), g["preds"])
+    kw = dict(scale=case["scale"], margin=case["margin"])
+    r64 = O.titanet_step(O.synth_state_dict(spec, loss, nc, dtype=torch.float64), spec, x.double(), y, loss, input_grad=True, **kw)
+    r32 = O.titanet_step(O.synth_state_dict(spec, loss, nc), spec, x, y, loss, input_grad=True, **kw)
+    # fp32-level accuracy where the tile leaves room for K-chunked accumulators (M/10 here: 5 per tile); the L/5 tiles (96
+    # rows x 2, one wave) keep one main accumulator over K = 1024, whose truncating accumulate costs 2.1e-4 (measured) --
+    # inside the 1e-3 contract, 14x the reference's own fp32 error
+    big_k = spec.hidden >= 1024
+    assert rel(emb, r64[0]) <= max(2.0 * rel(g["emb"], r64[0]), 3e-4 if big_k else 1e-4), "embeddings vs fp64 oracle"
+    # Gradients inherit the forward error through the train-mode BatchNorms (exact CUDA-core weight gradients change nothing,
+    # tests/diagnostics/big_case_diag.py): L/5 measures 1.4e-2 on its worst tensor and 2.9e-3 global rel-L2, where the fp32
+    # reference sits at 2.4e-3 / 8e-4; M/10 matches the fp32 reference's own error.
+    worst, worst32, l2, l2_32 = _grad_report(model, r64[3], r32[3])
+    assert worst <= max(3.0 * worst32, 2e-2 if big_k else 2e-3), (worst, worst32)
+    assert l2 <= max(3.0 * l2_32, 5e-3 if big_k else 2e-3), (l2, l2_32)
+    assert rel(xg.grad, r64[5]) <= max(3.0 * rel(g["dx"], r64[5]), 2e-2 if big_k else 2e-3)
+    if case["ragged"]:      # zero-padded frames still receive a gradient (no masking anywhere, src/learn.py:88)
+        assert bool((xg.grad[1, :, int(frames[1]):] != 0).any())
+    assert rel(model.state_dict()["loss_function.fc.weight"], g["buf:loss_function.fc.weight"]) < 1e-5
+
+
+def test_ragged_mel_batch_feeds_the_model_like_collate():
+    """configs[3] front end: per-utterance lengths on the device, each mel on its own length (own reflect padding), zero padded
+    to the batch maximum like datasets.collate_fn (src/datasets.py:48-73); the oracle does it utterance by utterance."""
+    from titanet_b200 import transforms
+    B = 6
+    wave, _ = O.synthetic_batch(B, seconds=8.0, n_classes=251, seed=7)
+    lens = torch.tensor([128000, 16000, 48000, 16160, 80000, 31999], dtype=torch.int32)
+    mel = transforms.MelSpectrogram(16000, n_fft=512, win_length=400, hop_length=160, n_mels=80, specaugment_probability=0.0)
+    x = mel.batch(wave.cuda(), lens.cuda())
+    ref, _ = O.collate_pad([O.mel_spectrogram(w[:n].view(1, -1)) for w, n in zip(wave, lens.tolist())])
+    assert x.shape == ref.shape == (B, 80, 801)
+    assert rel(x, ref) < 2e-5
+    for b, n in enumerate(lens.tolist()):
+        assert bool((x[b, :, 1 + n // 160:] == 0).all())
+    # device-side validation of the lengths (no host copy in a captured step): too short -> zeros, too long -> clipped to the row
+    bad = torch.tensor([100, 200000, 48000, 256, 257, 128000], dtype=torch.int32)
+    xb = mel.batch(wave.cuda(), bad.cuda())
+    assert bool((xb[0] == 0).all()) and bool((xb[3] == 0).all()) and bool(torch.isfinite(xb).all())
+    full = mel.batch(wave.cuda())
+    assert torch.equal(xb[1], full[1]) and torch.equal(xb[5], full[5]) and torch.equal(xb[2], x[2])
 
 
 def test_dropout_training_runs_and_is_finite():
@@ -146,5 +230,19 @@ def test_dropout_training_runs_and_is_finite():
     model.eval()
     with torch.no_grad():
         e1, e2 = model(x.cuda()), model(x.cuda())
-    # no dropout in eval mode (bitwise equality is not promised: reductions use float atomics)
-    assert torch.allclose(e1, e2, rtol=0, atol=1e-6)
+    # no dropout in eval mode, and no floating-point atomics in the forward pass: bit-for-bit equal
+    assert torch.equal(e1, e2)
+
+
+def test_reseed_dropout_reproduces_the_masks():
+    from titanet_b200 import modules
+    spec = O.TitaNetSpec.named("s", 2, dropout=0.1)
+    model = build_model(spec, "ce", 251).train()
+    x, y = train_inputs(spec, 251, 4, 101)
+    modules.reseed_dropout(1234)                       # index-less 'cuda' and 'cuda:0' are the same stream
+    a1 = model(x.cuda(), speakers=y.cuda())[2]
+    a2 = model(x.cuda(), speakers=y.cuda())[2]
+    modules.reseed_dropout(1234, device="cuda:0")
+    b1 = model(x.cuda(), speakers=y.cuda())[2]
+    b2 = model(x.cuda(), speakers=y.cuda())[2]
+    assert torch.equal(a1, b1) and torch.equal(a2, b2) and not torch.equal(a1, a2)

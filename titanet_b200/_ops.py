@@ -997,6 +997,7 @@ def rownorm_(w: Tensor, eps: float = 1e-12) -> Tensor:
     require_cuda(w)
     assert w.is_contiguous() and w.dtype == torch.float32
     call("tn_rownorm_inplace", ptr(w), w.shape[0], w.shape[1], float(eps))
+    torch.autograd.graph.increment_version(w)      # modified outside autograd's view (like ``.data = ...`` in the reference)
     return w
 
 

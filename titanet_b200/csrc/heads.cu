@@ -36,11 +36,16 @@ __global__ void __launch_bounds__(128) ce_kernel(const float* __restrict__ logit
   for (int j = lane; j < Cn; j += 32) s += expf(l[j] - mv);
   s = tn_warp_sum(s);
   const float lse = mv + logf(s);
-  const int y = (int)targets[row];
+  // a label outside [0, Cn) never indexes memory: its row's loss is NaN (F.cross_entropy raises; here the reference's own
+  // non-finite-loss guard, src/learn.py:110-112, stops the run)
+  const long long yt = targets[row];
+  const bool bad = yt < 0 || yt >= Cn;
+  const int y = bad ? 0 : (int)yt;
   if (dlogits)
-    for (int j = lane; j < Cn; j += 32) dlogits[(size_t)row * Cn + j] = (expf(l[j] - lse) - (j == y ? 1.f : 0.f)) * inv_B;
+    for (int j = lane; j < Cn; j += 32)
+      dlogits[(size_t)row * Cn + j] = bad ? __int_as_float(0x7fc00000) : (expf(l[j] - lse) - (j == y ? 1.f : 0.f)) * inv_B;
   if (lane == 0) {
-    loss_row[row] = lse - l[y];
+    loss_row[row] = bad ? __int_as_float(0x7fc00000) : lse - l[y];
     preds[row] = mi;
   }
 }
@@ -58,7 +63,9 @@ __global__ void __launch_bounds__(128) margin_kernel(const float* __restrict__ r
   if (row >= B) return;
   const float* rw = raw + (size_t)row * Cn;
   const float s = use_norm_scale ? norms[row] : scale;
-  const int y = (int)targets[row];
+  const long long yt = targets[row];
+  const bool bad = yt < 0 || yt >= Cn;           // out-of-range label: NaN loss for the row, no out-of-bounds access
+  const int y = bad ? 0 : (int)yt;
   float mv = -INFINITY;
   int mi = 0x7fffffff;
   float others = 0.f, cw = 0.f;       // sum_{j != y} exp(s c_j) and sum_{j != y} c_j exp(s c_j)
@@ -93,11 +100,11 @@ __global__ void __launch_bounds__(128) margin_kernel(const float* __restrict__ r
         const float c = fminf(fmaxf(r, -1.f), 1.f);
         g = s * expf(s * c) / den;
       }
-      draw[(size_t)row * Cn + j] = inside ? g * inv_B : 0.f;
+      draw[(size_t)row * Cn + j] = bad ? __int_as_float(0x7fc00000) : (inside ? g * inv_B : 0.f);
     }
   }
   if (lane == 0) {
-    loss_row[row] = logf(den) - num;
+    loss_row[row] = bad ? __int_as_float(0x7fc00000) : logf(den) - num;
     preds[row] = mi;
     if (dnorm) dnorm[row] = use_norm_scale ? (dnum * (cphi - m3) + cw / den) * inv_B : 0.f;
   }

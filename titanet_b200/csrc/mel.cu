@@ -47,11 +47,16 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float* __restric
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * MEL_FT;
-  const int L = lengths ? lengths[b] : L_full;
+  // per-utterance lengths are device data: never trust them with an address.  A length beyond the row is clipped to it; a
+  // length the reflect padding cannot serve (<= n_fft / 2, where torch.stft raises) yields an all-zero spectrogram.
+  int L = lengths ? lengths[b] : L_full;
+  if (L > L_stride) L = L_stride;
+  const bool bad_len = L <= N / 2;
+  if (bad_len) L = N / 2 + 1;
   const int T_src = 1 + L / hop;                             // frames of the (unstretched) spectrogram
   const double rate = aug.rates ? aug.rates[b] : 1.0;
   const bool stretch = rate != 1.0;
-  const int T_valid = stretch ? aug.frames[b] : T_src;       // frames this utterance produces; later ones are zero
+  const int T_valid = bad_len ? 0 : (stretch ? aug.frames[b] : T_src);   // frames this utterance produces; later ones are zero
   const int step = stretch ? 1 : 2;                          // output frames per FFT
   const float* x = wave + (size_t)b * L_stride;
   const int half = N / 2;

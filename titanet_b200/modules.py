@@ -73,10 +73,18 @@ class DropoutCtx:
 _GLOBAL_SEED_STATE = {}
 
 
+def _seed_key(device) -> str:
+    """One seed stream per physical device: 'cuda' and 'cuda:0' (the current device) are the same stream."""
+    dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return str(dev)
+
+
 def new_dropout_ctx(device, needed: bool) -> DropoutCtx:
     if not needed:
         return DropoutCtx(None)
-    key = str(device)
+    key = _seed_key(device)
     st = _GLOBAL_SEED_STATE.get(key)
     if st is None:
         st = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64).to(device)
@@ -85,9 +93,16 @@ def new_dropout_ctx(device, needed: bool) -> DropoutCtx:
 
 
 def reseed_dropout(seed: int, device="cuda"):
-    """Reset the dropout seed stream (for reproducible runs)."""
-    _GLOBAL_SEED_STATE[str(torch.device(device) if not isinstance(device, torch.device) else device)] = torch.tensor(
-        [seed & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64).to(device)
+    """Reset the dropout seed stream of ``device`` (for reproducible runs): the next forward passes draw the same masks as
+    the forward passes that followed the previous ``reseed_dropout(seed)``.  The state tensor is updated IN PLACE, so a
+    captured CUDA graph (which holds its address) follows."""
+    key = _seed_key(device)
+    value = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64)
+    st = _GLOBAL_SEED_STATE.get(key)
+    if st is None:
+        _GLOBAL_SEED_STATE[key] = value.to(torch.device(key))
+    else:
+        st.copy_(value)
 
 
 def _check_conv_supported(conv: nn.Conv1d):

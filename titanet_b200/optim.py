@@ -43,10 +43,22 @@ class FusedAdam(torch.optim.Optimizer):
         if plan is None or plan["ids"] != [id(p) for p in ps]:
             total = sum(p.numel() for p in ps)
             plan = dict(m=torch.zeros(total, device=dev), v=torch.zeros(total, device=dev), ids=[id(p) for p in ps],
-                        hyper=torch.zeros(10, device=dev), lr=None)
-            b1, b2 = group["betas"]
-            plan["hyper"].copy_(torch.tensor([group["lr"], b1, b2, group["eps"], group["weight_decay"], 0.0, 1.0, 1.0, 1.0 - b1, 1.0 - b2]))
-            plan["lr"] = group["lr"]
+                        hyper=torch.zeros(10, device=dev), hp=None)
+            # Resume: moments / step loaded by ``load_state_dict`` (a torch.optim.Adam or FusedAdam checkpoint, e.g. the
+            # "optimizer" entry the reference writes, src/learn.py:188-199) move into the flat buffers; the device step
+            # counter continues from the loaded step.
+            step0, off = 0.0, 0
+            for p in ps:
+                st = self.state[p]
+                n = p.numel()
+                if "exp_avg" in st:
+                    plan["m"][off:off + n].copy_(st["exp_avg"].reshape(-1))
+                if "exp_avg_sq" in st:
+                    plan["v"][off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                if "step" in st:
+                    step0 = max(step0, float(st["step"]))
+                off += n
+            plan["step0"] = step0
             off = 0
             for p in ps:          # expose the moments the way torch.optim.Adam does (views of the flat buffers)
                 st = self.state[p]
@@ -64,6 +76,11 @@ class FusedAdam(torch.optim.Optimizer):
         self._plans[gi] = plan
         return plan
 
+    @staticmethod
+    def _hyper_of(group):
+        b1, b2 = group["betas"]
+        return (float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]))
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -74,9 +91,36 @@ class FusedAdam(torch.optim.Optimizer):
             plan = self._plan(gi, group)
             if plan is None:
                 continue
-            if plan["lr"] != group["lr"]:                       # LR schedulers write param_groups[i]["lr"]
-                plan["hyper"][0:1].copy_(torch.tensor([group["lr"]]), non_blocking=True)
-                plan["lr"] = group["lr"]
+            hp = self._hyper_of(group)
+            if plan["hp"] is None:                              # first step of this plan: all ten entries, step included
+                lr, b1, b2, eps, wd = hp
+                plan["hyper"].copy_(torch.tensor([lr, b1, b2, eps, wd, plan["step0"], 1.0, 1.0, 1.0 - b1, 1.0 - b2]))
+                plan["hp"] = hp
+            elif plan["hp"] != hp:                              # LR schedulers (and users) write param_groups[i][...]
+                lr, b1, b2, eps, wd = hp
+                plan["hyper"][0:5].copy_(torch.tensor([lr, b1, b2, eps, wd]), non_blocking=True)
+                plan["hyper"][8:10].copy_(torch.tensor([1.0 - b1, 1.0 - b2]), non_blocking=True)
+                plan["hp"] = hp
             call("tn_adam_tick", ptr(plan["hyper"]))
             call("tn_adam_multi", ptr(plan["jobs"]), plan["njobs"], plan["max_n"], ptr(plan["hyper"]))
+            # the update ran outside autograd's view: bump the version counters so that saved-tensor checks and the
+            # per-step weight-split cache (ops.SplitCache) see the parameters as modified
+            torch.autograd.graph.increment_version([p for p in group["params"] if p.grad is not None])
         return loss
+
+    def state_dict(self):
+        """torch.optim.Adam's layout, ``step`` included (read back from the device counter), so that either optimizer can
+        resume from the other's checkpoint."""
+        for gi, group in enumerate(self.param_groups):
+            plan = self._plans.get(gi)
+            if plan is None:
+                continue
+            step = float(plan["hyper"][5]) if plan["hp"] is not None else plan["step0"]
+            for p in group["params"]:
+                if p in self.state and "exp_avg" in self.state[p]:
+                    self.state[p]["step"] = torch.tensor(step)
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._plans = {}                                        # rebuilt (from the loaded moments and step) on the next step

@@ -134,7 +134,9 @@ class MelSpectrogram:
               augment=None) -> torch.Tensor:
         """``[B, L]`` CUDA waveforms -> ``[B, n_mels, T]`` with ``T = 1 + L // hop``.  With
         ``lengths`` (samples per utterance) each utterance is transformed on its own length
-        (own reflect padding) and frames past it are zero, like ``collate_fn``.
+        (own reflect padding) and frames past it are zero, like ``collate_fn``.  ``lengths`` is device data (a static
+        buffer of a captured step), so it is validated on the device: a length beyond ``L`` is clipped to ``L`` and a
+        length <= ``n_fft // 2`` (which ``torch.stft`` rejects) produces an all-zero spectrogram.
 
         ``augment``: ``None`` (no SpecAugment), ``True`` (draw per utterance with ``draw_specaugment``) or a list of
         B ``SpecAugmentDraw`` / ``None``.  Stretched utterances have ``ceil(T_b / rate_b)`` frames; T becomes the
@@ -149,6 +151,8 @@ class MelSpectrogram:
                                    nwc=channels_last)
         B, L = waveforms.shape
         lens = [L] * B if lengths is None else [int(v) for v in lengths.tolist()]
+        if any(v <= self.n_fft // 2 or v > L for v in lens):      # host-visible here: refuse what torch.stft refuses
+            raise ValueError(f"utterance lengths must lie in ({self.n_fft // 2}, {L}] samples (reflect padding / row length)")
         src_frames = [self.n_frames(v) for v in lens]
         if augment is True:
             augment = [self.draw_specaugment(t) for t in src_frames]
