@@ -43,17 +43,24 @@ extern "C" {
 #define TN_EPI_ACCUM 2  /* z += previous contents of Z       */
 #define TN_GEMM_GRAD 8  /* tensor-core GEMMs: this is a gradient GEMM (the cheaper TF32 + bf16-correction split is allowed) */
 
-/* Scratch of the kernels that reduce across thread blocks WITHOUT floating-point atomics (BatchNorm statistics in the GEMM
- * epilogues, split-K): every block stores its partial result to `parts` and the last block of a group (device-wide ticket)
- * adds the partials in a fixed order, so a forward pass is reproducible bit for bit.
- *   parts   uninitialised fp32 workspace of parts_floats elements, 16-byte aligned (tn_*_scratch_floats says how many)
- *   tickets TN_TICKETS unsigned ints, ZERO on entry and returned to zero by every kernel that uses them: one array per
- *           stream may be shared by all calls (kernels that run concurrently must not share it) */
+/* Scratch of the kernels that reduce across thread blocks WITHOUT floating-point atomics, so that a forward pass is
+ * reproducible bit for bit:
+ *   accum   BatchNorm statistics of the GEMM epilogues: every block adds its per-channel partial sums into 120-bit fixed-point
+ *           accumulators (two unsigned 64-bit integer atomics per value: integer addition is associative, the order of
+ *           arrival does not matter); the last block of a channel group (ticket) reads the totals.  TN_ACCUM_WORDS(C)
+ *           64-bit words for C channels, ZERO on entry, returned to zero by the kernel.
+ *   tickets TN_TICKETS unsigned ints, ZERO on entry and returned to zero by every kernel that uses them.
+ *   parts   uninitialised fp32 workspace of parts_floats elements, 16-byte aligned: split-K partial tiles of
+ *           tn_conv_gemm_simt (tn_conv_gemm_simt_scratch_floats says how many), added in split order by the last block.
+ * One accum / tickets pair per stream may be shared by all calls (kernels that run concurrently must not share it). */
 #define TN_TICKETS 64
+#define TN_ACCUM_WORDS(C) (4 * (long long)(C) + TN_TICKETS / 2)
 typedef struct tn_scratch {
   float* parts;
   long long parts_floats;
   unsigned int* tickets;
+  unsigned long long* accum;
+  long long accum_words;
 } tn_scratch;
 
 const char* tn_last_error(void);
@@ -86,8 +93,9 @@ int tn_mel_specaug_fwd(const float* wave, const int* lengths, const float* windo
  * 510-513; src/losses.py:30,70).  stats (fp64 [2*Co], written; needs Co %% 4 == 0) receives the
  * per-channel sum and sum of squares of Z for the following BatchNorm.
  * transpose_w = 1 computes the data gradient (X := dZ, weight read as W[ci',co',K-1-k]).
- * scratch: required when tn_conv_gemm_simt_scratch_floats(...) > 0 (statistics, or a skinny problem run as split-K). */
-long long tn_conv_gemm_simt_scratch_floats(int B, int T, int Ci, int Co, int K, int flags, int with_stats);
+ * scratch: required for statistics (accum + tickets) and when tn_conv_gemm_simt_scratch_floats(...) > 0 (a skinny problem
+ * run as split-K: parts + tickets). */
+long long tn_conv_gemm_simt_scratch_floats(int B, int T, int Ci, int Co, int K, int flags);
 int tn_conv_gemm_simt(const float* X, const float* W, const float* bias, float* Z, double* stats, int B, int T, int Ci,
                       int Co, int K, int transpose_w, int flags, const tn_scratch* scratch, void* stream);
 /* dW[co,ci,k] += sum_r dZ[r,co] X[r+k-K/2,ci];  dbias[co] += sum_r dZ[r,co]   (ACCUMULATED) */
@@ -102,11 +110,10 @@ int tn_conv_wgrad_simt(const float* dZ, const float* X, float* dW, float* dbias,
  * hi*hi + one bf16 MMA carrying both corrections -- or 1 (plain TF32).  When the tile leaves TMEM columns free the main
  * products of consecutive K ranges and the corrections accumulate in separate TMEM accumulators that the epilogue adds
  * in fp32 (the tensor core's accumulate truncates).  Needs Kd %% 32 == 0 and M %% 128 == 0 (tn_gemm_tc_supported).
- * stats (fp64 [2*M], written): per-channel sum / sum of squares of Z; needs scratch (tn_gemm_tc_scratch_floats). */
+ * stats (fp64 [2*M], written): per-channel sum / sum of squares of Z; needs scratch (accum + tickets). */
 int tn_gemm_tc_supported(int R, int Kd, int M);
 int tn_gemm_tc_set_trace(long long* buf);      /* debug: clock64 timeline of two CTAs (256 int64), NULL = off */
 int tn_split_tf32(const float* W, float* ws, int M, int Kd, int transpose, void* stream);
-long long tn_gemm_tc_scratch_floats(int R, int M);
 int tn_gemm_tc(const float* X, const float* ws, const float* bias, float* Z, double* stats, int R, int Kd, int M, int flags,
                int nsplit, const tn_scratch* scratch, void* stream);
 /* Data gradient of a depthwise-separable block in ONE kernel: du = dZ[R,Co] W[Co,C] on the tensor
@@ -126,8 +133,8 @@ int tn_colsum(const float* x, float* out, int R, int C, void* stream);          
 /* ---- train-mode BatchNorm folded INTO its producer / consumer kernels --------------------------
  * tn_bn_fold describes the nn.BatchNorm1d that follows a conv (src/modules.py:128, src/models.py:454,
  * 512).  The *_bn GEMM entry points produce the statistics of Z in their epilogue as before; the
- * last CTA of each channel group to finish (device-wide tickets of the tn_scratch) adds the per-tile partial sums in tile
- * order, folds them into (scale, shift), stores (mean, invstd) for the backward pass and updates the running
+ * last CTA of each channel group to finish (device-wide tickets of the tn_scratch) reads the fixed-point totals,
+ * folds them into (scale, shift), stores (mean, invstd) for the backward pass and updates the running
  * statistics (momentum, unbiased variance) and num_batches_tracked -- i.e. tn_bn_finalize without its
  * launch.  n = samples per channel (B*T). */
 typedef struct tn_bn_fold {
@@ -163,6 +170,32 @@ int tn_conv_gemm_simt_bn(const float* X, const float* W, const float* bias, floa
 int tn_bn_stats_bwd(const float* dz_direct, const float* z, const float* dscale, const float* dshift, const float* mean,
                     const float* invstd, const float* gamma, double n, float* out, float* dbias, float* dgamma,
                     float* dbeta, int R, int C, void* stream);
+/* BatchNorm backward folded into the operand load of the data-gradient GEMM (pair kernel: R >= 512, M %% 256 == 0,
+ * tn_gemm_tc_bnbwd_supported).  dZ is the DIRECT gradient w.r.t. the pre-BatchNorm tensor z [R, Kd] (what the consumers of
+ * the lazy activation return); the transform warps build g = dZ + a[c] + b[c] z from the dZ tile and the z tile with the
+ * statistics-path coefficients a, b of tn_bn_stats_bwd (computed in the kernel from dscale, dshift, mean, invstd, gamma), feed
+ * it to the tensor core, write it to g_out (the weight-gradient GEMM's operand) and add its column sums to dbias
+ * (ACCUMULATED; may be NULL); dgamma / dbeta are written.  Replaces one tn_bn_stats_bwd launch per conv. */
+typedef struct tn_bn_bwd {
+  const float* z;        /* [R, Kd] pre-BatchNorm output of the conv                       */
+  const float* dscale;   /* [Kd] dL/dscale of the folded BatchNorm (sum over rows)         */
+  const float* dshift;   /* [Kd] dL/dshift                                                 */
+  const float* mean;     /* [Kd] saved by the forward fold                                 */
+  const float* invstd;   /* [Kd]                                                           */
+  const float* gamma;    /* [Kd] BatchNorm weight                                          */
+  double n;              /* samples per channel                                            */
+  float* g_out;          /* [R, Kd] out: full gradient w.r.t. z                            */
+  float* dbias;          /* [Kd] or NULL, ACCUMULATED: conv-bias gradient                  */
+  float* dgamma;         /* [Kd] out                                                       */
+  float* dbeta;          /* [Kd] out                                                       */
+} tn_bn_bwd;
+int tn_gemm_tc_bnbwd_supported(int R, int Kd, int M);
+int tn_gemm_tc_bnbwd(const float* dZ, const float* ws, const tn_bn_bwd* bnb, float* dX, int R, int Kd, int M, int flags,
+                     void* stream);
+int tn_gemm_tc_dwbwd_bn(const float* dZ, const float* ws, const tn_bn_bwd* bnb, const float* zprev, float* dzprev,
+                        const float* dw_w, float* g_dw, float* g_dbias, float* g_dscale, float* g_dshift, const float* scale,
+                        const float* shift, int relu, float drop_p, const unsigned long long* seed, unsigned int layer, int B,
+                        int T, int Co, int C, int K, void* stream);
 /* every weight split of a step in ONE launch: jobs (device array) = {W, ws, M, Kd, transpose} like tn_split_tf32 */
 typedef struct tn_split_job {
   const float* W;

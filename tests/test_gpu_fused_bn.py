@@ -51,7 +51,10 @@ def test_conv_bn_fused_matches_fp64(B, T, Ci, Co, K):
     y = ops.Act.apply(z, sc, sh, None, False, 0.0, 0)
     (y * gy.cuda()).sum().backward()
     assert _lib.COUNTS.get("tn_bn_bwd_coef", 0) == 0 and _lib.COUNTS.get("tn_stats_bwd", 0) == 0
-    assert _lib.COUNTS.get("tn_bn_stats_bwd", 0) == 1
+    # many rows and a 256-aligned channel count: the BatchNorm backward runs inside the data-gradient GEMM (tn_gemm_tc_bnbwd),
+    # otherwise as one pass of its own (tn_bn_stats_bwd)
+    fused = K == 1 and R >= 512 and Ci % 256 == 0 and Co % 32 == 0
+    assert _lib.COUNTS.get("tn_bn_stats_bwd", 0) == (0 if fused else 1) and _lib.COUNTS.get("tn_gemm_tc_bnbwd", 0) == (1 if fused else 0)
 
     xr, wr, br = (t.double().clone().requires_grad_(True) for t in (x, w, b))
     xx = xr.view(B, T, Ci).permute(0, 2, 1)

@@ -23,7 +23,7 @@ def run_tc(x, w, bias, nsplit, transpose=False, want_stats=True, flags=0, z0=Non
     call("tn_split_tf32", ptr(w), ptr(ws), M, Kd, int(transpose))
     z = torch.empty(R, M, device="cuda") if z0 is None else z0
     stats = torch.full((2 * M,), float("nan"), device="cuda", dtype=torch.float64) if want_stats else None   # written, not accumulated
-    sc, keep = scratch(x, LIB.query("tn_gemm_tc_scratch_floats", R, M)) if want_stats else (None, None)
+    sc, keep = scratch(x) if want_stats else (None, None)
     call("tn_gemm_tc", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), R, Kd, M, flags, nsplit, ctypes.byref(sc) if sc is not None else None)
     torch.cuda.synchronize()
     return z, stats, ws

@@ -117,9 +117,17 @@ class TnBnFold(ctypes.Structure):
                 ("invstd", ctypes.c_void_p)]
 
 
+class TnBnBwd(ctypes.Structure):
+    """``tn_bn_bwd`` of include/titanet_b200.h (BatchNorm backward folded into the data-gradient GEMM's operand load)."""
+    _fields_ = [("z", ctypes.c_void_p), ("dscale", ctypes.c_void_p), ("dshift", ctypes.c_void_p), ("mean", ctypes.c_void_p),
+                ("invstd", ctypes.c_void_p), ("gamma", ctypes.c_void_p), ("n", ctypes.c_double), ("g_out", ctypes.c_void_p),
+                ("dbias", ctypes.c_void_p), ("dgamma", ctypes.c_void_p), ("dbeta", ctypes.c_void_p)]
+
+
 class TnScratch(ctypes.Structure):
     """``tn_scratch`` of include/titanet_b200.h (workspace + tickets of the atomics-free cross-block reductions)."""
-    _fields_ = [("parts", ctypes.c_void_p), ("parts_floats", ctypes.c_longlong), ("tickets", ctypes.c_void_p)]
+    _fields_ = [("parts", ctypes.c_void_p), ("parts_floats", ctypes.c_longlong), ("tickets", ctypes.c_void_p),
+                ("accum", ctypes.c_void_p), ("accum_words", ctypes.c_longlong)]
 
 
 class TnSplitJob(ctypes.Structure):

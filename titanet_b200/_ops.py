@@ -20,7 +20,7 @@ from torch.autograd import Function
 import ctypes
 import weakref
 
-from ._lib import LIB, TnBnFold, TnScratch, TnSplitJob, call, ptr, require_cuda, stream
+from ._lib import LIB, TnBnBwd, TnBnFold, TnScratch, TnSplitJob, call, ptr, require_cuda, stream
 
 Tensor = torch.Tensor
 EPI_TANH, EPI_ACCUM, GEMM_GRAD = 1, 2, 8
@@ -132,20 +132,26 @@ def seed_next(state: Tensor) -> Tensor:
 
 
 _TICKETS = {}
+ACCUM_MAX_CHANNELS = 8192
 
 
-def scratch(ref: Tensor, floats: int):
-    """(ctypes ``tn_scratch``, keep-alive tensor): an uninitialised workspace of ``floats`` fp32 elements plus the
-    zero-initialised ticket array of the current stream (kernels return it to zero, so one array serves every call on a
-    stream).  The deterministic statistics / split-K reductions of the conv-GEMM entry points need it."""
+def scratch(ref: Tensor, floats: int = 0):
+    """(ctypes ``tn_scratch``, keep-alive tensor) for the atomics-free cross-block reductions of the conv-GEMM entry points:
+    the zero-initialised ticket array and fixed-point statistics accumulators of the current stream (kernels return both to
+    zero, so one pair serves every call on a stream, CUDA-graph replays included) plus, when ``floats`` > 0, an
+    uninitialised fp32 workspace for split-K partial tiles."""
     key = (ref.device, stream())
-    tk = _TICKETS.get(key)
-    if tk is None:
+    ent = _TICKETS.get(key)
+    if ent is None:
+        words = 4 * ACCUM_MAX_CHANNELS + TN_TICKETS // 2
         tk = torch.empty(TN_TICKETS, device=ref.device, dtype=torch.int32)
+        acc = torch.empty(words, device=ref.device, dtype=torch.int64)
         LIB.call("tn_zero", tk.data_ptr(), tk.numel() * 4, stream())
-        _TICKETS[key] = tk
-    parts = torch.empty(max(int(floats), 4), device=ref.device, dtype=torch.float32)
-    return TnScratch(parts.data_ptr(), parts.numel(), tk.data_ptr()), parts
+        LIB.call("tn_zero", acc.data_ptr(), acc.numel() * 8, stream())
+        ent = _TICKETS[key] = (tk, acc)
+    tk, acc = ent
+    parts = torch.empty(int(floats), device=ref.device, dtype=torch.float32) if floats > 0 else None
+    return TnScratch(ptr(parts), int(floats), tk.data_ptr(), acc.data_ptr(), acc.numel()), parts
 
 
 # ----------------------------------------------------------------------------
@@ -265,7 +271,7 @@ def _gemm_tc(x, w2, bias, z, stats, R, Kd, M, transpose, flags, nsplit, tag, ws=
     if ws is None:
         ws = torch.empty((3, M, Kd), device=x.device, dtype=torch.float32)
         call("tn_split_tf32", ptr(w2), ptr(ws), M, Kd, int(transpose))
-    sc, keep = scratch(x, LIB.query("tn_gemm_tc_scratch_floats", R, M)) if stats is not None else (None, None)
+    sc, keep = scratch(x) if stats is not None else (None, None)
     scp = ctypes.byref(sc) if sc is not None else None
     if bn is not None:
         call("tn_gemm_tc_bn", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), ctypes.byref(bn), R, Kd, M, flags, nsplit, scp, tag=tag)
@@ -275,7 +281,7 @@ def _gemm_tc(x, w2, bias, z, stats, R, Kd, M, transpose, flags, nsplit, tag, ws=
 
 def gemm_tc_raw(x, ws, bias, z, stats, R, Kd, M, flags, nsplit):
     """``tn_gemm_tc`` on raw tensors with the scratch it needs (tools / kernel tests)."""
-    sc, keep = scratch(x, LIB.query("tn_gemm_tc_scratch_floats", R, M)) if stats is not None else (None, None)
+    sc, keep = scratch(x) if stats is not None else (None, None)
     call("tn_gemm_tc", ptr(x), ptr(ws), ptr(bias), ptr(z), ptr(stats), R, Kd, M, flags, nsplit,
          ctypes.byref(sc) if sc is not None else None)
 
@@ -289,8 +295,8 @@ def _gemm_fwd(x, w3, bias, z, stats, B, T, transpose_w, flags, ws=None, bn=None)
     if not transpose_w and _tc_ok(R, Ci, Co, K):
         return _gemm_tc(x, w3, bias, z, stats, R, Ci, Co, 0, flags, TC_FWD_NSPLIT, f"fwd R{R} Ci{Ci} Co{Co} K1", ws=ws, bn=bn)
     co_out, ci_red = (Ci, Co) if transpose_w else (Co, Ci)
-    need = LIB.query("tn_conv_gemm_simt_scratch_floats", B, T, ci_red, co_out, K, flags, 1 if stats is not None else 0)
-    sc, keep = scratch(x, need) if need > 0 else (None, None)
+    need = LIB.query("tn_conv_gemm_simt_scratch_floats", B, T, ci_red, co_out, K, flags)
+    sc, keep = scratch(x, need) if (need > 0 or stats is not None) else (None, None)
     scp = ctypes.byref(sc) if sc is not None else None
     if transpose_w:
         call("tn_conv_gemm_simt", ptr(x), ptr(w3), ptr(bias), ptr(z), ptr(stats), B, T, Co, Ci, K, 1, flags, scp,
@@ -386,6 +392,29 @@ def _bn_backward(dz, z, dscale, dshift, fold, gamma, n, bias, R, Co):
     return g, db, dgamma, dbeta
 
 
+# BatchNorm backward folded into the data-gradient GEMM's operand load (tn_gemm_tc_bnbwd / tn_gemm_tc_dwbwd_bn): the transform
+# warps of the pair kernel build g = dz + a[c] + b[c] z on the fly and write it out once for the weight-gradient GEMM, so the
+# tn_bn_stats_bwd launch (read dz, z; write g) disappears.  TN_FUSE_BNBWD=0 restores the separate kernel (A/B).
+TC_FUSE_BNBWD = __import__("os").environ.get("TN_FUSE_BNBWD", "1") != "0"
+
+
+def _bnbwd_fusable(dz, R: int, Kd: int, M: int) -> bool:
+    return (TC_ENABLED and TC_FUSE_BNBWD and TC_BWD_NSPLIT == 3 and dz is not None and R >= 512 and M % 256 == 0 and Kd % 32 == 0
+            and M % 128 == 0)
+
+
+def _make_bn_bwd(dz, z, dscale, dshift, fold, gamma, n, bias, Co):
+    """(TnBnBwd, g, dbias, dgamma, dbeta, keep-alive list) for a fused BatchNorm backward."""
+    dscale = _c(dscale) if dscale is not None else zeros((Co,), z)
+    dshift = _c(dshift) if dshift is not None else zeros((Co,), z)
+    g = empty(z.shape, z)
+    db = zeros((Co,), z) if bias is not None else None
+    dgamma, dbeta = gempty((Co,), z), gempty((Co,), z)
+    bnb = TnBnBwd(ptr(z), ptr(dscale), ptr(dshift), fold[2].data_ptr(), fold[3].data_ptr(), ptr(gamma), float(n), ptr(g), ptr(db),
+                  ptr(dgamma), ptr(dbeta))
+    return bnb, g, db, dgamma, dbeta, (dscale, dshift)
+
+
 class ConvGemmBN(Function):
     """conv (as GEMM) followed by a TRAIN-mode BatchNorm1d, folded: returns the pre-BN tensor ``z`` and the
     per-channel ``(scale, shift)``.  The GEMM epilogue accumulates the statistics and its last CTA folds them
@@ -415,11 +444,21 @@ class ConvGemmBN(Function):
         B, T, n = ctx.meta
         w3 = w if w.dim() == 3 else w.unsqueeze(-1)
         Co, Ci, K = w3.shape
-        g, db, dgamma, dbeta = _bn_backward(dz, z, dscale, dshift, fold, gamma, n, bias, B * T, Co)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx = empty((B * T, Ci), x)
-            _gemm_fwd(g, w3, None, dx, None, B, T, 1, 0, ws=ctx.ws_t)
+        R = B * T
+        if ctx.needs_input_grad[0] and K == 1 and _bnbwd_fusable(dz, R, Co, Ci):
+            bnb, g, db, dgamma, dbeta, keep = _make_bn_bwd(_c(dz), z, dscale, dshift, fold, gamma, n, bias, Co)
+            ws = ctx.ws_t
+            if ws is None:
+                ws = torch.empty((3, Ci, Co), device=x.device, dtype=torch.float32)
+                call("tn_split_tf32", ptr(w3), ptr(ws), Ci, Co, 1)
+            dx = empty((R, Ci), x)
+            call("tn_gemm_tc_bnbwd", ptr(_c(dz)), ptr(ws), ctypes.byref(bnb), ptr(dx), R, Co, Ci, 0, tag=f"bnbwd+dgrad R{R} Ci{Co} Co{Ci} K1")
+        else:
+            g, db, dgamma, dbeta = _bn_backward(dz, z, dscale, dshift, fold, gamma, n, bias, R, Co)
+            dx = None
+            if ctx.needs_input_grad[0]:
+                dx = empty((R, Ci), x)
+                _gemm_fwd(g, w3, None, dx, None, B, T, 1, 0, ws=ctx.ws_t)
         dw = zeros(w.shape, w)
         _gemm_wgrad(g, x, dw if dw.dim() == 3 else dw.unsqueeze(-1), None, B, T)
         return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None, None
@@ -598,7 +637,7 @@ def _dw_pw_forward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, relu, p, layer
         if ws is None:
             ws = torch.empty((3, Co, C), device=z.device, dtype=torch.float32)
             call("tn_split_tf32", ptr(pw3), ptr(ws), Co, C, 0)
-        sc, keep = scratch(z, LIB.query("tn_gemm_tc_scratch_floats", R, Co)) if stats is not None else (None, None)
+        sc, keep = scratch(z) if stats is not None else (None, None)
         call("tn_gemm_tc_dwfwd", ptr(z), ptr(ws), ptr(dw_w), ptr(dw_b), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed),
              int(layer), ptr(pw_b), ptr(u), ptr(zo), ptr(stats), ctypes.byref(bn) if bn is not None else None, B, T, C, Co, K,
              ctypes.byref(sc) if sc is not None else None, tag=f"dw+fwd R{R} Ci{C} Co{Co} K1")
@@ -648,8 +687,9 @@ class DwPw(Function):
         return dzp, dscale, dshift, ddw, ddb, dpw, db_pw, None, None, None, None, None, None, None
 
 
-def _dwpw_dgrad(dz, pw3, ws_t, z, scale, shift, dw_w, dw_b, seed, relu, p, layer, B, T):
-    """Data gradient of pointwise(depthwise(act(z))): one fused tensor-core kernel when the shape allows."""
+def _dwpw_dgrad(dz, pw3, ws_t, z, scale, shift, dw_w, dw_b, seed, relu, p, layer, B, T, bnb=None):
+    """Data gradient of pointwise(depthwise(act(z))): one fused tensor-core kernel when the shape allows.  ``bnb`` (TnBnBwd):
+    ``dz`` is the direct gradient w.r.t. the block's pre-BatchNorm output and the BatchNorm backward runs inside the kernel."""
     C, K = dw_w.shape[0], dw_w.shape[-1]
     Co, R = pw3.shape[0], B * T
     dzp = empty(z.shape, z)
@@ -657,21 +697,31 @@ def _dwpw_dgrad(dz, pw3, ws_t, z, scale, shift, dw_w, dw_b, seed, relu, p, layer
     ddb = zeros((C,), z) if dw_b is not None else None
     dscale = zeros((C,), z) if scale is not None else None
     dshift = zeros((C,), z) if scale is not None else None
-    if (TC_ENABLED and TC_FUSE_DWBWD and R >= TC_MIN_ROWS and Co % 32 == 0 and C % 128 == 0 and K % 2 == 1 and K <= 11
-            and (R + 16) * C < 2 ** 32):
+    if _dwbwd_tc_ok(R, Co, C, K):
         ws = ws_t
         if ws is None:
             ws = torch.empty((3, C, Co), device=z.device, dtype=torch.float32)
             call("tn_split_tf32", ptr(pw3), ptr(ws), C, Co, 1)
-        call("tn_gemm_tc_dwbwd", ptr(dz), ptr(ws), ptr(z), ptr(dzp), ptr(dw_w), ptr(ddw), ptr(ddb), ptr(dscale), ptr(dshift),
-             ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer), B, T, Co, C, K, TC_BWD_NSPLIT,
-             tag=f"dgrad+dwbwd R{R} Ci{Co} Co{C} K1")
+        if bnb is not None:
+            call("tn_gemm_tc_dwbwd_bn", ptr(dz), ptr(ws), ctypes.byref(bnb), ptr(z), ptr(dzp), ptr(dw_w), ptr(ddw), ptr(ddb), ptr(dscale),
+                 ptr(dshift), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer), B, T, Co, C, K,
+                 tag=f"bnbwd+dgrad+dwbwd R{R} Ci{Co} Co{C} K1")
+        else:
+            call("tn_gemm_tc_dwbwd", ptr(dz), ptr(ws), ptr(z), ptr(dzp), ptr(dw_w), ptr(ddw), ptr(ddb), ptr(dscale), ptr(dshift),
+                 ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer), B, T, Co, C, K, TC_BWD_NSPLIT,
+                 tag=f"dgrad+dwbwd R{R} Ci{Co} Co{C} K1")
     else:
+        assert bnb is None, "the fused BatchNorm backward needs the tensor-core depthwise-backward kernel"
         du = empty(z.shape, z)
         _gemm_fwd(dz, pw3, None, du, None, B, T, 1, 0, ws=ws_t)
         call("tn_dw_bwd", ptr(du), ptr(z), ptr(dzp), ptr(dw_w), ptr(ddw), ptr(ddb), ptr(dscale), ptr(dshift), ptr(scale),
              ptr(shift), int(relu), float(p), ptr(seed), int(layer), B, T, C, K)
     return dzp, dscale, dshift, ddw, ddb
+
+
+def _dwbwd_tc_ok(R: int, Co: int, C: int, K: int) -> bool:
+    return (TC_ENABLED and TC_FUSE_DWBWD and R >= TC_MIN_ROWS and Co % 32 == 0 and C % 128 == 0 and K % 2 == 1 and K <= 11
+            and (R + 16) * C < 2 ** 32)
 
 
 class DwPwBN(Function):
@@ -701,10 +751,19 @@ class DwPwBN(Function):
         relu, p, layer, B, T, n = ctx.meta
         pw3 = pw_w if pw_w.dim() == 3 else pw_w.unsqueeze(-1)
         Co = pw3.shape[0]
-        g, db_pw, dgamma, dbeta = _bn_backward(dzo, zo, dscale_o, dshift_o, fold, gamma, n, pw_b, B * T, Co)
-        dpw = zeros(pw_w.shape, pw_w)
-        _gemm_wgrad(g, u, dpw if dpw.dim() == 3 else dpw.unsqueeze(-1), None, B, T)
-        dzp, dscale, dshift, ddw, ddb = _dwpw_dgrad(g, pw3, ctx.ws_t, z, scale, shift, dw_w, dw_b, seed, relu, p, layer, B, T)
+        R, C, K = B * T, dw_w.shape[0], dw_w.shape[-1]
+        if _bnbwd_fusable(dzo, R, Co, C) and _dwbwd_tc_ok(R, Co, C, K):
+            # data gradient first: its operand producer computes g (the BatchNorm backward) and writes it for the wgrad below
+            bnb, g, db_pw, dgamma, dbeta, keep = _make_bn_bwd(_c(dzo), zo, dscale_o, dshift_o, fold, gamma, n, pw_b, Co)
+            dzp, dscale, dshift, ddw, ddb = _dwpw_dgrad(_c(dzo), pw3, ctx.ws_t, z, scale, shift, dw_w, dw_b, seed, relu, p, layer, B, T,
+                                                        bnb=bnb)
+            dpw = zeros(pw_w.shape, pw_w)
+            _gemm_wgrad(g, u, dpw if dpw.dim() == 3 else dpw.unsqueeze(-1), None, B, T)
+        else:
+            g, db_pw, dgamma, dbeta = _bn_backward(dzo, zo, dscale_o, dshift_o, fold, gamma, n, pw_b, R, Co)
+            dpw = zeros(pw_w.shape, pw_w)
+            _gemm_wgrad(g, u, dpw if dpw.dim() == 3 else dpw.unsqueeze(-1), None, B, T)
+            dzp, dscale, dshift, ddw, ddb = _dwpw_dgrad(g, pw3, ctx.ws_t, z, scale, shift, dw_w, dw_b, seed, relu, p, layer, B, T)
         return (dzp, dscale, dshift, ddw, ddb, dpw, db_pw, dgamma, dbeta, None, None, None, None, None, None, None, None,
                 None, None, None)
 

@@ -23,13 +23,12 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
                                                         const float* __restrict__ bias, float* __restrict__ Z,
                                                         double* __restrict__ stats, int R, int T, int Ci, int Co, int K,
                                                         int transpose_w, int flags, int kk_per_split, tn_bn_fold bn, int has_bn,
-                                                        float* __restrict__ parts, unsigned int* __restrict__ tickets) {
+                                                        float* __restrict__ parts, unsigned int* __restrict__ tickets,
+                                                        unsigned long long* __restrict__ accum) {
   tn_grid_dep_sync();
   __shared__ float As[GK][GM + 4];
   __shared__ float Bs[GK][GN + 4];
-  __shared__ __align__(16) double fin[8 * 2 * GN];      // tn_stats_finish scratch; its head doubles as red1 / red2
-  float (*red1)[GN] = reinterpret_cast<float (*)[GN]>(fin);
-  float (*red2)[GN] = reinterpret_cast<float (*)[GN]>(reinterpret_cast<float*>(fin) + 16 * GN);
+  __shared__ float red1[16][GN], red2[16][GN];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int r0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
@@ -145,24 +144,24 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
     }
   }
   if (stats) {
-    // per-channel partial sums of this row tile in a fixed order -> parts[row tile][which][Co]; the last block of this
-    // 64-channel group adds the row tiles in order and (has_bn) folds the BatchNorm (tn_stats_finish)
+    // per-channel partial sums of this row tile in a fixed order, added into the fixed-point accumulators (integer atomics:
+    // order-independent); the last block of this 64-channel group reads the totals and (has_bn) folds the BatchNorm
 #pragma unroll
     for (int j = 0; j < 4; ++j) { red1[ty][tx * 4 + j] = s1[j]; red2[ty][tx * 4 + j] = s2[j]; }
     __syncthreads();
-    if (tid < GN) {
-      float a = 0.f, b = 0.f;
-#pragma unroll
-      for (int y = 0; y < 16; ++y) { a += red1[y][tid]; b += red2[y][tid]; }
-      const int n = n0 + tid;
+    unsigned int* flag = tn_fix_flag(accum, Co, (int)blockIdx.y);
+    if (tid < 2 * GN) {
+      const int which = tid / GN, ch = tid - which * GN;
+      const int n = n0 + ch;
       if (n < Co) {
-        parts[((size_t)blockIdx.x * 2 + 0) * Co + n] = a;
-        parts[((size_t)blockIdx.x * 2 + 1) * Co + n] = b;
+        float a = 0.f;
+#pragma unroll
+        for (int y = 0; y < 16; ++y) a += which ? red2[y][ch] : red1[y][ch];
+        tn_fix_add(accum, Co, which, n, a, flag);
       }
     }
     const int nC = min(GN, Co - n0);
-    tn_stats_finish(has_bn ? &bn : nullptr, stats, parts, (int)gridDim.x, Co, n0, nC, tickets + blockIdx.y, gridDim.x,
-                    blockIdx.y == 0, fin);
+    tn_stats_finish(has_bn ? &bn : nullptr, stats, accum, Co, n0, nC, tickets + blockIdx.y, flag, gridDim.x, blockIdx.y == 0);
   }
 }
 
@@ -255,15 +254,12 @@ static void conv_gemm_plan(long long R, int Ci, int Co, int K, int flags, int* s
   *kps_out = kps;
 }
 
-extern "C" long long tn_conv_gemm_simt_scratch_floats(int B, int T, int Ci, int Co, int K, int flags, int with_stats) {
+extern "C" long long tn_conv_gemm_simt_scratch_floats(int B, int T, int Ci, int Co, int K, int flags) {
   if (B <= 0 || T <= 0 || Ci <= 0 || Co <= 0 || K <= 0) return 0;
   const long long R = (long long)B * T;
   int splits, kps;
   conv_gemm_plan(R, Ci, Co, K, flags, &splits, &kps);
-  long long n = 0;
-  if (splits > 1) n = (long long)splits * R * Co;
-  else if (with_stats) n = (long long)tn_cdiv(R, GM) * 2 * Co;
-  return n;
+  return splits > 1 ? (long long)splits * R * Co : 0;
 }
 
 static int conv_gemm_launch(const float* X, const float* W, const float* bias, float* Z, double* stats, const tn_bn_fold* bn,
@@ -276,18 +272,22 @@ static int conv_gemm_launch(const float* X, const float* W, const float* bias, f
   int splits, kps;
   conv_gemm_plan(R, Ci, Co, K, flags, &splits, &kps);
   grid.z = splits;
-  const long long need = tn_conv_gemm_simt_scratch_floats(B, T, Ci, Co, K, flags, stats != nullptr);
-  if (need > 0) {
+  const long long need = tn_conv_gemm_simt_scratch_floats(B, T, Ci, Co, K, flags);
+  if (need > 0)
     TN_REQUIRE(scratch && scratch->parts && scratch->tickets && scratch->parts_floats >= need,
-               "conv_gemm: needs a tn_scratch with %lld floats (tn_conv_gemm_simt_scratch_floats) and the ticket array", need);
-    TN_REQUIRE(splits > 1 || (int)grid.y <= TN_TICKETS, "conv_gemm: statistics of more than %d channels are not supported", TN_TICKETS * GN);
+               "conv_gemm: split-K needs a tn_scratch with %lld floats (tn_conv_gemm_simt_scratch_floats) and the ticket array", need);
+  if (stats && splits == 1) {
+    TN_REQUIRE(scratch && scratch->accum && scratch->tickets && scratch->accum_words >= TN_ACCUM_WORDS(Co),
+               "conv_gemm: statistics need a tn_scratch with TN_ACCUM_WORDS(Co) zeroed accumulator words and the ticket array");
+    TN_REQUIRE((int)grid.y <= TN_TICKETS, "conv_gemm: statistics of more than %d channels are not supported", TN_TICKETS * GN);
   }
   tn_bn_fold f;
   memset(&f, 0, sizeof(f));
   const int fuse_bn = (bn && splits == 1) ? 1 : 0;
   if (fuse_bn) f = *bn;
   tn_launch(conv_gemm_kernel, grid, 256, 0, stream, X, W, bias, Z, splits > 1 ? (double*)nullptr : stats, (int)R, T, Ci, Co, K,
-            transpose_w, flags, kps, f, fuse_bn, scratch ? scratch->parts : (float*)nullptr, scratch ? scratch->tickets : (unsigned int*)nullptr);
+            transpose_w, flags, kps, f, fuse_bn, scratch ? scratch->parts : (float*)nullptr, scratch ? scratch->tickets : (unsigned int*)nullptr,
+            scratch ? scratch->accum : (unsigned long long*)nullptr);
   TN_LAUNCH_CHECK("conv_gemm_kernel");
   if (splits > 1 && stats) {                       // split-K: statistics (and the fold) from the finished tensor
     int rc = tn_colstats(Z, stats, (int)R, Co, stream);

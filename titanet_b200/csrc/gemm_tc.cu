@@ -230,7 +230,7 @@ struct TcParams {
   int R, Kd, M_total, BN, stages, nsplit, flags, tmem_cols;
   int corr;                     // 1: TF32 + BF16-correction split (gradient GEMMs), 0: 3xTF32 (forward GEMMs)
   int nacc;                     // TMEM accumulators per tile (>= 1), BN columns apart: nacc - 1 K-chunked main accumulators + 1 for the corrections
-  float* parts;                 // statistics partials [row tiles][2][M_total] (tn_stats_finish)
+  unsigned long long* accum;    // fixed-point statistics accumulators [hi 2 M_total | lo 2 M_total | flags] (tn_fix_add / tn_stats_finish)
   unsigned int* tickets;        // one per channel group, zero on entry, reset by the kernel
   int cluster2;          // launched as 2-CTA clusters along x: the two CTAs share (multicast) the weight tiles
   long long* trace;      // optional timeline buffer (debug): 128 slots per traced CTA
@@ -257,6 +257,11 @@ struct TcParams {
   float* g_dscale;       // [C]      ACCUMULATED (act only)
   float* g_dshift;       // [C]      ACCUMULATED (act only)
   TnAct act;
+  // BatchNorm backward folded into the operand load of a data-gradient GEMM (pair kernel): the B operand is
+  // g = dZ + a[c] + b[c] z, built by the transform warps from the dZ tile and the z tile (delivered into the B_lo buffers);
+  // g is also written to bnb.g_out for the weight-gradient GEMM and its column sums to bnb.dbias (see tn_bn_bwd)
+  tn_bn_bwd bnb;
+  int has_bnb;
 };
 
 // Epilogue for the fused depthwise backward.  The accumulator tile holds du[c, j] for the rows
@@ -861,14 +866,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
       if (p.stats) {
         // the two warps of each lane quadrant are combined in shared memory (fixed order) and the CTA's per-channel partial
-        // sums go to parts[row tile][which][channel]; tn_stats_finish adds the row tiles in order (no atomics)
+        // sums are added into the fixed-point accumulators (integer atomics: order-independent, see tn_fix_add)
         float* red = reinterpret_cast<float*>(smem + p.red_off);          // [2 halves][2 sums][128 channels]
         const int chl = (int)(threadIdx.x & 127u);
         red[(half * 2 + 0) * 128 + chl] = s1;
         red[(half * 2 + 1) * 128 + chl] = s2;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int which = tid >> 7, ch = tid & 127;                        // threads 0-127: sum, 128-255: sum of squares
-        p.parts[((size_t)blockIdx.x * 2 + which) * p.M_total + (co - chl) + ch] = red[which * 128 + ch] + red[(2 + which) * 128 + ch];
+        tn_fix_add(p.accum, p.M_total, which, (co - chl) + ch, red[which * 128 + ch] + red[(2 + which) * 128 + ch],
+                   tn_fix_flag(p.accum, p.M_total, (int)blockIdx.y));
         asm volatile("bar.sync 1, 256;" ::: "memory");                    // `red` is reused by the next channel half
       }
     }
@@ -881,8 +887,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
   if (p.cluster2) cluster_sync_all();        // the peer may still signal this CTA's barriers until its MMAs have drained
   if (p.stats)                               // group = this CTA's 128 * MT channels; the pipeline memory is free now
-    tn_stats_finish(p.has_bn ? &p.bn : nullptr, p.stats, p.parts, (int)gridDim.x, p.M_total, m0, 128 * MT, p.tickets + blockIdx.y,
-                    gridDim.x, blockIdx.y == 0, reinterpret_cast<double*>(smem));
+    tn_stats_finish(p.has_bn ? &p.bn : nullptr, p.stats, p.accum, p.M_total, m0, 128 * MT, p.tickets + blockIdx.y,
+                    tn_fix_flag(p.accum, p.M_total, (int)blockIdx.y), gridDim.x, blockIdx.y == 0);
   if (threadIdx.x == 0 && p.trace && blockIdx.y == 0 && blockIdx.x < 256) {
     unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[257 + 2 * blockIdx.x] = (long long)gt; }
   if (threadIdx.x == 0) { TC_TRACE(102); if (p.trace && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) {
@@ -1054,7 +1060,8 @@ __device__ __forceinline__ void tc2_dw_mainloop(const TcParams& p, uint8_t* smem
 template <int MODE, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ, TcParams p) {
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ,
+                const __grid_constant__ CUtensorMap tmG, TcParams p) {
   tn_grid_dep_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[5 * TC2_STAGES + 1 + 2 * TC2_STAGES];
@@ -1127,9 +1134,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tma_load_2d_2sm(smem_u32(a_hi(s)), &tmA_hi, fullA_leader0 + 8 * s, k0, m0 + (int)rank * 128);
         tma_load_2d_2sm(smem_u32(a_lo(s)), &tmA_lo, fullA_leader0 + 8 * s, k0, m0 + (int)rank * 128);
         const int padr = MODE == 2 ? (p.fdw_K >> 1) : 0;           // fused depthwise forward: PAD rows of halo in front
-        mbar_expect_tx(fullB0 + 8 * s, 2 * b_raw);
+        mbar_expect_tx(fullB0 + 8 * s, 2 * b_raw + (p.has_bnb ? 2 * b_half : 0u));
         tma_load_2d(smem_u32(b_hi(s, 0)), &tmB, fullB0 + 8 * s, k0, n0 + (int)rank * HB - padr);
         tma_load_2d(smem_u32(b_hi(s, 1)), &tmB, fullB0 + 8 * s, k0, n0 + BN2 + (int)rank * HB - padr);
+        if (MODE != 2 && p.has_bnb) {          // BatchNorm backward as operand producer: the z rows of the same box into B_lo
+          tma_load_2d(smem_u32(b_lo(s, 0)), &tmG, fullB0 + 8 * s, k0, n0 + (int)rank * HB);
+          tma_load_2d(smem_u32(b_lo(s, 1)), &tmG, fullB0 + 8 * s, k0, n0 + BN2 + (int)rank * HB);
+        }
       }
       if (MODE == 1) {
         // z boxes of the previous layer for the fused epilogue, group by group as the tensor core releases the stages
@@ -1228,6 +1239,106 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const int row_base = n0 + (int)rank * HB;
       if (p.fdw_K == 1) tc2_dw_mainloop<1, 4>(p, smem, stage_bytes, bh_off, b_raw, bl_off, b_half, fullB0, ready0, num_kc, row_base, BN2, HB, par, tid, lane);
       else tc2_dw_mainloop<3, 4>(p, smem, stage_bytes, bh_off, b_raw, bl_off, b_half, fullB0, ready0, num_kc, row_base, BN2, HB, par, tid, lane);
+    } else if (MODE != 2 && p.has_bnb) {
+      // ===== BatchNorm backward as the operand producer (train-mode BN behind the conv whose data gradient this GEMM is) =====
+      // g = dZ + a[c] + b[c] z with the per-channel statistics-path coefficients a, b (tn_bn_stats_bwd's arithmetic), computed
+      // here from (dscale, dshift, mean, invstd, gamma); dZ arrives in B_hi, z in B_lo; g is rounded / split in place, written to
+      // g_out for the weight-gradient GEMM (rows this pair owns, channel group 0 only) and summed per channel for the conv-bias
+      // gradient.  Replaces one tn_bn_stats_bwd launch (read dZ, z; write g) per conv.
+      constexpr int NT = 32 * EW;
+      constexpr int NI = (2 * 128 * 8 + NT - 1) / NT;              // float4s per thread and chunk (BN2 <= 256: HB <= 128)
+      float* sa = reinterpret_cast<float*>(smem + p.par_off);
+      float* sb = sa + p.Kd;
+      float* scs = sb + p.Kd;                                      // column sums of g over this CTA's owned rows
+      const tn_bn_bwd& q = p.bnb;
+      const bool owner = blockIdx.y == 0;
+      for (int ch = tid; ch < p.Kd; ch += NT) {
+        const double dsc = __ldg(q.dscale + ch), dsh = __ldg(q.dshift + ch), mu = __ldg(q.mean + ch), r = __ldg(q.invstd + ch), gm = __ldg(q.gamma + ch);
+        const double t = dsc - mu * dsh;                           // dL/d(invstd) / gamma
+        const double dvar = -0.5 * gm * t * r * r * r;
+        const double dmu = -dsh * gm * r - 2.0 * mu * dvar;
+        sa[ch] = (float)(dmu / q.n);
+        sb[ch] = (float)(2.0 * dvar / q.n);
+        scs[ch] = 0.f;
+        if (owner && blockIdx.x == 0) {                            // rank 0 of pair 0
+          q.dgamma[ch] = (float)(r * t);
+          q.dbeta[ch] = (float)dsh;
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");
+      // rows this pair owns (fused depthwise backward: the tile carries a halo that the neighbouring pairs own)
+      const int own_lo = MODE == 1 ? pair * p.BNo : n0;
+      const int own_hi = min(p.R, MODE == 1 ? own_lo + p.BNo : n0 + 2 * BN2);
+      const uint32_t cq = ((uint32_t)tid & 7u) ^ (((uint32_t)tid >> 3) & 7u);      // this thread's 16-byte chunk: fixed (NT % 64 == 0)
+      for (int kc = 0; kc < num_kc; ++kc) {
+        const int s = kc % S;
+        mbar_wait(fullB0 + 8 * s, (kc / S) & 1);
+        float4* hi = reinterpret_cast<float4*>(b_hi(s, 0));
+        float4* lo = reinterpret_cast<float4*>(b_lo(s, 0));
+        float4 v[NI], zz[NI];
+#pragma unroll
+        for (int k = 0; k < NI; ++k) {
+          const int i = tid + k * NT;
+          if (i < n4) { v[k] = hi[i]; zz[k] = lo[i]; }
+        }
+        // B_lo is overwritten below with the packed correction rows.  A thread's stores only touch the 128-byte row(s) it read
+        // from, and the eight 16-byte chunks of a row are read by eight consecutive threads of ONE warp in the same
+        // iteration k: a warp-level barrier is enough (a CTA-wide one per chunk cost more than the arithmetic).
+        __syncwarp();
+        const int ch = kc * TC_BK + 4 * (int)cq;
+        const float4 a4 = *reinterpret_cast<const float4*>(sa + ch), b4 = *reinterpret_cast<const float4*>(sb + ch);
+        float4 cs = tn_zero4();
+#pragma unroll
+        for (int k = 0; k < NI; ++k) {
+          const int i = tid + k * NT;
+          if (i < n4) {
+            const int row = i >> 3;                                // 0 .. 2 HB - 1 over both N tiles
+            const int t = row >= HB ? 1 : 0;
+            const int gr = n0 + t * BN2 + (int)rank * HB + (row - t * HB);
+            float4 g = tn_zero4();
+            if (gr >= 0 && gr < p.R) g = tn_fma4(b4, zz[k], v[k] + a4);
+            if (owner && gr >= own_lo && gr < own_hi) {
+              tn_st4(q.g_out + (size_t)gr * p.Kd + ch, g);
+              cs = cs + g;
+            }
+            uint4 h;
+            h.x = rna_tf32(g.x); h.y = rna_tf32(g.y); h.z = rna_tf32(g.z); h.w = rna_tf32(g.w);
+            reinterpret_cast<uint4*>(hi)[i] = h;
+            if (p.corr) {
+              tc_store_corr(reinterpret_cast<uint8_t*>(lo), (uint32_t)row, cq, g, h);
+            } else {
+              uint4 l;
+              l.x = rna_tf32(g.x - __uint_as_float(h.x)); l.y = rna_tf32(g.y - __uint_as_float(h.y));
+              l.z = rna_tf32(g.z - __uint_as_float(h.z)); l.w = rna_tf32(g.w - __uint_as_float(h.w));
+              reinterpret_cast<uint4*>(lo)[i] = l;
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready0 + 8 * s);
+        if (owner && q.dbias) {                                    // off the chunk's critical path
+          // the four row groups of a warp hold the same chunk at lanes (c ^ (row group & 7)) + 8 j: gather them into lanes
+          // 0-7 first, so that one shared-memory atomic instruction touches 32 distinct addresses (64 lanes on the same 4
+          // addresses serialised for ~2 us per chunk)
+          const uint32_t r0 = ((uint32_t)tid >> 3) & 7u & ~3u;     // (4 w) & 7: row-group base of this warp
+          float4 tot = cs;
+#pragma unroll
+          for (uint32_t j = 1; j < 4; ++j) {
+            const uint32_t src = (((uint32_t)lane & 7u) ^ r0 ^ ((r0 + j) & 7u)) + 8u * j;
+            tot.x += __shfl_sync(0xffffffffu, cs.x, src); tot.y += __shfl_sync(0xffffffffu, cs.y, src);
+            tot.z += __shfl_sync(0xffffffffu, cs.z, src); tot.w += __shfl_sync(0xffffffffu, cs.w, src);
+          }
+          if (lane < 8) {
+            float* d = scs + kc * TC_BK + 4 * (int)((uint32_t)lane ^ r0);
+            atomicAdd(d, tot.x); atomicAdd(d + 1, tot.y); atomicAdd(d + 2, tot.z); atomicAdd(d + 3, tot.w);
+          }
+        }
+      }
+      if (owner && q.dbias) {
+        asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");
+        for (int ch = tid; ch < p.Kd; ch += NT) atomicAdd(q.dbias + ch, scs[ch]);
+      }
     } else
     for (int kc = 0; kc < num_kc; ++kc) {
       const int s = kc % S;
@@ -1285,8 +1396,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       else if (nvalid > 0) tc_epilogue<false, false, false>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, s1, s2, half, EW / 4, na, BN2);
     }
     if (p.stats) {
-      // the warps of each lane quadrant are combined in shared memory in a fixed order; the CTA's per-channel partial sums go
-      // to parts[pair][which][channel] and tn_stats_finish adds the pairs in order (no atomics)
+      // the warps of each lane quadrant are combined in shared memory in a fixed order; the CTA's per-channel partial sums
+      // are added into the fixed-point accumulators (integer atomics: order-independent, see tn_fix_add)
       float* red = reinterpret_cast<float*>(smem + p.red_off);          // [EW/4 parts][2 sums][128 channels]
       const int chl = (int)(threadIdx.x & 127u);
       red[(half * 2 + 0) * 128 + chl] = s1;
@@ -1297,7 +1408,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         float acc = 0.f;
 #pragma unroll
         for (int pp = 0; pp < EW / 4; ++pp) acc += red[(pp * 2 + which) * 128 + ch];
-        p.parts[((size_t)pair * 2 + which) * p.M_total + (co - chl) + ch] = acc;
+        tn_fix_add(p.accum, p.M_total, which, (co - chl) + ch, acc, tn_fix_flag(p.accum, p.M_total, 2 * (int)blockIdx.y + (int)rank));
       }
     }
     }
@@ -1307,9 +1418,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
-  if (p.stats)                    // group = this CTA's 128 channels over all pairs; the pipeline memory is free now
-    tn_stats_finish(p.has_bn ? &p.bn : nullptr, p.stats, p.parts, (int)(gridDim.x >> 1), p.M_total, m0 + (int)rank * 128, 128,
-                    p.tickets + 2 * blockIdx.y + rank, gridDim.x >> 1, blockIdx.y == 0 && rank == 0, reinterpret_cast<double*>(smem));
+  if (p.stats)                    // group = this CTA's 128 channels over all pairs
+    tn_stats_finish(p.has_bn ? &p.bn : nullptr, p.stats, p.accum, p.M_total, m0 + (int)rank * 128, 128, p.tickets + 2 * blockIdx.y + rank,
+                    tn_fix_flag(p.accum, p.M_total, 2 * (int)blockIdx.y + (int)rank), gridDim.x >> 1, blockIdx.y == 0 && rank == 0);
 }
 
 // Split scheme per GEMM.  The weight split carries BOTH correction formats (ws = [3, M, Kd]: tf32 hi | tf32 lo | packed bf16
@@ -1761,12 +1872,6 @@ extern "C" int tn_split_tf32_batch(const tn_split_job* jobs_dev, int njobs, int 
   return TN_OK;
 }
 
-// upper bound of the statistics partials of the tensor-core GEMMs: row tiles have at least 32 rows
-extern "C" long long tn_gemm_tc_scratch_floats(int R, int M) {
-  if (R <= 0 || M <= 0) return 0;
-  return ((long long)(R + 31) / 32 + 1) * 2 * M;
-}
-
 // rows of output per CTA: the multiple of 16 that minimises waves * (tile rows + fixed cost).
 // `halo` extra MMA columns ride along (fused depthwise backward).
 static int pick_bn(long long R, int groups, int per_row_stage_bytes, int fixed_stage_bytes, int halo, int reserve, int* stages_out) {
@@ -1827,11 +1932,10 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   p.corr = tc_corr_for(grad);
   const float* ws_lo = ws + (size_t)(p.corr ? 2 : 1) * M * Kd;
   if (p.stats) {
-    TN_REQUIRE(scratch && scratch->parts && scratch->tickets && scratch->parts_floats >= tn_gemm_tc_scratch_floats(R, M),
-               "gemm_tc: statistics need a tn_scratch with tn_gemm_tc_scratch_floats(R, M) floats and the ticket array");
+    TN_REQUIRE(scratch && scratch->accum && scratch->tickets && scratch->accum_words >= TN_ACCUM_WORDS(M),
+               "gemm_tc: statistics need a tn_scratch with TN_ACCUM_WORDS(M) zeroed accumulator words and the ticket array");
     TN_REQUIRE(M / 128 <= TN_TICKETS, "gemm_tc: statistics of more than %d channels are not supported", TN_TICKETS * 128);
-    TN_REQUIRE(tn_aligned16(scratch->parts), "gemm_tc: scratch must be 16B aligned");
-    p.parts = scratch->parts; p.tickets = scratch->tickets;
+    p.accum = scratch->accum; p.tickets = scratch->tickets;
   }
   TN_REQUIRE(tn_gemm_tc_supported(R, Kd, M), "gemm_tc: unsupported shape R=%d K=%d M=%d (need K %% 32 == 0, M %% 128 == 0)", R, Kd, M);
   TN_REQUIRE(nsplit == 1 || nsplit == 3, "gemm_tc: nsplit must be 1 or 3");
@@ -1855,7 +1959,7 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
     }
     const int ew = (p.dw_K > 0 && p.dw_K <= 3) ? ew_sel : 8;
     const bool wide = ew > 8;
-    const int par2 = p.fdw_K > 0 ? (Kd * (3 + p.fdw_K) * 4 + 1023) / 1024 * 1024 : 0;
+    const int par2 = p.fdw_K > 0 ? (Kd * (3 + p.fdw_K) * 4 + 1023) / 1024 * 1024 : (p.has_bnb ? (Kd * 3 * 4 + 1023) / 1024 * 1024 : 0);
     const int raw2 = p.fdw_K > 0 ? 2 * 8 * TC_BK * 4 : 0;      // halo rows of the two raw tiles per stage
     const int red2 = (p.dw_K > 0 ? ((ew / 4) * 128 * (p.dw_K + 3) * 4 + 1023) / 1024 * 1024 : (p.fdw_K > 0 ? 4096 : 2048)) + par2;
     int best = 0; double best_cost = 1e30;
@@ -1877,8 +1981,9 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
       if ((rc = make_map(&mA_hi, ws, M, Kd, 128)) != TN_OK) return rc;
       if ((rc = make_map(&mA_lo, ws_lo, M, Kd, 128)) != TN_OK) return rc;
       if ((rc = make_map(&mB, X, R, Kd, best / 2 + (p.fdw_K > 0 ? 8 : 0))) != TN_OK) return rc;
-      CUtensorMap mZ = mB;
+      CUtensorMap mZ = mB, mG = mB;
       if (p.dw_K > 0 && (rc = make_map(&mZ, p.zprev, R, M, best, 32)) != TN_OK) return rc;
+      if (p.has_bnb && (rc = make_map(&mG, p.bnb.z, R, Kd, best / 2)) != TN_OK) return rc;
       p.R = R; p.Kd = Kd; p.M_total = M; p.BN = best; p.BNo = 2 * best - halo2; p.nsplit = 3;
       p.nacc = p.dw_K > 0 ? 1 : pick_nacc(256, best, Kd / TC_BK, 3);
       const size_t stage_bytes = 2ull * 128 * TC_BK * 4 + 4ull * (best / 2) * TC_BK * 4 + raw2;
@@ -1888,24 +1993,25 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
       dim3 grid(2 * (unsigned)tn_cdiv(R, p.BNo), M / 256);
       if (p.fdw_K > 0) {
         TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tn_launch_cluster(gemm_tc2_kernel<2, 16>, grid, 64 + 32 * 16, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
+        tn_launch_cluster(gemm_tc2_kernel<2, 16>, grid, 64 + 32 * 16, smem, stream, 2, mA_hi, mA_lo, mB, mZ, mG, p);
       } else if (wide && ew == 16) {
         TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tn_launch_cluster(gemm_tc2_kernel<1, 16>, grid, 64 + 32 * 16, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
+        tn_launch_cluster(gemm_tc2_kernel<1, 16>, grid, 64 + 32 * 16, smem, stream, 2, mA_hi, mA_lo, mB, mZ, mG, p);
       } else if (wide) {
         TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tn_launch_cluster(gemm_tc2_kernel<1, 12>, grid, 64 + 32 * 12, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
+        tn_launch_cluster(gemm_tc2_kernel<1, 12>, grid, 64 + 32 * 12, smem, stream, 2, mA_hi, mA_lo, mB, mZ, mG, p);
       } else if (p.dw_K > 0) {
         TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tn_launch_cluster(gemm_tc2_kernel<1, 8>, grid, TC_GEMM_THREADS, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
+        tn_launch_cluster(gemm_tc2_kernel<1, 8>, grid, TC_GEMM_THREADS, smem, stream, 2, mA_hi, mA_lo, mB, mZ, mG, p);
       } else {
         TN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tn_launch_cluster(gemm_tc2_kernel<0, 8>, grid, TC_GEMM_THREADS, smem, stream, 2, mA_hi, mA_lo, mB, mZ, p);
+        tn_launch_cluster(gemm_tc2_kernel<0, 8>, grid, TC_GEMM_THREADS, smem, stream, 2, mA_hi, mA_lo, mB, mZ, mG, p);
       }
       TN_LAUNCH_CHECK("gemm_tc2_kernel");
       return TN_OK;
     }
   }
+  TN_UNSUPPORTED(p.has_bnb, "gemm_tc: the BatchNorm-backward operand producer needs the pair kernel (R >= 512, M %% 256 == 0; R=%d M=%d)", R, M);
   const int MT = (M % 256 == 0) ? 2 : 1;
   const int groups = M / (128 * MT);
   const int mult = nsplit == 3 ? 2 : 1;
@@ -1993,6 +2099,32 @@ extern "C" int tn_gemm_tc_bn(const float* X, const float* ws, const float* bias,
   return launch_gemm_tc(X, ws, p, R, Kd, M, nsplit, scratch, stream);
 }
 
+static int check_bnb(const tn_bn_bwd* b) {
+  TN_REQUIRE(b && b->z && b->dscale && b->dshift && b->mean && b->invstd && b->gamma && b->g_out && b->dgamma && b->dbeta && b->n >= 1.0,
+             "bn backward producer: null field");
+  TN_REQUIRE(tn_aligned16(b->z) && tn_aligned16(b->g_out), "bn backward producer: z and g_out must be 16B aligned");
+  return TN_OK;
+}
+extern "C" int tn_gemm_tc_bnbwd_supported(int R, int Kd, int M) {
+  return (tn_gemm_tc_supported(R, Kd, M) && R >= 512 && M % 256 == 0) ? 1 : 0;
+}
+// Data gradient of a conv followed by a train-mode BatchNorm with the BatchNorm backward folded into the operand load:
+//   g = dZ + a[c] + b[c] z  (tn_bn_stats_bwd's arithmetic, per 32-channel chunk in shared memory), dX = g W,
+//   g_out = g (for the weight-gradient GEMM), dbias += column sums of g, dgamma / dbeta written.
+extern "C" int tn_gemm_tc_bnbwd(const float* dZ, const float* ws, const tn_bn_bwd* bnb, float* dX, int R, int Kd, int M, int flags,
+                                void* stream) {
+  TN_REQUIRE(dX, "gemm_tc_bnbwd: null output");
+  int rc = check_bnb(bnb);
+  if (rc != TN_OK) return rc;
+  TN_UNSUPPORTED(!tn_gemm_tc_bnbwd_supported(R, Kd, M), "gemm_tc_bnbwd: unsupported shape R=%d K=%d M=%d", R, Kd, M);
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.Z = dX; p.flags = (flags & TN_EPI_ACCUM) | TN_GEMM_GRAD;
+  TN_UNSUPPORTED(flags & (TN_EPI_TANH | TN_EPI_ACCUM), "gemm_tc_bnbwd: epilogue flags are not supported");
+  p.bnb = *bnb; p.has_bnb = 1;
+  return launch_gemm_tc(dZ, ws, p, R, Kd, M, 3, nullptr, stream);
+}
+
 // Forward of a depthwise-separable conv block + train-mode BatchNorm fold in ONE kernel:
 //   u = depthwise_K(act(z)) + b_dw  (transform warps, from the raw z tile)   [also written to u_out for the backward wgrad]
 //   Z = u W^T + b_pw  (tensor cores, 3xTF32), statistics of Z, BatchNorm fold by the last CTA (bn may be NULL: stats only / none)
@@ -2026,10 +2158,10 @@ extern "C" int tn_gemm_tc_dwfwd(const float* z, const float* ws, const float* dw
 //   dzprev = act'(zprev) * scale * depthwise_K^T(du),   dw += ..., dbias += ..., dscale += ..., dshift += ...
 // i.e. tn_gemm_tc(dgrad) followed by tn_dw_bwd, without du ever leaving the SM.  scale == NULL: zprev is
 // already the activation (first sub-block of a mega-block) and dzprev is the gradient w.r.t. it.
-extern "C" int tn_gemm_tc_dwbwd(const float* dZ, const float* ws, const float* zprev, float* dzprev, const float* dw_w,
-                                float* g_dw, float* g_dbias, float* g_dscale, float* g_dshift, const float* scale,
-                                const float* shift, int relu, float drop_p, const unsigned long long* seed,
-                                unsigned int layer, int B, int T, int Co, int C, int K, int nsplit, void* stream) {
+static int dwbwd_impl(const float* dZ, const float* ws, const float* zprev, float* dzprev, const float* dw_w,
+                      float* g_dw, float* g_dbias, float* g_dscale, float* g_dshift, const float* scale,
+                      const float* shift, int relu, float drop_p, const unsigned long long* seed,
+                      unsigned int layer, int B, int T, int Co, int C, int K, int nsplit, const tn_bn_bwd* bnb, void* stream) {
   TN_REQUIRE(zprev && dzprev && dw_w && g_dw, "gemm_tc_dwbwd: null tensor");
   TN_REQUIRE(K >= 1 && K <= 11 && (K & 1), "gemm_tc_dwbwd: unsupported depthwise kernel size %d (odd sizes 1..11)", K);
   TN_REQUIRE(!scale || (shift && g_dscale && g_dshift), "gemm_tc_dwbwd: scale given without shift/dscale/dshift");
@@ -2042,5 +2174,28 @@ extern "C" int tn_gemm_tc_dwbwd(const float* dZ, const float* ws, const float* z
   p.dw_K = K; p.dw_T = T; p.dw_w = dw_w; p.zprev = zprev; p.dzprev = dzprev;
   p.g_dw = g_dw; p.g_db = g_dbias; p.g_dscale = g_dscale; p.g_dshift = g_dshift;
   p.act = tn_make_act(scale, shift, relu, drop_p, seed, layer);
+  if (bnb) {
+    int rc = check_bnb(bnb);
+    if (rc != TN_OK) return rc;
+    TN_UNSUPPORTED(!tn_gemm_tc_bnbwd_supported((int)R, Co, C) || nsplit != 3, "gemm_tc_dwbwd_bn: unsupported shape R=%lld K=%d M=%d", R, Co, C);
+    p.bnb = *bnb; p.has_bnb = 1;
+  }
   return launch_gemm_tc(dZ, ws, p, (int)R, Co, C, nsplit, nullptr, stream);
+}
+extern "C" int tn_gemm_tc_dwbwd(const float* dZ, const float* ws, const float* zprev, float* dzprev, const float* dw_w,
+                                float* g_dw, float* g_dbias, float* g_dscale, float* g_dshift, const float* scale,
+                                const float* shift, int relu, float drop_p, const unsigned long long* seed,
+                                unsigned int layer, int B, int T, int Co, int C, int K, int nsplit, void* stream) {
+  return dwbwd_impl(dZ, ws, zprev, dzprev, dw_w, g_dw, g_dbias, g_dscale, g_dshift, scale, shift, relu, drop_p, seed, layer, B, T, Co, C, K,
+                    nsplit, nullptr, stream);
+}
+// the same with the BatchNorm backward of the conv's OUTPUT folded into the operand load (dZ is the direct gradient w.r.t.
+// the pre-BatchNorm tensor z; see tn_gemm_tc_bnbwd)
+extern "C" int tn_gemm_tc_dwbwd_bn(const float* dZ, const float* ws, const tn_bn_bwd* bnb, const float* zprev, float* dzprev,
+                                   const float* dw_w, float* g_dw, float* g_dbias, float* g_dscale, float* g_dshift, const float* scale,
+                                   const float* shift, int relu, float drop_p, const unsigned long long* seed, unsigned int layer,
+                                   int B, int T, int Co, int C, int K, void* stream) {
+  TN_REQUIRE(bnb, "gemm_tc_dwbwd_bn: null tn_bn_bwd");
+  return dwbwd_impl(dZ, ws, zprev, dzprev, dw_w, g_dw, g_dbias, g_dscale, g_dshift, scale, shift, relu, drop_p, seed, layer, B, T, Co, C, K,
+                    3, bnb, stream);
 }

@@ -10,34 +10,56 @@
 // ---------------------------------------------------------------------------
 // squeeze: mean over time of the lazy activation
 // ---------------------------------------------------------------------------
-// One block owns one utterance and 64 channels (16 quads x 16 row lanes) and walks all T frames; the lanes are combined in
-// a fixed order in shared memory, so m is reproducible bit for bit (the forward pass has no floating-point atomics) and is
-// WRITTEN, not accumulated.
+// A cluster of SE_SPLIT thread blocks owns one utterance and 64 channels (16 quads x 16 row lanes per block); block r of the
+// cluster walks the r-th part of the T frames.  Lanes are combined in a fixed order in shared memory, the blocks' partial sums
+// are combined in rank order by block 0 through distributed shared memory: m is reproducible bit for bit (no floating-point
+// atomics in the forward pass), WRITTEN, not accumulated, and the grid is SE_SPLIT x larger than one block per (utterance,
+// channel group) could make it (an HBM-bound reduction needs the bytes in flight).
+#define SE_SPLIT 4
 __global__ void __launch_bounds__(TN_EW_THREADS) se_mean_kernel(const float* __restrict__ z, float* __restrict__ m, TnAct act,
                                                                 int T, int C, float inv_T) {
   tn_grid_dep_sync();
   act = tn_act_init(act);
   __shared__ float4 red[TN_EW_THREADS];
+  __shared__ float4 part[16];
   const int q = threadIdx.x & 15, lane = threadIdx.x >> 4;
-  const int b = blockIdx.y;
-  const int c = blockIdx.x * 64 + 4 * q;
+  const int b = blockIdx.z;
+  const int c = blockIdx.y * 64 + 4 * q;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int tchunk = (T + SE_SPLIT - 1) / SE_SPLIT;
+  const int t0 = (int)rank * tchunk, t1 = min(T, t0 + tchunk);
   float4 s = tn_zero4();
   if (c < C) {
-    const float* zb = z + (size_t)b * T * C + c;
 #pragma unroll 4
-    for (int t = lane; t < T; t += 16) {
+    for (int t = t0 + lane; t < t1; t += 16) {
       const size_t off = ((size_t)b * T + t) * C + c;
-      s = s + tn_act4(act, tn_ld4(zb + (size_t)t * C), c, off >> 2, nullptr);
+      s = s + tn_act4(act, tn_ld4(z + off), c, off >> 2, nullptr);
     }
   }
   red[threadIdx.x] = s;
   __syncthreads();
-  if (threadIdx.x < 16 && c < C) {
+  if (threadIdx.x < 16) {
     float4 a = red[q];
 #pragma unroll
     for (int l = 1; l < 16; ++l) a = a + red[l * 16 + q];
+    part[q] = a;
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (rank == 0 && threadIdx.x < 16 && c < C) {
+    float4 a = part[q];
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(&part[q]);
+#pragma unroll
+    for (uint32_t r = 1; r < SE_SPLIT; ++r) {
+      uint32_t remote;
+      float4 v;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+      asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote));
+      a = a + v;
+    }
     tn_st4(m + (size_t)b * C + c, a * inv_T);
   }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers' shared memory stays alive until read
 }
 
 // excitation MLP of batch item b by one block.  sm: m[C] + h[Cr].  m is read with ld.cg: in the fused kernels it was
@@ -289,8 +311,9 @@ extern "C" int tn_se_mean(const float* z3, float* m, const float* scale, const f
                           const unsigned long long* seed, unsigned int layer, int B, int T, int C, void* stream) {
   SE_COMMON_CHECK("se_mean");
   TN_REQUIRE(z3 && m && (scale == nullptr) == (shift == nullptr), "se_mean: null tensor");
-  dim3 grid(tn_cdiv(C, 64), B);
-  tn_launch(se_mean_kernel, grid, TN_EW_THREADS, 0, stream, z3, m, tn_make_act(scale, shift, relu, drop_p, seed, layer), T, C, 1.0f / (float)T);
+  dim3 grid(SE_SPLIT, tn_cdiv(C, 64), B);              // clusters of SE_SPLIT blocks along x
+  tn_launch_cluster(se_mean_kernel, grid, TN_EW_THREADS, 0, stream, SE_SPLIT, z3, m, tn_make_act(scale, shift, relu, drop_p, seed, layer), T, C,
+                    1.0f / (float)T);
   TN_LAUNCH_CHECK("se_mean_kernel");
   return TN_OK;
 }

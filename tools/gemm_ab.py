@@ -14,7 +14,7 @@ st = torch.empty(2 * M, dtype=torch.float64, device=dev)
 gamma, beta, rm, rv = torch.ones(M, device=dev), torch.zeros(M, device=dev), torch.zeros(M, device=dev), torch.ones(M, device=dev)
 nbt = torch.zeros((), dtype=torch.int64, device=dev); fold = torch.empty(4, M, device=dev)
 bn = ops.make_bn_fold(gamma, beta, rm, rv, nbt, 0.1, 1e-5, float(R), fold[0], fold[1], fold[2], fold[3])
-sc, keep = ops.scratch(x, LIB.query("tn_gemm_tc_scratch_floats", R, M))
+sc, keep = ops.scratch(x)
 def plain(): call("tn_gemm_tc", ptr(x), ptr(ws), ptr(b), ptr(z), None, R, K, M, 0, 3, None)
 def grad(): call("tn_gemm_tc", ptr(x), ptr(ws), ptr(b), ptr(z), None, R, K, M, 8, 3, None)
 def stats(): call("tn_gemm_tc", ptr(x), ptr(ws), ptr(b), ptr(z), ptr(st), R, K, M, 0, 3, ctypes.byref(sc))
