@@ -259,9 +259,84 @@ __device__ __forceinline__ void tn_fix_add(unsigned long long* accum, int C_tota
   atomicAdd(accum + (size_t)(2 + which) * C_total + c, lq);
 }
 
+// read-back + fold of channels [c0, c0 + nC) by `nthreads` threads (this one is number `tid`): the totals are final
+struct TnFoldConst { double inv_n, unbias; };     // 1 / n and n / (n - 1) (1 when n == 1), computed on the host
+static inline TnFoldConst tn_fold_const(double n) {
+  TnFoldConst c;
+  c.inv_n = n > 0.0 ? 1.0 / n : 0.0;
+  c.unbias = n > 1.0 ? n / (n - 1.0) : 1.0;
+  return c;
+}
+__device__ __forceinline__ void tn_stats_fold_channels(const tn_bn_fold* f, double* stats, unsigned long long* accum, int C_total,
+                                                       int c0, int nC, unsigned int* flag, bool bump_nbt, int tid, int nthreads,
+                                                       TnFoldConst fc) {
+  const double inv_n = fc.inv_n, unbias = fc.unbias;
+  const bool bad = __ldcg(flag) != 0u;
+  for (int cb = tid; cb < nC; cb += 4 * nthreads) {
+    // up to four channels per thread and pass: all sixteen loads are issued before anything is used (one global round trip
+    // per pass, not per channel -- a single warp folds 128 channels in one pass)
+    unsigned long long w[4][4];
+    float pre[4][4];                                  // gamma, beta, running_mean, running_var: loaded up front as well (the
+                                                      // stores below may alias them as far as the compiler knows)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cl = cb + j * nthreads;
+      if (cl < nC) {
+        const unsigned long long* a = accum + c0 + cl;
+        w[j][0] = __ldcg(a); w[j][1] = __ldcg(a + C_total); w[j][2] = __ldcg(a + 2 * (size_t)C_total); w[j][3] = __ldcg(a + 3 * (size_t)C_total);
+        if (f) {
+          pre[j][0] = __ldg(f->gamma + c0 + cl); pre[j][1] = __ldg(f->beta + c0 + cl);
+          if (f->running_mean) { pre[j][2] = f->running_mean[c0 + cl]; pre[j][3] = f->running_var[c0 + cl]; }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+    const int cl = cb + j * nthreads;
+    if (cl >= nC) break;
+    const int c = c0 + cl;
+    unsigned long long* a = accum + c;
+    const unsigned long long h1 = w[j][0], h2 = w[j][1], l1 = w[j][2], l2 = w[j][3];
+    a[0] = 0ull; a[C_total] = 0ull; a[2 * (size_t)C_total] = 0ull; a[3 * (size_t)C_total] = 0ull;
+    double s1 = (double)(long long)h1 * 0.0625 + (double)l1 * 8.673617379884035e-19;      // 2^-60
+    double s2 = (double)(long long)h2 * 0.0625 + (double)l2 * 8.673617379884035e-19;
+    if (bad) s1 = s2 = __longlong_as_double(0x7ff8000000000000ll);
+    if (stats) { stats[c] = s1; stats[C_total + c] = s2; }
+    if (f) {
+      // few fp64 operations per channel (the fp64 pipe is slow): one reciprocal, and 1 / sqrt by one fp64 Newton step on the
+      // fp32 rsqrt (error ~2^-44, then rounded to fp32)
+      // inv_n = 1 / n and unbias = n / (n - 1) come from the host: an fp64 division per channel is most of this tail
+      const double m = s1 * inv_n;
+      double var = s2 * inv_n - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mean = (float)m;
+      const double ve = var + (double)f->eps;
+      double r = (double)rsqrtf((float)ve);
+      r = r * (1.5 - 0.5 * ve * r * r);
+      const float invstd = (float)r;
+      if (f->running_mean) {
+        const float unbiased = (float)(var * unbias);
+        f->running_mean[c] = (1.f - f->momentum) * pre[j][2] + f->momentum * mean;
+        f->running_var[c] = (1.f - f->momentum) * pre[j][3] + f->momentum * unbiased;
+      }
+      const float sc = pre[j][0] * invstd;
+      f->scale[c] = sc;
+      f->shift[c] = pre[j][1] - mean * sc;
+      f->mean[c] = mean;
+      f->invstd[c] = invstd;
+    }
+    }
+  }
+  if (nthreads <= 32) __syncwarp(); else __syncthreads();
+  if (tid == 0) {
+    *flag = 0u;
+    if (f && bump_nbt && f->num_batches_tracked) *f->num_batches_tracked += 1;
+  }
+}
+
 __device__ __forceinline__ void tn_stats_finish(const tn_bn_fold* f, double* stats, unsigned long long* accum, int C_total,
                                                 int c0, int nC, unsigned int* ticket, unsigned int* flag,
-                                                unsigned int blocks_in_group, bool bump_nbt) {
+                                                unsigned int blocks_in_group, bool bump_nbt, TnFoldConst fc) {
   __shared__ unsigned int s_is_last;
   __threadfence();                                   // this thread's atomics before the block's ticket
   __syncthreads();
@@ -273,47 +348,7 @@ __device__ __forceinline__ void tn_stats_finish(const tn_bn_fold* f, double* sta
   __syncthreads();
   if (!s_is_last) return;
   __threadfence();
-  const int nthreads = blockDim.x * blockDim.y;
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const bool bad = __ldcg(flag) != 0u;
-  for (int cl = tid; cl < nC; cl += nthreads) {
-    const int c = c0 + cl;
-    unsigned long long* a = accum + c;
-    const unsigned long long h1 = __ldcg(a), h2 = __ldcg(a + C_total), l1 = __ldcg(a + 2 * (size_t)C_total), l2 = __ldcg(a + 3 * (size_t)C_total);
-    a[0] = 0ull; a[C_total] = 0ull; a[2 * (size_t)C_total] = 0ull; a[3 * (size_t)C_total] = 0ull;
-    double s1 = (double)(long long)h1 * 0.0625 + (double)l1 * 8.673617379884035e-19;      // 2^-60
-    double s2 = (double)(long long)h2 * 0.0625 + (double)l2 * 8.673617379884035e-19;
-    if (bad) s1 = s2 = __longlong_as_double(0x7ff8000000000000ll);
-    if (stats) { stats[c] = s1; stats[C_total + c] = s2; }
-    if (f) {
-      // few fp64 operations per channel (the fp64 pipe is slow and this is a serial tail of the GEMM): one reciprocal, and
-      // 1 / sqrt by one fp64 Newton step on the fp32 rsqrt (error ~2^-44, then rounded to fp32)
-      const double n = f->n, inv_n = 1.0 / n;
-      const double m = s1 * inv_n;
-      double var = s2 * inv_n - m * m;
-      if (var < 0.0) var = 0.0;
-      const float mean = (float)m;
-      const double ve = var + (double)f->eps;
-      double r = (double)rsqrtf((float)ve);
-      r = r * (1.5 - 0.5 * ve * r * r);
-      const float invstd = (float)r;
-      if (f->running_mean) {
-        const float unbiased = n > 1.0 ? (float)(var * n * (double)(1.0f / (float)(n - 1.0))) : (float)var;
-        f->running_mean[c] = (1.f - f->momentum) * f->running_mean[c] + f->momentum * mean;
-        f->running_var[c] = (1.f - f->momentum) * f->running_var[c] + f->momentum * unbiased;
-      }
-      const float sc = __ldg(f->gamma + c) * invstd;
-      f->scale[c] = sc;
-      f->shift[c] = __ldg(f->beta + c) - mean * sc;
-      f->mean[c] = mean;
-      f->invstd[c] = invstd;
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    *flag = 0u;
-    if (f && bump_nbt && f->num_batches_tracked) *f->num_batches_tracked += 1;
-  }
+  tn_stats_fold_channels(f, stats, accum, C_total, c0, nC, flag, bump_nbt, threadIdx.y * blockDim.x + threadIdx.x, blockDim.x * blockDim.y, fc);
 }
 
 // ---------------------------------------------------------------------------

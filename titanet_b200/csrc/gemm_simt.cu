@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
                                                         double* __restrict__ stats, int R, int T, int Ci, int Co, int K,
                                                         int transpose_w, int flags, int kk_per_split, tn_bn_fold bn, int has_bn,
                                                         float* __restrict__ parts, unsigned int* __restrict__ tickets,
-                                                        unsigned long long* __restrict__ accum) {
+                                                        unsigned long long* __restrict__ accum, TnFoldConst fc) {
   tn_grid_dep_sync();
   __shared__ float As[GK][GM + 4];
   __shared__ float Bs[GK][GN + 4];
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
       }
     }
     const int nC = min(GN, Co - n0);
-    tn_stats_finish(has_bn ? &bn : nullptr, stats, accum, Co, n0, nC, tickets + blockIdx.y, flag, gridDim.x, blockIdx.y == 0);
+    tn_stats_finish(has_bn ? &bn : nullptr, stats, accum, Co, n0, nC, tickets + blockIdx.y, flag, gridDim.x, blockIdx.y == 0, fc);
   }
 }
 
@@ -287,7 +287,7 @@ static int conv_gemm_launch(const float* X, const float* W, const float* bias, f
   if (fuse_bn) f = *bn;
   tn_launch(conv_gemm_kernel, grid, 256, 0, stream, X, W, bias, Z, splits > 1 ? (double*)nullptr : stats, (int)R, T, Ci, Co, K,
             transpose_w, flags, kps, f, fuse_bn, scratch ? scratch->parts : (float*)nullptr, scratch ? scratch->tickets : (unsigned int*)nullptr,
-            scratch ? scratch->accum : (unsigned long long*)nullptr);
+            scratch ? scratch->accum : (unsigned long long*)nullptr, tn_fold_const(fuse_bn ? f.n : 1.0));
   TN_LAUNCH_CHECK("conv_gemm_kernel");
   if (splits > 1 && stats) {                       // split-K: statistics (and the fold) from the finished tensor
     int rc = tn_colstats(Z, stats, (int)R, Co, stream);

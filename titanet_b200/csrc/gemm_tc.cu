@@ -223,6 +223,38 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tbase, float* __restrict__ 
   }
 }
 
+// statistics pre-pass of the plain epilogue: the same values x = acc + bias the store pass will write, summed per channel
+// (sum, sum of squares) in the same column order -- nothing is stored.  See the pair kernel's epilogue for why it runs first.
+template <bool FULL>
+__device__ __forceinline__ void tc_epilogue_stats(uint32_t tbase, int BN, int nvalid, float bv, float& s1, float& s2, int half,
+                                                  int nparts, int nacc, int astride) {
+  for (int c0 = 32 * half; c0 < BN; c0 += 32 * nparts) {
+    float v[32];
+    const bool two = c0 + 16 < BN;
+    tc_ld16_issue(tbase + c0, v);
+    if (two) tc_ld16_issue(tbase + c0 + 16, v + 16);
+    tc_ld_wait(v, 32);
+    for (int a = 1; a < nacc; ++a) {
+      float w[32];
+      tc_ld16_issue(tbase + a * astride + c0, w);
+      if (two) tc_ld16_issue(tbase + a * astride + c0 + 16, w + 16);
+      tc_ld_wait(w, 32);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < 16 || two) v[j] += w[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j >= 16 && !two) break;
+      if (FULL || (c0 + j < nvalid)) {
+        const float x = v[j] + bv;
+        s1 += x;
+        s2 = fmaf(x, x, s2);
+      }
+    }
+  }
+}
+
 struct TcParams {
   const float* bias;
   float* Z;
@@ -248,7 +280,8 @@ struct TcParams {
   uint32_t z_off1;       // byte offset of the second z tile in the (freed) pipeline memory when !z_early
   uint32_t red_off;      // byte offset of the per-channel reduction staging buffer (behind the pipeline stages)
   const float* dw_w;     // [C, K]
-  tn_bn_fold bn;         // has_bn: the last CTA folds the statistics into (scale, shift) (tn_bn_fold_last)
+  tn_bn_fold bn;         // has_bn: the last CTA of a channel group folds the statistics into (scale, shift)
+  TnFoldConst fc;
   int has_bn;
   const float* zprev;    // [R, C]
   float* dzprev;         // [R, C]
@@ -888,7 +921,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (p.cluster2) cluster_sync_all();        // the peer may still signal this CTA's barriers until its MMAs have drained
   if (p.stats)                               // group = this CTA's 128 * MT channels; the pipeline memory is free now
     tn_stats_finish(p.has_bn ? &p.bn : nullptr, p.stats, p.accum, p.M_total, m0, 128 * MT, p.tickets + blockIdx.y,
-                    tn_fix_flag(p.accum, p.M_total, (int)blockIdx.y), gridDim.x, blockIdx.y == 0);
+                    tn_fix_flag(p.accum, p.M_total, (int)blockIdx.y), gridDim.x, blockIdx.y == 0, p.fc);
   if (threadIdx.x == 0 && p.trace && blockIdx.y == 0 && blockIdx.x < 256) {
     unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[257 + 2 * blockIdx.x] = (long long)gt; }
   if (threadIdx.x == 0) { TC_TRACE(102); if (p.trace && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) {
@@ -911,6 +944,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // signalled in both CTAs by the leader's multicast tcgen05.commit).
 // ---------------------------------------------------------------------------
 #define TC2_STAGES 3
+// debug timeline of the pair kernel (tn_gemm_tc_set_trace): globaltimer (ns) of CTA 0 -> slots [0, 64), of CTA gridDim.x / 2 (rounded
+// to its pair's leader) -> slots [64, 128)
+#define TC2_TRACE(slot) do { if (p.trace && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == ((gridDim.x / 2) & ~1u))) { \
+    unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); \
+    p.trace[(blockIdx.x == 0 ? 0 : 64) + (slot)] = (long long)gt_; } } while (0)
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_leader, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1) : "memory");
@@ -1063,6 +1101,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ,
                 const __grid_constant__ CUtensorMap tmG, TcParams p) {
   tn_grid_dep_sync();
+  if (threadIdx.x == 0) TC2_TRACE(0);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[5 * TC2_STAGES + 1 + 2 * TC2_STAGES];
   __shared__ uint32_t tmem_base_slot;
@@ -1120,6 +1159,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  if (threadIdx.x == 0) TC2_TRACE(1);
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs) =====
@@ -1159,6 +1199,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           for (int b = b0; b < b1; ++b)
             tma_load_2d(smem_u32(z_ptr(b)), &tmZ, zbar0 + 8 * g, m0 + (int)rank * 128 + (b >> 1) * 32, n0 + (b & 1) * BN2);
         }
+      }
+    }
+    if (MODE != 1 && p.stats) {
+      // ===== statistics ticket + BatchNorm fold, by this otherwise idle warp, WHILE the epilogue warps store the tile =====
+      // The epilogue warps first run a statistics-only pass over the accumulators, add their per-channel sums into the
+      // fixed-point accumulators and arrive on named barrier 3.  Fence + ticket + (last CTA of the group:) read-back, fold and
+      // stores are a chain of ~3 global round trips (~2.5 us as a serial tail of the kernel, measured); here they overlap the
+      // ~2.5 us the other warps spend writing Z.
+      __syncwarp();                            // lane 0 comes out of the producer loop: reconverge before the named barrier
+      if (lane == 0) TC2_TRACE(10);
+      asm volatile("bar.sync 3, %0;" ::"n"(32 * EW + 32) : "memory");
+      if (lane == 0) TC2_TRACE(11);
+      const int grp = 2 * (int)blockIdx.y + (int)rank;
+      unsigned int last = 0;
+      if (lane == 0) {
+        __threadfence();
+        TC2_TRACE(12);
+        const unsigned int t = atomicAdd(p.tickets + grp, 1u);
+        last = (t == (gridDim.x >> 1) - 1) ? 1u : 0u;
+        if (last) p.tickets[grp] = 0u;
+        TC2_TRACE(13);
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        __threadfence();
+        tn_stats_fold_channels(p.has_bn ? &p.bn : nullptr, p.stats, p.accum, p.M_total, m0 + (int)rank * 128, 128, tn_fix_flag(p.accum, p.M_total, grp),
+                               blockIdx.y == 0 && rank == 0, lane, 32, p.fc);
       }
     }
   } else if (warp == 1) {
@@ -1359,7 +1426,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(ready0 + 8 * s);                 // one arrival per warp on this CTA's barrier
     }
+    if (tid == 0) TC2_TRACE(2);
     mbar_wait(accum_bar, 0);
+    if (tid == 0) TC2_TRACE(3);
     tc_fence_after();
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int co = m0 + (int)rank * 128 + quad * 32 + lane;
@@ -1384,20 +1453,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
     } else {
     const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int r0 = n0 + t * BN2;
-      const int nvalid = min(BN2, p.R - r0);
-      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * 256);
-      float* zp = p.Z + (size_t)r0 * p.M_total + co;
-      const int na = p.nacc > 1 ? p.nacc : 1;
-      if (nvalid == BN2) tc_epilogue<false, false, true>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, s1, s2, half, EW / 4, na, BN2);
-      else if (nvalid > 0) tc_epilogue<false, false, false>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, s1, s2, half, EW / 4, na, BN2);
-    }
+    const int na = p.nacc > 1 ? p.nacc : 1;
     if (p.stats) {
+      // statistics first (no stores yet), so that the ticket / fold chain of warp 0 overlaps the store pass below
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int nvalid = min(BN2, p.R - (n0 + t * BN2));
+        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * 256);
+        if (nvalid == BN2) tc_epilogue_stats<true>(tbase, BN2, nvalid, bv, s1, s2, half, EW / 4, na, BN2);
+        else if (nvalid > 0) tc_epilogue_stats<false>(tbase, BN2, nvalid, bv, s1, s2, half, EW / 4, na, BN2);
+      }
       // the warps of each lane quadrant are combined in shared memory in a fixed order; the CTA's per-channel partial sums
       // are added into the fixed-point accumulators (integer atomics: order-independent, see tn_fix_add)
+      if (tid == 0) TC2_TRACE(4);
       float* red = reinterpret_cast<float*>(smem + p.red_off);          // [EW/4 parts][2 sums][128 channels]
       const int chl = (int)(threadIdx.x & 127u);
       red[(half * 2 + 0) * 128 + chl] = s1;
@@ -1410,17 +1479,30 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         for (int pp = 0; pp < EW / 4; ++pp) acc += red[(pp * 2 + which) * 128 + ch];
         tn_fix_add(p.accum, p.M_total, which, (co - chl) + ch, acc, tn_fix_flag(p.accum, p.M_total, 2 * (int)blockIdx.y + (int)rank));
       }
+      if (tid == 0) TC2_TRACE(5);
+      asm volatile("bar.arrive 3, %0;" ::"n"(32 * EW + 32) : "memory");      // warp 0 takes it from here
+    }
+    if (tid == 0) TC2_TRACE(6);
+    float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int r0 = n0 + t * BN2;
+      const int nvalid = min(BN2, p.R - r0);
+      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * 256);
+      float* zp = p.Z + (size_t)r0 * p.M_total + co;
+      if (nvalid == BN2) tc_epilogue<false, false, true>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, d1, d2, half, EW / 4, na, BN2);
+      else if (nvalid > 0) tc_epilogue<false, false, false>(tbase, zp, (size_t)p.M_total, BN2, nvalid, bv, d1, d2, half, EW / 4, na, BN2);
     }
     }
   }
+  if (threadIdx.x == 64) TC2_TRACE(7);
+  if (threadIdx.x == 0) TC2_TRACE(14);
   tc_fence_before();
   cluster_sync_all();                                     // the peer reads this CTA's smem / signals its barriers until its MMAs drained
+  if (threadIdx.x == 0) TC2_TRACE(8);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
-  if (p.stats)                    // group = this CTA's 128 channels over all pairs
-    tn_stats_finish(p.has_bn ? &p.bn : nullptr, p.stats, p.accum, p.M_total, m0 + (int)rank * 128, 128, p.tickets + 2 * blockIdx.y + rank,
-                    tn_fix_flag(p.accum, p.M_total, 2 * (int)blockIdx.y + (int)rank), gridDim.x >> 1, blockIdx.y == 0 && rank == 0);
 }
 
 // Split scheme per GEMM.  The weight split carries BOTH correction formats (ws = [3, M, Kd]: tf32 hi | tf32 lo | packed bf16
@@ -1936,6 +2018,7 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
                "gemm_tc: statistics need a tn_scratch with TN_ACCUM_WORDS(M) zeroed accumulator words and the ticket array");
     TN_REQUIRE(M / 128 <= TN_TICKETS, "gemm_tc: statistics of more than %d channels are not supported", TN_TICKETS * 128);
     p.accum = scratch->accum; p.tickets = scratch->tickets;
+    p.fc = tn_fold_const(p.has_bn ? p.bn.n : 1.0);
   }
   TN_REQUIRE(tn_gemm_tc_supported(R, Kd, M), "gemm_tc: unsupported shape R=%d K=%d M=%d (need K %% 32 == 0, M %% 128 == 0)", R, Kd, M);
   TN_REQUIRE(nsplit == 1 || nsplit == 3, "gemm_tc: nsplit must be 1 or 3");
@@ -1986,6 +2069,7 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
       if (p.has_bnb && (rc = make_map(&mG, p.bnb.z, R, Kd, best / 2)) != TN_OK) return rc;
       p.R = R; p.Kd = Kd; p.M_total = M; p.BN = best; p.BNo = 2 * best - halo2; p.nsplit = 3;
       p.nacc = p.dw_K > 0 ? 1 : pick_nacc(256, best, Kd / TC_BK, 3);
+      p.trace = g_trace;
       const size_t stage_bytes = 2ull * 128 * TC_BK * 4 + 4ull * (best / 2) * TC_BK * 4 + raw2;
       p.red_off = (uint32_t)(stage_bytes * TC2_STAGES);
       p.par_off = (uint32_t)(stage_bytes * TC2_STAGES + red2 - par2);
