@@ -241,6 +241,13 @@ int tn_tanh_bwd(const float* dh, const float* h, float* out, long long n, void* 
 /* m[b,c] = mean_t act(z3)[b,t,c]  (written, fixed-order reduction; scale == NULL: z3 is already the activation) */
 int tn_se_mean(const float* z3, float* m, const float* scale, const float* shift, int relu, float drop_p,
                const unsigned long long* seed, unsigned int layer, int B, int T, int C, void* stream);
+/* tn_se_mean + tn_se_mlp_fwd in ONE launch: a thread-block cluster per utterance squeezes, exchanges the means and the hidden
+ * layer's partial sums through distributed shared memory in a fixed order (reproducible, no atomics) and writes m and gate.
+ * Needs tn_se_squeeze_excite_supported(C, Cr) (C <= 1024, Cr a power of two >= 8). */
+int tn_se_squeeze_excite_supported(int C, int Cr);
+int tn_se_squeeze_excite(const float* z3, float* m, float* gate, const float* W1, const float* W2, const float* scale,
+                         const float* shift, int relu, float drop_p, const unsigned long long* seed, unsigned int layer, int B,
+                         int T, int C, int Cr, void* stream);
 /* tn_tail_bwd1 + tn_se_mlp_bwd in one launch (dgate, dW1, dW2 ACCUMULATED; counters: B zeroed unsigned ints, device-wide tickets reset by the kernel) */
 int tn_tail_bwd1_mlp(const float* dout, const float* out, const float* z3, float* dgate, unsigned int* counters,
                      const float* gate, const float* m, const float* W1, const float* W2, float* dm, float* dW1, float* dW2,

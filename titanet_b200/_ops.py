@@ -614,6 +614,8 @@ TC_FUSE_DWBWD = __import__("os").environ.get("TN_FUSE_DWBWD", "1") != "0"     # 
 import os as _os
 FUSE_BLOCK_ENTRY = _os.environ.get("TN_FUSE_BLOCK_ENTRY", "0") == "1"
 FUSE_SE_MLP = _os.environ.get("TN_FUSE_SE_MLP", "0") == "1"
+# squeeze + excitation forward as one cluster kernel (tn_se_squeeze_excite: DSMEM exchange, no atomics); 0 = two launches (A/B)
+FUSE_SE_FWD = _os.environ.get("TN_FUSE_SE_FWD", "1") != "0"
 
 
 # TN_FUSE_DWFWD=1: the depthwise conv as the pointwise GEMM's operand producer (tn_gemm_tc_dwfwd).  Parity-green and 1.3 us
@@ -834,8 +836,12 @@ class SETail(Function):
         Cr = W1.shape[0]
         m, gate = empty((B, C), z3), empty((B, C), z3)
         out = empty(z3.shape, z3)
-        call("tn_se_mean", ptr(z3), ptr(m), ptr(sc3), ptr(sh3), 1, float(p3), ptr(seed), int(layer3), B, T, C)
-        call("tn_se_mlp_fwd", ptr(m), ptr(W1), ptr(W2), ptr(gate), B, C, Cr)
+        if FUSE_SE_FWD and LIB.query("tn_se_squeeze_excite_supported", C, Cr):
+            call("tn_se_squeeze_excite", ptr(z3), ptr(m), ptr(gate), ptr(W1), ptr(W2), ptr(sc3), ptr(sh3), 1, float(p3), ptr(seed),
+                 int(layer3), B, T, C, Cr)
+        else:
+            call("tn_se_mean", ptr(z3), ptr(m), ptr(sc3), ptr(sh3), 1, float(p3), ptr(seed), int(layer3), B, T, C)
+            call("tn_se_mlp_fwd", ptr(m), ptr(W1), ptr(W2), ptr(gate), B, C, Cr)
         call("tn_tail_fwd", ptr(z3), ptr(s), ptr(gate), ptr(out), ptr(sc3), ptr(sh3), float(p3), int(layer3), ptr(scs), ptr(shs),
              float(p_o), int(layer_o), ptr(seed), B, T, C)
         ctx.save_for_backward(z3, sc3, sh3, s, scs, shs, W1, W2, seed, m, gate, out)
