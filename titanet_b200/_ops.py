@@ -721,6 +721,12 @@ def _dwpw_dgrad(dz, pw3, ws_t, z, scale, shift, dw_w, dw_b, seed, relu, p, layer
     return dzp, dscale, dshift, ddw, ddb
 
 
+# TN_RECOMPUTE_U=1: do not keep the depthwise outputs u for the backward pass (3 of the 9 tensors a mega-block saves); the
+# weight-gradient GEMM's operand is recomputed by one tn_dw_fwd launch per sub-block (same dropout seed and layer id: the same
+# values).  ~6 % slower per step, one third less activation memory: what lets the batch sweep reach 2048 on one GPU.
+RECOMPUTE_U = __import__("os").environ.get("TN_RECOMPUTE_U", "0") == "1"
+
+
 def _dwbwd_tc_ok(R: int, Co: int, C: int, K: int) -> bool:
     return (TC_ENABLED and TC_FUSE_DWBWD and R >= TC_MIN_ROWS and Co % 32 == 0 and C % 128 == 0 and K % 2 == 1 and K <= 11
             and (R + 16) * C < 2 ** 32)
@@ -743,7 +749,7 @@ class DwPwBN(Function):
         n = float(B * T)
         bn = make_bn_fold(gamma, beta, rm, rv, nbt, momentum, eps, n, fold[0], fold[1], fold[2], fold[3])
         u, zo, ctx.ws_t = _dw_pw_forward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, relu, p, layer, B, T, stats, bn)
-        ctx.save_for_backward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, u, zo, gamma, fold)
+        ctx.save_for_backward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, None if RECOMPUTE_U else u, zo, gamma, fold)
         ctx.meta = (relu, p, layer, B, T, n)
         return zo, fold[0], fold[1]
 
@@ -753,6 +759,10 @@ class DwPwBN(Function):
         relu, p, layer, B, T, n = ctx.meta
         pw3 = pw_w if pw_w.dim() == 3 else pw_w.unsqueeze(-1)
         Co = pw3.shape[0]
+        if u is None:                 # TN_RECOMPUTE_U: rebuild the wgrad operand (identical values: stateless dropout hash)
+            u = empty(z.shape, z)
+            call("tn_dw_fwd", ptr(z), ptr(u), ptr(dw_w), ptr(dw_b), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer),
+                 B, T, dw_w.shape[0], dw_w.shape[-1])
         R, C, K = B * T, dw_w.shape[0], dw_w.shape[-1]
         if _bnbwd_fusable(dzo, R, Co, C) and _dwbwd_tc_ok(R, Co, C, K):
             # data gradient first: its operand producer computes g (the BatchNorm backward) and writes it for the wgrad below

@@ -74,6 +74,13 @@ class GraphedTrainStep:
                 self._body()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        # the eager warm-up steps left a step's worth of activations cached in the default pool; the capture below allocates
+        # its own (graph-private) pool of the same size, so return the cached blocks first: the peak reservation is ONE step
+        # (TitaNet-S at batch 2048: ~90 GB instead of ~180 GB)
+        for p in self.params:
+            p.grad = None
+        self.emb = self.preds = self.loss = None
+        torch.cuda.empty_cache()
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.kernel_launches()
         with torch.cuda.graph(self.graph):
@@ -87,6 +94,42 @@ class GraphedTrainStep:
             if self.lengths is None:
                 raise ValueError("this step was captured without per-utterance lengths")
             self.lengths.copy_(lengths, non_blocking=True)
+
+    # ---- double-buffered input staging -------------------------------------------------------------------------------
+    # ``prefetch`` copies the NEXT step's (pinned) host inputs into a staging buffer on a copy stream while the current step
+    # is still running; ``run_prefetched`` waits for that copy, moves the staging buffer into the static inputs (a 12 MB
+    # device-to-device copy: ~4 us) and replays the step.  What a data loader with pinned buffers does; without it every
+    # step waits ~0.25 ms for its own PCIe transfer.
+    def prefetch(self, wave: torch.Tensor, labels: torch.Tensor, lengths: Optional[torch.Tensor] = None):
+        if not hasattr(self, "_stage"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage = [(torch.empty_like(self.wave), torch.empty_like(self.labels),
+                            None if self.lengths is None else torch.empty_like(self.lengths), torch.cuda.Event()) for _ in range(2)]
+            self._stage_i = 0
+            self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+            for e in self._consumed:
+                e.record(torch.cuda.current_stream(self.device))
+        w, l, n, ev = self._stage[self._stage_i]
+        self._copy_stream.wait_event(self._consumed[self._stage_i])      # the step that read this buffer last has consumed it
+        with torch.cuda.stream(self._copy_stream):
+            w.copy_(wave, non_blocking=True)
+            l.copy_(labels, non_blocking=True)
+            if n is not None and lengths is not None:
+                n.copy_(lengths, non_blocking=True)
+            ev.record(self._copy_stream)
+
+    def run_prefetched(self) -> torch.Tensor:
+        i = self._stage_i
+        w, l, n, ev = self._stage[i]
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        self.wave.copy_(w, non_blocking=True)
+        self.labels.copy_(l, non_blocking=True)
+        if n is not None:
+            self.lengths.copy_(n, non_blocking=True)
+        self._consumed[i].record(cur)
+        self._stage_i = 1 - i
+        return self.run()
 
     def run(self) -> torch.Tensor:
         """One step on whatever is in the static input buffers."""

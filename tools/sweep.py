@@ -3,7 +3,7 @@
 ``python tools/sweep.py [--model s] [--batches 32,64,...] [--out gpurun_out/sweep.jsonl]`` runs ``bench.py`` once per batch
 size in a fresh process (no CPU baseline; 5 timed steps after 3 warm-up steps) and collects the JSON lines.  A batch is
 skipped when the previous one's peak reservation says it would not fit in HBM (activations grow linearly with the batch;
-TitaNet-S at batch 2048 does not fit: the eager warm-up pool and the CUDA-graph pool each hold a step's ~90 GB).
+TitaNet-S at batch 2048 holds ~90 GB of saved activations; TN_RECOMPUTE_U=1 drops a third of them).
 """
 import argparse
 import json
@@ -19,8 +19,9 @@ def main():
     ap.add_argument("--model", default="s")
     ap.add_argument("--blocks", type=int, default=17)
     ap.add_argument("--seconds", type=float, default=3.0)
-    ap.add_argument("--batches", default="32,64,128,256,512,1024")
+    ap.add_argument("--batches", default="32,64,128,256,512,1024,2048")
     ap.add_argument("--hbm-gb", type=float, default=150.0, help="skip a batch predicted to need more than this")
+    ap.add_argument("--gpus", type=int, default=1, help="ranks (torchrun) per run: the batch is per GPU (weak scaling)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
@@ -32,8 +33,11 @@ def main():
                 continue
             cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--batch", str(b), "--model", args.model, "--blocks",
                    str(args.blocks), "--seconds", str(args.seconds), "--steps", "5", "--warmup", "3", "--no-cpu-baseline"]
+            if args.gpus > 1:
+                cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr",
+                       "127.0.0.1", "--master-port", "29671"] + cmd[1:] + ["--gpus", str(args.gpus)]
             try:
-                res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+                res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
             except subprocess.TimeoutExpired:
                 print(f"batch {b}: timed out", flush=True)
                 break
