@@ -1440,9 +1440,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16);
       float* red = reinterpret_cast<float*>(smem + p.red_off);
       constexpr int NP = EW / 4, NT = 32 * EW;
-      if (EW > 8) {                                           // 128-register budget: narrow windows only (host: K <= 3)
+      if (EW > 12) {                                          // 113-register budget: narrow windows only (host: K <= 3)
         if (p.dw_K == 1) tc_epilogue_dwbwd<1>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT);
         else tc_epilogue_dwbwd<3>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT);
+      } else if (EW > 8) {                                    // 146 registers: windows up to K = 7 (host)
+        switch (p.dw_K) {
+          case 1: tc_epilogue_dwbwd<1>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT); break;
+          case 3: tc_epilogue_dwbwd<3>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT); break;
+          case 5: tc_epilogue_dwbwd<5>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT); break;
+          default: tc_epilogue_dwbwd<7>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT); break;
+        }
       } else switch (p.dw_K) {
         case 1: tc_epilogue_dwbwd<1>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT); break;
         case 3: tc_epilogue_dwbwd<3>(tbase, p, act, co, n0, half, z_ptr(ba), red, BN2, z_ptr(bb), NP, NT); break;
@@ -2040,7 +2047,9 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
       const int v = e ? atoi(e) : 16;
       ew_sel = (v == 8 || v == 12) ? v : 16;
     }
-    const int ew = (p.dw_K > 0 && p.dw_K <= 3) ? ew_sel : 8;
+    static int ew7 = -1;                                       // epilogue warps of the fused backward for 3 < K <= 7: 8 or 12
+    if (ew7 < 0) { const char* e = getenv("TN_TC_EW7"); ew7 = (e && atoi(e) == 8) ? 8 : 12; }
+    const int ew = (p.dw_K > 0 && p.dw_K <= 3) ? ew_sel : ((p.dw_K > 3 && p.dw_K <= 7) ? ew7 : 8);
     const bool wide = ew > 8;
     const int par2 = p.fdw_K > 0 ? (Kd * (3 + p.fdw_K) * 4 + 1023) / 1024 * 1024 : (p.has_bnb ? (Kd * 3 * 4 + 1023) / 1024 * 1024 : 0);
     const int raw2 = p.fdw_K > 0 ? 2 * 8 * TC_BK * 4 : 0;      // halo rows of the two raw tiles per stage
