@@ -102,6 +102,13 @@ int tn_conv_gemm_simt(const float* X, const float* W, const float* bias, float* 
 int tn_conv_wgrad_simt(const float* dZ, const float* X, float* dW, float* dbias, int B, int T, int Ci, int Co, int K,
                        void* stream);
 
+/* K-tap dense conv as one tensor-core GEMM (the prolog conv, src/models.py:370): tn_im2col_nwc unrolls the taps into the
+ * reduction dimension, out[r, tap*Ci + ci] = x[r + tap - K/2, ci] (zero outside the utterance and from K*Ci up to Kpad, a
+ * multiple of 32); tn_conv_weight_gemm reorders the weight the same way (to_gemm = 1: w[Co,Ci,K] -> w3[Co,Kpad]) and its
+ * gradient back (to_gemm = 0: dw3[Co,Kpad] -> dw[Co,Ci,K]).  conv(x, w) = out w3^T then runs on tn_gemm_tc / tn_gemm_tc_bn. */
+int tn_im2col_nwc(const float* x, float* out, int B, int T, int Ci, int K, int Kpad, void* stream);
+int tn_conv_weight_gemm(const float* src, float* dst, int Co, int Ci, int K, int Kpad, int to_gemm, void* stream);
+
 /* Tensor-core path for the 1x1 convs / linears (tcgen05 + TMEM + TMA, split arithmetic = fp32-equivalent):
  * Z[R,M] = bias + X[R,Kd] W[M,Kd]^T.  ws = split weights [3, M, Kd] from tn_split_tf32
  * (transpose = 1 reads W as [Kd, M]: the data-gradient GEMM); its layout is private to the library

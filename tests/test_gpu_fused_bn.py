@@ -229,3 +229,41 @@ def test_depthwise_fused_into_gemm_operand(B, T, C, Co, K, lazy, p):
         zr = F.conv1d(ur, pw_w.double(), pw_b.double()).permute(0, 2, 1).reshape(R, Co)
         assert rel(outs[0][0], ur.permute(0, 2, 1).reshape(R, C)) < 1e-5
         assert rel(outs[0][1], zr) < 1e-5
+
+
+def test_prolog_conv_as_tensor_core_gemm_matches_fp64():
+    """The K-tap dense conv of the prolog (ConvBlock1d(80, H, 3), src/models.py:370) with its taps unrolled into the reduction
+    dimension (tn_im2col_nwc + tn_conv_weight_gemm) runs as one tcgen05 GEMM + BatchNorm fold; forward and the gradients of the
+    weight, bias, gamma, beta against fp64 torch.  (An input that needs a gradient keeps the CUDA-core kernel.)"""
+    from titanet_b200 import _lib, modules
+    from titanet_b200.modules import Lazy
+    B, T, Ci, Co, K = 64, 301, 80, 256, 3
+    g = torch.Generator().manual_seed(11)
+    x = 0.3 * torch.randn(B, Ci, T, generator=g)
+    gy = torch.randn(B * T, Co, generator=g)
+    conv = modules.Conv1dSamePadding(Ci, Co, K)
+    bn_gpu = _bn(Co, g)
+    ref_conv = torch.nn.Conv1d(Ci, Co, K, padding=K // 2).double()
+    ref_conv.load_state_dict({k: v.double() for k, v in conv.state_dict().items()})
+    bn_ref = _bn(Co, g).double().train()
+    bn_ref.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in bn_gpu.state_dict().items()})
+    conv, bn_gpu = conv.cuda(), bn_gpu.cuda().train()
+    _lib.COUNTS.clear()
+    z, sc, sh = conv._fwd_bn(Lazy.from_ncw(x.cuda()), bn_gpu)
+    assert _lib.COUNTS.get("tn_im2col_nwc", 0) == 1 and _lib.COUNTS.get("tn_gemm_tc_bn", 0) == 1 and _lib.COUNTS.get("tn_conv_gemm_simt_bn", 0) == 0
+    y = ops_act(z, sc, sh)
+    (y * gy.cuda()).sum().backward()
+    assert _lib.COUNTS.get("tn_wgrad_tc", 0) == 1
+    yr = bn_ref(ref_conv(x.double())).permute(0, 2, 1).reshape(B * T, Co)
+    (yr * gy.double()).sum().backward()
+    assert rel(y, yr) < 1e-5
+    assert rel(conv.weight.grad, ref_conv.weight.grad) < 2e-3                       # plain-TF32 weight-gradient GEMM
+    assert rel(bn_gpu.weight.grad, bn_ref.weight.grad) < 1e-4 and rel(bn_gpu.bias.grad, bn_ref.bias.grad) < 1e-4
+    assert rel(bn_gpu.running_var, bn_ref.running_var) < 1e-5
+    gmax = float(ref_conv.weight.grad.abs().max())
+    assert float(conv.bias.grad.abs().max()) < 1e-3 * gmax                           # mathematically zero in front of a train-mode BatchNorm
+
+
+def ops_act(z, sc, sh):
+    from titanet_b200 import _ops as ops
+    return ops.Act.apply(z, sc, sh, None, False, 0.0, 0)

@@ -464,6 +464,53 @@ class ConvGemmBN(Function):
         return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None, None
 
 
+class Im2Col(Function):
+    """X3[r, tap * Ci + ci] = x[r + tap - K/2, ci] (zero outside the utterance / up to Kpad): a K-tap dense conv becomes the
+    1x1 GEMM X3 W3^T on the tensor cores.  No input gradient (the caller takes the CUDA-core path when the input needs one)."""
+
+    @staticmethod
+    def forward(ctx, x, B: int, T: int, K: int, Kpad: int):
+        x = _c(x)
+        out = empty((B * T, Kpad), x)
+        call("tn_im2col_nwc", ptr(x), ptr(out), B, T, x.shape[1], K, Kpad)
+        ctx.mark_non_differentiable(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        return None, None, None, None, None
+
+
+class ConvWeightAsGemm(Function):
+    """w[Co, Ci, K] -> w3[Co, Kpad, 1] with w3[co, tap * Ci + ci] = w[co, ci, tap]; backward reorders the gradient back."""
+
+    @staticmethod
+    def forward(ctx, w, Kpad: int):
+        w = _c(w)
+        Co, Ci, K = w.shape
+        w3 = empty((Co, Kpad, 1), w)
+        call("tn_conv_weight_gemm", ptr(w), ptr(w3), Co, Ci, K, Kpad, 1)
+        ctx.meta = (Co, Ci, K, Kpad)
+        return w3
+
+    @staticmethod
+    def backward(ctx, dw3):
+        Co, Ci, K, Kpad = ctx.meta
+        dw = gempty((Co, Ci, K), dw3)
+        call("tn_conv_weight_gemm", ptr(_c(dw3)), ptr(dw), Co, Ci, K, Kpad, 0)
+        return dw, None
+
+
+# TN_PROLOG_TC=0: keep the K-tap dense conv (prolog) on the exact-fp32 CUDA-core kernel (A/B)
+PROLOG_TC = __import__("os").environ.get("TN_PROLOG_TC", "1") != "0"
+
+
+def conv_ktap_as_gemm_ok(x: Tensor, w: Tensor, B: int, T: int) -> bool:
+    """A dense K-tap conv whose unrolled reduction fits one GEMM tile row (Ci * K <= 512) and whose input needs no gradient."""
+    Co, Ci, K = w.shape
+    return (TC_ENABLED and PROLOG_TC and K > 1 and not x.requires_grad and B * T >= 512 and Co % 128 == 0 and Ci * K <= 512)
+
+
 def _bn_trainable(bn: torch.nn.BatchNorm1d) -> bool:
     return (bn.training or bn.running_mean is None) and bn.momentum is not None and bn.affine
 

@@ -103,6 +103,67 @@ extern "C" int tn_nwc_to_ncw(const float* x, float* y, int B, int C, int T, void
 }
 
 // ---------------------------------------------------------------------------
+// K-tap dense conv as ONE tensor-core GEMM (the prolog ConvBlock1d(80, H, 3), src/models.py:370): the taps are unrolled
+// into the reduction dimension,  X3[r, tap * Ci + ci] = x[r + tap - K/2, ci]  (zero outside the utterance, zero padding up
+// to Kpad, a multiple of 32), W3[co, tap * Ci + ci] = w[co, ci, tap], so that conv(x, w) = X3 W3^T runs on tn_gemm_tc_bn
+// like every 1x1 conv instead of the CUDA-core kernel (the last contraction that was left there).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_nwc_kernel(const float* __restrict__ x, float* __restrict__ out, int R, int T, int Ci,
+                                                         int K, int Kpad) {
+  tn_grid_dep_sync();
+  const int pad = K / 2;
+  const int q4 = Kpad >> 2;                                       // float4s per output row
+  const size_t total = (size_t)R * q4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / q4), kk = (int)(i - (size_t)r * q4) * 4;
+    const int t = r % T;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kk + j;
+      const int tap = k / Ci, ci = k - tap * Ci;
+      const int tt = t + tap - pad;
+      v[j] = (tap < K && tt >= 0 && tt < T) ? __ldg(x + (size_t)(r + tap - pad) * Ci + ci) : 0.f;
+    }
+    tn_st4(out + (size_t)r * Kpad + kk, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+extern "C" int tn_im2col_nwc(const float* x, float* out, int B, int T, int Ci, int K, int Kpad, void* stream) {
+  TN_REQUIRE(x && out && B > 0 && T > 0 && Ci > 0 && K > 0 && (K & 1) && Kpad >= K * Ci && Kpad % 4 == 0 && tn_aligned16(out),
+             "im2col_nwc: bad arguments (B=%d T=%d Ci=%d K=%d Kpad=%d)", B, T, Ci, K, Kpad);
+  const long long R = (long long)B * T;
+  TN_REQUIRE(R < (1ll << 31), "im2col_nwc: B*T too large");
+  long long blocks = (R * (Kpad / 4) + 255) / 256;
+  if (blocks > (long long)tn_num_sms() * 16) blocks = (long long)tn_num_sms() * 16;
+  tn_launch(im2col_nwc_kernel, (unsigned)blocks, 256, 0, stream, x, out, (int)R, T, Ci, K, Kpad);
+  TN_LAUNCH_CHECK("im2col_nwc_kernel");
+  return TN_OK;
+}
+// to_gemm = 1: w3[co, tap * Ci + ci] = w[co, ci, tap] (zeros up to Kpad);  to_gemm = 0: w[co, ci, tap] = w3[co, tap * Ci + ci]
+__global__ void conv_weight_gemm_kernel(const float* __restrict__ src, float* __restrict__ dst, int Co, int Ci, int K, int Kpad, int to_gemm) {
+  tn_grid_dep_sync();
+  const int n = to_gemm ? Co * Kpad : Co * Ci * K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (to_gemm) {
+      const int co = i / Kpad, kk = i - co * Kpad;
+      const int tap = kk / Ci, ci = kk - tap * Ci;
+      dst[i] = tap < K ? src[((size_t)co * Ci + ci) * K + tap] : 0.f;
+    } else {
+      const int co = i / (Ci * K), rem = i - co * Ci * K;
+      const int ci = rem / K, tap = rem - ci * K;
+      dst[i] = src[(size_t)co * Kpad + tap * Ci + ci];
+    }
+  }
+}
+extern "C" int tn_conv_weight_gemm(const float* src, float* dst, int Co, int Ci, int K, int Kpad, int to_gemm, void* stream) {
+  TN_REQUIRE(src && dst && Co > 0 && Ci > 0 && K > 0 && Kpad >= K * Ci, "conv_weight_gemm: bad arguments");
+  const int n = to_gemm ? Co * Kpad : Co * Ci * K;
+  tn_launch(conv_weight_gemm_kernel, tn_cdiv(n, 256), 256, 0, stream, src, dst, Co, Ci, K, Kpad, to_gemm);
+  TN_LAUNCH_CHECK("conv_weight_gemm_kernel");
+  return TN_OK;
+}
+
+// ---------------------------------------------------------------------------
 // materialise a lazy activation / its backward
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(TN_EW_THREADS) act_fwd_kernel(const float* __restrict__ z, float* __restrict__ y,

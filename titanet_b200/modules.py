@@ -138,6 +138,13 @@ class Conv1dSamePadding(nn.Conv1d):
         _check_conv_supported(self)
         if self.groups == 1:
             x = x.materialise()
+            if ops.conv_ktap_as_gemm_ok(x.z, self.weight, x.B, x.T):
+                # K taps unrolled into the reduction dimension: the conv runs as one tensor-core GEMM (+ BatchNorm fold)
+                K = self.weight.shape[2]
+                kpad = (self.weight.shape[1] * K + 31) // 32 * 32
+                x3 = ops.Im2Col.apply(x.z, x.B, x.T, K, kpad)
+                w3 = ops.ConvWeightAsGemm.apply(self.weight, kpad)
+                return ops.conv_gemm_bn(x3, w3, self.bias, bn, x.B, x.T)
             return ops.conv_gemm_bn(x.z, self.weight, self.bias, bn, x.B, x.T)
         z, stats = self._fwd(x, want_stats=bn.training)
         scale, shift = ops.bn_fold(stats, bn, float(z.shape[0]))
