@@ -257,9 +257,44 @@ def graph_time_kernel(kind: str, R: int, Ci: int, Co: int, B: int, dropout: floa
     x, out = rnd(R, Ci), torch.empty(R, Co, device=dev)
     w = rnd(Co, Ci) / math.sqrt(Ci)
     ws = torch.empty(3, Co, Ci, device=dev)
+    import ctypes
+    from titanet_b200 import _ops as ops
+    from titanet_b200._lib import TnBnBwd
+
+    def bn_bwd_desc(C):          # BatchNorm-backward operand producer over the GEMM's input (C channels)
+        zo, g = rnd(R, C), torch.empty(R, C, device=dev)
+        v = [0.01 * rnd(C), 0.01 * rnd(C), 0.1 * rnd(C), torch.rand(C, device=dev) + 0.5, torch.rand(C, device=dev) + 0.5,
+             torch.empty(C, device=dev), torch.empty(C, device=dev), torch.zeros(C, device=dev)]
+        return TnBnBwd(ptr(zo), ptr(v[0]), ptr(v[1]), ptr(v[2]), ptr(v[3]), ptr(v[4]), float(R), ptr(g), ptr(v[7]), ptr(v[5]), ptr(v[6])), (zo, g, v)
+
     if kind == "tn_wgrad_tc":
         dz, dw = rnd(R, Co), torch.zeros(Co, Ci, device=dev)
         fn = lambda: call("tn_wgrad_tc", ptr(dz), ptr(x), ptr(dw), R, Ci, Co)
+    elif kind == "tn_gemm_tc_dwbwd_bn":
+        # tag convention: Ci = channels of dZ (reduction), Co = channels of the depthwise input
+        call("tn_split_tf32", ptr(rnd(Ci, Co) / math.sqrt(Ci)), ptr(ws), Co, Ci, 1)
+        zp, dzp = rnd(R, Co), torch.empty(R, Co, device=dev)
+        dww, ddw = rnd(Co, 1, 3), torch.zeros(Co, 3, device=dev)
+        acc = torch.zeros(3, Co, device=dev)
+        sc, sh = torch.rand(Co, device=dev) + 0.5, 0.1 * rnd(Co)
+        seed = torch.tensor([1], dtype=torch.int64, device=dev)
+        bnb, keep = bn_bwd_desc(Ci)
+        fn = lambda: call("tn_gemm_tc_dwbwd_bn", ptr(x), ptr(ws), ctypes.byref(bnb), ptr(zp), ptr(dzp), ptr(dww), ptr(ddw), acc[0].data_ptr(),
+                          acc[1].data_ptr(), acc[2].data_ptr(), ptr(sc), ptr(sh), 1, float(dropout), ptr(seed) if dropout > 0 else None,
+                          3, B, T, Ci, Co, 3)
+    elif kind == "tn_gemm_tc_bnbwd":
+        call("tn_split_tf32", ptr(rnd(Ci, Co) / math.sqrt(Ci)), ptr(ws), Co, Ci, 1)
+        bnb, keep = bn_bwd_desc(Ci)
+        fn = lambda: call("tn_gemm_tc_bnbwd", ptr(x), ptr(ws), ctypes.byref(bnb), ptr(out), R, Ci, Co, 0)
+    elif kind == "tn_gemm_tc_bn":
+        call("tn_split_tf32", ptr(w), ptr(ws), Co, Ci, 0)
+        bias, st = rnd(Co), torch.empty(2 * Co, dtype=torch.float64, device=dev)
+        fold = torch.empty(4, Co, device=dev)
+        bnp = [torch.ones(Co, device=dev), torch.zeros(Co, device=dev), torch.zeros(Co, device=dev), torch.ones(Co, device=dev),
+               torch.zeros((), dtype=torch.int64, device=dev)]
+        bn = ops.make_bn_fold(bnp[0], bnp[1], bnp[2], bnp[3], bnp[4], 0.1, 1e-5, float(R), fold[0], fold[1], fold[2], fold[3])
+        scr, keep = ops.scratch(x)
+        fn = lambda: call("tn_gemm_tc_bn", ptr(x), ptr(ws), ptr(bias), ptr(out), ptr(st), ctypes.byref(bn), R, Ci, Co, 0, 3, ctypes.byref(scr))
     elif kind == "tn_gemm_tc_dwbwd":
         # tag convention: Ci = channels of dZ (reduction), Co = channels of the depthwise input
         call("tn_split_tf32", ptr(rnd(Ci, Co) / math.sqrt(Ci)), ptr(ws), Co, Ci, 1)
@@ -300,6 +335,22 @@ def graph_time_kernel(kind: str, R: int, Ci: int, Co: int, B: int, dropout: floa
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e3 / reps
+
+
+def step_traffic_model(args, B):
+    """Bytes the step's kernels move by design (sum of every kernel's unique inputs + outputs), against SURVEY section 8d's
+    compulsory figure.  Per mega-block, in units of one [B, H, T] fp32 tensor A_H:
+      forward 18 = skip GEMM 2 + 3 x (depthwise 2 + pointwise GEMM 2) + squeeze 1 + tail 3
+      backward 39 = tail pass 1 3 + tail pass 2 6 + 3 x (BatchNorm-backward / dgrad / depthwise-backward kernel 5 + wgrad 2)
+                    + skip (BatchNorm-backward / dgrad 4 + wgrad 2) + gradient sum of the block input 3
+    (round 1: 18 + 43).  Prolog / epilog / pooling / decoder: epilog GEMM and its backward, the materialised epilog activation
+    and the attentive pooling move ~16 A_1536 fwd+bwd; the mel front end 4 L + A_80."""
+    T = 1 + int(args.seconds * SAMPLE_RATE) // 160
+    H = {"s": 256, "m": 512, "l": 1024}[args.model.lower()]
+    a_h, a_e, a_m = 4.0 * B * T * H, 4.0 * B * T * 1536, 4.0 * B * T * 80
+    moved = args.blocks * 57 * a_h + 16 * a_e + 6 * a_h + 8 * a_m + 4.0 * B * args.seconds * SAMPLE_RATE
+    compulsory = 3.0 * (args.blocks * 11 * a_h + (a_m + a_h) + (a_h + a_e) + 2 * a_e + 4.0 * B * args.seconds * SAMPLE_RATE + a_m)
+    return {"step_traffic_bytes": moved, "compulsory_bytes": compulsory, "ratio": round(moved / compulsory, 3)}
 
 
 def metric_name(args) -> str:
@@ -417,6 +468,10 @@ def run_ours(args):
             per_launch_s = graph_time_kernel(kind, f["R"], f["Ci"], f["Co"], B, args.dropout, dev) * 1e-6
             if kind == "tn_gemm_tc_dwbwd":          # reads dZ and z_prev, writes dz_prev (+ weights); du never leaves the SM
                 byts = 4.0 * (f["R"] * f["Ci"] + 2 * f["R"] * f["Co"] + f["Ci"] * f["Co"])
+            if kind == "tn_gemm_tc_dwbwd_bn":       # + the BatchNorm backward: reads dZ, z (of this conv), z_prev; writes g, dz_prev
+                byts = 4.0 * (3 * f["R"] * f["Ci"] + 2 * f["R"] * f["Co"] + f["Ci"] * f["Co"])
+            if kind == "tn_gemm_tc_bnbwd":          # reads dZ, z; writes g, dX
+                byts = 4.0 * (3 * f["R"] * f["Ci"] + f["R"] * f["Co"] + f["Ci"] * f["Co"])
             if kind == "tn_gemm_tc_dwfwd":          # reads z, writes u (kept for the backward wgrad) and Z (+ weights)
                 byts = 4.0 * (2 * f["R"] * f["Ci"] + f["R"] * f["Co"] + f["Ci"] * f["Co"])
             traffic = None                          # DRAM bytes per launch of this kernel from the committed ncu --set full capture
@@ -439,7 +494,7 @@ def run_ours(args):
                     "algorithmic_tflop_s": round(ach_tf, 2), "tf32_peak_tflop_s": round(tf32_peak, 1),
                     "tf32_peak_source": pk["tf32_source"],
                     "tensor_frac_of_tf32_peak": round(ach_tf / tf32_peak, 4),
-                    "mma_issue_factor": 2 if kind == "tn_gemm_tc_dwbwd" else (1 if kind == "tn_wgrad_tc" else 3),
+                    "mma_issue_factor": 2 if kind in ("tn_gemm_tc_dwbwd", "tn_gemm_tc_dwbwd_bn", "tn_gemm_tc_bnbwd") else (1 if kind == "tn_wgrad_tc" else 3),
                     "timing": "CUDA events around a CUDA graph of 20 back-to-back launches of this shape",
                     "eager_ms_per_step_by_entry_point": {k: round(v[1] / prof_steps, 3) for k, v in
                                                          sorted(groups.items(), key=lambda kv: -kv[1][1])}}
@@ -458,7 +513,7 @@ def run_ours(args):
         "l2": "per-step working set (~2 GB of activations) >> 126 MB L2; no explicit flush",
         "e2e": {"value": round(e2e, 1), "unit": "utterances/s", "h2d_bytes_per_step": B * L * 4 + B * 8 + (B * 4 if args.ragged else 0), "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e, 3)},
-        "gpu_launches": launches, "cuda_graph": not args.no_graph,
+        "gpu_launches": launches, "cuda_graph": not args.no_graph, "traffic_model": step_traffic_model(args, B),
         "hbm_peak_gb": round(torch.cuda.max_memory_reserved(dev) / 2**30, 2), "clocks": clocks, "roofline": roof,
     }
     if not args.no_cpu_baseline and world == 1:

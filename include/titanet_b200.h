@@ -181,8 +181,10 @@ int tn_bn_stats_bwd(const float* dz_direct, const float* z, const float* dscale,
  * tn_gemm_tc_bnbwd_supported).  dZ is the DIRECT gradient w.r.t. the pre-BatchNorm tensor z [R, Kd] (what the consumers of
  * the lazy activation return); the transform warps build g = dZ + a[c] + b[c] z from the dZ tile and the z tile with the
  * statistics-path coefficients a, b of tn_bn_stats_bwd (computed in the kernel from dscale, dshift, mean, invstd, gamma), feed
- * it to the tensor core, write it to g_out (the weight-gradient GEMM's operand) and add its column sums to dbias
- * (ACCUMULATED; may be NULL); dgamma / dbeta are written.  Replaces one tn_bn_stats_bwd launch per conv. */
+ * it to the tensor core and write it to g_out (the weight-gradient GEMM's operand); dgamma / dbeta are written, and dbias
+ * (may be NULL) is written as ZERO: the bias of a conv in front of a train-mode BatchNorm has no gradient when dZ comes
+ * from the consumers of the lazy activation (sum_r g = sum_r dZ - gamma invstd dshift = 0; the reference's value is the
+ * rounding noise of that cancellation).  Replaces one tn_bn_stats_bwd launch per conv. */
 typedef struct tn_bn_bwd {
   const float* z;        /* [R, Kd] pre-BatchNorm output of the conv                       */
   const float* dscale;   /* [Kd] dL/dscale of the folded BatchNorm (sum over rows)         */
@@ -192,7 +194,7 @@ typedef struct tn_bn_bwd {
   const float* gamma;    /* [Kd] BatchNorm weight                                          */
   double n;              /* samples per channel                                            */
   float* g_out;          /* [R, Kd] out: full gradient w.r.t. z                            */
-  float* dbias;          /* [Kd] or NULL, ACCUMULATED: conv-bias gradient                  */
+  float* dbias;          /* [Kd] or NULL, out: conv-bias gradient (identically zero, see above) */
   float* dgamma;         /* [Kd] out                                                       */
   float* dbeta;          /* [Kd] out                                                       */
 } tn_bn_bwd;

@@ -1310,13 +1310,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       // ===== BatchNorm backward as the operand producer (train-mode BN behind the conv whose data gradient this GEMM is) =====
       // g = dZ + a[c] + b[c] z with the per-channel statistics-path coefficients a, b (tn_bn_stats_bwd's arithmetic), computed
       // here from (dscale, dshift, mean, invstd, gamma); dZ arrives in B_hi, z in B_lo; g is rounded / split in place, written to
-      // g_out for the weight-gradient GEMM (rows this pair owns, channel group 0 only) and summed per channel for the conv-bias
-      // gradient.  Replaces one tn_bn_stats_bwd launch (read dZ, z; write g) per conv.
+      // g_out for the weight-gradient GEMM (rows this pair owns, channel group 0 only).  Replaces one tn_bn_stats_bwd launch
+      // (read dZ, z; write g) per conv.
       constexpr int NT = 32 * EW;
       constexpr int NI = (2 * 128 * 8 + NT - 1) / NT;              // float4s per thread and chunk (BN2 <= 256: HB <= 128)
       float* sa = reinterpret_cast<float*>(smem + p.par_off);
       float* sb = sa + p.Kd;
-      float* scs = sb + p.Kd;                                      // column sums of g over this CTA's owned rows
       const tn_bn_bwd& q = p.bnb;
       const bool owner = blockIdx.y == 0;
       for (int ch = tid; ch < p.Kd; ch += NT) {
@@ -1326,10 +1325,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const double dmu = -dsh * gm * r - 2.0 * mu * dvar;
         sa[ch] = (float)(dmu / q.n);
         sb[ch] = (float)(2.0 * dvar / q.n);
-        scs[ch] = 0.f;
         if (owner && blockIdx.x == 0) {                            // rank 0 of pair 0
           q.dgamma[ch] = (float)(r * t);
           q.dbeta[ch] = (float)dsh;
+          // The conv bias in front of a train-mode BatchNorm has NO gradient: sum_r g = sum_r dZ - gamma invstd dshift, and
+          // the consumers of the lazy activation produce dZ = (dL/dpre) * scale with dshift = sum_r dL/dpre, so the two terms
+          // cancel exactly (the reference's value is the rounding noise of that cancellation).  Written as 0.
+          if (q.dbias) q.dbias[ch] = 0.f;
         }
       }
       asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");
@@ -1354,7 +1356,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         __syncwarp();
         const int ch = kc * TC_BK + 4 * (int)cq;
         const float4 a4 = *reinterpret_cast<const float4*>(sa + ch), b4 = *reinterpret_cast<const float4*>(sb + ch);
-        float4 cs = tn_zero4();
 #pragma unroll
         for (int k = 0; k < NI; ++k) {
           const int i = tid + k * NT;
@@ -1364,10 +1365,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const int gr = n0 + t * BN2 + (int)rank * HB + (row - t * HB);
             float4 g = tn_zero4();
             if (gr >= 0 && gr < p.R) g = tn_fma4(b4, zz[k], v[k] + a4);
-            if (owner && gr >= own_lo && gr < own_hi) {
-              tn_st4(q.g_out + (size_t)gr * p.Kd + ch, g);
-              cs = cs + g;
-            }
+            if (owner && gr >= own_lo && gr < own_hi) tn_st4(q.g_out + (size_t)gr * p.Kd + ch, g);
             uint4 h;
             h.x = rna_tf32(g.x); h.y = rna_tf32(g.y); h.z = rna_tf32(g.z); h.w = rna_tf32(g.w);
             reinterpret_cast<uint4*>(hi)[i] = h;
@@ -1384,27 +1382,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(ready0 + 8 * s);
-        if (owner && q.dbias) {                                    // off the chunk's critical path
-          // the four row groups of a warp hold the same chunk at lanes (c ^ (row group & 7)) + 8 j: gather them into lanes
-          // 0-7 first, so that one shared-memory atomic instruction touches 32 distinct addresses (64 lanes on the same 4
-          // addresses serialised for ~2 us per chunk)
-          const uint32_t r0 = ((uint32_t)tid >> 3) & 7u & ~3u;     // (4 w) & 7: row-group base of this warp
-          float4 tot = cs;
-#pragma unroll
-          for (uint32_t j = 1; j < 4; ++j) {
-            const uint32_t src = (((uint32_t)lane & 7u) ^ r0 ^ ((r0 + j) & 7u)) + 8u * j;
-            tot.x += __shfl_sync(0xffffffffu, cs.x, src); tot.y += __shfl_sync(0xffffffffu, cs.y, src);
-            tot.z += __shfl_sync(0xffffffffu, cs.z, src); tot.w += __shfl_sync(0xffffffffu, cs.w, src);
-          }
-          if (lane < 8) {
-            float* d = scs + kc * TC_BK + 4 * (int)((uint32_t)lane ^ r0);
-            atomicAdd(d, tot.x); atomicAdd(d + 1, tot.y); atomicAdd(d + 2, tot.z); atomicAdd(d + 3, tot.w);
-          }
-        }
-      }
-      if (owner && q.dbias) {
-        asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");
-        for (int ch = tid; ch < p.Kd; ch += NT) atomicAdd(q.dbias + ch, scs[ch]);
       }
     } else
     for (int kc = 0; kc < num_kc; ++kc) {
@@ -1437,6 +1414,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const int ba = 2 * quad, bb = 2 * quad + 1;                      // this channel block's two z boxes
       mbar_wait(zbar0 + 8 * (ba / zcap), 0);
       mbar_wait(zbar0 + 8 * (bb / zcap), 0);
+      if (tid == 0) TC2_TRACE(20);
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16);
       float* red = reinterpret_cast<float*>(smem + p.red_off);
       constexpr int NP = EW / 4, NT = 32 * EW;
@@ -2018,6 +1996,7 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   TN_REQUIRE(X && ws, "gemm_tc: null tensor");
   const bool grad = (p.flags & TN_GEMM_GRAD) != 0 || p.dw_K > 0;
   p.flags &= ~TN_GEMM_GRAD;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("TN_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.flags |= dbg & (2048 | 4096 | 8192 | 16384); }   // experiments only
   p.corr = tc_corr_for(grad);
   const float* ws_lo = ws + (size_t)(p.corr ? 2 : 1) * M * Kd;
   if (p.stats) {
@@ -2051,7 +2030,7 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
     if (ew7 < 0) { const char* e = getenv("TN_TC_EW7"); ew7 = (e && atoi(e) == 8) ? 8 : 12; }
     const int ew = (p.dw_K > 0 && p.dw_K <= 3) ? ew_sel : ((p.dw_K > 3 && p.dw_K <= 7) ? ew7 : 8);
     const bool wide = ew > 8;
-    const int par2 = p.fdw_K > 0 ? (Kd * (3 + p.fdw_K) * 4 + 1023) / 1024 * 1024 : (p.has_bnb ? (Kd * 3 * 4 + 1023) / 1024 * 1024 : 0);
+    const int par2 = p.fdw_K > 0 ? (Kd * (3 + p.fdw_K) * 4 + 1023) / 1024 * 1024 : (p.has_bnb ? (Kd * 2 * 4 + 1023) / 1024 * 1024 : 0);
     const int raw2 = p.fdw_K > 0 ? 2 * 8 * TC_BK * 4 : 0;      // halo rows of the two raw tiles per stage
     const int red2 = (p.dw_K > 0 ? ((ew / 4) * 128 * (p.dw_K + 3) * 4 + 1023) / 1024 * 1024 : (p.fdw_K > 0 ? 4096 : 2048)) + par2;
     int best = 0; double best_cost = 1e30;
