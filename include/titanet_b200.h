@@ -110,14 +110,16 @@ int tn_im2col_nwc(const float* x, float* out, int B, int T, int Ci, int K, int K
 int tn_conv_weight_gemm(const float* src, float* dst, int Co, int Ci, int K, int Kpad, int to_gemm, void* stream);
 
 /* Tensor-core path for the 1x1 convs / linears (tcgen05 + TMEM + TMA, split arithmetic = fp32-equivalent):
- * Z[R,M] = bias + X[R,Kd] W[M,Kd]^T.  ws = split weights [3, M, Kd] from tn_split_tf32
+ * Z[R,M] = bias + X[R,Kd] W[M,Kd]^T.  ws = split weights [TN_WS_PLANES, M, Kd] from tn_split_tf32
  * (transpose = 1 reads W as [Kd, M]: the data-gradient GEMM); its layout is private to the library
- * (ws[0] = tf32(W); ws[1] = tf32(W - ws[0]); ws[2] = the packed bf16 correction rows).
- * nsplit: 3 = fp32-equivalent -- forward GEMMs run 3xTF32 (hi*hi + lo*hi + hi*lo), gradient GEMMs (TN_GEMM_GRAD) tf32
- * hi*hi + one bf16 MMA carrying both corrections -- or 1 (plain TF32).  When the tile leaves TMEM columns free the main
- * products of consecutive K ranges and the corrections accumulate in separate TMEM accumulators that the epilogue adds
+ * (ws[0] = tf32(W); ws[1] = tf32(W - ws[0]); ws[2] / ws[3] = the packed bf16 / scaled-fp16 correction rows).
+ * nsplit: 3 = fp32-equivalent -- forward GEMMs run tf32 hi*hi + one fp16 MMA over a doubled K that carries both
+ * corrections with exponent-balanced scales (operand rounding = 3xTF32's, two tensor issues instead of three), gradient
+ * GEMMs (TN_GEMM_GRAD) the same with bf16 (fp32's exponent range) -- or 1 (plain TF32).  When the tile leaves TMEM columns
+ * free the main products of consecutive K ranges and the corrections accumulate in separate TMEM accumulators that the epilogue adds
  * in fp32 (the tensor core's accumulate truncates).  Needs Kd %% 32 == 0 and M %% 128 == 0 (tn_gemm_tc_supported).
  * stats (fp64 [2*M], written): per-channel sum / sum of squares of Z; needs scratch (accum + tickets). */
+#define TN_WS_PLANES 4
 int tn_gemm_tc_supported(int R, int Kd, int M);
 int tn_gemm_tc_set_trace(long long* buf);      /* debug: clock64 timeline of two CTAs (256 int64), NULL = off */
 int tn_split_tf32(const float* W, float* ws, int M, int Kd, int transpose, void* stream);
@@ -242,7 +244,11 @@ int tn_act_fwd(const float* z, float* y, const float* scale, const float* shift,
                const unsigned long long* seed, unsigned int layer, int R, int C, void* stream);
 int tn_act_bwd(const float* dy, const float* z, float* dz, float* dscale, float* dshift, const float* scale,
                const float* shift, int relu, float drop_p, const unsigned long long* seed, unsigned int layer, int R, int C,
-               void* stream);                                                        /* dscale/dshift ACCUMULATED */
+               void* stream);
+/* the same for an activation with two consumers: dy2 (or NULL) is added to dy on load (replaces autograd's sum kernel) */
+int tn_act_bwd2(const float* dy, const float* dy2, const float* z, float* dz, float* dscale, float* dshift, const float* scale,
+                const float* shift, int relu, float drop_p, const unsigned long long* seed, unsigned int layer, int R, int C,
+                void* stream);                                                        /* dscale/dshift ACCUMULATED */
 int tn_tanh_bwd(const float* dh, const float* h, float* out, long long n, void* stream);
 
 /* ---- squeeze-excitation + mega-block tail: SqueezeExcitation.forward

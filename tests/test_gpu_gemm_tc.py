@@ -19,7 +19,7 @@ def run_tc(x, w, bias, nsplit, transpose=False, want_stats=True, flags=0, z0=Non
     from titanet_b200._ops import scratch
     R, Kd = x.shape
     M = w.shape[1] if transpose else w.shape[0]
-    ws = torch.empty(3, M, Kd, device="cuda")
+    ws = torch.empty(4, M, Kd, device="cuda")
     call("tn_split_tf32", ptr(w), ptr(ws), M, Kd, int(transpose))
     z = torch.empty(R, M, device="cuda") if z0 is None else z0
     stats = torch.full((2 * M,), float("nan"), device="cuda", dtype=torch.float64) if want_stats else None   # written, not accumulated

@@ -178,6 +178,38 @@ def test_bn_fold_act_chain(ops, training):
         assert int(bn.num_batches_tracked) == 0
 
 
+@pytest.mark.parametrize("R,C", [(64, 3072), (1203, 1536), (37, 80), (500, 192), (3000, 256), (9, 4)])
+def test_act_two_consumers_and_colsum_slab_tiling(ops, R, C):
+    """tn_act_fwd / tn_act_bwd2 (two gradients summed on load) / tn_colsum over the slab tiling: wide tensors (several 256-channel
+    slabs), few rows, channel counts that do not fill a slab, row counts that are not a multiple of the unroll."""
+    from titanet_b200._lib import call, ptr
+    g = torch.Generator().manual_seed(R + C)
+    z = torch.randn(R, C, generator=g, dtype=torch.float64)
+    sc = 0.5 + torch.rand(C, generator=g, dtype=torch.float64)
+    sh = 0.3 * torch.randn(C, generator=g, dtype=torch.float64)
+    d1, d2 = torch.randn(R, C, generator=g, dtype=torch.float64), torch.randn(R, C, generator=g, dtype=torch.float64)
+    zr, scr, shr = (t.clone().requires_grad_(True) for t in (z, sc, sh))
+    yr = torch.relu(zr * scr + shr)
+    (yr * d1).sum().backward(retain_graph=True)
+    one = [t.grad.clone() for t in (zr, scr, shr)]
+    (yr * d2).sum().backward()
+    both = [t.grad.clone() for t in (zr, scr, shr)]
+    zg, scg, shg = (t.float().to(dev()).requires_grad_(True) for t in (z, sc, sh))
+    ya, yb = ops.Act2.apply(zg, scg, shg, None, True, 0.0, 0)
+    assert ya.data_ptr() == yb.data_ptr() and rel(ya, yr) < 1e-6
+    ((ya * d1.float().to(dev())).sum() + (yb * d2.float().to(dev())).sum()).backward()
+    for got, want in zip((zg.grad, scg.grad, shg.grad), both):
+        assert rel(got, want) < 2e-5
+    zg.grad = scg.grad = shg.grad = None
+    ya, yb = ops.Act2.apply(zg, scg, shg, None, True, 0.0, 0)
+    (yb * d1.float().to(dev())).sum().backward()              # only the second alias is used
+    for got, want in zip((zg.grad, scg.grad, shg.grad), one):
+        assert rel(got, want) < 2e-5
+    out = torch.zeros(C, device=dev())
+    call("tn_colsum", ptr(zg.detach()), ptr(out), R, C)
+    assert rel(out, z.float().double().sum(0)) < 2e-5
+
+
 def test_colstats_bn_over_batch(ops):
     B, C = 6, 96
     g = torch.Generator().manual_seed(5)

@@ -199,6 +199,7 @@ TC_FWD_NSPLIT = 3
 TC_BWD_NSPLIT = 3
 TC_WGRAD = True
 TC_MIN_ROWS = 256
+WS_PLANES = 4      # include/titanet_b200.h TN_WS_PLANES: tf32 hi | tf32 lo | bf16 correction rows | scaled-fp16 correction rows
 
 
 def _tc_ok(R: int, Kd: int, M: int, K: int) -> bool:
@@ -216,14 +217,14 @@ class SplitCache:
         dev = self.weights[0].device
         self.ptrs = [w.data_ptr() for w in self.weights]
         jobs, self.views, off = [], {}, 0
-        total = sum(6 * w.numel() for w in self.weights)
+        total = sum(2 * WS_PLANES * w.numel() for w in self.weights)
         self.buf = torch.empty(total, device=dev, dtype=torch.float32)
         for i, w in enumerate(self.weights):
             Co, Ci = w.shape[0], w.shape[1]
             n = Co * Ci
-            fwd = self.buf[off:off + 3 * n].view(3, Co, Ci)
-            bwd = self.buf[off + 3 * n:off + 6 * n].view(3, Ci, Co)
-            off += 6 * n
+            fwd = self.buf[off:off + WS_PLANES * n].view(WS_PLANES, Co, Ci)
+            bwd = self.buf[off + WS_PLANES * n:off + 2 * WS_PLANES * n].view(WS_PLANES, Ci, Co)
+            off += 2 * WS_PLANES * n
             jobs.append(TnSplitJob(w.data_ptr(), fwd.data_ptr(), Co, Ci, 0, 0))
             jobs.append(TnSplitJob(w.data_ptr(), bwd.data_ptr(), Ci, Co, 1, 0))
             self.views[id(w)] = (i, fwd, bwd)
@@ -257,7 +258,7 @@ _SPLITS = weakref.WeakValueDictionary()
 
 
 def cached_splits(w: Tensor):
-    """(ws_fwd [3, Co, Ci], ws_dgrad [3, Ci, Co]) of a weight refreshed this step, else None."""
+    """(ws_fwd [WS_PLANES, Co, Ci], ws_dgrad [WS_PLANES, Ci, Co]) of a weight refreshed this step, else None."""
     cache = _SPLITS.get(id(w))
     return cache.lookup(w) if cache is not None else None
 
@@ -269,7 +270,7 @@ def make_bn_fold(gamma, beta, rm, rv, nbt, momentum, eps, n, scale, shift, mean,
 
 def _gemm_tc(x, w2, bias, z, stats, R, Kd, M, transpose, flags, nsplit, tag, ws=None, bn=None):
     if ws is None:
-        ws = torch.empty((3, M, Kd), device=x.device, dtype=torch.float32)
+        ws = torch.empty((WS_PLANES, M, Kd), device=x.device, dtype=torch.float32)
         call("tn_split_tf32", ptr(w2), ptr(ws), M, Kd, int(transpose))
     sc, keep = scratch(x) if stats is not None else (None, None)
     scp = ctypes.byref(sc) if sc is not None else None
@@ -449,7 +450,7 @@ class ConvGemmBN(Function):
             bnb, g, db, dgamma, dbeta, keep = _make_bn_bwd(_c(dz), z, dscale, dshift, fold, gamma, n, bias, Co)
             ws = ctx.ws_t
             if ws is None:
-                ws = torch.empty((3, Ci, Co), device=x.device, dtype=torch.float32)
+                ws = torch.empty((WS_PLANES, Ci, Co), device=x.device, dtype=torch.float32)
                 call("tn_split_tf32", ptr(w3), ptr(ws), Ci, Co, 1)
             dx = empty((R, Ci), x)
             call("tn_gemm_tc_bnbwd", ptr(_c(dz)), ptr(ws), ctypes.byref(bnb), ptr(dx), R, Co, Ci, 0, tag=f"bnbwd+dgrad R{R} Ci{Co} Co{Ci} K1")
@@ -620,6 +621,43 @@ class Act(Function):
         return dz, dscale, dshift, None, None, None, None
 
 
+class Act2(Function):
+    """``Act`` for an activation with TWO consumers (the epilog output feeds the attention MLP and the pooling,
+    src/models.py:564-584): returns the materialised tensor twice (two aliases of one buffer), so that each consumer's
+    gradient arrives on its own and ``tn_act_bwd2`` adds them while loading -- autograd's sum of the two [R, C]
+    gradients (read 2, write 1) never runs."""
+
+    @staticmethod
+    def forward(ctx, z, scale, shift, seed, relu: bool, p: float, layer: int):
+        z, scale, shift = _c(z), _c(scale), _c(shift)
+        R, C = z.shape
+        y = empty(z.shape, z)
+        if p > 0 and seed is None:
+            raise ValueError("dropout needs a seed tensor")
+        call("tn_act_fwd", ptr(z), ptr(y), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed), int(layer), R, C)
+        ctx.save_for_backward(z, scale, shift, seed)
+        ctx.meta = (relu, p, layer)
+        ctx.set_materialize_grads(False)
+        return y, y.detach()
+
+    @staticmethod
+    def backward(ctx, dy1, dy2):
+        z, scale, shift, seed = ctx.saved_tensors
+        relu, p, layer = ctx.meta
+        R, C = z.shape
+        if dy1 is None:
+            dy1, dy2 = dy2, None
+        if dy1 is None:
+            return None, None, None, None, None, None, None
+        dy1 = _c(dy1)
+        dy2 = _c(dy2) if dy2 is not None else None
+        dz = empty(z.shape, z)
+        dscale, dshift = zeros((C,), z), zeros((C,), z)
+        call("tn_act_bwd2", ptr(dy1), ptr(dy2), ptr(z), ptr(dz), ptr(dscale), ptr(dshift), ptr(scale), ptr(shift), int(relu),
+             float(p), ptr(seed), int(layer), R, C)
+        return dz, dscale, dshift, None, None, None, None
+
+
 class Depthwise(Function):
     """u = depthwise_K(act(z)) + bias; act = identity when scale is None."""
 
@@ -684,7 +722,7 @@ def _dw_pw_forward(z, scale, shift, dw_w, dw_b, pw_w, pw_b, seed, relu, p, layer
     if (TC_FUSE_DWFWD and TC_FWD_NSPLIT == 3 and _tc_ok(R, C, Co, pw3.shape[2]) and K % 2 == 1 and K <= 7 and (R + 16) * C < 2 ** 32):
         ws = sp[0] if sp else None
         if ws is None:
-            ws = torch.empty((3, Co, C), device=z.device, dtype=torch.float32)
+            ws = torch.empty((WS_PLANES, Co, C), device=z.device, dtype=torch.float32)
             call("tn_split_tf32", ptr(pw3), ptr(ws), Co, C, 0)
         sc, keep = scratch(z) if stats is not None else (None, None)
         call("tn_gemm_tc_dwfwd", ptr(z), ptr(ws), ptr(dw_w), ptr(dw_b), ptr(scale), ptr(shift), int(relu), float(p), ptr(seed),
@@ -749,7 +787,7 @@ def _dwpw_dgrad(dz, pw3, ws_t, z, scale, shift, dw_w, dw_b, seed, relu, p, layer
     if _dwbwd_tc_ok(R, Co, C, K):
         ws = ws_t
         if ws is None:
-            ws = torch.empty((3, C, Co), device=z.device, dtype=torch.float32)
+            ws = torch.empty((WS_PLANES, C, Co), device=z.device, dtype=torch.float32)
             call("tn_split_tf32", ptr(pw3), ptr(ws), C, Co, 1)
         if bnb is not None:
             call("tn_gemm_tc_dwbwd_bn", ptr(dz), ptr(ws), ctypes.byref(bnb), ptr(z), ptr(dzp), ptr(dw_w), ptr(ddw), ptr(ddb), ptr(dscale),

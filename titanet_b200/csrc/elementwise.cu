@@ -166,48 +166,94 @@ extern "C" int tn_conv_weight_gemm(const float* src, float* dst, int Co, int Ci,
 // ---------------------------------------------------------------------------
 // materialise a lazy activation / its backward
 // ---------------------------------------------------------------------------
+// Slab tiling of the streaming [R, C] kernels below.  blockIdx.y owns a slab of up to 64 channel quads (256 channels = 1 KB
+// per row), the block's 256 threads are `nq` quads x `lanes` row lanes, blockIdx.x owns a contiguous range of rows that each
+// thread walks FOUR rows at a time: four independent 16-byte loads per input tensor are in flight per thread (the first
+// version walked one row per iteration with one load in flight, and a [R, 1536] tensor was one 256-thread pass and a
+// half-empty second one per row: 2.3 - 2.7 TB/s; a [64, 3072] tensor ran on two blocks).
+struct TnSlab {
+  TnTile tl;
+  int q;          // this thread's absolute channel quad
+  int r0, r1;     // the block's rows
+};
+__device__ __forceinline__ TnSlab tn_slab(int R, int C, int rpb) {
+  TnSlab s;
+  const int Q = C >> 2, q_lo = (int)blockIdx.y * 64, nq = min(64, Q - q_lo);
+  s.tl.Q = Q; s.tl.qpb = nq; s.tl.lanes = TN_EW_THREADS / nq;
+  s.tl.q0 = (int)threadIdx.x % nq; s.tl.lane = (int)threadIdx.x / nq; s.tl.active = s.tl.lane < s.tl.lanes;
+  s.q = q_lo + s.tl.q0;
+  s.r0 = (int)blockIdx.x * rpb; s.r1 = min(R, s.r0 + rpb);
+  return s;
+}
+// rows per block for a slab-tiled kernel: `blocks_per_sm` blocks per SM over all slabs, at least 8 rows each
+static int slab_rows_per_block(long long R, int C, int blocks_per_sm) {
+  const int slabs = tn_cdiv(C >> 2, 64);
+  long long row_blocks = ((long long)tn_num_sms() * blocks_per_sm + slabs - 1) / slabs;
+  if (row_blocks < 1) row_blocks = 1;
+  long long rpb = (R + row_blocks - 1) / row_blocks;
+  if (rpb < 8) rpb = 8;
+  return (int)rpb;
+}
+
 __global__ void __launch_bounds__(TN_EW_THREADS) act_fwd_kernel(const float* __restrict__ z, float* __restrict__ y,
                                                                 TnAct act, int R, int C, int rpb) {
   tn_grid_dep_sync();
   act = tn_act_init(act);
-  TnTile tl = tn_tile(C);
-  int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
-  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
-    int q = qb + tl.q0;
-    if (!tl.active || q >= tl.Q) continue;
-    for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
-      size_t off = (size_t)r * C + 4 * q;
-      tn_st4(y + off, tn_act4(act, tn_ld4(z + off), 4 * q, off >> 2, nullptr));
-    }
+  const TnSlab sl = tn_slab(R, C, rpb);
+  if (!sl.tl.active) return;
+  const int step = sl.tl.lanes;
+  for (int r = sl.r0 + sl.tl.lane; r < sl.r1; r += 4 * step) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (r + k * step < sl.r1) v[k] = tn_ld4(z + (size_t)(r + k * step) * C + 4 * sl.q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (r + k * step < sl.r1) {
+        const size_t off = (size_t)(r + k * step) * C + 4 * sl.q;
+        tn_st4(y + off, tn_act4(act, v[k], 4 * sl.q, off >> 2, nullptr));
+      }
   }
 }
 
-__global__ void __launch_bounds__(TN_EW_THREADS) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+// dy2 (optional): a second gradient of the same activation (two consumers), added on load -- replaces autograd's add kernel
+__global__ void __launch_bounds__(TN_EW_THREADS) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2,
+                                                                const float* __restrict__ z,
                                                                 float* __restrict__ dz, float* __restrict__ dscale,
                                                                 float* __restrict__ dshift, TnAct act, int R, int C, int rpb) {
   tn_grid_dep_sync();
   act = tn_act_init(act);
   __shared__ float4 red[TN_EW_THREADS];
-  TnTile tl = tn_tile(C);
-  int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
-  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
-    int q = qb + tl.q0;
-    float4 a_sc = tn_zero4(), a_sh = tn_zero4();
-    if (tl.active && q < tl.Q) {
-      const float4 sc = tn_ld4(act.scale + 4 * q);
-      for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
-        size_t off = (size_t)r * C + 4 * q;
-        float4 zz = tn_ld4(z + off), m;
-        tn_act4(act, zz, 4 * q, off >> 2, &m);
-        float4 g = tn_ld4(dy + off) * m;
-        a_sc = tn_fma4(g, zz, a_sc);
-        a_sh = a_sh + g;
-        tn_st4(dz + off, g * sc);
-      }
+  const TnSlab sl = tn_slab(R, C, rpb);
+  float4 a_sc = tn_zero4(), a_sh = tn_zero4();
+  if (sl.tl.active) {
+    const float4 sc = tn_ld4(act.scale + 4 * sl.q);
+    const int step = sl.tl.lanes;
+    for (int r = sl.r0 + sl.tl.lane; r < sl.r1; r += 4 * step) {
+      float4 zz[4], g[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (r + k * step < sl.r1) {
+          const size_t off = (size_t)(r + k * step) * C + 4 * sl.q;
+          zz[k] = tn_ld4(z + off);
+          g[k] = tn_ld4(dy + off);
+          if (dy2) g[k] = g[k] + tn_ld4(dy2 + off);
+        }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (r + k * step < sl.r1) {
+          const size_t off = (size_t)(r + k * step) * C + 4 * sl.q;
+          float4 m;
+          tn_act4(act, zz[k], 4 * sl.q, off >> 2, &m);
+          const float4 gm = g[k] * m;
+          a_sc = tn_fma4(gm, zz[k], a_sc);
+          a_sh = a_sh + gm;
+          tn_st4(dz + off, gm * sc);
+        }
     }
-    tn_lane_reduce_atomic(tl, a_sc, q, dscale, red);
-    tn_lane_reduce_atomic(tl, a_sh, q, dshift, red);
   }
+  tn_lane_reduce_atomic(sl.tl, a_sc, sl.q, dscale, red);
+  tn_lane_reduce_atomic(sl.tl, a_sh, sl.q, dshift, red);
 }
 
 extern "C" int tn_act_fwd(const float* z, float* y, const float* scale, const float* shift, int relu, float drop_p,
@@ -215,23 +261,32 @@ extern "C" int tn_act_fwd(const float* z, float* y, const float* scale, const fl
   TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0, "act_fwd: need C %% 4 == 0 (R=%d C=%d)", R, C);
   TN_REQUIRE(scale && shift, "act_fwd: scale/shift are required");
   TN_REQUIRE(tn_aligned16(z) && tn_aligned16(y) && tn_aligned16(scale) && tn_aligned16(shift), "act_fwd: pointers must be 16B aligned");
-  int rpb = rows_per_block(R);
-  tn_launch(act_fwd_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, z, y, tn_make_act(scale, shift, relu, drop_p, seed, layer), R, C, rpb);
+  const int rpb = slab_rows_per_block(R, C, 8);
+  tn_launch(act_fwd_kernel, dim3(tn_cdiv(R, rpb), tn_cdiv(C >> 2, 64)), TN_EW_THREADS, 0, stream, z, y,
+            tn_make_act(scale, shift, relu, drop_p, seed, layer), R, C, rpb);
   TN_LAUNCH_CHECK("act_fwd_kernel");
   return TN_OK;
 }
 
-// dz = dy * act'(z) * scale ; dscale += sum dy*act'*z ; dshift += sum dy*act'   (accumulating)
+// dz = (dy + dy2) * act'(z) * scale ; dscale += sum (dy + dy2)*act'*z ; dshift += sum (dy + dy2)*act'   (accumulating)
+extern "C" int tn_act_bwd2(const float* dy, const float* dy2, const float* z, float* dz, float* dscale, float* dshift,
+                           const float* scale, const float* shift, int relu, float drop_p, const unsigned long long* seed,
+                           unsigned int layer, int R, int C, void* stream) {
+  TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0, "act_bwd: need C %% 4 == 0 (R=%d C=%d)", R, C);
+  TN_REQUIRE(scale && shift && dscale && dshift, "act_bwd: scale/shift/dscale/dshift are required");
+  TN_REQUIRE(tn_aligned16(z) && tn_aligned16(dy) && tn_aligned16(dy2) && tn_aligned16(dz) && tn_aligned16(scale) && tn_aligned16(shift),
+             "act_bwd: pointers must be 16B aligned");
+  // every block ends in two atomics per channel and same-address atomics serialise in L2: few, fat blocks (4 per SM over all slabs)
+  const int rpb = slab_rows_per_block(R, C, 4);
+  tn_launch(act_bwd_kernel, dim3(tn_cdiv(R, rpb), tn_cdiv(C >> 2, 64)), TN_EW_THREADS, 0, stream, dy, dy2, z, dz, dscale, dshift,
+            tn_make_act(scale, shift, relu, drop_p, seed, layer), R, C, rpb);
+  TN_LAUNCH_CHECK("act_bwd_kernel");
+  return TN_OK;
+}
 extern "C" int tn_act_bwd(const float* dy, const float* z, float* dz, float* dscale, float* dshift, const float* scale,
                           const float* shift, int relu, float drop_p, const unsigned long long* seed, unsigned int layer, int R,
                           int C, void* stream) {
-  TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0, "act_bwd: need C %% 4 == 0 (R=%d C=%d)", R, C);
-  TN_REQUIRE(scale && shift && dscale && dshift, "act_bwd: scale/shift/dscale/dshift are required");
-  TN_REQUIRE(tn_aligned16(z) && tn_aligned16(dy) && tn_aligned16(dz) && tn_aligned16(scale) && tn_aligned16(shift), "act_bwd: pointers must be 16B aligned");
-  int rpb = rows_per_block(R);
-  tn_launch(act_bwd_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, dy, z, dz, dscale, dshift, tn_make_act(scale, shift, relu, drop_p, seed, layer), R, C, rpb);
-  TN_LAUNCH_CHECK("act_bwd_kernel");
-  return TN_OK;
+  return tn_act_bwd2(dy, nullptr, z, dz, dscale, dshift, scale, shift, relu, drop_p, seed, layer, R, C, stream);
 }
 
 // ---------------------------------------------------------------------------
@@ -279,20 +334,23 @@ extern "C" int tn_colstats(const float* x, double* stats, int R, int C, void* st
 __global__ void __launch_bounds__(TN_EW_THREADS) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int R, int C, int rpb) {
   tn_grid_dep_sync();
   __shared__ float4 red[TN_EW_THREADS];
-  TnTile tl = tn_tile(C);
-  int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
-  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
-    int q = qb + tl.q0;
-    float4 s1 = tn_zero4();
-    if (tl.active && q < tl.Q)
-      for (int r = r0 + tl.lane; r < r1; r += tl.lanes) s1 = s1 + tn_ld4(x + (size_t)r * C + 4 * q);
-    tn_lane_reduce_atomic(tl, s1, q, out, red);
+  const TnSlab sl = tn_slab(R, C, rpb);
+  float4 s1 = tn_zero4();
+  if (sl.tl.active) {
+    const int step = sl.tl.lanes;
+    for (int r = sl.r0 + sl.tl.lane; r < sl.r1; r += 4 * step) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = (r + k * step < sl.r1) ? tn_ld4(x + (size_t)(r + k * step) * C + 4 * sl.q) : tn_zero4();
+      s1 = s1 + ((v[0] + v[1]) + (v[2] + v[3]));
+    }
   }
+  tn_lane_reduce_atomic(sl.tl, s1, sl.q, out, red);
 }
 extern "C" int tn_colsum(const float* x, float* out, int R, int C, void* stream) {
   TN_REQUIRE(R > 0 && C > 0 && C % 4 == 0 && tn_aligned16(x) && out, "colsum: need C %% 4 == 0 and aligned x (R=%d C=%d)", R, C);
-  int rpb = rows_per_block(R);
-  tn_launch(colsum_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, x, out, R, C, rpb);
+  const int rpb = slab_rows_per_block(R, C, 4);
+  tn_launch(colsum_kernel, dim3(tn_cdiv(R, rpb), tn_cdiv(C >> 2, 64)), TN_EW_THREADS, 0, stream, x, out, R, C, rpb);
   TN_LAUNCH_CHECK("colsum_kernel");
   return TN_OK;
 }

@@ -182,6 +182,175 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------
+// Skinny linear layers (few rows): the decoder's Linear(2D, E) on [B, 3072], the loss heads' Linear(E, classes) and their
+// data gradients (src/models.py:510-513, src/losses.py:30, 70).  conv_gemm_kernel above walks the reduction 16 scalars at a
+// time with one global round trip exposed per chunk (45 us for [64, 3072] x [3072, 192]: latency, not work).  Here a block
+// owns 64 rows x 32 output channels x a slice of the reduction; chunks of 32 reduction elements are fetched with 16-byte
+// loads one chunk AHEAD of the arithmetic (registers), and a thread owns 8 rows x 1 channel.  Split-K partial tiles are
+// added by the last block of a tile in split order (ticket), so the result does not depend on the order the blocks ran in.
+//   Z[r, n] = bias[n] + sum_k X[r, k] Wt(k, n);   TRANS = 0: W is [N, KK] (forward), TRANS = 1: W is [KK, N] (data gradient)
+// ---------------------------------------------------------------------------
+#define SK_ROWS 64
+#define SK_COLS 32
+#define SK_KC 32
+template <int TRANS, int VEC>
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restrict__ X, const float* __restrict__ W,
+                                                          const float* __restrict__ bias, float* __restrict__ Z, int R, int KK, int N,
+                                                          int k_per_split, float* __restrict__ parts, unsigned int* __restrict__ tickets) {
+  tn_grid_dep_sync();
+  __shared__ __align__(16) float Xs[SK_KC][SK_ROWS + 4];     // [k][row]
+  __shared__ __align__(16) float Ws[SK_KC][SK_COLS + 4];     // [k][n]
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * SK_COLS, r0 = blockIdx.z * SK_ROWS;
+  const int k_begin = blockIdx.y * k_per_split, k_end = min(KK, k_begin + k_per_split);
+  const int tx = tid & 31, ty = tid >> 5;                    // this thread: channel n0 + tx, rows r0 + 8 ty .. + 7
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  // loader roles.  X chunk: 64 rows x 8 quads -> two quads per thread; W chunk: 32 x 8 quads -> one per thread
+  const int xr = tid >> 3, xq = tid & 7;                     // rows xr and xr + 32, reduction quad xq
+  const int wa = tid >> 3, wq = tid & 7;                     // TRANS 0: channel wa, reduction quad wq; TRANS 1: reduction row wa, channel quad wq
+  float4 xv[2], wv;
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = r0 + xr + 32 * h, k = k0 + 4 * xq;
+      float4 v = tn_zero4();
+      if (r < R) {
+        const float* src = X + (size_t)r * KK + k;
+        if (VEC && k + 3 < k_end) v = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          if (k < k_end) v.x = __ldg(src);
+          if (k + 1 < k_end) v.y = __ldg(src + 1);
+          if (k + 2 < k_end) v.z = __ldg(src + 2);
+          if (k + 3 < k_end) v.w = __ldg(src + 3);
+        }
+      }
+      xv[h] = v;
+    }
+    float4 v = tn_zero4();
+    if (TRANS == 0) {
+      const int n = n0 + wa, k = k0 + 4 * wq;
+      if (n < N) {
+        const float* src = W + (size_t)n * KK + k;
+        if (VEC && k + 3 < k_end) v = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          if (k < k_end) v.x = __ldg(src);
+          if (k + 1 < k_end) v.y = __ldg(src + 1);
+          if (k + 2 < k_end) v.z = __ldg(src + 2);
+          if (k + 3 < k_end) v.w = __ldg(src + 3);
+        }
+      }
+    } else {
+      const int k = k0 + wa, n = n0 + 4 * wq;
+      if (k < k_end) {
+        const float* src = W + (size_t)k * N + n;
+        if (VEC && n + 3 < N) v = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          if (n < N) v.x = __ldg(src);
+          if (n + 1 < N) v.y = __ldg(src + 1);
+          if (n + 2 < N) v.z = __ldg(src + 2);
+          if (n + 3 < N) v.w = __ldg(src + 3);
+        }
+      }
+    }
+    wv = v;
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = xr + 32 * h;
+      Xs[4 * xq + 0][m] = xv[h].x; Xs[4 * xq + 1][m] = xv[h].y; Xs[4 * xq + 2][m] = xv[h].z; Xs[4 * xq + 3][m] = xv[h].w;
+    }
+    if (TRANS == 0) {
+      Ws[4 * wq + 0][wa] = wv.x; Ws[4 * wq + 1][wa] = wv.y; Ws[4 * wq + 2][wa] = wv.z; Ws[4 * wq + 3][wa] = wv.w;
+    } else {
+      *reinterpret_cast<float4*>(&Ws[wa][4 * wq]) = wv;
+    }
+  };
+  if (k_begin < k_end) fetch(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += SK_KC) {
+    stage();
+    __syncthreads();
+    if (k0 + SK_KC < k_end) fetch(k0 + SK_KC);               // next chunk in flight while this one is multiplied
+#pragma unroll
+    for (int k = 0; k < SK_KC; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&Xs[k][8 * ty]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&Xs[k][8 * ty + 4]);
+      const float b = Ws[k][tx];
+      acc[0] = fmaf(a0.x, b, acc[0]); acc[1] = fmaf(a0.y, b, acc[1]); acc[2] = fmaf(a0.z, b, acc[2]); acc[3] = fmaf(a0.w, b, acc[3]);
+      acc[4] = fmaf(a1.x, b, acc[4]); acc[5] = fmaf(a1.y, b, acc[5]); acc[6] = fmaf(a1.z, b, acc[6]); acc[7] = fmaf(a1.w, b, acc[7]);
+    }
+    __syncthreads();
+  }
+  const int n = n0 + tx;
+  const float bv = (bias && n < N) ? __ldg(bias + n) : 0.f;
+  if (gridDim.y == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + 8 * ty + i;
+      if (r < R && n < N) Z[(size_t)r * N + n] = acc[i] + bv;
+    }
+    return;
+  }
+  float* mine = parts + (size_t)blockIdx.y * R * N;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + 8 * ty + i;
+    if (r < R && n < N) mine[(size_t)r * N + n] = acc[i];
+  }
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int* tk = tickets + blockIdx.z * gridDim.x + blockIdx.x;
+    const unsigned int t = atomicAdd(tk, 1u);
+    s_last = (t == gridDim.y - 1) ? 1u : 0u;
+    if (s_last) *tk = 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // the last block of the tile adds the partial tiles in split order; eight splits' loads are issued before their additions
+  const int nz = (int)gridDim.y;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = bv;
+  for (int z0 = 0; z0 < nz; z0 += 4) {
+    float pv[4][8];
+#pragma unroll
+    for (int zz = 0; zz < 4; ++zz)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 8 * ty + i;
+        pv[zz][i] = (z0 + zz < nz && r < R && n < N) ? __ldcg(parts + ((size_t)(z0 + zz) * R + r) * N + n) : 0.f;
+      }
+#pragma unroll
+    for (int zz = 0; zz < 4; ++zz)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += pv[zz][i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + 8 * ty + i;
+    if (r < R && n < N) Z[(size_t)r * N + n] = v[i];
+  }
+}
+
+// the skinny kernel takes 1-tap layers with few rows and a plain epilogue (statistics, if wanted, come from tn_colstats)
+static bool skinny_ok(long long R, int K, int flags) { return K == 1 && R <= 512 && flags == 0; }
+static void skinny_plan(long long R, int KK, int N, int* splits_out, int* kps_out) {
+  const long long tiles = (long long)tn_cdiv(N, SK_COLS) * tn_cdiv(R, SK_ROWS);
+  int splits = (int)((2ll * tn_num_sms() + tiles - 1) / tiles);
+  if (splits > KK / (4 * SK_KC)) splits = KK / (4 * SK_KC);          // at least four chunks per split
+  if (tiles > TN_TICKETS) splits = 1;
+  if (splits < 1) splits = 1;
+  int kps = ((KK + splits - 1) / splits + SK_KC - 1) / SK_KC * SK_KC;
+  *splits_out = (KK + kps - 1) / kps;
+  *kps_out = kps;
+}
+
 // dW[co, ci, k] += sum_r dZ[r, co] * X[r + k - pad, ci]; rows split over blockIdx.z
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ dZ, const float* __restrict__ X,
                                                          float* __restrict__ dW, float* __restrict__ dbias, int R, int T,
@@ -275,7 +444,8 @@ extern "C" long long tn_conv_gemm_simt_scratch_floats(int B, int T, int Ci, int 
   if (B <= 0 || T <= 0 || Ci <= 0 || Co <= 0 || K <= 0) return 0;
   const long long R = (long long)B * T;
   int splits, kps;
-  conv_gemm_plan(R, Ci, Co, K, flags, &splits, &kps);
+  if (skinny_ok(R, K, flags)) skinny_plan(R, Ci, Co, &splits, &kps);
+  else conv_gemm_plan(R, Ci, Co, K, flags, &splits, &kps);
   return splits > 1 ? (long long)splits * R * Co : 0;
 }
 
@@ -287,12 +457,36 @@ static int conv_gemm_launch(const float* X, const float* W, const float* bias, f
   TN_REQUIRE(R < (1ll << 31) && tn_cdiv(Co, GN) <= 65535, "conv_gemm: shape too large");
   dim3 grid(tn_cdiv(R, GM), tn_cdiv(Co, GN));
   int splits, kps;
-  conv_gemm_plan(R, Ci, Co, K, flags, &splits, &kps);
+  const bool skinny = skinny_ok(R, K, flags);
+  if (skinny) skinny_plan(R, Ci, Co, &splits, &kps);
+  else conv_gemm_plan(R, Ci, Co, K, flags, &splits, &kps);
   grid.z = splits;
   const long long need = tn_conv_gemm_simt_scratch_floats(B, T, Ci, Co, K, flags);
   if (need > 0)
     TN_REQUIRE(scratch && scratch->parts && scratch->tickets && scratch->parts_floats >= need,
                "conv_gemm: split-K needs a tn_scratch with %lld floats (tn_conv_gemm_simt_scratch_floats) and the ticket array", need);
+  if (skinny) {
+    // X rows are Ci floats apart, W rows Ci (forward) or Co (data gradient): 16-byte loads need those multiples of 4
+    const bool vec = (Ci % 4 == 0) && (transpose_w ? Co % 4 == 0 : true) && tn_aligned16(X) && tn_aligned16(W);
+    dim3 g(tn_cdiv(Co, SK_COLS), splits, tn_cdiv(R, SK_ROWS));
+    float* parts = scratch ? scratch->parts : (float*)nullptr;
+    unsigned int* tickets = scratch ? scratch->tickets : (unsigned int*)nullptr;
+    if (transpose_w) {
+      if (vec) tn_launch(skinny_gemm_kernel<1, 1>, g, 256, 0, stream, X, W, bias, Z, (int)R, Ci, Co, kps, parts, tickets);
+      else tn_launch(skinny_gemm_kernel<1, 0>, g, 256, 0, stream, X, W, bias, Z, (int)R, Ci, Co, kps, parts, tickets);
+    } else {
+      if (vec) tn_launch(skinny_gemm_kernel<0, 1>, g, 256, 0, stream, X, W, bias, Z, (int)R, Ci, Co, kps, parts, tickets);
+      else tn_launch(skinny_gemm_kernel<0, 0>, g, 256, 0, stream, X, W, bias, Z, (int)R, Ci, Co, kps, parts, tickets);
+    }
+    TN_LAUNCH_CHECK("skinny_gemm_kernel");
+    if (stats) {
+      int rc = tn_colstats(Z, stats, (int)R, Co, stream);
+      if (rc != TN_OK) return rc;
+      if (bn) return tn_bn_finalize(stats, bn->n, bn->gamma, bn->beta, bn->running_mean, bn->running_var, bn->num_batches_tracked,
+                                    bn->momentum, bn->eps, 1, bn->scale, bn->shift, bn->mean, bn->invstd, Co, stream);
+    }
+    return TN_OK;
+  }
   if (stats && splits == 1) {
     TN_REQUIRE(scratch && scratch->accum && scratch->tickets && scratch->accum_words >= TN_ACCUM_WORDS(Co),
                "conv_gemm: statistics need a tn_scratch with TN_ACCUM_WORDS(Co) zeroed accumulator words and the ticket array");

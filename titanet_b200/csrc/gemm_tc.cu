@@ -149,15 +149,42 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float first, float second) {
   const __nv_bfloat162 t = __floats2bfloat162_rn(first, second);      // .x (low half, lower address) = first
   return *reinterpret_cast<const uint32_t*>(&t);
 }
+// Forward GEMMs (p.corr = 2): the correction operands are fp16 with exponent-balanced scales,
+//   (xl * 16) . (wh / 16)  and  (xh / 256) . (wl * 256)         (TC_F16_SA = 16, TC_F16_SC = 256: powers of two, exact)
+// fp16 carries 11 significand bits, so each correction product is good to 2^-12 of itself = 2^-24 of the result: the operand
+// rounding of this scheme equals 3xTF32's (7.6e-8 rms, tools/split_precision.py) at two tensor-pipe issues per 32 bytes of K
+// instead of three.  The scales keep all four operands in fp16's normal range for activations of typical magnitude
+// 2^-6 .. 2^20 and weights 2^-10 .. 2^16 (smaller values lose relative, not absolute, precision; conversions saturate, so
+// the worst case is the plain-TF32 product, never an infinity).  Gradient GEMMs stay on bf16 (p.corr = 1): gradients of
+// magnitude 1e-8 are below fp16's range.
+#define TC_F16_SA 16.0f
+#define TC_F16_SC 256.0f
+__device__ __forceinline__ uint32_t pack_f16x2(float first, float second) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first));   // d.lo = second operand
+  return r;
+}
 // v = four consecutive K elements (logical 16-byte fp32 chunk c = 0..7) of row `row` of a [rows x 32 fp32] SWIZZLE_128B
-// tile, h = their tf32 parts: write bf16(v - h) to K' = 4c.. and bf16(h) to K' = 32 + 4c.. of the bf16 tile at lo_base
-__device__ __forceinline__ void tc_store_corr(uint8_t* lo_base, uint32_t row, uint32_t c, float4 v, uint4 h) {
+// tile, h = their tf32 parts: write the 16-bit (v - h) to K' = 4c.. and the 16-bit h to K' = 32 + 4c.. of the tile at lo_base
+// (F16 = false: bf16, unscaled; F16 = true: fp16, scaled as above)
+template <bool F16>
+__device__ __forceinline__ void tc_store_corr_t(uint8_t* lo_base, uint32_t row, uint32_t c, float4 v, uint4 h) {
   const float hx = __uint_as_float(h.x), hy = __uint_as_float(h.y), hz = __uint_as_float(h.z), hw = __uint_as_float(h.w);
-  const uint2 plo = make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
-  const uint2 phi = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
+  uint2 plo, phi;
+  if (F16) {
+    plo = make_uint2(pack_f16x2((v.x - hx) * TC_F16_SA, (v.y - hy) * TC_F16_SA), pack_f16x2((v.z - hz) * TC_F16_SA, (v.w - hw) * TC_F16_SA));
+    phi = make_uint2(pack_f16x2(hx * (1.f / TC_F16_SC), hy * (1.f / TC_F16_SC)), pack_f16x2(hz * (1.f / TC_F16_SC), hw * (1.f / TC_F16_SC)));
+  } else {
+    plo = make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
+    phi = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
+  }
   uint8_t* r = lo_base + row * 128u + ((c & 1u) << 3);
   *reinterpret_cast<uint2*>(r + ((((c >> 1)) ^ (row & 7u)) << 4)) = plo;
   *reinterpret_cast<uint2*>(r + (((4u + (c >> 1)) ^ (row & 7u)) << 4)) = phi;
+}
+__device__ __forceinline__ void tc_store_corr(uint8_t* lo_base, uint32_t row, uint32_t c, float4 v, uint4 h, int corr = 1) {
+  if (corr == 2) tc_store_corr_t<true>(lo_base, row, c, v, h);
+  else tc_store_corr_t<false>(lo_base, row, c, v, h);
 }
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -165,9 +192,10 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// instruction descriptor of the bf16 correction MMA from the tf32 one: A / B format TF32 (2) -> BF16 (1)
-__device__ __forceinline__ uint32_t tc_idesc_bf16(uint32_t idesc_tf32) {
-  return (idesc_tf32 & ~((7u << 7) | (7u << 10))) | (1u << 7) | (1u << 10);
+// instruction descriptor of the 16-bit correction MMA from the tf32 one: A / B format TF32 (2) -> BF16 (1) or F16 (0)
+__device__ __forceinline__ uint32_t tc_idesc_bf16(uint32_t idesc_tf32, int corr = 1) {
+  const uint32_t fmt = corr == 2 ? 0u : 1u;
+  return (idesc_tf32 & ~((7u << 7) | (7u << 10))) | (fmt << 7) | (fmt << 10);
 }
 
 // shared-memory matrix descriptor, K-major operand tile of TC_BK fp32 per row:
@@ -260,7 +288,7 @@ struct TcParams {
   float* Z;
   double* stats;
   int R, Kd, M_total, BN, stages, nsplit, flags, tmem_cols;
-  int corr;                     // 1: TF32 + BF16-correction split (gradient GEMMs), 0: 3xTF32 (forward GEMMs)
+  int corr;                     // 2: TF32 + scaled-fp16 correction (forward GEMMs), 1: TF32 + bf16 correction (gradient GEMMs), 0: 3xTF32
   int nacc;                     // TMEM accumulators per tile (>= 1), BN columns apart: nacc - 1 K-chunked main accumulators + 1 for the corrections
   unsigned long long* accum;    // fixed-point statistics accumulators [hi 2 M_total | lo 2 M_total | flags] (tn_fix_add / tn_stats_finish)
   unsigned int* tickets;        // one per channel group, zero on entry, reset by the kernel
@@ -611,7 +639,7 @@ __device__ __forceinline__ void tc_dw_mainloop(const TcParams& p, uint8_t* smem,
           l.z = rna_tf32(acc.z - __uint_as_float(h.z)); l.w = rna_tf32(acc.w - __uint_as_float(h.w));
           const uint32_t o = (uint32_t)j * 128u + ((q ^ ((uint32_t)j & 7u)) << 4);
           *reinterpret_cast<uint4*>(bh + o) = h;
-          if (p.corr) tc_store_corr(reinterpret_cast<uint8_t*>(bl), (uint32_t)j, (uint32_t)q, acc, h);
+          if (p.corr) tc_store_corr(reinterpret_cast<uint8_t*>(bl), (uint32_t)j, (uint32_t)q, acc, h, p.corr);
           else *reinterpret_cast<uint4*>(bl + o) = l;
         }
       }
@@ -785,14 +813,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             } else if (nacc > 1) {
               tc_mma_tf32(d, dah + adv, dbh + adv, idesc, acc);
               if (p.corr) {
-                tc_mma_bf16(dc, dal + adv, dbl + adv, tc_idesc_bf16(idesc), accc);
+                tc_mma_bf16(dc, dal + adv, dbl + adv, tc_idesc_bf16(idesc, p.corr), accc);
               } else {
                 tc_mma_tf32(dc, dal + adv, dbh + adv, idesc, accc);
                 tc_mma_tf32(dc, dah + adv, dbl + adv, idesc, 1u);
               }
             } else if (p.corr) {
               tc_mma_tf32(d, dah + adv, dbh + adv, idesc, acc);
-              tc_mma_bf16(d, dal + adv, dbl + adv, tc_idesc_bf16(idesc), 1u);
+              tc_mma_bf16(d, dal + adv, dbl + adv, tc_idesc_bf16(idesc, p.corr), 1u);
             } else {
               tc_mma_tf32(d, dal + adv, dbh + adv, idesc, acc);
               tc_mma_tf32(d, dah + adv, dbl + adv, idesc, 1u);
@@ -848,7 +876,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           l.x = rna_tf32(v.x - __uint_as_float(h.x)); l.y = rna_tf32(v.y - __uint_as_float(h.y));
           l.z = rna_tf32(v.z - __uint_as_float(h.z)); l.w = rna_tf32(v.w - __uint_as_float(h.w));
           reinterpret_cast<uint4*>(hi)[i] = h;
-          if (p.corr) tc_store_corr(reinterpret_cast<uint8_t*>(lo), (uint32_t)i >> 3, ((uint32_t)i & 7u) ^ (((uint32_t)i >> 3) & 7u), v, h);
+          if (p.corr) tc_store_corr(reinterpret_cast<uint8_t*>(lo), (uint32_t)i >> 3, ((uint32_t)i & 7u) ^ (((uint32_t)i >> 3) & 7u), v, h, p.corr);
           else reinterpret_cast<uint4*>(lo)[i] = l;
         }
         fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -1075,7 +1103,7 @@ __device__ __forceinline__ void tc2_dw_mainloop(const TcParams& p, uint8_t* smem
           l.z = rna_tf32(acc.z - __uint_as_float(h.z)); l.w = rna_tf32(acc.w - __uint_as_float(h.w));
           const uint32_t o = (uint32_t)j * 128u + ((q ^ ((uint32_t)j & 7u)) << 4);
           *reinterpret_cast<uint4*>(bh + o) = h;
-          if (p.corr) tc_store_corr(reinterpret_cast<uint8_t*>(bl), (uint32_t)j, (uint32_t)q, acc, h);
+          if (p.corr) tc_store_corr(reinterpret_cast<uint8_t*>(bl), (uint32_t)j, (uint32_t)q, acc, h, p.corr);
           else *reinterpret_cast<uint4*>(bl + o) = l;
         }
       }
@@ -1259,14 +1287,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             if (nacc > 1) {
               tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, acc);
               if (p.corr) {
-                tc_mma_bf16_2sm(dc, dal + adv, dbl + adv, tc_idesc_bf16(idesc), accc);
+                tc_mma_bf16_2sm(dc, dal + adv, dbl + adv, tc_idesc_bf16(idesc, p.corr), accc);
               } else {
                 tc_mma_tf32_2sm(dc, dal + adv, dbh + adv, idesc, accc);
                 tc_mma_tf32_2sm(dc, dah + adv, dbl + adv, idesc, 1u);
               }
             } else if (p.corr) {
               tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, acc);
-              tc_mma_bf16_2sm(d, dal + adv, dbl + adv, tc_idesc_bf16(idesc), 1u);
+              tc_mma_bf16_2sm(d, dal + adv, dbl + adv, tc_idesc_bf16(idesc, p.corr), 1u);
             } else {
               tc_mma_tf32_2sm(d, dal + adv, dbh + adv, idesc, acc);
               tc_mma_tf32_2sm(d, dah + adv, dbl + adv, idesc, 1u);
@@ -1370,7 +1398,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             h.x = rna_tf32(g.x); h.y = rna_tf32(g.y); h.z = rna_tf32(g.z); h.w = rna_tf32(g.w);
             reinterpret_cast<uint4*>(hi)[i] = h;
             if (p.corr) {
-              tc_store_corr(reinterpret_cast<uint8_t*>(lo), (uint32_t)row, cq, g, h);
+              tc_store_corr(reinterpret_cast<uint8_t*>(lo), (uint32_t)row, cq, g, h, p.corr);
             } else {
               uint4 l;
               l.x = rna_tf32(g.x - __uint_as_float(h.x)); l.y = rna_tf32(g.y - __uint_as_float(h.y));
@@ -1396,7 +1424,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         l.x = rna_tf32(v.x - __uint_as_float(h.x)); l.y = rna_tf32(v.y - __uint_as_float(h.y));
         l.z = rna_tf32(v.z - __uint_as_float(h.z)); l.w = rna_tf32(v.w - __uint_as_float(h.w));
         reinterpret_cast<uint4*>(hi)[i] = h;
-        if (p.corr) tc_store_corr(reinterpret_cast<uint8_t*>(lo), (uint32_t)i >> 3, ((uint32_t)i & 7u) ^ (((uint32_t)i >> 3) & 7u), v, h);
+        if (p.corr) tc_store_corr(reinterpret_cast<uint8_t*>(lo), (uint32_t)i >> 3, ((uint32_t)i & 7u) ^ (((uint32_t)i >> 3) & 7u), v, h, p.corr);
         else reinterpret_cast<uint4*>(lo)[i] = l;
       }
       fence_proxy_async();
@@ -1490,46 +1518,52 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   }
 }
 
-// Split scheme per GEMM.  The weight split carries BOTH correction formats (ws = [3, M, Kd]: tf32 hi | tf32 lo | packed bf16
-// correction rows), so the launcher chooses per call:
-//   forward GEMMs  -> 3xTF32 (operand rounding 8e-8 rms, the same as fp32): what reaches the train-mode BatchNorms must be
-//                     fp32-equivalent (S/17 at batch 4, embeddings vs fp64 over 8 runs: 7.0e-4 .. 7.7e-4 with 3xTF32,
-//                     7.3e-4 .. 1.18e-3 with the bf16 correction, 5.8e-4 for the fp32 reference itself)
-//   gradient GEMMs -> TF32 + one bf16 correction MMA (TN_GEMM_GRAD flag / the fused depthwise backward): 6.6e-7 rms, one third
-//                     fewer tensor-pipe cycles; gradients are judged against the fp32 reference's own error (1e-2).
-// TN_TC_FWD_CORR=1 / TN_TC_BWD_CORR=0 override (A/B runs).
+// Split scheme per GEMM.  The weight split carries every format (ws = [4, M, Kd]: tf32 hi | tf32 lo | packed bf16 correction
+// rows | packed scaled-fp16 correction rows), so the launcher chooses per call:
+//   forward GEMMs  -> corr = 2: TF32 hi*hi + ONE fp16 MMA over a doubled K with exponent-balanced operand scales (operand
+//                     rounding 7.6e-8 rms = 3xTF32's = fp32 level, at two tensor-pipe issues per 32 bytes of K instead of
+//                     three).  What reaches the train-mode BatchNorms must be fp32-equivalent: S/17 at batch 4, embeddings
+//                     vs fp64 over 8 runs were 7.0e-4 .. 7.7e-4 with 3xTF32, 7.3e-4 .. 1.18e-3 with the bf16 correction
+//                     (round-1 tree), 5.8e-4 for the fp32 reference itself.  TN_TC_FWD_CORR=0 selects 3xTF32, =1 bf16.
+//   gradient GEMMs -> corr = 1: TF32 + one bf16 correction MMA (TN_GEMM_GRAD flag / the fused depthwise backward): 6.6e-7
+//                     rms; bf16 keeps fp32's exponent range, which gradients need.  TN_TC_BWD_CORR=0 / 2 override (A/B runs).
 static int tc_corr_for(bool grad) {
   static int fwd = -1, bwd = -1;
   if (fwd < 0) {
     const char* e = getenv("TN_TC_FWD_CORR");
-    fwd = (e && e[0] == '1') ? 1 : 0;
+    fwd = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
     e = getenv("TN_TC_BWD_CORR");
-    bwd = (e && e[0] == '0') ? 0 : 1;
+    bwd = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
   }
   return grad ? bwd : fwd;
 }
 
 // ---------------------------------------------------------------------------
-// weight split: ws[0] = rna_tf32(W), ws[1] = rna_tf32(W - ws[0]), ws[2] = the packed bf16 correction rows; optional transpose
+// weight split: ws[0] = rna_tf32(W), ws[1] = rna_tf32(W - ws[0]), ws[2] / ws[3] = the packed bf16 / scaled fp16 correction rows;
+// optional transpose
 // ---------------------------------------------------------------------------
 // ws[2] holds, per row and 32-element K chunk, 64 bf16 = [bf16(hi) x32 | bf16(x - hi) x32] in the 128 bytes that hold 32 tf32
 // values in the other two planes (the weight side of the bf16 correction MMA, see tc_store_corr)
-__device__ __forceinline__ void split_store(float* hi, float* lo, float* cr, size_t i, int k, float x) {
+__device__ __forceinline__ void split_store(float* hi, float* lo, float* cr, float* cf, size_t i, int k, float x) {
   const float h = __uint_as_float(rna_tf32(x));
   hi[i] = h;
   lo[i] = __uint_as_float(rna_tf32(x - h));
   __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(cr + (i - (size_t)(k & 31))) + (k & 31);
   c[0] = __float2bfloat16_rn(h);
   c[32] = __float2bfloat16_rn(x - h);
+  // ws[3]: the fp16 flavour with the weight side of the exponent-balanced scales (see TC_F16_SA / TC_F16_SC)
+  unsigned short* f = reinterpret_cast<unsigned short*>(cf + (i - (size_t)(k & 31))) + (k & 31);
+  f[0] = (unsigned short)(pack_f16x2(h * (1.f / TC_F16_SA), 0.f) & 0xffffu);
+  f[32] = (unsigned short)(pack_f16x2((x - h) * TC_F16_SC, 0.f) & 0xffffu);
 }
 __global__ void split_tf32_kernel(const float* __restrict__ W, float* __restrict__ ws, int M, int Kd, int transpose) {
   tn_grid_dep_sync();
-  // output [3, M, Kd]; input [M, Kd] or (transpose) [Kd, M]
+  // output [4, M, Kd]; input [M, Kd] or (transpose) [Kd, M]
   const size_t n = (size_t)M * Kd;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / Kd), k = (int)(i - (size_t)m * Kd);
     const float x = transpose ? W[(size_t)k * M + m] : W[i];
-    split_store(ws, ws + n, ws + 2 * n, i, k, x);
+    split_store(ws, ws + n, ws + 2 * n, ws + 3 * n, i, k, x);
   }
 }
 
@@ -1927,7 +1961,7 @@ __global__ void split_tf32_batch_kernel(const tn_split_job* __restrict__ jobs) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / j.Kd), k = (int)(i - (size_t)m * j.Kd);
     const float x = j.transpose ? j.W[(size_t)k * j.M + m] : j.W[i];
-    split_store(j.ws, j.ws + n, j.ws + 2 * n, i, k, x);
+    split_store(j.ws, j.ws + n, j.ws + 2 * n, j.ws + 3 * n, i, k, x);
   }
 }
 extern "C" int tn_split_tf32_batch(const tn_split_job* jobs_dev, int njobs, int max_elems, void* stream) {
@@ -1998,7 +2032,7 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   p.flags &= ~TN_GEMM_GRAD;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("TN_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.flags |= dbg & (2048 | 4096 | 8192 | 16384); }   // experiments only
   p.corr = tc_corr_for(grad);
-  const float* ws_lo = ws + (size_t)(p.corr ? 2 : 1) * M * Kd;
+  const float* ws_lo = ws + (size_t)(p.corr == 2 ? 3 : p.corr ? 2 : 1) * M * Kd;
   if (p.stats) {
     TN_REQUIRE(scratch && scratch->accum && scratch->tickets && scratch->accum_words >= TN_ACCUM_WORDS(M),
                "gemm_tc: statistics need a tn_scratch with TN_ACCUM_WORDS(M) zeroed accumulator words and the ticket array");

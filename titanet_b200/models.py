@@ -243,10 +243,14 @@ class AttentiveStatsPooling(nn.Module):
         self.out_linear = nn.Linear(hidden_size, input_size)
 
     def _fwd(self, enc: Lazy) -> torch.Tensor:
-        x = enc.materialise()
-        h, _ = ops.conv_gemm(x.z, self.in_linear.weight, self.in_linear.bias, x.B, x.T, tanh=True)
-        e, _ = ops.conv_gemm(h, self.out_linear.weight, self.out_linear.bias, x.B, x.T)
-        return ops.ASPPool.apply(e, x.z, x.B, x.T, float(self.eps))
+        if enc.scale is not None:
+            # the two consumers get their own alias of the materialised activation: no gradient-sum kernel (ops.Act2)
+            xa, xb = ops.Act2.apply(enc.z, enc.scale, enc.shift, enc.seed, enc.relu, enc.p, enc.layer)
+        else:
+            xa = xb = enc.z
+        h, _ = ops.conv_gemm(xa, self.in_linear.weight, self.in_linear.bias, enc.B, enc.T, tanh=True)
+        e, _ = ops.conv_gemm(h, self.out_linear.weight, self.out_linear.bias, enc.B, enc.T)
+        return ops.ASPPool.apply(e, xb, enc.B, enc.T, float(self.eps))
 
     def forward(self, encodings):
         require_cuda(encodings)

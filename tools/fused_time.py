@@ -7,7 +7,7 @@ B, T, C, Co, K = 64, 301, 256, 256, 3
 R = B * T
 g = lambda *s: torch.randn(*s, device="cuda")
 dz, z, dzp = g(R, Co), g(R, C), torch.empty(R, C, device="cuda")
-pw = g(Co, C) / 16; ws = torch.empty(3, C, Co, device="cuda"); call("tn_split_tf32", ptr(pw), ptr(ws), C, Co, 1)
+pw = g(Co, C) / 16; ws = torch.empty(4, C, Co, device="cuda"); call("tn_split_tf32", ptr(pw), ptr(ws), C, Co, 1)
 dw_w = g(C, 1, K); ddw = torch.zeros(C, K, device="cuda"); ddb, dsc, dsh = (torch.zeros(C, device="cuda") for _ in range(3))
 sc, sh = torch.rand(C, device="cuda") + 0.5, g(C) * 0.1
 seed = torch.tensor([5], dtype=torch.int64, device="cuda")

@@ -9,7 +9,7 @@ from torch.profiler import profile, ProfilerActivity
 ap = argparse.ArgumentParser()
 ap.add_argument("--model", default="s"); ap.add_argument("--blocks", type=int, default=17); ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--seconds", type=float, default=3.0); ap.add_argument("--loss", default="ce"); ap.add_argument("--dropout", type=float, default=0.1)
-ap.add_argument("--replays", type=int, default=5); ap.add_argument("--out", default="")
+ap.add_argument("--replays", type=int, default=5); ap.add_argument("--out", default=""); ap.add_argument("--timeline", default="", help="write the launch-by-launch timeline of the last replay (start us, duration us, gap to the previous kernel, name)")
 a = ap.parse_args()
 from titanet_b200 import losses, models, transforms
 from titanet_b200.engine import GraphedTrainStep
@@ -40,5 +40,16 @@ for name, (n, t) in rows:
     short = name.split("(")[0][:70]
     print(f"| `{short}` | {n / a.replays:.0f} | {t / n:.2f} | {t / a.replays:.1f} | {100 * t / tot:.1f}% |")
 print(f"\nsum of kernel time per step: {tot / a.replays / 1e3:.3f} ms over {sum(n for n, _ in agg.values()) / a.replays:.0f} launches")
+if a.timeline:
+    evs = sorted((ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA and ev.device_time > 0), key=lambda e: e.time_range.start)
+    per = len(evs) // a.replays
+    last = evs[-per:]
+    t0 = last[0].time_range.start
+    with open(a.timeline, "w") as f:
+        prev_end = t0
+        for ev in last:
+            st = ev.time_range.start
+            f.write(f"{st - t0:9.1f} {ev.device_time:8.2f} {st - prev_end:6.2f}  {ev.name.split('(')[0][:80]}\n")
+            prev_end = st + ev.device_time
 if a.out:
     json.dump({k: {"launches_per_step": n / a.replays, "us_per_launch": t / n} for k, (n, t) in rows}, open(a.out, "w"), indent=1)

@@ -7,7 +7,7 @@ from titanet_b200._ops import gemm_tc_raw
 from titanet_b200._lib import call, ptr
 R, K, M = 19264, 256, 256
 x = torch.randn(R, K, device="cuda"); w = torch.randn(M, K, device="cuda") / math.sqrt(K); b = torch.randn(M, device="cuda")
-z = torch.empty(R, M, device="cuda"); ws = torch.empty(3, M, K, device="cuda"); st = torch.zeros(2 * M, device="cuda", dtype=torch.float64)
+z = torch.empty(R, M, device="cuda"); ws = torch.empty(4, M, K, device="cuda"); st = torch.zeros(2 * M, device="cuda", dtype=torch.float64)
 dst = torch.zeros(2 * M, dtype=torch.float64, device="cuda"); y = torch.empty(R, M, device="cuda"); dw = torch.zeros(M, K, device="cuda")
 call("tn_split_tf32", ptr(w), ptr(ws), M, K, 0)
 def gemm(n=3): gemm_tc_raw(x, ws, b, z, st, R, K, M, 0, n)

@@ -10,8 +10,8 @@ R = B * T
 g = lambda *s: torch.randn(*s, device="cuda")
 x, z = g(R, C), torch.empty(R, C, device="cuda")
 w = g(C, C) / math.sqrt(C); b = g(C)
-ws = torch.empty(3, C, C, device="cuda"); call("tn_split_tf32", ptr(w), ptr(ws), C, C, 0)
-wst = torch.empty(3, C, C, device="cuda"); call("tn_split_tf32", ptr(w), ptr(wst), C, C, 1)
+ws = torch.empty(4, C, C, device="cuda"); call("tn_split_tf32", ptr(w), ptr(ws), C, C, 0)
+wst = torch.empty(4, C, C, device="cuda"); call("tn_split_tf32", ptr(w), ptr(wst), C, C, 1)
 st = torch.empty(2 * C, dtype=torch.float64, device="cuda"); fold = torch.empty(4, C, device="cuda")
 bnp = [torch.ones(C, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"), torch.zeros((), dtype=torch.int64, device="cuda")]
 bn = ops.make_bn_fold(bnp[0], bnp[1], bnp[2], bnp[3], bnp[4], 0.1, 1e-5, float(R), fold[0], fold[1], fold[2], fold[3])

@@ -11,7 +11,7 @@ ap.add_argument("--nsplit", type=int, default=3); ap.add_argument("--iters", typ
 a = ap.parse_args()
 x = torch.randn(a.R, a.K, device="cuda"); w = torch.randn(a.M, a.K, device="cuda") / math.sqrt(a.K); b = torch.randn(a.M, device="cuda")
 z = torch.empty(a.R, a.M, device="cuda"); st = torch.zeros(2 * a.M, device="cuda", dtype=torch.float64)
-ws = torch.empty(3, a.M, a.K, device="cuda")
+ws = torch.empty(4, a.M, a.K, device="cuda")
 if a.nostats: st = None
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 def run():

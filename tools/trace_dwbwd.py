@@ -11,7 +11,7 @@ P = float(os.environ.get("P", 0.1))
 R = B * T
 g = lambda *s: torch.randn(*s, device="cuda")
 dz, zo, zprev, dzp, gout = g(R, C), g(R, C), g(R, C), torch.empty(R, C, device="cuda"), torch.empty(R, C, device="cuda")
-pw = g(C, C) / math.sqrt(C); ws = torch.empty(3, C, C, device="cuda"); call("tn_split_tf32", ptr(pw), ptr(ws), C, C, 1)
+pw = g(C, C) / math.sqrt(C); ws = torch.empty(4, C, C, device="cuda"); call("tn_split_tf32", ptr(pw), ptr(ws), C, C, 1)
 dww = g(C, 1, K); ddw = torch.zeros(C, K, device="cuda"); acc = torch.zeros(4, C, device="cuda")
 sc, sh = torch.rand(C, device="cuda") + 0.5, 0.1 * g(C)
 seed = torch.tensor([1], dtype=torch.int64, device="cuda")

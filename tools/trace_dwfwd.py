@@ -9,7 +9,7 @@ P = float(os.environ.get("P", 0.1))
 R = B * T
 g = lambda *s: torch.randn(*s, device="cuda")
 z, u, zo = g(R, C), torch.empty(R, C, device="cuda"), torch.empty(R, Co, device="cuda")
-pw = g(Co, C) / 16; ws = torch.empty(3, Co, C, device="cuda"); call("tn_split_tf32", ptr(pw), ptr(ws), Co, C, 0)
+pw = g(Co, C) / 16; ws = torch.empty(4, Co, C, device="cuda"); call("tn_split_tf32", ptr(pw), ptr(ws), Co, C, 0)
 dw_w, dw_b, pw_b = g(C, 1, K), g(C), g(Co)
 sc, sh = torch.rand(C, device="cuda") + 0.5, g(C) * 0.1
 seed = torch.tensor([5], dtype=torch.int64, device="cuda")

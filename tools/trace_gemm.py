@@ -6,7 +6,7 @@ from titanet_b200._ops import gemm_tc_raw
 from titanet_b200._lib import LIB, call, ptr
 R, K, M, nsplit = (int(v) for v in (sys.argv[1:5] + ["19264", "256", "256", "3"][len(sys.argv) - 1:]))
 x = torch.randn(R, K, device="cuda"); w = torch.randn(M, K, device="cuda") / math.sqrt(K)
-z = torch.empty(R, M, device="cuda"); ws = torch.empty(3, M, K, device="cuda")
+z = torch.empty(R, M, device="cuda"); ws = torch.empty(4, M, K, device="cuda")
 tr = torch.zeros(1024, dtype=torch.int64, device="cuda")
 call("tn_split_tf32", ptr(w), ptr(ws), M, K, 0)
 for _ in range(3): gemm_tc_raw(x, ws, None, z, None, R, K, M, 0, nsplit)

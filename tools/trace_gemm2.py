@@ -6,7 +6,7 @@ from titanet_b200 import _ops as ops
 from titanet_b200._lib import LIB, call, ptr
 R, K, M = (int(v) for v in (sys.argv[1:4] + ["19264", "256", "256"][len(sys.argv) - 1:]))
 x = torch.randn(R, K, device="cuda"); w = torch.randn(M, K, device="cuda") / math.sqrt(K); b = torch.randn(M, device="cuda")
-z = torch.empty(R, M, device="cuda"); ws = torch.empty(3, M, K, device="cuda")
+z = torch.empty(R, M, device="cuda"); ws = torch.empty(4, M, K, device="cuda")
 call("tn_split_tf32", ptr(w), ptr(ws), M, K, 0)
 st = torch.empty(2 * M, dtype=torch.float64, device="cuda")
 gamma, beta, rm, rv = torch.ones(M, device="cuda"), torch.zeros(M, device="cuda"), torch.zeros(M, device="cuda"), torch.ones(M, device="cuda")
