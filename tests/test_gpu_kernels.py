@@ -54,7 +54,8 @@ def test_transpose_roundtrip(ops):
 
 
 @pytest.mark.parametrize("B,T,Ci,Co,K", [(2, 37, 80, 64, 3), (3, 50, 64, 64, 1), (2, 33, 48, 251, 1), (1, 70, 16, 96, 5),
-                                         (4, 1, 3072, 192, 1)])
+                                         (4, 1, 3072, 192, 1), (300, 1, 3072, 192, 1), (64, 1, 192, 251, 1), (70, 1, 333, 100, 1),
+                                         (1, 600, 64, 96, 1)])
 def test_conv_gemm_fwd_bwd(ops, B, T, Ci, Co, K):
     g = torch.Generator().manual_seed(1)
     x = torch.randn(B, Ci, T, generator=g, dtype=torch.float64)
