@@ -977,6 +977,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #define TC2_TRACE(slot) do { if (p.trace && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == ((gridDim.x / 2) & ~1u))) { \
     unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); \
     p.trace[(blockIdx.x == 0 ? 0 : 64) + (slot)] = (long long)gt_; } } while (0)
+// per-chunk events of CTA 0 -> slots [256, 512): 16 slots per event kind (producer issue, operand arrived, transform done, MMA waits
+// passed, MMAs issued)
+#define TC2_TRACE2(kind, kc) do { if (p.trace && blockIdx.y == 0 && blockIdx.x == 0 && (kc) < 16) { \
+    unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); \
+    p.trace[256 + 16 * (kind) + (kc)] = (long long)gt_; } } while (0)
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_leader, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1) : "memory");
@@ -1198,9 +1203,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int s = kc % S;
         if (kc >= S) mbar_wait(empty0 + 8 * s, ((kc / S) - 1) & 1);
         const int k0 = kc * TC_BK;
+        if ((p.flags & 8192) && kc >= S) {                       // TN_TC_DEBUG=8192: weight tiles only for the first S chunks (timing experiment)
+          if (leader) mbar_arrive(fullA0 + 8 * s);
+        } else {
         if (leader) mbar_expect_tx(fullA0 + 8 * s, 4 * a_tile);   // both CTAs' hi + lo weight tiles
         tma_load_2d_2sm(smem_u32(a_hi(s)), &tmA_hi, fullA_leader0 + 8 * s, k0, m0 + (int)rank * 128);
         tma_load_2d_2sm(smem_u32(a_lo(s)), &tmA_lo, fullA_leader0 + 8 * s, k0, m0 + (int)rank * 128);
+        }
         const int padr = MODE == 2 ? (p.fdw_K >> 1) : 0;           // fused depthwise forward: PAD rows of halo in front
         mbar_expect_tx(fullB0 + 8 * s, 2 * b_raw + (p.has_bnb ? 2 * b_half : 0u));
         tma_load_2d(smem_u32(b_hi(s, 0)), &tmB, fullB0 + 8 * s, k0, n0 + (int)rank * HB - padr);
@@ -1209,6 +1218,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           tma_load_2d(smem_u32(b_lo(s, 0)), &tmG, fullB0 + 8 * s, k0, n0 + (int)rank * HB);
           tma_load_2d(smem_u32(b_lo(s, 1)), &tmG, fullB0 + 8 * s, k0, n0 + BN2 + (int)rank * HB);
         }
+        TC2_TRACE2(0, kc);
       }
       if (MODE == 1) {
         // z boxes of the previous layer for the fused epilogue, group by group as the tensor core releases the stages
@@ -1267,20 +1277,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int s = kc % S;
         const uint32_t ph = (kc / S) & 1;
         mbar_wait(fullA0 + 8 * s, ph);
+        TC2_TRACE2(5, kc);
         mbar_wait(ready0 + 8 * s, ph);
+        TC2_TRACE2(6, kc);
         mbar_wait(readyP0 + 8 * s, ph);
+        TC2_TRACE2(3, kc);
         tc_fence_after();
         const uint64_t dah = umma_desc_k128(smem_u32(a_hi(s))), dal = umma_desc_k128(smem_u32(a_lo(s)));
         const int am = (kc * nmain) / num_kc;
         const bool new_main = am != prev_am;
         prev_am = am;
+        const bool inter = (p.flags & 32768) != 0;        // TN_TC_DEBUG=32768: alternate the two N tiles (independent accumulators) instead of tile after tile
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
+        for (int it = 0; it < 2 * (TC_BK / 8); ++it) {
+          const int t = inter ? (it & 1) : (it >> 2), kk = inter ? (it >> 1) : (it & 3);
           const uint64_t dbh = umma_desc_k128(smem_u32(b_hi(s, t))), dbl = umma_desc_k128(smem_u32(b_lo(s, t)));
           const uint32_t d = tmem_base + (uint32_t)(t * 256 + am * BN2);
           const uint32_t dc = tmem_base + (uint32_t)(t * 256 + (nacc - 1) * BN2);
-#pragma unroll
-          for (int kk = 0; kk < TC_BK / 8; ++kk) {
+          {
+            if (it == 1) TC2_TRACE2(7, kc);                // after the first tile-0 MMA pair was issued
             const uint64_t adv = (uint64_t)(kk * 2);
             const uint32_t acc = (new_main && kk == 0) ? 0u : 1u;
             const uint32_t accc = (kc > 0 || kk > 0) ? 1u : 0u;
@@ -1293,8 +1308,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 tc_mma_tf32_2sm(dc, dah + adv, dbl + adv, idesc, 1u);
               }
             } else if (p.corr) {
+              if (p.flags & 16384) tc_mma_bf16_2sm(d, dah + adv, dbh + adv, tc_idesc_bf16(idesc, p.corr), acc);   // TN_TC_DEBUG=16384: main product as kind::f16 on the same bytes (timing experiment, wrong numbers)
+              else
               tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, acc);
-              tc_mma_bf16_2sm(d, dal + adv, dbl + adv, tc_idesc_bf16(idesc, p.corr), 1u);
+              if (!(p.flags & 4096))                                           // TN_TC_DEBUG=4096: no correction MMA (timing experiment)
+                tc_mma_bf16_2sm(d, dal + adv, dbl + adv, tc_idesc_bf16(idesc, p.corr), 1u);
             } else {
               tc_mma_tf32_2sm(d, dal + adv, dbh + adv, idesc, acc);
               tc_mma_tf32_2sm(d, dah + adv, dbl + adv, idesc, 1u);
@@ -1302,7 +1320,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             }
           }
         }
+        TC2_TRACE2(8, kc);
         tc_commit_2sm(empty0 + 8 * s, (uint16_t)3);       // stage free in both CTAs once these MMAs have read it
+        TC2_TRACE2(4, kc);
       }
       tc_commit_2sm(accum_bar, (uint16_t)3);              // accumulators complete (both CTAs)
     } else if (!leader && lane == 0) {
@@ -1415,9 +1435,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     for (int kc = 0; kc < num_kc; ++kc) {
       const int s = kc % S;
       mbar_wait(fullB0 + 8 * s, (kc / S) & 1);
+      if (tid == 0) TC2_TRACE2(1, kc);
       float4* hi = reinterpret_cast<float4*>(b_hi(s, 0));
       float4* lo = reinterpret_cast<float4*>(b_lo(s, 0));
-      for (int i = tid; i < n4; i += 32 * EW) {
+      for (int i = tid; i < ((p.flags & 2048) ? 0 : n4); i += 32 * EW) {       // TN_TC_DEBUG=2048: no transform (timing experiment)
         const float4 v = hi[i];
         uint4 h, l;
         h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
@@ -1430,6 +1451,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(ready0 + 8 * s);                 // one arrival per warp on this CTA's barrier
+      if (tid == 0) TC2_TRACE2(2, kc);
     }
     if (tid == 0) TC2_TRACE(2);
     mbar_wait(accum_bar, 0);
@@ -1613,6 +1635,7 @@ static int make_map(CUtensorMap* map, const float* base, long long rows, long lo
 // a [128*MT, NB] fp32 TMEM tile and adds it to dW with vectorised red.global.add.v4.f32.
 // ---------------------------------------------------------------------------
 #define WG_BK 32                         // rows per chunk
+#define WG_THREADS 320                   // TMA + MMA + 8 epilogue warps (two per TMEM lane quadrant)
 
 // MN-major tf32 operands only exist in the SWIZZLE_128B_BASE32B shared-memory layout (32-byte
 // swizzle chunks, 4-row period: byte-address bits [5,7) ^= bits [7,9)); the matching TMA mode is
@@ -1629,10 +1652,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 struct WgParams {
   float* dW;
   int R, Co, Ci, NB, stages, rows_per_split, tmem_cols;
+  int dbg;          // TN_WG_DEBUG (timing experiments): 1 = no red.global stores, 2 = no epilogue at all
 };
 
 template <int MT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, WgParams p) {
   tn_grid_dep_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1700,33 +1724,47 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         tc_commit(accum_bar);
       }
-    } else {
+    } else if (!(p.dbg & 2)) {
       mbar_wait(accum_bar, 0);
       tc_fence_after();
-      const int quad = warp & 3;
+      const int quad = warp & 3, half = (warp - 2) >> 2;
       // Epilogue through shared memory (the pipeline stages are free now): TMEM hands each thread one output channel
       // (row of dW), so a direct red.global.add.v4 would touch 32 different 128-byte lines per warp instruction; staged,
       // each warp instruction adds 512 contiguous bytes of one row.  Rows are padded to NB + 4 floats (conflict-free).
+      // EIGHT epilogue warps: the two warps of a TMEM lane quadrant take alternate 64-column groups (four tcgen05.ld.x16 in
+      // flight per wait) and alternate rows of the drain.  With four warps and one load per wait the epilogue was 6.0 of the
+      // kernel's 12.7 us (4.5 us of it TMEM -> shared memory -> registers, 1.5 us the reductions themselves).
       float* stg = reinterpret_cast<float*>(smem) + (size_t)(quad * 32) * (NB + 4);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        for (int c0 = 0; c0 < NB; c0 += 16) {
-          float v[16];
-          tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 256 + c0), v);
+        for (int c0 = 64 * half; c0 < NB; c0 += 128) {
+          float v[64];
+          const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 256 + c0);
+          const int ng = min(4, (NB - c0) / 16);        // NB is a multiple of 16
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (g < ng) tc_ld16_issue(ta + 16 * g, v + 16 * g);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 64; ++j) asm volatile("" : "+f"(v[j]));
           float4* dst = reinterpret_cast<float4*>(stg + (size_t)lane * (NB + 4) + c0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 16; ++j)
+            if (j < 4 * ng) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        __syncwarp();                                 // each warp stages and drains its own 32 rows
-        for (int r = 0; r < 32; ++r) {
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");       // the quadrant's two warps: staging complete
+        for (int r = half; r < 32; r += 2) {
           float* grow = p.dW + (size_t)(co0 + mt * 128 + quad * 32 + r) * p.Ci + ci0;
           for (int c = 4 * lane; c < NB; c += 128) {
             const float4 x = *reinterpret_cast<const float4*>(stg + (size_t)r * (NB + 4) + c);
+            if (!(p.dbg & 1))
             asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(grow + c), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
           }
         }
-        __syncwarp();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");       // drained before the next tile is staged
       }
+    } else if (warp == 2) {
+      mbar_wait(accum_bar, 0);
     }
   }
   tc_fence_before();
@@ -1884,7 +1922,7 @@ extern "C" int tn_wgrad_tc(const float* dZ, const float* U, float* dW, int R, in
       if ((rc = make_map_mn(&mA, dZ, R, Co, 4)) != TN_OK) return rc;
       if ((rc = make_map_mn(&mB, U, R, Ci, NB2 / 64)) != TN_OK) return rc;
       WgParams p;
-      p.dW = dW; p.R = R; p.Co = Co; p.Ci = Ci; p.NB = NB2; p.stages = stages2; p.rows_per_split = (int)cps * WG_BK;
+      p.dW = dW; p.R = R; p.Co = Co; p.Ci = Ci; p.NB = NB2; p.stages = stages2; p.rows_per_split = (int)cps * WG_BK; p.dbg = 0;
       int cols = 32;
       while (cols < NB2) cols <<= 1;
       p.tmem_cols = cols;
@@ -1924,6 +1962,7 @@ extern "C" int tn_wgrad_tc(const float* dZ, const float* U, float* dW, int R, in
   if ((rc = make_map_mn(&mB, U, R, Ci, NB / 32)) != TN_OK) return rc;
   WgParams p;
   p.dW = dW; p.R = R; p.Co = Co; p.Ci = Ci; p.NB = NB; p.stages = stages; p.rows_per_split = (int)cps * WG_BK;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("TN_WG_DEBUG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   int cols = MT == 2 ? 512 : 32;
   while (MT == 1 && cols < NB) cols <<= 1;
   p.tmem_cols = cols;
@@ -1931,10 +1970,10 @@ extern "C" int tn_wgrad_tc(const float* dZ, const float* U, float* dW, int R, in
   dim3 grid(co_groups, ci_blocks, splits);
   if (MT == 2) {
     TN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tn_launch(wgrad_tc_kernel<2>, grid, TC_THREADS, smem, stream, mA, mB, p);
+    tn_launch(wgrad_tc_kernel<2>, grid, WG_THREADS, smem, stream, mA, mB, p);
   } else {
     TN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tn_launch(wgrad_tc_kernel<1>, grid, TC_THREADS, smem, stream, mA, mB, p);
+    tn_launch(wgrad_tc_kernel<1>, grid, WG_THREADS, smem, stream, mA, mB, p);
   }
   TN_LAUNCH_CHECK("wgrad_tc_kernel");
   return TN_OK;
@@ -2030,7 +2069,7 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   TN_REQUIRE(X && ws, "gemm_tc: null tensor");
   const bool grad = (p.flags & TN_GEMM_GRAD) != 0 || p.dw_K > 0;
   p.flags &= ~TN_GEMM_GRAD;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("TN_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.flags |= dbg & (2048 | 4096 | 8192 | 16384); }   // experiments only
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("TN_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.flags |= dbg & (2048 | 4096 | 8192 | 16384 | 32768); }   // experiments only
   p.corr = tc_corr_for(grad);
   const float* ws_lo = ws + (size_t)(p.corr == 2 ? 3 : p.corr ? 2 : 1) * M * Kd;
   if (p.stats) {

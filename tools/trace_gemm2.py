@@ -35,3 +35,11 @@ for base, nm in ((0, "CTA 0"), (64, "CTA mid")):
     print(f"--- {nm}: us since kernel entry")
     for k in sorted(names, key=lambda k: t[base + k]):
         if t[base + k]: print(f"  {(t[base + k] - t0) / 1e3:7.2f}  {names[k]}")
+
+# per-chunk events of CTA 0 (slots 256 + 16 kind + chunk)
+kinds = ["TMA issued", "B arrived (warp 2)", "transform done (warp 2)", "A arrived (MMA warp)", "local ready", "peer ready", "first MMAs issued", "all MMAs issued", "commit issued"]
+order = [0, 1, 2, 5, 6, 3, 7, 8, 4]
+t0 = t[0]
+print("--- CTA 0 per K chunk, us since kernel entry: " + " | ".join(kinds))
+for kc in range(min(16, K // 32)):
+    print(f"  chunk {kc:2d}: " + " ".join(f"{(t[256 + 16 * k + kc] - t0) / 1e3:7.2f}" if t[256 + 16 * k + kc] else "      -" for k in order))
