@@ -1566,17 +1566,22 @@ static int tc_corr_for(bool grad) {
 // ---------------------------------------------------------------------------
 // ws[2] holds, per row and 32-element K chunk, 64 bf16 = [bf16(hi) x32 | bf16(x - hi) x32] in the 128 bytes that hold 32 tf32
 // values in the other two planes (the weight side of the bf16 correction MMA, see tc_store_corr)
-__device__ __forceinline__ void split_store(float* hi, float* lo, float* cr, float* cf, size_t i, int k, float x) {
+// planes: bit p set = write ws[p] (the batched per-step split writes only the planes the step's GEMMs read)
+__device__ __forceinline__ void split_store(float* hi, float* lo, float* cr, float* cf, size_t i, int k, float x, int planes = 15) {
   const float h = __uint_as_float(rna_tf32(x));
   hi[i] = h;
-  lo[i] = __uint_as_float(rna_tf32(x - h));
-  __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(cr + (i - (size_t)(k & 31))) + (k & 31);
-  c[0] = __float2bfloat16_rn(h);
-  c[32] = __float2bfloat16_rn(x - h);
-  // ws[3]: the fp16 flavour with the weight side of the exponent-balanced scales (see TC_F16_SA / TC_F16_SC)
-  unsigned short* f = reinterpret_cast<unsigned short*>(cf + (i - (size_t)(k & 31))) + (k & 31);
-  f[0] = (unsigned short)(pack_f16x2(h * (1.f / TC_F16_SA), 0.f) & 0xffffu);
-  f[32] = (unsigned short)(pack_f16x2((x - h) * TC_F16_SC, 0.f) & 0xffffu);
+  if (planes & 2) lo[i] = __uint_as_float(rna_tf32(x - h));
+  if (planes & 4) {
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(cr + (i - (size_t)(k & 31))) + (k & 31);
+    c[0] = __float2bfloat16_rn(h);
+    c[32] = __float2bfloat16_rn(x - h);
+  }
+  if (planes & 8) {
+    // ws[3]: the fp16 flavour with the weight side of the exponent-balanced scales (see TC_F16_SA / TC_F16_SC)
+    unsigned short* f = reinterpret_cast<unsigned short*>(cf + (i - (size_t)(k & 31))) + (k & 31);
+    f[0] = (unsigned short)(pack_f16x2(h * (1.f / TC_F16_SA), 0.f) & 0xffffu);
+    f[32] = (unsigned short)(pack_f16x2((x - h) * TC_F16_SC, 0.f) & 0xffffu);
+  }
 }
 __global__ void split_tf32_kernel(const float* __restrict__ W, float* __restrict__ ws, int M, int Kd, int transpose) {
   tn_grid_dep_sync();
@@ -1993,21 +1998,27 @@ extern "C" int tn_split_tf32(const float* W, float* ws, int M, int Kd, int trans
   return TN_OK;
 }
 
-__global__ void split_tf32_batch_kernel(const tn_split_job* __restrict__ jobs) {
+// planes_fwd / planes_bwd: the planes the forward GEMMs (jobs with transpose = 0) and the gradient GEMMs (transpose = 1) read
+__global__ void split_tf32_batch_kernel(const tn_split_job* __restrict__ jobs, int planes_fwd, int planes_bwd) {
   tn_grid_dep_sync();
   const tn_split_job j = jobs[blockIdx.y];
   const size_t n = (size_t)j.M * j.Kd;
+  const int planes = j.transpose ? planes_bwd : planes_fwd;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / j.Kd), k = (int)(i - (size_t)m * j.Kd);
     const float x = j.transpose ? j.W[(size_t)k * j.M + m] : j.W[i];
-    split_store(j.ws, j.ws + n, j.ws + 2 * n, j.ws + 3 * n, i, k, x);
+    split_store(j.ws, j.ws + n, j.ws + 2 * n, j.ws + 3 * n, i, k, x, planes);
   }
 }
+// Every weight split of a step in one launch.  Only the planes this configuration's GEMMs read are written: tf32 hi + the
+// correction plane of the forward scheme for the [M, Kd] orientation, tf32 hi + the gradient scheme's for the transposed one
+// (52.9 -> 60.6 us when the fourth plane was added, half of it with two planes per orientation).
 extern "C" int tn_split_tf32_batch(const tn_split_job* jobs_dev, int njobs, int max_elems, void* stream) {
   TN_REQUIRE(jobs_dev && njobs > 0 && njobs <= 65535 && max_elems > 0, "split_tf32_batch: bad arguments");
   int bx = (max_elems + 255) / 256;
   if (bx > 64) bx = 64;
-  tn_launch(split_tf32_batch_kernel, dim3(bx, njobs), 256, 0, stream, jobs_dev);
+  const int plane_of[3] = {2, 4, 8};                 // corr 0 -> tf32 lo, 1 -> bf16 rows, 2 -> scaled fp16 rows
+  tn_launch(split_tf32_batch_kernel, dim3(bx, njobs), 256, 0, stream, jobs_dev, 1 | plane_of[tc_corr_for(false)], 1 | plane_of[tc_corr_for(true)]);
   TN_LAUNCH_CHECK("split_tf32_batch_kernel");
   return TN_OK;
 }

@@ -7,13 +7,14 @@
 // batched form reproduces datasets.collate_fn's zero padding of frames past each
 // utterance's own length (src/datasets.py:48-73).
 //
-// One block transforms a tile of MEL_FT consecutive frames of one utterance.  Two real
+// One block transforms a tile of MEL_FT (a launch parameter) consecutive frames of one utterance.  Two real
 // frames share one complex radix-2 FFT in shared memory (frame A in the real lane,
 // frame B in the imaginary lane), the spectra are separated with the conjugate-symmetry
 // identity, and the tile is written out in one coalesced pass in either layout.
 #include "common.cuh"
+#include <stdlib.h>
 
-#define MEL_FT 16
+#define MEL_FT_MAX 32     // frames per block (even, chosen by the launcher so that the grid fills whole waves)
 #define MEL_THREADS 256
 
 // SpecAugment (src/transforms.py:168-175, 187-201) for given per-utterance draws; all pointers NULL = off.
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_kernel(const float* __restric
                                                           const float* __restrict__ window, const float* __restrict__ fb,
                                                           const int* __restrict__ band_lo, const int* __restrict__ band_hi,
                                                           float* __restrict__ out, int L_stride, int L_full, int T_out,
-                                                          int N, int log2N, int hop, int n_mels, int nwc, TnSpecAug aug) {
+                                                          int N, int log2N, int hop, int n_mels, int nwc, TnSpecAug aug, int MEL_FT) {
   tn_grid_dep_sync();
   extern __shared__ float smem[];
   const int NF = N / 2 + 1;
@@ -184,13 +185,27 @@ static int mel_launch(const float* wave, const int* lengths, const float* window
   TN_REQUIRE(lengths || L_full > n_fft / 2, "mel_fwd: reflect padding needs more than n_fft/2 samples (L=%d)", L_full);
   TN_REQUIRE(L_full <= L_stride, "mel_fwd: L_full > L_stride");
   const int NF = n_fft / 2 + 1;
-  size_t smem = sizeof(float) * ((size_t)2 * n_fft + n_fft + n_fft + 2 * NF + (size_t)MEL_FT * (n_mels + 1));
-  if (smem > 48 * 1024) {
-    TN_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto smem_for = [&](int ft) { return sizeof(float) * ((size_t)2 * n_fft + n_fft + n_fft + 2 * NF + (size_t)ft * (n_mels + 1)); };
+  TN_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(MEL_FT_MAX)));
+  // frames per block: the even count in [8, 32] that minimises waves x frames.  B = 64, T = 301 with 16 frames per block is
+  // 1216 blocks on 148 x 8 resident ones -- a second wave of 32 blocks that doubled the kernel's time (127 us).
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    TN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mel_kernel, MEL_THREADS, smem_for(MEL_FT_MAX)));
+    if (per_sm < 1) per_sm = 1;
   }
-  dim3 grid(tn_cdiv(T_out, MEL_FT), B);
+  const long long cap = (long long)per_sm * tn_num_sms();
+  int ft = 16;
+  long long best = -1;
+  for (int f = 8; f <= MEL_FT_MAX; f += 2) {
+    const long long blocks = (long long)tn_cdiv(T_out, f) * B, cost = ((blocks + cap - 1) / cap) * (f + 2);     // + 2: the block's twiddle / window set-up
+    if (best < 0 || cost < best || (cost == best && f == 16)) { best = cost; ft = f; }
+  }
+  if (const char* e = getenv("TN_MEL_FT")) { const int v = atoi(e); if (v >= 2 && v <= MEL_FT_MAX && v % 2 == 0) ft = v; }    // tuning knob
+  const size_t smem = smem_for(ft);
+  dim3 grid(tn_cdiv(T_out, ft), B);
   tn_launch(mel_kernel, grid, MEL_THREADS, smem, stream, wave, lengths, window, fb, band_lo, band_hi, out, L_stride,
-                                                                 L_full, T_out, n_fft, log2N, hop, n_mels, nwc, aug);
+                                                                 L_full, T_out, n_fft, log2N, hop, n_mels, nwc, aug, ft);
   TN_LAUNCH_CHECK("mel_kernel");
   return TN_OK;
 }
