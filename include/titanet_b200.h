@@ -207,13 +207,15 @@ int tn_gemm_tc_dwbwd_bn(const float* dZ, const float* ws, const tn_bn_bwd* bnb, 
                         const float* dw_w, float* g_dw, float* g_dbias, float* g_dscale, float* g_dshift, const float* scale,
                         const float* shift, int relu, float drop_p, const unsigned long long* seed, unsigned int layer, int B,
                         int T, int Co, int C, int K, void* stream);
-/* every weight split of a step in ONE launch: jobs (device array) = {W, ws, M, Kd, transpose} like tn_split_tf32 */
+/* every weight split of a step in ONE launch: jobs (device array) = {W, ws, M, Kd, transpose, tile0} like tn_split_tf32;
+ * tile0 = number of 32 x 32 tiles of the jobs before this one (a job has ceil(M / 32) * (Kd / 32)), total_tiles = their sum.
+ * Only the planes the step's GEMMs read are written (forward scheme for transpose = 0, gradient scheme for transpose = 1). */
 typedef struct tn_split_job {
   const float* W;
   float* ws;
-  int M, Kd, transpose, pad_;
+  int M, Kd, transpose, tile0;
 } tn_split_job;
-int tn_split_tf32_batch(const tn_split_job* jobs_dev, int njobs, int max_elems, void* stream);
+int tn_split_tf32_batch(const tn_split_job* jobs_dev, int njobs, int total_tiles, void* stream);
 
 /* ---- depthwise conv with fused lazy-activation prologue:
  *      DepthwiseConv1d's first conv (src/modules.py:64-75) after BN/ReLU/Dropout

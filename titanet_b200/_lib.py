@@ -133,7 +133,7 @@ class TnScratch(ctypes.Structure):
 class TnSplitJob(ctypes.Structure):
     """``tn_split_job`` of include/titanet_b200.h."""
     _fields_ = [("W", ctypes.c_void_p), ("ws", ctypes.c_void_p), ("M", ctypes.c_int), ("Kd", ctypes.c_int),
-                ("transpose", ctypes.c_int), ("pad_", ctypes.c_int)]
+                ("transpose", ctypes.c_int), ("tile0", ctypes.c_int)]
 
 
 class TnAdamJob(ctypes.Structure):

@@ -216,7 +216,7 @@ class SplitCache:
         self.weights = [w for w in weights]
         dev = self.weights[0].device
         self.ptrs = [w.data_ptr() for w in self.weights]
-        jobs, self.views, off = [], {}, 0
+        jobs, self.views, off, tiles = [], {}, 0, 0
         total = sum(2 * WS_PLANES * w.numel() for w in self.weights)
         self.buf = torch.empty(total, device=dev, dtype=torch.float32)
         for i, w in enumerate(self.weights):
@@ -225,21 +225,24 @@ class SplitCache:
             fwd = self.buf[off:off + WS_PLANES * n].view(WS_PLANES, Co, Ci)
             bwd = self.buf[off + WS_PLANES * n:off + 2 * WS_PLANES * n].view(WS_PLANES, Ci, Co)
             off += 2 * WS_PLANES * n
-            jobs.append(TnSplitJob(w.data_ptr(), fwd.data_ptr(), Co, Ci, 0, 0))
-            jobs.append(TnSplitJob(w.data_ptr(), bwd.data_ptr(), Ci, Co, 1, 0))
+            # tile0: the job's first 32 x 32 tile in the step's tile list (tn_split_tf32_batch)
+            jobs.append(TnSplitJob(w.data_ptr(), fwd.data_ptr(), Co, Ci, 0, tiles))
+            tiles += -(-Co // 32) * (Ci // 32)
+            jobs.append(TnSplitJob(w.data_ptr(), bwd.data_ptr(), Ci, Co, 1, tiles))
+            tiles += -(-Ci // 32) * (Co // 32)
             self.views[id(w)] = (i, fwd, bwd)
         arr = (TnSplitJob * len(jobs))(*jobs)
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         self.jobs = raw.to(dev)
         self.njobs = len(jobs)
-        self.max_elems = max(w.numel() for w in self.weights)
+        self.total_tiles = tiles
         self.versions = [-1] * len(self.weights)
 
     def stale(self) -> bool:
         return any(w.data_ptr() != p for w, p in zip(self.weights, self.ptrs))
 
     def refresh(self):
-        call("tn_split_tf32_batch", ptr(self.jobs), self.njobs, self.max_elems)
+        call("tn_split_tf32_batch", ptr(self.jobs), self.njobs, self.total_tiles)
         self.versions = [w._version for w in self.weights]
         for w in self.weights:
             _SPLITS[id(w)] = self

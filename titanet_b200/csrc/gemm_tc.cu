@@ -1998,27 +1998,67 @@ extern "C" int tn_split_tf32(const float* W, float* ws, int M, int Kd, int trans
   return TN_OK;
 }
 
-// planes_fwd / planes_bwd: the planes the forward GEMMs (jobs with transpose = 0) and the gradient GEMMs (transpose = 1) read
-__global__ void split_tf32_batch_kernel(const tn_split_job* __restrict__ jobs, int planes_fwd, int planes_bwd) {
+// planes_fwd / planes_bwd: the planes the forward GEMMs (jobs with transpose = 0) and the gradient GEMMs (transpose = 1) read.
+// 32 x 32 tiles, 256 threads: a transposed job reads W[k, m] along m and writes ws[m, k] along k through shared memory (the
+// first version read the transposed weights with a stride of M floats per thread: 50 us per step for 25 MB of weights).
+__global__ void __launch_bounds__(256) split_tf32_batch_kernel(const tn_split_job* __restrict__ jobs, int njobs, int total_tiles,
+                                                               int tiles_per_block, int planes_fwd, int planes_bwd) {
   tn_grid_dep_sync();
-  const tn_split_job j = jobs[blockIdx.y];
-  const size_t n = (size_t)j.M * j.Kd;
-  const int planes = j.transpose ? planes_bwd : planes_fwd;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int m = (int)(i / j.Kd), k = (int)(i - (size_t)m * j.Kd);
-    const float x = j.transpose ? j.W[(size_t)k * j.M + m] : j.W[i];
-    split_store(j.ws, j.ws + n, j.ws + 2 * n, j.ws + 3 * n, i, k, x, planes);
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  // this block's contiguous range of the step's tiles (job.tile0 = index of the job's first tile): one search, then a walk
+  const int t_begin = blockIdx.x * tiles_per_block, t_end = min(total_tiles, t_begin + tiles_per_block);
+  if (t_begin >= t_end) return;
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].tile0 <= t_begin) lo = mid; else hi = mid - 1;
+  }
+  int ji = lo;
+  tn_split_job j = jobs[ji];
+  int tiles_k = j.Kd / 32, ntiles = tiles_k * ((j.M + 31) / 32);       // Kd % 32 == 0 (tn_split_tf32's contract)
+  for (int tg = t_begin; tg < t_end; ++tg) {
+    while (tg - j.tile0 >= ntiles) {
+      j = jobs[++ji];
+      tiles_k = j.Kd / 32; ntiles = tiles_k * ((j.M + 31) / 32);
+    }
+    const int t = tg - j.tile0;
+    const size_t n = (size_t)j.M * j.Kd;
+    const int planes = j.transpose ? planes_bwd : planes_fwd;
+    const int m0 = (t / tiles_k) * 32, k0 = (t % tiles_k) * 32;
+    if (j.transpose) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = k0 + ty + 8 * i, m = m0 + tx;
+        tile[ty + 8 * i][tx] = m < j.M ? j.W[(size_t)k * j.M + m] : 0.f;
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty + 8 * i, k = k0 + tx;
+      if (m < j.M) {
+        const size_t idx = (size_t)m * j.Kd + k;
+        const float x = j.transpose ? tile[tx][ty + 8 * i] : j.W[idx];
+        split_store(j.ws, j.ws + n, j.ws + 2 * n, j.ws + 3 * n, idx, k, x, planes);
+      }
+    }
+    if (j.transpose) __syncthreads();
   }
 }
-// Every weight split of a step in one launch.  Only the planes this configuration's GEMMs read are written: tf32 hi + the
-// correction plane of the forward scheme for the [M, Kd] orientation, tf32 hi + the gradient scheme's for the transposed one
-// (52.9 -> 60.6 us when the fourth plane was added, half of it with two planes per orientation).
-extern "C" int tn_split_tf32_batch(const tn_split_job* jobs_dev, int njobs, int max_elems, void* stream) {
-  TN_REQUIRE(jobs_dev && njobs > 0 && njobs <= 65535 && max_elems > 0, "split_tf32_batch: bad arguments");
-  int bx = (max_elems + 255) / 256;
-  if (bx > 64) bx = 64;
+// Every weight split of a step in one launch: the 32 x 32 tiles of all jobs form one list (job.tile0 = the job's first tile,
+// total_tiles = their number) that a grid of ~8 blocks per SM walks in contiguous ranges.  Only the planes this configuration's
+// GEMMs read are written: tf32 hi + the forward scheme's correction plane for the [M, Kd] orientation, tf32 hi + the gradient
+// scheme's for the transposed one.
+extern "C" int tn_split_tf32_batch(const tn_split_job* jobs_dev, int njobs, int total_tiles, void* stream) {
+  TN_REQUIRE(jobs_dev && njobs > 0 && total_tiles > 0, "split_tf32_batch: bad arguments");
+  int blocks = tn_num_sms() * 8;
+  if (blocks > total_tiles) blocks = total_tiles;
+  const int tpb = (total_tiles + blocks - 1) / blocks;
+  blocks = (total_tiles + tpb - 1) / tpb;
   const int plane_of[3] = {2, 4, 8};                 // corr 0 -> tf32 lo, 1 -> bf16 rows, 2 -> scaled fp16 rows
-  tn_launch(split_tf32_batch_kernel, dim3(bx, njobs), 256, 0, stream, jobs_dev, 1 | plane_of[tc_corr_for(false)], 1 | plane_of[tc_corr_for(true)]);
+  tn_launch(split_tf32_batch_kernel, blocks, 256, 0, stream, jobs_dev, njobs, total_tiles, tpb, 1 | plane_of[tc_corr_for(false)],
+            1 | plane_of[tc_corr_for(true)]);
   TN_LAUNCH_CHECK("split_tf32_batch_kernel");
   return TN_OK;
 }
