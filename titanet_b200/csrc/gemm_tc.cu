@@ -1657,13 +1657,18 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 struct WgParams {
   float* dW;
   int R, Co, Ci, NB, stages, rows_per_split, tmem_cols;
-  int dbg;          // TN_WG_DEBUG (timing experiments): 1 = no red.global stores, 2 = no epilogue at all
+  long long* trace; // tn_gemm_tc_set_trace: globaltimer stamps of CTA 0 (slots 0..15) and of the last CTA (16..31)
+  int dbg;          // TN_WG_DEBUG (timing experiments): 1 = no reductions, 2 = no epilogue at all, 4 = red.global.add.v4 drain instead of bulk reductions
 };
 
+#define WG_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (blockIdx.z == 0 || blockIdx.z == gridDim.z - 1)) { \
+    unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); \
+    p.trace[(blockIdx.z == 0 ? 0 : 16) + (slot)] = (long long)gt_; } } while (0)
 template <int MT>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, WgParams p) {
   tn_grid_dep_sync();
+  if (threadIdx.x == 0) WG_TRACE(0);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 1];
   __shared__ uint32_t tmem_base_slot;
@@ -1693,6 +1698,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  if (threadIdx.x == 0) WG_TRACE(1);
 
   if (num_kc > 0) {
     if (warp == 0) {
@@ -1706,6 +1712,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tma_load_3d(base, &tmA, fb, 0, ra + kc * WG_BK, co0 / 32);
           tma_load_3d(base + a_bytes, &tmB, fb, 0, ra + kc * WG_BK, ci0 / 32);
         }
+        WG_TRACE(2);
       }
     } else if (warp == 1) {
       if (lane == 0) {
@@ -1726,12 +1733,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
           tc_commit(empty0 + 8 * s);
+          if (kc == 0) WG_TRACE(3);
         }
         tc_commit(accum_bar);
+        WG_TRACE(4);
       }
     } else if (!(p.dbg & 2)) {
       mbar_wait(accum_bar, 0);
       tc_fence_after();
+      if (threadIdx.x == 64) WG_TRACE(5);
       const int quad = warp & 3, half = (warp - 2) >> 2;
       // Epilogue through shared memory (the pipeline stages are free now): TMEM hands each thread one output channel
       // (row of dW), so a direct red.global.add.v4 would touch 32 different 128-byte lines per warp instruction; staged,
@@ -1757,16 +1767,32 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int j = 0; j < 16; ++j)
             if (j < 4 * ng) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
+        fence_proxy_async();                                                // the bulk engine (async proxy) reads what was just stored
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");       // the quadrant's two warps: staging complete
-        for (int r = half; r < 32; r += 2) {
-          float* grow = p.dW + (size_t)(co0 + mt * 128 + quad * 32 + r) * p.Ci + ci0;
-          for (int c = 4 * lane; c < NB; c += 128) {
-            const float4 x = *reinterpret_cast<const float4*>(stg + (size_t)r * (NB + 4) + c);
-            if (!(p.dbg & 1))
-            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(grow + c), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+        if (threadIdx.x == 64) WG_TRACE(6);
+        if (p.dbg & 4) {
+          // TN_WG_DEBUG=4: the earlier drain, one red.global.add.v4 per thread and 16 bytes (A/B)
+          for (int r = half; r < 32; r += 2) {
+            float* grow = p.dW + (size_t)(co0 + mt * 128 + quad * 32 + r) * p.Ci + ci0;
+            for (int c = 4 * lane; c < NB; c += 128) {
+              const float4 x = *reinterpret_cast<const float4*>(stg + (size_t)r * (NB + 4) + c);
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(grow + c), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+            }
+          }
+        } else if (!(p.dbg & 1)) {
+          // drain: ONE bulk reduction per staged row (NB floats, contiguous in dW): cp.reduce.async.bulk adds the row in L2
+          // without a shared-memory read, an address and an instruction per 16 bytes on the SM (8192 red.v4 per CTA before)
+          const int r = half + 2 * lane;
+          if (r < 32) {
+            float* grow = p.dW + (size_t)(co0 + mt * 128 + quad * 32 + r) * p.Ci + ci0;
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                         ::"l"(grow), "r"(smem_u32(stg + (size_t)r * (NB + 4))), "r"((uint32_t)NB * 4u) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
           }
         }
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");       // drained before the next tile is staged
+        if (threadIdx.x == 64) WG_TRACE(7);
       }
     } else if (warp == 2) {
       mbar_wait(accum_bar, 0);
@@ -1774,6 +1800,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) WG_TRACE(8);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
@@ -1927,7 +1954,7 @@ extern "C" int tn_wgrad_tc(const float* dZ, const float* U, float* dW, int R, in
       if ((rc = make_map_mn(&mA, dZ, R, Co, 4)) != TN_OK) return rc;
       if ((rc = make_map_mn(&mB, U, R, Ci, NB2 / 64)) != TN_OK) return rc;
       WgParams p;
-      p.dW = dW; p.R = R; p.Co = Co; p.Ci = Ci; p.NB = NB2; p.stages = stages2; p.rows_per_split = (int)cps * WG_BK; p.dbg = 0;
+      p.dW = dW; p.R = R; p.Co = Co; p.Ci = Ci; p.NB = NB2; p.stages = stages2; p.rows_per_split = (int)cps * WG_BK; p.dbg = 0; p.trace = nullptr;
       int cols = 32;
       while (cols < NB2) cols <<= 1;
       p.tmem_cols = cols;
@@ -1968,6 +1995,7 @@ extern "C" int tn_wgrad_tc(const float* dZ, const float* U, float* dW, int R, in
   WgParams p;
   p.dW = dW; p.R = R; p.Co = Co; p.Ci = Ci; p.NB = NB; p.stages = stages; p.rows_per_split = (int)cps * WG_BK;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("TN_WG_DEBUG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
+  p.trace = g_trace;
   int cols = MT == 2 ? 512 : 32;
   while (MT == 1 && cols < NB) cols <<= 1;
   p.tmem_cols = cols;
