@@ -284,6 +284,12 @@ int tn_tail_bwd2(const float* dout, const float* out, const float* z3, const flo
                  float* dz3, float* ds, float* dsc3, float* dsh3, float* dscs, float* dshs, const float* scale3,
                  const float* shift3, float drop3, unsigned int layer3, const float* scale_s, const float* shift_s,
                  float drop_o, const unsigned long long* seed, int B, int T, int C, void* stream);
+/* the same; out may be NULL: the ReLU / dropout mask of the block output is then recomputed from z3, s and the gate exactly as
+ * tn_tail_fwd computed it (layer_o = tn_tail_fwd's), so `out` is not read (one [B*T, C] tensor less for this HBM-bound pass) */
+int tn_tail_bwd2r(const float* dout, const float* out, const float* z3, const float* s, const float* gate, const float* dm,
+                  float* dz3, float* ds, float* dsc3, float* dsh3, float* dscs, float* dshs, const float* scale3,
+                  const float* shift3, float drop3, unsigned int layer3, const float* scale_s, const float* shift_s, float drop_o,
+                  unsigned int layer_o, const unsigned long long* seed, int B, int T, int C, void* stream);
 
 /* stand-alone SE gate multiply (SqueezeExcitation.forward outside a MegaBlock, src/modules.py:187-189):
  * out = x * gate[b,c];  backward: dx = dout * gate, dgate[b,c] += sum_t dout * x  (dgate ACCUMULATED) */

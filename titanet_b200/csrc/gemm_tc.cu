@@ -92,6 +92,12 @@ __device__ __forceinline__ uint32_t cluster_cta_rank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// one lane of a converged warp (elect.sync): the tcgen05 issue sites branch on it from warp-uniform code
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -1203,13 +1209,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int s = kc % S;
         if (kc >= S) mbar_wait(empty0 + 8 * s, ((kc / S) - 1) & 1);
         const int k0 = kc * TC_BK;
-        if ((p.flags & 8192) && kc >= S) {                       // TN_TC_DEBUG=8192: weight tiles only for the first S chunks (timing experiment)
-          if (leader) mbar_arrive(fullA0 + 8 * s);
-        } else {
         if (leader) mbar_expect_tx(fullA0 + 8 * s, 4 * a_tile);   // both CTAs' hi + lo weight tiles
         tma_load_2d_2sm(smem_u32(a_hi(s)), &tmA_hi, fullA_leader0 + 8 * s, k0, m0 + (int)rank * 128);
         tma_load_2d_2sm(smem_u32(a_lo(s)), &tmA_lo, fullA_leader0 + 8 * s, k0, m0 + (int)rank * 128);
-        }
         const int padr = MODE == 2 ? (p.fdw_K >> 1) : 0;           // fused depthwise forward: PAD rows of halo in front
         mbar_expect_tx(fullB0 + 8 * s, 2 * b_raw + (p.has_bnb ? 2 * b_half : 0u));
         tma_load_2d(smem_u32(b_hi(s, 0)), &tmB, fullB0 + 8 * s, k0, n0 + (int)rank * HB - padr);
@@ -1268,63 +1270,65 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
-    if (leader && lane == 0) {
+    // The WHOLE warp runs the loop (waits, descriptors: warp-uniform values in uniform registers) and one elected lane issues.
+    // Issued from `if (lane == 0)` code, every tcgen05.mma was wrapped by the compiler in an ELECT / BRA.U.ANY serialisation loop
+    // with its operands moved from vector to uniform registers each time: 105 cycles per M = 256, N = 144 MMA against 72 from
+    // uniform code (tools/utccp_test.cu) -- the mainloop was bound by the issuing thread, not by the tensor pipe.
+    if (leader) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((256u >> 4) << 24);
+      const uint32_t idesc_c = tc_idesc_bf16(idesc, p.corr);
       // accumulator plan as in gemm_tc_kernel: nacc - 1 K-chunked main accumulators + one for the corrections, BN2 columns apart
       const int nacc = (MODE != 1 && p.nacc > 1) ? p.nacc : 1, nmain = nacc > 1 ? nacc - 1 : 1;
+      const int corr = p.corr;
       int prev_am = -1;
       for (int kc = 0; kc < num_kc; ++kc) {
         const int s = kc % S;
         const uint32_t ph = (kc / S) & 1;
         mbar_wait(fullA0 + 8 * s, ph);
-        TC2_TRACE2(5, kc);
         mbar_wait(ready0 + 8 * s, ph);
-        TC2_TRACE2(6, kc);
         mbar_wait(readyP0 + 8 * s, ph);
-        TC2_TRACE2(3, kc);
         tc_fence_after();
         const uint64_t dah = umma_desc_k128(smem_u32(a_hi(s))), dal = umma_desc_k128(smem_u32(a_lo(s)));
         const int am = (kc * nmain) / num_kc;
         const bool new_main = am != prev_am;
         prev_am = am;
-        const bool inter = (p.flags & 32768) != 0;        // TN_TC_DEBUG=32768: alternate the two N tiles (independent accumulators) instead of tile after tile
+        if (tc_elect_one()) {
+          TC2_TRACE2(3, kc);
 #pragma unroll
-        for (int it = 0; it < 2 * (TC_BK / 8); ++it) {
-          const int t = inter ? (it & 1) : (it >> 2), kk = inter ? (it >> 1) : (it & 3);
-          const uint64_t dbh = umma_desc_k128(smem_u32(b_hi(s, t))), dbl = umma_desc_k128(smem_u32(b_lo(s, t)));
-          const uint32_t d = tmem_base + (uint32_t)(t * 256 + am * BN2);
-          const uint32_t dc = tmem_base + (uint32_t)(t * 256 + (nacc - 1) * BN2);
-          {
-            if (it == 1) TC2_TRACE2(7, kc);                // after the first tile-0 MMA pair was issued
-            const uint64_t adv = (uint64_t)(kk * 2);
-            const uint32_t acc = (new_main && kk == 0) ? 0u : 1u;
-            const uint32_t accc = (kc > 0 || kk > 0) ? 1u : 0u;
-            if (nacc > 1) {
-              tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, acc);
-              if (p.corr) {
-                tc_mma_bf16_2sm(dc, dal + adv, dbl + adv, tc_idesc_bf16(idesc, p.corr), accc);
+          for (int t = 0; t < 2; ++t) {
+            const uint64_t dbh = umma_desc_k128(smem_u32(b_hi(s, t))), dbl = umma_desc_k128(smem_u32(b_lo(s, t)));
+            const uint32_t d = tmem_base + (uint32_t)(t * 256 + am * BN2);
+            const uint32_t dc = tmem_base + (uint32_t)(t * 256 + (nacc - 1) * BN2);
+#pragma unroll
+            for (int kk = 0; kk < TC_BK / 8; ++kk) {
+              const uint64_t adv = (uint64_t)(kk * 2);
+              const uint32_t acc = (new_main && kk == 0) ? 0u : 1u;
+              const uint32_t accc = (kc > 0 || kk > 0) ? 1u : 0u;
+              if (nacc > 1) {
+                tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, acc);
+                if (corr) {
+                  tc_mma_bf16_2sm(dc, dal + adv, dbl + adv, idesc_c, accc);
+                } else {
+                  tc_mma_tf32_2sm(dc, dal + adv, dbh + adv, idesc, accc);
+                  tc_mma_tf32_2sm(dc, dah + adv, dbl + adv, idesc, 1u);
+                }
+              } else if (corr) {
+                tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, acc);
+                tc_mma_bf16_2sm(d, dal + adv, dbl + adv, idesc_c, 1u);
               } else {
-                tc_mma_tf32_2sm(dc, dal + adv, dbh + adv, idesc, accc);
-                tc_mma_tf32_2sm(dc, dah + adv, dbl + adv, idesc, 1u);
+                tc_mma_tf32_2sm(d, dal + adv, dbh + adv, idesc, acc);
+                tc_mma_tf32_2sm(d, dah + adv, dbl + adv, idesc, 1u);
+                tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, 1u);
               }
-            } else if (p.corr) {
-              if (p.flags & 16384) tc_mma_bf16_2sm(d, dah + adv, dbh + adv, tc_idesc_bf16(idesc, p.corr), acc);   // TN_TC_DEBUG=16384: main product as kind::f16 on the same bytes (timing experiment, wrong numbers)
-              else
-              tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, acc);
-              if (!(p.flags & 4096))                                           // TN_TC_DEBUG=4096: no correction MMA (timing experiment)
-                tc_mma_bf16_2sm(d, dal + adv, dbl + adv, tc_idesc_bf16(idesc, p.corr), 1u);
-            } else {
-              tc_mma_tf32_2sm(d, dal + adv, dbh + adv, idesc, acc);
-              tc_mma_tf32_2sm(d, dah + adv, dbl + adv, idesc, 1u);
-              tc_mma_tf32_2sm(d, dah + adv, dbh + adv, idesc, 1u);
             }
           }
+          tc_commit_2sm(empty0 + 8 * s, (uint16_t)3);       // stage free in both CTAs once these MMAs have read it
+          TC2_TRACE2(4, kc);
         }
-        TC2_TRACE2(8, kc);
-        tc_commit_2sm(empty0 + 8 * s, (uint16_t)3);       // stage free in both CTAs once these MMAs have read it
-        TC2_TRACE2(4, kc);
+        __syncwarp();
       }
-      tc_commit_2sm(accum_bar, (uint16_t)3);              // accumulators complete (both CTAs)
+      if (tc_elect_one()) tc_commit_2sm(accum_bar, (uint16_t)3);              // accumulators complete (both CTAs)
+      __syncwarp();
     } else if (!leader && lane == 0) {
       for (int kc = 0; kc < num_kc; ++kc) {               // forward this CTA's operand-ready events to the leader
         const int s = kc % S;
@@ -1438,7 +1442,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       if (tid == 0) TC2_TRACE2(1, kc);
       float4* hi = reinterpret_cast<float4*>(b_hi(s, 0));
       float4* lo = reinterpret_cast<float4*>(b_lo(s, 0));
-      for (int i = tid; i < ((p.flags & 2048) ? 0 : n4); i += 32 * EW) {       // TN_TC_DEBUG=2048: no transform (timing experiment)
+      for (int i = tid; i < n4; i += 32 * EW) {
         const float4 v = hi[i];
         uint4 h, l;
         h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
@@ -2148,7 +2152,7 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   TN_REQUIRE(X && ws, "gemm_tc: null tensor");
   const bool grad = (p.flags & TN_GEMM_GRAD) != 0 || p.dw_K > 0;
   p.flags &= ~TN_GEMM_GRAD;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("TN_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.flags |= dbg & (2048 | 4096 | 8192 | 16384 | 32768); }   // experiments only
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("TN_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.flags |= dbg & (2048 | 4096 | 8192 | 16384); }   // experiments only
   p.corr = tc_corr_for(grad);
   const float* ws_lo = ws + (size_t)(p.corr == 2 ? 3 : p.corr ? 2 : 1) * M * Kd;
   if (p.stats) {

@@ -267,16 +267,29 @@ __global__ void __launch_bounds__(TN_EW_THREADS) tail_fwd_kernel(const float* __
     const int q = qb + tl.q0;
     if (!tl.active || q >= tl.Q) continue;
     const float4 ssc = tn_ld4(act_s.scale + 4 * q), ssh = tn_ld4(act_s.shift + 4 * q);
-    for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
-      const int b = r / T;
-      size_t off = (size_t)r * C + 4 * q;
-      float4 a3 = tn_act4(act3, tn_ld4(z3 + off), 4 * q, off >> 2, nullptr);
-      float4 g = tn_ld4(gate + (size_t)b * C + 4 * q);
-      float4 v = tn_fma4(g, a3, tn_fma4(tn_ld4(s + off), ssc, ssh));
-      float4 keep = tn_drop4(act_o, off >> 2);
-      v.x = v.x > 0.f ? v.x * keep.x : 0.f; v.y = v.y > 0.f ? v.y * keep.y : 0.f;
-      v.z = v.z > 0.f ? v.z * keep.z : 0.f; v.w = v.w > 0.f ? v.w * keep.w : 0.f;
-      tn_st4(out + off, v);
+    // four rows per iteration: their eight 16-byte loads are issued before the first is used
+    for (int r = r0 + tl.lane; r < r1; r += 4 * tl.lanes) {
+      float4 zv[4], sv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (r + k * tl.lanes < r1) {
+          const size_t off = (size_t)(r + k * tl.lanes) * C + 4 * q;
+          zv[k] = tn_ld4(z3 + off);
+          sv[k] = tn_ld4(s + off);
+        }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (r + k * tl.lanes < r1) {
+          const int rr = r + k * tl.lanes, b = rr / T;
+          const size_t off = (size_t)rr * C + 4 * q;
+          float4 a3 = tn_act4(act3, zv[k], 4 * q, off >> 2, nullptr);
+          float4 g = tn_ld4(gate + (size_t)b * C + 4 * q);
+          float4 v = tn_fma4(g, a3, tn_fma4(sv[k], ssc, ssh));
+          float4 keep = tn_drop4(act_o, off >> 2);
+          v.x = v.x > 0.f ? v.x * keep.x : 0.f; v.y = v.y > 0.f ? v.y * keep.y : 0.f;
+          v.z = v.z > 0.f ? v.z * keep.z : 0.f; v.w = v.w > 0.f ? v.w * keep.w : 0.f;
+          tn_st4(out + off, v);
+        }
     }
   }
 }
@@ -301,11 +314,22 @@ __global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd1_kernel(const float* _
     const int q = qb + tl.q0;
     float4 acc = tn_zero4();
     if (tl.active && q < tl.Q)
-      for (int t = t0 + tl.lane; t < t1; t += tl.lanes) {
-        size_t off = ((size_t)b * T + t) * C + 4 * q;
-        float4 g = tail_gout(tn_ld4(dout + off), tn_ld4(out + off), inv_keep_o);
-        float4 a3 = tn_act4(act3, tn_ld4(z3 + off), 4 * q, off >> 2, nullptr);
-        acc = tn_fma4(g, a3, acc);
+      for (int t = t0 + tl.lane; t < t1; t += 4 * tl.lanes) {
+        float4 dv[4], ov[4], zv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (t + k * tl.lanes < t1) {
+            const size_t off = ((size_t)b * T + t + k * tl.lanes) * C + 4 * q;
+            dv[k] = tn_ld4(dout + off); ov[k] = tn_ld4(out + off); zv[k] = tn_ld4(z3 + off);
+          }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (t + k * tl.lanes < t1) {
+            const size_t off = ((size_t)b * T + t + k * tl.lanes) * C + 4 * q;
+            float4 g = tail_gout(dv[k], ov[k], inv_keep_o);
+            float4 a3 = tn_act4(act3, zv[k], 4 * q, off >> 2, nullptr);
+            acc = tn_fma4(g, a3, acc);
+          }
       }
     tn_lane_reduce_atomic(tl, acc, q, dgate + (size_t)b * C, red);
   }
@@ -341,17 +365,20 @@ __global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd1_mlp_kernel(const floa
   if (tn_last_block_of(counters + b, gridDim.x)) se_mlp_bwd_block(sm, b, dgate, gate, m, W1, W2, dm, dW1, dW2, C, Cr);
 }
 
-// pass 2: dz3, ds and the four per-channel reductions
+// pass 2: dz3, ds and the four per-channel reductions.  out == NULL: the mask of the block's output ReLU + dropout is
+// RECOMPUTED from z3, s and the gate with the forward kernel's own expressions (bit-identical decisions) instead of being
+// read back from `out`: one [R, C] tensor less to read (6 -> 5 tensors moved by this HBM-bound kernel).
 __global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd2_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                                                   const float* __restrict__ z3, const float* __restrict__ s,
                                                                   const float* __restrict__ gate, const float* __restrict__ dm,
                                                                   float* __restrict__ dz3, float* __restrict__ ds,
                                                                   float* __restrict__ dsc3, float* __restrict__ dsh3,
                                                                   float* __restrict__ dscs, float* __restrict__ dshs,
-                                                                  TnAct act3, TnAct act_s, float inv_keep_o, float inv_T, int R,
+                                                                  TnAct act3, TnAct act_s, TnAct act_o, float inv_keep_o, float inv_T, int R,
                                                                   int T, int C, int rpb) {
   tn_grid_dep_sync();
   act3 = tn_act_init(act3);
+  act_o = tn_act_init(act_o);
   __shared__ float4 red[TN_EW_THREADS];
   TnTile tl = tn_tile(C);
   const int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
@@ -359,23 +386,44 @@ __global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd2_kernel(const float* _
     const int q = qb + tl.q0;
     float4 a1 = tn_zero4(), a2 = tn_zero4(), a3s = tn_zero4(), a4 = tn_zero4();
     if (tl.active && q < tl.Q) {
-      const float4 sc3 = tn_ld4(act3.scale + 4 * q), scs = tn_ld4(act_s.scale + 4 * q);
-      for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
-        const int b = r / T;
-        size_t off = (size_t)r * C + 4 * q;
-        float4 g = tail_gout(tn_ld4(dout + off), tn_ld4(out + off), inv_keep_o);
-        float4 zz = tn_ld4(z3 + off), mult;
-        tn_act4(act3, zz, 4 * q, off >> 2, &mult);
-        float4 gt = tn_ld4(gate + (size_t)b * C + 4 * q);
-        float4 dmean = tn_ld4(dm + (size_t)b * C + 4 * q) * inv_T;
-        float4 da = tn_fma4(g, gt, dmean) * mult;          // dL/d pre3
-        a1 = tn_fma4(da, zz, a1);
-        a2 = a2 + da;
-        tn_st4(dz3 + off, da * sc3);
-        float4 sv = tn_ld4(s + off);
-        a3s = tn_fma4(g, sv, a3s);
-        a4 = a4 + g;
-        tn_st4(ds + off, g * scs);
+      const float4 sc3 = tn_ld4(act3.scale + 4 * q), scs = tn_ld4(act_s.scale + 4 * q), shs = tn_ld4(act_s.shift + 4 * q);
+      // two rows per iteration: their loads are issued before the first is used
+      for (int r = r0 + tl.lane; r < r1; r += 2 * tl.lanes) {
+        float4 dv[2], ov[2], zv[2], sv[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          if (r + k * tl.lanes < r1) {
+            const size_t off = (size_t)(r + k * tl.lanes) * C + 4 * q;
+            dv[k] = tn_ld4(dout + off); zv[k] = tn_ld4(z3 + off); sv[k] = tn_ld4(s + off);
+            if (out) ov[k] = tn_ld4(out + off);
+          }
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          if (r + k * tl.lanes < r1) {
+            const int rr = r + k * tl.lanes, b = rr / T;
+            const size_t off = (size_t)rr * C + 4 * q;
+            float4 zz = zv[k], mult;
+            const float4 a3 = tn_act4(act3, zz, 4 * q, off >> 2, &mult);
+            const float4 gt = tn_ld4(gate + (size_t)b * C + 4 * q);
+            float4 g;
+            if (out) {
+              g = tail_gout(dv[k], ov[k], inv_keep_o);
+            } else {
+              // forward: v = gate * a3 + (s * scale_s + shift_s); out = v > 0 ? v * keep : 0
+              const float4 v = tn_fma4(gt, a3, tn_fma4(sv[k], scs, shs));
+              const float4 keep = tn_drop4(act_o, off >> 2);
+              g = make_float4(v.x > 0.f ? dv[k].x * keep.x : 0.f, v.y > 0.f ? dv[k].y * keep.y : 0.f,
+                              v.z > 0.f ? dv[k].z * keep.z : 0.f, v.w > 0.f ? dv[k].w * keep.w : 0.f);
+            }
+            float4 dmean = tn_ld4(dm + (size_t)b * C + 4 * q) * inv_T;
+            float4 da = tn_fma4(g, gt, dmean) * mult;          // dL/d pre3
+            a1 = tn_fma4(da, zz, a1);
+            a2 = a2 + da;
+            tn_st4(dz3 + off, da * sc3);
+            a3s = tn_fma4(g, sv[k], a3s);
+            a4 = a4 + g;
+            tn_st4(ds + off, g * scs);
+          }
       }
     }
     tn_lane_reduce_atomic(tl, a1, q, dsc3, red);
@@ -519,23 +567,34 @@ extern "C" int tn_tail_bwd1_mlp(const float* dout, const float* out, const float
   return TN_OK;
 }
 
-// dsc3/dsh3/dscs/dshs are ACCUMULATED into (caller zeroes them)
-extern "C" int tn_tail_bwd2(const float* dout, const float* out, const float* z3, const float* s, const float* gate,
-                            const float* dm, float* dz3, float* ds, float* dsc3, float* dsh3, float* dscs, float* dshs,
-                            const float* scale3, const float* shift3, float drop3, unsigned int layer3, const float* scale_s,
-                            const float* shift_s, float drop_o, const unsigned long long* seed, int B, int T, int C, void* stream) {
+// dsc3/dsh3/dscs/dshs are ACCUMULATED into (caller zeroes them).  out == NULL: the output mask is recomputed (needs layer_o, the
+// dropout site of the block output, as given to tn_tail_fwd).
+extern "C" int tn_tail_bwd2r(const float* dout, const float* out, const float* z3, const float* s, const float* gate,
+                             const float* dm, float* dz3, float* ds, float* dsc3, float* dsh3, float* dscs, float* dshs,
+                             const float* scale3, const float* shift3, float drop3, unsigned int layer3, const float* scale_s,
+                             const float* shift_s, float drop_o, unsigned int layer_o, const unsigned long long* seed, int B, int T,
+                             int C, void* stream) {
   SE_COMMON_CHECK("tail_bwd2");
-  TN_REQUIRE(dout && out && z3 && s && gate && dm && dz3 && ds && dsc3 && dsh3 && dscs && dshs && scale3 && shift3 && scale_s && shift_s,
+  TN_REQUIRE(dout && z3 && s && gate && dm && dz3 && ds && dsc3 && dsh3 && dscs && dshs && scale3 && shift3 && scale_s && shift_s,
              "tail_bwd2: null tensor");
   long long R = (long long)B * T;
   TN_REQUIRE(R < (1ll << 31), "tail_bwd2: B*T too large");
   int rpb = tail_rows_per_block(R);
   float inv_keep_o = drop_o > 0.f ? 1.f / (1.f - drop_o) : 1.f;
-  tn_launch(tail_bwd2_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, 
+  tn_launch(tail_bwd2_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream,
       dout, out, z3, s, gate, dm, dz3, ds, dsc3, dsh3, dscs, dshs, tn_make_act(scale3, shift3, 1, drop3, seed, layer3),
-      tn_make_act(scale_s, shift_s, 0, 0.f, seed, 0), inv_keep_o, 1.0f / (float)T, (int)R, T, C, rpb);
+      tn_make_act(scale_s, shift_s, 0, 0.f, seed, 0), tn_make_act(scale_s, shift_s, 1, drop_o, seed, layer_o), inv_keep_o,
+      1.0f / (float)T, (int)R, T, C, rpb);
   TN_LAUNCH_CHECK("tail_bwd2_kernel");
   return TN_OK;
+}
+extern "C" int tn_tail_bwd2(const float* dout, const float* out, const float* z3, const float* s, const float* gate,
+                            const float* dm, float* dz3, float* ds, float* dsc3, float* dsh3, float* dscs, float* dshs,
+                            const float* scale3, const float* shift3, float drop3, unsigned int layer3, const float* scale_s,
+                            const float* shift_s, float drop_o, const unsigned long long* seed, int B, int T, int C, void* stream) {
+  TN_REQUIRE(out, "tail_bwd2: null tensor (tn_tail_bwd2r recomputes the mask without `out`)");
+  return tn_tail_bwd2r(dout, out, z3, s, gate, dm, dz3, ds, dsc3, dsh3, dscs, dshs, scale3, shift3, drop3, layer3, scale_s, shift_s,
+                       drop_o, 0u, seed, B, T, C, stream);
 }
 
 // ---------------------------------------------------------------------------

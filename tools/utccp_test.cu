@@ -132,6 +132,55 @@ __global__ void __launch_bounds__(128, 1) rate(long long* out, int mode, int n, 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512u) : "memory");
 }
 
+// the same MMA stream issued from WARP-UNIFORM code: all 32 lanes of warp 0 run the loop and compute the (uniform) descriptors,
+// one elected lane issues.  Under `if (tid == 0)` the compiler wraps every tcgen05.mma in an ELECT / BRA.U.ANY serialisation loop
+// and moves its operands from vector to uniform registers (R2UR) each time.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+__global__ void __launch_bounds__(128, 1) rate_uniform(long long* out, int n, int reps) {
+  extern __shared__ __align__(1024) uint8_t dyn[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tslot;
+  uint8_t* sm = (uint8_t*)(((uintptr_t)dyn + 1023) & ~(uintptr_t)1023);
+  uint8_t* sa = sm; uint8_t* sb = sm + 128 * 128;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 + 256) * 32; i += 128) reinterpret_cast<float*>(sm)[i] = 0.001f * (float)(i % 97);
+  if (tid == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar))); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tslot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = tslot;
+  if (warp == 0) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t da = desc_k128(s32(sa)), db = desc_k128(s32(sb));
+    const long long t0 = clock64();
+    for (int i = 0; i < reps; i += 4) {
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                       ::"r"(tbase), "l"(da + (uint64_t)(2 * kk)), "l"(db + (uint64_t)(2 * kk)), "r"(idesc), "r"(1u) : "memory");
+      }
+      __syncwarp();
+    }
+    if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar)) : "memory");
+    __syncwarp();
+    mbar_wait(s32(&bar), 0);
+    if (tid == 0) out[blockIdx.x] = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512u) : "memory");
+}
+
 int main() {
   float hA[128 * 32], hB[NN * 32], hD[2][128 * NN];
   srand(1);
@@ -173,6 +222,15 @@ int main() {
         cudaMemcpy(hT, dT, ctas * sizeof(long long), cudaMemcpyDeviceToHost);
         long long mx = 0; for (int i = 0; i < ctas; ++i) mx = hT[i] > mx ? hT[i] : mx;
         printf("%3d CTA(s), M=128 N=%3d K=8 tf32, A from %s: %6.1f clk per MMA (floor %d)\n", ctas, n, mode ? "tensor memory" : "shared memory", mx / 512.0, n / 2);
+        if (mode == 0) {
+          cudaFuncSetAttribute(rate_uniform, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+          rate_uniform<<<ctas, 128, 64 * 1024>>>(dT, n, 512); cudaDeviceSynchronize();
+          rate_uniform<<<ctas, 128, 64 * 1024>>>(dT, n, 512);
+          if (cudaDeviceSynchronize() != cudaSuccess) { printf("rate_uniform failed\n"); return 1; }
+          cudaMemcpy(hT, dT, ctas * sizeof(long long), cudaMemcpyDeviceToHost);
+          mx = 0; for (int i = 0; i < ctas; ++i) mx = hT[i] > mx ? hT[i] : mx;
+          printf("%3d CTA(s), M=128 N=%3d K=8 tf32, A from shared memory, warp-uniform issue + elect.sync: %6.1f clk per MMA\n", ctas, n, mx / 512.0);
+        }
       }
   return 0;
 }
