@@ -779,9 +779,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop, one elected lane issues (see gemm_tc2_kernel) =====
+    {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc_c = tc_idesc_bf16(idesc, p.corr);
+      const int corr = p.corr;
       // Accumulator plan (p.nacc > 1 when the tile leaves TMEM columns free): the tensor core's fp32 accumulate truncates, an
       // error that grows with the number of MMAs chained into one accumulator (measured 1.8e-6 rms at K = 256, 1.1e-5 at
       // K = 1536 for 3 MMAs per 8 of K).  So the main products hi*hi of consecutive K ranges go to nacc - 1 separate
@@ -793,15 +795,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int s = kc % S;
         const uint32_t ph = (kc / S) & 1;
         mbar_wait(full0 + 8 * s, ph);
-        TC_TRACE(40 + kc);
         if (split) mbar_wait(ready0 + 8 * s, ph);
-        TC_TRACE(60 + kc);
         tc_fence_after();
         const uint64_t dbh = umma_desc_k128(smem_u32(b_hi(s)));
         const uint64_t dbl = split ? umma_desc_k128(smem_u32(b_lo(s))) : 0;
         const int am = (kc * nmain) / num_kc;              // main accumulator of this K chunk
         const bool new_main = am != prev_am;
         prev_am = am;
+        if (tc_elect_one()) {
+        TC_TRACE(60 + kc);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           const uint64_t dah = umma_desc_k128(smem_u32(a_hi(s, mt)));
@@ -818,15 +820,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               tc_mma_tf32(d, dah + adv, dbh + adv, idesc, acc);
             } else if (nacc > 1) {
               tc_mma_tf32(d, dah + adv, dbh + adv, idesc, acc);
-              if (p.corr) {
-                tc_mma_bf16(dc, dal + adv, dbl + adv, tc_idesc_bf16(idesc, p.corr), accc);
+              if (corr) {
+                tc_mma_bf16(dc, dal + adv, dbl + adv, idesc_c, accc);
               } else {
                 tc_mma_tf32(dc, dal + adv, dbh + adv, idesc, accc);
                 tc_mma_tf32(dc, dah + adv, dbl + adv, idesc, 1u);
               }
-            } else if (p.corr) {
+            } else if (corr) {
               tc_mma_tf32(d, dah + adv, dbh + adv, idesc, acc);
-              tc_mma_bf16(d, dal + adv, dbl + adv, tc_idesc_bf16(idesc, p.corr), 1u);
+              tc_mma_bf16(d, dal + adv, dbl + adv, idesc_c, 1u);
             } else {
               tc_mma_tf32(d, dal + adv, dbh + adv, idesc, acc);
               tc_mma_tf32(d, dah + adv, dbl + adv, idesc, 1u);
@@ -837,8 +839,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (p.cluster2) tc_commit_mc(empty0 + 8 * s, (uint16_t)3);   // stage free (in both CTAs) once these MMAs have read it
         else tc_commit(empty0 + 8 * s);
         TC_TRACE(80 + kc);
+        }
+        __syncwarp();
       }
-      tc_commit(accum_bar);                  // accumulators complete
+      if (tc_elect_one()) tc_commit(accum_bar);                  // accumulators complete
+      __syncwarp();
     }
   } else {
     // ===== transform warps (split only), then epilogue =====
@@ -1719,7 +1724,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         WG_TRACE(2);
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      {
+        // the whole warp runs the loop, one elected lane issues (see gemm_tc2_kernel)
         // tf32, fp32 accumulate, A and B MN-major (bits 15, 16), M = 128, N = NB
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
         for (int kc = 0; kc < num_kc; ++kc) {
@@ -1727,20 +1733,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(full0 + 8 * s, (kc / S) & 1);
           tc_fence_after();
           const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+          if (tc_elect_one()) {
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
+            for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-            for (int k8 = 0; k8 < WG_BK / 8; ++k8) {
-              const uint64_t da = umma_desc_mn128(base + mt * 4 * slab + k8 * 1024, slab);
-              const uint64_t db = umma_desc_mn128(base + a_bytes + k8 * 1024, slab);
-              tc_mma_tf32(tmem_base + (uint32_t)(mt * 256), da, db, idesc, (kc > 0 || k8 > 0) ? 1u : 0u);
+              for (int k8 = 0; k8 < WG_BK / 8; ++k8) {
+                const uint64_t da = umma_desc_mn128(base + mt * 4 * slab + k8 * 1024, slab);
+                const uint64_t db = umma_desc_mn128(base + a_bytes + k8 * 1024, slab);
+                tc_mma_tf32(tmem_base + (uint32_t)(mt * 256), da, db, idesc, (kc > 0 || k8 > 0) ? 1u : 0u);
+              }
             }
+            tc_commit(empty0 + 8 * s);
+            if (kc == 0) WG_TRACE(3);
           }
-          tc_commit(empty0 + 8 * s);
-          if (kc == 0) WG_TRACE(3);
+          __syncwarp();
         }
-        tc_commit(accum_bar);
-        WG_TRACE(4);
+        if (tc_elect_one()) { tc_commit(accum_bar); WG_TRACE(4); }
+        __syncwarp();
       }
     } else if (!(p.dbg & 2)) {
       mbar_wait(accum_bar, 0);
@@ -1867,22 +1876,26 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     } else if (warp == 1) {
-      if (leader && lane == 0) {
+      if (leader) {
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NB2 >> 3) << 17) | ((256u >> 4) << 24);
         for (int kc = 0; kc < num_kc; ++kc) {
           const int s = kc % S;
           mbar_wait(full0 + 8 * s, (kc / S) & 1);
           tc_fence_after();
           const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+          if (tc_elect_one()) {
 #pragma unroll
-          for (int k8 = 0; k8 < WG_BK / 8; ++k8) {
-            const uint64_t da = umma_desc_mn128(base + k8 * 1024, slab);
-            const uint64_t db = umma_desc_mn128(base + a_bytes + k8 * 1024, slab);
-            tc_mma_tf32_2sm(tmem_base, da, db, idesc, (kc > 0 || k8 > 0) ? 1u : 0u);
+            for (int k8 = 0; k8 < WG_BK / 8; ++k8) {
+              const uint64_t da = umma_desc_mn128(base + k8 * 1024, slab);
+              const uint64_t db = umma_desc_mn128(base + a_bytes + k8 * 1024, slab);
+              tc_mma_tf32_2sm(tmem_base, da, db, idesc, (kc > 0 || k8 > 0) ? 1u : 0u);
+            }
+            tc_commit_2sm(empty0 + 8 * s, (uint16_t)3);
           }
-          tc_commit_2sm(empty0 + 8 * s, (uint16_t)3);
+          __syncwarp();
         }
-        tc_commit_2sm(accum_bar, (uint16_t)3);
+        if (tc_elect_one()) tc_commit_2sm(accum_bar, (uint16_t)3);
+        __syncwarp();
       }
     } else {
       mbar_wait(accum_bar, 0);
