@@ -1019,6 +1019,15 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_local_addr, uin
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar_local_addr), "r"(cta));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// The same without the cluster-scope release fence (MEMBAR.ALL.GPU in SASS, ~1.2 us per chunk on the mainloop's critical path,
+// measured with the per-chunk timeline).  Used to forward "this CTA's operand tile is in SHARED memory": the tile's writers ran
+// fence.proxy.async after their stores and arrived (release) on the CTA-local barrier this thread has just acquired, so the
+// stores are complete before this arrive is issued; there is no global-memory traffic to order.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_local_addr, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar_local_addr), "r"(cta));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 
 // Fused depthwise-forward operand producer of the pair kernel (MODE 2, 16 transform warps = 512 threads): like
 // tc_dw_mainloop, but this CTA holds HB = BN2/2 rows of each of the two N tiles.  Per K chunk TMA delivers, per tile, the raw z
@@ -1338,7 +1347,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       for (int kc = 0; kc < num_kc; ++kc) {               // forward this CTA's operand-ready events to the leader
         const int s = kc % S;
         mbar_wait(ready0 + 8 * s, (kc / S) & 1);
-        mbar_arrive_cluster(readyP0 + 8 * s, 0u);
+        mbar_arrive_cluster_relaxed(readyP0 + 8 * s, 0u);
       }
     }
   } else {
@@ -1447,15 +1456,30 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       if (tid == 0) TC2_TRACE2(1, kc);
       float4* hi = reinterpret_cast<float4*>(b_hi(s, 0));
       float4* lo = reinterpret_cast<float4*>(b_lo(s, 0));
-      for (int i = tid; i < n4; i += 32 * EW) {
-        const float4 v = hi[i];
-        uint4 h, l;
-        h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-        l.x = rna_tf32(v.x - __uint_as_float(h.x)); l.y = rna_tf32(v.y - __uint_as_float(h.y));
-        l.z = rna_tf32(v.z - __uint_as_float(h.z)); l.w = rna_tf32(v.w - __uint_as_float(h.w));
-        reinterpret_cast<uint4*>(hi)[i] = h;
-        if (p.corr) tc_store_corr(reinterpret_cast<uint8_t*>(lo), (uint32_t)i >> 3, ((uint32_t)i & 7u) ^ (((uint32_t)i >> 3) & 7u), v, h, p.corr);
-        else reinterpret_cast<uint4*>(lo)[i] = l;
+      // this thread's float4s of the chunk are all loaded before the first is split (the stage cycle TMA -> split -> MMA -> release
+      // bounds the mainloop once the MMAs issue at the tensor pipe's rate; one load at a time cost ~0.3 us of it per chunk)
+      constexpr int NTT = 32 * EW, NIT = (2 * 128 * 8 + NTT - 1) / NTT;       // HB <= 128
+      float4 vv[NIT];
+#pragma unroll
+      for (int k = 0; k < NIT; ++k)
+        if (tid + k * NTT < n4) vv[k] = hi[tid + k * NTT];
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {
+        const int i = tid + k * NTT;
+        if (i < n4) {
+          const float4 v = vv[k];
+          uint4 h;
+          h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+          reinterpret_cast<uint4*>(hi)[i] = h;
+          if (p.corr) {
+            tc_store_corr(reinterpret_cast<uint8_t*>(lo), (uint32_t)i >> 3, ((uint32_t)i & 7u) ^ (((uint32_t)i >> 3) & 7u), v, h, p.corr);
+          } else {
+            uint4 l;
+            l.x = rna_tf32(v.x - __uint_as_float(h.x)); l.y = rna_tf32(v.y - __uint_as_float(h.y));
+            l.z = rna_tf32(v.z - __uint_as_float(h.z)); l.w = rna_tf32(v.w - __uint_as_float(h.w));
+            reinterpret_cast<uint4*>(lo)[i] = l;
+          }
+        }
       }
       fence_proxy_async();
       __syncwarp();
