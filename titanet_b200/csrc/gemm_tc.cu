@@ -1408,6 +1408,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       for (int kc = 0; kc < num_kc; ++kc) {
         const int s = kc % S;
         mbar_wait(fullB0 + 8 * s, (kc / S) & 1);
+        if (tid == 0) TC2_TRACE2(1, kc);
         float4* hi = reinterpret_cast<float4*>(b_hi(s, 0));
         float4* lo = reinterpret_cast<float4*>(b_lo(s, 0));
         float4 v[NI], zz[NI];
@@ -1448,6 +1449,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(ready0 + 8 * s);
+        if (tid == 0) TC2_TRACE2(2, kc);
       }
     } else
     for (int kc = 0; kc < num_kc; ++kc) {

@@ -47,3 +47,9 @@ for base, nm in ((0, "CTA 0"), (64, "CTA mid")):
     print(f"--- {nm}: us since kernel entry")
     for k in sorted(names, key=lambda k: t[base + k]):
         if t[base + k]: print(f"  {(t[base + k] - t0) / 1e3:7.2f}  {names[k]}")
+
+kinds = ["TMA issued", "operands arrived (warp 2)", "producer done (warp 2)", "MMA: operands ready", "MMAs + commit issued"]
+order = [0, 1, 2, 3, 4]
+print("--- CTA 0 per K chunk, us since kernel entry: " + " | ".join(kinds))
+for kc in range(min(16, C // 32)):
+    print(f"  chunk {kc:2d}: " + " ".join(f"{(t[256 + 16 * k + kc] - t[0]) / 1e3:7.2f}" if t[256 + 16 * k + kc] else "      -" for k in order))
