@@ -1215,14 +1215,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   if (threadIdx.x == 0) TC2_TRACE(1);
 
   if (warp == 0) {
-    // ===== TMA producer (both CTAs) =====
-    if (lane == 0) {
+    // ===== TMA producer (both CTAs): the whole warp runs the loops, one elected lane issues (uniform operands, see the MMA issuer) =====
+    {
       uint32_t fullA_leader0;                                       // the same barrier in the even (leader) CTA of the pair
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(fullA_leader0) : "r"(fullA0), "r"(0u));
       for (int kc = 0; kc < num_kc; ++kc) {
         const int s = kc % S;
         if (kc >= S) mbar_wait(empty0 + 8 * s, ((kc / S) - 1) & 1);
         const int k0 = kc * TC_BK;
+        if (tc_elect_one()) {
         if (leader) mbar_expect_tx(fullA0 + 8 * s, 4 * a_tile);   // both CTAs' hi + lo weight tiles
         tma_load_2d_2sm(smem_u32(a_hi(s)), &tmA_hi, fullA_leader0 + 8 * s, k0, m0 + (int)rank * 128);
         tma_load_2d_2sm(smem_u32(a_lo(s)), &tmA_lo, fullA_leader0 + 8 * s, k0, m0 + (int)rank * 128);
@@ -1235,6 +1236,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           tma_load_2d(smem_u32(b_lo(s, 1)), &tmG, fullB0 + 8 * s, k0, n0 + BN2 + (int)rank * HB);
         }
         TC2_TRACE2(0, kc);
+        }
+        __syncwarp();
       }
       if (MODE == 1) {
         // z boxes of the previous layer for the fused epilogue, group by group as the tensor core releases the stages
@@ -1249,9 +1252,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             for (int st = 0; st < num_kc; ++st) mbar_wait(empty0 + 8 * st, 0u);
           }
           const int b0 = g * zcap, b1 = min(8, b0 + zcap);
-          mbar_expect_tx(zbar0 + 8 * g, (uint32_t)(b1 - b0) * z_box);
-          for (int b = b0; b < b1; ++b)
-            tma_load_2d(smem_u32(z_ptr(b)), &tmZ, zbar0 + 8 * g, m0 + (int)rank * 128 + (b >> 1) * 32, n0 + (b & 1) * BN2);
+          if (tc_elect_one()) {
+            mbar_expect_tx(zbar0 + 8 * g, (uint32_t)(b1 - b0) * z_box);
+            for (int b = b0; b < b1; ++b)
+              tma_load_2d(smem_u32(z_ptr(b)), &tmZ, zbar0 + 8 * g, m0 + (int)rank * 128 + (b >> 1) * 32, n0 + (b & 1) * BN2);
+          }
+          __syncwarp();
         }
       }
     }
