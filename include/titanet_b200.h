@@ -284,12 +284,14 @@ int tn_tail_bwd2(const float* dout, const float* out, const float* z3, const flo
                  float* dz3, float* ds, float* dsc3, float* dsh3, float* dscs, float* dshs, const float* scale3,
                  const float* shift3, float drop3, unsigned int layer3, const float* scale_s, const float* shift_s,
                  float drop_o, const unsigned long long* seed, int B, int T, int C, void* stream);
-/* the same; out may be NULL: the ReLU / dropout mask of the block output is then recomputed from z3, s and the gate exactly as
- * tn_tail_fwd computed it (layer_o = tn_tail_fwd's), so `out` is not read (one [B*T, C] tensor less for this HBM-bound pass) */
-int tn_tail_bwd2r(const float* dout, const float* out, const float* z3, const float* s, const float* gate, const float* dm,
-                  float* dz3, float* ds, float* dsc3, float* dsh3, float* dscs, float* dshs, const float* scale3,
-                  const float* shift3, float drop3, unsigned int layer3, const float* scale_s, const float* shift_s, float drop_o,
-                  unsigned int layer_o, const unsigned long long* seed, int B, int T, int C, void* stream);
+/* squeeze + excitation + tail forward in ONE cluster kernel (tn_se_squeeze_excite + tn_tail_fwd): each block keeps its
+ * activated z3 tile in shared memory between the squeeze and the tail, so z3 is read once.  Needs
+ * tn_se_tail_fwd_supported(T, C, Cr) (cluster plan of tn_se_squeeze_excite and a tile of at most 160 KB per block). */
+int tn_se_tail_fwd_supported(int T, int C, int Cr);
+int tn_se_tail_fwd(const float* z3, const float* s, float* m, float* gate, float* out, const float* W1, const float* W2,
+                   const float* scale3, const float* shift3, float drop3, unsigned int layer3, const float* scale_s,
+                   const float* shift_s, float drop_o, unsigned int layer_o, const unsigned long long* seed, int B, int T, int C,
+                   int Cr, void* stream);
 
 /* stand-alone SE gate multiply (SqueezeExcitation.forward outside a MegaBlock, src/modules.py:187-189):
  * out = x * gate[b,c];  backward: dx = dout * gate, dgate[b,c] += sum_t dout * x  (dgate ACCUMULATED) */

@@ -704,8 +704,8 @@ FUSE_BLOCK_ENTRY = _os.environ.get("TN_FUSE_BLOCK_ENTRY", "0") == "1"
 FUSE_SE_MLP = _os.environ.get("TN_FUSE_SE_MLP", "0") == "1"
 # squeeze + excitation forward as one cluster kernel (tn_se_squeeze_excite: DSMEM exchange, no atomics); 0 = two launches (A/B)
 FUSE_SE_FWD = _os.environ.get("TN_FUSE_SE_FWD", "1") != "0"
-# tn_tail_bwd2r without `out`: the block-output ReLU / dropout mask recomputed from its inputs; 0 = read it back from `out` (A/B)
-TAIL_RECOMPUTE_MASK = _os.environ.get("TN_TAIL_RECOMPUTE", "1") != "0"
+# ... and the mega-block tail in the same launch (tn_se_tail_fwd: the activated z3 tile stays in shared memory); 0 = separate tail (A/B)
+FUSE_SE_TAIL = _os.environ.get("TN_FUSE_SE_TAIL", "1") != "0"
 
 
 # TN_FUSE_DWFWD=1: the depthwise conv as the pointwise GEMM's operand producer (tn_gemm_tc_dwfwd).  Parity-green and 1.3 us
@@ -936,6 +936,13 @@ class SETail(Function):
         Cr = W1.shape[0]
         m, gate = empty((B, C), z3), empty((B, C), z3)
         out = empty(z3.shape, z3)
+        if FUSE_SE_TAIL and LIB.query("tn_se_tail_fwd_supported", T, C, Cr):
+            # squeeze + excitation + tail in one cluster kernel: the activated z3 tile stays in shared memory in between
+            call("tn_se_tail_fwd", ptr(z3), ptr(s), ptr(m), ptr(gate), ptr(out), ptr(W1), ptr(W2), ptr(sc3), ptr(sh3), float(p3),
+                 int(layer3), ptr(scs), ptr(shs), float(p_o), int(layer_o), ptr(seed), B, T, C, Cr)
+            ctx.save_for_backward(z3, sc3, sh3, s, scs, shs, W1, W2, seed, m, gate, out)
+            ctx.meta = (p3, layer3, p_o, layer_o, B, T)
+            return out
         if FUSE_SE_FWD and LIB.query("tn_se_squeeze_excite_supported", C, Cr):
             call("tn_se_squeeze_excite", ptr(z3), ptr(m), ptr(gate), ptr(W1), ptr(W2), ptr(sc3), ptr(sh3), 1, float(p3), ptr(seed),
                  int(layer3), B, T, C, Cr)
@@ -967,10 +974,9 @@ class SETail(Function):
             call("tn_se_mlp_bwd", ptr(dgate), ptr(gate), ptr(m), ptr(W1), ptr(W2), ptr(dm), ptr(dW1), ptr(dW2), B, C, Cr)
         dz3, ds = empty(z3.shape, z3), empty(z3.shape, z3)
         red = zeros((4, C), z3)
-        # the output mask is recomputed from z3, s and the gate (TAIL_RECOMPUTE_MASK): `out` is not read by this pass
-        call("tn_tail_bwd2r", ptr(dout), None if TAIL_RECOMPUTE_MASK else ptr(out), ptr(z3), ptr(s), ptr(gate), ptr(dm), ptr(dz3),
-             ptr(ds), red[0].data_ptr(), red[1].data_ptr(), red[2].data_ptr(), red[3].data_ptr(), ptr(sc3), ptr(sh3), float(p3),
-             int(layer3), ptr(scs), ptr(shs), float(p_o), int(layer_o), ptr(seed), B, T, C)
+        call("tn_tail_bwd2", ptr(dout), ptr(out), ptr(z3), ptr(s), ptr(gate), ptr(dm), ptr(dz3), ptr(ds), red[0].data_ptr(),
+             red[1].data_ptr(), red[2].data_ptr(), red[3].data_ptr(), ptr(sc3), ptr(sh3), float(p3), int(layer3), ptr(scs),
+             ptr(shs), float(p_o), ptr(seed), B, T, C)
         return dz3, red[0], red[1], ds, red[2], red[3], dW1, dW2, None, None, None, None, None, None, None
 
 

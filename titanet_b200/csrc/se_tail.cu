@@ -6,6 +6,7 @@
 // post-ReLU/dropout output of sub-block 3 (src/models.py:435-449), and
 // MegaBlock.forward (src/models.py:467-472).
 #include "common.cuh"
+#include <stdlib.h>
 
 // ---------------------------------------------------------------------------
 // squeeze: mean over time of the lazy activation
@@ -160,6 +161,150 @@ __global__ void __launch_bounds__(TN_EW_THREADS) se_squeeze_excite_kernel(const 
   asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers' shared memory stays alive until read
 }
 
+// Squeeze + excitation + mega-block tail in ONE launch (SqueezeExcitation.forward + the residual tail of MegaBlock.forward,
+// src/modules.py:173-189, src/models.py:467-472).  Same cluster as se_squeeze_excite_kernel (G channel groups x S parts of
+// T, <= 8 blocks per utterance), but every block KEEPS its activated a3 = dropout(relu(bn(z3))) tile in shared memory while it
+// sums it (T/S rows x CPC channels: 38.6 KB for T = 301, C = 256), fetches the finished gate of its channel group from the
+// group leader through distributed shared memory, and writes out = dropout(relu(bn(s) + gate * a3)) from the tile.  z3 is read
+// once (the two-launch path read it twice and hashed its dropout mask twice) and one launch ramp / drain disappears.
+template <int CPC>
+// (four blocks per SM: 512 blocks of a batch of 64 must be ONE wave -- at 74 registers it was three per SM, two waves, 29 us instead of 20)
+__global__ void __launch_bounds__(TN_EW_THREADS, 4) se_tail_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sk,
+                                                                    float* __restrict__ m, float* __restrict__ gate,
+                                                                    float* __restrict__ out, const float* __restrict__ W1,
+                                                                    const float* __restrict__ W2, TnAct act, TnAct act_s, TnAct act_o,
+                                                                    int T, int C, int Cr, int G, int S, float inv_T) {
+  tn_grid_dep_sync();
+  act = tn_act_init(act);
+  act_o = tn_act_init(act_o);
+  constexpr int Q = CPC / 4, LANES = TN_EW_THREADS / Q;
+  extern __shared__ __align__(16) float4 tile[];     // [rows of this part][Q]: the activated a3 tile
+  __shared__ float4 red[TN_EW_THREADS];
+  __shared__ __align__(16) float mg[CPC];            // leader: mean of this group's channels
+  __shared__ __align__(16) float gs[CPC];            // leader: gate of this group's channels
+  __shared__ float hp[256];                          // leader: this group's share of W1 m (Cr <= 256)
+  __shared__ float hs[256];                          // relu(W1 m)
+  const int q = threadIdx.x % Q, lane = threadIdx.x / Q;
+  const int b = blockIdx.y;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int g = (int)rank / S, sp = (int)rank % S;
+  const int c = g * CPC + 4 * q;
+  const int tchunk = (T + S - 1) / S;
+  const int t0 = sp * tchunk, t1 = min(T, t0 + tchunk);
+  float4 s = tn_zero4();
+  if (c < C) {
+    // four rows per iteration in flight; the sum runs in the order of the two-launch kernel (t ascending per lane)
+    for (int t = t0 + lane; t < t1; t += 4 * LANES) {
+      float4 zv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t + k * LANES < t1) zv[k] = tn_ld4(z + ((size_t)b * T + t + k * LANES) * C + c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t + k * LANES < t1) {
+          const size_t off = ((size_t)b * T + t + k * LANES) * C + c;
+          const float4 a3 = tn_act4(act, zv[k], c, off >> 2, nullptr);
+          tile[(size_t)(t + k * LANES - t0) * Q + q] = a3;
+          s = s + a3;
+        }
+    }
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < Q) {
+    float4 a = red[q];
+#pragma unroll
+    for (int l = 1; l < LANES; ++l) a = a + red[l * Q + q];
+    red[q] = a;                                      // this block's partial (read by the group leader)
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const bool leader = sp == 0;
+  if (leader && threadIdx.x < Q) {
+    float4 a = red[q];
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(&red[q]);
+    for (int r = 1; r < S; ++r) {                    // T parts in rank order
+      uint32_t remote;
+      float4 v;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank + (uint32_t)r));
+      asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote));
+      a = a + v;
+    }
+    a = a * inv_T;
+    *reinterpret_cast<float4*>(mg + 4 * q) = a;
+    if (c < C) tn_st4(m + (size_t)b * C + c, a);
+  }
+  __syncthreads();
+  if (leader) {
+    const int TPJ = TN_EW_THREADS / Cr;              // host guarantees 1 <= TPJ <= 32, a power of two, CPC % TPJ == 0
+    const int j = threadIdx.x / TPJ, part = threadIdx.x % TPJ, per = CPC / TPJ;
+    float a = 0.f;
+    for (int i = 0; i < per; ++i) {
+      const int cc = part * per + i;
+      if (g * CPC + cc < C) a = fmaf(__ldg(W1 + (size_t)j * C + g * CPC + cc), mg[cc], a);
+    }
+    for (int o = TPJ >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (part == 0) hp[j] = a;
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (leader) {
+    for (int j = threadIdx.x; j < Cr; j += TN_EW_THREADS) {
+      float a = 0.f;
+      const uint32_t local = (uint32_t)__cvta_generic_to_shared(&hp[j]);
+      for (int gg = 0; gg < G; ++gg) {               // groups in order
+        uint32_t remote;
+        float v;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"((uint32_t)(gg * S)));
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote));
+        a += v;
+      }
+      hs[j] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    for (int cc = threadIdx.x; cc < CPC; cc += TN_EW_THREADS) {
+      const int ch = g * CPC + cc;
+      float gv = 0.f;
+      if (ch < C) {
+        float a = 0.f;
+        for (int j = 0; j < Cr; ++j) a = fmaf(__ldg(W2 + (size_t)ch * Cr + j), hs[j], a);
+        gv = 1.f / (1.f + expf(-a));
+        gate[(size_t)b * C + ch] = gv;
+      }
+      gs[cc] = gv;
+    }
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");   // gates are in the leaders' shared memory
+  // ===== tail: out = dropout(relu(bn_s(s) + gate * a3)) from the tile =====
+  float4 gq = tn_zero4();
+  {
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(&gs[4 * q]);
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"((uint32_t)(g * S)));
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(gq.x), "=f"(gq.y), "=f"(gq.z), "=f"(gq.w) : "r"(remote));
+  }
+  if (c < C) {
+    const float4 ssc = tn_ld4(act_s.scale + c), ssh = tn_ld4(act_s.shift + c);
+    for (int t = t0 + lane; t < t1; t += 4 * LANES) {
+      float4 sv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t + k * LANES < t1) sv[k] = tn_ld4(sk + ((size_t)b * T + t + k * LANES) * C + c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t + k * LANES < t1) {
+          const size_t off = ((size_t)b * T + t + k * LANES) * C + c;
+          const float4 a3 = tile[(size_t)(t + k * LANES - t0) * Q + q];
+          float4 v = tn_fma4(gq, a3, tn_fma4(sv[k], ssc, ssh));
+          const float4 keep = tn_drop4(act_o, off >> 2);
+          v.x = v.x > 0.f ? v.x * keep.x : 0.f; v.y = v.y > 0.f ? v.y * keep.y : 0.f;
+          v.z = v.z > 0.f ? v.z * keep.z : 0.f; v.w = v.w > 0.f ? v.w * keep.w : 0.f;
+          tn_st4(out + off, v);
+        }
+    }
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers' shared memory stays alive until read
+}
+
 // excitation MLP of batch item b by one block.  sm: m[C] + h[Cr].  m is read with ld.cg: in the fused kernels it was
 // just accumulated by other blocks' atomics (performed in L2).
 __device__ __forceinline__ void se_mlp_fwd_block(float* sm, int b, const float* __restrict__ m, const float* __restrict__ W1,
@@ -267,29 +412,17 @@ __global__ void __launch_bounds__(TN_EW_THREADS) tail_fwd_kernel(const float* __
     const int q = qb + tl.q0;
     if (!tl.active || q >= tl.Q) continue;
     const float4 ssc = tn_ld4(act_s.scale + 4 * q), ssh = tn_ld4(act_s.shift + 4 * q);
-    // four rows per iteration: their eight 16-byte loads are issued before the first is used
-    for (int r = r0 + tl.lane; r < r1; r += 4 * tl.lanes) {
-      float4 zv[4], sv[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (r + k * tl.lanes < r1) {
-          const size_t off = (size_t)(r + k * tl.lanes) * C + 4 * q;
-          zv[k] = tn_ld4(z3 + off);
-          sv[k] = tn_ld4(s + off);
-        }
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (r + k * tl.lanes < r1) {
-          const int rr = r + k * tl.lanes, b = rr / T;
-          const size_t off = (size_t)rr * C + 4 * q;
-          float4 a3 = tn_act4(act3, zv[k], 4 * q, off >> 2, nullptr);
-          float4 g = tn_ld4(gate + (size_t)b * C + 4 * q);
-          float4 v = tn_fma4(g, a3, tn_fma4(sv[k], ssc, ssh));
-          float4 keep = tn_drop4(act_o, off >> 2);
-          v.x = v.x > 0.f ? v.x * keep.x : 0.f; v.y = v.y > 0.f ? v.y * keep.y : 0.f;
-          v.z = v.z > 0.f ? v.z * keep.z : 0.f; v.w = v.w > 0.f ? v.w * keep.w : 0.f;
-          tn_st4(out + off, v);
-        }
+    // (four rows in flight per iteration measured slower in this kernel: 15.0 -> 16.6 us)
+    for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
+      const int b = r / T;
+      size_t off = (size_t)r * C + 4 * q;
+      float4 a3 = tn_act4(act3, tn_ld4(z3 + off), 4 * q, off >> 2, nullptr);
+      float4 g = tn_ld4(gate + (size_t)b * C + 4 * q);
+      float4 v = tn_fma4(g, a3, tn_fma4(tn_ld4(s + off), ssc, ssh));
+      float4 keep = tn_drop4(act_o, off >> 2);
+      v.x = v.x > 0.f ? v.x * keep.x : 0.f; v.y = v.y > 0.f ? v.y * keep.y : 0.f;
+      v.z = v.z > 0.f ? v.z * keep.z : 0.f; v.w = v.w > 0.f ? v.w * keep.w : 0.f;
+      tn_st4(out + off, v);
     }
   }
 }
@@ -314,22 +447,11 @@ __global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd1_kernel(const float* _
     const int q = qb + tl.q0;
     float4 acc = tn_zero4();
     if (tl.active && q < tl.Q)
-      for (int t = t0 + tl.lane; t < t1; t += 4 * tl.lanes) {
-        float4 dv[4], ov[4], zv[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (t + k * tl.lanes < t1) {
-            const size_t off = ((size_t)b * T + t + k * tl.lanes) * C + 4 * q;
-            dv[k] = tn_ld4(dout + off); ov[k] = tn_ld4(out + off); zv[k] = tn_ld4(z3 + off);
-          }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (t + k * tl.lanes < t1) {
-            const size_t off = ((size_t)b * T + t + k * tl.lanes) * C + 4 * q;
-            float4 g = tail_gout(dv[k], ov[k], inv_keep_o);
-            float4 a3 = tn_act4(act3, zv[k], 4 * q, off >> 2, nullptr);
-            acc = tn_fma4(g, a3, acc);
-          }
+      for (int t = t0 + tl.lane; t < t1; t += tl.lanes) {
+        size_t off = ((size_t)b * T + t) * C + 4 * q;
+        float4 g = tail_gout(tn_ld4(dout + off), tn_ld4(out + off), inv_keep_o);
+        float4 a3 = tn_act4(act3, tn_ld4(z3 + off), 4 * q, off >> 2, nullptr);
+        acc = tn_fma4(g, a3, acc);
       }
     tn_lane_reduce_atomic(tl, acc, q, dgate + (size_t)b * C, red);
   }
@@ -365,20 +487,17 @@ __global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd1_mlp_kernel(const floa
   if (tn_last_block_of(counters + b, gridDim.x)) se_mlp_bwd_block(sm, b, dgate, gate, m, W1, W2, dm, dW1, dW2, C, Cr);
 }
 
-// pass 2: dz3, ds and the four per-channel reductions.  out == NULL: the mask of the block's output ReLU + dropout is
-// RECOMPUTED from z3, s and the gate with the forward kernel's own expressions (bit-identical decisions) instead of being
-// read back from `out`: one [R, C] tensor less to read (6 -> 5 tensors moved by this HBM-bound kernel).
+// pass 2: dz3, ds and the four per-channel reductions
 __global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd2_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                                                   const float* __restrict__ z3, const float* __restrict__ s,
                                                                   const float* __restrict__ gate, const float* __restrict__ dm,
                                                                   float* __restrict__ dz3, float* __restrict__ ds,
                                                                   float* __restrict__ dsc3, float* __restrict__ dsh3,
                                                                   float* __restrict__ dscs, float* __restrict__ dshs,
-                                                                  TnAct act3, TnAct act_s, TnAct act_o, float inv_keep_o, float inv_T, int R,
+                                                                  TnAct act3, TnAct act_s, float inv_keep_o, float inv_T, int R,
                                                                   int T, int C, int rpb) {
   tn_grid_dep_sync();
   act3 = tn_act_init(act3);
-  act_o = tn_act_init(act_o);
   __shared__ float4 red[TN_EW_THREADS];
   TnTile tl = tn_tile(C);
   const int r0 = blockIdx.x * rpb, r1 = min(R, r0 + rpb);
@@ -386,44 +505,23 @@ __global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd2_kernel(const float* _
     const int q = qb + tl.q0;
     float4 a1 = tn_zero4(), a2 = tn_zero4(), a3s = tn_zero4(), a4 = tn_zero4();
     if (tl.active && q < tl.Q) {
-      const float4 sc3 = tn_ld4(act3.scale + 4 * q), scs = tn_ld4(act_s.scale + 4 * q), shs = tn_ld4(act_s.shift + 4 * q);
-      // two rows per iteration: their loads are issued before the first is used
-      for (int r = r0 + tl.lane; r < r1; r += 2 * tl.lanes) {
-        float4 dv[2], ov[2], zv[2], sv[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-          if (r + k * tl.lanes < r1) {
-            const size_t off = (size_t)(r + k * tl.lanes) * C + 4 * q;
-            dv[k] = tn_ld4(dout + off); zv[k] = tn_ld4(z3 + off); sv[k] = tn_ld4(s + off);
-            if (out) ov[k] = tn_ld4(out + off);
-          }
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-          if (r + k * tl.lanes < r1) {
-            const int rr = r + k * tl.lanes, b = rr / T;
-            const size_t off = (size_t)rr * C + 4 * q;
-            float4 zz = zv[k], mult;
-            const float4 a3 = tn_act4(act3, zz, 4 * q, off >> 2, &mult);
-            const float4 gt = tn_ld4(gate + (size_t)b * C + 4 * q);
-            float4 g;
-            if (out) {
-              g = tail_gout(dv[k], ov[k], inv_keep_o);
-            } else {
-              // forward: v = gate * a3 + (s * scale_s + shift_s); out = v > 0 ? v * keep : 0
-              const float4 v = tn_fma4(gt, a3, tn_fma4(sv[k], scs, shs));
-              const float4 keep = tn_drop4(act_o, off >> 2);
-              g = make_float4(v.x > 0.f ? dv[k].x * keep.x : 0.f, v.y > 0.f ? dv[k].y * keep.y : 0.f,
-                              v.z > 0.f ? dv[k].z * keep.z : 0.f, v.w > 0.f ? dv[k].w * keep.w : 0.f);
-            }
-            float4 dmean = tn_ld4(dm + (size_t)b * C + 4 * q) * inv_T;
-            float4 da = tn_fma4(g, gt, dmean) * mult;          // dL/d pre3
-            a1 = tn_fma4(da, zz, a1);
-            a2 = a2 + da;
-            tn_st4(dz3 + off, da * sc3);
-            a3s = tn_fma4(g, sv[k], a3s);
-            a4 = a4 + g;
-            tn_st4(ds + off, g * scs);
-          }
+      const float4 sc3 = tn_ld4(act3.scale + 4 * q), scs = tn_ld4(act_s.scale + 4 * q);
+      for (int r = r0 + tl.lane; r < r1; r += tl.lanes) {
+        const int b = r / T;
+        size_t off = (size_t)r * C + 4 * q;
+        float4 g = tail_gout(tn_ld4(dout + off), tn_ld4(out + off), inv_keep_o);
+        float4 zz = tn_ld4(z3 + off), mult;
+        tn_act4(act3, zz, 4 * q, off >> 2, &mult);
+        float4 gt = tn_ld4(gate + (size_t)b * C + 4 * q);
+        float4 dmean = tn_ld4(dm + (size_t)b * C + 4 * q) * inv_T;
+        float4 da = tn_fma4(g, gt, dmean) * mult;          // dL/d pre3
+        a1 = tn_fma4(da, zz, a1);
+        a2 = a2 + da;
+        tn_st4(dz3 + off, da * sc3);
+        float4 sv = tn_ld4(s + off);
+        a3s = tn_fma4(g, sv, a3s);
+        a4 = a4 + g;
+        tn_st4(ds + off, g * scs);
       }
     }
     tn_lane_reduce_atomic(tl, a1, q, dsc3, red);
@@ -499,6 +597,41 @@ extern "C" int tn_se_squeeze_excite(const float* z3, float* m, float* gate, cons
   return TN_OK;
 }
 
+// shared memory of one block's a3 tile in the fused squeeze + excitation + tail kernel, or 0 when that kernel does not apply
+static size_t se_tail_tile_bytes(int T, int C, int Cr) {
+  int cpc, G, S;
+  if (!se_fused_plan(C, Cr, &cpc, &G, &S)) return 0;
+  const size_t bytes = (size_t)((T + S - 1) / S) * cpc * sizeof(float);
+  return bytes <= 160 * 1024 ? bytes : 0;
+}
+extern "C" int tn_se_tail_fwd_supported(int T, int C, int Cr) { return se_tail_tile_bytes(T, C, Cr) > 0 ? 1 : 0; }
+// m[B, C], gate[B, C] (saved for the backward pass) and out[B*T, C] from z3, s in one launch: tn_se_squeeze_excite + tn_tail_fwd
+extern "C" int tn_se_tail_fwd(const float* z3, const float* s, float* m, float* gate, float* out, const float* W1, const float* W2,
+                              const float* scale3, const float* shift3, float drop3, unsigned int layer3, const float* scale_s,
+                              const float* shift_s, float drop_o, unsigned int layer_o, const unsigned long long* seed, int B, int T,
+                              int C, int Cr, void* stream) {
+  SE_COMMON_CHECK("se_tail_fwd");
+  TN_REQUIRE(z3 && s && m && gate && out && W1 && W2 && scale3 && shift3 && scale_s && shift_s, "se_tail_fwd: null tensor");
+  int cpc, G, S;
+  const size_t smem = se_tail_tile_bytes(T, C, Cr);
+  TN_UNSUPPORTED(smem == 0 || !se_fused_plan(C, Cr, &cpc, &G, &S), "se_tail_fwd: unsupported shape T=%d C=%d Cr=%d", T, C, Cr);
+  TN_REQUIRE((long long)B * T * C < (1ll << 33), "se_tail_fwd: B*T*C too large");
+  dim3 grid(G * S, B);
+  const TnAct act3 = tn_make_act(scale3, shift3, 1, drop3, seed, layer3), act_s = tn_make_act(scale_s, shift_s, 0, 0.f, seed, 0),
+              act_o = tn_make_act(scale_s, shift_s, 1, drop_o, seed, layer_o);
+  if (cpc == 64) {
+    TN_CUDA(cudaFuncSetAttribute(se_tail_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tn_launch_cluster(se_tail_fwd_kernel<64>, grid, TN_EW_THREADS, smem, stream, G * S, z3, s, m, gate, out, W1, W2, act3, act_s, act_o, T, C, Cr, G, S,
+                      1.0f / (float)T);
+  } else {
+    TN_CUDA(cudaFuncSetAttribute(se_tail_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tn_launch_cluster(se_tail_fwd_kernel<128>, grid, TN_EW_THREADS, smem, stream, G * S, z3, s, m, gate, out, W1, W2, act3, act_s, act_o, T, C, Cr, G, S,
+                      1.0f / (float)T);
+  }
+  TN_LAUNCH_CHECK("se_tail_fwd_kernel");
+  return TN_OK;
+}
+
 extern "C" int tn_se_mlp_fwd(const float* m, const float* W1, const float* W2, float* gate, int B, int C, int Cr, void* stream) {
   TN_REQUIRE(B > 0 && C > 0 && Cr > 0 && m && W1 && W2 && gate, "se_mlp_fwd: bad arguments");
   size_t smem = sizeof(float) * (size_t)(C + Cr);
@@ -567,34 +700,23 @@ extern "C" int tn_tail_bwd1_mlp(const float* dout, const float* out, const float
   return TN_OK;
 }
 
-// dsc3/dsh3/dscs/dshs are ACCUMULATED into (caller zeroes them).  out == NULL: the output mask is recomputed (needs layer_o, the
-// dropout site of the block output, as given to tn_tail_fwd).
-extern "C" int tn_tail_bwd2r(const float* dout, const float* out, const float* z3, const float* s, const float* gate,
-                             const float* dm, float* dz3, float* ds, float* dsc3, float* dsh3, float* dscs, float* dshs,
-                             const float* scale3, const float* shift3, float drop3, unsigned int layer3, const float* scale_s,
-                             const float* shift_s, float drop_o, unsigned int layer_o, const unsigned long long* seed, int B, int T,
-                             int C, void* stream) {
+// dsc3/dsh3/dscs/dshs are ACCUMULATED into (caller zeroes them)
+extern "C" int tn_tail_bwd2(const float* dout, const float* out, const float* z3, const float* s, const float* gate,
+                            const float* dm, float* dz3, float* ds, float* dsc3, float* dsh3, float* dscs, float* dshs,
+                            const float* scale3, const float* shift3, float drop3, unsigned int layer3, const float* scale_s,
+                            const float* shift_s, float drop_o, const unsigned long long* seed, int B, int T, int C, void* stream) {
   SE_COMMON_CHECK("tail_bwd2");
-  TN_REQUIRE(dout && z3 && s && gate && dm && dz3 && ds && dsc3 && dsh3 && dscs && dshs && scale3 && shift3 && scale_s && shift_s,
+  TN_REQUIRE(dout && out && z3 && s && gate && dm && dz3 && ds && dsc3 && dsh3 && dscs && dshs && scale3 && shift3 && scale_s && shift_s,
              "tail_bwd2: null tensor");
   long long R = (long long)B * T;
   TN_REQUIRE(R < (1ll << 31), "tail_bwd2: B*T too large");
   int rpb = tail_rows_per_block(R);
   float inv_keep_o = drop_o > 0.f ? 1.f / (1.f - drop_o) : 1.f;
-  tn_launch(tail_bwd2_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream,
+  tn_launch(tail_bwd2_kernel, tn_cdiv(R, rpb), TN_EW_THREADS, 0, stream, 
       dout, out, z3, s, gate, dm, dz3, ds, dsc3, dsh3, dscs, dshs, tn_make_act(scale3, shift3, 1, drop3, seed, layer3),
-      tn_make_act(scale_s, shift_s, 0, 0.f, seed, 0), tn_make_act(scale_s, shift_s, 1, drop_o, seed, layer_o), inv_keep_o,
-      1.0f / (float)T, (int)R, T, C, rpb);
+      tn_make_act(scale_s, shift_s, 0, 0.f, seed, 0), inv_keep_o, 1.0f / (float)T, (int)R, T, C, rpb);
   TN_LAUNCH_CHECK("tail_bwd2_kernel");
   return TN_OK;
-}
-extern "C" int tn_tail_bwd2(const float* dout, const float* out, const float* z3, const float* s, const float* gate,
-                            const float* dm, float* dz3, float* ds, float* dsc3, float* dsh3, float* dscs, float* dshs,
-                            const float* scale3, const float* shift3, float drop3, unsigned int layer3, const float* scale_s,
-                            const float* shift_s, float drop_o, const unsigned long long* seed, int B, int T, int C, void* stream) {
-  TN_REQUIRE(out, "tail_bwd2: null tensor (tn_tail_bwd2r recomputes the mask without `out`)");
-  return tn_tail_bwd2r(dout, out, z3, s, gate, dm, dz3, ds, dsc3, dsh3, dscs, dshs, scale3, shift3, drop3, layer3, scale_s, shift_s,
-                       drop_o, 0u, seed, B, T, C, stream);
 }
 
 // ---------------------------------------------------------------------------
