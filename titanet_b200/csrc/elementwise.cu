@@ -276,8 +276,9 @@ extern "C" int tn_act_bwd2(const float* dy, const float* dy2, const float* z, fl
   TN_REQUIRE(scale && shift && dscale && dshift, "act_bwd: scale/shift/dscale/dshift are required");
   TN_REQUIRE(tn_aligned16(z) && tn_aligned16(dy) && tn_aligned16(dy2) && tn_aligned16(dz) && tn_aligned16(scale) && tn_aligned16(shift),
              "act_bwd: pointers must be 16B aligned");
-  // every block ends in two atomics per channel and same-address atomics serialise in L2: few, fat blocks (4 per SM over all slabs)
-  const int rpb = slab_rows_per_block(R, C, 4);
+  // every block ends in two atomics per channel and same-address atomics serialise in L2: few, fat blocks -- THREE per SM over all
+  // slabs: the kernel needs 74 registers, three blocks are resident per SM, and a grid of four per SM was two waves
+  const int rpb = slab_rows_per_block(R, C, 3);
   tn_launch(act_bwd_kernel, dim3(tn_cdiv(R, rpb), tn_cdiv(C >> 2, 64)), TN_EW_THREADS, 0, stream, dy, dy2, z, dz, dscale, dshift,
             tn_make_act(scale, shift, relu, drop_p, seed, layer), R, C, rpb);
   TN_LAUNCH_CHECK("act_bwd_kernel");
