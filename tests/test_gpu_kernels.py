@@ -114,6 +114,7 @@ def lazy_ref(z, scale, shift, relu):
 
 
 @pytest.mark.parametrize("K,C,T,B,lazy", [(3, 64, 50, 3, True), (7, 32, 33, 2, True), (11, 32, 64, 2, True), (3, 256, 101, 2, False),
+                                          (7, 128, 45, 2, True), (11, 256, 70, 3, True), (9, 384, 37, 2, False), (15, 132, 40, 1, True),
                                           (1, 1536, 9, 2, True), (15, 16, 40, 1, True)])
 def test_depthwise_fwd_bwd(ops, K, C, T, B, lazy):
     g = torch.Generator().manual_seed(3)
