@@ -340,15 +340,20 @@ def graph_time_kernel(kind: str, R: int, Ci: int, Co: int, B: int, dropout: floa
 def step_traffic_model(args, B):
     """Bytes the step's kernels move by design (sum of every kernel's unique inputs + outputs), against SURVEY section 8d's
     compulsory figure.  Per mega-block, in units of one [B, H, T] fp32 tensor A_H:
-      forward 18 = skip GEMM 2 + 3 x (depthwise 2 + pointwise GEMM 2) + squeeze 1 + tail 3
+      forward 17 = skip GEMM 2 + 3 x (depthwise 2 + pointwise GEMM 2) + squeeze / excitation / tail in one kernel 3
+                   (18 = squeeze 1 + tail 3 where the fused kernel's shared-memory tile does not fit: TitaNet-L at 8 s)
       backward 39 = tail pass 1 3 + tail pass 2 6 + 3 x (BatchNorm-backward / dgrad / depthwise-backward kernel 5 + wgrad 2)
                     + skip (BatchNorm-backward / dgrad 4 + wgrad 2) + gradient sum of the block input 3
     (round 1: 18 + 43).  Prolog / epilog / pooling / decoder: epilog GEMM and its backward, the materialised epilog activation
-    and the attentive pooling move ~16 A_1536 fwd+bwd; the mel front end 4 L + A_80."""
+    and the attentive pooling move ~13 A_1536 fwd+bwd (16 before the two gradients of the epilog activation were summed on
+    load by tn_act_bwd2); the mel front end 4 L + A_80."""
     T = 1 + int(args.seconds * SAMPLE_RATE) // 160
     H = {"s": 256, "m": 512, "l": 1024}[args.model.lower()]
     a_h, a_e, a_m = 4.0 * B * T * H, 4.0 * B * T * 1536, 4.0 * B * T * 80
-    moved = args.blocks * 57 * a_h + 16 * a_e + 6 * a_h + 8 * a_m + 4.0 * B * args.seconds * SAMPLE_RATE
+    cpc = 64 if (H + 63) // 64 <= 8 else 128                                   # tn_se_tail_fwd's plan (se_tail.cu: se_fused_plan)
+    parts = max(1, min(4, 8 // ((H + cpc - 1) // cpc)))
+    fused_tail = ((T + parts - 1) // parts) * cpc * 4 <= 160 * 1024
+    moved = args.blocks * (56 if fused_tail else 57) * a_h + 13 * a_e + 6 * a_h + 8 * a_m + 4.0 * B * args.seconds * SAMPLE_RATE
     compulsory = 3.0 * (args.blocks * 11 * a_h + (a_m + a_h) + (a_h + a_e) + 2 * a_e + 4.0 * B * args.seconds * SAMPLE_RATE + a_m)
     return {"step_traffic_bytes": moved, "compulsory_bytes": compulsory, "ratio": round(moved / compulsory, 3)}
 
