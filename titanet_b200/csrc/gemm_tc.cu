@@ -1,5 +1,5 @@
 // 1x1-convolution / linear layers on the 5th-generation tensor cores (tcgen05 + TMEM),
-// operands staged by TMA, fp32-equivalent "3xTF32" arithmetic.
+// operands staged by TMA, fp32-equivalent split arithmetic.
 //
 //   Z[r, co] = bias[co] + sum_ci X[r, ci] * W[co, ci]          X: [R, Kd]  W: [M, Kd]  Z: [R, M]
 //
@@ -10,17 +10,19 @@
 // BatchNorm statistics (sum z, sum z^2 per channel) are thread-local sums, and for a
 // fixed row the 32 lanes of a warp write 32 consecutive floats (one 128 B line).
 //
-// Precision: fp32 operands are split hi = rna_tf32(x), lo = x - hi.  Default scheme: one kind::tf32 MMA hi*hi plus ONE
-// kind::f16 (bf16) MMA over a doubled K that carries both corrections lo*hi + hi*lo (see tc_store_corr below).  The original
-// "3xTF32" scheme (three tf32 MMAs hi*hi + lo*hi + hi*lo) is kept behind TN_TC_3XTF32=1.  Both accumulate into
-// the same fp32 TMEM tile and are fp32-equivalent (SURVEY.md §7 hard part 1 shows plain TF32 breaks the
-// 1e-3 parity contract through train-mode BatchNorm).  The weight split is precomputed
-// (tn_split_tf32, tiny); the activation tile is split in shared memory by the four
-// transform warps between the TMA arrival and the MMA issue.  nsplit = 1 skips the
-// split (the tensor core truncates fp32 to tf32) for the backward GEMMs.
+// Precision: fp32 operands are split hi = rna_tf32(x), lo = x - hi.  One kind::tf32 MMA hi*hi plus ONE kind::f16 MMA over a
+// doubled K that carries both corrections lo*hi + hi*lo (tc_store_corr): scaled fp16 in forward GEMMs (operand rounding =
+// 3xTF32's), bf16 in gradient GEMMs (fp32's exponent range); the original three-MMA 3xTF32 scheme stays selectable
+// (tc_corr_for).  All accumulate in fp32 TMEM tiles and are fp32-equivalent (SURVEY.md §7 hard part 1 shows plain TF32
+// breaks the 1e-3 parity contract through train-mode BatchNorm).  The weight split is precomputed once per step
+// (tn_split_tf32_batch); the activation tile is split in shared memory by the transform warps between the TMA arrival and
+// the MMA issue.  nsplit = 1 skips the split (the tensor core truncates fp32 to tf32).
 //
-// Warp roles (192 threads, 1 CTA / SM): warp 0 TMA producer, warp 1 TMEM allocator +
-// MMA issuer, warps 2-5 operand transform then epilogue (TMEM -> registers -> global).
+// Kernels: gemm_tc2_kernel (a cta_group::2 pair of CTAs per 256 channels x 2 N tiles: the main path), gemm_tc_kernel (one CTA,
+// shapes the pair kernel does not take), wgrad_tc_kernel (weight gradients, MN-major operands, split-K).  Warp roles: warp 0
+// TMA producer, warp 1 TMEM allocator + MMA issuer, the others operand transform, then epilogue (TMEM -> registers ->
+// global).  The tcgen05.mma / TMA issue sites run in WARP-UNIFORM code and branch on one elect.sync (tc_elect_one): from
+// `if (lane == 0)` code the compiler serialises every such instruction through an ELECT / BRA.U.ANY loop.
 // Reference ops replaced: the pointwise Conv1dSamePadding(C, C', 1) of DepthwiseConv1d
 // (src/modules.py:76-78), the skip nn.Conv1d (src/models.py:452-455), the epilog conv
 // (src/models.py:384) and the ASP linears (src/models.py:549-551).
@@ -2197,7 +2199,6 @@ static int launch_gemm_tc(const float* X, const float* ws, TcParams p, int R, in
   TN_REQUIRE(X && ws, "gemm_tc: null tensor");
   const bool grad = (p.flags & TN_GEMM_GRAD) != 0 || p.dw_K > 0;
   p.flags &= ~TN_GEMM_GRAD;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("TN_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.flags |= dbg & (2048 | 4096 | 8192 | 16384); }   // experiments only
   p.corr = tc_corr_for(grad);
   const float* ws_lo = ws + (size_t)(p.corr == 2 ? 3 : p.corr ? 2 : 1) * M * Kd;
   if (p.stats) {

@@ -37,8 +37,8 @@ for base, nm in ((0, "CTA 0"), (64, "CTA mid")):
         if t[base + k]: print(f"  {(t[base + k] - t0) / 1e3:7.2f}  {names[k]}")
 
 # per-chunk events of CTA 0 (slots 256 + 16 kind + chunk)
-kinds = ["TMA issued", "B arrived (warp 2)", "transform done (warp 2)", "A arrived (MMA warp)", "local ready", "peer ready", "first MMAs issued", "all MMAs issued", "commit issued"]
-order = [0, 1, 2, 5, 6, 3, 7, 8, 4]
+kinds = ["TMA issued", "B arrived (warp 2)", "transform done (warp 2)", "MMA: operands of both CTAs ready", "MMAs + commit issued"]
+order = [0, 1, 2, 3, 4]
 t0 = t[0]
 print("--- CTA 0 per K chunk, us since kernel entry: " + " | ".join(kinds))
 for kc in range(min(16, K // 32)):
