@@ -158,3 +158,28 @@ def test_fused_dgrad_depthwise_backward(B, T, C, Co, K, lazy, p):
         tols = [1e-5, 2e-5] + ([1e-4, 1e-4] if lazy else []) + [1e-4, 1e-4, 2e-3, 1e-4]
         for a_, r_, tol in zip(res[0], ref, tols):
             assert rel(a_, r_) < tol
+
+
+def test_batched_split_writes_the_planes_the_gemms_read():
+    """tn_split_tf32_batch (one tile list over all weights, transposed weights through shared memory, only the planes each
+    orientation's GEMMs read) against the stand-alone tn_split_tf32 on ragged shapes: plane 0 (tf32 hi) always, plane 3
+    (scaled fp16 correction rows) for the forward orientation, plane 2 (bf16 correction rows) for the transposed one."""
+    from titanet_b200 import _ops as ops
+    from titanet_b200._lib import call, ptr
+    g = torch.Generator().manual_seed(11)
+    ws = [torch.nn.Parameter((torch.randn(co, ci, 1, generator=g) / math.sqrt(ci)).cuda()) for co, ci in ((256, 256), (128, 1536), (1536, 128), (384, 96), (128, 32))]
+    cache = ops.SplitCache(ws)
+    cache.buf.fill_(float("nan"))
+    cache.refresh()
+    torch.cuda.synchronize()
+    for w in ws:
+        fwd, bwd = cache.lookup(w)
+        Co, Ci = w.shape[0], w.shape[1]
+        ref_f = torch.empty(ops.WS_PLANES, Co, Ci, device="cuda")
+        ref_b = torch.empty(ops.WS_PLANES, Ci, Co, device="cuda")
+        call("tn_split_tf32", ptr(w), ptr(ref_f), Co, Ci, 0)
+        call("tn_split_tf32", ptr(w), ptr(ref_b), Ci, Co, 1)
+        torch.cuda.synchronize()
+        assert torch.equal(fwd[0], ref_f[0]) and torch.equal(fwd[3].view(torch.int32), ref_f[3].view(torch.int32))
+        assert torch.equal(bwd[0], ref_b[0]) and torch.equal(bwd[2].view(torch.int32), ref_b[2].view(torch.int32))
+        assert torch.equal(ref_b[0], ref_f[0].t())

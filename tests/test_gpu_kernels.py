@@ -259,6 +259,34 @@ def test_se_tail_fwd_bwd(ops):
         assert rel(gp[i].grad, ref[i].grad) < 5e-5, i
 
 
+@pytest.mark.parametrize("B,T,C,Cr,p3,po", [(5, 301, 256, 16, 0.1, 0.1), (3, 77, 512, 32, 0.0, 0.0), (2, 150, 128, 8, 0.2, 0.0), (2, 801, 64, 8, 0.1, 0.1)])
+def test_se_tail_fused_forward_equals_two_launch_path(ops, B, T, C, Cr, p3, po):
+    """tn_se_tail_fwd (squeeze + excitation + tail as one cluster kernel, activated tile kept in shared memory) against
+    tn_se_squeeze_excite + tn_tail_fwd: same arithmetic in the same order, so means, gates and outputs are bit-identical."""
+    from titanet_b200._lib import LIB
+    if not LIB.query("tn_se_tail_fwd_supported", T, C, Cr):
+        pytest.skip("shape outside the fused kernel's plan")
+    g = torch.Generator().manual_seed(B * T + C)
+    mk = lambda *s: torch.randn(*s, generator=g).to(dev())
+    z3, s = mk(B * T, C), mk(B * T, C)
+    sc3, sh3 = (0.5 + torch.rand(C, generator=g)).to(dev()), 0.3 * mk(C)
+    scs, shs = (0.5 + torch.rand(C, generator=g)).to(dev()), 0.3 * mk(C)
+    W1, W2 = mk(Cr, C) / math.sqrt(C), mk(C, Cr) / math.sqrt(Cr)
+    seed = torch.tensor([12345], dtype=torch.int64, device=dev())
+    outs = []
+    for fused in (True, False):
+        old = ops.FUSE_SE_TAIL
+        ops.FUSE_SE_TAIL = fused
+        try:
+            out = ops.SETail.apply(z3, sc3, sh3, s, scs, shs, W1, W2, seed if (p3 > 0 or po > 0) else None, p3, 3, po, 4, B, T)
+        finally:
+            ops.FUSE_SE_TAIL = old
+        outs.append(out.clone())
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    assert float(outs[0].abs().max()) > 0
+
+
 def test_asp_pool_fwd_bwd(ops):
     B, T, D = 3, 45, 96
     g = torch.Generator().manual_seed(7)
