@@ -1,5 +1,7 @@
 #!/bin/bash
-# same-box A/B of the benchmark step: the tree of the round's first commit (exported to the git-ignored _prev/) against HEAD, alternating
+# same-box A/B of the benchmark step: the tree of the round's first commit (exported to the git-ignored _prev/) against HEAD, alternating.
+# _prev/ is made in the build container with:  mkdir _prev && git archive 24e7abe | tar -x -C _prev && (cd _prev && python -m titanet_b200._build)
+# (gpurun ships git-ignored files, so both trees and both libraries travel to the GPU box)
 mkdir -p gpurun_out
 show() { python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1', d['ms_per_step'], 'ms/step', d['value'], 'utt/s   e2e', d['e2e']['value'], '  dominant GEMM us/launch', d['roofline']['us_per_launch'])"; }
 for i in 1 2; do
