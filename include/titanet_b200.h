@@ -280,6 +280,11 @@ int tn_tail_fwd(const float* z3, const float* s, const float* gate, float* out, 
 int tn_tail_bwd1(const float* dout, const float* out, const float* z3, float* dgate, const float* scale3,
                  const float* shift3, float drop3, unsigned int layer3, float drop_o, const unsigned long long* seed, int B, int T,
                  int C, void* stream);
+/* the same for a block output with two consumers: the gradients dout and dout2 are added on load and dsum = dout + dout2 is
+ * written for tn_tail_bwd2 (replaces autograd's sum kernel) */
+int tn_tail_bwd1s(const float* dout, const float* dout2, float* dsum, const float* out, const float* z3, float* dgate,
+                  const float* scale3, const float* shift3, float drop3, unsigned int layer3, float drop_o,
+                  const unsigned long long* seed, int B, int T, int C, void* stream);
 int tn_tail_bwd2(const float* dout, const float* out, const float* z3, const float* s, const float* gate, const float* dm,
                  float* dz3, float* ds, float* dsc3, float* dsh3, float* dscs, float* dshs, const float* scale3,
                  const float* shift3, float drop3, unsigned int layer3, const float* scale_s, const float* shift_s,

@@ -706,6 +706,9 @@ FUSE_SE_MLP = _os.environ.get("TN_FUSE_SE_MLP", "0") == "1"
 FUSE_SE_FWD = _os.environ.get("TN_FUSE_SE_FWD", "1") != "0"
 # ... and the mega-block tail in the same launch (tn_se_tail_fwd: the activated z3 tile stays in shared memory); 0 = separate tail (A/B)
 FUSE_SE_TAIL = _os.environ.get("TN_FUSE_SE_TAIL", "1") != "0"
+# the block output as two aliases (ops.SETail2): the next block's two consumers send their gradients separately and
+# tn_tail_bwd1s adds them on load; 0 = one output and autograd's sum kernel (A/B)
+SE_TAIL_TWO_OUT = _os.environ.get("TN_SE_TAIL_TWO_OUT", "1") != "0"
 
 
 # TN_FUSE_DWFWD=1: the depthwise conv as the pointwise GEMM's operand producer (tn_gemm_tc_dwfwd).  Parity-green and 1.3 us
@@ -957,27 +960,60 @@ class SETail(Function):
 
     @staticmethod
     def backward(ctx, dout):
-        z3, sc3, sh3, s, scs, shs, W1, W2, seed, m, gate, out = ctx.saved_tensors
-        p3, layer3, p_o, layer_o, B, T = ctx.meta
-        C, Cr = z3.shape[1], W1.shape[0]
-        dout = _c(dout)
-        dgate = zeros((B, C), z3)
-        dm = empty((B, C), z3)
-        dW1, dW2 = zeros(W1.shape, W1), zeros(W2.shape, W2)
-        if FUSE_SE_MLP:
-            tickets = zeros((B,), z3, torch.int32)
-            call("tn_tail_bwd1_mlp", ptr(dout), ptr(out), ptr(z3), ptr(dgate), ptr(tickets), ptr(gate), ptr(m), ptr(W1), ptr(W2), ptr(dm),
-                 ptr(dW1), ptr(dW2), ptr(sc3), ptr(sh3), float(p3), int(layer3), float(p_o), ptr(seed), B, T, C, Cr)
-        else:
-            call("tn_tail_bwd1", ptr(dout), ptr(out), ptr(z3), ptr(dgate), ptr(sc3), ptr(sh3), float(p3), int(layer3), float(p_o),
-                 ptr(seed), B, T, C)
-            call("tn_se_mlp_bwd", ptr(dgate), ptr(gate), ptr(m), ptr(W1), ptr(W2), ptr(dm), ptr(dW1), ptr(dW2), B, C, Cr)
-        dz3, ds = empty(z3.shape, z3), empty(z3.shape, z3)
-        red = zeros((4, C), z3)
-        call("tn_tail_bwd2", ptr(dout), ptr(out), ptr(z3), ptr(s), ptr(gate), ptr(dm), ptr(dz3), ptr(ds), red[0].data_ptr(),
-             red[1].data_ptr(), red[2].data_ptr(), red[3].data_ptr(), ptr(sc3), ptr(sh3), float(p3), int(layer3), ptr(scs),
-             ptr(shs), float(p_o), ptr(seed), B, T, C)
-        return dz3, red[0], red[1], ds, red[2], red[3], dW1, dW2, None, None, None, None, None, None, None
+        return _se_tail_backward(ctx, dout, None)
+
+
+def _se_tail_backward(ctx, dout, dout2):
+    """Backward of SETail / SETail2.  ``dout2``: the gradient that reached the second alias of the block output (or None);
+    tn_tail_bwd1s adds the two while loading and writes the sum once for pass 2."""
+    z3, sc3, sh3, s, scs, shs, W1, W2, seed, m, gate, out = ctx.saved_tensors
+    p3, layer3, p_o, layer_o, B, T = ctx.meta
+    C, Cr = z3.shape[1], W1.shape[0]
+    if dout is None:
+        dout, dout2 = dout2, None
+    if dout is None:
+        return (None,) * 15
+    dout = _c(dout)
+    dgate = zeros((B, C), z3)
+    dm = empty((B, C), z3)
+    dW1, dW2 = zeros(W1.shape, W1), zeros(W2.shape, W2)
+    if dout2 is not None:
+        dsum = empty(z3.shape, z3)
+        call("tn_tail_bwd1s", ptr(dout), ptr(_c(dout2)), ptr(dsum), ptr(out), ptr(z3), ptr(dgate), ptr(sc3), ptr(sh3), float(p3),
+             int(layer3), float(p_o), ptr(seed), B, T, C)
+        call("tn_se_mlp_bwd", ptr(dgate), ptr(gate), ptr(m), ptr(W1), ptr(W2), ptr(dm), ptr(dW1), ptr(dW2), B, C, Cr)
+        dout = dsum
+    elif FUSE_SE_MLP:
+        tickets = zeros((B,), z3, torch.int32)
+        call("tn_tail_bwd1_mlp", ptr(dout), ptr(out), ptr(z3), ptr(dgate), ptr(tickets), ptr(gate), ptr(m), ptr(W1), ptr(W2), ptr(dm),
+             ptr(dW1), ptr(dW2), ptr(sc3), ptr(sh3), float(p3), int(layer3), float(p_o), ptr(seed), B, T, C, Cr)
+    else:
+        call("tn_tail_bwd1", ptr(dout), ptr(out), ptr(z3), ptr(dgate), ptr(sc3), ptr(sh3), float(p3), int(layer3), float(p_o),
+             ptr(seed), B, T, C)
+        call("tn_se_mlp_bwd", ptr(dgate), ptr(gate), ptr(m), ptr(W1), ptr(W2), ptr(dm), ptr(dW1), ptr(dW2), B, C, Cr)
+    dz3, ds = empty(z3.shape, z3), empty(z3.shape, z3)
+    red = zeros((4, C), z3)
+    call("tn_tail_bwd2", ptr(dout), ptr(out), ptr(z3), ptr(s), ptr(gate), ptr(dm), ptr(dz3), ptr(ds), red[0].data_ptr(),
+         red[1].data_ptr(), red[2].data_ptr(), red[3].data_ptr(), ptr(sc3), ptr(sh3), float(p3), int(layer3), ptr(scs),
+         ptr(shs), float(p_o), ptr(seed), B, T, C)
+    return dz3, red[0], red[1], ds, red[2], red[3], dW1, dW2, None, None, None, None, None, None, None
+
+
+class SETail2(Function):
+    """``SETail`` whose output has TWO consumers (the next mega-block's skip conv and its first depthwise conv,
+    src/models.py:467-469): returns the block output twice (two aliases of one buffer) so that each consumer's gradient
+    arrives on its own and the backward adds them while loading (tn_tail_bwd1s) -- autograd's sum kernel on the 16 inner block
+    outputs (read 2, write 1 [B*T, C] tensors each) never runs."""
+
+    @staticmethod
+    def forward(ctx, *args):
+        out = SETail.forward(ctx, *args)
+        ctx.set_materialize_grads(False)
+        return out, out.detach()
+
+    @staticmethod
+    def backward(ctx, dout, dout2):
+        return _se_tail_backward(ctx, dout, dout2)
 
 
 class MeanT(Function):

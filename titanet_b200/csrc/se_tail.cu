@@ -457,6 +457,35 @@ __global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd1_kernel(const float* _
   }
 }
 
+// pass 1 for a block output with TWO consumers (the next mega-block's skip conv and first depthwise conv): the two gradients
+// are added while loading and their sum is written once for pass 2 -- autograd's separate sum kernel (read 2, write 1, then
+// read again here) is folded into this pass.  dsum may alias neither input.
+__global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd1s_kernel(const float* __restrict__ dout, const float* __restrict__ dout2,
+                                                                   float* __restrict__ dsum, const float* __restrict__ out,
+                                                                   const float* __restrict__ z3, float* __restrict__ dgate,
+                                                                   TnAct act3, float inv_keep_o, int T, int C, int tpb) {
+  tn_grid_dep_sync();
+  act3 = tn_act_init(act3);
+  __shared__ float4 red[TN_EW_THREADS];
+  TnTile tl = tn_tile(C);
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * tpb, t1 = min(T, t0 + tpb);
+  for (int qb = 0; qb < tl.Q; qb += tl.qpb) {
+    const int q = qb + tl.q0;
+    float4 acc = tn_zero4();
+    if (tl.active && q < tl.Q)
+      for (int t = t0 + tl.lane; t < t1; t += tl.lanes) {
+        size_t off = ((size_t)b * T + t) * C + 4 * q;
+        const float4 d = tn_ld4(dout + off) + tn_ld4(dout2 + off);
+        tn_st4(dsum + off, d);
+        float4 g = tail_gout(d, tn_ld4(out + off), inv_keep_o);
+        float4 a3 = tn_act4(act3, tn_ld4(z3 + off), 4 * q, off >> 2, nullptr);
+        acc = tn_fma4(g, a3, acc);
+      }
+    tn_lane_reduce_atomic(tl, acc, q, dgate + (size_t)b * C, red);
+  }
+}
+
 // pass 1 + the excitation MLP's backward: the last block of batch item b turns dgate[b] into dm[b], dW1 +=, dW2 +=
 __global__ void __launch_bounds__(TN_EW_THREADS) tail_bwd1_mlp_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                                                       const float* __restrict__ z3, float* __restrict__ dgate,
@@ -678,6 +707,22 @@ extern "C" int tn_tail_bwd1(const float* dout, const float* out, const float* z3
   float inv_keep_o = drop_o > 0.f ? 1.f / (1.f - drop_o) : 1.f;
   tn_launch(tail_bwd1_kernel, grid, TN_EW_THREADS, 0, stream, dout, out, z3, dgate, tn_make_act(scale3, shift3, 1, drop3, seed, layer3), inv_keep_o, T, C, tpb);
   TN_LAUNCH_CHECK("tail_bwd1_kernel");
+  return TN_OK;
+}
+
+// the same for two gradients of the block output: dsum = dout + dout2 is written for tn_tail_bwd2; dgate ACCUMULATED
+extern "C" int tn_tail_bwd1s(const float* dout, const float* dout2, float* dsum, const float* out, const float* z3, float* dgate,
+                             const float* scale3, const float* shift3, float drop3, unsigned int layer3, float drop_o,
+                             const unsigned long long* seed, int B, int T, int C, void* stream) {
+  SE_COMMON_CHECK("tail_bwd1s");
+  TN_REQUIRE(dout && dout2 && dsum && out && z3 && dgate && scale3 && shift3, "tail_bwd1s: null tensor");
+  TN_REQUIRE(dsum != dout && dsum != dout2, "tail_bwd1s: dsum must not alias a gradient");
+  int tpb = time_per_block(B, T);
+  dim3 grid(tn_cdiv(T, tpb), B);
+  float inv_keep_o = drop_o > 0.f ? 1.f / (1.f - drop_o) : 1.f;
+  tn_launch(tail_bwd1s_kernel, grid, TN_EW_THREADS, 0, stream, dout, dout2, dsum, out, z3, dgate, tn_make_act(scale3, shift3, 1, drop3, seed, layer3),
+            inv_keep_o, T, C, tpb);
+  TN_LAUNCH_CHECK("tail_bwd1s_kernel");
   return TN_OK;
 }
 

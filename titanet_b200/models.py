@@ -177,7 +177,7 @@ class MegaBlock(nn.Module):
             p1 = first._dropout if self.training else 0.0
             y = Lazy(z1, B, T, sc1, sh1, relu=True, p=p1, seed=dctx.seed if p1 > 0 else None, layer=dctx.next_layer())
         else:
-            s, scs, shs = ops.conv_gemm_bn(x.z, skip_conv.weight, skip_conv.bias, skip_bn, B, T)
+            s, scs, shs = ops.conv_gemm_bn(x.z2 if x.z2 is not None else x.z, skip_conv.weight, skip_conv.bias, skip_bn, B, T)
             y = x
         for j in range(1 if fused_entry else 0, n_sub):
             y = self.sub_blocks[j]._fwd(y, dctx)
@@ -186,9 +186,14 @@ class MegaBlock(nn.Module):
         se = self.sub_blocks[n_sub]
         p_o = float(self.dropout) if self.training else 0.0
         seed = dctx.seed if (p_o > 0 or y.p > 0) else None
-        out = ops.SETail.apply(y.z, y.scale, y.shift, s, scs, shs, se.excitation[0].weight, se.excitation[2].weight, seed,
-                               y.p, y.layer, p_o, dctx.next_layer(), B, T)
-        return Lazy(out, B, T)
+        args = (y.z, y.scale, y.shift, s, scs, shs, se.excitation[0].weight, se.excitation[2].weight, seed,
+                y.p, y.layer, p_o, dctx.next_layer(), B, T)
+        if ops.SE_TAIL_TWO_OUT and torch.is_grad_enabled():
+            # two aliases of the block output: a following mega-block feeds its skip conv from the second one, so that the two
+            # gradients reach SETail2.backward separately (summed on load) instead of through an autograd sum kernel
+            out, out2 = ops.SETail2.apply(*args)
+            return Lazy(out, B, T, z2=out2)
+        return Lazy(ops.SETail.apply(*args), B, T)
 
     def forward(self, prolog_outputs):
         require_cuda(prolog_outputs)

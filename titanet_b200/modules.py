@@ -34,6 +34,7 @@ class Lazy:
     p: float = 0.0
     seed: Optional[Tensor] = None
     layer: int = 0
+    z2: Optional[Tensor] = None      # second alias of a plain ``z`` for its second consumer (ops.SETail2), or None
 
     @property
     def C(self) -> int:
