@@ -43,6 +43,11 @@ class Lazy:
     def materialise(self) -> "Lazy":
         if self.scale is None:
             return self
+        if torch.is_grad_enabled():
+            # two aliases (ops.Act2): a consumer pair (a mega-block's skip conv and first depthwise conv) sends its gradients
+            # separately and tn_act_bwd2 adds them on load
+            y, y2 = ops.Act2.apply(self.z, self.scale, self.shift, self.seed, self.relu, self.p, self.layer)
+            return Lazy(y, self.B, self.T, z2=y2)
         y = ops.Act.apply(self.z, self.scale, self.shift, self.seed, self.relu, self.p, self.layer)
         return Lazy(y, self.B, self.T)
 
